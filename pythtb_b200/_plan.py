@@ -1,0 +1,143 @@
+"""Model compiler: flattens a ``tb_model`` into the SoA buffers the kernels
+stream ("plan").  Layout is documented in ``csrc/tbk_plan.cuh`` and DESIGN.md.
+
+The plan restates the accumulation of ``tb_model._gen_ham``
+(/root/reference/pythtb.py:894-924): the on-site block first, then every
+hopping in list order contributing ``amp*phase`` to (i,j) and its conjugate to
+(j,i).  Only lower-triangle elements are kept (numpy's ``eigh`` reads
+UPLO='L'), and the Bloch phase is factored as  exp(2 pi i k.R) * gauge(tau)
+so that phases are shared by all hoppings with the same lattice vector R.
+"""
+import numpy as np
+
+PH_CONJ = 1 << 30
+
+
+class Plan(object):
+    """Host-side compiled model (numpy arrays, C-contiguous)."""
+
+    __slots__ = ("dim_k", "nsta", "nph", "nel", "nterm", "convention", "ph_R", "tau",
+                 "el_ptr", "el_row", "el_col", "t_ph", "t_amp", "pm_ptr", "pm_el", "pm_amp",
+                 "norb", "nspin")
+
+    def nbytes(self):
+        return sum(getattr(self, k).nbytes for k in
+                   ("ph_R", "tau", "el_ptr", "el_row", "el_col", "t_ph", "t_amp", "pm_ptr", "pm_el", "pm_amp"))
+
+
+def _canon(rper):
+    """Canonical representative of +-R: first non-zero component positive.
+    Returns (key, conj_flag) or (None, False) for R = 0."""
+    for x in rper:
+        if x > 0:
+            return rper, False
+        if x < 0:
+            return tuple(-y for y in rper), True
+    return None, False
+
+
+def compile_plan(model, convention=1):
+    """Build the plan from any object exposing the reference's attribute names
+    (``_dim_k,_nspin,_norb,_nsta,_per,_orb,_site_energies,_hoppings``)."""
+    if convention not in (1, 2):
+        raise Exception("\n\nconvention must be 1 (PythTB, orbital positions in the phase) or 2")
+    dim_k, nspin, norb, nsta = model._dim_k, model._nspin, model._norb, model._nsta
+    per = list(model._per)
+    rows, cols, amps, phs = [], [], [], []
+    table = {}
+
+    def phase_id(rper):
+        key, cj = _canon(rper)
+        if key is None:
+            return -1
+        idx = table.get(key)
+        if idx is None:
+            idx = len(table)
+            table[key] = idx
+        return idx | (PH_CONJ if cj else 0)
+
+    def add(row, col, val, ph):
+        if row < col:
+            return
+        val = complex(val)
+        if val == 0.0:
+            return
+        rows.append(row)
+        cols.append(col)
+        amps.append(val)
+        phs.append(ph)
+
+    # on-site block, pythtb.py:894-898
+    for i in range(norb):
+        if nspin == 1:
+            add(i, i, complex(model._site_energies[i]).real, -1)
+        else:
+            blk = np.array(model._site_energies[i], dtype=complex).reshape(2, 2)
+            for s in range(2):
+                for sp in range(2):
+                    val = blk[s, sp]
+                    if s == sp:
+                        val = val.real      # LAPACK ignores the imaginary part of the diagonal
+                    add(2 * i + s, 2 * i + sp, val, -1)
+    # hoppings in list order, pythtb.py:900-924
+    for hop in model._hoppings:
+        blk = np.array(hop[0], dtype=complex).reshape(nspin, nspin)
+        i, j = int(hop[1]), int(hop[2])
+        if dim_k > 0:
+            rvec = np.array(hop[3])
+            rper = tuple(int(rvec[p]) for p in per)
+        else:
+            rper = ()
+        ph_f = phase_id(rper)
+        ph_c = phase_id(tuple(-x for x in rper))
+        for s in range(nspin):
+            for sp in range(nspin):
+                add(i * nspin + s, j * nspin + sp, blk[s, sp], ph_f)
+                add(j * nspin + sp, i * nspin + s, np.conj(blk[s, sp]), ph_c)
+
+    nterm = len(rows)
+    rows = np.array(rows, dtype=np.int64)
+    cols = np.array(cols, dtype=np.int64)
+    amps = np.array(amps, dtype=complex)
+    phs = np.array(phs, dtype=np.int64)
+    p = Plan()
+    p.dim_k, p.nsta, p.norb, p.nspin, p.convention = dim_k, nsta, norb, nspin, convention
+    p.nph = len(table)
+    p.ph_R = np.zeros((max(p.nph, 1), max(dim_k, 1)), dtype=np.float64)
+    for key, idx in table.items():
+        p.ph_R[idx, :dim_k] = key
+    tau = np.zeros((max(nsta, 1), max(dim_k, 1)), dtype=np.float64)
+    if dim_k > 0:
+        tau[:nsta, :dim_k] = np.repeat(np.asarray(model._orb, dtype=float)[:, per], nspin, axis=0)
+    p.tau = tau
+    # ---- element-major CSR (stable: keeps the reference's accumulation order)
+    key = rows * nsta + cols
+    order = np.argsort(key, kind="stable")
+    skey = key[order]
+    uniq, first = np.unique(skey, return_index=True)
+    p.nel = len(uniq)
+    p.nterm = nterm
+    p.el_ptr = np.append(first, nterm).astype(np.int32)
+    p.el_row = (uniq // nsta).astype(np.int32)
+    p.el_col = (uniq % nsta).astype(np.int32)
+    p.t_ph = phs[order].astype(np.int32)
+    p.t_amp = np.ascontiguousarray(amps[order].view(np.float64).reshape(-1, 2))
+    # ---- phase-major CSR
+    el_of_term = np.empty(nterm, dtype=np.int64)
+    el_of_term[order] = np.searchsorted(uniq, skey)
+    bucket = np.where(phs < 0, p.nph, phs & (PH_CONJ - 1))
+    order2 = np.argsort(bucket, kind="stable")
+    counts = np.bincount(bucket, minlength=p.nph + 1)
+    p.pm_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    cj = np.where(phs >= 0, phs & PH_CONJ, 0)
+    p.pm_el = (el_of_term | cj)[order2].astype(np.int32)
+    p.pm_amp = np.ascontiguousarray(amps[order2].view(np.float64).reshape(-1, 2))
+    if nterm == 0:
+        p.t_amp = np.zeros((1, 2))
+        p.pm_amp = np.zeros((1, 2))
+        p.t_ph = np.zeros(1, dtype=np.int32)
+        p.pm_el = np.zeros(1, dtype=np.int32)
+    if p.nel == 0:
+        p.el_row = np.zeros(1, dtype=np.int32)
+        p.el_col = np.zeros(1, dtype=np.int32)
+    return p

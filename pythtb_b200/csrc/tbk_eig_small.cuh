@@ -1,0 +1,139 @@
+// tbk_eig_small.cuh — one-thread-per-matrix Hermitian eigensolvers for the
+// tiny matrices of 2-band / spinor models (replaces numpy.linalg.eigh at
+// pythtb.py:939/944 for n <= 4).  Everything stays in registers.
+//
+// Conventions (pythtb.py:947-949): eigenvalues ascending, eigenvector b is
+// returned as the ROW w[b][0..n), not conjugated: H * w[b]^T = ev[b] * w[b]^T.
+#pragma once
+#include "tbk_common.cuh"
+
+namespace tbk {
+
+// ---------------------------------------------------------------------------
+// n = 2, closed form.  H = [[h00, conj(h10)], [h10, h11]] (lower triangle in,
+// like LAPACK UPLO='L' which numpy uses by default).
+// ---------------------------------------------------------------------------
+TBK_HD void eigh2(double h00, double h11, cplx h10, double ev[2], cplx w[2][2], bool want_vec) {
+  const double mean = 0.5 * (h00 + h11);
+  const double delta = 0.5 * (h00 - h11);
+  const double b2 = norm2(h10);
+  const double r = sqrt(delta * delta + b2);
+  ev[0] = mean - r;
+  ev[1] = mean + r;
+  if (!want_vec) return;
+  const cplx b = conj(h10);  // H[0][1]
+  if (b2 == 0.0) {
+    // diagonal matrix: order the unit vectors by eigenvalue
+    const bool swap = h00 > h11;
+    w[0][0] = mk(swap ? 0.0 : 1.0, 0.0);
+    w[0][1] = mk(swap ? 1.0 : 0.0, 0.0);
+    w[1][0] = mk(swap ? 1.0 : 0.0, 0.0);
+    w[1][1] = mk(swap ? 0.0 : 1.0, 0.0);
+    return;
+  }
+  // cancellation-free choice of the two null-vector formulas
+  const double big = fabs(delta) + r;                  // |delta| + r > 0
+  const double inv = 1.0 / sqrt(b2 + big * big);
+  if (delta >= 0.0) {
+    w[0][0] = inv * b;        w[0][1] = mk(-big * inv, 0.0);   // lower band
+    w[1][0] = mk(big * inv, 0.0); w[1][1] = inv * conj(b);     // upper band
+  } else {
+    w[0][0] = mk(-big * inv, 0.0); w[0][1] = inv * conj(b);
+    w[1][0] = inv * b;        w[1][1] = mk(big * inv, 0.0);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// 3 <= N <= 4 (compile time): cyclic complex Jacobi on packed storage.
+//   dg[N]                real diagonal
+//   lo[N(N-1)/2]         strict lower triangle, lo[r(r-1)/2 + c] = H[r][c], r > c
+//   w[N][N]              on exit rows = eigenvectors (if want_vec)
+// All loops over matrix indices are fully unrolled so the arrays live in
+// registers.
+// ---------------------------------------------------------------------------
+template <int N>
+struct JacobiPacked {
+  static constexpr int NL = N * (N - 1) / 2;
+  TBK_HD static constexpr int idx(int r, int c) { return r * (r - 1) / 2 + c; }
+
+  TBK_HD static cplx get(const cplx lo[], int r, int c) {
+    return r > c ? lo[idx(r, c)] : conj(lo[idx(c, r)]);
+  }
+  TBK_HD static void set(cplx lo[], int r, int c, cplx v) {
+    if (r > c) lo[idx(r, c)] = v; else lo[idx(c, r)] = conj(v);
+  }
+
+  TBK_HD static void solve(double dg[N], cplx lo[NL], cplx w[N][N], bool want_vec) {
+    if (want_vec) {
+#pragma unroll
+      for (int a = 0; a < N; ++a)
+#pragma unroll
+        for (int b = 0; b < N; ++b) w[a][b] = mk(a == b ? 1.0 : 0.0, 0.0);
+    }
+    double fro = 0.0;
+#pragma unroll
+    for (int a = 0; a < N; ++a) fro = fma(dg[a], dg[a], fro);
+#pragma unroll
+    for (int a = 0; a < NL; ++a) fro += 2.0 * norm2(lo[a]);
+    const double tol = 1.0e-31 * fro;   // |off|_F <= 3e-16 |H|_F
+    for (int sweep = 0; sweep < 24; ++sweep) {
+      double off = 0.0;
+#pragma unroll
+      for (int a = 0; a < NL; ++a) off += norm2(lo[a]);
+      if (off <= tol) break;
+#pragma unroll
+      for (int p = 0; p < N - 1; ++p) {
+#pragma unroll
+        for (int q = p + 1; q < N; ++q) {
+          const cplx apq = conj(lo[idx(q, p)]);       // H[p][q]
+          const double g2 = norm2(apq);
+          if (g2 > 1.0e-300) {
+            const double g = sqrt(g2);
+            const cplx ph = mk(apq.re / g, apq.im / g);   // e^{i phi}
+            const double theta = (dg[q] - dg[p]) / (2.0 * g);
+            const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+            const double c = 1.0 / sqrt(fma(t, t, 1.0));
+            const double s = t * c;
+            dg[p] -= t * g;
+            dg[q] += t * g;
+            lo[idx(q, p)] = mk(0.0, 0.0);
+            const cplx se = s * conj(ph);              // s e^{-i phi}
+            const cplx ce = c * conj(ph);              // c e^{-i phi}
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+              if (r != p && r != q) {
+                const cplx arp = get(lo, r, p), arq = get(lo, r, q);
+                set(lo, r, p, c * arp - arq * se);
+                set(lo, r, q, s * arp + arq * ce);
+              }
+            }
+            if (want_vec) {
+#pragma unroll
+              for (int o = 0; o < N; ++o) {
+                const cplx vp = w[p][o], vq = w[q][o];
+                w[p][o] = c * vp - vq * se;
+                w[q][o] = s * vp + vq * ce;
+              }
+            }
+          }
+        }
+      }
+    }
+    // ascending order (selection sort, unrolled; swaps rows of w)
+#pragma unroll
+    for (int a = 0; a < N - 1; ++a) {
+#pragma unroll
+      for (int b = a + 1; b < N; ++b) {
+        if (dg[b] < dg[a]) {
+          const double t = dg[a]; dg[a] = dg[b]; dg[b] = t;
+          if (want_vec) {
+#pragma unroll
+            for (int o = 0; o < N; ++o) { const cplx z = w[a][o]; w[a][o] = w[b][o]; w[b][o] = z; }
+          }
+        }
+      }
+    }
+  }
+};
+
+}  // namespace tbk

@@ -1,0 +1,89 @@
+// tbk_internal.cuh — shared by the .cu translation units of libtbk_b200.so:
+// error plumbing, the device-resident model, thread-group types for the SPMD
+// eigensolver / LU code, and small launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/tbk.h"
+#include "tbk_common.cuh"
+#include "tbk_plan.cuh"
+
+namespace tbk {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define TBK_CUDA(call)                                   \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+#define TBK_LAUNCH_CHECK(name)                               \
+  do {                                                       \
+    cudaError_t e__ = cudaGetLastError();                    \
+    if (e__ != cudaSuccess) return cuda_fail(e__, name);     \
+  } while (0)
+
+constexpr int kNumSM = 148;           // B200
+constexpr int kMaxSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
+
+// ---------------------------------------------------------------- thread groups
+#if defined(__CUDACC__)
+template <int G>
+struct TileGroup {
+  int t;
+  unsigned mask;
+  __device__ TileGroup() {
+    const int lane = threadIdx.x & 31;
+    t = lane % G;
+    mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - t));
+  }
+  __device__ int tid() const { return t; }
+  __device__ int size() const { return G; }
+  __device__ void sync() { __syncwarp(mask); }
+  __device__ double sum(double x) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(mask, x, o, G);
+    return x;
+  }
+};
+
+struct BlockGroup {
+  double* red;  // [32] shared scratch
+  __device__ explicit BlockGroup(double* r) : red(r) {}
+  __device__ int tid() const { return threadIdx.x; }
+  __device__ int size() const { return blockDim.x; }
+  __device__ void sync() { __syncthreads(); }
+  __device__ double sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if ((threadIdx.x & 31) == 0) red[w] = x;
+    __syncthreads();
+    double s = 0.0;
+    for (int i = 0; i < nw; ++i) s += red[i];
+    __syncthreads();
+    return s;
+  }
+};
+
+struct ThreadGroup {  // a "group" of one thread (serial code paths)
+  __device__ int tid() const { return 0; }
+  __device__ int size() const { return 1; }
+  __device__ void sync() {}
+  __device__ double sum(double x) { return x; }
+};
+#endif
+
+}  // namespace tbk
+
+// The opaque model handle of tbk.h
+struct tbk_model {
+  tbk::PlanView pv;   // device pointers
+  void* blob;         // single device allocation backing every array
+  size_t blob_bytes;
+  int device;
+  int max_terms_per_phase;
+};

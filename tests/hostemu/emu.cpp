@@ -1,0 +1,108 @@
+// tests/hostemu/emu.cpp — TEST INFRASTRUCTURE ONLY.
+// Compiles the TBK_HD math of pythtb_b200/csrc/*.cuh with g++ so the CPU test
+// suite can unit-test the device arithmetic (eigensolvers, Hamiltonian
+// assembly, overlap/determinant code) without a GPU.  Never loaded by the
+// product package.
+#include <vector>
+#include <cstring>
+#include "tbk_common.cuh"
+#include "tbk_eig_small.cuh"
+#include "tbk_eig_group.cuh"
+#include "tbk_plan.cuh"
+#include "tbk_berry.cuh"
+
+using namespace tbk;
+
+struct HostGroup {
+  int tid() const { return 0; }
+  int size() const { return 1; }
+  void sync() {}
+  double sum(double x) { return x; }
+};
+
+extern "C" {
+
+void emu_eigh2(double h00, double h11, double h10re, double h10im, double* ev, double* w) {
+  cplx ww[2][2];
+  eigh2(h00, h11, mk(h10re, h10im), ev, ww, true);
+  std::memcpy(w, ww, sizeof(ww));
+}
+
+// H: full n x n row-major complex (interleaved); lower triangle is used.
+int emu_jacobi(int n, const double* H, double* ev, double* w) {
+  const cplx* h = (const cplx*)H;
+  if (n == 3) {
+    double dg[3]; cplx lo[3]; cplx ww[3][3];
+    for (int r = 0; r < 3; ++r) { dg[r] = h[r * 3 + r].re; for (int c = 0; c < r; ++c) lo[JacobiPacked<3>::idx(r, c)] = h[r * 3 + c]; }
+    JacobiPacked<3>::solve(dg, lo, ww, true);
+    std::memcpy(ev, dg, sizeof(dg)); std::memcpy(w, ww, sizeof(ww));
+    return 0;
+  }
+  if (n == 4) {
+    double dg[4]; cplx lo[6]; cplx ww[4][4];
+    for (int r = 0; r < 4; ++r) { dg[r] = h[r * 4 + r].re; for (int c = 0; c < r; ++c) lo[JacobiPacked<4>::idx(r, c)] = h[r * 4 + c]; }
+    JacobiPacked<4>::solve(dg, lo, ww, true);
+    std::memcpy(ev, dg, sizeof(dg)); std::memcpy(w, ww, sizeof(ww));
+    return 0;
+  }
+  return -1;
+}
+
+// A: n x n column-major with leading dimension lda (lower triangle valid).
+// Outputs: ev[n] ascending, evec[n][n] rows = eigenvectors (reference layout).
+int emu_heev_group(int n, double* A, int lda, int want_vec, double* ev, double* evec) {
+  std::vector<char> buf(eig_scratch_bytes(n));
+  EigScratch s = eig_scratch_carve(buf.data(), n);
+  HostGroup g;
+  cplx* a = (cplx*)A;
+  int info = heev_group(g, n, a, lda, s, want_vec != 0);
+  std::vector<int> rank(n);
+  eig_rank(g, n, s.d, rank.data());
+  cplx* out = (cplx*)evec;
+  for (int i = 0; i < n; ++i) {
+    ev[rank[i]] = s.d[i];
+    if (want_vec)
+      for (int o = 0; o < n; ++o) out[(size_t)rank[i] * n + o] = a[o + (size_t)i * lda];
+  }
+  return info;
+}
+
+// Hamiltonian assembly from a compiled plan (host pointers), Convention I/II.
+void emu_gen_ham(const PlanView* pv, const double* k, int64_t nk, double* H) {
+  const int n = pv->nsta;
+  std::vector<cplx> ph(pv->nph > 0 ? pv->nph : 1);
+  for (int64_t ik = 0; ik < nk; ++ik) {
+    cplx* h = (cplx*)H + (size_t)ik * n * n;
+    plan_phases(*pv, k + ik * pv->dim_k, ph.data(), 1);
+    for (int e = 0; e < pv->nel; ++e) {
+      const cplx v = plan_element(*pv, e, ph.data(), 1);
+      const int r = pv->el_row[e], c = pv->el_col[e];
+      h[(size_t)r * n + c] = v;
+      if (r != c) h[(size_t)c * n + r] = conj(v);
+    }
+    if (pv->convention == 1) plan_gauge_matrix(*pv, k + ik * pv->dim_k, h, n);
+  }
+}
+
+// det of the overlap matrix of two row-blocks a[nocc][n], b[nocc][n]; returns
+// the unit-modulus phase of the determinant (re, im) and log|det|.
+void emu_link_det(int nocc, int n, const double* a, const double* b, double* out3) {
+  std::vector<cplx> M((size_t)nocc * nocc);
+  overlap_rows((const cplx*)a, n, (const cplx*)b, n, nocc, n, M.data(), nocc);
+  double lg;
+  cplx u = lu_det_phase(M.data(), nocc, nocc, &lg);
+  out3[0] = u.re; out3[1] = u.im; out3[2] = lg;
+}
+
+// polar factor of a small matrix (in place), row-major nocc x nocc
+int emu_polar(int nocc, double* M) {
+  std::vector<cplx> w1((size_t)nocc * nocc), w2((size_t)nocc * nocc);
+  return polar_unitary((cplx*)M, nocc, w1.data(), w2.data());
+}
+
+// eigenvalue phases of a unitary (general complex) matrix, row-major
+int emu_eigvals(int n, double* M, double* ev_re_im) {
+  return comqr_eigvals((cplx*)M, n, n, (cplx*)ev_re_im);
+}
+
+}  // extern "C"
