@@ -1,0 +1,345 @@
+"""B200 engine: the only numerical backend of ``pythtb_b200``.
+
+PyTorch is used for device memory, pinned host buffers and streams; all
+arithmetic happens in the hand-written sm_100a kernels of libtbk_b200.so,
+called through the C ABI of ``include/tbk.h``.  If the library or a CUDA
+device is missing every numerical call raises — there is no CPU fallback.
+
+The engine methods mirror the seams of the reference
+(``_gen_ham``/``_sol_ham``/``solve_all``/``solve_on_grid``/``_one_berry_loop``/
+``_one_flux_plane``/``position_*``; file:line in the docstrings).
+"""
+import ctypes
+import os
+import weakref
+
+import numpy as np
+
+from . import _lib
+
+_engine = None
+
+
+def get_engine():
+    global _engine
+    if _engine is None:
+        _engine = B200Engine()
+    return _engine
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class DeviceStore(object):
+    """Wavefunction storage of a ``wf_array``: a device tensor plus a lazily
+    synchronised pinned host mirror (the reference keeps ``_wfs`` in host
+    memory and lets users index/mutate it, pythtb.py:2419, 2662-2672).
+
+    state: 'empty'  nothing materialised (all zeros, like the reference's np.zeros)
+           'host'   the host mirror is authoritative (it has been handed out)
+           'device' the device tensor is authoritative
+    """
+
+    def __init__(self, engine, shape):
+        self.engine = engine
+        self.shape = tuple(int(x) for x in shape)
+        self._host_t = None
+        self._host = None
+        self._dev = None
+        self.state = "empty"
+
+    def host(self):
+        """Host ndarray (a view the caller may mutate)."""
+        torch = self.engine.torch
+        if self._host is None:
+            self._host_t = torch.zeros(self.shape, dtype=torch.complex128, pin_memory=True)
+            self._host = self._host_t.numpy()
+        if self.state == "device":
+            self._host_t.copy_(self._dev, non_blocking=False)
+        self.state = "host"
+        return self._host
+
+    def replace_host(self, arr):
+        torch = self.engine.torch
+        arr = np.ascontiguousarray(arr, dtype=complex)
+        self.shape = arr.shape
+        self._host_t = torch.empty(self.shape, dtype=torch.complex128, pin_memory=True)
+        self._host = self._host_t.numpy()
+        self._host[...] = arr
+        self._dev = None
+        self.state = "host"
+
+    def dev(self, will_write):
+        """Device tensor, uploaded if the host mirror is newer."""
+        torch = self.engine.torch
+        if self._dev is None or tuple(self._dev.shape) != self.shape:
+            self._dev = torch.zeros(self.shape, dtype=torch.complex128, device=self.engine.device)
+            if self.state == "device":
+                self.state = "empty"
+        if self.state == "host":
+            self._dev.copy_(self._host_t, non_blocking=True)
+        if will_write:
+            self.state = "device"
+        # after a read-only use the host mirror stays authoritative: the caller may
+        # still hold (and mutate) the view it was given
+        return self._dev
+
+
+class B200Engine(object):
+    def __init__(self):
+        self.lib = _lib.load()          # raises if the .so is missing
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("pythtb_b200: no CUDA device visible. This package runs only on a GPU "
+                               "(built for B200 / sm_100a); there is no CPU fallback.")
+        self.torch = torch
+        self.device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", torch.cuda.current_device())))
+        torch.cuda.set_device(self.device)
+        self._ws = None
+        self.launches = 0               # kernels launched through this engine (bench bookkeeping)
+
+    # ------------------------------------------------------------------ helpers
+    def stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def workspace(self, nbytes):
+        nbytes = int(nbytes)
+        if nbytes <= 0:
+            nbytes = 256
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = self.torch.empty(nbytes, dtype=self.torch.uint8, device=self.device)
+        return self._ws
+
+    def to_dev(self, arr, dtype=None):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype))
+        return t.to(self.device, non_blocking=False)
+
+    def model_handle(self, model):
+        """Upload (once) the compiled plan of ``model``; cached on the plan."""
+        plan = model._plan()
+        h = getattr(plan, "_handle", None)
+        if h is not None:
+            return h, plan
+        d = _lib.ModelDesc(plan.dim_k, plan.nsta, plan.nph, plan.nel, plan.nterm, plan.convention)
+        for name in ("ph_R", "tau", "el_ptr", "el_row", "el_col", "t_ph", "t_amp", "pm_ptr", "pm_el", "pm_amp"):
+            setattr(d, name, getattr(plan, name).ctypes.data)
+        out = ctypes.c_void_p(0)
+        _lib.check(self.lib.tbk_model_create(ctypes.byref(d), ctypes.byref(out)))
+        handle = ctypes.c_void_p(out.value)
+        plan._handle = handle
+        weakref.finalize(plan, self.lib.tbk_model_destroy, handle)
+        return handle, plan
+
+    # ------------------------------------------------------- Hamiltonian / eigh
+    def gen_ham(self, model, klist):
+        """tb_model._gen_ham batched (pythtb.py:874-925) -> [nk,n,n] complex."""
+        torch = self.torch
+        handle, plan = self.model_handle(model)
+        nk, n = klist.shape[0], plan.nsta
+        kd = self.to_dev(klist, np.float64) if plan.dim_k > 0 else None
+        ham = torch.empty((nk, n, n), dtype=torch.complex128, device=self.device)
+        _lib.check(self.lib.tbk_gen_ham(handle, _ptr(kd), nk, _ptr(ham), self.stream()))
+        self.launches += 1
+        return ham.cpu().numpy()
+
+    def eigh(self, ham, eig_vectors):
+        """_sol_ham batched (pythtb.py:927-953): rows of evec are eigenvectors."""
+        torch = self.torch
+        ham = np.ascontiguousarray(ham, dtype=complex)
+        batch, n = ham.shape[0], ham.shape[1]
+        hd = self.to_dev(ham)
+        ev = torch.empty((batch, n), dtype=torch.float64, device=self.device)
+        vec = torch.empty((batch, n, n), dtype=torch.complex128, device=self.device) if eig_vectors else None
+        wsb = self.lib.tbk_eigh_workspace(n, batch, int(eig_vectors))
+        ws = self.workspace(wsb)
+        _lib.check(self.lib.tbk_eigh_batched(_ptr(hd), n, batch, _ptr(ev), _ptr(vec), _ptr(ws), ws.numel(), self.stream()))
+        self.launches += 1
+        return ev.cpu().numpy(), (vec.cpu().numpy() if eig_vectors else None)
+
+    def solve_all_device(self, model, kd, nk, eig_vectors):
+        """Fused assembly+eigh for a device k-list; returns device tensors in the
+        reference layouts eval[band,k], evec[band,k,orb(,spin)] (pythtb.py:1040-1045)."""
+        torch = self.torch
+        handle, plan = self.model_handle(model)
+        n = plan.nsta
+        ev = torch.empty((n, nk), dtype=torch.float64, device=self.device)
+        vec = None
+        if eig_vectors:
+            vec = torch.empty((n, nk, n), dtype=torch.complex128, device=self.device)
+        ws = self.workspace(self.lib.tbk_solve_workspace(n, nk, int(eig_vectors)))
+        _lib.check(self.lib.tbk_solve_k(handle, _ptr(kd), nk, _ptr(ev), nk, 1, _ptr(vec), nk * n, n,
+                                        _ptr(ws), ws.numel(), self.stream()))
+        self.launches += 1
+        return ev, vec
+
+    def solve_all(self, model, klist, eig_vectors):
+        nk = klist.shape[0]
+        if nk == 0:      # empty k-list: nothing to launch (reference returns empty arrays)
+            ev_h = np.zeros((model._nsta, 0), dtype=float)
+            if not eig_vectors:
+                return ev_h
+            tail = (model._norb,) if model._nspin == 1 else (model._norb, 2)
+            return ev_h, np.zeros((model._nsta, 0) + tail, dtype=complex)
+        kd = self.to_dev(klist, np.float64) if model._dim_k > 0 else None
+        ev, vec = self.solve_all_device(model, kd, nk, eig_vectors)
+        ev_h = ev.cpu().numpy()
+        if not eig_vectors:
+            return ev_h
+        vec_h = vec.cpu().numpy()
+        if model._nspin == 2:
+            vec_h = vec_h.reshape(model._nsta, nk, model._norb, 2)
+        return ev_h, vec_h
+
+    # ------------------------------------------------------------ wf_array ops
+    def new_store(self, shape):
+        return DeviceStore(self, shape)
+
+    def pbc_phases(self, orb, nspin, k_dirs):
+        """exp(-2 pi i tau_j[k_dir]) per state (pythtb.py:2729-2736), [len(k_dirs), nsta]."""
+        out = []
+        for kd in k_dirs:
+            ffac = np.exp(-2.0j * np.pi * np.asarray(orb)[:, kd])
+            out.append(np.repeat(ffac, nspin))
+        return np.array(out, dtype=complex)
+
+    def solve_grid(self, model, store, mesh_arr, start_k, row0=0, nrows=None, wrap0=True):
+        """wf_array.solve_on_grid + impose_pbc (pythtb.py:2421-2532) into ``store``;
+        returns the minimal gaps as a device tensor (or None)."""
+        torch = self.torch
+        handle, plan = self.model_handle(model)
+        nd, n = len(mesh_arr), plan.nsta
+        if nrows is None:
+            nrows = int(mesh_arr[0]) - 1
+        wfs = store.dev(will_write=True)
+        phase = self.to_dev(self.pbc_phases(model._orb, model._nspin, [model._per[d] for d in range(nd)]))
+        gaps = torch.empty(max(n - 1, 1), dtype=torch.float64, device=self.device) if n > 1 else None
+        npts = nrows * int(np.prod(np.asarray(mesh_arr[1:]) - 1)) if nd > 1 else nrows
+        ws = self.workspace(self.lib.tbk_solve_workspace(n, max(npts, 1), 1))
+        start = (ctypes.c_double * nd)(*[float(x) for x in start_k])
+        mesh = (ctypes.c_int32 * nd)(*[int(x) for x in mesh_arr])
+        _lib.check(self.lib.tbk_solve_grid(handle, start, mesh, nd, int(row0), int(nrows), int(bool(wrap0)),
+                                           _ptr(wfs), _ptr(phase), _ptr(gaps), _ptr(ws), ws.numel(), self.stream()))
+        self.launches += 2 if gaps is not None else 1
+        return gaps
+
+    def impose_boundary(self, store, dim_arr, mesh_dir, phase):
+        """impose_pbc / impose_loop on the device (pythtb.py:2674-2791)."""
+        shape = store.shape
+        wfs = store.dev(will_write=True)
+        outer = int(np.prod(shape[:mesh_dir])) if mesh_dir > 0 else 1
+        length = shape[mesh_dir]
+        inner = int(np.prod(shape[mesh_dir + 1:dim_arr])) if mesh_dir + 1 < dim_arr else 1
+        nsta_arr = shape[dim_arr]
+        n = int(np.prod(shape[dim_arr + 1:]))
+        ph = self.to_dev(phase) if phase is not None else None
+        _lib.check(self.lib.tbk_impose_boundary(_ptr(wfs), outer, length, inner, nsta_arr, n, _ptr(ph), self.stream()))
+        self.launches += 1
+
+    def _view(self, store, dim_arr, occ):
+        wfs = store.dev(will_write=False)
+        shape = store.shape
+        nsta_arr = shape[dim_arr]
+        n = int(np.prod(shape[dim_arr + 1:]))
+        occ = np.asarray(occ, dtype=np.int64)
+        if occ.size == 0:
+            raise Exception("\n\nNo states selected.")
+        occ = np.where(occ < 0, occ + nsta_arr, occ)
+        if occ.min() < 0 or occ.max() >= nsta_arr:
+            raise IndexError("index in occ out of bounds")
+        occ_d = self.to_dev(occ.astype(np.int32))
+        view = _lib.WfView(wfs.data_ptr(), n, nsta_arr, len(occ), occ_d.data_ptr())
+        strides = [int(np.prod(shape[d + 1:dim_arr])) * nsta_arr * n for d in range(dim_arr)]
+        return view, strides, (wfs, occ_d)
+
+    def berry_strings(self, store, dim_arr, occ, dir, berry_evals):
+        """_one_berry_loop for every string along ``dir`` (pythtb.py:2979-3029,
+        3798-3838); raw phases in [-pi,pi), shape other_axes (+[nocc])."""
+        torch = self.torch
+        view, strides, keep = self._view(store, dim_arr, occ)
+        mesh = store.shape[:dim_arr]
+        other = [d for d in range(dim_arr) if d != dir]
+        oshape = tuple(mesh[d] for d in other)
+        offs = np.zeros(oshape if oshape else (1,), dtype=np.int64)
+        for ax, d in enumerate(other):
+            sh = [1] * len(other)
+            sh[ax] = mesh[d]
+            offs = offs + (np.arange(mesh[d], dtype=np.int64) * strides[d]).reshape(sh)
+        offs = np.ascontiguousarray(offs.reshape(-1))
+        nstr, npts, nocc = offs.size, mesh[dir], view.nocc
+        offs_d = self.to_dev(offs)
+        out = torch.empty((nstr, nocc) if berry_evals else (nstr,), dtype=torch.float64, device=self.device)
+        ws = self.workspace(self.lib.tbk_berry_workspace(nocc, view.n, nstr, npts, int(berry_evals)))
+        _lib.check(self.lib.tbk_berry_strings(ctypes.byref(view), _ptr(offs_d), nstr, npts, strides[dir],
+                                              int(berry_evals), _ptr(out), _ptr(ws), ws.numel(), self.stream()))
+        self.launches += 2
+        res = out.cpu().numpy()
+        return res.reshape(oshape + ((nocc,) if berry_evals else ()))
+
+    def flux(self, store, dim_arr, occ, dirs, individual):
+        """_one_flux_plane on every 2-D slice spanned by ``dirs`` (pythtb.py:3133-3202).
+        Returns plaquette phases [rest..., n0-1, n1-1] or their sums [rest...]."""
+        tot, plq = self.flux_device(store, dim_arr, occ, dirs, want_total=not individual, want_plaq=individual)
+        mesh = store.shape[:dim_arr]
+        rest = [d for d in range(dim_arr) if d not in dirs]
+        rshape = tuple(mesh[d] for d in rest)
+        if individual:
+            return plq.cpu().numpy().reshape(rshape + (mesh[dirs[0]] - 1, mesh[dirs[1]] - 1))
+        return tot.cpu().numpy().reshape(rshape)
+
+    def flux_device(self, store, dim_arr, occ, dirs, want_total=True, want_plaq=False):
+        torch = self.torch
+        view, strides, keep = self._view(store, dim_arr, occ)
+        mesh = store.shape[:dim_arr]
+        rest = [d for d in range(dim_arr) if d not in dirs]
+        rshape = tuple(mesh[d] for d in rest)
+        offs = np.zeros(rshape if rshape else (1,), dtype=np.int64)
+        for ax, d in enumerate(rest):
+            sh = [1] * len(rest)
+            sh[ax] = mesh[d]
+            offs = offs + (np.arange(mesh[d], dtype=np.int64) * strides[d]).reshape(sh)
+        offs = np.ascontiguousarray(offs.reshape(-1))
+        nslice = offs.size
+        n0, n1 = mesh[dirs[0]], mesh[dirs[1]]
+        offs_d = self.to_dev(offs)
+        plq = torch.empty((nslice, n0 - 1, n1 - 1), dtype=torch.float64, device=self.device) if want_plaq else None
+        tot = torch.empty((nslice,), dtype=torch.float64, device=self.device) if want_total else None
+        ws = self.workspace(self.lib.tbk_flux_workspace(view.nocc, view.n, nslice, n0, n1))
+        _lib.check(self.lib.tbk_flux_plane(ctypes.byref(view), _ptr(offs_d), nslice, n0, strides[dirs[0]], n1,
+                                           strides[dirs[1]], _ptr(plq), _ptr(tot), _ptr(ws), ws.numel(), self.stream()))
+        self.launches += 2 if want_total else 1
+        return tot, plq
+
+    # ------------------------------------------------------- position operator
+    def _pos(self, model, dir):
+        return np.repeat(np.asarray(model._orb, dtype=float)[:, dir], model._nspin)
+
+    def position_matrix(self, model, evec, dir):
+        """tb_model.position_matrix batched (pythtb.py:2034-2113): evec[batch,nocc,n]."""
+        torch = self.torch
+        evec = np.ascontiguousarray(evec, dtype=complex)
+        batch, nocc, n = evec.shape
+        ed = self.to_dev(evec)
+        pos = self.to_dev(self._pos(model, dir), np.float64)
+        x = torch.empty((batch, nocc, nocc), dtype=torch.complex128, device=self.device)
+        _lib.check(self.lib.tbk_position_matrix(_ptr(ed), batch, nocc, n, _ptr(pos), _ptr(x), self.stream()))
+        self.launches += 1
+        return x.cpu().numpy()
+
+    def position_hwf(self, model, evec, dir, hwf_evec, orbital_basis):
+        """tb_model.position_hwf batched (pythtb.py:2162-2279)."""
+        torch = self.torch
+        evec = np.ascontiguousarray(evec, dtype=complex)
+        batch, nocc, n = evec.shape
+        ed = self.to_dev(evec)
+        pos = self.to_dev(self._pos(model, dir), np.float64)
+        hwfc = torch.empty((batch, nocc), dtype=torch.float64, device=self.device)
+        hwf = None
+        if hwf_evec:
+            hwf = torch.empty((batch, nocc, n if orbital_basis else nocc), dtype=torch.complex128, device=self.device)
+        ws = self.workspace(self.lib.tbk_position_hwf_workspace(nocc, n, batch))
+        _lib.check(self.lib.tbk_position_hwf(_ptr(ed), batch, nocc, n, _ptr(pos), _ptr(hwfc), _ptr(hwf),
+                                             int(bool(orbital_basis)), _ptr(ws), ws.numel(), self.stream()))
+        self.launches += 3
+        return hwfc.cpu().numpy(), (hwf.cpu().numpy() if hwf_evec else None)

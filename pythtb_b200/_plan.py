@@ -16,10 +16,6 @@ PH_CONJ = 1 << 30
 class Plan(object):
     """Host-side compiled model (numpy arrays, C-contiguous)."""
 
-    __slots__ = ("dim_k", "nsta", "nph", "nel", "nterm", "convention", "ph_R", "tau",
-                 "el_ptr", "el_row", "el_col", "t_ph", "t_amp", "pm_ptr", "pm_el", "pm_amp",
-                 "norb", "nspin")
-
     def nbytes(self):
         return sum(getattr(self, k).nbytes for k in
                    ("ph_R", "tau", "el_ptr", "el_row", "el_col", "t_ph", "t_amp", "pm_ptr", "pm_el", "pm_amp"))

@@ -1,0 +1,664 @@
+// tbk_solve.cu — Bloch-Hamiltonian assembly fused with batched Hermitian
+// diagonalisation (the reference's _gen_ham -> _sol_ham loop,
+// pythtb.py:1047-1060 and 2475-2525), written for sm_100a.
+//
+// Kernel families (chosen by nsta):
+//   solve_small_kernel<N>   N = 2,3,4: one k-point per thread, H and the
+//                           eigenvectors never leave registers; closed form for
+//                           N = 2, cyclic Jacobi for N = 3,4.
+//   solve_tile_kernel<G>    5 <= nsta <= 32: one k-point per G-lane tile of a
+//                           warp (G = 8,16,32), matrix resident in shared memory.
+//   solve_block_kernel      nsta > 32: one k-point per CTA, matrix in shared
+//                           memory up to nsta = 112, else in an L2/HBM workspace.
+// All of them generate k on the fly (mesh descriptor) or read a k-list, build
+// the lower triangle of H from the compiled plan, diagonalise, apply the
+// Convention-I gauge, and write the reference's output layouts directly
+// (solve_all's eval[band,k] / evec[band,k,orb] or the wf_array grid with its
+// periodic images and the running minimum of the direct gaps).
+#include "tbk_internal.cuh"
+#include "tbk_eig_small.cuh"
+#include "tbk_eig_group.cuh"
+
+namespace tbk {
+
+struct KSrc {
+  const double* klist;  // [npts][dim_k], or nullptr -> mesh descriptor below
+  int dim_k;
+  int row0;             // offset added to the axis-0 mesh index (shards)
+  double start[TBK_MAX_DIM];
+  double den[TBK_MAX_DIM];   // mesh[d]-1 as double
+};
+
+struct OutSpec {
+  int mode;  // 0 = list (solve_all layouts), 1 = grid (wf_array slab)
+  double* eval; long long ev_sb, ev_sk;
+  cplx* evec;   long long vc_sb, vc_sk;
+  int nd;
+  int cnt[TBK_MAX_DIM];            // solved points per axis
+  int full[TBK_MAX_DIM];           // storage extent per axis
+  long long gstride[TBK_MAX_DIM];  // storage stride per axis, complex elements
+  int wrap[TBK_MAX_DIM];           // write the periodic image along this axis
+  const cplx* pbc_phase;           // [nd][n]
+  unsigned long long* gaps_bits;   // [n-1] running min of non-negative doubles, or null
+};
+
+__device__ __forceinline__ void decode_index(long long idx, const OutSpec& o, int mi[TBK_MAX_DIM]) {
+#pragma unroll
+  for (int d = TBK_MAX_DIM - 1; d >= 0; --d) {
+    if (d < o.nd) {
+      const long long q = idx / o.cnt[d];
+      mi[d] = (int)(idx - q * o.cnt[d]);
+      idx = q;
+    } else {
+      mi[d] = 0;
+    }
+  }
+}
+
+__device__ __forceinline__ void load_k(const KSrc& ks, long long idx, const int mi[TBK_MAX_DIM], double k[TBK_MAX_DIM]) {
+#pragma unroll
+  for (int d = 0; d < TBK_MAX_DIM; ++d) {
+    if (d < ks.dim_k) {
+      if (ks.klist) k[d] = ks.klist[idx * ks.dim_k + d];
+      else k[d] = ks.start[d] + (double)(mi[d] + (d == 0 ? ks.row0 : 0)) / ks.den[d];   // pythtb.py:2477
+    } else {
+      k[d] = 0.0;
+    }
+  }
+}
+
+__device__ __forceinline__ void atomic_min_nonneg(unsigned long long* addr, double v) {
+  atomicMin(addr, (unsigned long long)__double_as_longlong(v));
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, int n, unsigned long long v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ===========================================================================
+// One k-point per thread, N = 2..4
+// ===========================================================================
+template <int N>
+__global__ void __launch_bounds__(128)
+solve_small_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long long npts, OutSpec out,
+                   int want_vec, int stage_plan) {
+  constexpr int NP = N * (N + 1) / 2;
+  extern __shared__ __align__(16) char smem[];
+  // ---- stage the (tiny) plan in shared memory: every thread walks the same term list
+  const int nterm = pv.nterm, nph = pv.nph, dk = pv.dim_k;
+  const int* pm_ptr = pv.pm_ptr;
+  const int* pm_pk = nullptr;          // packed lower index | conj flag
+  const cplx* pm_amp = (const cplx*)pv.pm_amp;
+  const double* ph_R = pv.ph_R;
+  const double* tau = pv.tau;
+  if (hsrc == nullptr && stage_plan) {
+    cplx* s_amp = (cplx*)smem;
+    double* s_R = (double*)(s_amp + nterm);
+    double* s_tau = s_R + nph * dk;
+    int* s_ptr = (int*)(s_tau + N * dk);
+    int* s_pk = s_ptr + (nph + 2);
+    for (int t = threadIdx.x; t < nterm; t += blockDim.x) {
+      s_amp[t] = pm_amp[t];
+      const int e = pv.pm_el[t];
+      const int id = e & TBK_PH_MASK;
+      const int r = pv.el_row[id], c = pv.el_col[id];
+      s_pk[t] = (r * (r + 1) / 2 + c) | (e & TBK_PH_CONJ);
+    }
+    for (int t = threadIdx.x; t < nph * dk; t += blockDim.x) s_R[t] = ph_R[t];
+    for (int t = threadIdx.x; t < N * dk; t += blockDim.x) s_tau[t] = tau[t];
+    for (int t = threadIdx.x; t < nph + 2; t += blockDim.x) s_ptr[t] = pm_ptr[t];
+    __syncthreads();
+    pm_amp = s_amp; ph_R = s_R; tau = s_tau; pm_ptr = s_ptr; pm_pk = s_pk;
+  }
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool active = idx < npts;
+  int mi[TBK_MAX_DIM] = {0, 0, 0, 0};
+  double k[TBK_MAX_DIM] = {0.0, 0.0, 0.0, 0.0};
+  double ev[N];
+  cplx w[N][N];
+#pragma unroll
+  for (int b = 0; b < N; ++b) ev[b] = 0.0;
+  if (active) {
+    cplx acc[NP];
+#pragma unroll
+    for (int e = 0; e < NP; ++e) acc[e] = mk(0.0, 0.0);
+    if (hsrc != nullptr) {
+      const cplx* h = hsrc + idx * (long long)(N * N);
+#pragma unroll
+      for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) acc[r * (r + 1) / 2 + c] = h[r * N + c];
+    } else {
+      if (out.mode == 1) decode_index(idx, out, mi);
+      load_k(ks, idx, mi, k);
+      // phase-major accumulation: one sincospi per unique lattice vector
+      for (int p = 0; p <= nph; ++p) {
+        cplx z = mk(1.0, 0.0);
+        if (p < nph) {
+          double x = 0.0;
+          for (int d = 0; d < dk; ++d) x = fma(k[d], ph_R[p * dk + d], x);
+          z = expi_turns(x);
+        }
+        const int t1 = pm_ptr[p + 1];
+        for (int t = pm_ptr[p]; t < t1; ++t) {
+          int pk;
+          if (pm_pk) pk = pm_pk[t];
+          else {
+            const int e = pv.pm_el[t];
+            const int id = e & TBK_PH_MASK;
+            const int r = pv.el_row[id], c = pv.el_col[id];
+            pk = (r * (r + 1) / 2 + c) | (e & TBK_PH_CONJ);
+          }
+          const cplx a = pm_amp[t];
+          cplx zz = z;
+          if (pk & TBK_PH_CONJ) zz.im = -zz.im;
+          pk &= TBK_PH_MASK;
+#pragma unroll
+          for (int e = 0; e < NP; ++e)
+            if (pk == e) fma_acc(acc[e], a, zz);
+        }
+      }
+    }
+    // ---- diagonalise
+    if constexpr (N == 2) {
+      eigh2(acc[0].re, acc[2].re, acc[1], ev, w, want_vec != 0);
+    } else {
+      double dg[N];
+      cplx lo[N * (N - 1) / 2];
+#pragma unroll
+      for (int r = 0; r < N; ++r) {
+        dg[r] = acc[r * (r + 1) / 2 + r].re;
+#pragma unroll
+        for (int c = 0; c < r; ++c) lo[r * (r - 1) / 2 + c] = acc[r * (r + 1) / 2 + c];
+      }
+      JacobiPacked<N>::solve(dg, lo, w, want_vec != 0);
+#pragma unroll
+      for (int b = 0; b < N; ++b) ev[b] = dg[b];
+    }
+    // ---- Convention I gauge: u_I[b][j] = conj(d_j) u_II[b][j], d_j = exp(2 pi i k.tau_j)
+    if (want_vec && hsrc == nullptr && pv.convention == 1 && dk > 0) {
+#pragma unroll
+      for (int o = 0; o < N; ++o) {
+        double x = 0.0;
+        for (int d = 0; d < dk; ++d) x = fma(k[d], tau[o * dk + d], x);
+        const cplx dj = expi_turns(x);
+#pragma unroll
+        for (int b = 0; b < N; ++b) w[b][o] = cmul(dj, w[b][o]);
+      }
+    }
+    // ---- write
+    if (out.mode == 0) {
+      if (out.eval) {
+#pragma unroll
+        for (int b = 0; b < N; ++b) out.eval[b * out.ev_sb + idx * out.ev_sk] = ev[b];
+      }
+      if (want_vec) {
+#pragma unroll
+        for (int b = 0; b < N; ++b) {
+          cplx* dst = out.evec + b * out.vc_sb + idx * out.vc_sk;
+#pragma unroll
+          for (int o = 0; o < N; ++o) dst[o] = w[b][o];
+        }
+      }
+    } else {
+      long long base = 0;
+#pragma unroll
+      for (int d = 0; d < TBK_MAX_DIM; ++d)
+        if (d < out.nd) base += mi[d] * out.gstride[d];
+      cplx* dst = out.evec + base;
+#pragma unroll
+      for (int b = 0; b < N; ++b)
+#pragma unroll
+        for (int o = 0; o < N; ++o) dst[b * N + o] = w[b][o];
+      // periodic images (impose_pbc, pythtb.py:2729-2747), every subset of the
+      // axes on which this point sits at index 0
+      int zero_mask = 0;
+      for (int d = 0; d < out.nd; ++d)
+        if (mi[d] == 0 && out.wrap[d]) zero_mask |= 1 << d;
+      if (zero_mask) {
+        for (int m = 1; m < (1 << out.nd); ++m) {
+          if ((m & zero_mask) != m) continue;
+          long long off = base;
+          cplx f[N];
+#pragma unroll
+          for (int o = 0; o < N; ++o) f[o] = mk(1.0, 0.0);
+          for (int d = 0; d < out.nd; ++d) {
+            if (m & (1 << d)) {
+              off += (long long)(out.full[d] - 1) * out.gstride[d];
+#pragma unroll
+              for (int o = 0; o < N; ++o) f[o] = f[o] * out.pbc_phase[d * N + o];
+            }
+          }
+          cplx* im = out.evec + off;
+#pragma unroll
+          for (int b = 0; b < N; ++b)
+#pragma unroll
+            for (int o = 0; o < N; ++o) im[b * N + o] = w[b][o] * f[o];
+        }
+      }
+    }
+  }
+  // ---- running minimum of the direct gaps (pythtb.py:2484, 2529-2530)
+  if (out.mode == 1 && out.gaps_bits != nullptr) {
+#pragma unroll
+    for (int b = 0; b < N - 1; ++b) {
+      double g = active ? (ev[b + 1] - ev[b]) : INFINITY;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) g = fmin(g, __shfl_xor_sync(0xffffffffu, g, o));
+      if ((threadIdx.x & 31) == 0) atomic_min_nonneg(out.gaps_bits + b, g);
+    }
+  }
+}
+
+// ===========================================================================
+// One k-point per thread group, matrix in shared memory or in a workspace
+// ===========================================================================
+struct GroupShape {
+  int n, lda, nph;
+  size_t off_scr, off_ph, off_rank, off_k, region;   // byte offsets inside a per-matrix region
+  bool a_in_smem;
+};
+
+static GroupShape group_shape(int n, int nph, bool a_in_smem) {
+  GroupShape s;
+  s.n = n; s.lda = n | 1; s.nph = nph; s.a_in_smem = a_in_smem;
+  size_t off = a_in_smem ? (size_t)n * s.lda * 16 : 0;
+  s.off_scr = off;  off += (eig_scratch_bytes(n) + 15) & ~(size_t)15;
+  s.off_ph = off;   off += (size_t)(nph > 0 ? nph : 1) * 16;
+  s.off_rank = off; off += ((size_t)n * 4 + 15) & ~(size_t)15;
+  s.off_k = off;    off += 64;
+  s.region = off;
+  return s;
+}
+
+template <class G>
+__device__ void solve_one_matrix(G& g, const PlanView& pv, const KSrc& ks, const cplx* __restrict__ hsrc,
+                                 long long idx, const OutSpec& out, int want_vec, const GroupShape& gs,
+                                 cplx* A, char* region) {
+  const int n = gs.n, lda = gs.lda;
+  EigScratch s = eig_scratch_carve(region + gs.off_scr, n);
+  cplx* ph = (cplx*)(region + gs.off_ph);
+  int* rank = (int*)(region + gs.off_rank);
+  double* kbuf = (double*)(region + gs.off_k);
+  int* mibuf = (int*)(kbuf + TBK_MAX_DIM);
+  // ---- k-point
+  if (g.tid() == 0) {
+    int mi[TBK_MAX_DIM] = {0, 0, 0, 0};
+    double k[TBK_MAX_DIM];
+    if (out.mode == 1) decode_index(idx, out, mi);
+    load_k(ks, idx, mi, k);
+    for (int d = 0; d < TBK_MAX_DIM; ++d) { kbuf[d] = k[d]; mibuf[d] = mi[d]; }
+  }
+  for (int i = g.tid(); i < n * lda; i += g.size()) A[i] = mk(0.0, 0.0);
+  g.sync();
+  // ---- lower triangle of H
+  if (hsrc != nullptr) {
+    const cplx* h = hsrc + idx * (long long)n * n;
+    for (int q = g.tid(); q < n * n; q += g.size()) {
+      const int r = q / n, c = q - r * n;
+      if (c <= r) A[r + (size_t)c * lda] = h[q];
+    }
+  } else {
+    for (int p = g.tid(); p < pv.nph; p += g.size()) {
+      double x = 0.0;
+      for (int d = 0; d < pv.dim_k; ++d) x = fma(kbuf[d], pv.ph_R[p * pv.dim_k + d], x);
+      ph[p] = expi_turns(x);
+    }
+    g.sync();
+    for (int e = g.tid(); e < pv.nel; e += g.size())
+      A[pv.el_row[e] + (size_t)pv.el_col[e] * lda] = plan_element(pv, e, ph, 1);
+  }
+  g.sync();
+  // ---- diagonalise
+  const int info = heev_group(g, n, A, lda, s, want_vec != 0);
+  eig_rank(g, n, s.d, rank);
+  if (info != 0) {   // not converged: poison the eigenvalues so that it cannot go unnoticed
+    for (int i = g.tid(); i < n; i += g.size()) s.d[i] = NAN;
+    g.sync();
+  }
+  // ---- gauge factors conj(d_o) -> s.work, sorted eigenvalues -> s.e
+  for (int o = g.tid(); o < n; o += g.size()) {
+    cplx f = mk(1.0, 0.0);
+    if (want_vec && hsrc == nullptr && pv.convention == 1 && pv.dim_k > 0) f = conj(plan_gauge(pv, kbuf, o));
+    s.work[o] = f;
+    s.e[rank[o]] = s.d[o];
+  }
+  g.sync();
+  // ---- write
+  if (out.mode == 0) {
+    if (out.eval)
+      for (int b = g.tid(); b < n; b += g.size()) out.eval[b * out.ev_sb + idx * out.ev_sk] = s.e[b];
+    if (want_vec) {
+      for (int q = g.tid(); q < n * n; q += g.size()) {
+        const int i = q / n, o = q - i * n;
+        out.evec[rank[i] * out.vc_sb + idx * out.vc_sk + o] = A[o + (size_t)i * lda] * s.work[o];
+      }
+    }
+  } else {
+    long long base = 0;
+    int zero_mask = 0;
+    for (int d = 0; d < out.nd; ++d) {
+      base += mibuf[d] * out.gstride[d];
+      if (mibuf[d] == 0 && out.wrap[d]) zero_mask |= 1 << d;
+    }
+    for (int q = g.tid(); q < n * n; q += g.size()) {
+      const int i = q / n, o = q - i * n;
+      const cplx v = A[o + (size_t)i * lda] * s.work[o];
+      const long long at = (long long)rank[i] * n + o;
+      out.evec[base + at] = v;
+      if (zero_mask) {
+        for (int m = 1; m < (1 << out.nd); ++m) {
+          if ((m & zero_mask) != m) continue;
+          long long off = base;
+          cplx f = v;
+          for (int d = 0; d < out.nd; ++d)
+            if (m & (1 << d)) {
+              off += (long long)(out.full[d] - 1) * out.gstride[d];
+              f = f * out.pbc_phase[d * n + o];
+            }
+          out.evec[off + at] = f;
+        }
+      }
+    }
+    if (out.gaps_bits != nullptr)
+      for (int b = g.tid(); b < n - 1; b += g.size()) atomic_min_nonneg(out.gaps_bits + b, s.e[b + 1] - s.e[b]);
+  }
+  g.sync();
+}
+
+template <int G>
+__global__ void __launch_bounds__(128)
+solve_tile_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long long npts, OutSpec out,
+                  int want_vec, GroupShape gs) {
+  extern __shared__ __align__(16) char smem[];
+  constexpr int MATS = 128 / G;
+  TileGroup<G> g;
+  const int sub = threadIdx.x / G;
+  char* region = smem + (size_t)sub * gs.region;
+  cplx* A = (cplx*)region;
+  for (long long idx = (long long)blockIdx.x * MATS + sub; idx < npts; idx += (long long)gridDim.x * MATS)
+    solve_one_matrix(g, pv, ks, hsrc, idx, out, want_vec, gs, A, region);
+}
+
+__global__ void __launch_bounds__(256)
+solve_block_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long long npts, OutSpec out,
+                   int want_vec, GroupShape gs, cplx* gA) {
+  extern __shared__ __align__(16) char smem[];
+  __shared__ double red[32];
+  BlockGroup g(red);
+  cplx* A = gs.a_in_smem ? (cplx*)smem : gA + (size_t)blockIdx.x * gs.n * gs.lda;
+  for (long long idx = blockIdx.x; idx < npts; idx += gridDim.x)
+    solve_one_matrix(g, pv, ks, hsrc, idx, out, want_vec, gs, A, smem);
+}
+
+// ===========================================================================
+// Full H(k) output (tb_model._gen_ham)
+// ===========================================================================
+__global__ void __launch_bounds__(128)
+gen_ham_kernel(PlanView pv, const double* __restrict__ klist, long long nk, cplx* __restrict__ ham) {
+  extern __shared__ __align__(16) char smem[];
+  cplx* ph = (cplx*)smem;                       // [nph]
+  cplx* dj = ph + (pv.nph > 0 ? pv.nph : 1);    // [n]
+  const int n = pv.nsta;
+  for (long long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
+    double k[TBK_MAX_DIM] = {0.0, 0.0, 0.0, 0.0};
+    for (int d = 0; d < pv.dim_k; ++d) k[d] = klist[ik * pv.dim_k + d];
+    for (int p = threadIdx.x; p < pv.nph; p += blockDim.x) {
+      double x = 0.0;
+      for (int d = 0; d < pv.dim_k; ++d) x = fma(k[d], pv.ph_R[p * pv.dim_k + d], x);
+      ph[p] = expi_turns(x);
+    }
+    for (int o = threadIdx.x; o < n; o += blockDim.x)
+      dj[o] = (pv.convention == 1 && pv.dim_k > 0) ? plan_gauge(pv, k, o) : mk(1.0, 0.0);
+    cplx* h = ham + ik * (long long)n * n;
+    for (int q = threadIdx.x; q < n * n; q += blockDim.x) h[q] = mk(0.0, 0.0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < pv.nel; e += blockDim.x) {
+      const int r = pv.el_row[e], c = pv.el_col[e];
+      cplx v = plan_element(pv, e, ph, 1);
+      v = cmul(dj[r], v) * dj[c];               // H_I = D^H H_II D
+      if (r == c) v.im = 0.0;
+      h[(size_t)r * n + c] = v;
+      if (r != c) h[(size_t)c * n + r] = conj(v);
+    }
+    __syncthreads();
+  }
+}
+
+// ===========================================================================
+// host-side launch logic
+// ===========================================================================
+static size_t small_plan_smem(const PlanView& pv, int n) {
+  return (size_t)pv.nterm * 16 + (size_t)pv.nph * pv.dim_k * 8 + (size_t)n * pv.dim_k * 8 +
+         (size_t)(pv.nph + 2) * 4 + (size_t)pv.nterm * 4 + 64;
+}
+
+static int block_threads_for(int n) { return n <= 64 ? 64 : (n <= 128 ? 128 : 256); }
+
+static int launch_solve(const PlanView& pv, const KSrc& ks, const cplx* hsrc, int n, long long npts,
+                        const OutSpec& out, int want_vec, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (npts <= 0) return TBK_OK;
+  if (n <= 4 && n >= 2) {
+    const size_t sm = hsrc ? 0 : small_plan_smem(pv, n);
+    const int stage = (!hsrc && sm <= 40 * 1024) ? 1 : 0;
+    const size_t dyn = stage ? sm : 0;
+    const long long blocks = (npts + 127) / 128;
+    if (blocks > 0x7fffffffLL) { set_error("too many k-points for one launch"); return TBK_ERR_ARG; }
+    if (n == 2) solve_small_kernel<2><<<(unsigned)blocks, 128, dyn, st>>>(pv, ks, hsrc, npts, out, want_vec, stage);
+    else if (n == 3) solve_small_kernel<3><<<(unsigned)blocks, 128, dyn, st>>>(pv, ks, hsrc, npts, out, want_vec, stage);
+    else solve_small_kernel<4><<<(unsigned)blocks, 128, dyn, st>>>(pv, ks, hsrc, npts, out, want_vec, stage);
+    TBK_LAUNCH_CHECK("solve_small_kernel");
+    return TBK_OK;
+  }
+  const int nph = hsrc ? 0 : pv.nph;
+  if (n <= 32) {
+    const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
+    const int mats = 128 / G;
+    GroupShape gs = group_shape(n, nph, true);
+    const size_t dyn = gs.region * mats;
+    if (dyn > (size_t)kMaxSmem) { set_error("model needs %zu bytes of shared memory per CTA", dyn); return TBK_ERR_UNSUPPORTED; }
+    int per_sm = (int)((size_t)kMaxSmem / (dyn + 1024));
+    if (per_sm > 12) per_sm = 12;
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (npts + mats - 1) / mats;
+    if (blocks > (long long)kNumSM * per_sm) blocks = (long long)kNumSM * per_sm;
+#define TBK_TILE_LAUNCH(GG)                                                                                   \
+    do {                                                                                                      \
+      TBK_CUDA(cudaFuncSetAttribute(solve_tile_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+      solve_tile_kernel<GG><<<(unsigned)blocks, 128, dyn, st>>>(pv, ks, hsrc, npts, out, want_vec, gs);       \
+    } while (0)
+    if (G == 8) TBK_TILE_LAUNCH(8);
+    else if (G == 16) TBK_TILE_LAUNCH(16);
+    else TBK_TILE_LAUNCH(32);
+#undef TBK_TILE_LAUNCH
+    TBK_LAUNCH_CHECK("solve_tile_kernel");
+    return TBK_OK;
+  }
+  // one matrix per CTA
+  GroupShape gs = group_shape(n, nph, true);
+  bool in_smem = gs.region <= (size_t)kMaxSmem;
+  if (!in_smem) gs = group_shape(n, nph, false);
+  if (gs.region > (size_t)kMaxSmem) { set_error("nsta=%d with %d phases does not fit shared memory", n, nph); return TBK_ERR_UNSUPPORTED; }
+  const int threads = block_threads_for(n);
+  int per_sm = in_smem ? (int)((size_t)kMaxSmem / (gs.region + 1024)) : 2;
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  long long blocks = npts < (long long)kNumSM * per_sm ? npts : (long long)kNumSM * per_sm;
+  cplx* gA = nullptr;
+  if (!in_smem) {
+    const size_t need = (size_t)blocks * n * gs.lda * 16;
+    if (ws == nullptr || ws_bytes < need) { set_error("workspace too small: need %zu bytes, have %zu", need, ws_bytes); return TBK_ERR_WORKSPACE; }
+    gA = (cplx*)ws;
+  }
+  TBK_CUDA(cudaFuncSetAttribute(solve_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs.region));
+  solve_block_kernel<<<(unsigned)blocks, threads, gs.region, st>>>(pv, ks, hsrc, npts, out, want_vec, gs, gA);
+  TBK_LAUNCH_CHECK("solve_block_kernel");
+  return TBK_OK;
+}
+
+static size_t solve_ws_bytes(int n, long long npts) {
+  if (n <= 96) return 0;   // always shared-memory resident
+  long long blocks = npts < (long long)kNumSM * 2 ? npts : (long long)kNumSM * 2;
+  if (blocks < 1) blocks = 1;
+  return (size_t)blocks * n * (n | 1) * 16;
+}
+
+// n == 1 is trivial but must work (single-orbital models)
+__global__ void solve_n1_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long long npts, OutSpec out, int want_vec) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= npts) return;
+  int mi[TBK_MAX_DIM] = {0, 0, 0, 0};
+  double k[TBK_MAX_DIM];
+  double e0;
+  if (hsrc) e0 = hsrc[idx].re;
+  else {
+    if (out.mode == 1) decode_index(idx, out, mi);
+    load_k(ks, idx, mi, k);
+    cplx acc = mk(0.0, 0.0);
+    for (int e = 0; e < pv.nel; ++e) {
+      for (int t = pv.el_ptr[e]; t < pv.el_ptr[e + 1]; ++t) {
+        const cplx a = mk(pv.t_amp[2 * t], pv.t_amp[2 * t + 1]);
+        const int p = pv.t_ph[t];
+        if (p < 0) acc = acc + a;
+        else {
+          double x = 0.0;
+          for (int d = 0; d < pv.dim_k; ++d) x = fma(k[d], pv.ph_R[(p & TBK_PH_MASK) * pv.dim_k + d], x);
+          cplx z = expi_turns(x);
+          if (p & TBK_PH_CONJ) z.im = -z.im;
+          fma_acc(acc, a, z);
+        }
+      }
+    }
+    e0 = acc.re;
+  }
+  if (out.mode == 0) {
+    if (out.eval) out.eval[idx * out.ev_sk] = e0;
+    if (want_vec) out.evec[idx * out.vc_sk] = mk(1.0, 0.0);
+  } else {
+    long long base = 0;
+    int zero_mask = 0;
+    for (int d = 0; d < out.nd; ++d) {
+      base += mi[d] * out.gstride[d];
+      if (mi[d] == 0 && out.wrap[d]) zero_mask |= 1 << d;
+    }
+    out.evec[base] = mk(1.0, 0.0);
+    for (int m = 1; m < (1 << out.nd); ++m) {
+      if ((m & zero_mask) != m) continue;
+      long long off = base;
+      cplx f = mk(1.0, 0.0);
+      for (int d = 0; d < out.nd; ++d)
+        if (m & (1 << d)) { off += (long long)(out.full[d] - 1) * out.gstride[d]; f = f * out.pbc_phase[d]; }
+      out.evec[off] = f;
+    }
+  }
+}
+
+}  // namespace tbk
+
+using namespace tbk;
+
+extern "C" {
+
+int tbk_gen_ham(const tbk_model* m, const double* k_dev, int64_t nk, double* ham_dev, void* stream) {
+  if (!m || !ham_dev || nk < 0 || (m->pv.dim_k > 0 && !k_dev)) { set_error("tbk_gen_ham: bad argument"); return TBK_ERR_ARG; }
+  if (nk == 0) return TBK_OK;
+  const size_t dyn = (size_t)((m->pv.nph > 0 ? m->pv.nph : 1) + m->pv.nsta) * 16;
+  if (dyn > (size_t)kMaxSmem) { set_error("tbk_gen_ham: phase table too large"); return TBK_ERR_UNSUPPORTED; }
+  TBK_CUDA(cudaFuncSetAttribute(gen_ham_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  const long long blocks = nk < (long long)kNumSM * 8 ? nk : (long long)kNumSM * 8;
+  gen_ham_kernel<<<(unsigned)blocks, 128, dyn, (cudaStream_t)stream>>>(m->pv, k_dev, nk, (cplx*)ham_dev);
+  TBK_LAUNCH_CHECK("gen_ham_kernel");
+  return TBK_OK;
+}
+
+size_t tbk_eigh_workspace(int32_t n, int64_t batch, int32_t) { return solve_ws_bytes(n, batch); }
+
+int tbk_eigh_batched(const double* ham_dev, int32_t n, int64_t batch, double* eval_dev, double* evec_dev,
+                     void* ws_dev, size_t ws_bytes, void* stream) {
+  if (!ham_dev || !eval_dev || n < 1 || batch < 0) { set_error("tbk_eigh_batched: bad argument"); return TBK_ERR_ARG; }
+  PlanView pv;
+  memset(&pv, 0, sizeof(pv));
+  pv.nsta = n; pv.convention = 2;
+  KSrc ks;
+  memset(&ks, 0, sizeof(ks));
+  OutSpec out;
+  memset(&out, 0, sizeof(out));
+  out.mode = 0;
+  out.eval = eval_dev; out.ev_sb = 1; out.ev_sk = n;
+  out.evec = (cplx*)evec_dev; out.vc_sb = n; out.vc_sk = (long long)n * n;
+  const int want_vec = evec_dev != nullptr;
+  if (n == 1) {
+    solve_n1_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(pv, ks, (const cplx*)ham_dev, batch, out, want_vec);
+    TBK_LAUNCH_CHECK("solve_n1_kernel");
+    return TBK_OK;
+  }
+  return launch_solve(pv, ks, (const cplx*)ham_dev, n, batch, out, want_vec, ws_dev, ws_bytes, (cudaStream_t)stream);
+}
+
+size_t tbk_solve_workspace(int32_t nsta, int64_t nk, int32_t) { return solve_ws_bytes(nsta, nk); }
+
+int tbk_solve_k(const tbk_model* m, const double* k_dev, int64_t nk, double* eval_dev, int64_t ev_sb, int64_t ev_sk,
+                double* evec_dev, int64_t vc_sb, int64_t vc_sk, void* ws_dev, size_t ws_bytes, void* stream) {
+  if (!m || nk < 0 || (!eval_dev && !evec_dev) || (m->pv.dim_k > 0 && !k_dev)) { set_error("tbk_solve_k: bad argument"); return TBK_ERR_ARG; }
+  KSrc ks;
+  memset(&ks, 0, sizeof(ks));
+  ks.klist = k_dev; ks.dim_k = m->pv.dim_k;
+  OutSpec out;
+  memset(&out, 0, sizeof(out));
+  out.mode = 0;
+  out.eval = eval_dev; out.ev_sb = ev_sb; out.ev_sk = ev_sk;
+  out.evec = (cplx*)evec_dev; out.vc_sb = vc_sb; out.vc_sk = vc_sk;
+  const int want_vec = evec_dev != nullptr;
+  if (m->pv.nsta == 1) {
+    solve_n1_kernel<<<(unsigned)((nk + 127) / 128), 128, 0, (cudaStream_t)stream>>>(m->pv, ks, nullptr, nk, out, want_vec);
+    TBK_LAUNCH_CHECK("solve_n1_kernel");
+    return TBK_OK;
+  }
+  return launch_solve(m->pv, ks, nullptr, m->pv.nsta, nk, out, want_vec, ws_dev, ws_bytes, (cudaStream_t)stream);
+}
+
+int tbk_solve_grid(const tbk_model* m, const double* start_k, const int32_t* mesh, int32_t nd, int32_t row0,
+                   int32_t nrows, int32_t wrap0, double* wfs_dev, const double* pbc_phase_dev, double* gaps_dev,
+                   void* ws_dev, size_t ws_bytes, void* stream) {
+  if (!m || !start_k || !mesh || !wfs_dev || !pbc_phase_dev || nd < 1 || nd > TBK_MAX_DIM || nd != m->pv.dim_k ||
+      nrows < 0 || row0 < 0) {
+    set_error("tbk_solve_grid: bad argument (nd=%d dim_k=%d)", nd, m ? m->pv.dim_k : -1);
+    return TBK_ERR_ARG;
+  }
+  const int n = m->pv.nsta;
+  KSrc ks;
+  memset(&ks, 0, sizeof(ks));
+  ks.klist = nullptr; ks.dim_k = nd; ks.row0 = row0;
+  OutSpec out;
+  memset(&out, 0, sizeof(out));
+  out.mode = 1; out.nd = nd;
+  out.evec = (cplx*)wfs_dev;
+  out.pbc_phase = (const cplx*)pbc_phase_dev;
+  long long npts = 1;
+  for (int d = 0; d < nd; ++d) {
+    if (mesh[d] < 2) { set_error("tbk_solve_grid: mesh extent must be >= 2"); return TBK_ERR_ARG; }
+    ks.start[d] = start_k[d];
+    ks.den[d] = (double)(mesh[d] - 1);
+    out.cnt[d] = d == 0 ? nrows : mesh[d] - 1;
+    out.full[d] = d == 0 ? nrows + 1 : mesh[d];
+    out.wrap[d] = d == 0 ? (wrap0 != 0) : 1;
+    npts *= out.cnt[d];
+  }
+  long long stride = (long long)n * n;
+  for (int d = nd - 1; d >= 0; --d) { out.gstride[d] = stride; stride *= out.full[d]; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gaps_dev && n > 1) {
+    out.gaps_bits = (unsigned long long*)gaps_dev;
+    fill_u64_kernel<<<(n - 1 + 127) / 128, 128, 0, st>>>(out.gaps_bits, n - 1, 0x7FF0000000000000ULL);
+    TBK_LAUNCH_CHECK("fill_u64_kernel");
+  }
+  if (n == 1) {
+    if (npts > 0) solve_n1_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(m->pv, ks, nullptr, npts, out, 1);
+    TBK_LAUNCH_CHECK("solve_n1_kernel");
+    return TBK_OK;
+  }
+  return launch_solve(m->pv, ks, nullptr, n, npts, out, 1, ws_dev, ws_bytes, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,291 @@
+"""``wf_array`` with the PythTB 1.8.0 interface (/root/reference/pythtb.py:2283-3205)
+on top of the B200 engine.
+
+Wavefunctions live on the GPU; the reference's host array ``_wfs`` is a lazily
+synchronised mirror (``DeviceStore``), so ``solve_on_grid`` followed by
+``berry_phase``/``berry_flux`` never moves eigenvectors over PCIe, while manual
+fills (``wf[i,j]=evec``) and direct ``_wfs`` access keep working.
+
+Only the sequential 2*pi continuity post-processing (pythtb.py:3036-3065,
+3867-3921) runs on the host, with the reference's algorithm.
+"""
+import copy
+
+import numpy as np
+
+from .model import _is_int, _offdiag_approximation_warning_and_stop
+
+__all__ = ["wf_array"]
+
+
+# ---------------------------------------------------------------------------
+# branch-cut post-processing (host, O(strings * nocc^2))
+# ---------------------------------------------------------------------------
+def no_2pi(x, clos):
+    """Shift x by multiples of 2 pi until it is within pi of clos (pythtb.py:3867-3874)."""
+    while abs(clos - x) > np.pi:
+        if clos - x > np.pi:
+            x += 2.0 * np.pi
+        elif clos - x < -1.0 * np.pi:
+            x -= 2.0 * np.pi
+    return x
+
+
+def _one_phase_cont(pha, clos):
+    """Unwrap a 1-D sequence of phases, the first one relative to clos (pythtb.py:3876-3888)."""
+    ret = np.copy(pha)
+    prev = clos
+    for i in range(len(ret)):
+        ret[i] = no_2pi(ret[i], prev)
+        prev = ret[i]
+    return ret
+
+
+def _array_phases_cont(arr_pha, clos):
+    """Greedy nearest-neighbour matching of sets of phases between consecutive
+    strings, then unwrapping (pythtb.py:3890-3921; ``<=`` tie-break kept)."""
+    ret = np.zeros_like(arr_pha)
+    for i in range(arr_pha.shape[0]):
+        cmpr = clos if i == 0 else ret[i - 1, :]
+        avail = list(range(arr_pha.shape[1]))
+        for j in range(cmpr.shape[0]):
+            best_k, min_dist = None, 1.0e10
+            for k in avail:
+                cur = np.abs(np.exp(1.0j * cmpr[j]) - np.exp(1.0j * arr_pha[i, k]))
+                if cur <= min_dist:
+                    min_dist, best_k = cur, k
+            avail.remove(best_k)
+            ret[i, j] = no_2pi(arr_pha[i, best_k], cmpr[j])
+    return ret
+
+
+class wf_array(object):
+    """``wf_array(model, mesh_arr, nsta_arr=None)`` (pythtb.py:2388-2419)."""
+
+    def __init__(self, model, mesh_arr, nsta_arr=None):
+        if nsta_arr is None:
+            self._nsta_arr = model._nsta
+        else:
+            if not _is_int(nsta_arr):
+                raise Exception("\n\nArgument nsta_arr not an integer")
+            self._nsta_arr = nsta_arr
+        self._nspin = model._nspin
+        self._norb = model._norb
+        self._orb = np.copy(model._orb)
+        self._model = copy.deepcopy(model)
+        self._mesh_arr = np.array(mesh_arr)
+        self._dim_arr = len(self._mesh_arr)
+        if True in (self._mesh_arr <= 1).tolist():
+            raise Exception("\n\nDimension of wf_array object in each direction must be 2 or larger.")
+        self._store = self._model._engine().new_store(self._wfs_shape(self._nsta_arr))
+
+    def _wfs_shape(self, nsta):
+        shape = [int(m) for m in self._mesh_arr] + [int(nsta), int(self._norb)]
+        if self._nspin == 2:
+            shape.append(2)
+        return tuple(shape)
+
+    def __deepcopy__(self, memo):
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k == "_store":
+                continue
+            setattr(new, k, copy.deepcopy(v, memo))
+        new._store = self._model._engine().new_store(self._store.shape)
+        if self._store.state != "empty":
+            new._store.replace_host(np.array(self._store.host(), copy=True))
+        return new
+
+    # the reference's host array (pythtb.py:2419); handing it out makes it authoritative
+    @property
+    def _wfs(self):
+        return self._store.host()
+
+    @_wfs.setter
+    def _wfs(self, value):
+        self._store.replace_host(value)
+
+    # ------------------------------------------------------------ grid solves
+    def solve_on_grid(self, start_k):
+        """pythtb.py:2421-2532: solve on k = start_k + i/(N-1), i < N-1, impose
+        the periodic images on every axis, return the minimal direct gaps.
+        One fused kernel launch for the whole mesh."""
+        if self._dim_arr != self._model._dim_k:
+            raise Exception("\n\nIf using solve_on_grid method, dimension of wf_array must equal"
+                            "\ndim_k of the tight-binding model!")
+        if self._nsta_arr != self._model._nsta:
+            raise Exception("\n\nWhen initializing this object, you specified nsta_arr to be " + str(self._nsta_arr) +
+                            ", but\nthis does not match the total number of bands specified in the model,"
+                            "\nwhich was " + str(self._model._nsta) + ".  If you wish to use the solve_on_grid method, do"
+                            "\nnot specify the nsta_arr parameter when initializing this object.\n\n")
+        if self._dim_arr < 1 or self._dim_arr > 4:
+            raise Exception("\n\nWrong dimensionality!")
+        start = np.array(start_k, dtype=float).reshape(-1)
+        if start.shape[0] != self._dim_arr:
+            raise Exception("\n\nk-vector of wrong shape!")
+        self._start_k = start_k
+        eng = self._model._engine()
+        gaps = eng.solve_grid(self._model, self._store, self._mesh_arr, start)
+        if self._nsta_arr <= 1:
+            return None
+        return self._gaps_to_host(gaps)
+
+    @staticmethod
+    def _gaps_to_host(gaps):
+        return gaps if isinstance(gaps, np.ndarray) else gaps.cpu().numpy()
+
+    def solve_on_one_point(self, kpt, mesh_indices):
+        """pythtb.py:2534-2566."""
+        (_, evec) = self._model.solve_one(kpt, eig_vectors=True)
+        key = (mesh_indices,) if _is_int(mesh_indices) else tuple(mesh_indices)
+        self._wfs[key] = evec
+
+    def choose_states(self, subset):
+        """pythtb.py:2568-2607."""
+        subset = np.array(subset, dtype=int)
+        if subset.ndim != 1:
+            raise Exception("\n\nParameter subset must be a one-dimensional array.")
+        if self._dim_arr > 4:
+            raise Exception("\n\n_dim_array too large.")
+        new = copy.deepcopy(self)
+        new._nsta_arr = subset.shape[0]
+        sel = (slice(None),) * self._dim_arr + (subset,)
+        new._wfs = self._wfs[sel]
+        return new
+
+    def empty_like(self, nsta_arr=None):
+        """pythtb.py:2609-2642 (contents are unspecified, like np.empty_like)."""
+        new = copy.deepcopy(self)
+        if nsta_arr is not None:
+            new._nsta_arr = nsta_arr
+            new._store = self._model._engine().new_store(self._wfs_shape(nsta_arr))
+        return new
+
+    # -------------------------------------------------------------- indexing
+    def _check_key(self, key):
+        if self._dim_arr == 1:
+            if not _is_int(key):
+                raise TypeError("Key should be an integer!")
+            if key < (-1) * self._mesh_arr[0] or key >= self._mesh_arr[0]:
+                raise IndexError("Key outside the range!")
+        else:
+            if len(key) != self._dim_arr:
+                raise TypeError("Wrong dimensionality of key!")
+            for i, k in enumerate(key):
+                if not _is_int(k):
+                    raise TypeError("Key should be set of integers!")
+                if k < (-1) * self._mesh_arr[i] or k >= self._mesh_arr[i]:
+                    raise IndexError("Key outside the range!")
+
+    def __getitem__(self, key):
+        self._check_key(key)
+        return self._wfs[key if self._dim_arr == 1 else tuple(key)]
+
+    def __setitem__(self, key, value):
+        self._check_key(key)
+        self._wfs[key if self._dim_arr == 1 else tuple(key)] = np.array(value, dtype=complex)
+
+    # --------------------------------------------------- boundary conditions
+    def impose_pbc(self, mesh_dir, k_dir):
+        """pythtb.py:2674-2749: last slice := first slice * exp(-2 pi i tau_j[k_dir])."""
+        if k_dir not in self._model._per:
+            raise Exception("Periodic boundary condition can be specified only along periodic directions!")
+        if mesh_dir < 0 or mesh_dir >= self._dim_arr or mesh_dir > 3:
+            raise Exception("\n\nWrong value of mesh_dir.")
+        eng = self._model._engine()
+        phase = eng.pbc_phases(self._orb, self._nspin, [k_dir])[0]
+        eng.impose_boundary(self._store, self._dim_arr, mesh_dir, phase)
+
+    def impose_loop(self, mesh_dir):
+        """pythtb.py:2751-2791: last slice := first slice."""
+        if mesh_dir < 0 or mesh_dir >= self._dim_arr or mesh_dir > 3:
+            raise Exception("\n\nWrong value of mesh_dir.")
+        self._model._engine().impose_boundary(self._store, self._dim_arr, mesh_dir, None)
+
+    # ----------------------------------------------------- position operator
+    def _occ(self, occ, allow_none=True):
+        if (isinstance(occ, str) and occ == "All") or (allow_none and occ is None):
+            return np.arange(self._nsta_arr, dtype=int)
+        occ = np.array(occ, dtype=int)
+        if occ.ndim != 1:
+            raise Exception("\n\nParameter occ must be a one-dimensional array or string \"All\" or None.")
+        return occ
+
+    def _evec_at(self, key, occ):
+        occ = self._occ(occ, allow_none=False)
+        if self._model._assume_position_operator_diagonal == False:  # noqa: E712
+            _offdiag_approximation_warning_and_stop()
+        return self._wfs[tuple(key)][occ]
+
+    def position_matrix(self, key, occ, dir):
+        """pythtb.py:2793-2813."""
+        return self._model.position_matrix(self._evec_at(key, occ), dir)
+
+    def position_expectation(self, key, occ, dir):
+        """pythtb.py:2815-2835."""
+        return self._model.position_expectation(self._evec_at(key, occ), dir)
+
+    def position_hwf(self, key, occ, dir, hwf_evec=False, basis="wavefunction"):
+        """pythtb.py:2837-2861."""
+        return self._model.position_hwf(self._evec_at(key, occ), dir, hwf_evec, basis)
+
+    # ------------------------------------------------------------ Berry phase
+    def berry_phase(self, occ="All", dir=None, contin=True, berry_evals=False):
+        """pythtb.py:2863-3066.  Overlaps, determinants / polar factors, ordered
+        products and the unitary eigenvalues run on the GPU for all strings at
+        once; the 2 pi continuity pass stays on the host."""
+        occ = self._occ(occ)
+        if self._model._assume_position_operator_diagonal == False:  # noqa: E712
+            _offdiag_approximation_warning_and_stop()
+        if self._dim_arr == 1:
+            dir_use = 0
+        elif self._dim_arr in (2, 3):
+            if dir is None or not (0 <= dir < self._dim_arr):
+                raise Exception("\n\nWrong direction for Berry phase calculation!")
+            dir_use = dir
+        else:
+            raise Exception("\n\nWrong dimensionality!")
+        eng = self._model._engine()
+        ret = eng.berry_strings(self._store, self._dim_arr, occ, dir_use, berry_evals)
+        if self._dim_arr == 1 and not berry_evals:
+            ret = float(np.asarray(ret).reshape(-1)[0])
+        else:
+            ret = np.array(ret, dtype=float)
+        if contin:
+            if not berry_evals:
+                if self._dim_arr == 2:
+                    ret = _one_phase_cont(ret, ret[0])
+                elif self._dim_arr == 3:
+                    for i in range(ret.shape[1]):
+                        clos = ret[0, 0] if i == 0 else ret[0, i - 1]
+                        ret[:, i] = _one_phase_cont(ret[:, i], clos)
+            else:
+                if self._dim_arr == 2:
+                    ret = _array_phases_cont(ret, ret[0, :])
+                elif self._dim_arr == 3:
+                    for i in range(ret.shape[1]):
+                        clos = ret[0, 0, :] if i == 0 else ret[0, i - 1, :]
+                        ret[:, i] = _array_phases_cont(ret[:, i], clos)
+        return ret
+
+    # ------------------------------------------------------------- Berry flux
+    def berry_flux(self, occ="All", dirs=None, individual_phases=False):
+        """pythtb.py:3068-3205: plaquette phases / integrated Berry curvature on
+        every 2-D slice spanned by ``dirs``; one fused launch for all plaquettes."""
+        occ = self._occ(occ)
+        if self._model._assume_position_operator_diagonal == False:  # noqa: E712
+            _offdiag_approximation_warning_and_stop()
+        if dirs is None:
+            dirs = [0, 1]
+        if dirs[0] == dirs[1]:
+            raise Exception("Need to specify two different directions for Berry flux calculation.")
+        if dirs[0] >= self._dim_arr or dirs[1] >= self._dim_arr or dirs[0] < 0 or dirs[1] < 0:
+            raise Exception("Direction for Berry flux calculation out of bounds.")
+        if self._dim_arr not in (2, 3, 4):
+            raise Exception("\n\nWrong dimensionality!")
+        eng = self._model._engine()
+        res = eng.flux(self._store, self._dim_arr, occ, [int(dirs[0]), int(dirs[1])], individual_phases)
+        if self._dim_arr == 2 and not individual_phases:
+            return np.float64(res.reshape(-1)[0])
+        return res

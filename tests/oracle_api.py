@@ -1,0 +1,94 @@
+"""TEST INFRASTRUCTURE: the PythTB public API served by the numpy oracle.
+
+``tests/cases.py`` drives ``mod.tb_model`` / ``mod.wf_array``.  This module is
+such a ``mod`` whose numerical seams are answered by ``oracle/pythtb_oracle.py``
+instead of the CUDA engine, so the oracle can be checked against the golden
+fixtures on a CPU-only box through exactly the host logic (model building,
+plan-independent bookkeeping, continuity post-processing) that the product
+uses.  The product package never imports this file or the oracle.
+"""
+import numpy as np
+
+from oracle import pythtb_oracle as orc
+from pythtb_b200 import model as _model
+from pythtb_b200 import wfarray as _wfarray
+
+
+class _HostStore(object):
+    def __init__(self, shape):
+        self.shape = tuple(int(x) for x in shape)
+        self.arr = np.zeros(self.shape, dtype=complex)
+        self.state = "host"
+
+    def host(self):
+        return self.arr
+
+    def replace_host(self, arr):
+        self.arr = np.array(arr, dtype=complex)
+        self.shape = self.arr.shape
+
+
+class OracleEngine(object):
+    """Same method set as pythtb_b200._engine.B200Engine, numpy arithmetic."""
+
+    def new_store(self, shape):
+        return _HostStore(shape)
+
+    def gen_ham(self, model, klist):
+        return orc.gen_ham(model, klist if model._dim_k > 0 else None)
+
+    def eigh(self, ham, eig_vectors):
+        if not eig_vectors:
+            return orc.sol_ham(ham, False), None
+        return orc.sol_ham(ham, True)
+
+    def solve_all(self, model, klist, eig_vectors):
+        if model._dim_k == 0:
+            res = orc.solve_all(model, None, eig_vectors)
+            if not eig_vectors:
+                return res[:, None]
+            return res[0][:, None], res[1][:, None]
+        return orc.solve_all(model, klist, eig_vectors)
+
+    def pbc_phases(self, orb, nspin, k_dirs):
+        return np.array([np.repeat(np.exp(-2.0j * np.pi * np.asarray(orb)[:, kd]), nspin) for kd in k_dirs])
+
+    def solve_grid(self, model, store, mesh_arr, start_k, row0=0, nrows=None, wrap0=True):
+        wfs, gaps = orc.solve_on_grid(model, mesh_arr, start_k)
+        store.arr[...] = wfs
+        return gaps
+
+    def impose_boundary(self, store, dim_arr, mesh_dir, phase):
+        if phase is None:
+            orc.impose_loop(store.arr, mesh_dir)
+        else:
+            tail = store.arr.shape[dim_arr + 1:]
+            idx_last = [slice(None)] * mesh_dir + [-1]
+            idx_first = [slice(None)] * mesh_dir + [0]
+            store.arr[tuple(idx_last)] = store.arr[tuple(idx_first)] * phase.reshape(tail)
+
+    def berry_strings(self, store, dim_arr, occ, dir, berry_evals):
+        return np.asarray(orc.berry_phase(store.arr, dim_arr, occ, dir, contin=False, berry_evals=berry_evals))
+
+    def flux(self, store, dim_arr, occ, dirs, individual):
+        return np.asarray(orc.berry_flux(store.arr, dim_arr, occ, dirs, individual_phases=individual))
+
+    def position_matrix(self, model, evec, dir):
+        return np.array([orc.position_matrix(model, e, dir) for e in evec])
+
+    def position_hwf(self, model, evec, dir, hwf_evec, orbital_basis):
+        if not hwf_evec:
+            return np.array([orc.position_hwf(model, e, dir) for e in evec]), None
+        res = [orc.position_hwf(model, e, dir, True, "orbital" if orbital_basis else "bloch") for e in evec]
+        return np.array([r[0] for r in res]), np.array([np.asarray(r[1]).reshape(r[1].shape[0], -1) for r in res])
+
+
+_ENGINE = OracleEngine()
+
+
+class tb_model(_model.tb_model):
+    _engine_factory = staticmethod(lambda: _ENGINE)
+
+
+class wf_array(_wfarray.wf_array):
+    pass

@@ -1,0 +1,70 @@
+"""CPU checks of the drop-in boundary: libtbk_b200.so loads and exports every
+symbol include/tbk.h declares; the product fails loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "tbk.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(tbk_[a-z0-9_]+)\s*\(", txt)))
+
+
+def _lib_path():
+    from pythtb_b200 import build
+    return build.build()
+
+
+def test_library_exports_header_symbols():
+    lib = ctypes.CDLL(_lib_path())
+    syms = _header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib, s), "libtbk_b200.so does not export " + s
+
+
+def test_binding_table_matches_header():
+    from pythtb_b200 import _lib
+    assert sorted(_lib.SYMBOLS) == _header_symbols()
+    lib = _lib.load()
+    assert lib.tbk_version() >= 100
+    assert lib.tbk_last_error() is not None
+
+
+def test_host_argument_validation_without_gpu():
+    """Entry points reject bad arguments before touching the device."""
+    from pythtb_b200 import _lib
+    lib = _lib.load()
+    out = ctypes.c_void_p(0)
+    assert lib.tbk_model_create(None, ctypes.byref(out)) == -1
+    assert b"null" in lib.tbk_last_error()
+    assert lib.tbk_gen_ham(None, None, 1, None, None) == -1
+    assert lib.tbk_model_destroy(None) == 0
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import pythtb_b200
+    from tests import models as M
+    m = M.haldane(pythtb_b200)            # model building is host-only and works
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        m.solve_all([[0.0, 0.0]])
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        pythtb_b200.wf_array(m, [5, 5])
+
+
+def test_no_oracle_in_product():
+    """The product package must never import the oracle or the host emulation."""
+    pkg = os.path.join(ROOT, "pythtb_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "hostemu" not in txt.replace("tests/hostemu", ""), f

@@ -1,0 +1,173 @@
+"""GPU parity tests (run on the B200 with ``-m gpu``): every case of
+tests/cases.py through the product path (pythtb_b200 -> ctypes C-ABI ->
+sm_100a kernels) against the fixtures produced by the unmodified reference,
+plus oracle comparisons on seeded inputs and size-independent properties at
+the BASELINE.json sizes."""
+import io
+import os
+import contextlib
+
+import numpy as np
+import pytest
+
+from tests import cases, compare, models as M
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _mod():
+    import pythtb_b200
+    return pythtb_b200
+
+
+@pytest.mark.parametrize("name", sorted(cases.ALL_CASES))
+def test_case_matches_reference(name):
+    want = np.load(os.path.join(GOLD, name + ".npz"))
+    with contextlib.redirect_stdout(io.StringIO()):
+        got = cases.ALL_CASES[name](_mod())
+    bad = compare.compare_case(name, got, want)
+    assert not bad, "\n".join(bad)
+
+
+def test_native_library_is_loaded():
+    """The tests above must have gone through libtbk_b200.so."""
+    mod = _mod()
+    M.haldane(mod).solve_all([[0.1, 0.2]])
+    with open("/proc/self/maps") as f:
+        assert "libtbk_b200.so" in f.read()
+
+
+def _residual(model, k, ev, evec):
+    from oracle import pythtb_oracle as orc
+    ham = orc.gen_ham(model, k)
+    worst = 0.0
+    for i in range(len(k)):
+        v = evec[:, i].reshape(model._nsta, -1)
+        worst = max(worst, np.max(np.abs(ham[i] @ v.T - v.T * ev[:, i][None, :])))
+        worst = max(worst, np.max(np.abs(v.conj() @ v.T - np.eye(model._nsta))))
+    return worst
+
+
+@pytest.mark.parametrize("spec", [
+    dict(norb=2, dim=2, nhop=5, nspin=1, seed=21), dict(norb=3, dim=1, nhop=5, nspin=1, seed=22),
+    dict(norb=4, dim=2, nhop=9, nspin=1, seed=23), dict(norb=2, dim=3, nhop=8, nspin=2, seed=24),
+    dict(norb=7, dim=2, nhop=20, nspin=1, seed=25), dict(norb=6, dim=1, nhop=14, nspin=2, seed=26),
+    dict(norb=24, dim=2, nhop=70, nspin=1, seed=27), dict(norb=33, dim=1, nhop=90, nspin=1, seed=28),
+    dict(norb=60, dim=2, nhop=200, nspin=1, seed=29), dict(norb=120, dim=1, nhop=400, nspin=1, seed=30),
+])
+def test_random_models_against_oracle(spec):
+    """Every eigensolver family (registers / tile / CTA-smem / CTA-workspace)."""
+    from oracle import pythtb_oracle as orc
+    mod = _mod()
+    m = M.random_model(mod, **spec)
+    k = np.random.RandomState(spec["seed"]).rand(37, spec["dim"]) * 2 - 1
+    ev_ref = orc.solve_all(m, k)
+    ev = m.solve_all(k)
+    scale = max(1.0, np.max(np.abs(ev_ref)))
+    assert np.max(np.abs(ev - ev_ref)) <= compare.TOL_EVAL * scale
+    ev2, evec = m.solve_all(k, eig_vectors=True)
+    assert np.max(np.abs(ev2 - ev_ref)) <= compare.TOL_EVAL * scale
+    assert _residual(m, k, ev2, evec) <= 1e-11 * scale
+    ham = np.array([np.asarray(m._gen_ham(kk)).reshape(m._nsta, m._nsta) for kk in k[:3]])
+    assert np.max(np.abs(ham - orc.gen_ham(m, k[:3]))) <= compare.TOL_HAM * scale
+
+
+def test_large_ribbon_and_slab_eigenvalues():
+    """Configs 4/5 sizes on a few k-points: norb 200 ribbon, norb 499 slab."""
+    from oracle import pythtb_oracle as orc
+    mod = _mod()
+    rib = M.bn_ribbon(mod, 100)
+    k = [[0.0], [0.123], [0.5]]
+    assert np.max(np.abs(rib.solve_all(k) - orc.solve_all(rib, k))) <= 1e-10 * 4
+    ev, evec = rib.solve_all(k, eig_vectors=True)
+    assert _residual(rib, np.array(k), ev, evec) <= 1e-10
+    slab = M.cubic_slab(mod, 250)
+    k2 = [[0.1, 0.2], [0.0, 0.5]]
+    assert np.max(np.abs(slab.solve_all(k2) - orc.solve_all(slab, k2))) <= 1e-10 * 4
+
+
+def test_chern_number_full_mesh():
+    """BASELINE config 2 at full size: 1024x1024 Haldane mesh, Chern integer exact,
+    total flux equal to the sum of the plaquette phases, gaps match a subsample."""
+    mod = _mod()
+    m = M.haldane(mod, delta=0.0)
+    w = mod.wf_array(m, [1025, 1025])
+    gaps = w.solve_on_grid([-0.5, -0.5])
+    flux = w.berry_flux([0])
+    chern = flux / (2 * np.pi)
+    assert abs(chern - round(chern)) < 1e-9 and abs(round(chern)) == 1
+    plaq = w.berry_flux([0], individual_phases=True)
+    assert plaq.shape == (1024, 1024)
+    assert abs(plaq.sum() - flux) < 1e-8
+    flux1 = w.berry_flux([1])
+    assert abs(flux + flux1) < 1e-8            # the two bands carry opposite Chern numbers
+    assert gaps.shape == (1,) and 0.5 < gaps[0] < 2.0
+    # periodic images: last row/column equal the first up to the pbc phase
+    wfs = w._wfs
+    ph = np.exp(-2j * np.pi * m._orb[:, 0])
+    assert np.max(np.abs(wfs[-1, 5] - wfs[0, 5] * ph)) < 1e-14
+    # Kane-Mele: Z2-odd phase has zero total Chern number for the occupied pair
+    km = M.kane_mele(mod, "odd")
+    wk = mod.wf_array(km, [257, 257])
+    wk.solve_on_grid([-0.5, -0.5])
+    assert abs(wk.berry_flux([0, 1])) < 1e-7
+
+
+def test_solve_on_grid_subsample_vs_oracle():
+    """129x129 Haldane / Kane-Mele grids against the oracle (gauge-invariant)."""
+    from oracle import pythtb_oracle as orc
+    mod = _mod()
+    for m, occ in ((M.haldane(mod, 0.0), [0]), (M.kane_mele(mod, "even"), [0, 1])):
+        w = mod.wf_array(m, [129, 129])
+        gaps = w.solve_on_grid([-0.5, -0.5])
+        wfs_ref, gaps_ref = orc.solve_on_grid(m, [129, 129], [-0.5, -0.5])
+        assert np.max(np.abs(gaps - gaps_ref)) < 1e-10
+        ref_plaq = orc.berry_flux(wfs_ref, 2, occ, None, True)
+        got_plaq = w.berry_flux(occ, individual_phases=True)
+        assert np.max(np.abs(compare.circ_diff(got_plaq, ref_plaq, 2 * np.pi))) < 1e-8
+        ref_ph = orc.berry_phase(wfs_ref, 2, occ, 1, contin=False)
+        got_ph = w.berry_phase(occ, 1, contin=False)
+        assert np.max(np.abs(compare.circ_diff(got_ph, ref_ph, 2 * np.pi))) < 1e-8
+
+
+def test_w90_silicon_fixture():
+    """Config 3 in miniature: the silicon Wannier90 model (arrays from the
+    reference's parse) on the fixture k-points."""
+    mod = _mod()
+    z = np.load(os.path.join(GOLD, "w90.npz"))
+    for tag in ("full", "small"):
+        pre = "silicon_%s_" % tag
+        m = mod.tb_model(3, 3, z[pre + "lat"], z[pre + "orb"])
+        m.set_onsite(z[pre + "site_energies"].real)
+        m._bulk_set_hops(z[pre + "hop_amp"], z[pre + "hop_i"], z[pre + "hop_j"], z[pre + "hop_R"])
+        ev = m.solve_all(z["silicon_k"])
+        want = z["silicon_%s_evals" % tag]
+        assert np.max(np.abs(ev - want)) <= 1e-10 * max(1.0, np.max(np.abs(want)))
+    # Wannier90's own interpolation (text precision of silicon_band.dat)
+    full = mod.tb_model(3, 3, z["silicon_full_lat"], z["silicon_full_orb"])
+    full.set_onsite(z["silicon_full_site_energies"].real)
+    full._bulk_set_hops(z["silicon_full_hop_amp"], z["silicon_full_hop_i"], z["silicon_full_hop_j"], z["silicon_full_hop_R"])
+    assert np.max(np.abs(full.solve_all(z["silicon_band_kpts"]) - z["silicon_band_ene"])) < 1e-4
+
+
+def test_edge_cases():
+    mod = _mod()
+    one = mod.tb_model(1, 1, [[1.0]], [[0.0]])                       # single orbital
+    one.set_onsite([0.3])
+    one.set_hop(-1.0, 0, 0, [1])
+    k = np.linspace(0, 1, 7)[:, None]
+    assert np.allclose(one.solve_all(k)[0], 0.3 - 2 * np.cos(2 * np.pi * k[:, 0]), atol=1e-13)
+    ev, evec = one.solve_all(k, eig_vectors=True)
+    assert evec.shape == (1, 7, 1) and np.allclose(np.abs(evec), 1.0)
+    w = mod.wf_array(one, [8])
+    assert w.solve_on_grid([0.0]) is None
+    assert abs(w.berry_phase([0])) < 1e-12 or abs(abs(w.berry_phase([0])) - 2 * np.pi) < 1e-12
+    mol = M.molecule(mod)                                            # 0-D: no k argument
+    assert mol.solve_all().shape == (3,)
+    with pytest.raises(Exception):
+        M.haldane(mod).solve_all([[0.1, 0.2, 0.3]])                  # wrong k shape
+    with pytest.raises(Exception):
+        mod.wf_array(M.haldane(mod), [5]).solve_on_grid([0.0])       # dim mismatch
+    empty = M.haldane(mod).solve_all(np.zeros((0, 2)))               # empty k list
+    assert empty.shape == (2, 0)
