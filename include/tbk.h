@@ -119,9 +119,15 @@ int tbk_solve_k(const tbk_model* model, const double* k_dev, int64_t nk,
  *     wfs_dev[local_row][i_1]..[i_{nd-1}][state][orb(,spin)]
  * whose axis-0 extent is nrows+1 (the extra row is the periodic image / halo
  * of the next shard) and whose other extents are mesh[d].  Periodic images
- * along axes d >= 1 are always written (x pbc_phase); the image along axis 0
- * is written only when wrap0 != 0 (single shard: row0 == 0 and
- * nrows == mesh[0]-1).
+ * along axes d >= 1 are always written (x pbc_phase).  The closing row of
+ * axis 0 depends on wrap0:
+ *   1  single shard (row0 == 0, nrows == mesh[0]-1): the image of row 0 is written;
+ *   0  left untouched — the caller fills it with the next shard's first row
+ *      (tbk_halo_pack + an NCCL ring shift);
+ *   2  solved in this launch as global row row0+nrows (the periodic image
+ *      row 0 x pbc_phase when that index is mesh[0]-1): no communication, the
+ *      values are bit-identical to the neighbour's first row.
+ * ws_dev / ws_bytes: tbk_solve_workspace(nsta, npts, 1).
  *   pbc_phase_dev [nd][nsta] complex128 = exp(-2 pi i tau_j[per[d]])  (:2729)
  *   gaps_dev [nsta-1] minimal direct gaps over the solved rows (:2484,:2529);
  *            may be NULL.
@@ -130,6 +136,13 @@ int tbk_solve_grid(const tbk_model* model, const double* start_k_host, const int
                    int32_t nd, int32_t row0, int32_t nrows, int32_t wrap0,
                    double* wfs_dev, const double* pbc_phase_dev, double* gaps_dev,
                    void* ws_dev, size_t ws_bytes, void* stream);
+
+/* Multi-GPU: pack the first local row of a shard ([npoints][nsta_arr][n]
+ * complex128) into a contiguous send buffer for the ring shift that closes the
+ * neighbour's slab; phase_dev [n] (the pbc phase of pythtb.py:2729, applied by
+ * rank 0 whose row becomes the last rank's periodic image) or NULL. */
+int tbk_halo_pack(const double* row_dev, double* dst_dev, int64_t npoints, int32_t nsta_arr, int32_t n,
+                  const double* phase_dev, void* stream);
 
 /* wf_array.impose_pbc / impose_loop (pythtb.py:2674-2791) on a device array of
  * shape [outer][len][inner][nsta_arr][n]: slice len-1 = slice 0 (* phase[n]).
@@ -192,6 +205,12 @@ size_t tbk_position_hwf_workspace(int32_t nocc, int32_t n, int64_t batch);
 int tbk_position_hwf(const double* evec_dev, int64_t batch, int32_t nocc, int32_t n,
                      const double* pos_dev, double* hwfc_dev, double* hwf_dev,
                      int32_t orbital_basis, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* Name of the kernel family the calling thread's last solve call dispatched to
+ * (benchmark / profile bookkeeping). */
+const char* tbk_last_kernel(void);
+/* Number of kernels this library has launched in this process (all threads). */
+int64_t tbk_launch_count(void);
 
 /* L2 flush helper for benchmarks: overwrites buf_dev[bytes] (bytes > L2 size). */
 int tbk_flush_l2(void* buf_dev, size_t bytes, void* stream);

@@ -97,9 +97,13 @@ class B200Engine(object):
         self.device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", torch.cuda.current_device())))
         torch.cuda.set_device(self.device)
         self._ws = None
-        self.launches = 0               # kernels launched through this engine (bench bookkeeping)
 
     # ------------------------------------------------------------------ helpers
+    @property
+    def launches(self):
+        """Kernels launched by libtbk_b200.so in this process (counted inside the library)."""
+        return int(self.lib.tbk_launch_count())
+
     def stream(self):
         return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -141,7 +145,6 @@ class B200Engine(object):
         kd = self.to_dev(klist, np.float64) if plan.dim_k > 0 else None
         ham = torch.empty((nk, n, n), dtype=torch.complex128, device=self.device)
         _lib.check(self.lib.tbk_gen_ham(handle, _ptr(kd), nk, _ptr(ham), self.stream()))
-        self.launches += 1
         return ham.cpu().numpy()
 
     def eigh(self, ham, eig_vectors):
@@ -155,7 +158,6 @@ class B200Engine(object):
         wsb = self.lib.tbk_eigh_workspace(n, batch, int(eig_vectors))
         ws = self.workspace(wsb)
         _lib.check(self.lib.tbk_eigh_batched(_ptr(hd), n, batch, _ptr(ev), _ptr(vec), _ptr(ws), ws.numel(), self.stream()))
-        self.launches += 1
         return ev.cpu().numpy(), (vec.cpu().numpy() if eig_vectors else None)
 
     def solve_all_device(self, model, kd, nk, eig_vectors):
@@ -171,7 +173,6 @@ class B200Engine(object):
         ws = self.workspace(self.lib.tbk_solve_workspace(n, nk, int(eig_vectors)))
         _lib.check(self.lib.tbk_solve_k(handle, _ptr(kd), nk, _ptr(ev), nk, 1, _ptr(vec), nk * n, n,
                                         _ptr(ws), ws.numel(), self.stream()))
-        self.launches += 1
         return ev, vec
 
     def solve_all(self, model, klist, eig_vectors):
@@ -204,25 +205,83 @@ class B200Engine(object):
             out.append(np.repeat(ffac, nspin))
         return np.array(out, dtype=complex)
 
-    def solve_grid(self, model, store, mesh_arr, start_k, row0=0, nrows=None, wrap0=True):
-        """wf_array.solve_on_grid + impose_pbc (pythtb.py:2421-2532) into ``store``;
-        returns the minimal gaps as a device tensor (or None)."""
+    def _cached(self, owner, key, make):
+        """Small device constants (pbc phases, occ lists, slice offsets) are
+        uploaded once per owner object, not once per call."""
+        cache = owner.__dict__.setdefault("_tbk_dev_cache", {})
+        val = cache.get(key)
+        if val is None:
+            val = cache[key] = make()
+        return val
+
+    def solve_grid(self, model, store, mesh_arr, start_k, row0=0, nrows=None, wrap0=1, want_gaps=True):
+        """wf_array.solve_on_grid + impose_pbc (pythtb.py:2421-2532) into ``store``
+        (local rows [row0, row0+nrows] of mesh axis 0); returns the minimal gaps
+        over the rows solved here as a device tensor (or None).
+        wrap0: 1 = write the periodic image of row 0 (single shard), 0 = leave the
+        closing row to a halo exchange, 2 = compute the closing row in this launch."""
         torch = self.torch
         handle, plan = self.model_handle(model)
         nd, n = len(mesh_arr), plan.nsta
         if nrows is None:
             nrows = int(mesh_arr[0]) - 1
         wfs = store.dev(will_write=True)
-        phase = self.to_dev(self.pbc_phases(model._orb, model._nspin, [model._per[d] for d in range(nd)]))
-        gaps = torch.empty(max(n - 1, 1), dtype=torch.float64, device=self.device) if n > 1 else None
-        npts = nrows * int(np.prod(np.asarray(mesh_arr[1:]) - 1)) if nd > 1 else nrows
+        phase = self._cached(plan, ("pbc", nd), lambda: self.to_dev(
+            self.pbc_phases(model._orb, model._nspin, [model._per[d] for d in range(nd)])))
+        gaps = torch.empty(n - 1, dtype=torch.float64, device=self.device) if (n > 1 and want_gaps) else None
+        npts = (nrows + 1) * int(np.prod(np.asarray(mesh_arr[1:]) - 1)) if nd > 1 else nrows + 1
         ws = self.workspace(self.lib.tbk_solve_workspace(n, max(npts, 1), 1))
         start = (ctypes.c_double * nd)(*[float(x) for x in start_k])
         mesh = (ctypes.c_int32 * nd)(*[int(x) for x in mesh_arr])
-        _lib.check(self.lib.tbk_solve_grid(handle, start, mesh, nd, int(row0), int(nrows), int(bool(wrap0)),
+        _lib.check(self.lib.tbk_solve_grid(handle, start, mesh, nd, int(row0), int(nrows), int(wrap0),
                                            _ptr(wfs), _ptr(phase), _ptr(gaps), _ptr(ws), ws.numel(), self.stream()))
-        self.launches += 2 if gaps is not None else 1
+        self.last_solve_kernel = _lib.last_kernel(self.lib)
         return gaps
+
+    # ---------------------------------------------------------- multi-GPU plumbing
+    def halo_ring_shift(self, store, dim_arr, phase, rank, nranks):
+        """Close every rank's slab with the first row of the next rank: one
+        grouped NCCL send/recv over NVLink (rank r sends its row 0 to r-1; rank 0's
+        row goes to the last rank multiplied by the pbc phase, pythtb.py:2729)."""
+        import torch.distributed as dist
+        wfs = store.dev(will_write=True)
+        row = wfs[0]
+        nsta_arr = store.shape[dim_arr]
+        n = int(np.prod(store.shape[dim_arr + 1:]))
+        send = self.torch.empty_like(row)
+        ph = self.to_dev(phase) if phase is not None else None
+        _lib.check(self.lib.tbk_halo_pack(_ptr(row), _ptr(send), row.numel() // (nsta_arr * n), nsta_arr, n,
+                                          _ptr(ph), self.stream()))
+        recv = wfs[wfs.shape[0] - 1]
+        ops = [dist.P2POp(dist.isend, send, (rank - 1) % nranks), dist.P2POp(dist.irecv, recv, (rank + 1) % nranks)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    def allreduce(self, x, op):
+        """Sum / min of a small result vector over the ranks (NCCL)."""
+        import torch.distributed as dist
+        t = x if not isinstance(x, np.ndarray) else self.to_dev(np.ascontiguousarray(x, dtype=np.float64))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MIN)
+        return t.cpu().numpy() if isinstance(x, np.ndarray) else t
+
+    def allgather_rows(self, local, nranks, n0):
+        """Gather per-rank row blocks (host arrays, rows along axis 0); returns the
+        list of blocks in rank order.  Row counts follow from the sharding rule, so
+        only one padded all-gather is needed."""
+        import torch.distributed as dist
+        torch = self.torch
+        base, rem = divmod(n0 - 1, nranks)
+        maxrows = base + 2
+        tail = local.shape[1:]
+        pad = np.zeros((maxrows,) + tail, dtype=np.float64)
+        pad[:local.shape[0]] = local
+        out = torch.empty((nranks, maxrows) + tail, dtype=torch.float64, device=self.device)
+        dist.all_gather_into_tensor(out, self.to_dev(pad).reshape((1, maxrows) + tail))
+        cnt = torch.tensor([local.shape[0]], dtype=torch.int64, device=self.device)
+        cnts = torch.empty(nranks, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(cnts, cnt)
+        out_h, cnts_h = out.cpu().numpy(), cnts.cpu().numpy()
+        return [out_h[r, :cnts_h[r]] for r in range(nranks)]
 
     def impose_boundary(self, store, dim_arr, mesh_dir, phase):
         """impose_pbc / impose_loop on the device (pythtb.py:2674-2791)."""
@@ -235,7 +294,6 @@ class B200Engine(object):
         n = int(np.prod(shape[dim_arr + 1:]))
         ph = self.to_dev(phase) if phase is not None else None
         _lib.check(self.lib.tbk_impose_boundary(_ptr(wfs), outer, length, inner, nsta_arr, n, _ptr(ph), self.stream()))
-        self.launches += 1
 
     def _view(self, store, dim_arr, occ):
         wfs = store.dev(will_write=False)
@@ -248,10 +306,24 @@ class B200Engine(object):
         occ = np.where(occ < 0, occ + nsta_arr, occ)
         if occ.min() < 0 or occ.max() >= nsta_arr:
             raise IndexError("index in occ out of bounds")
-        occ_d = self.to_dev(occ.astype(np.int32))
+        occ_d = self._cached(store, ("occ", tuple(int(x) for x in occ)), lambda: self.to_dev(occ.astype(np.int32)))
         view = _lib.WfView(wfs.data_ptr(), n, nsta_arr, len(occ), occ_d.data_ptr())
         strides = [int(np.prod(shape[d + 1:dim_arr])) * nsta_arr * n for d in range(dim_arr)]
         return view, strides, (wfs, occ_d)
+
+    def _offsets(self, store, dim_arr, axes, strides):
+        """Element offsets of every slice/string labelled by the mesh axes ``axes`` (device, cached)."""
+        mesh = store.shape[:dim_arr]
+
+        def make():
+            oshape = tuple(mesh[d] for d in axes)
+            offs = np.zeros(oshape if oshape else (1,), dtype=np.int64)
+            for ax, d in enumerate(axes):
+                sh = [1] * len(axes)
+                sh[ax] = mesh[d]
+                offs = offs + (np.arange(mesh[d], dtype=np.int64) * strides[d]).reshape(sh)
+            return self.to_dev(np.ascontiguousarray(offs.reshape(-1)))
+        return self._cached(store, ("offs", tuple(store.shape), tuple(axes)), make)
 
     def berry_strings(self, store, dim_arr, occ, dir, berry_evals):
         """_one_berry_loop for every string along ``dir`` (pythtb.py:2979-3029,
@@ -261,19 +333,12 @@ class B200Engine(object):
         mesh = store.shape[:dim_arr]
         other = [d for d in range(dim_arr) if d != dir]
         oshape = tuple(mesh[d] for d in other)
-        offs = np.zeros(oshape if oshape else (1,), dtype=np.int64)
-        for ax, d in enumerate(other):
-            sh = [1] * len(other)
-            sh[ax] = mesh[d]
-            offs = offs + (np.arange(mesh[d], dtype=np.int64) * strides[d]).reshape(sh)
-        offs = np.ascontiguousarray(offs.reshape(-1))
-        nstr, npts, nocc = offs.size, mesh[dir], view.nocc
-        offs_d = self.to_dev(offs)
+        offs_d = self._offsets(store, dim_arr, other, strides)
+        nstr, npts, nocc = int(offs_d.numel()), mesh[dir], view.nocc
         out = torch.empty((nstr, nocc) if berry_evals else (nstr,), dtype=torch.float64, device=self.device)
         ws = self.workspace(self.lib.tbk_berry_workspace(nocc, view.n, nstr, npts, int(berry_evals)))
         _lib.check(self.lib.tbk_berry_strings(ctypes.byref(view), _ptr(offs_d), nstr, npts, strides[dir],
                                               int(berry_evals), _ptr(out), _ptr(ws), ws.numel(), self.stream()))
-        self.launches += 2
         res = out.cpu().numpy()
         return res.reshape(oshape + ((nocc,) if berry_evals else ()))
 
@@ -288,27 +353,23 @@ class B200Engine(object):
             return plq.cpu().numpy().reshape(rshape + (mesh[dirs[0]] - 1, mesh[dirs[1]] - 1))
         return tot.cpu().numpy().reshape(rshape)
 
+    def flux_total(self, store, dim_arr, occ, dirs):
+        """Sum of the plaquette phases of every local 2-D slice, as a device tensor [nslice]."""
+        return self.flux_device(store, dim_arr, occ, dirs, want_total=True, want_plaq=False)[0]
+
     def flux_device(self, store, dim_arr, occ, dirs, want_total=True, want_plaq=False):
         torch = self.torch
         view, strides, keep = self._view(store, dim_arr, occ)
         mesh = store.shape[:dim_arr]
         rest = [d for d in range(dim_arr) if d not in dirs]
-        rshape = tuple(mesh[d] for d in rest)
-        offs = np.zeros(rshape if rshape else (1,), dtype=np.int64)
-        for ax, d in enumerate(rest):
-            sh = [1] * len(rest)
-            sh[ax] = mesh[d]
-            offs = offs + (np.arange(mesh[d], dtype=np.int64) * strides[d]).reshape(sh)
-        offs = np.ascontiguousarray(offs.reshape(-1))
-        nslice = offs.size
+        offs_d = self._offsets(store, dim_arr, rest, strides)
+        nslice = int(offs_d.numel())
         n0, n1 = mesh[dirs[0]], mesh[dirs[1]]
-        offs_d = self.to_dev(offs)
         plq = torch.empty((nslice, n0 - 1, n1 - 1), dtype=torch.float64, device=self.device) if want_plaq else None
         tot = torch.empty((nslice,), dtype=torch.float64, device=self.device) if want_total else None
         ws = self.workspace(self.lib.tbk_flux_workspace(view.nocc, view.n, nslice, n0, n1))
         _lib.check(self.lib.tbk_flux_plane(ctypes.byref(view), _ptr(offs_d), nslice, n0, strides[dirs[0]], n1,
                                            strides[dirs[1]], _ptr(plq), _ptr(tot), _ptr(ws), ws.numel(), self.stream()))
-        self.launches += 2 if want_total else 1
         return tot, plq
 
     # ------------------------------------------------------- position operator
@@ -324,7 +385,6 @@ class B200Engine(object):
         pos = self.to_dev(self._pos(model, dir), np.float64)
         x = torch.empty((batch, nocc, nocc), dtype=torch.complex128, device=self.device)
         _lib.check(self.lib.tbk_position_matrix(_ptr(ed), batch, nocc, n, _ptr(pos), _ptr(x), self.stream()))
-        self.launches += 1
         return x.cpu().numpy()
 
     def position_hwf(self, model, evec, dir, hwf_evec, orbital_basis):
@@ -341,5 +401,4 @@ class B200Engine(object):
         ws = self.workspace(self.lib.tbk_position_hwf_workspace(nocc, n, batch))
         _lib.check(self.lib.tbk_position_hwf(_ptr(ed), batch, nocc, n, _ptr(pos), _ptr(hwfc), _ptr(hwf),
                                              int(bool(orbital_basis)), _ptr(ws), ws.numel(), self.stream()))
-        self.launches += 3
         return hwfc.cpu().numpy(), (hwf.cpu().numpy() if hwf_evec else None)

@@ -19,7 +19,7 @@ SYMBOLS = [
     "tbk_eigh_workspace", "tbk_eigh_batched", "tbk_solve_workspace", "tbk_solve_k", "tbk_solve_grid",
     "tbk_impose_boundary", "tbk_flux_workspace", "tbk_flux_plane", "tbk_berry_workspace",
     "tbk_berry_strings", "tbk_position_matrix", "tbk_position_hwf_workspace", "tbk_position_hwf",
-    "tbk_flush_l2",
+    "tbk_flush_l2", "tbk_halo_pack", "tbk_last_kernel", "tbk_launch_count",
 ]
 
 
@@ -76,6 +76,9 @@ def load():
         "tbk_position_hwf_workspace": (SZ, [I32, I32, I64]),
         "tbk_position_hwf": (ctypes.c_int, [V, I64, I32, I32, V, V, V, I32, V, SZ, V]),
         "tbk_flush_l2": (ctypes.c_int, [V, SZ, V]),
+        "tbk_halo_pack": (ctypes.c_int, [V, V, I64, I32, I32, V, V]),
+        "tbk_last_kernel": (ctypes.c_char_p, []),
+        "tbk_launch_count": (c_int64, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -90,3 +93,9 @@ def check(rc):
     if rc != 0:
         msg = load().tbk_last_error()
         raise TbkError("\n\nlibtbk_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+def last_kernel(lib):
+    """Name of the kernel family the last solve call on this thread dispatched to."""
+    name = lib.tbk_last_kernel()
+    return name.decode() if name else "?"

@@ -1,11 +1,38 @@
 // tbk_api.cu — error plumbing, model upload, misc entry points of libtbk_b200.so.
 #include <stdarg.h>
+#include <atomic>
+#include <mutex>
 #include <vector>
 #include "tbk_internal.cuh"
 
 namespace tbk {
 
 static thread_local char g_err[512] = "";
+static thread_local const char* g_last_kernel = "";
+
+static std::atomic<long long> g_launches{0};
+
+void note_kernel(const char* name) { g_last_kernel = name; }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- per-device array of self-resetting tickets for "last CTA finishes the reduction" kernels.
+// One-time 4 KB allocation per device (zeroed once); a call takes the next slot round-robin.  A
+// ticket is incremented with atomicInc(slot, nblocks-1), which wraps it back to 0 by itself.
+static unsigned* g_tickets[64] = {nullptr};
+static unsigned g_next_ticket[64] = {0};
+static std::mutex g_ticket_mu;
+
+unsigned* take_ticket() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(g_ticket_mu);
+  if (!g_tickets[dev]) {
+    if (cudaMalloc(&g_tickets[dev], kTicketSlots * sizeof(unsigned)) != cudaSuccess) return nullptr;
+    if (cudaMemset(g_tickets[dev], 0, kTicketSlots * sizeof(unsigned)) != cudaSuccess) return nullptr;
+  }
+  const unsigned slot = g_next_ticket[dev]++ % kTicketSlots;
+  return g_tickets[dev] + slot;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -95,6 +122,40 @@ int tbk_model_create(const tbk_model_desc* d, tbk_model** out) {
   pv.pm_ptr = (const int*)(b + segs[7].off);
   pv.pm_el = (const int*)(b + segs[8].off);
   pv.pm_amp = (const double*)(b + segs[9].off);
+  // ---- dense coefficient form for the register-resident small-matrix mesh kernel
+  DenseSmall& ds = m->dense;
+  memset(&ds, 0, sizeof(ds));
+  if (d->nsta >= 2 && d->nsta <= 4 && d->nph <= kDenseMaxPh && d->dim_k >= 1) {
+    ds.valid = 1;
+    ds.nph = d->nph;
+    for (int p = 0; p < d->nph; ++p)
+      for (int x = 0; x < d->dim_k; ++x) ds.R[p][x] = d->ph_R[p * d->dim_k + x];
+    for (int o = 0; o < d->nsta; ++o)
+      for (int x = 0; x < d->dim_k; ++x) ds.tau[o][x] = d->tau[o * d->dim_k + x];
+    double A[kDenseMaxPh][kDenseMaxEl][2] = {}, B[kDenseMaxPh][kDenseMaxEl][2] = {};
+    for (int p = 0; p <= d->nph; ++p) {
+      for (int t = d->pm_ptr[p]; t < d->pm_ptr[p + 1]; ++t) {
+        const int e = d->pm_el[t] & TBK_PH_MASK;
+        const bool cj = (d->pm_el[t] & TBK_PH_CONJ) != 0;
+        const int r = d->el_row[e], c = d->el_col[e];
+        const int pk = r * (r + 1) / 2 + c;
+        const double ar = d->pm_amp[2 * t], ai = d->pm_amp[2 * t + 1];
+        if (p == d->nph) { ds.C[pk][0] += ar; ds.C[pk][1] += ai; }
+        else if (!cj) { A[p][pk][0] += ar; A[p][pk][1] += ai; }
+        else { B[p][pk][0] += ar; B[p][pk][1] += ai; }
+      }
+    }
+    for (int p = 0; p < d->nph; ++p)
+      for (int e = 0; e < kDenseMaxEl; ++e) {
+        ds.P[p][e][0] = A[p][e][0] + B[p][e][0];
+        ds.P[p][e][1] = A[p][e][1] + B[p][e][1];
+        // Q = i (A - B)
+        ds.Q[p][e][0] = -(A[p][e][1] - B[p][e][1]);
+        ds.Q[p][e][1] = A[p][e][0] - B[p][e][0];
+        if (ds.P[p][e][0] != 0.0 || ds.P[p][e][1] != 0.0 || ds.Q[p][e][0] != 0.0 || ds.Q[p][e][1] != 0.0)
+          ds.mask[p] |= 1u << e;
+      }
+  }
   *out = m;
   return TBK_OK;
 }
@@ -105,6 +166,10 @@ int tbk_model_destroy(tbk_model* m) {
   delete m;
   return TBK_OK;
 }
+
+const char* tbk_last_kernel(void) { return g_last_kernel; }
+
+int64_t tbk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int tbk_flush_l2(void* buf_dev, size_t bytes, void* stream) {
   if (!buf_dev || bytes < 32) { set_error("tbk_flush_l2: bad buffer"); return TBK_ERR_ARG; }

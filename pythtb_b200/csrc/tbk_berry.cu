@@ -103,6 +103,180 @@ flux_small_kernel(WfView v, const long long* __restrict__ slice_off, long long n
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Row-marching plaquette kernel for register-sized states (nocc <= 2, n <= 4):
+// the Berry-flux kernel of BASELINE configs[1].
+//
+// Link-variable form: with a=(i,j), b=(i+1,j), c=(i+1,j+1),
+// d=(i,j+1) and L(x,y) = det <x|y>,
+//     phase(i,j) = -arg[ L(a,b) L(b,c) L(c,d) L(d,a) ]
+// and L(c,d) = conj(V(i,j+1)), L(d,a) = conj(H(i,j)) where V(i,j) = L((i,j),(i+1,j)) is the
+// vertical and H(i,j) = L((i,j),(i,j+1)) the horizontal link.  A CTA owns 127 plaquette
+// columns and marches down `ti` rows: thread t computes V(i, col0+t) (128 of them, shared through
+// smem) and H(i+1, col) which it keeps in a register for the next row, so each plaquette costs
+// two link determinants and each occupied state is fetched from HBM once per tile row.
+// The plane sum is finished by the last CTA (ticket) in a fixed order: one launch, deterministic.
+// ---------------------------------------------------------------------------
+constexpr int kFluxThreads = 128;
+constexpr int kFluxCols = kFluxThreads - 1;
+
+struct FluxTiling {
+  int ti;                 // plaquette rows per tile
+  long long nbx, nrb;     // column blocks, row blocks per slice
+  long long ntiles;       // nslice * nrb * nbx
+};
+
+static FluxTiling flux_tiling(long long nslice, long long n0, long long n1) {
+  FluxTiling t;
+  t.nbx = (n1 - 1 + kFluxCols - 1) / kFluxCols;
+  int ti = 32;
+  while (ti > 1 && nslice * ((n0 - 1 + ti - 1) / ti) * t.nbx < (long long)kNumSM * 4) ti >>= 1;
+  t.ti = ti;
+  t.nrb = (n0 - 1 + ti - 1) / ti;
+  t.ntiles = nslice * t.nrb * t.nbx;
+  return t;
+}
+
+template <int NOCC, int N>
+struct OccState {
+  cplx u[NOCC][N];
+  __device__ __forceinline__ void load(const cplx* __restrict__ p, const int* occ) {
+#pragma unroll
+    for (int m = 0; m < NOCC; ++m) {
+      const double2* src = reinterpret_cast<const double2*>(p + (long long)occ[m] * N);
+#pragma unroll
+      for (int o = 0; o < N; ++o) { const double2 t = __ldg(src + o); u[m][o] = mk(t.x, t.y); }
+    }
+  }
+};
+
+// det <a|b> for NOCC <= 2
+template <int NOCC, int N>
+__device__ __forceinline__ cplx link_det(const OccState<NOCC, N>& a, const OccState<NOCC, N>& b) {
+  cplx M[NOCC][NOCC];
+#pragma unroll
+  for (int m = 0; m < NOCC; ++m)
+#pragma unroll
+    for (int q = 0; q < NOCC; ++q) {
+      cplx acc = mk(0.0, 0.0);
+#pragma unroll
+      for (int o = 0; o < N; ++o) fma_acc_conj(acc, a.u[m][o], b.u[q][o]);
+      M[m][q] = acc;
+    }
+  if constexpr (NOCC == 1) return M[0][0];
+  else return M[0][0] * M[1][1] - M[0][1] * M[1][0];
+}
+
+template <int NOCC, int N>
+__global__ void __launch_bounds__(kFluxThreads)
+flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0, long long stride0, long long n1,
+                 long long stride1, FluxTiling tl, long long nslice, double* __restrict__ plaq,
+                 double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ total) {
+  __shared__ cplx s_v[2][kFluxThreads];
+  __shared__ double s_red[kFluxThreads / 32];
+  __shared__ int s_occ[NOCC];
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  if (tid < NOCC) s_occ[tid] = v.occ[tid];
+  __syncthreads();
+  const long long p0 = n0 - 1, p1 = n1 - 1;
+  for (long long tile = blockIdx.x; tile < tl.ntiles; tile += gridDim.x) {
+    const long long s = tile / (tl.nrb * tl.nbx);
+    const long long rem = tile - s * tl.nrb * tl.nbx;
+    const long long rb = rem / tl.nbx, bx = rem - rb * tl.nbx;
+    const long long col = bx * kFluxCols + tid;            // mesh column of this thread's vertical link
+    const bool has_col = col < n1;
+    const bool owner = tid < kFluxCols && col < p1;        // owns plaquette column `col`
+    const long long i0 = rb * tl.ti;
+    const long long i1 = (i0 + tl.ti < p0) ? i0 + tl.ti : p0;
+    const cplx* base = v.wfs + slice_off[s] + col * stride1;
+    OccState<NOCC, N> a, b, c;
+    cplx hda = mk(1.0, 0.0);                               // L(d,a) = conj(H(i,col))
+    if (has_col) a.load(base + i0 * stride0, s_occ);
+    if (owner) {
+      c.load(base + i0 * stride0 + stride1, s_occ);        // d of the first row
+      hda = conj(link_det<NOCC, N>(a, c));
+    }
+    double acc = 0.0;
+    for (long long i = i0; i < i1; ++i) {
+      const int buf = (int)(i & 1);
+      cplx lab = mk(0.0, 0.0);
+      if (has_col) {
+        b.load(base + (i + 1) * stride0, s_occ);
+        lab = link_det<NOCC, N>(a, b);                     // V(i, col)
+      }
+      s_v[buf][tid] = lab;
+      __syncthreads();
+      if (owner) {
+        c.load(base + (i + 1) * stride0 + stride1, s_occ);
+        const cplx lbc = link_det<NOCC, N>(b, c);          // H(i+1, col)
+        cplx prod = lab * lbc;
+        prod = mulc(prod, s_v[buf][tid + 1]);              // L(c,d) = conj(V(i, col+1))
+        prod = prod * hda;
+        const double phase = neg_arg(prod);
+        if (plaq) plaq[(s * p0 + i) * p1 + col] = phase;
+        acc += phase;
+        hda = conj(lbc);
+      }
+      a = b;
+    }
+    if (partial) {
+      // fixed-order CTA sum -> partial[tile]
+      double x = acc;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      __syncthreads();
+      if ((tid & 31) == 0) s_red[tid >> 5] = x;
+      __syncthreads();
+      if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kFluxThreads / 32; ++w) t += s_red[w];
+        partial[tile] = t;
+      }
+    }
+    __syncthreads();
+  }
+  if (!partial) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const long long per = tl.nrb * tl.nbx;
+  for (long long s = 0; s < nslice; ++s) {
+    double x = 0.0;
+    for (long long i = tid; i < per; i += kFluxThreads) x += __ldcg(partial + s * per + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    __syncthreads();
+    if ((tid & 31) == 0) s_red[tid >> 5] = x;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < kFluxThreads / 32; ++w) t += s_red[w];
+      total[s] = t;
+    }
+  }
+}
+
+template <int NOCC, int N>
+static int launch_flux_rows(const WfView& v, const long long* off, long long nslice, long long n0, long long stride0,
+                            long long n1, long long stride1, double* plaq, double* total, double* partial, cudaStream_t st) {
+  const FluxTiling tl = flux_tiling(nslice, n0, n1);
+  unsigned* ticket = nullptr;
+  if (total) {
+    ticket = take_ticket();
+    if (!ticket) { set_error("tbk_flux_plane: cannot allocate the reduction tickets"); return TBK_ERR_CUDA; }
+  }
+  const int grid = (int)(tl.ntiles < (long long)kNumSM * 8 ? tl.ntiles : (long long)kNumSM * 8);
+  flux_rows_kernel<NOCC, N><<<grid, kFluxThreads, 0, st>>>(v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
+                                                          total ? partial : nullptr, ticket, total);
+  TBK_LAUNCH_CHECK("flux_rows_kernel");
+  return TBK_OK;
+}
+
 // sum partial[s][0..count) in a fixed order -> total[s]
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const double* __restrict__ partial, long long count, double* __restrict__ total) {
@@ -325,6 +499,16 @@ impose_boundary_kernel(cplx* __restrict__ wfs, long long outer, long long len, l
   }
 }
 
+// dst[q] = src[q] (* phase[q % n]): packs the first local row of a shard for the ring shift
+__global__ void __launch_bounds__(256)
+halo_pack_kernel(const cplx* __restrict__ src, cplx* __restrict__ dst, long long total, int n, const cplx* __restrict__ phase) {
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    cplx v = src[q];
+    if (phase) v = v * phase[(int)(q % n)];
+    dst[q] = v;
+  }
+}
+
 // X[k][m][q] = sum_o conj(A[k][m][o]) pos[o] A[k][q][o]
 __global__ void __launch_bounds__(256)
 position_matrix_kernel(const cplx* __restrict__ evec, long long batch, int nocc, int n, const double* __restrict__ pos,
@@ -402,10 +586,23 @@ int tbk_impose_boundary(double* wfs_dev, int64_t outer, int64_t len, int64_t inn
   return TBK_OK;
 }
 
+int tbk_halo_pack(const double* row_dev, double* dst_dev, int64_t npoints, int32_t nsta_arr, int32_t n,
+                  const double* phase_dev, void* stream) {
+  if (!row_dev || !dst_dev || npoints < 0 || nsta_arr < 1 || n < 1) { set_error("tbk_halo_pack: bad argument"); return TBK_ERR_ARG; }
+  const long long total = npoints * nsta_arr * n;
+  if (total == 0) return TBK_OK;
+  long long blocks = (total + 255) / 256;
+  if (blocks > kNumSM * 16) blocks = kNumSM * 16;
+  halo_pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const cplx*)row_dev, (cplx*)dst_dev, total, n, (const cplx*)phase_dev);
+  TBK_LAUNCH_CHECK("halo_pack_kernel");
+  return TBK_OK;
+}
+
 size_t tbk_flux_workspace(int32_t nocc, int32_t n, int64_t nslice, int64_t n0, int64_t n1) {
   (void)n;
   const long long bx = (n1 - 1 + 255) / 256;
   size_t bytes = align256((size_t)(nslice * (n0 - 1) * (bx > 0 ? bx : 1)) * 8);   // block partial sums
+  bytes += align256((size_t)flux_tiling(nslice, n0, n1).ntiles * 8);
   if (nocc > 4) {
     const long long nlinks = nslice * ((n0 - 1) * n1 + n0 * (n1 - 1));
     bytes += align256((size_t)nlinks * 16);
@@ -436,6 +633,20 @@ int tbk_flux_plane(const tbk_wf_view* view, const int64_t* slice_off_dev, int64_
   double* partial = total_dev ? (double*)ws : nullptr;
   ws += align256((size_t)(nslice * p0 * bx) * 8);
   const long long* off = (const long long*)slice_off_dev;
+  if (view->nocc <= 2 && view->n >= 2 && view->n <= 4 && view->nocc <= view->n) {
+    double* part2 = (double*)ws;
+    int rc = TBK_OK;
+    const int key = view->nocc * 10 + view->n;
+    switch (key) {
+      case 12: rc = launch_flux_rows<1, 2>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, st); break;
+      case 22: rc = launch_flux_rows<2, 2>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, st); break;
+      case 13: rc = launch_flux_rows<1, 3>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, st); break;
+      case 23: rc = launch_flux_rows<2, 3>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, st); break;
+      case 14: rc = launch_flux_rows<1, 4>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, st); break;
+      default: rc = launch_flux_rows<2, 4>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, st); break;
+    }
+    return rc;
+  }
   if (view->nocc <= 4) {
     switch (view->nocc) {
       case 1: flux_small_kernel<1><<<grid, 256, 0, st>>>(v, off, n0, stride0, n1, stride1, plaq_dev, partial); break;

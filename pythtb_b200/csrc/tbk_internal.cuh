@@ -12,6 +12,10 @@
 namespace tbk {
 
 void set_error(const char* fmt, ...);
+void count_launch();                    // every kernel this library launches is counted (tbk_launch_count)
+void note_kernel(const char* name);     // remembered for tbk_last_kernel()
+constexpr int kTicketSlots = 1024;
+unsigned* take_ticket();                // zero-initialised, self-resetting device counter (see tbk_api.cu)
 int cuda_fail(cudaError_t e, const char* what);
 
 #define TBK_CUDA(call)                                   \
@@ -24,6 +28,7 @@ int cuda_fail(cudaError_t e, const char* what);
   do {                                                       \
     cudaError_t e__ = cudaGetLastError();                    \
     if (e__ != cudaSuccess) return cuda_fail(e__, name);     \
+    tbk::count_launch();                                     \
   } while (0)
 
 constexpr int kNumSM = 148;           // B200
@@ -79,9 +84,29 @@ struct ThreadGroup {  // a "group" of one thread (serial code paths)
 
 }  // namespace tbk
 
+namespace tbk {
+// Dense coefficient form of a small model (nsta <= 4, nph <= kDenseMaxPh), passed BY VALUE as a
+// kernel parameter so that every coefficient is a constant-bank operand of the FP64 pipe:
+//   H_e(k) = C_e + sum_p ( P_ep cos(2 pi k.R_p) + Q_ep sin(2 pi k.R_p) ),  e = lower-triangle element
+// with P = A + B, Q = i (A - B) where A (B) collects the amplitudes multiplying E_p (conj E_p).
+constexpr int kDenseMaxPh = 8;
+constexpr int kDenseMaxEl = 10;   // 4*5/2
+struct DenseSmall {
+  int valid;                       // 0: model does not fit this form
+  int nph;
+  unsigned mask[kDenseMaxPh];      // bit e: (P,Q)[p][e] != 0
+  double C[kDenseMaxEl][2];
+  double P[kDenseMaxPh][kDenseMaxEl][2];
+  double Q[kDenseMaxPh][kDenseMaxEl][2];
+  double R[kDenseMaxPh][TBK_MAX_DIM];
+  double tau[4][TBK_MAX_DIM];
+};
+}  // namespace tbk
+
 // The opaque model handle of tbk.h
 struct tbk_model {
   tbk::PlanView pv;   // device pointers
+  tbk::DenseSmall dense;
   void* blob;         // single device allocation backing every array
   size_t blob_bytes;
   int device;

@@ -1,0 +1,239 @@
+// tbk_mesh_small.cuh — wf_array.solve_on_grid for 2 <= nsta <= 4 on a regular
+// mesh (pythtb.py:2421-2532): the headline kernel of BASELINE configs[1]
+// (Haldane / Kane-Mele, 1024 x 1024).  Included by tbk_solve.cu.
+//
+// Design (B200): the kernel is bound by the 16 n^2 bytes it must write per
+// k-point, so everything else is arranged to stay below that:
+//   * one k-point per thread per step, threads along the FASTEST mesh axis, a CTA
+//     walks `ti` consecutive indices of the remaining (flattened) axes;
+//   * exp(2 pi i k.R) = exp(2 pi i k_outer.R_outer) * exp(2 pi i k_last R_last): the
+//     second factor is computed once per thread per tile, the first once per CTA
+//     per mesh row (shared memory) — about 0.4 sincospi per k-point instead of
+//     nph + nsta;
+//   * H(k) from a dense coefficient table held in the kernel-parameter constant
+//     bank (DenseSmall): 4 FMA per (element, phase), no indexed accumulators;
+//   * closed-form (n = 2) / Jacobi (n = 3, 4) eigensolver in registers;
+//   * Convention-I gauge, periodic images and the running minimum of the direct
+//     gaps fused in; the gap reduction finishes in the last CTA (ticket), so a
+//     grid solve is ONE launch.
+#pragma once
+
+namespace tbk {
+
+constexpr int kMeshThreads = 128;
+constexpr int kMeshMaxRows = 16;
+
+struct MeshTiling {
+  int ti;               // outer indices per tile
+  int nbx;              // tiles along the last axis
+  long long outer;      // product of cnt[d], d < nd-1
+  long long ntiles;
+  int closing_g;        // global axis-0 index that is the periodic image of row 0 (wrap0 == 2), else -1
+};
+
+template <int N, int NPH>
+__global__ void __launch_bounds__(kMeshThreads)
+mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__ KSrc ks,
+                  const __grid_constant__ OutSpec out, const __grid_constant__ MeshTiling tl, int gauge,
+                  double* __restrict__ gap_partial, unsigned* __restrict__ ticket, double* __restrict__ gaps_out) {
+  constexpr int NP = N * (N + 1) / 2;
+  constexpr int NQ = NPH + N;                       // phases, then per-state gauge factors
+  __shared__ cplx s_out[kMeshMaxRows][NQ];
+  __shared__ long long s_base[kMeshMaxRows];
+  __shared__ int s_flags[kMeshMaxRows];             // bits 0..3 zero_mask, bit 8 closing row, bit 9 valid
+  __shared__ double s_red[kMeshThreads / 32][N];
+  __shared__ int s_last;
+  const int nd = out.nd;
+  const int last = nd - 1;
+  const int nph = ds.nph;
+  const int tid = threadIdx.x;
+  double gmin[N - 1];
+#pragma unroll
+  for (int b = 0; b < N - 1; ++b) gmin[b] = INFINITY;
+
+  for (long long tile = blockIdx.x; tile < tl.ntiles; tile += gridDim.x) {
+    const long long by = tile / tl.nbx;
+    const int bx = (int)(tile - by * tl.nbx);
+    // ---- per-row (outer index) factors, one (row, q) pair per thread
+    __syncthreads();                                // previous tile's readers are done
+    for (int t = tid; t < tl.ti * NQ; t += kMeshThreads) {
+      const int r = t / NQ, q = t - r * NQ;
+      long long o = by * tl.ti + r;
+      const bool valid = o < tl.outer;
+      int mi[TBK_MAX_DIM] = {0, 0, 0, 0};
+      double x = 0.0;
+      bool closing = false;
+      long long base = 0;
+      int zmask = 0;
+      if (valid) {
+        for (int d = last - 1; d >= 0; --d) {       // C-order decode over the outer axes
+          const long long qq = o / out.cnt[d];
+          mi[d] = (int)(o - qq * out.cnt[d]);
+          o = qq;
+        }
+        for (int d = 0; d < last; ++d) {
+          int g = mi[d] + (d == 0 ? ks.row0 : 0);
+          if (d == 0 && g == tl.closing_g) { g = 0; closing = true; }
+          const double kd = ks.start[d] + (double)g / ks.den[d];                   // pythtb.py:2477
+          const double c = q < NPH ? (q < nph ? ds.R[q][d] : 0.0) : ds.tau[q - NPH][d];
+          x = fma(kd, c, x);
+          base += mi[d] * out.gstride[d];
+          if (mi[d] == 0 && out.wrap[d]) zmask |= 1 << d;
+        }
+      }
+      s_out[r][q] = expi_turns(x);
+      if (q == 0) {
+        s_base[r] = base;
+        s_flags[r] = zmask | (closing ? 256 : 0) | (valid ? 512 : 0);
+      }
+    }
+    // ---- per-thread factors along the fastest axis
+    const int j = bx * kMeshThreads + tid;
+    const bool active = j < out.cnt[last];
+    const int gj = j + (last == 0 ? ks.row0 : 0);
+    const bool closing_j = (last == 0 && gj == tl.closing_g);
+    const double kl = ks.start[last] + (double)(closing_j ? 0 : gj) / ks.den[last];
+    cplx fc[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const double c = q < NPH ? (q < nph ? ds.R[q][last] : 0.0) : ds.tau[q - NPH][last];
+      fc[q] = (q < NPH && q >= nph) ? mk(1.0, 0.0) : expi_turns(kl * c);
+    }
+    const int zlast = (j == 0 && out.wrap[last]) ? (1 << last) : 0;
+    __syncthreads();
+    if (active) {
+      for (int r = 0; r < tl.ti; ++r) {
+        const int fl = s_flags[r];
+        if (!(fl & 512)) break;
+        // ---- H(k), lower triangle
+        cplx acc[NP];
+#pragma unroll
+        for (int e = 0; e < NP; ++e) acc[e] = mk(ds.C[e][0], ds.C[e][1]);
+#pragma unroll
+        for (int p = 0; p < NPH; ++p) {
+          if (p < nph) {
+            const cplx z = s_out[r][p] * fc[p];     // exp(2 pi i k.R_p)
+            const unsigned m = ds.mask[p];
+#pragma unroll
+            for (int e = 0; e < NP; ++e) {
+              if (m & (1u << e)) {
+                acc[e].re = fma(ds.P[p][e][0], z.re, acc[e].re);
+                acc[e].re = fma(ds.Q[p][e][0], z.im, acc[e].re);
+                acc[e].im = fma(ds.P[p][e][1], z.re, acc[e].im);
+                acc[e].im = fma(ds.Q[p][e][1], z.im, acc[e].im);
+              }
+            }
+          }
+        }
+        // ---- diagonalise (rows of w = eigenvectors, ascending eigenvalues)
+        double ev[N];
+        cplx w[N][N];
+        if constexpr (N == 2) {
+          eigh2(acc[0].re, acc[2].re, acc[1], ev, w, true);
+        } else {
+          double dg[N];
+          cplx lo[N * (N - 1) / 2];
+#pragma unroll
+          for (int rr = 0; rr < N; ++rr) {
+            dg[rr] = acc[rr * (rr + 1) / 2 + rr].re;
+#pragma unroll
+            for (int c = 0; c < rr; ++c) lo[rr * (rr - 1) / 2 + c] = acc[rr * (rr + 1) / 2 + c];
+          }
+          JacobiPacked<N>::solve(dg, lo, w, true);
+#pragma unroll
+          for (int b = 0; b < N; ++b) ev[b] = dg[b];
+        }
+#pragma unroll
+        for (int b = 0; b < N - 1; ++b) gmin[b] = fmin(gmin[b], ev[b + 1] - ev[b]);
+        // ---- Convention-I gauge u_I[b][o] = conj(d_o) u_II[b][o] (+ pbc phase on a closing row)
+        const bool closing = (fl & 256) || closing_j;
+#pragma unroll
+        for (int o = 0; o < N; ++o) {
+          if (gauge) {
+            const cplx f = conj(s_out[r][NPH + o] * fc[NPH + o]);
+#pragma unroll
+            for (int b = 0; b < N; ++b) w[b][o] = w[b][o] * f;
+          }
+          if (closing) {                            // axis-0 image of global row 0 (pythtb.py:2729); a second
+            const cplx ph = out.pbc_phase[o];       // multiply, so the values equal the unsharded image bit for bit
+#pragma unroll
+            for (int b = 0; b < N; ++b) w[b][o] = w[b][o] * ph;
+          }
+        }
+        // ---- store (+ periodic images)
+        const long long base = s_base[r] + (long long)j * out.gstride[last];
+        cplx* dst = out.evec + base;
+#pragma unroll
+        for (int b = 0; b < N; ++b)
+#pragma unroll
+          for (int o = 0; o < N; ++o) dst[b * N + o] = w[b][o];
+        const int zero_mask = (fl & 15) | zlast;
+        if (zero_mask) {
+          for (int m = 1; m < (1 << nd); ++m) {
+            if ((m & zero_mask) != m) continue;
+            long long off = base;
+            cplx im[N][N];
+#pragma unroll
+            for (int b = 0; b < N; ++b)
+#pragma unroll
+              for (int o = 0; o < N; ++o) im[b][o] = w[b][o];
+            for (int d = 0; d < nd; ++d) {           // one multiply per wrapped axis, in axis order
+              if (m & (1 << d)) {
+                off += (long long)(out.full[d] - 1) * out.gstride[d];
+#pragma unroll
+                for (int o = 0; o < N; ++o) {
+                  const cplx ph = out.pbc_phase[d * N + o];
+#pragma unroll
+                  for (int b = 0; b < N; ++b) im[b][o] = im[b][o] * ph;
+                }
+              }
+            }
+            cplx* dsti = out.evec + off;
+#pragma unroll
+            for (int b = 0; b < N; ++b)
+#pragma unroll
+              for (int o = 0; o < N; ++o) dsti[b * N + o] = im[b][o];
+          }
+        }
+      }
+    }
+  }
+  // ---- minimal direct gaps (pythtb.py:2484, 2529-2530): CTA partial, last CTA finishes
+  if (gaps_out == nullptr) return;
+#pragma unroll
+  for (int b = 0; b < N - 1; ++b) {
+    double g = gmin[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) g = fmin(g, __shfl_xor_sync(0xffffffffu, g, o));
+    if ((tid & 31) == 0) s_red[tid >> 5][b] = g;
+  }
+  __syncthreads();
+  if (tid < N - 1) {
+    double g = s_red[0][tid];
+    for (int wv = 1; wv < kMeshThreads / 32; ++wv) g = fmin(g, s_red[wv][tid]);
+    gap_partial[(size_t)blockIdx.x * (N - 1) + tid] = g;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+#pragma unroll
+  for (int b = 0; b < N - 1; ++b) {
+    double g = INFINITY;
+    for (int i = tid; i < (int)gridDim.x; i += kMeshThreads) g = fmin(g, __ldcg(gap_partial + (size_t)i * (N - 1) + b));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) g = fmin(g, __shfl_xor_sync(0xffffffffu, g, o));
+    __syncthreads();
+    if ((tid & 31) == 0) s_red[tid >> 5][b] = g;
+    __syncthreads();
+    if (tid == 0) {
+      double t = s_red[0][b];
+      for (int wv = 1; wv < kMeshThreads / 32; ++wv) t = fmin(t, s_red[wv][b]);
+      gaps_out[b] = t;
+    }
+  }
+}
+
+}  // namespace tbk

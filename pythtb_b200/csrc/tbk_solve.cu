@@ -25,6 +25,7 @@ struct KSrc {
   const double* klist;  // [npts][dim_k], or nullptr -> mesh descriptor below
   int dim_k;
   int row0;             // offset added to the axis-0 mesh index (shards)
+  int closing_g;        // global axis-0 index solved as the periodic image of row 0 (wrap0 == 2), or -1
   double start[TBK_MAX_DIM];
   double den[TBK_MAX_DIM];   // mesh[d]-1 as double
 };
@@ -60,11 +61,19 @@ __device__ __forceinline__ void load_k(const KSrc& ks, long long idx, const int 
   for (int d = 0; d < TBK_MAX_DIM; ++d) {
     if (d < ks.dim_k) {
       if (ks.klist) k[d] = ks.klist[idx * ks.dim_k + d];
-      else k[d] = ks.start[d] + (double)(mi[d] + (d == 0 ? ks.row0 : 0)) / ks.den[d];   // pythtb.py:2477
+      else {
+        int g = mi[d] + (d == 0 ? ks.row0 : 0);
+        if (d == 0 && g == ks.closing_g) g = 0;     // periodic image of row 0, phase applied at the store
+        k[d] = ks.start[d] + (double)g / ks.den[d];                                     // pythtb.py:2477
+      }
     } else {
       k[d] = 0.0;
     }
   }
+}
+
+__device__ __forceinline__ bool is_closing(const KSrc& ks, const int mi[TBK_MAX_DIM]) {
+  return ks.klist == nullptr && ks.closing_g >= 0 && mi[0] + ks.row0 == ks.closing_g;
 }
 
 __device__ __forceinline__ void atomic_min_nonneg(unsigned long long* addr, double v) {
@@ -76,8 +85,12 @@ __global__ void fill_u64_kernel(unsigned long long* p, int n, unsigned long long
   if (i < n) p[i] = v;
 }
 
+}  // namespace tbk
+#include "tbk_mesh_small.cuh"
+namespace tbk {
+
 // ===========================================================================
-// One k-point per thread, N = 2..4
+// One k-point per thread, N = 2..4 (k-lists, and meshes the tiled kernel does not take)
 // ===========================================================================
 template <int N>
 __global__ void __launch_bounds__(128)
@@ -206,6 +219,12 @@ solve_small_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long lon
 #pragma unroll
       for (int d = 0; d < TBK_MAX_DIM; ++d)
         if (d < out.nd) base += mi[d] * out.gstride[d];
+      if (is_closing(ks, mi)) {
+#pragma unroll
+        for (int o = 0; o < N; ++o)
+#pragma unroll
+          for (int b = 0; b < N; ++b) w[b][o] = w[b][o] * out.pbc_phase[o];
+      }
       cplx* dst = out.evec + base;
 #pragma unroll
       for (int b = 0; b < N; ++b)
@@ -220,21 +239,25 @@ solve_small_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long lon
         for (int m = 1; m < (1 << out.nd); ++m) {
           if ((m & zero_mask) != m) continue;
           long long off = base;
-          cplx f[N];
-#pragma unroll
-          for (int o = 0; o < N; ++o) f[o] = mk(1.0, 0.0);
-          for (int d = 0; d < out.nd; ++d) {
-            if (m & (1 << d)) {
-              off += (long long)(out.full[d] - 1) * out.gstride[d];
-#pragma unroll
-              for (int o = 0; o < N; ++o) f[o] = f[o] * out.pbc_phase[d * N + o];
-            }
-          }
-          cplx* im = out.evec + off;
+          cplx im[N][N];
 #pragma unroll
           for (int b = 0; b < N; ++b)
 #pragma unroll
-            for (int o = 0; o < N; ++o) im[b * N + o] = w[b][o] * f[o];
+            for (int o = 0; o < N; ++o) im[b][o] = w[b][o];
+          for (int d = 0; d < out.nd; ++d) {         // one multiply per wrapped axis, in axis order
+            if (m & (1 << d)) {
+              off += (long long)(out.full[d] - 1) * out.gstride[d];
+#pragma unroll
+              for (int o = 0; o < N; ++o)
+#pragma unroll
+                for (int b = 0; b < N; ++b) im[b][o] = im[b][o] * out.pbc_phase[d * N + o];
+            }
+          }
+          cplx* dsti = out.evec + off;
+#pragma unroll
+          for (int b = 0; b < N; ++b)
+#pragma unroll
+            for (int o = 0; o < N; ++o) dsti[b * N + o] = im[b][o];
         }
       }
     }
@@ -338,13 +361,15 @@ __device__ void solve_one_matrix(G& g, const PlanView& pv, const KSrc& ks, const
   } else {
     long long base = 0;
     int zero_mask = 0;
+    const bool closing = is_closing(ks, mibuf);
     for (int d = 0; d < out.nd; ++d) {
       base += mibuf[d] * out.gstride[d];
       if (mibuf[d] == 0 && out.wrap[d]) zero_mask |= 1 << d;
     }
     for (int q = g.tid(); q < n * n; q += g.size()) {
       const int i = q / n, o = q - i * n;
-      const cplx v = A[o + (size_t)i * lda] * s.work[o];
+      cplx v = A[o + (size_t)i * lda] * s.work[o];
+      if (closing) v = v * out.pbc_phase[o];      // image of global row 0 (same two-step rounding as the unsharded image)
       const long long at = (long long)rank[i] * n + o;
       out.evec[base + at] = v;
       if (zero_mask) {
@@ -449,6 +474,7 @@ static int launch_solve(const PlanView& pv, const KSrc& ks, const cplx* hsrc, in
     else if (n == 3) solve_small_kernel<3><<<(unsigned)blocks, 128, dyn, st>>>(pv, ks, hsrc, npts, out, want_vec, stage);
     else solve_small_kernel<4><<<(unsigned)blocks, 128, dyn, st>>>(pv, ks, hsrc, npts, out, want_vec, stage);
     TBK_LAUNCH_CHECK("solve_small_kernel");
+    note_kernel("solve_small_kernel");
     return TBK_OK;
   }
   const int nph = hsrc ? 0 : pv.nph;
@@ -473,6 +499,7 @@ static int launch_solve(const PlanView& pv, const KSrc& ks, const cplx* hsrc, in
     else TBK_TILE_LAUNCH(32);
 #undef TBK_TILE_LAUNCH
     TBK_LAUNCH_CHECK("solve_tile_kernel");
+    note_kernel("solve_tile_kernel");
     return TBK_OK;
   }
   // one matrix per CTA
@@ -494,10 +521,13 @@ static int launch_solve(const PlanView& pv, const KSrc& ks, const cplx* hsrc, in
   TBK_CUDA(cudaFuncSetAttribute(solve_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs.region));
   solve_block_kernel<<<(unsigned)blocks, threads, gs.region, st>>>(pv, ks, hsrc, npts, out, want_vec, gs, gA);
   TBK_LAUNCH_CHECK("solve_block_kernel");
+  note_kernel("solve_block_kernel");
   return TBK_OK;
 }
 
+constexpr int kMeshGridCap = kNumSM * 8;
 static size_t solve_ws_bytes(int n, long long npts) {
+  if (n <= 4) return (size_t)kMeshGridCap * 4 * 8;   // per-CTA gap partials of mesh_small_kernel
   if (n <= 96) return 0;   // always shared-memory resident
   long long blocks = npts < (long long)kNumSM * 2 ? npts : (long long)kNumSM * 2;
   if (blocks < 1) blocks = 1;
@@ -542,11 +572,12 @@ __global__ void solve_n1_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ h
       base += mi[d] * out.gstride[d];
       if (mi[d] == 0 && out.wrap[d]) zero_mask |= 1 << d;
     }
-    out.evec[base] = mk(1.0, 0.0);
+    const cplx v0 = is_closing(ks, mi) ? out.pbc_phase[0] : mk(1.0, 0.0);
+    out.evec[base] = v0;
     for (int m = 1; m < (1 << out.nd); ++m) {
       if ((m & zero_mask) != m) continue;
       long long off = base;
-      cplx f = mk(1.0, 0.0);
+      cplx f = v0;
       for (int d = 0; d < out.nd; ++d)
         if (m & (1 << d)) { off += (long long)(out.full[d] - 1) * out.gstride[d]; f = f * out.pbc_phase[d]; }
       out.evec[off] = f;
@@ -582,6 +613,7 @@ int tbk_eigh_batched(const double* ham_dev, int32_t n, int64_t batch, double* ev
   pv.nsta = n; pv.convention = 2;
   KSrc ks;
   memset(&ks, 0, sizeof(ks));
+  ks.closing_g = -1;
   OutSpec out;
   memset(&out, 0, sizeof(out));
   out.mode = 0;
@@ -603,7 +635,7 @@ int tbk_solve_k(const tbk_model* m, const double* k_dev, int64_t nk, double* eva
   if (!m || nk < 0 || (!eval_dev && !evec_dev) || (m->pv.dim_k > 0 && !k_dev)) { set_error("tbk_solve_k: bad argument"); return TBK_ERR_ARG; }
   KSrc ks;
   memset(&ks, 0, sizeof(ks));
-  ks.klist = k_dev; ks.dim_k = m->pv.dim_k;
+  ks.klist = k_dev; ks.dim_k = m->pv.dim_k; ks.closing_g = -1;
   OutSpec out;
   memset(&out, 0, sizeof(out));
   out.mode = 0;
@@ -618,11 +650,53 @@ int tbk_solve_k(const tbk_model* m, const double* k_dev, int64_t nk, double* eva
   return launch_solve(m->pv, ks, nullptr, m->pv.nsta, nk, out, want_vec, ws_dev, ws_bytes, (cudaStream_t)stream);
 }
 
+// mesh_small_kernel dispatch; returns 1 if it took the job, 0 if the shape does not fit, < 0 on error
+static int launch_mesh_small(const tbk_model* m, const KSrc& ks, const OutSpec& out, double* gaps_dev,
+                             void* ws, size_t ws_bytes, cudaStream_t st) {
+  const DenseSmall& ds = m->dense;
+  const int n = m->pv.nsta, nd = out.nd;
+  if (!ds.valid || n < 2 || n > 4) return 0;
+  if (nd > 1 && out.cnt[nd - 1] < 48) return 0;       // too few points along the fastest axis to fill a CTA row
+  MeshTiling tl;
+  tl.outer = 1;
+  for (int d = 0; d < nd - 1; ++d) tl.outer *= out.cnt[d];
+  tl.nbx = (out.cnt[nd - 1] + kMeshThreads - 1) / kMeshThreads;
+  // rows per tile: amortise the per-tile sincospi but keep >= ~4 tiles per SM
+  int ti = 8;
+  while (ti > 1 && ((tl.outer + ti - 1) / ti) * tl.nbx < (long long)kNumSM * 4) ti >>= 1;
+  if (tl.outer < ti) ti = (int)tl.outer;
+  tl.ti = ti;
+  tl.ntiles = ((tl.outer + ti - 1) / ti) * tl.nbx;
+  tl.closing_g = ks.closing_g;
+  if (tl.ntiles <= 0) return 1;
+  const int grid = (int)(tl.ntiles < kMeshGridCap ? tl.ntiles : kMeshGridCap);
+  double* partial = nullptr;
+  unsigned* ticket = nullptr;
+  if (gaps_dev) {
+    const size_t need = (size_t)grid * (n - 1) * 8;
+    if (!ws || ws_bytes < need) { set_error("tbk_solve_grid: workspace too small (%zu < %zu)", ws_bytes, need); return TBK_ERR_WORKSPACE; }
+    partial = (double*)ws;
+    ticket = take_ticket();
+    if (!ticket) { set_error("tbk_solve_grid: cannot allocate the reduction tickets"); return TBK_ERR_CUDA; }
+  }
+  const int gauge = (m->pv.convention == 1 && m->pv.dim_k > 0) ? 1 : 0;
+#define TBK_MESH_LAUNCH(NN, PP) \
+  mesh_small_kernel<NN, PP><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev)
+  const bool p4 = ds.nph <= 4;
+  if (n == 2) { if (p4) TBK_MESH_LAUNCH(2, 4); else TBK_MESH_LAUNCH(2, 8); }
+  else if (n == 3) { if (p4) TBK_MESH_LAUNCH(3, 4); else TBK_MESH_LAUNCH(3, 8); }
+  else { if (p4) TBK_MESH_LAUNCH(4, 4); else TBK_MESH_LAUNCH(4, 8); }
+#undef TBK_MESH_LAUNCH
+  TBK_LAUNCH_CHECK("mesh_small_kernel");
+  note_kernel("mesh_small_kernel");
+  return 1;
+}
+
 int tbk_solve_grid(const tbk_model* m, const double* start_k, const int32_t* mesh, int32_t nd, int32_t row0,
                    int32_t nrows, int32_t wrap0, double* wfs_dev, const double* pbc_phase_dev, double* gaps_dev,
                    void* ws_dev, size_t ws_bytes, void* stream) {
   if (!m || !start_k || !mesh || !wfs_dev || !pbc_phase_dev || nd < 1 || nd > TBK_MAX_DIM || nd != m->pv.dim_k ||
-      nrows < 0 || row0 < 0) {
+      nrows < 0 || row0 < 0 || wrap0 < 0 || wrap0 > 2) {
     set_error("tbk_solve_grid: bad argument (nd=%d dim_k=%d)", nd, m ? m->pv.dim_k : -1);
     return TBK_ERR_ARG;
   }
@@ -630,6 +704,7 @@ int tbk_solve_grid(const tbk_model* m, const double* start_k, const int32_t* mes
   KSrc ks;
   memset(&ks, 0, sizeof(ks));
   ks.klist = nullptr; ks.dim_k = nd; ks.row0 = row0;
+  ks.closing_g = wrap0 == 2 ? mesh[0] - 1 : -1;
   OutSpec out;
   memset(&out, 0, sizeof(out));
   out.mode = 1; out.nd = nd;
@@ -640,23 +715,29 @@ int tbk_solve_grid(const tbk_model* m, const double* start_k, const int32_t* mes
     if (mesh[d] < 2) { set_error("tbk_solve_grid: mesh extent must be >= 2"); return TBK_ERR_ARG; }
     ks.start[d] = start_k[d];
     ks.den[d] = (double)(mesh[d] - 1);
-    out.cnt[d] = d == 0 ? nrows : mesh[d] - 1;
+    out.cnt[d] = d == 0 ? nrows + (wrap0 == 2 ? 1 : 0) : mesh[d] - 1;
     out.full[d] = d == 0 ? nrows + 1 : mesh[d];
-    out.wrap[d] = d == 0 ? (wrap0 != 0) : 1;
+    out.wrap[d] = d == 0 ? (wrap0 == 1) : 1;
     npts *= out.cnt[d];
   }
   long long stride = (long long)n * n;
   for (int d = nd - 1; d >= 0; --d) { out.gstride[d] = stride; stride *= out.full[d]; }
   cudaStream_t st = (cudaStream_t)stream;
-  if (gaps_dev && n > 1) {
-    out.gaps_bits = (unsigned long long*)gaps_dev;
-    fill_u64_kernel<<<(n - 1 + 127) / 128, 128, 0, st>>>(out.gaps_bits, n - 1, 0x7FF0000000000000ULL);
-    TBK_LAUNCH_CHECK("fill_u64_kernel");
-  }
   if (n == 1) {
     if (npts > 0) solve_n1_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(m->pv, ks, nullptr, npts, out, 1);
     TBK_LAUNCH_CHECK("solve_n1_kernel");
+    note_kernel("solve_n1_kernel");
     return TBK_OK;
+  }
+  if (npts > 0) {
+    const int took = launch_mesh_small(m, ks, out, gaps_dev, ws_dev, ws_bytes, st);
+    if (took < 0) return took;
+    if (took == 1) return TBK_OK;
+  }
+  if (gaps_dev) {
+    out.gaps_bits = (unsigned long long*)gaps_dev;
+    fill_u64_kernel<<<(n - 1 + 127) / 128, 128, 0, st>>>(out.gaps_bits, n - 1, 0x7FF0000000000000ULL);
+    TBK_LAUNCH_CHECK("fill_u64_kernel");
   }
   return launch_solve(m->pv, ks, nullptr, n, npts, out, 1, ws_dev, ws_bytes, st);
 }

@@ -59,10 +59,38 @@ def _array_phases_cont(arr_pha, clos):
     return ret
 
 
-class wf_array(object):
-    """``wf_array(model, mesh_arr, nsta_arr=None)`` (pythtb.py:2388-2419)."""
+class _Shard(object):
+    """Contiguous slab of the leading mesh axis owned by one rank (one process
+    per GPU).  The N0-1 solved rows are split as evenly as possible; the local
+    array has one extra row that closes the slab: the first row of the next
+    rank, or — on the last rank — the periodic image of global row 0
+    (pythtb.py:2740-2741).  Every plaquette / link along axis 0 then belongs to
+    exactly one rank."""
 
-    def __init__(self, model, mesh_arr, nsta_arr=None):
+    def __init__(self, rank, nranks, n0):
+        rank, nranks, n0 = int(rank), int(nranks), int(n0)
+        if not (0 <= rank < nranks):
+            raise Exception("\n\nshard=(rank, nranks): rank out of range")
+        if n0 - 1 < nranks:
+            raise Exception("\n\nMesh axis 0 has fewer solved rows than ranks.")
+        self.rank, self.nranks, self.n0 = rank, nranks, n0
+        base, rem = divmod(n0 - 1, nranks)
+        self.row0 = rank * base + min(rank, rem)
+        self.nrows = base + (1 if rank < rem else 0)
+        self.is_last = rank == nranks - 1
+
+
+class wf_array(object):
+    """``wf_array(model, mesh_arr, nsta_arr=None)`` (pythtb.py:2388-2419).
+
+    ``shard=(rank, nranks)`` (extension) slices mesh axis 0 over the GPUs of
+    one box, one process per GPU under ``torch.distributed``: this object then
+    holds rows ``[row0, row0+nrows]`` only, ``solve_on_grid`` closes the slab
+    with the neighbour's first row (NCCL ring shift over NVLink, or an in-kernel
+    recomputation for tiny matrices), and ``berry_flux``/``berry_phase``/the
+    gaps are reduced over the ranks so every rank returns the global result."""
+
+    def __init__(self, model, mesh_arr, nsta_arr=None, shard=None, halo="auto"):
         if nsta_arr is None:
             self._nsta_arr = model._nsta
         else:
@@ -77,10 +105,24 @@ class wf_array(object):
         self._dim_arr = len(self._mesh_arr)
         if True in (self._mesh_arr <= 1).tolist():
             raise Exception("\n\nDimension of wf_array object in each direction must be 2 or larger.")
+        self._shard = None
+        if shard is not None:
+            self._shard = _Shard(shard[0], shard[1], self._mesh_arr[0])
+            if self._shard.nranks == 1:
+                self._shard = None
+        if halo not in ("auto", "exchange", "recompute"):
+            raise Exception("\n\nhalo must be 'auto', 'exchange' or 'recompute'")
+        self._halo = halo
         self._store = self._model._engine().new_store(self._wfs_shape(self._nsta_arr))
 
+    def _local_mesh(self):
+        mesh = [int(m) for m in self._mesh_arr]
+        if self._shard is not None:
+            mesh[0] = self._shard.nrows + 1
+        return mesh
+
     def _wfs_shape(self, nsta):
-        shape = [int(m) for m in self._mesh_arr] + [int(nsta), int(self._norb)]
+        shape = self._local_mesh() + [int(nsta), int(self._norb)]
         if self._nspin == 2:
             shape.append(2)
         return tuple(shape)
@@ -125,15 +167,48 @@ class wf_array(object):
         if start.shape[0] != self._dim_arr:
             raise Exception("\n\nk-vector of wrong shape!")
         self._start_k = start_k
-        eng = self._model._engine()
-        gaps = eng.solve_grid(self._model, self._store, self._mesh_arr, start)
+        gaps = self._solve_on_grid_device(start)
         if self._nsta_arr <= 1:
             return None
         return self._gaps_to_host(gaps)
 
+    def _halo_mode(self):
+        """How the row that closes a shard is obtained: 'exchange' = NCCL ring
+        shift of the neighbour's first row; 'recompute' = the solve kernel
+        computes that one extra row itself (bit-identical to the neighbour's,
+        cheaper than a collective's latency when the matrices are tiny)."""
+        if self._halo != "auto":
+            return self._halo
+        return "recompute" if self._model._nsta <= 16 else "exchange"
+
+    def _solve_on_grid_device(self, start, want_gaps=True):
+        """Launch the fused grid solve (and, when sharded, close the slab and
+        reduce the gaps over ranks); results stay engine-resident."""
+        eng = self._model._engine()
+        start = np.array(start, dtype=float).reshape(-1)
+        sh = self._shard
+        if sh is None:
+            return eng.solve_grid(self._model, self._store, self._mesh_arr, start, want_gaps=want_gaps)
+        mode = self._halo_mode()
+        gaps = eng.solve_grid(self._model, self._store, self._mesh_arr, start, row0=sh.row0, nrows=sh.nrows,
+                              wrap0=(2 if mode == "recompute" else 0), want_gaps=want_gaps)
+        if mode == "exchange":
+            # rank r needs the first row of rank r+1; rank 0's row reaches the last
+            # rank multiplied by the pbc phase (pythtb.py:2729, 2740-2741)
+            phase = None
+            if sh.rank == 0:
+                phase = eng.pbc_phases(self._orb, self._nspin, [self._model._per[0]])[0]
+            eng.halo_ring_shift(self._store, self._dim_arr, phase, sh.rank, sh.nranks)
+        if gaps is not None and want_gaps:
+            gaps = eng.allreduce(gaps, "min")
+        return gaps
+
     @staticmethod
     def _gaps_to_host(gaps):
         return gaps if isinstance(gaps, np.ndarray) else gaps.cpu().numpy()
+
+    def _last_solve_kernel(self):
+        return getattr(self._model._engine(), "last_solve_kernel", "?")
 
     def solve_on_one_point(self, kpt, mesh_indices):
         """pythtb.py:2534-2566."""
@@ -231,6 +306,21 @@ class wf_array(object):
         return self._model.position_hwf(self._evec_at(key, occ), dir, hwf_evec, basis)
 
     # ------------------------------------------------------------ Berry phase
+    @staticmethod
+    def _wrap(x):
+        """Back into [-pi, pi): the range of -numpy.angle (pythtb.py:3831)."""
+        return -np.angle(np.exp(-1.0j * np.asarray(x, dtype=float)))
+
+    def _gather_axis0(self, local, axis, with_closing_row):
+        """Concatenate per-rank results along ``axis`` (which indexes mesh axis
+        0).  Every rank contributes its ``nrows`` owned rows; the last rank also
+        the closing row when the result has one entry per mesh point."""
+        sh = self._shard
+        take = sh.nrows + (1 if (with_closing_row and sh.is_last) else 0)
+        local = np.moveaxis(np.asarray(local, dtype=float), axis, 0)[:take]
+        parts = self._model._engine().allgather_rows(np.ascontiguousarray(local), sh.nranks, sh.n0)
+        return np.moveaxis(np.concatenate(parts, axis=0), 0, axis)
+
     def berry_phase(self, occ="All", dir=None, contin=True, berry_evals=False):
         """pythtb.py:2863-3066.  Overlaps, determinants / polar factors, ordered
         products and the unitary eigenvalues run on the GPU for all strings at
@@ -248,6 +338,16 @@ class wf_array(object):
             raise Exception("\n\nWrong dimensionality!")
         eng = self._model._engine()
         ret = eng.berry_strings(self._store, self._dim_arr, occ, dir_use, berry_evals)
+        if self._shard is not None:
+            if dir_use == 0:
+                # a string along axis 0 crosses every rank: det(prod M) = prod det(M), so the
+                # phase is the wrapped sum of the per-rank phases
+                if berry_evals:
+                    raise Exception("\n\nberry_evals=True along the sharded mesh axis needs the ordered product of "
+                                    "link matrices across ranks; use dir != 0 or an unsharded wf_array.")
+                ret = self._wrap(eng.allreduce(np.asarray(ret, dtype=float), "sum"))
+            else:
+                ret = self._gather_axis0(ret, 0, with_closing_row=True)
         if self._dim_arr == 1 and not berry_evals:
             ret = float(np.asarray(ret).reshape(-1)[0])
         else:
@@ -270,9 +370,7 @@ class wf_array(object):
         return ret
 
     # ------------------------------------------------------------- Berry flux
-    def berry_flux(self, occ="All", dirs=None, individual_phases=False):
-        """pythtb.py:3068-3205: plaquette phases / integrated Berry curvature on
-        every 2-D slice spanned by ``dirs``; one fused launch for all plaquettes."""
+    def _check_flux_args(self, occ, dirs):
         occ = self._occ(occ)
         if self._model._assume_position_operator_diagonal == False:  # noqa: E712
             _offdiag_approximation_warning_and_stop()
@@ -284,8 +382,37 @@ class wf_array(object):
             raise Exception("Direction for Berry flux calculation out of bounds.")
         if self._dim_arr not in (2, 3, 4):
             raise Exception("\n\nWrong dimensionality!")
+        return occ, [int(dirs[0]), int(dirs[1])]
+
+    def _berry_flux_device(self, occ, dirs=None, local_only=False):
+        """Total flux per 2-D slice, engine-resident (summed over ranks unless
+        ``local_only``)."""
+        occ, dirs = self._check_flux_args(occ, dirs)
         eng = self._model._engine()
-        res = eng.flux(self._store, self._dim_arr, occ, [int(dirs[0]), int(dirs[1])], individual_phases)
+        tot = eng.flux_total(self._store, self._dim_arr, occ, dirs)
+        if self._shard is not None and not local_only and 0 in dirs:
+            tot = eng.allreduce(tot, "sum")
+        return tot
+
+    def berry_flux(self, occ="All", dirs=None, individual_phases=False):
+        """pythtb.py:3068-3205: plaquette phases / integrated Berry curvature on
+        every 2-D slice spanned by ``dirs``; one fused launch for all plaquettes."""
+        occ, dirs = self._check_flux_args(occ, dirs)
+        eng = self._model._engine()
+        sh = self._shard
+        if not individual_phases and (sh is None or 0 in dirs):
+            res = self._berry_flux_device(occ, dirs)
+            res = res if isinstance(res, np.ndarray) else res.cpu().numpy()
+            rest = [d for d in range(self._dim_arr) if d not in dirs]
+            res = res.reshape(tuple(int(self._mesh_arr[d]) for d in rest))
+        else:
+            res = eng.flux(self._store, self._dim_arr, occ, dirs, individual_phases)
+            if sh is not None:
+                rest = [d for d in range(self._dim_arr) if d not in dirs]
+                if 0 in dirs:        # plaquette rows along mesh axis 0: all local ones are owned
+                    res = self._gather_axis0(res, len(rest) + dirs.index(0), with_closing_row=False)
+                else:                # mesh axis 0 labels the slices
+                    res = self._gather_axis0(res, rest.index(0), with_closing_row=True)
         if self._dim_arr == 2 and not individual_phases:
-            return np.float64(res.reshape(-1)[0])
+            return np.float64(np.asarray(res).reshape(-1)[0])
         return res

@@ -53,10 +53,52 @@ class OracleEngine(object):
     def pbc_phases(self, orb, nspin, k_dirs):
         return np.array([np.repeat(np.exp(-2.0j * np.pi * np.asarray(orb)[:, kd]), nspin) for kd in k_dirs])
 
-    def solve_grid(self, model, store, mesh_arr, start_k, row0=0, nrows=None, wrap0=True):
-        wfs, gaps = orc.solve_on_grid(model, mesh_arr, start_k)
-        store.arr[...] = wfs
-        return gaps
+    def solve_grid(self, model, store, mesh_arr, start_k, row0=0, nrows=None, wrap0=1, want_gaps=True):
+        """Same contract as B200Engine.solve_grid: fills the local rows
+        [row0, row0+nrows] of a shard (the closing row only for wrap0 in (1, 2))."""
+        wfs, _ = orc.solve_on_grid(model, mesh_arr, start_k)
+        n0 = int(mesh_arr[0])
+        if nrows is None:
+            nrows = n0 - 1
+        store.arr[:nrows] = wfs[row0:row0 + nrows]
+        if wrap0 in (1, 2, True):
+            store.arr[nrows] = wfs[row0 + nrows]
+        if model._nsta <= 1 or not want_gaps:
+            return None
+        # minimal gaps over the rows solved here only (so that the cross-rank min is exercised)
+        kpts = orc.grid_kpoints(start_k, mesh_arr).reshape(tuple(np.asarray(mesh_arr) - 1) + (len(mesh_arr),))
+        ev = orc.sol_ham(orc.gen_ham(model, kpts[row0:row0 + nrows].reshape(-1, len(mesh_arr))), False)
+        return (ev[:, 1:] - ev[:, :-1]).min(axis=0)
+
+    # ---- multi-rank plumbing over torch.distributed (gloo on CPU in the tests)
+    def halo_ring_shift(self, store, dim_arr, phase, rank, nranks):
+        import torch
+        import torch.distributed as dist
+        row = np.array(store.arr[0], copy=True)
+        if phase is not None:
+            row = row * np.asarray(phase).reshape(store.arr.shape[dim_arr + 1:])
+        send = torch.from_numpy(np.ascontiguousarray(row).view(np.float64))
+        recv = torch.empty_like(send)
+        reqs = [dist.isend(send, (rank - 1) % nranks), dist.irecv(recv, (rank + 1) % nranks)]
+        for r in reqs:
+            r.wait()
+        store.arr[-1] = recv.numpy().view(np.complex128).reshape(store.arr.shape[1:])
+
+    def allreduce(self, x, op):
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(np.array(x, dtype=np.float64, copy=True).reshape(-1))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MIN)
+        return t.numpy().reshape(np.shape(x))
+
+    def allgather_rows(self, local, nranks, n0):
+        import torch.distributed as dist
+        parts = [None] * nranks
+        dist.all_gather_object(parts, np.asarray(local))
+        return parts
+
+    def flux_total(self, store, dim_arr, occ, dirs):
+        return np.asarray(orc.berry_flux(store.arr, dim_arr, occ, dirs, individual_phases=False)).reshape(-1)
 
     def impose_boundary(self, store, dim_arr, mesh_dir, phase):
         if phase is None:

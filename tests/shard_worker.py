@@ -1,0 +1,66 @@
+"""Worker of tests/test_sharded_gloo.py: one rank of a world_size-N gloo group.
+Drives the product's host-side sharding logic (pythtb_b200.wfarray) with the
+numpy oracle engine and compares every global result with the unsharded one."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch.distributed as dist
+    from tests import models as M, oracle_api as api, compare
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        for halo in ("exchange", "recompute"):
+            for model, occ, mesh in ((M.haldane(api, 0.0), [0], [14, 9]), (M.kane_mele(api, "odd"), [0, 1], [9, 8])):
+                full = api.wf_array(model, mesh)
+                gaps_ref = full.solve_on_grid([-0.5, -0.5])
+                w = api.wf_array(model, mesh, shard=(rank, world), halo=halo)
+                gaps = w.solve_on_grid([-0.5, -0.5])
+                assert np.max(np.abs(gaps - gaps_ref)) < 1e-12, (gaps, gaps_ref)
+                sh = w._shard
+                # the local slab equals the corresponding rows of the unsharded array
+                assert np.max(np.abs(w._wfs - full._wfs[sh.row0:sh.row0 + sh.nrows + 1])) < 1e-12
+                for dirs in (None, [1, 0]):
+                    f_ref = full.berry_flux(occ, dirs)
+                    f = w.berry_flux(occ, dirs)
+                    assert abs(f - f_ref) < 1e-10, (f, f_ref)
+                    p_ref = full.berry_flux(occ, dirs, individual_phases=True)
+                    p = w.berry_flux(occ, dirs, individual_phases=True)
+                    assert p.shape == p_ref.shape
+                    assert np.max(np.abs(compare.circ_diff(p, p_ref, 2 * np.pi))) < 1e-10
+                for d in (0, 1):
+                    b_ref = full.berry_phase(occ, d, contin=False)
+                    b = w.berry_phase(occ, d, contin=False)
+                    assert b.shape == b_ref.shape, (b.shape, b_ref.shape)
+                    assert np.max(np.abs(compare.circ_diff(b, b_ref, 2 * np.pi))) < 1e-10
+                bc_ref = full.berry_phase(occ, 1, contin=True)
+                bc = w.berry_phase(occ, 1, contin=True)
+                assert np.max(np.abs(compare.circ_diff(bc, bc_ref, 2 * np.pi))) < 1e-10
+                if len(occ) > 1:
+                    e_ref = full.berry_phase(occ, 1, contin=False, berry_evals=True)
+                    e = w.berry_phase(occ, 1, contin=False, berry_evals=True)
+                    assert np.max(np.abs(compare.circ_diff(e, e_ref, 2 * np.pi))) < 1e-10
+        # 3-D mesh: axis 0 sharded, flux on planes that do / do not contain it
+        m3 = M.random_model(api, norb=2, dim=3, nhop=6, nspin=1, seed=5)
+        full = api.wf_array(m3, [7, 5, 6])
+        full.solve_on_grid([0.0, 0.1, 0.2])
+        w = api.wf_array(m3, [7, 5, 6], shard=(rank, world), halo="exchange")
+        w.solve_on_grid([0.0, 0.1, 0.2])
+        for dirs in ([0, 1], [1, 2], [2, 0]):
+            for ind in (False, True):
+                a, b = full.berry_flux([0], dirs, ind), w.berry_flux([0], dirs, ind)
+                assert np.shape(a) == np.shape(b), (dirs, ind, np.shape(a), np.shape(b))
+                assert np.max(np.abs(compare.circ_diff(np.asarray(b), np.asarray(a), 2 * np.pi))) < 1e-10
+        print("rank %d ok" % rank)
+    finally:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -171,3 +171,82 @@ def test_edge_cases():
         mod.wf_array(M.haldane(mod), [5]).solve_on_grid([0.0])       # dim mismatch
     empty = M.haldane(mod).solve_all(np.zeros((0, 2)))               # empty k list
     assert empty.shape == (2, 0)
+
+
+def _band_projectors(wfs, nsta):
+    """Gauge-invariant per-band projectors |u><u| of a _wfs array [..., band, orb(,spin)]."""
+    v = wfs.reshape((-1, nsta, nsta))
+    return np.einsum("kbi,kbj->kbij", v, v.conj())
+
+
+@pytest.mark.parametrize("spec,mesh", [
+    (dict(norb=2, dim=1, nhop=3, nspin=1, seed=41), [203]),            # 1-D mesh, n=2
+    (dict(norb=3, dim=2, nhop=5, nspin=1, seed=42), [6, 131]),          # n=3, NPH<=4? (random) / Jacobi
+    (dict(norb=2, dim=2, nhop=7, nspin=2, seed=43), [5, 70]),           # spinor n=4, nph up to 8
+    (dict(norb=2, dim=3, nhop=4, nspin=1, seed=44), [4, 5, 66]),        # 3-D mesh
+    (dict(norb=4, dim=2, nhop=4, nspin=1, seed=45), [9, 50]),           # n=4 scalar
+    (dict(norb=2, dim=2, nhop=16, nspin=1, seed=46), [5, 64]),          # nph > 8 -> generic kernel
+    (dict(norb=2, dim=2, nhop=4, nspin=1, seed=47), [70, 5]),           # short fastest axis -> generic kernel
+])
+def test_mesh_kernels_against_oracle(spec, mesh):
+    """wf_array.solve_on_grid through every mesh kernel variant: gaps, per-band
+    projectors at every mesh point (incl. periodic images), plaquette phases."""
+    from oracle import pythtb_oracle as orc
+    mod = _mod()
+    m = M.random_model(mod, **spec)
+    start = [0.13, -0.27, 0.4][:len(mesh)]
+    w = mod.wf_array(m, mesh)
+    gaps = w.solve_on_grid(start)
+    wfs_ref, gaps_ref = orc.solve_on_grid(m, mesh, start)
+    assert np.max(np.abs(gaps - gaps_ref)) < 1e-10
+    wfs = np.array(w._wfs)
+    assert wfs.shape == wfs_ref.shape
+    n = m._nsta
+    if np.min(gaps_ref) > 1e-3:      # projectors are only defined for non-degenerate bands
+        pa, pb = _band_projectors(wfs, n), _band_projectors(wfs_ref, n)
+        assert np.max(np.abs(pa - pb)) < 1e-9
+    if len(mesh) >= 2:
+        got = w.berry_flux([0], individual_phases=True)
+        ref = orc.berry_flux(wfs_ref, len(mesh), [0], None, True)
+        assert np.max(np.abs(compare.circ_diff(got, ref, 2 * np.pi))) < 1e-8
+        assert abs(compare.circ_diff(np.sum(w.berry_flux([0])), ref.sum(), 2 * np.pi)) < 1e-7
+    else:
+        got = w.berry_phase([0])
+        ref = orc.berry_phase(wfs_ref, 1, [0])
+        assert abs(compare.circ_diff(got, ref, 2 * np.pi)) < 1e-8
+
+
+@pytest.mark.parametrize("which", ["haldane", "kane_mele", "random7"])
+def test_shard_slabs_bit_identical(which):
+    """Multi-GPU slabs emulated on one GPU: solving rows [row0, row0+nrows] with the
+    closing row recomputed in-launch (wrap0=2) gives exactly the rows of the unsharded array."""
+    mod = _mod()
+    from pythtb_b200 import _engine
+    eng = _engine.get_engine()
+    if which == "haldane":
+        m, mesh = M.haldane(mod, 0.0), [41, 130]
+    elif which == "kane_mele":
+        m, mesh = M.kane_mele(mod, "odd"), [23, 67]
+    else:
+        m, mesh = M.random_model(mod, norb=7, dim=2, nhop=12, nspin=1, seed=3), [13, 9]
+    full = mod.wf_array(m, mesh)
+    gaps_full = full.solve_on_grid([-0.5, -0.5])
+    ref = np.array(full._wfs)
+    world = 3
+    gaps_min = None
+    for rank in range(world):
+        w = mod.wf_array(m, mesh, shard=(rank, world), halo="recompute")
+        sh = w._shard
+        g = eng.solve_grid(w._model, w._store, w._mesh_arr, np.array([-0.5, -0.5]), row0=sh.row0, nrows=sh.nrows, wrap0=2)
+        g = g.cpu().numpy()
+        gaps_min = g if gaps_min is None else np.minimum(gaps_min, g)
+        got = np.array(w._wfs)
+        assert got.shape[0] == sh.nrows + 1
+        assert np.array_equal(got, ref[sh.row0:sh.row0 + sh.nrows + 1]), (which, rank)
+        # halo-exchange variant: the closing row is left untouched by the launch
+        w2 = mod.wf_array(m, mesh, shard=(rank, world), halo="exchange")
+        eng.solve_grid(w2._model, w2._store, w2._mesh_arr, np.array([-0.5, -0.5]), row0=sh.row0, nrows=sh.nrows, wrap0=0)
+        got2 = np.array(w2._wfs)
+        assert np.array_equal(got2[:-1], ref[sh.row0:sh.row0 + sh.nrows])
+        assert np.all(got2[-1] == 0)
+    assert np.array_equal(gaps_min, gaps_full)
