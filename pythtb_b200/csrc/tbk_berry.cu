@@ -112,14 +112,21 @@ flux_small_kernel(WfView v, const long long* __restrict__ slice_off, long long n
 // d=(i,j+1) and L(x,y) = det <x|y>,
 //     phase(i,j) = -arg[ L(a,b) L(b,c) L(c,d) L(d,a) ]
 // and L(c,d) = conj(V(i,j+1)), L(d,a) = conj(H(i,j)) where V(i,j) = L((i,j),(i+1,j)) is the
-// vertical and H(i,j) = L((i,j),(i,j+1)) the horizontal link.  A CTA owns 127 plaquette
-// columns and marches down `ti` rows: thread t computes V(i, col0+t) (128 of them, shared through
-// smem) and H(i+1, col) which it keeps in a register for the next row, so each plaquette costs
-// two link determinants and each occupied state is fetched from HBM once per tile row.
-// The plane sum is finished by the last CTA (ticket) in a fixed order: one launch, deterministic.
+// vertical and H(i,j) = L((i,j),(i,j+1)) the horizontal link.  A WARP owns 31 plaquette columns
+// and marches down `ti` rows: lane t computes V(i, col0+t) (32 of them; the right neighbour's comes
+// by shuffle) and H(i+1, col), which it keeps in a register for the next row, so each plaquette
+// costs two link determinants, there is no block barrier in the row loop, and the loads of row
+// i+2 are in flight while row i+1 is being reduced.
+// When only the plane sum is wanted, plaquettes whose loop product z has Re z > 1/2 and
+// Re z > 8 |Im z| (|arg z| < 0.125) are multiplied together — at most 24 per product, so
+// |sum of args| < pi and arg(prod) = sum(arg) exactly — and ONE atan2 is taken per thread per tile;
+// any other plaquette gets its own atan2.  The plane sum is finished by the last CTA (ticket) in a
+// fixed order: one launch, deterministic.
 // ---------------------------------------------------------------------------
 constexpr int kFluxThreads = 128;
-constexpr int kFluxCols = kFluxThreads - 1;
+constexpr int kFluxWarpCols = 31;
+constexpr int kFluxCols = kFluxWarpCols * (kFluxThreads / 32);
+constexpr int kFluxMaxRows = 24;
 
 struct FluxTiling {
   int ti;                 // plaquette rows per tile
@@ -127,15 +134,28 @@ struct FluxTiling {
   long long ntiles;       // nslice * nrb * nbx
 };
 
-static FluxTiling flux_tiling(long long nslice, long long n0, long long n1) {
+// One balanced wave: as many tiles as CTAs can be resident (`resident` = #SM x CTAs per SM), all of
+// (nearly) the same height; more column blocks than resident CTAs -> full-height tiles, grid-stride.
+static FluxTiling flux_tiling(long long nslice, long long n0, long long n1, long long resident) {
   FluxTiling t;
   t.nbx = (n1 - 1 + kFluxCols - 1) / kFluxCols;
-  int ti = 32;
-  while (ti > 1 && nslice * ((n0 - 1 + ti - 1) / ti) * t.nbx < (long long)kNumSM * 4) ti >>= 1;
-  t.ti = ti;
-  t.nrb = (n0 - 1 + ti - 1) / ti;
+  const long long p0 = n0 - 1;
+  long long per_col = resident / (nslice * t.nbx);       // tiles per column block
+  if (per_col < 1) per_col = 1;
+  if (per_col > p0) per_col = p0;
+  long long ti = (p0 + per_col - 1) / per_col;
+  if (ti < 4 && p0 >= 4) ti = 4;                          // keep the per-tile first-row loads amortised
+  t.ti = (int)ti;
+  t.nrb = (p0 + ti - 1) / ti;
   t.ntiles = nslice * t.nrb * t.nbx;
   return t;
+}
+// upper bound of ntiles over every `resident` the launcher may use (workspace sizing)
+static long long flux_tiles_bound(long long nslice, long long n0, long long n1) {
+  const long long nbx = (n1 - 1 + kFluxCols - 1) / kFluxCols;
+  const long long a = nslice * nbx * ((n0 - 1 + 3) / 4 + 3);
+  const long long b = (long long)kNumSM * 16 + nslice * nbx;
+  return a < b ? a : b;
 }
 
 template <int NOCC, int N>
@@ -144,7 +164,7 @@ struct OccState {
   __device__ __forceinline__ void load(const cplx* __restrict__ p, const int* occ) {
 #pragma unroll
     for (int m = 0; m < NOCC; ++m) {
-      const double2* src = reinterpret_cast<const double2*>(p + (long long)occ[m] * N);
+      const double2* src = reinterpret_cast<const double2*>(p + occ[m] * N);
 #pragma unroll
       for (int o = 0; o < N; ++o) { const double2 t = __ldg(src + o); u[m][o] = mk(t.x, t.y); }
     }
@@ -168,66 +188,95 @@ __device__ __forceinline__ cplx link_det(const OccState<NOCC, N>& a, const OccSt
   else return M[0][0] * M[1][1] - M[0][1] * M[1][0];
 }
 
-template <int NOCC, int N>
+template <int NOCC, int N, bool WANT_PLAQ>
 __global__ void __launch_bounds__(kFluxThreads)
 flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0, long long stride0, long long n1,
                  long long stride1, FluxTiling tl, long long nslice, double* __restrict__ plaq,
                  double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ total) {
-  __shared__ cplx s_v[2][kFluxThreads];
   __shared__ double s_red[kFluxThreads / 32];
-  __shared__ int s_occ[NOCC];
   __shared__ int s_last;
-  const int tid = threadIdx.x;
-  if (tid < NOCC) s_occ[tid] = v.occ[tid];
-  __syncthreads();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int occ[NOCC];
+#pragma unroll
+  for (int m = 0; m < NOCC; ++m) occ[m] = v.occ[m];
   const long long p0 = n0 - 1, p1 = n1 - 1;
   for (long long tile = blockIdx.x; tile < tl.ntiles; tile += gridDim.x) {
     const long long s = tile / (tl.nrb * tl.nbx);
     const long long rem = tile - s * tl.nrb * tl.nbx;
     const long long rb = rem / tl.nbx, bx = rem - rb * tl.nbx;
-    const long long col = bx * kFluxCols + tid;            // mesh column of this thread's vertical link
+    const long long col = bx * kFluxCols + warp * kFluxWarpCols + lane;   // mesh column of this lane's vertical link
     const bool has_col = col < n1;
-    const bool owner = tid < kFluxCols && col < p1;        // owns plaquette column `col`
+    const bool owner = lane < kFluxWarpCols && col < p1;                  // owns plaquette column `col`
     const long long i0 = rb * tl.ti;
-    const long long i1 = (i0 + tl.ti < p0) ? i0 + tl.ti : p0;
-    const cplx* base = v.wfs + slice_off[s] + col * stride1;
-    OccState<NOCC, N> a, b, c;
+    const int nrow = (int)((i0 + tl.ti < p0 ? i0 + tl.ti : p0) - i0);
+    const cplx* pa = v.wfs + slice_off[s] + col * stride1 + i0 * stride0;  // u(i0, col)
+    // Register rotation instead of copies: (s0,s1,s2) take the roles (a, b, prefetch of next b) and
+    // (c0,c1) the roles (c, prefetch of next c); the roles advance every row, period 6.
+    OccState<NOCC, N> s0, s1, s2, c0, c1;
     cplx hda = mk(1.0, 0.0);                               // L(d,a) = conj(H(i,col))
-    if (has_col) a.load(base + i0 * stride0, s_occ);
+    if (has_col) { s0.load(pa, occ); s1.load(pa + stride0, occ); }
     if (owner) {
-      c.load(base + i0 * stride0 + stride1, s_occ);        // d of the first row
-      hda = conj(link_det<NOCC, N>(a, c));
+      c1.load(pa + stride1, occ);                          // d of the first row
+      hda = conj(link_det<NOCC, N>(s0, c1));
+      c0.load(pa + stride0 + stride1, occ);
     }
     double acc = 0.0;
-    for (long long i = i0; i < i1; ++i) {
-      const int buf = (int)(i & 1);
-      cplx lab = mk(0.0, 0.0);
-      if (has_col) {
-        b.load(base + (i + 1) * stride0, s_occ);
-        lab = link_det<NOCC, N>(a, b);                     // V(i, col)
-      }
-      s_v[buf][tid] = lab;
-      __syncthreads();
-      if (owner) {
-        c.load(base + (i + 1) * stride0 + stride1, s_occ);
-        const cplx lbc = link_det<NOCC, N>(b, c);          // H(i+1, col)
-        cplx prod = lab * lbc;
-        prod = mulc(prod, s_v[buf][tid + 1]);              // L(c,d) = conj(V(i, col+1))
-        prod = prod * hda;
-        const double phase = neg_arg(prod);
-        if (plaq) plaq[(s * p0 + i) * p1 + col] = phase;
-        acc += phase;
-        hda = conj(lbc);
-      }
-      a = b;
+    cplx prod = mk(1.0, 0.0);
+    double* pq = WANT_PLAQ ? plaq + (s * p0 + i0) * p1 + col : nullptr;
+    int r = 0;
+#define TBK_FLUX_STEP(A, B, BN, C, CN)                                                            \
+    {                                                                                             \
+      if (r >= nrow) break;                                                                       \
+      pa += stride0;                                       /* now u(i0+r+1, col) */               \
+      if (r + 1 < nrow) {                                  /* prefetch the next row */            \
+        if (has_col) BN.load(pa + stride0, occ);                                                  \
+        if (owner) CN.load(pa + stride0 + stride1, occ);                                          \
+      }                                                                                           \
+      cplx lab = mk(0.0, 0.0);                                                                    \
+      if (has_col) lab = link_det<NOCC, N>(A, B);          /* V(i, col) */                        \
+      cplx right;                                          /* V(i, col+1) from the next lane */   \
+      right.re = __shfl_down_sync(0xffffffffu, lab.re, 1);                                        \
+      right.im = __shfl_down_sync(0xffffffffu, lab.im, 1);                                        \
+      if (owner) {                                                                                \
+        const cplx lbc = link_det<NOCC, N>(B, C);          /* H(i+1, col) */                      \
+        cplx z = lab * lbc;                                                                       \
+        z = mulc(z, right);                                /* L(c,d) = conj(V(i, col+1)) */       \
+        z = z * hda;                                                                              \
+        hda = conj(lbc);                                                                          \
+        if (WANT_PLAQ) {                                                                          \
+          const double phase = neg_arg(z);                                                        \
+          pq[0] = phase;                                                                          \
+          pq += p1;                                                                               \
+          acc += phase;                                                                           \
+        } else if (z.re > 0.5 && z.re > 8.0 * fabs(z.im)) {                                       \
+          prod = prod * z;                                                                        \
+        } else {                                                                                  \
+          acc += neg_arg(z);                                                                      \
+        }                                                                                         \
+      }                                                                                           \
+      ++r;                                                                                        \
     }
+    for (;;) {
+      TBK_FLUX_STEP(s0, s1, s2, c0, c1)
+      TBK_FLUX_STEP(s1, s2, s0, c1, c0)
+      TBK_FLUX_STEP(s2, s0, s1, c0, c1)
+      TBK_FLUX_STEP(s0, s1, s2, c1, c0)
+      TBK_FLUX_STEP(s1, s2, s0, c0, c1)
+      TBK_FLUX_STEP(s2, s0, s1, c1, c0)
+      if (!WANT_PLAQ && (r % 24) == 0) {                   // at most 24 small angles per product
+        if (owner) acc += neg_arg(prod);
+        prod = mk(1.0, 0.0);
+      }
+    }
+#undef TBK_FLUX_STEP
+    if (!WANT_PLAQ && owner) acc += neg_arg(prod);
     if (partial) {
       // fixed-order CTA sum -> partial[tile]
       double x = acc;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
       __syncthreads();
-      if ((tid & 31) == 0) s_red[tid >> 5] = x;
+      if (lane == 0) s_red[warp] = x;
       __syncthreads();
       if (tid == 0) {
         double t = 0.0;
@@ -235,7 +284,6 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
         partial[tile] = t;
       }
     }
-    __syncthreads();
   }
   if (!partial) return;
   __threadfence();
@@ -251,7 +299,7 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
     __syncthreads();
-    if ((tid & 31) == 0) s_red[tid >> 5] = x;
+    if (lane == 0) s_red[warp] = x;
     __syncthreads();
     if (tid == 0) {
       double t = 0.0;
@@ -264,15 +312,28 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
 template <int NOCC, int N>
 static int launch_flux_rows(const WfView& v, const long long* off, long long nslice, long long n0, long long stride0,
                             long long n1, long long stride1, double* plaq, double* total, double* partial, cudaStream_t st) {
-  const FluxTiling tl = flux_tiling(nslice, n0, n1);
+  static int occ_plaq = 0, occ_sum = 0;                   // resident CTAs per SM of the two variants
+  if (occ_plaq == 0) {
+    int a = 0, b = 0;
+    TBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, flux_rows_kernel<NOCC, N, true>, kFluxThreads, 0));
+    TBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, flux_rows_kernel<NOCC, N, false>, kFluxThreads, 0));
+    occ_sum = b > 0 ? (b > 16 ? 16 : b) : 1;
+    occ_plaq = a > 0 ? (a > 16 ? 16 : a) : 1;
+  }
+  const long long resident = (long long)kNumSM * (plaq ? occ_plaq : occ_sum);
+  const FluxTiling tl = flux_tiling(nslice, n0, n1, resident);
   unsigned* ticket = nullptr;
   if (total) {
     ticket = take_ticket();
     if (!ticket) { set_error("tbk_flux_plane: cannot allocate the reduction tickets"); return TBK_ERR_CUDA; }
   }
-  const int grid = (int)(tl.ntiles < (long long)kNumSM * 8 ? tl.ntiles : (long long)kNumSM * 8);
-  flux_rows_kernel<NOCC, N><<<grid, kFluxThreads, 0, st>>>(v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
-                                                          total ? partial : nullptr, ticket, total);
+  const int grid = (int)(tl.ntiles < resident ? tl.ntiles : resident);
+  if (plaq)
+    flux_rows_kernel<NOCC, N, true><<<grid, kFluxThreads, 0, st>>>(v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
+                                                                  total ? partial : nullptr, ticket, total);
+  else
+    flux_rows_kernel<NOCC, N, false><<<grid, kFluxThreads, 0, st>>>(v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
+                                                                   partial, ticket, total);
   TBK_LAUNCH_CHECK("flux_rows_kernel");
   return TBK_OK;
 }
@@ -602,7 +663,7 @@ size_t tbk_flux_workspace(int32_t nocc, int32_t n, int64_t nslice, int64_t n0, i
   (void)n;
   const long long bx = (n1 - 1 + 255) / 256;
   size_t bytes = align256((size_t)(nslice * (n0 - 1) * (bx > 0 ? bx : 1)) * 8);   // block partial sums
-  bytes += align256((size_t)flux_tiling(nslice, n0, n1).ntiles * 8);
+  bytes += align256((size_t)flux_tiles_bound(nslice, n0, n1) * 8);
   if (nocc > 4) {
     const long long nlinks = nslice * ((n0 - 1) * n1 + n0 * (n1 - 1));
     bytes += align256((size_t)nlinks * 16);

@@ -33,7 +33,11 @@ TBK_HD void eigh2(double h00, double h11, cplx h10, double ev[2], cplx w[2][2], 
   }
   // cancellation-free choice of the two null-vector formulas
   const double big = fabs(delta) + r;                  // |delta| + r > 0
+#if defined(__CUDA_ARCH__)
+  const double inv = rsqrt(b2 + big * big);
+#else
   const double inv = 1.0 / sqrt(b2 + big * big);
+#endif
   if (delta >= 0.0) {
     w[0][0] = inv * b;        w[0][1] = mk(-big * inv, 0.0);   // lower band
     w[1][0] = mk(big * inv, 0.0); w[1][1] = inv * conj(b);     // upper band
@@ -85,26 +89,35 @@ struct JacobiPacked {
       for (int p = 0; p < N - 1; ++p) {
 #pragma unroll
         for (int q = p + 1; q < N; ++q) {
-          const cplx apq = conj(lo[idx(q, p)]);       // H[p][q]
+          const cplx apq = conj(lo[idx(q, p)]);       // H[p][q] = g e^{i phi}
           const double g2 = norm2(apq);
           if (g2 > 1.0e-300) {
-            const double g = sqrt(g2);
-            const cplx ph = mk(apq.re / g, apq.im / g);   // e^{i phi}
-            const double theta = (dg[q] - dg[p]) / (2.0 * g);
-            const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
-            const double c = 1.0 / sqrt(fma(t, t, 1.0));
-            const double s = t * c;
-            dg[p] -= t * g;
-            dg[q] += t * g;
+            // Rotation J = [[c, s e^{i phi}], [-s e^{-i phi}, c]] with t = tan(theta) the smaller root of
+            // t^2 + 2 tau t - 1 = 0, tau = (d_q - d_p) / (2 g).  Written without normalising apq:
+            //   big = |delta| + sqrt(delta^2 + g^2), delta = (d_q - d_p)/2
+            //   t g = sgn(delta) g^2 / big,  c = big / sqrt(big^2 + g^2),  s e^{-i phi} = sgn(delta) conj(apq) / sqrt(big^2 + g^2)
+            // (one sqrt, one rsqrt, one division per rotation).
+            const double delta = 0.5 * (dg[q] - dg[p]);
+            const double big = fabs(delta) + sqrt(fma(delta, delta, g2));
+            const double sgn = delta >= 0.0 ? 1.0 : -1.0;
+            const double tg = sgn * (g2 / big);
+#if defined(__CUDA_ARCH__)
+            const double rs = rsqrt(fma(big, big, g2));
+#else
+            const double rs = 1.0 / sqrt(fma(big, big, g2));
+#endif
+            const double c = big * rs;
+            const cplx se = (sgn * rs) * conj(apq);    // s e^{-i phi}
+            const cplx sc = conj(se);                  // s e^{+i phi}
+            dg[p] -= tg;
+            dg[q] += tg;
             lo[idx(q, p)] = mk(0.0, 0.0);
-            const cplx se = s * conj(ph);              // s e^{-i phi}
-            const cplx ce = c * conj(ph);              // c e^{-i phi}
 #pragma unroll
             for (int r = 0; r < N; ++r) {
               if (r != p && r != q) {
                 const cplx arp = get(lo, r, p), arq = get(lo, r, q);
                 set(lo, r, p, c * arp - arq * se);
-                set(lo, r, q, s * arp + arq * ce);
+                set(lo, r, q, arp * sc + c * arq);
               }
             }
             if (want_vec) {
@@ -112,7 +125,7 @@ struct JacobiPacked {
               for (int o = 0; o < N; ++o) {
                 const cplx vp = w[p][o], vq = w[q][o];
                 w[p][o] = c * vp - vq * se;
-                w[q][o] = s * vp + vq * ce;
+                w[q][o] = vp * sc + c * vq;
               }
             }
           }

@@ -24,15 +24,55 @@ constexpr int kMeshThreads = 128;
 constexpr int kMeshMaxRows = 16;
 
 struct MeshTiling {
-  int ti;               // outer indices per tile
-  int nbx;              // tiles along the last axis
-  long long outer;      // product of cnt[d], d < nd-1
-  long long ntiles;
+  int nbx;              // 128-wide column blocks along the last axis
+  int outer;            // product of cnt[d], d < nd-1  ("rows")
+  unsigned nseg;        // outer * nbx row segments (< 2^31, checked by the launcher), column block major
   int closing_g;        // global axis-0 index that is the periodic image of row 0 (wrap0 == 2), else -1
 };
 
-template <int N, int NPH>
-__global__ void __launch_bounds__(kMeshThreads)
+template <int N>
+struct EigRows {
+  cplx w[N][N];
+};
+
+// periodic images of one mesh point (pythtb.py:2729-2747): every subset of the axes on which the
+// point sits at index 0; one multiply per wrapped axis, in axis order (so that a shard's closing row
+// and the unsharded image agree bit for bit).  Cold path: kept out of line.
+template <int N>
+__device__ __noinline__ void mesh_store_images(const EigRows<N>& e, const OutSpec& out, long long base, int zero_mask) {
+  const int nd = out.nd;
+  for (int m = 1; m < (1 << nd); ++m) {
+    if ((m & zero_mask) != m) continue;
+    long long off = base;
+    cplx im[N][N];
+#pragma unroll
+    for (int b = 0; b < N; ++b)
+#pragma unroll
+      for (int o = 0; o < N; ++o) im[b][o] = e.w[b][o];
+    for (int d = 0; d < nd; ++d) {
+      if (m & (1 << d)) {
+        off += (long long)(out.full[d] - 1) * out.gstride[d];
+#pragma unroll
+        for (int o = 0; o < N; ++o) {
+          const cplx ph = out.pbc_phase[d * N + o];
+#pragma unroll
+          for (int b = 0; b < N; ++b) im[b][o] = im[b][o] * ph;
+        }
+      }
+    }
+    cplx* dsti = out.evec + off;
+#pragma unroll
+    for (int b = 0; b < N; ++b)
+#pragma unroll
+      for (int o = 0; o < N; ++o) dsti[b * N + o] = im[b][o];
+  }
+}
+
+// Persistent kernel: the grid is one balanced wave (#SM x resident CTAs); CTA c owns the row
+// segments [c*nseg/G, (c+1)*nseg/G) — a contiguous run of rows inside one column block (two at a
+// block boundary), processed in chunks of <= kMeshMaxRows rows.
+template <int N, int NPH, int MINB>
+__global__ void __launch_bounds__(kMeshThreads, MINB)
 mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__ KSrc ks,
                   const __grid_constant__ OutSpec out, const __grid_constant__ MeshTiling tl, int gauge,
                   double* __restrict__ gap_partial, unsigned* __restrict__ ticket, double* __restrict__ gaps_out) {
@@ -40,89 +80,106 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
   constexpr int NQ = NPH + N;                       // phases, then per-state gauge factors
   __shared__ cplx s_out[kMeshMaxRows][NQ];
   __shared__ long long s_base[kMeshMaxRows];
-  __shared__ int s_flags[kMeshMaxRows];             // bits 0..3 zero_mask, bit 8 closing row, bit 9 valid
+  __shared__ int s_flags[kMeshMaxRows];             // bits 0..3 zero_mask, bit 8 closing row
   __shared__ double s_red[kMeshThreads / 32][N];
+  __shared__ cplx s_pbc0[N];                        // pbc phase of axis 0 (closing rows of a shard)
   __shared__ int s_last;
+  if (threadIdx.x < N) s_pbc0[threadIdx.x] = tl.closing_g >= 0 ? out.pbc_phase[threadIdx.x] : mk(1.0, 0.0);
   const int nd = out.nd;
   const int last = nd - 1;
-  const int nph = ds.nph;
+  const int nph = ds.nph;   // phases p >= nph are zero-padded in the table: they contribute exactly 0
   const int tid = threadIdx.x;
   double gmin[N - 1];
 #pragma unroll
   for (int b = 0; b < N - 1; ++b) gmin[b] = INFINITY;
 
-  for (long long tile = blockIdx.x; tile < tl.ntiles; tile += gridDim.x) {
-    const long long by = tile / tl.nbx;
-    const int bx = (int)(tile - by * tl.nbx);
-    // ---- per-row (outer index) factors, one (row, q) pair per thread
-    __syncthreads();                                // previous tile's readers are done
-    for (int t = tid; t < tl.ti * NQ; t += kMeshThreads) {
-      const int r = t / NQ, q = t - r * NQ;
-      long long o = by * tl.ti + r;
-      const bool valid = o < tl.outer;
-      int mi[TBK_MAX_DIM] = {0, 0, 0, 0};
-      double x = 0.0;
-      bool closing = false;
-      long long base = 0;
-      int zmask = 0;
-      if (valid) {
-        for (int d = last - 1; d >= 0; --d) {       // C-order decode over the outer axes
-          const long long qq = o / out.cnt[d];
-          mi[d] = (int)(o - qq * out.cnt[d]);
-          o = qq;
-        }
-        for (int d = 0; d < last; ++d) {
-          int g = mi[d] + (d == 0 ? ks.row0 : 0);
-          if (d == 0 && g == tl.closing_g) { g = 0; closing = true; }
-          const double kd = ks.start[d] + (double)g / ks.den[d];                   // pythtb.py:2477
-          const double c = q < NPH ? (q < nph ? ds.R[q][d] : 0.0) : ds.tau[q - NPH][d];
-          x = fma(kd, c, x);
-          base += mi[d] * out.gstride[d];
-          if (mi[d] == 0 && out.wrap[d]) zmask |= 1 << d;
-        }
-      }
-      s_out[r][q] = expi_turns(x);
-      if (q == 0) {
-        s_base[r] = base;
-        s_flags[r] = zmask | (closing ? 256 : 0) | (valid ? 512 : 0);
-      }
-    }
-    // ---- per-thread factors along the fastest axis
+  // balanced split: the first (nseg % G) CTAs take one segment more (32-bit arithmetic only)
+  const unsigned per = tl.nseg / gridDim.x, extra = tl.nseg - per * gridDim.x;
+  unsigned seg = per * blockIdx.x + (blockIdx.x < extra ? blockIdx.x : extra);
+  const unsigned seg_end = seg + per + (blockIdx.x < extra ? 1u : 0u);
+  while (seg < seg_end) {
+    const int bx = (int)(seg / (unsigned)tl.outer);
+    const int row_lo = (int)(seg - (unsigned)bx * (unsigned)tl.outer);
+    int row_hi = row_lo + (int)(seg_end - seg);
+    if (row_hi > tl.outer) row_hi = tl.outer;
+    seg += (unsigned)(row_hi - row_lo);
+    // ---- per-thread factors along the fastest axis: R components are integers, so every phase
+    // factor is a power of E1 = exp(2 pi i k_last) (one sincospi); the gauge factors need one
+    // sincospi per distinct orbital position (both spin components of an orbital share it)
     const int j = bx * kMeshThreads + tid;
     const bool active = j < out.cnt[last];
     const int gj = j + (last == 0 ? ks.row0 : 0);
     const bool closing_j = (last == 0 && gj == tl.closing_g);
     const double kl = ks.start[last] + (double)(closing_j ? 0 : gj) / ks.den[last];
     cplx fc[NQ];
+    {
+      const cplx e1 = expi_turns(kl);
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const double c = q < NPH ? (q < nph ? ds.R[q][last] : 0.0) : ds.tau[q - NPH][last];
-      fc[q] = (q < NPH && q >= nph) ? mk(1.0, 0.0) : expi_turns(kl * c);
+      for (int p = 0; p < NPH; ++p) {
+        const int m = (int)ds.R[p][last];            // 0 for the zero-padded phases p >= nph
+        const int am = m < 0 ? -m : m;
+        cplx z = mk(1.0, 0.0);
+        for (int i = 0; i < am; ++i) z = z * e1;
+        if (m < 0) z.im = -z.im;
+        fc[p] = z;
+      }
+#pragma unroll
+      for (int o = 0; o < N; ++o) {
+        if (o > 0 && ds.tau[o][last] == ds.tau[o - 1][last]) fc[NPH + o] = fc[NPH + o - 1];
+        else fc[NPH + o] = expi_turns(kl * ds.tau[o][last]);
+      }
     }
     const int zlast = (j == 0 && out.wrap[last]) ? (1 << last) : 0;
-    __syncthreads();
-    if (active) {
-      for (int r = 0; r < tl.ti; ++r) {
-        const int fl = s_flags[r];
-        if (!(fl & 512)) break;
-        // ---- H(k), lower triangle
+    cplx* const dst_col = out.evec + (long long)j * out.gstride[last];
+
+    for (int chunk = row_lo; chunk < row_hi; chunk += kMeshMaxRows) {
+      const int nrows = row_hi - chunk < kMeshMaxRows ? row_hi - chunk : kMeshMaxRows;
+      // ---- per-row (outer index) factors, one (row, q) pair per thread
+      __syncthreads();                              // previous chunk's readers are done
+      for (int t = tid; t < nrows * NQ; t += kMeshThreads) {
+        const int r = t / NQ, q = t - r * NQ;
+        unsigned o = (unsigned)(chunk + r);
+        double x = 0.0;
+        bool closing = false;
+        long long base = 0;
+        int zmask = 0;
+        for (int d = last - 1; d >= 0; --d) {       // C-order decode over the outer axes, innermost first
+          unsigned idx = o;
+          if (d > 0) {
+            const unsigned qq = o / (unsigned)out.cnt[d];
+            idx = o - qq * (unsigned)out.cnt[d];
+            o = qq;
+          }
+          int g = (int)idx + (d == 0 ? ks.row0 : 0);
+          if (d == 0 && g == tl.closing_g) { g = 0; closing = true; }
+          const double kd = ks.start[d] + (double)g / ks.den[d];                   // pythtb.py:2477
+          const double c = q < NPH ? (q < nph ? ds.R[q][d] : 0.0) : ds.tau[q - NPH][d];
+          x = fma(kd, c, x);
+          base += (long long)idx * out.gstride[d];
+          if (idx == 0 && out.wrap[d]) zmask |= 1 << d;
+        }
+        s_out[r][q] = expi_turns(x);
+        if (q == 0) {
+          s_base[r] = base;
+          s_flags[r] = zmask | (closing ? 256 : 0);
+        }
+      }
+      __syncthreads();
+      if (!active) continue;
+      for (int r = 0; r < nrows; ++r) {
+        // ---- H(k), lower triangle: straight-line over the zero-padded coefficient table
         cplx acc[NP];
 #pragma unroll
         for (int e = 0; e < NP; ++e) acc[e] = mk(ds.C[e][0], ds.C[e][1]);
 #pragma unroll
         for (int p = 0; p < NPH; ++p) {
-          if (p < nph) {
-            const cplx z = s_out[r][p] * fc[p];     // exp(2 pi i k.R_p)
-            const unsigned m = ds.mask[p];
+          const cplx z = s_out[r][p] * fc[p];       // exp(2 pi i k.R_p)
 #pragma unroll
-            for (int e = 0; e < NP; ++e) {
-              if (m & (1u << e)) {
-                acc[e].re = fma(ds.P[p][e][0], z.re, acc[e].re);
-                acc[e].re = fma(ds.Q[p][e][0], z.im, acc[e].re);
-                acc[e].im = fma(ds.P[p][e][1], z.re, acc[e].im);
-                acc[e].im = fma(ds.Q[p][e][1], z.im, acc[e].im);
-              }
-            }
+          for (int e = 0; e < NP; ++e) {
+            acc[e].re = fma(ds.P[p][e][0], z.re, acc[e].re);
+            acc[e].re = fma(ds.Q[p][e][0], z.im, acc[e].re);
+            acc[e].im = fma(ds.P[p][e][1], z.re, acc[e].im);
+            acc[e].im = fma(ds.Q[p][e][1], z.im, acc[e].im);
           }
         }
         // ---- diagonalise (rows of w = eigenvectors, ascending eigenvalues)
@@ -146,6 +203,7 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
 #pragma unroll
         for (int b = 0; b < N - 1; ++b) gmin[b] = fmin(gmin[b], ev[b + 1] - ev[b]);
         // ---- Convention-I gauge u_I[b][o] = conj(d_o) u_II[b][o] (+ pbc phase on a closing row)
+        const int fl = s_flags[r];
         const bool closing = (fl & 256) || closing_j;
 #pragma unroll
         for (int o = 0; o < N; ++o) {
@@ -155,45 +213,26 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
             for (int b = 0; b < N; ++b) w[b][o] = w[b][o] * f;
           }
           if (closing) {                            // axis-0 image of global row 0 (pythtb.py:2729); a second
-            const cplx ph = out.pbc_phase[o];       // multiply, so the values equal the unsharded image bit for bit
+            const cplx ph = s_pbc0[o];              // multiply, so the values equal the unsharded image bit for bit
 #pragma unroll
             for (int b = 0; b < N; ++b) w[b][o] = w[b][o] * ph;
           }
         }
         // ---- store (+ periodic images)
-        const long long base = s_base[r] + (long long)j * out.gstride[last];
-        cplx* dst = out.evec + base;
+        const long long base = s_base[r];
+        cplx* dst = dst_col + base;
 #pragma unroll
         for (int b = 0; b < N; ++b)
 #pragma unroll
           for (int o = 0; o < N; ++o) dst[b * N + o] = w[b][o];
         const int zero_mask = (fl & 15) | zlast;
-        if (zero_mask) {
-          for (int m = 1; m < (1 << nd); ++m) {
-            if ((m & zero_mask) != m) continue;
-            long long off = base;
-            cplx im[N][N];
+        if (zero_mask) {                            // cold: a copy in local memory for the out-of-line call
+          EigRows<N> eg;
 #pragma unroll
-            for (int b = 0; b < N; ++b)
+          for (int b = 0; b < N; ++b)
 #pragma unroll
-              for (int o = 0; o < N; ++o) im[b][o] = w[b][o];
-            for (int d = 0; d < nd; ++d) {           // one multiply per wrapped axis, in axis order
-              if (m & (1 << d)) {
-                off += (long long)(out.full[d] - 1) * out.gstride[d];
-#pragma unroll
-                for (int o = 0; o < N; ++o) {
-                  const cplx ph = out.pbc_phase[d * N + o];
-#pragma unroll
-                  for (int b = 0; b < N; ++b) im[b][o] = im[b][o] * ph;
-                }
-              }
-            }
-            cplx* dsti = out.evec + off;
-#pragma unroll
-            for (int b = 0; b < N; ++b)
-#pragma unroll
-              for (int o = 0; o < N; ++o) dsti[b * N + o] = im[b][o];
-          }
+            for (int o = 0; o < N; ++o) eg.w[b][o] = w[b][o];
+          mesh_store_images<N>(eg, out, base + (long long)j * out.gstride[last], zero_mask);
         }
       }
     }

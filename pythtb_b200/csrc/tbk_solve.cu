@@ -15,6 +15,7 @@
 // Convention-I gauge, and write the reference's output layouts directly
 // (solve_all's eval[band,k] / evec[band,k,orb] or the wf_array grid with its
 // periodic images and the running minimum of the direct gaps).
+#include <stdlib.h>
 #include "tbk_internal.cuh"
 #include "tbk_eig_small.cuh"
 #include "tbk_eig_group.cuh"
@@ -658,18 +659,24 @@ static int launch_mesh_small(const tbk_model* m, const KSrc& ks, const OutSpec& 
   if (!ds.valid || n < 2 || n > 4) return 0;
   if (nd > 1 && out.cnt[nd - 1] < 48) return 0;       // too few points along the fastest axis to fill a CTA row
   MeshTiling tl;
-  tl.outer = 1;
-  for (int d = 0; d < nd - 1; ++d) tl.outer *= out.cnt[d];
+  long long outer = 1;
+  for (int d = 0; d < nd - 1; ++d) outer *= out.cnt[d];
   tl.nbx = (out.cnt[nd - 1] + kMeshThreads - 1) / kMeshThreads;
-  // rows per tile: amortise the per-tile sincospi but keep >= ~4 tiles per SM
-  int ti = 8;
-  while (ti > 1 && ((tl.outer + ti - 1) / ti) * tl.nbx < (long long)kNumSM * 4) ti >>= 1;
-  if (tl.outer < ti) ti = (int)tl.outer;
-  tl.ti = ti;
-  tl.ntiles = ((tl.outer + ti - 1) / ti) * tl.nbx;
+  const long long nseg = outer * tl.nbx;
+  if (nseg <= 0) return 1;
+  if (nseg >= 0x7fffffffLL) return 0;                 // 32-bit tile arithmetic in the kernel: leave huge meshes to the generic path
+  tl.outer = (int)outer;
+  tl.nseg = (unsigned)nseg;
   tl.closing_g = ks.closing_g;
-  if (tl.ntiles <= 0) return 1;
-  const int grid = (int)(tl.ntiles < kMeshGridCap ? tl.ntiles : kMeshGridCap);
+  const bool p4 = ds.nph <= 4;
+  // one balanced wave: #SM x (CTAs resident per SM) persistent CTAs, each with an equal share of rows
+  int occ = n == 2 ? (p4 ? 6 : 4) : (n == 3 ? 3 : 2);
+  if (n == 2 && p4) { const char* e = getenv("TBK_MESH_OCC"); if (e && atoi(e) == 5) occ = 5; }   // tuning knob
+  long long want = (long long)kNumSM * occ;
+  // at least ~4 rows per CTA so the per-CTA sincospi prologue stays amortised
+  if (want > (nseg + 3) / 4) want = (nseg + 3) / 4;
+  if (want < 1) want = 1;
+  const int grid = (int)want;
   double* partial = nullptr;
   unsigned* ticket = nullptr;
   if (gaps_dev) {
@@ -680,12 +687,11 @@ static int launch_mesh_small(const tbk_model* m, const KSrc& ks, const OutSpec& 
     if (!ticket) { set_error("tbk_solve_grid: cannot allocate the reduction tickets"); return TBK_ERR_CUDA; }
   }
   const int gauge = (m->pv.convention == 1 && m->pv.dim_k > 0) ? 1 : 0;
-#define TBK_MESH_LAUNCH(NN, PP) \
-  mesh_small_kernel<NN, PP><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev)
-  const bool p4 = ds.nph <= 4;
-  if (n == 2) { if (p4) TBK_MESH_LAUNCH(2, 4); else TBK_MESH_LAUNCH(2, 8); }
-  else if (n == 3) { if (p4) TBK_MESH_LAUNCH(3, 4); else TBK_MESH_LAUNCH(3, 8); }
-  else { if (p4) TBK_MESH_LAUNCH(4, 4); else TBK_MESH_LAUNCH(4, 8); }
+#define TBK_MESH_LAUNCH(NN, PP, MB) \
+  mesh_small_kernel<NN, PP, MB><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev)
+  if (n == 2) { if (p4) { if (occ == 6) TBK_MESH_LAUNCH(2, 4, 6); else TBK_MESH_LAUNCH(2, 4, 5); } else TBK_MESH_LAUNCH(2, 8, 4); }
+  else if (n == 3) { if (p4) TBK_MESH_LAUNCH(3, 4, 3); else TBK_MESH_LAUNCH(3, 8, 3); }
+  else { if (p4) TBK_MESH_LAUNCH(4, 4, 2); else TBK_MESH_LAUNCH(4, 8, 2); }
 #undef TBK_MESH_LAUNCH
   TBK_LAUNCH_CHECK("mesh_small_kernel");
   note_kernel("mesh_small_kernel");

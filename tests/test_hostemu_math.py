@@ -1,0 +1,112 @@
+"""CPU unit tests of the DEVICE arithmetic: the TBK_HD headers of pythtb_b200/csrc compiled by
+g++ (tests/hostemu) and checked against numpy/LAPACK — eigh2, register Jacobi (n = 3, 4), the group
+Householder+QL solver, link determinants, polar factors and unitary eigenvalues.  Lets the math of
+the CUDA kernels be verified in the GPU-less build container; the product never uses this build."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from tests import hostemu
+
+DP = ctypes.POINTER(ctypes.c_double)
+
+
+def _p(a):
+    return a.ctypes.data_as(DP)
+
+
+def _rand_herm(rng, n, degenerate=False):
+    a = rng.randn(n, n) + 1j * rng.randn(n, n)
+    h = a + a.conj().T
+    if degenerate:                       # exactly repeated eigenvalues (Kramers-like pairs)
+        q, _ = np.linalg.qr(a)
+        lam = np.repeat(rng.randn((n + 1) // 2), 2)[:n]
+        h = (q * lam) @ q.conj().T
+        h = 0.5 * (h + h.conj().T)
+    return h
+
+
+def _check_eig(h, ev, w, tol=1e-12):
+    """rows of w are eigenvectors (not conjugated): H w[b]^T = ev[b] w[b]^T."""
+    n = h.shape[0]
+    scale = max(1.0, np.max(np.abs(h)))
+    assert np.all(np.diff(ev) >= 0)
+    assert np.max(np.abs(ev - np.linalg.eigvalsh(h))) < 1e-12 * scale * n
+    assert np.max(np.abs(h @ w.T - w.T * ev[None, :])) < tol * scale * n
+    assert np.max(np.abs(w.conj() @ w.T - np.eye(n))) < tol * n
+
+
+def test_eigh2_closed_form():
+    lib = hostemu.lib()
+    rng = np.random.RandomState(1)
+    cases = [(rng.randn(), rng.randn(), complex(rng.randn(), rng.randn())) for _ in range(200)]
+    cases += [(1.0, 1.0, 0j), (2.0, -1.0, 0j), (-1.0, 2.0, 0j), (0.3, 0.3, 1e-9 + 0j), (1.0, 1.0 + 1e-13, 1e-3j),
+              (1e8, -1e8, 1.0 + 1j), (0.0, 0.0, 1e-140 + 0j)]  # below ~1e-150 |h10|^2 is denormal: documented limit
+    for h00, h11, h10 in cases:
+        ev = np.zeros(2)
+        w = np.zeros((2, 2), dtype=complex)
+        lib.emu_eigh2(ctypes.c_double(h00), ctypes.c_double(h11), ctypes.c_double(h10.real), ctypes.c_double(h10.imag),
+                      _p(ev), _p(w.view(np.float64)))
+        h = np.array([[h00, np.conj(h10)], [h10, h11]])
+        _check_eig(h, ev, w)
+
+
+@pytest.mark.parametrize("n", [3, 4])
+def test_register_jacobi(n):
+    lib = hostemu.lib()
+    rng = np.random.RandomState(10 + n)
+    mats = [_rand_herm(rng, n) for _ in range(200)] + [_rand_herm(rng, n, degenerate=True) for _ in range(50)]
+    mats += [np.diag(rng.randn(n)).astype(complex), np.zeros((n, n), dtype=complex), np.eye(n, dtype=complex) * 3.0]
+    for h in mats:
+        ev = np.zeros(n)
+        w = np.zeros((n, n), dtype=complex)
+        hc = np.ascontiguousarray(h)
+        assert lib.emu_jacobi(n, _p(hc.view(np.float64)), _p(ev), _p(w.view(np.float64))) == 0
+        _check_eig(h, ev, w)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 8, 17, 32, 40, 64])
+def test_group_heev(n):
+    lib = hostemu.lib()
+    rng = np.random.RandomState(100 + n)
+    for trial in range(6):
+        h = _rand_herm(rng, n, degenerate=(trial == 5 and n > 2))
+        lda = n | 1
+        a = np.zeros((n, lda), dtype=complex)           # a[c, r] = A(r, c) column-major
+        a[:, :n] = np.tril(h).T                          # lower triangle only; upper left as garbage-free zeros
+        ev = np.zeros(n)
+        vec = np.zeros((n, n), dtype=complex)
+        info = lib.emu_heev_group(n, _p(a.view(np.float64)), lda, 1, _p(ev), _p(vec.view(np.float64)))
+        assert info == 0
+        _check_eig(h, ev, vec, tol=1e-12)
+        a[:, :n] = np.tril(h).T
+        ev2 = np.zeros(n)
+        assert lib.emu_heev_group(n, _p(a.view(np.float64)), lda, 0, _p(ev2), None) == 0
+        assert np.max(np.abs(ev2 - ev)) < 1e-12 * max(1.0, np.max(np.abs(ev))) * n
+
+
+def test_link_det_polar_eigvals():
+    lib = hostemu.lib()
+    rng = np.random.RandomState(7)
+    for nocc, n in ((1, 2), (2, 4), (3, 7), (6, 10), (12, 30)):
+        a = rng.randn(nocc, n) + 1j * rng.randn(nocc, n)
+        b = a + 0.3 * (rng.randn(nocc, n) + 1j * rng.randn(nocc, n))
+        out = np.zeros(3)
+        lib.emu_link_det(nocc, n, _p(np.ascontiguousarray(a).view(np.float64)), _p(np.ascontiguousarray(b).view(np.float64)), _p(out))
+        det = np.linalg.det(a.conj() @ b.T)
+        assert abs(complex(out[0], out[1]) - det / abs(det)) < 1e-11
+        assert abs(out[2] - np.log(abs(det))) < 1e-10
+        m = np.ascontiguousarray(a.conj() @ b.T)
+        u, _, vh = np.linalg.svd(m)
+        pol = m.copy()
+        assert lib.emu_polar(nocc, _p(pol.view(np.float64))) > 0      # iteration count (-1 = singular)
+        assert np.max(np.abs(pol - u @ vh)) < 1e-10
+        uni = np.ascontiguousarray(u @ vh)
+        want = np.sort(np.angle(np.linalg.eigvals(uni)))
+        ev = np.zeros(nocc, dtype=complex)
+        work = uni.copy()
+        assert lib.emu_eigvals(nocc, _p(work.view(np.float64)), _p(ev.view(np.float64))) == 0
+        got = np.sort(np.angle(ev))
+        assert np.max(np.abs(np.exp(1j * got) - np.exp(1j * want))) < 1e-9
+        assert np.max(np.abs(np.abs(ev) - 1.0)) < 1e-10
