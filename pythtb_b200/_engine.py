@@ -97,6 +97,9 @@ class B200Engine(object):
         self.device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", torch.cuda.current_device())))
         torch.cuda.set_device(self.device)
         self._ws = None
+        self._host_results = {}
+        self._dev_index = self.device.index
+        self._raw_stream = torch._C._cuda_getCurrentRawStream
 
     # ------------------------------------------------------------------ helpers
     @property
@@ -105,7 +108,21 @@ class B200Engine(object):
         return int(self.lib.tbk_launch_count())
 
     def stream(self):
-        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+        # raw cudaStream_t of torch's current stream (one C call; torch.cuda.current_stream() costs ~10 us)
+        return ctypes.c_void_p(self._raw_stream(self._dev_index))
+
+    def host_result(self, n):
+        """A small pinned host buffer the kernels write their results into directly
+        (pinned memory is device-addressable under UVA): a result costs one stream
+        synchronisation instead of a cudaMemcpy.  Returns (tensor, numpy view)."""
+        buf = self._host_results.get(n)
+        if buf is None:
+            t = self.torch.zeros(max(int(n), 1), dtype=self.torch.float64, pin_memory=True)
+            buf = self._host_results[n] = (t, t.numpy())
+        return buf
+
+    def sync(self):
+        self.torch.cuda.current_stream(self.device).synchronize()
 
     def workspace(self, nbytes):
         nbytes = int(nbytes)
@@ -214,10 +231,12 @@ class B200Engine(object):
             val = cache[key] = make()
         return val
 
-    def solve_grid(self, model, store, mesh_arr, start_k, row0=0, nrows=None, wrap0=1, want_gaps=True):
+    def solve_grid(self, model, store, mesh_arr, start_k, row0=0, nrows=None, wrap0=1, want_gaps=True,
+                   host_result=False):
         """wf_array.solve_on_grid + impose_pbc (pythtb.py:2421-2532) into ``store``
         (local rows [row0, row0+nrows] of mesh axis 0); returns the minimal gaps
-        over the rows solved here as a device tensor (or None).
+        over the rows solved here as a device tensor — or, with ``host_result``, as a
+        host array (the call then synchronises the stream) — or None.
         wrap0: 1 = write the periodic image of row 0 (single shard), 0 = leave the
         closing row to a halo exchange, 2 = compute the closing row in this launch."""
         torch = self.torch
@@ -226,17 +245,33 @@ class B200Engine(object):
         if nrows is None:
             nrows = int(mesh_arr[0]) - 1
         wfs = store.dev(will_write=True)
-        phase = self._cached(plan, ("pbc", nd), lambda: self.to_dev(
-            self.pbc_phases(model._orb, model._nspin, [model._per[d] for d in range(nd)])))
-        gaps = torch.empty(n - 1, dtype=torch.float64, device=self.device) if (n > 1 and want_gaps) else None
-        npts = (nrows + 1) * int(np.prod(np.asarray(mesh_arr[1:]) - 1)) if nd > 1 else nrows + 1
-        ws = self.workspace(self.lib.tbk_solve_workspace(n, max(npts, 1), 1))
+        cache = plan.__dict__.setdefault("_tbk_dev_cache", {})
+        phase = cache.get(("pbc", nd))
+        if phase is None:
+            phase = cache[("pbc", nd)] = self.to_dev(
+                self.pbc_phases(model._orb, model._nspin, [model._per[d] for d in range(nd)]))
+        gaps = gaps_h = None
+        if n > 1 and want_gaps:
+            if host_result:
+                gaps, gaps_h = self.host_result(n - 1)
+            else:
+                gaps = torch.empty(n - 1, dtype=torch.float64, device=self.device)
+        npts = nrows + 1
+        for d in range(1, nd):
+            npts *= int(mesh_arr[d]) - 1
+        ws = self.workspace(self.lib.tbk_solve_workspace(n, npts, 1))
         start = (ctypes.c_double * nd)(*[float(x) for x in start_k])
         mesh = (ctypes.c_int32 * nd)(*[int(x) for x in mesh_arr])
         _lib.check(self.lib.tbk_solve_grid(handle, start, mesh, nd, int(row0), int(nrows), int(wrap0),
                                            _ptr(wfs), _ptr(phase), _ptr(gaps), _ptr(ws), ws.numel(), self.stream()))
-        self.last_solve_kernel = _lib.last_kernel(self.lib)
+        if gaps_h is not None:
+            self.sync()
+            return gaps_h.copy()
         return gaps
+
+    @property
+    def last_solve_kernel(self):
+        return _lib.last_kernel(self.lib)
 
     # ---------------------------------------------------------- multi-GPU plumbing
     def halo_ring_shift(self, store, dim_arr, phase, rank, nranks):
@@ -298,17 +333,30 @@ class B200Engine(object):
     def _view(self, store, dim_arr, occ):
         wfs = store.dev(will_write=False)
         shape = store.shape
-        nsta_arr = shape[dim_arr]
-        n = int(np.prod(shape[dim_arr + 1:]))
-        occ = np.asarray(occ, dtype=np.int64)
-        if occ.size == 0:
-            raise Exception("\n\nNo states selected.")
-        occ = np.where(occ < 0, occ + nsta_arr, occ)
-        if occ.min() < 0 or occ.max() >= nsta_arr:
-            raise IndexError("index in occ out of bounds")
-        occ_d = self._cached(store, ("occ", tuple(int(x) for x in occ)), lambda: self.to_dev(occ.astype(np.int32)))
-        view = _lib.WfView(wfs.data_ptr(), n, nsta_arr, len(occ), occ_d.data_ptr())
-        strides = [int(np.prod(shape[d + 1:dim_arr])) * nsta_arr * n for d in range(dim_arr)]
+        key = ("view", shape, dim_arr, tuple(int(x) for x in occ))
+        cache = store.__dict__.setdefault("_tbk_dev_cache", {})
+        hit = cache.get(key)
+        if hit is None:
+            nsta_arr = shape[dim_arr]
+            n = 1
+            for x in shape[dim_arr + 1:]:
+                n *= int(x)
+            occ = np.asarray(occ, dtype=np.int64)
+            if occ.size == 0:
+                raise Exception("\n\nNo states selected.")
+            occ = np.where(occ < 0, occ + nsta_arr, occ)
+            if occ.min() < 0 or occ.max() >= nsta_arr:
+                raise IndexError("index in occ out of bounds")
+            occ_d = self.to_dev(occ.astype(np.int32))
+            strides = []
+            for d in range(dim_arr):
+                st = nsta_arr * n
+                for x in shape[d + 1:dim_arr]:
+                    st *= int(x)
+                strides.append(st)
+            hit = cache[key] = (n, nsta_arr, len(occ), occ_d, strides)
+        n, nsta_arr, nocc, occ_d, strides = hit
+        view = _lib.WfView(wfs.data_ptr(), n, nsta_arr, nocc, occ_d.data_ptr())
         return view, strides, (wfs, occ_d)
 
     def _offsets(self, store, dim_arr, axes, strides):
@@ -353,11 +401,12 @@ class B200Engine(object):
             return plq.cpu().numpy().reshape(rshape + (mesh[dirs[0]] - 1, mesh[dirs[1]] - 1))
         return tot.cpu().numpy().reshape(rshape)
 
-    def flux_total(self, store, dim_arr, occ, dirs):
-        """Sum of the plaquette phases of every local 2-D slice, as a device tensor [nslice]."""
-        return self.flux_device(store, dim_arr, occ, dirs, want_total=True, want_plaq=False)[0]
+    def flux_total(self, store, dim_arr, occ, dirs, host_result=False):
+        """Sum of the plaquette phases of every local 2-D slice: a device tensor [nslice], or with
+        ``host_result`` a host array (written by the kernel into pinned memory; the call synchronises)."""
+        return self.flux_device(store, dim_arr, occ, dirs, want_total=True, want_plaq=False, host_result=host_result)[0]
 
-    def flux_device(self, store, dim_arr, occ, dirs, want_total=True, want_plaq=False):
+    def flux_device(self, store, dim_arr, occ, dirs, want_total=True, want_plaq=False, host_result=False):
         torch = self.torch
         view, strides, keep = self._view(store, dim_arr, occ)
         mesh = store.shape[:dim_arr]
@@ -366,10 +415,20 @@ class B200Engine(object):
         nslice = int(offs_d.numel())
         n0, n1 = mesh[dirs[0]], mesh[dirs[1]]
         plq = torch.empty((nslice, n0 - 1, n1 - 1), dtype=torch.float64, device=self.device) if want_plaq else None
-        tot = torch.empty((nslice,), dtype=torch.float64, device=self.device) if want_total else None
+        tot = tot_h = None
+        if want_total:
+            if host_result and nslice <= 4096:
+                tot, tot_h = self.host_result(nslice)
+            else:
+                tot = torch.empty((nslice,), dtype=torch.float64, device=self.device)
         ws = self.workspace(self.lib.tbk_flux_workspace(view.nocc, view.n, nslice, n0, n1))
         _lib.check(self.lib.tbk_flux_plane(ctypes.byref(view), _ptr(offs_d), nslice, n0, strides[dirs[0]], n1,
                                            strides[dirs[1]], _ptr(plq), _ptr(tot), _ptr(ws), ws.numel(), self.stream()))
+        if tot_h is not None:
+            self.sync()
+            return tot_h.copy(), plq
+        if host_result and tot is not None:
+            return tot.cpu().numpy(), plq
         return tot, plq
 
     # ------------------------------------------------------- position operator

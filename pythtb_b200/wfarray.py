@@ -167,7 +167,7 @@ class wf_array(object):
         if start.shape[0] != self._dim_arr:
             raise Exception("\n\nk-vector of wrong shape!")
         self._start_k = start_k
-        gaps = self._solve_on_grid_device(start)
+        gaps = self._solve_on_grid_device(start, host_result=True)
         if self._nsta_arr <= 1:
             return None
         return self._gaps_to_host(gaps)
@@ -181,14 +181,16 @@ class wf_array(object):
             return self._halo
         return "recompute" if self._model._nsta <= 16 else "exchange"
 
-    def _solve_on_grid_device(self, start, want_gaps=True):
+    def _solve_on_grid_device(self, start, want_gaps=True, host_result=False):
         """Launch the fused grid solve (and, when sharded, close the slab and
-        reduce the gaps over ranks); results stay engine-resident."""
+        reduce the gaps over ranks); results stay engine-resident unless
+        ``host_result`` asks for a host array (unsharded: zero-copy)."""
         eng = self._model._engine()
         start = np.array(start, dtype=float).reshape(-1)
         sh = self._shard
         if sh is None:
-            return eng.solve_grid(self._model, self._store, self._mesh_arr, start, want_gaps=want_gaps)
+            return eng.solve_grid(self._model, self._store, self._mesh_arr, start, want_gaps=want_gaps,
+                                  host_result=host_result)
         mode = self._halo_mode()
         gaps = eng.solve_grid(self._model, self._store, self._mesh_arr, start, row0=sh.row0, nrows=sh.nrows,
                               wrap0=(2 if mode == "recompute" else 0), want_gaps=want_gaps)
@@ -384,11 +386,13 @@ class wf_array(object):
             raise Exception("\n\nWrong dimensionality!")
         return occ, [int(dirs[0]), int(dirs[1])]
 
-    def _berry_flux_device(self, occ, dirs=None, local_only=False):
+    def _berry_flux_device(self, occ, dirs=None, local_only=False, host_result=False):
         """Total flux per 2-D slice, engine-resident (summed over ranks unless
-        ``local_only``)."""
+        ``local_only``); ``host_result`` returns a host array (unsharded: zero-copy)."""
         occ, dirs = self._check_flux_args(occ, dirs)
         eng = self._model._engine()
+        if self._shard is None:
+            return eng.flux_total(self._store, self._dim_arr, occ, dirs, host_result=host_result)
         tot = eng.flux_total(self._store, self._dim_arr, occ, dirs)
         if self._shard is not None and not local_only and 0 in dirs:
             tot = eng.allreduce(tot, "sum")
@@ -401,7 +405,7 @@ class wf_array(object):
         eng = self._model._engine()
         sh = self._shard
         if not individual_phases and (sh is None or 0 in dirs):
-            res = self._berry_flux_device(occ, dirs)
+            res = self._berry_flux_device(occ, dirs, host_result=True)
             res = res if isinstance(res, np.ndarray) else res.cpu().numpy()
             rest = [d for d in range(self._dim_arr) if d not in dirs]
             res = res.reshape(tuple(int(self._mesh_arr[d]) for d in rest))

@@ -53,7 +53,7 @@ class OracleEngine(object):
     def pbc_phases(self, orb, nspin, k_dirs):
         return np.array([np.repeat(np.exp(-2.0j * np.pi * np.asarray(orb)[:, kd]), nspin) for kd in k_dirs])
 
-    def solve_grid(self, model, store, mesh_arr, start_k, row0=0, nrows=None, wrap0=1, want_gaps=True):
+    def solve_grid(self, model, store, mesh_arr, start_k, row0=0, nrows=None, wrap0=1, want_gaps=True, host_result=False):
         """Same contract as B200Engine.solve_grid: fills the local rows
         [row0, row0+nrows] of a shard (the closing row only for wrap0 in (1, 2))."""
         wfs, _ = orc.solve_on_grid(model, mesh_arr, start_k)
@@ -97,7 +97,7 @@ class OracleEngine(object):
         dist.all_gather_object(parts, np.asarray(local))
         return parts
 
-    def flux_total(self, store, dim_arr, occ, dirs):
+    def flux_total(self, store, dim_arr, occ, dirs, host_result=False):
         return np.asarray(orc.berry_flux(store.arr, dim_arr, occ, dirs, individual_phases=False)).reshape(-1)
 
     def impose_boundary(self, store, dim_arr, mesh_dir, phase):

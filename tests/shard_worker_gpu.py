@@ -1,0 +1,47 @@
+"""One rank of the multi-GPU parity check (launched by torchrun / tests/test_gpu_multi.py):
+sharded wf_array over NCCL against the unsharded array computed on the same GPU."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import pythtb_b200 as tb
+    from tests import models as M, compare
+    try:
+        cases = [(M.haldane(tb, 0.0), [0], [130, 97]), (M.kane_mele(tb, "odd"), [0, 1], [67, 70]),
+                 (M.random_model(tb, norb=7, dim=2, nhop=12, nspin=1, seed=3), [0, 1, 2], [21, 11])]
+        for halo in ("exchange", "recompute", "auto"):
+            for model, occ, mesh in cases:
+                full = tb.wf_array(model, mesh)
+                gaps_ref = full.solve_on_grid([-0.5, -0.5])
+                w = tb.wf_array(model, mesh, shard=(rank, world), halo=halo)
+                gaps = w.solve_on_grid([-0.5, -0.5])
+                assert np.array_equal(gaps, gaps_ref), (halo, gaps, gaps_ref)
+                sh = w._shard
+                # slabs are bit-identical to the rows of the unsharded array, closing row included
+                assert np.array_equal(np.array(w._wfs), np.array(full._wfs)[sh.row0:sh.row0 + sh.nrows + 1]), (halo, rank)
+                f_ref, f = full.berry_flux(occ), w.berry_flux(occ)
+                assert abs(f - f_ref) < 1e-9, (f, f_ref)
+                p_ref, p = full.berry_flux(occ, individual_phases=True), w.berry_flux(occ, individual_phases=True)
+                assert p.shape == p_ref.shape and np.max(np.abs(compare.circ_diff(p, p_ref, 2 * np.pi))) < 1e-10
+                for d in (0, 1):
+                    b_ref, b = full.berry_phase(occ, d, contin=False), w.berry_phase(occ, d, contin=False)
+                    assert b.shape == b_ref.shape and np.max(np.abs(compare.circ_diff(b, b_ref, 2 * np.pi))) < 1e-9
+        print("rank %d ok" % rank)
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
