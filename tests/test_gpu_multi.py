@@ -23,7 +23,15 @@ def test_sharded_wf_array_over_nccl():
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "shard_worker_gpu.py")]
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
-    assert res.returncode == 0, res.stdout[-4000:]
+    # own process group + hard kill on timeout: a hung rank must never outlive the test
+    import signal
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, start_new_session=True)
+    try:
+        out, _ = proc.communicate(timeout=180)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, _ = proc.communicate()
+        raise AssertionError("multi-GPU worker timed out:\n" + out[-4000:])
+    assert proc.returncode == 0, out[-4000:]
     for r in range(world):
-        assert "rank %d ok" % r in res.stdout
+        assert "rank %d ok" % r in out
