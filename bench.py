@@ -284,6 +284,8 @@ def run_b200(args):
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches0 = eng.launches
+    step_device()
+    launches = eng.launches - launches0           # kernels of libtbk_b200.so per step (counted inside the library)
     barrier()
     for s in range(args.steps):
         flush_l2()
@@ -291,7 +293,6 @@ def run_b200(args):
         out = step_device()
         ev1[s].record()
     barrier()
-    launches = (eng.launches - launches0) // args.steps
     dev_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
     gaps_d, flux_d = out
     flux_val = float(flux_d) if not hasattr(flux_d, "cpu") else float(flux_d.cpu().reshape(-1)[0])
@@ -349,7 +350,10 @@ def run_b200(args):
             "data": "synthetic",
             "config": {"workload": _workload_name(args.workload, world), "norb": model._norb, "nspin": model._nspin,
                        "occ": occ, "mesh_per_gpu": [ROWS_PER_RANK, COLS], "l2": "256 MiB flush between steps (untimed); events per step, host kept ahead of the device",
-                       "parallelism": "mesh rows sliced over %d GPU(s)" % world},
+                       "parallelism": "mesh rows sliced over %d GPU(s)" % world,
+                       "halo": (w._halo_mode() if world > 1 else None),
+                       "cross_rank_reduction": ("in-kernel over NVLink peer memory" if (world > 1 and eng._peer) else
+                                                ("nccl all_reduce" if world > 1 else None))},
             "stages": {"solve_on_grid_ms": k_ms, "berry_flux_ms": f_ms,
                        "kpoints_per_s_solve": kpts_per_step_rank * world / (k_ms * 1e-3),
                        "plaquettes_per_s_flux": kpts_per_step_rank * world / (f_ms * 1e-3)},

@@ -137,6 +137,23 @@ int tbk_solve_grid(const tbk_model* model, const double* start_k_host, const int
                    double* wfs_dev, const double* pbc_phase_dev, double* gaps_dev,
                    void* ws_dev, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Multi-GPU peer group (one process per GPU on one NVLink/NVSwitch box).
+ * The reductions that end solve_on_grid (min direct gaps, pythtb.py:2529-2530)
+ * and berry_flux (plane sum, pythtb.py:3148) are finished ACROSS ranks inside
+ * the producing kernel: its last CTA stores the rank's partial result into a
+ * mailbox in every peer's HBM (CUDA-IPC mapped, stores travel over NVLink),
+ * waits for the peers' contributions and combines them in rank order — no
+ * NCCL launch and no extra kernel (csrc/tbk_peer.cuh).
+ *   tbk_peer_create   allocates this rank's mailbox, returns its 64-byte IPC handle;
+ *   tbk_peer_connect  maps the peers' mailboxes (handles: [nranks][64] bytes, any
+ *                     out-of-band all-gather — the Python layer uses torch.distributed);
+ * All ranks must issue the same sequence of *_x calls with a non-NULL peer. */
+typedef struct tbk_peer tbk_peer;
+int tbk_peer_create(int32_t rank, int32_t nranks, tbk_peer** out, void* handle_out);
+int tbk_peer_connect(tbk_peer* peer, const void* handles);
+int tbk_peer_destroy(tbk_peer* peer);
+
 /* Multi-GPU: pack the first local row of a shard ([npoints][nsta_arr][n]
  * complex128) into a contiguous send buffer for the ring shift that closes the
  * neighbour's slab; phase_dev [n] (the pbc phase of pythtb.py:2729, applied by
@@ -205,6 +222,21 @@ size_t tbk_position_hwf_workspace(int32_t nocc, int32_t n, int64_t batch);
 int tbk_position_hwf(const double* evec_dev, int64_t batch, int32_t nocc, int32_t n,
                      const double* pos_dev, double* hwfc_dev, double* hwf_dev,
                      int32_t orbital_basis, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* tbk_solve_grid / tbk_flux_plane with the cross-rank reduction fused in: gaps_dev
+ * (all ranks) receives the minimum over ranks, total_dev the sum over ranks (rank order).
+ * Supported when the shard is solved by the register-resident mesh kernel (nsta <= 4) /
+ * the row-marching flux kernel (nocc <= 2, n <= 4) and nslice <= 16; otherwise
+ * TBK_ERR_UNSUPPORTED is returned before anything is launched and the caller reduces
+ * with NCCL.  peer == NULL behaves exactly like the plain entry points. */
+int tbk_solve_grid_x(const tbk_model* model, const double* start_k_host, const int32_t* mesh_host,
+                     int32_t nd, int32_t row0, int32_t nrows, int32_t wrap0,
+                     double* wfs_dev, const double* pbc_phase_dev, double* gaps_dev,
+                     void* ws_dev, size_t ws_bytes, tbk_peer* peer, void* stream);
+int tbk_flux_plane_x(const tbk_wf_view* view, const int64_t* slice_off_dev, int64_t nslice,
+                     int64_t n0, int64_t stride0, int64_t n1, int64_t stride1,
+                     double* plaq_dev, double* total_dev,
+                     void* ws_dev, size_t ws_bytes, tbk_peer* peer, void* stream);
 
 /* Name of the kernel family the calling thread's last solve call dispatched to
  * (benchmark / profile bookkeeping). */

@@ -98,6 +98,7 @@ class B200Engine(object):
         torch.cuda.set_device(self.device)
         self._ws = None
         self._host_results = {}
+        self._peer = None
         self._dev_index = self.device.index
         self._raw_stream = torch._C._cuda_getCurrentRawStream
 
@@ -232,7 +233,7 @@ class B200Engine(object):
         return val
 
     def solve_grid(self, model, store, mesh_arr, start_k, row0=0, nrows=None, wrap0=1, want_gaps=True,
-                   host_result=False):
+                   host_result=False, reduce_ranks=None):
         """wf_array.solve_on_grid + impose_pbc (pythtb.py:2421-2532) into ``store``
         (local rows [row0, row0+nrows] of mesh axis 0); returns the minimal gaps
         over the rows solved here as a device tensor — or, with ``host_result``, as a
@@ -262,10 +263,31 @@ class B200Engine(object):
         ws = self.workspace(self.lib.tbk_solve_workspace(n, npts, 1))
         start = (ctypes.c_double * nd)(*[float(x) for x in start_k])
         mesh = (ctypes.c_int32 * nd)(*[int(x) for x in mesh_arr])
-        _lib.check(self.lib.tbk_solve_grid(handle, start, mesh, nd, int(row0), int(nrows), int(wrap0),
-                                           _ptr(wfs), _ptr(phase), _ptr(gaps), _ptr(ws), ws.numel(), self.stream()))
+        args = (handle, start, mesh, nd, int(row0), int(nrows), int(wrap0), _ptr(wfs), _ptr(phase), _ptr(gaps),
+                _ptr(ws), ws.numel())
+        reduced = reduce_ranks is None
+        launched = False
+        if gaps is not None and reduce_ranks is not None:
+            # minimum over the ranks inside the kernel, through NVLink peer memory (csrc/tbk_peer.cuh)
+            peer = self.peer_group(*reduce_ranks)
+            if peer is not None:
+                rc = self.lib.tbk_solve_grid_x(*args, peer, self.stream())
+                if rc == 0:
+                    reduced = launched = True
+                elif rc != _lib.ERR_UNSUPPORTED:
+                    _lib.check(rc)
+        if not launched:
+            _lib.check(self.lib.tbk_solve_grid(*args, self.stream()))
+        if gaps is not None and not reduced:
+            # not eligible for the fused reduction: NCCL all-reduce of the per-rank minima
+            if gaps_h is not None:
+                self.sync()
+                return self.allreduce(gaps_h.copy(), "min")
+            return self.allreduce(gaps, "min")
         if gaps_h is not None:
             self.sync()
+            if not np.all(np.isfinite(gaps_h)):
+                raise _lib.TbkError("\n\nsolve_on_grid: a peer rank never delivered its gaps (fused reduction timed out)")
             return gaps_h.copy()
         return gaps
 
@@ -274,6 +296,29 @@ class B200Engine(object):
         return _lib.last_kernel(self.lib)
 
     # ---------------------------------------------------------- multi-GPU plumbing
+    def peer_group(self, rank, nranks):
+        """The NVLink peer-memory mailbox group used by the fused cross-rank reductions
+        (csrc/tbk_peer.cuh): created once per process, IPC handles exchanged through
+        torch.distributed.  Returns the opaque handle, or None when unavailable
+        (more than 8 ranks, or PYTHTB_B200_PEER=0)."""
+        if self._peer is not None:
+            return self._peer if self._peer is not False else None
+        self._peer = False
+        if nranks > 8 or os.environ.get("PYTHTB_B200_PEER", "1") == "0":
+            return None
+        import torch.distributed as dist
+        handle = ctypes.create_string_buffer(64)
+        out = ctypes.c_void_p(0)
+        _lib.check(self.lib.tbk_peer_create(int(rank), int(nranks), ctypes.byref(out), handle))
+        all_handles = [None] * nranks
+        dist.all_gather_object(all_handles, bytes(handle.raw))
+        blob = ctypes.create_string_buffer(b"".join(all_handles), 64 * nranks)
+        peer = ctypes.c_void_p(out.value)
+        _lib.check(self.lib.tbk_peer_connect(peer, blob))
+        dist.barrier()                      # every mailbox is mapped everywhere before the first collective
+        self._peer = peer
+        return peer
+
     def halo_ring_shift(self, store, dim_arr, phase, rank, nranks):
         """Close every rank's slab with the first row of the next rank: one
         grouped NCCL send/recv over NVLink (rank r sends its row 0 to r-1; rank 0's
@@ -401,12 +446,14 @@ class B200Engine(object):
             return plq.cpu().numpy().reshape(rshape + (mesh[dirs[0]] - 1, mesh[dirs[1]] - 1))
         return tot.cpu().numpy().reshape(rshape)
 
-    def flux_total(self, store, dim_arr, occ, dirs, host_result=False):
+    def flux_total(self, store, dim_arr, occ, dirs, host_result=False, reduce_ranks=None):
         """Sum of the plaquette phases of every local 2-D slice: a device tensor [nslice], or with
         ``host_result`` a host array (written by the kernel into pinned memory; the call synchronises)."""
-        return self.flux_device(store, dim_arr, occ, dirs, want_total=True, want_plaq=False, host_result=host_result)[0]
+        return self.flux_device(store, dim_arr, occ, dirs, want_total=True, want_plaq=False, host_result=host_result,
+                                reduce_ranks=reduce_ranks)[0]
 
-    def flux_device(self, store, dim_arr, occ, dirs, want_total=True, want_plaq=False, host_result=False):
+    def flux_device(self, store, dim_arr, occ, dirs, want_total=True, want_plaq=False, host_result=False,
+                    reduce_ranks=None):
         torch = self.torch
         view, strides, keep = self._view(store, dim_arr, occ)
         mesh = store.shape[:dim_arr]
@@ -422,10 +469,32 @@ class B200Engine(object):
             else:
                 tot = torch.empty((nslice,), dtype=torch.float64, device=self.device)
         ws = self.workspace(self.lib.tbk_flux_workspace(view.nocc, view.n, nslice, n0, n1))
-        _lib.check(self.lib.tbk_flux_plane(ctypes.byref(view), _ptr(offs_d), nslice, n0, strides[dirs[0]], n1,
-                                           strides[dirs[1]], _ptr(plq), _ptr(tot), _ptr(ws), ws.numel(), self.stream()))
+        args = (ctypes.byref(view), _ptr(offs_d), nslice, n0, strides[dirs[0]], n1, strides[dirs[1]], _ptr(plq),
+                _ptr(tot), _ptr(ws), ws.numel())
+        reduced = reduce_ranks is None
+        launched = False
+        if tot is not None and reduce_ranks is not None:
+            # sum over the ranks inside the kernel, through NVLink peer memory (csrc/tbk_peer.cuh)
+            peer = self.peer_group(*reduce_ranks)
+            if peer is not None:
+                rc = self.lib.tbk_flux_plane_x(*args, peer, self.stream())
+                if rc == 0:
+                    reduced = launched = True
+                elif rc != _lib.ERR_UNSUPPORTED:
+                    _lib.check(rc)
+        if not launched:
+            _lib.check(self.lib.tbk_flux_plane(*args, self.stream()))
+        if tot is not None and not reduced:
+            # not eligible for the fused reduction: NCCL all-reduce of the per-rank sums
+            if tot_h is not None:
+                self.sync()
+                return self.allreduce(tot_h.copy(), "sum"), plq
+            tot = self.allreduce(tot, "sum")
+            return (tot.cpu().numpy() if host_result else tot), plq
         if tot_h is not None:
             self.sync()
+            if not np.all(np.isfinite(tot_h)):
+                raise _lib.TbkError("\n\nberry_flux: a peer rank never delivered its partial sum (fused reduction timed out)")
             return tot_h.copy(), plq
         if host_result and tot is not None:
             return tot.cpu().numpy(), plq

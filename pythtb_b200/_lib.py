@@ -19,7 +19,8 @@ SYMBOLS = [
     "tbk_eigh_workspace", "tbk_eigh_batched", "tbk_solve_workspace", "tbk_solve_k", "tbk_solve_grid",
     "tbk_impose_boundary", "tbk_flux_workspace", "tbk_flux_plane", "tbk_berry_workspace",
     "tbk_berry_strings", "tbk_position_matrix", "tbk_position_hwf_workspace", "tbk_position_hwf",
-    "tbk_flush_l2", "tbk_halo_pack", "tbk_last_kernel", "tbk_launch_count",
+    "tbk_flush_l2", "tbk_halo_pack", "tbk_last_kernel", "tbk_launch_count", "tbk_peer_create", "tbk_peer_connect",
+    "tbk_peer_destroy", "tbk_solve_grid_x", "tbk_flux_plane_x",
 ]
 
 
@@ -40,6 +41,9 @@ class WfView(ctypes.Structure):
 
 class TbkError(Exception):
     pass
+
+
+ERR_UNSUPPORTED = -5
 
 
 _lib = None
@@ -77,6 +81,11 @@ def load():
         "tbk_position_hwf": (ctypes.c_int, [V, I64, I32, I32, V, V, V, I32, V, SZ, V]),
         "tbk_flush_l2": (ctypes.c_int, [V, SZ, V]),
         "tbk_halo_pack": (ctypes.c_int, [V, V, I64, I32, I32, V, V]),
+        "tbk_peer_create": (ctypes.c_int, [I32, I32, ctypes.POINTER(V), V]),
+        "tbk_peer_connect": (ctypes.c_int, [V, V]),
+        "tbk_peer_destroy": (ctypes.c_int, [V]),
+        "tbk_solve_grid_x": (ctypes.c_int, [V, c_double_p, c_int32_p, I32, I32, I32, I32, V, V, V, V, SZ, V, V]),
+        "tbk_flux_plane_x": (ctypes.c_int, [ctypes.POINTER(WfView), V, I64, I64, I64, I64, I64, V, V, V, SZ, V, V]),
         "tbk_last_kernel": (ctypes.c_char_p, []),
         "tbk_launch_count": (c_int64, []),
     }

@@ -167,6 +167,55 @@ int tbk_model_destroy(tbk_model* m) {
   return TBK_OK;
 }
 
+int tbk_peer_create(int32_t rank, int32_t nranks, tbk_peer** out, void* handle_out) {
+  if (!out || !handle_out || nranks < 1 || nranks > kPeerMaxRanks || rank < 0 || rank >= nranks) {
+    set_error("tbk_peer_create: bad argument (rank=%d nranks=%d, at most %d ranks)", rank, nranks, kPeerMaxRanks);
+    return TBK_ERR_ARG;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  tbk_peer* p = new tbk_peer();
+  memset(p, 0, sizeof(*p));
+  p->rank = rank; p->nranks = nranks;
+  TBK_CUDA(cudaGetDevice(&p->device));
+  void* mem = nullptr;
+  cudaError_t e = cudaMalloc(&mem, kPeerMailboxBytes);
+  if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(mailbox)"); }
+  e = cudaMemset(mem, 0, kPeerMailboxBytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, mem);
+  if (e != cudaSuccess) { cudaFree(mem); delete p; return cuda_fail(e, "cudaIpcGetMemHandle"); }
+  memcpy(handle_out, &h, sizeof(h));
+  p->box[rank] = (double*)mem;
+  *out = p;
+  return TBK_OK;
+}
+
+int tbk_peer_connect(tbk_peer* p, const void* handles) {
+  if (!p || !handles) { set_error("tbk_peer_connect: null argument"); return TBK_ERR_ARG; }
+  for (int r = 0; r < p->nranks; ++r) {
+    if (r == p->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * sizeof(h), sizeof(h));
+    void* mem = nullptr;
+    TBK_CUDA(cudaIpcOpenMemHandle(&mem, h, cudaIpcMemLazyEnablePeerAccess));
+    p->box[r] = (double*)mem;
+  }
+  p->connected = true;
+  return TBK_OK;
+}
+
+int tbk_peer_destroy(tbk_peer* p) {
+  if (!p) return TBK_OK;
+  for (int r = 0; r < p->nranks; ++r) {
+    if (!p->box[r]) continue;
+    if (r == p->rank) cudaFree(p->box[r]);
+    else cudaIpcCloseMemHandle(p->box[r]);
+  }
+  delete p;
+  return TBK_OK;
+}
+
 const char* tbk_last_kernel(void) { return g_last_kernel; }
 
 int64_t tbk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

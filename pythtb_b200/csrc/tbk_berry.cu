@@ -192,8 +192,10 @@ template <int NOCC, int N, bool WANT_PLAQ>
 __global__ void __launch_bounds__(kFluxThreads)
 flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0, long long stride0, long long n1,
                  long long stride1, FluxTiling tl, long long nslice, double* __restrict__ plaq,
-                 double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ total) {
+                 double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ total,
+                 const __grid_constant__ PeerView peer) {
   __shared__ double s_red[kFluxThreads / 32];
+  __shared__ double s_fin[kPeerMaxVals];
   __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int occ[NOCC];
@@ -304,14 +306,20 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
     if (tid == 0) {
       double t = 0.0;
       for (int w = 0; w < kFluxThreads / 32; ++w) t += s_red[w];
-      total[s] = t;
+      if (peer.nranks > 1) s_fin[s] = t;
+      else total[s] = t;
     }
+  }
+  if (peer.nranks > 1) {                                  // sum over the ranks, through the peers' mailboxes
+    __syncthreads();
+    peer_allreduce(peer, s_fin, (int)nslice, 0, total, &s_last);
   }
 }
 
 template <int NOCC, int N>
 static int launch_flux_rows(const WfView& v, const long long* off, long long nslice, long long n0, long long stride0,
-                            long long n1, long long stride1, double* plaq, double* total, double* partial, cudaStream_t st) {
+                            long long n1, long long stride1, double* plaq, double* total, double* partial, tbk_peer* peer,
+                            cudaStream_t st) {
   static int occ_plaq = 0, occ_sum = 0;                   // resident CTAs per SM of the two variants
   if (occ_plaq == 0) {
     int a = 0, b = 0;
@@ -328,12 +336,13 @@ static int launch_flux_rows(const WfView& v, const long long* off, long long nsl
     if (!ticket) { set_error("tbk_flux_plane: cannot allocate the reduction tickets"); return TBK_ERR_CUDA; }
   }
   const int grid = (int)(tl.ntiles < resident ? tl.ntiles : resident);
+  const PeerView pview = total ? peer_next(peer) : peer_next(nullptr);
   if (plaq)
     flux_rows_kernel<NOCC, N, true><<<grid, kFluxThreads, 0, st>>>(v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
-                                                                  total ? partial : nullptr, ticket, total);
+                                                                  total ? partial : nullptr, ticket, total, pview);
   else
     flux_rows_kernel<NOCC, N, false><<<grid, kFluxThreads, 0, st>>>(v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
-                                                                   partial, ticket, total);
+                                                                   partial, ticket, total, pview);
   TBK_LAUNCH_CHECK("flux_rows_kernel");
   return TBK_OK;
 }
@@ -675,6 +684,13 @@ size_t tbk_flux_workspace(int32_t nocc, int32_t n, int64_t nslice, int64_t n0, i
 int tbk_flux_plane(const tbk_wf_view* view, const int64_t* slice_off_dev, int64_t nslice, int64_t n0, int64_t stride0,
                    int64_t n1, int64_t stride1, double* plaq_dev, double* total_dev, void* ws_dev, size_t ws_bytes,
                    void* stream) {
+  return tbk_flux_plane_x(view, slice_off_dev, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, ws_dev, ws_bytes,
+                          nullptr, stream);
+}
+
+int tbk_flux_plane_x(const tbk_wf_view* view, const int64_t* slice_off_dev, int64_t nslice, int64_t n0, int64_t stride0,
+                     int64_t n1, int64_t stride1, double* plaq_dev, double* total_dev, void* ws_dev, size_t ws_bytes,
+                     tbk_peer* peer, void* stream) {
   if (!view || !view->wfs_dev || !view->occ_dev || !slice_off_dev || nslice < 1 || n0 < 2 || n1 < 2 || view->nocc < 1 ||
       (!plaq_dev && !total_dev)) {
     set_error("tbk_flux_plane: bad argument");
@@ -694,17 +710,22 @@ int tbk_flux_plane(const tbk_wf_view* view, const int64_t* slice_off_dev, int64_
   double* partial = total_dev ? (double*)ws : nullptr;
   ws += align256((size_t)(nslice * p0 * bx) * 8);
   const long long* off = (const long long*)slice_off_dev;
-  if (view->nocc <= 2 && view->n >= 2 && view->n <= 4 && view->nocc <= view->n) {
+  const bool rows_kernel = view->nocc <= 2 && view->n >= 2 && view->n <= 4 && view->nocc <= view->n;
+  if (peer && peer->connected && peer->nranks > 1 && total_dev && !(rows_kernel && nslice <= kPeerMaxVals)) {
+    set_error("tbk_flux_plane_x: the fused cross-rank sum needs nocc <= 2, n <= 4 and at most %d slices", kPeerMaxVals);
+    return TBK_ERR_UNSUPPORTED;
+  }
+  if (rows_kernel) {
     double* part2 = (double*)ws;
     int rc = TBK_OK;
     const int key = view->nocc * 10 + view->n;
     switch (key) {
-      case 12: rc = launch_flux_rows<1, 2>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, st); break;
-      case 22: rc = launch_flux_rows<2, 2>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, st); break;
-      case 13: rc = launch_flux_rows<1, 3>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, st); break;
-      case 23: rc = launch_flux_rows<2, 3>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, st); break;
-      case 14: rc = launch_flux_rows<1, 4>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, st); break;
-      default: rc = launch_flux_rows<2, 4>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, st); break;
+      case 12: rc = launch_flux_rows<1, 2>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, peer, st); break;
+      case 22: rc = launch_flux_rows<2, 2>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, peer, st); break;
+      case 13: rc = launch_flux_rows<1, 3>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, peer, st); break;
+      case 23: rc = launch_flux_rows<2, 3>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, peer, st); break;
+      case 14: rc = launch_flux_rows<1, 4>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, peer, st); break;
+      default: rc = launch_flux_rows<2, 4>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, peer, st); break;
     }
     return rc;
   }

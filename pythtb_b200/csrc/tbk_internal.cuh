@@ -8,6 +8,7 @@
 #include "../../include/tbk.h"
 #include "tbk_common.cuh"
 #include "tbk_plan.cuh"
+#include "tbk_peer.cuh"
 
 namespace tbk {
 
@@ -112,3 +113,24 @@ struct tbk_model {
   int device;
   int max_terms_per_phase;
 };
+
+// The opaque peer group of tbk.h: this rank's mailbox and the IPC mappings of the others
+struct tbk_peer {
+  int rank, nranks, device;
+  unsigned long long epoch;          // advanced by every collective issued through this group
+  double* box[tbk::kPeerMaxRanks];   // box[rank] is the local allocation
+  bool connected;
+};
+
+namespace tbk {
+// PeerView for the next collective (advances the epoch); nranks = 0 view when peer is null
+inline PeerView peer_next(tbk_peer* p) {
+  PeerView v;
+  memset(&v, 0, sizeof(v));
+  if (p && p->connected && p->nranks > 1) {
+    v.rank = p->rank; v.nranks = p->nranks; v.epoch = ++p->epoch;
+    for (int r = 0; r < p->nranks; ++r) v.box[r] = p->box[r];
+  }
+  return v;
+}
+}  // namespace tbk

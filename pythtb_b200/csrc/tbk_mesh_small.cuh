@@ -75,7 +75,8 @@ template <int N, int NPH, int MINB>
 __global__ void __launch_bounds__(kMeshThreads, MINB)
 mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__ KSrc ks,
                   const __grid_constant__ OutSpec out, const __grid_constant__ MeshTiling tl, int gauge,
-                  double* __restrict__ gap_partial, unsigned* __restrict__ ticket, double* __restrict__ gaps_out) {
+                  double* __restrict__ gap_partial, unsigned* __restrict__ ticket, double* __restrict__ gaps_out,
+                  const __grid_constant__ PeerView peer) {
   constexpr int NP = N * (N + 1) / 2;
   constexpr int NQ = NPH + N;                       // phases, then per-state gauge factors
   __shared__ cplx s_out[kMeshMaxRows][NQ];
@@ -84,6 +85,7 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
   __shared__ double s_red[kMeshThreads / 32][N];
   __shared__ cplx s_pbc0[N];                        // pbc phase of axis 0 (closing rows of a shard)
   __shared__ int s_last;
+  __shared__ double s_fin[N];
   if (threadIdx.x < N) s_pbc0[threadIdx.x] = tl.closing_g >= 0 ? out.pbc_phase[threadIdx.x] : mk(1.0, 0.0);
   const int nd = out.nd;
   const int last = nd - 1;
@@ -270,8 +272,13 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
     if (tid == 0) {
       double t = s_red[0][b];
       for (int wv = 1; wv < kMeshThreads / 32; ++wv) t = fmin(t, s_red[wv][b]);
-      gaps_out[b] = t;
+      if (peer.nranks > 1) s_fin[b] = t;
+      else gaps_out[b] = t;
     }
+  }
+  if (peer.nranks > 1) {                            // minimum over the ranks, through the peers' mailboxes
+    __syncthreads();
+    peer_allreduce(peer, s_fin, N - 1, 1, gaps_out, &s_last);
   }
 }
 

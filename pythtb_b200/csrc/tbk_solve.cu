@@ -652,8 +652,17 @@ int tbk_solve_k(const tbk_model* m, const double* k_dev, int64_t nk, double* eva
 }
 
 // mesh_small_kernel dispatch; returns 1 if it took the job, 0 if the shape does not fit, < 0 on error
+static bool mesh_small_takes(const tbk_model* m, const OutSpec& out) {
+  const int n = m->pv.nsta, nd = out.nd;
+  if (!m->dense.valid || n < 2 || n > 4) return false;
+  if (nd > 1 && out.cnt[nd - 1] < 48) return false;   // too few points along the fastest axis to fill a CTA row
+  long long nseg = (out.cnt[nd - 1] + kMeshThreads - 1) / kMeshThreads;
+  for (int d = 0; d < nd - 1; ++d) nseg *= out.cnt[d];
+  return nseg > 0 && nseg < 0x7fffffffLL;
+}
+
 static int launch_mesh_small(const tbk_model* m, const KSrc& ks, const OutSpec& out, double* gaps_dev,
-                             void* ws, size_t ws_bytes, cudaStream_t st) {
+                             void* ws, size_t ws_bytes, tbk_peer* peer, cudaStream_t st) {
   const DenseSmall& ds = m->dense;
   const int n = m->pv.nsta, nd = out.nd;
   if (!ds.valid || n < 2 || n > 4) return 0;
@@ -687,8 +696,9 @@ static int launch_mesh_small(const tbk_model* m, const KSrc& ks, const OutSpec& 
     if (!ticket) { set_error("tbk_solve_grid: cannot allocate the reduction tickets"); return TBK_ERR_CUDA; }
   }
   const int gauge = (m->pv.convention == 1 && m->pv.dim_k > 0) ? 1 : 0;
+  const PeerView pview = gaps_dev ? peer_next(peer) : peer_next(nullptr);
 #define TBK_MESH_LAUNCH(NN, PP, MB) \
-  mesh_small_kernel<NN, PP, MB><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev)
+  mesh_small_kernel<NN, PP, MB><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview)
   if (n == 2) { if (p4) { if (occ == 6) TBK_MESH_LAUNCH(2, 4, 6); else TBK_MESH_LAUNCH(2, 4, 5); } else TBK_MESH_LAUNCH(2, 8, 4); }
   else if (n == 3) { if (p4) TBK_MESH_LAUNCH(3, 4, 3); else TBK_MESH_LAUNCH(3, 8, 3); }
   else { if (p4) TBK_MESH_LAUNCH(4, 4, 2); else TBK_MESH_LAUNCH(4, 8, 2); }
@@ -701,6 +711,13 @@ static int launch_mesh_small(const tbk_model* m, const KSrc& ks, const OutSpec& 
 int tbk_solve_grid(const tbk_model* m, const double* start_k, const int32_t* mesh, int32_t nd, int32_t row0,
                    int32_t nrows, int32_t wrap0, double* wfs_dev, const double* pbc_phase_dev, double* gaps_dev,
                    void* ws_dev, size_t ws_bytes, void* stream) {
+  return tbk_solve_grid_x(m, start_k, mesh, nd, row0, nrows, wrap0, wfs_dev, pbc_phase_dev, gaps_dev, ws_dev, ws_bytes,
+                          nullptr, stream);
+}
+
+int tbk_solve_grid_x(const tbk_model* m, const double* start_k, const int32_t* mesh, int32_t nd, int32_t row0,
+                     int32_t nrows, int32_t wrap0, double* wfs_dev, const double* pbc_phase_dev, double* gaps_dev,
+                     void* ws_dev, size_t ws_bytes, tbk_peer* peer, void* stream) {
   if (!m || !start_k || !mesh || !wfs_dev || !pbc_phase_dev || nd < 1 || nd > TBK_MAX_DIM || nd != m->pv.dim_k ||
       nrows < 0 || row0 < 0 || wrap0 < 0 || wrap0 > 2) {
     set_error("tbk_solve_grid: bad argument (nd=%d dim_k=%d)", nd, m ? m->pv.dim_k : -1);
@@ -735,8 +752,13 @@ int tbk_solve_grid(const tbk_model* m, const double* start_k, const int32_t* mes
     note_kernel("solve_n1_kernel");
     return TBK_OK;
   }
+  const bool fused = peer && peer->connected && peer->nranks > 1 && gaps_dev;
+  if (fused && !(npts > 0 && mesh_small_takes(m, out))) {
+    set_error("tbk_solve_grid_x: the fused cross-rank reduction needs the register-resident mesh kernel (nsta <= 4)");
+    return TBK_ERR_UNSUPPORTED;
+  }
   if (npts > 0) {
-    const int took = launch_mesh_small(m, ks, out, gaps_dev, ws_dev, ws_bytes, st);
+    const int took = launch_mesh_small(m, ks, out, gaps_dev, ws_dev, ws_bytes, peer, st);
     if (took < 0) return took;
     if (took == 1) return TBK_OK;
   }

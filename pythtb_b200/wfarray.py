@@ -192,8 +192,11 @@ class wf_array(object):
             return eng.solve_grid(self._model, self._store, self._mesh_arr, start, want_gaps=want_gaps,
                                   host_result=host_result)
         mode = self._halo_mode()
+        # the minimum over ranks is taken by the engine (fused into the kernel over NVLink peer
+        # memory where the kernel family supports it, NCCL all-reduce otherwise)
         gaps = eng.solve_grid(self._model, self._store, self._mesh_arr, start, row0=sh.row0, nrows=sh.nrows,
-                              wrap0=(2 if mode == "recompute" else 0), want_gaps=want_gaps)
+                              wrap0=(2 if mode == "recompute" else 0), want_gaps=want_gaps,
+                              host_result=host_result, reduce_ranks=(sh.rank, sh.nranks))
         if mode == "exchange":
             # rank r needs the first row of rank r+1; rank 0's row reaches the last
             # rank multiplied by the pbc phase (pythtb.py:2729, 2740-2741)
@@ -201,8 +204,6 @@ class wf_array(object):
             if sh.rank == 0:
                 phase = eng.pbc_phases(self._orb, self._nspin, [self._model._per[0]])[0]
             eng.halo_ring_shift(self._store, self._dim_arr, phase, sh.rank, sh.nranks)
-        if gaps is not None and want_gaps:
-            gaps = eng.allreduce(gaps, "min")
         return gaps
 
     @staticmethod
@@ -393,10 +394,9 @@ class wf_array(object):
         eng = self._model._engine()
         if self._shard is None:
             return eng.flux_total(self._store, self._dim_arr, occ, dirs, host_result=host_result)
-        tot = eng.flux_total(self._store, self._dim_arr, occ, dirs)
-        if self._shard is not None and not local_only and 0 in dirs:
-            tot = eng.allreduce(tot, "sum")
-        return tot
+        sh = self._shard
+        reduce_ranks = (sh.rank, sh.nranks) if (not local_only and 0 in dirs) else None
+        return eng.flux_total(self._store, self._dim_arr, occ, dirs, host_result=host_result, reduce_ranks=reduce_ranks)
 
     def berry_flux(self, occ="All", dirs=None, individual_phases=False):
         """pythtb.py:3068-3205: plaquette phases / integrated Berry curvature on

@@ -53,7 +53,8 @@ class OracleEngine(object):
     def pbc_phases(self, orb, nspin, k_dirs):
         return np.array([np.repeat(np.exp(-2.0j * np.pi * np.asarray(orb)[:, kd]), nspin) for kd in k_dirs])
 
-    def solve_grid(self, model, store, mesh_arr, start_k, row0=0, nrows=None, wrap0=1, want_gaps=True, host_result=False):
+    def solve_grid(self, model, store, mesh_arr, start_k, row0=0, nrows=None, wrap0=1, want_gaps=True, host_result=False,
+                   reduce_ranks=None):
         """Same contract as B200Engine.solve_grid: fills the local rows
         [row0, row0+nrows] of a shard (the closing row only for wrap0 in (1, 2))."""
         wfs, _ = orc.solve_on_grid(model, mesh_arr, start_k)
@@ -68,7 +69,8 @@ class OracleEngine(object):
         # minimal gaps over the rows solved here only (so that the cross-rank min is exercised)
         kpts = orc.grid_kpoints(start_k, mesh_arr).reshape(tuple(np.asarray(mesh_arr) - 1) + (len(mesh_arr),))
         ev = orc.sol_ham(orc.gen_ham(model, kpts[row0:row0 + nrows].reshape(-1, len(mesh_arr))), False)
-        return (ev[:, 1:] - ev[:, :-1]).min(axis=0)
+        gaps = (ev[:, 1:] - ev[:, :-1]).min(axis=0)
+        return self.allreduce(gaps, "min") if reduce_ranks is not None else gaps
 
     # ---- multi-rank plumbing over torch.distributed (gloo on CPU in the tests)
     def halo_ring_shift(self, store, dim_arr, phase, rank, nranks):
@@ -97,8 +99,9 @@ class OracleEngine(object):
         dist.all_gather_object(parts, np.asarray(local))
         return parts
 
-    def flux_total(self, store, dim_arr, occ, dirs, host_result=False):
-        return np.asarray(orc.berry_flux(store.arr, dim_arr, occ, dirs, individual_phases=False)).reshape(-1)
+    def flux_total(self, store, dim_arr, occ, dirs, host_result=False, reduce_ranks=None):
+        tot = np.asarray(orc.berry_flux(store.arr, dim_arr, occ, dirs, individual_phases=False)).reshape(-1)
+        return self.allreduce(tot, "sum") if reduce_ranks is not None else tot
 
     def impose_boundary(self, store, dim_arr, mesh_dir, phase):
         if phase is None:
