@@ -244,6 +244,11 @@ const char* tbk_last_kernel(void);
 /* Number of kernels this library has launched in this process (all threads). */
 int64_t tbk_launch_count(void);
 
+/* Block the calling host thread until everything enqueued on `stream` has finished
+ * (cudaStreamSynchronize); the host layer uses it after a call whose results are
+ * written straight into pinned host memory. */
+int tbk_stream_sync(void* stream);
+
 /* L2 flush helper for benchmarks: overwrites buf_dev[bytes] (bytes > L2 size). */
 int tbk_flush_l2(void* buf_dev, size_t bytes, void* stream);
 

@@ -220,6 +220,11 @@ const char* tbk_last_kernel(void) { return g_last_kernel; }
 
 int64_t tbk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int tbk_stream_sync(void* stream) {
+  TBK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return TBK_OK;
+}
+
 int tbk_flush_l2(void* buf_dev, size_t bytes, void* stream) {
   if (!buf_dev || bytes < 32) { set_error("tbk_flush_l2: bad buffer"); return TBK_ERR_ARG; }
   static double v = 0.0;

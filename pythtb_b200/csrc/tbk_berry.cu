@@ -347,6 +347,267 @@ static int launch_flux_rows(const WfView& v, const long long* off, long long nsl
   return TBK_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Bulk-copy ring variant of the plaquette kernel (contiguous mesh columns): the rows of a tile
+// are streamed into a shared-memory ring by cp.async.bulk (the TMA engine, 1-D form) signalling
+// one mbarrier per stage, so the bytes in flight per SM are set by the ring depth (tens of KB)
+// instead of by the registers a thread can spare for prefetching — ncu showed the register
+// version waiting on loads for 59 % of its cycles with ~20 KB in flight per SM.
+// A CTA owns 128 plaquette columns x `ti` rows; thread t owns plaquette column t and reads the
+// states of columns t and t+1 from the ring, so every k-point block is fetched from HBM once per
+// tile (plus one halo row), and every thread owns a plaquette (no shuffle, no idle lane).
+// Per plaquette: V(i,j) = det<a|b>, V(i,j+1) = det<d|c>, H(i+1,j) = det<b|c>, H(i,j) carried:
+//     phase = -arg[ V(i,j) H(i+1,j) conj V(i,j+1) conj H(i,j) ]        (pythtb.py:3855-3861)
+// ---------------------------------------------------------------------------
+constexpr int kRingThreads = 128;
+constexpr int kRingMaxStages = 8;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done = 0;
+  const unsigned a = smem_u32(bar);
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  }
+}
+
+struct RingTiling {
+  int ti;                 // plaquette rows per tile
+  int stages;
+  unsigned stage_bytes;
+  long long nbx, nrb, ntiles;
+};
+
+template <int NOCC, int N>
+struct RingState {
+  cplx u[NOCC][N];
+  __device__ __forceinline__ void load(const cplx* p, const int (&occ)[NOCC]) {     // shared memory
+#pragma unroll
+    for (int m = 0; m < NOCC; ++m)
+#pragma unroll
+      for (int o = 0; o < N; ++o) u[m][o] = p[occ[m] * N + o];
+  }
+};
+template <int NOCC, int N>
+__device__ __forceinline__ cplx ring_link(const RingState<NOCC, N>& a, const RingState<NOCC, N>& b) {
+  cplx M[NOCC][NOCC];
+#pragma unroll
+  for (int m = 0; m < NOCC; ++m)
+#pragma unroll
+    for (int q = 0; q < NOCC; ++q) {
+      cplx acc = mk(0.0, 0.0);
+#pragma unroll
+      for (int o = 0; o < N; ++o) fma_acc_conj(acc, a.u[m][o], b.u[q][o]);
+      M[m][q] = acc;
+    }
+  if constexpr (NOCC == 1) return M[0][0];
+  else return M[0][0] * M[1][1] - M[0][1] * M[1][0];
+}
+
+template <int NOCC, int N, bool WANT_PLAQ>
+__global__ void __launch_bounds__(kRingThreads)
+flux_ring_kernel(WfView v, const long long* __restrict__ slice_off, long long n0, long long stride0, long long n1,
+                 RingTiling tl, long long nslice, double* __restrict__ plaq, double* __restrict__ partial,
+                 unsigned* __restrict__ ticket, double* __restrict__ total, const __grid_constant__ PeerView peer) {
+  extern __shared__ __align__(128) char ring[];
+  __shared__ __align__(8) unsigned long long s_bar[kRingMaxStages];
+  __shared__ double s_red[kRingThreads / 32];
+  __shared__ double s_fin[kPeerMaxVals];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int D = tl.stages;
+  const int blk = v.nsta_arr * v.n;                         // complex elements per mesh point
+  int occ[NOCC];
+#pragma unroll
+  for (int m = 0; m < NOCC; ++m) occ[m] = v.occ[m];
+  if (tid == 0) {
+    for (int sg = 0; sg < D; ++sg) mbar_init(&s_bar[sg], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long p0 = n0 - 1, p1 = n1 - 1;
+  unsigned q_cons = 0;                                      // rows consumed so far by this CTA (stage = q % D)
+  for (long long tile = blockIdx.x; tile < tl.ntiles; tile += gridDim.x) {
+    const long long s = tile / (tl.nrb * tl.nbx);
+    const long long rem = tile - s * tl.nrb * tl.nbx;
+    const long long rb = rem / tl.nbx, bx = rem - rb * tl.nbx;
+    const long long c0 = bx * kRingThreads;
+    const long long col = c0 + tid;
+    const bool owner = col < p1;
+    const long long i0 = rb * tl.ti;
+    const int nrow = (int)((i0 + tl.ti < p0 ? i0 + tl.ti : p0) - i0);     // plaquette rows; nrow + 1 mesh rows
+    const int ncl = (int)(n1 - c0 < kRingThreads + 1 ? n1 - c0 : kRingThreads + 1);
+    const unsigned row_bytes = (unsigned)ncl * (unsigned)blk * 16u;
+    const cplx* g0 = v.wfs + slice_off[s] + c0 * (long long)blk + i0 * stride0;
+    // ---- producer prologue: the first min(D, nrow + 1) rows of the tile
+    if (tid == 0) {
+      const int pre = nrow + 1 < D ? nrow + 1 : D;
+      for (int r = 0; r < pre; ++r) {
+        const unsigned sg = (q_cons + r) % D;
+        mbar_expect_tx(&s_bar[sg], row_bytes);
+        bulk_g2s(ring + (size_t)sg * tl.stage_bytes, g0 + (long long)r * stride0, row_bytes, &s_bar[sg]);
+      }
+    }
+    RingState<NOCC, N> A, Ad, B, Bc;
+    cplx hda = mk(1.0, 0.0);
+    double acc = 0.0;
+    cplx prod = mk(1.0, 0.0);
+    int nprod = 0;
+    double* pq = WANT_PLAQ ? plaq + (s * p0 + i0) * p1 + col : nullptr;
+    for (int r = 0; r <= nrow; ++r) {
+      const unsigned sg = q_cons % D;
+      mbar_wait(&s_bar[sg], (q_cons / D) & 1u);
+      if (owner) {
+        const cplx* row = reinterpret_cast<const cplx*>(ring + (size_t)sg * tl.stage_bytes) + (size_t)tid * blk;
+        B.load(row, occ);
+        Bc.load(row + blk, occ);
+        const cplx hn = ring_link<NOCC, N>(B, Bc);         // H(i0 + r, col)
+        if (r > 0) {
+          cplx z = ring_link<NOCC, N>(A, B) * hn;          // V(i, col) H(i+1, col)
+          z = mulc(z, ring_link<NOCC, N>(Ad, Bc));         // conj V(i, col+1)
+          z = z * hda;                                     // conj H(i, col)
+          if (WANT_PLAQ) {
+            const double phase = neg_arg(z);
+            pq[0] = phase;
+            pq += p1;
+            acc += phase;
+          } else if (z.re > 0.5 && z.re > 8.0 * fabs(z.im)) {
+            prod = prod * z;                               // |arg z| < 0.125: at most 24 per product
+            if (++nprod == 24) { acc += neg_arg(prod); prod = mk(1.0, 0.0); nprod = 0; }
+          } else {
+            acc += neg_arg(z);
+          }
+        }
+        hda = conj(hn);
+        A = B;
+        Ad = Bc;
+      }
+      ++q_cons;
+      __syncthreads();                                     // every thread is done with stage sg
+      if (tid == 0 && r + D <= nrow) {                     // refill it with row r + D of this tile
+        mbar_expect_tx(&s_bar[sg], row_bytes);
+        bulk_g2s(ring + (size_t)sg * tl.stage_bytes, g0 + (long long)(r + D) * stride0, row_bytes, &s_bar[sg]);
+      }
+    }
+    if (!WANT_PLAQ && owner && nprod) acc += neg_arg(prod);
+    if (partial) {
+      double x = acc;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      if (lane == 0) s_red[warp] = x;
+      __syncthreads();
+      if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kRingThreads / 32; ++w) t += s_red[w];
+        partial[tile] = t;
+      }
+      __syncthreads();
+    }
+  }
+  if (!partial) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const long long per = tl.nrb * tl.nbx;
+  for (long long s = 0; s < nslice; ++s) {
+    double x = 0.0;
+    for (long long i = tid; i < per; i += kRingThreads) x += __ldcg(partial + s * per + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = x;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < kRingThreads / 32; ++w) t += s_red[w];
+      if (peer.nranks > 1) s_fin[s] = t;
+      else total[s] = t;
+    }
+  }
+  if (peer.nranks > 1) {                                  // sum over the ranks, through the peers' mailboxes
+    __syncthreads();
+    peer_allreduce(peer, s_fin, (int)nslice, 0, total, &s_last);
+  }
+}
+
+// tiles of the ring kernel: one balanced wave of `resident` CTAs where the mesh allows it
+static RingTiling ring_tiling(long long nslice, long long n0, long long n1, int blk, long long resident, int stages,
+                              unsigned stage_bytes) {
+  RingTiling t;
+  t.stages = stages;
+  t.stage_bytes = stage_bytes;
+  t.nbx = (n1 - 1 + kRingThreads - 1) / kRingThreads;
+  const long long p0 = n0 - 1;
+  long long per_col = resident / (nslice * t.nbx);
+  if (per_col < 1) per_col = 1;
+  if (per_col > p0) per_col = p0;
+  long long ti = (p0 + per_col - 1) / per_col;
+  if (ti < 8 && p0 >= 8) ti = 8;                          // one halo row per tile: keep the re-read below ~12 %
+  t.ti = (int)ti;
+  t.nrb = (p0 + ti - 1) / ti;
+  t.ntiles = nslice * t.nrb * t.nbx;
+  (void)blk;
+  return t;
+}
+static long long ring_tiles_bound(long long nslice, long long n0, long long n1) {
+  const long long nbx = (n1 - 1 + kRingThreads - 1) / kRingThreads;
+  return nslice * nbx * ((n0 - 1 + 7) / 8 + 1) + (long long)kNumSM * 16;
+}
+
+template <int NOCC, int N>
+static int launch_flux_ring(const WfView& v, const long long* off, long long nslice, long long n0, long long stride0,
+                            long long n1, double* plaq, double* total, double* partial, tbk_peer* peer, cudaStream_t st) {
+  const int blk = v.nsta_arr * v.n;
+  const unsigned stage_bytes = (unsigned)((((size_t)(kRingThreads + 1) * blk * 16) + 127) & ~(size_t)127);
+  const int stages = stage_bytes <= 12 * 1024 ? 4 : (stage_bytes <= 40 * 1024 ? 3 : 2);
+  const size_t dyn = (size_t)stages * stage_bytes;
+  auto kern_p = flux_ring_kernel<NOCC, N, true>;
+  auto kern_s = flux_ring_kernel<NOCC, N, false>;
+  static int occ_p = 0, occ_s = 0;
+  static size_t occ_dyn = 0;
+  if (occ_p == 0 || occ_dyn != dyn) {
+    TBK_CUDA(cudaFuncSetAttribute(kern_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    TBK_CUDA(cudaFuncSetAttribute(kern_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    int a = 0, b = 0;
+    TBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, kern_p, kRingThreads, dyn));
+    TBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern_s, kRingThreads, dyn));
+    occ_p = a > 0 ? (a > 6 ? 6 : a) : 1;
+    occ_s = b > 0 ? (b > 6 ? 6 : b) : 1;
+    occ_dyn = dyn;
+  }
+  const long long resident = (long long)kNumSM * (plaq ? occ_p : occ_s);
+  const RingTiling tl = ring_tiling(nslice, n0, n1, blk, resident, stages, stage_bytes);
+  unsigned* ticket = nullptr;
+  if (total) {
+    ticket = take_ticket();
+    if (!ticket) { set_error("tbk_flux_plane: cannot allocate the reduction tickets"); return TBK_ERR_CUDA; }
+  }
+  const int grid = (int)(tl.ntiles < resident ? tl.ntiles : resident);
+  const PeerView pview = total ? peer_next(peer) : peer_next(nullptr);
+  if (plaq)
+    kern_p<<<grid, kRingThreads, dyn, st>>>(v, off, n0, stride0, n1, tl, nslice, plaq, total ? partial : nullptr, ticket,
+                                            total, pview);
+  else
+    kern_s<<<grid, kRingThreads, dyn, st>>>(v, off, n0, stride0, n1, tl, nslice, plaq, partial, ticket, total, pview);
+  TBK_LAUNCH_CHECK("flux_ring_kernel");
+  note_kernel("flux_ring_kernel");
+  return TBK_OK;
+}
+
 // sum partial[s][0..count) in a fixed order -> total[s]
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const double* __restrict__ partial, long long count, double* __restrict__ total) {
@@ -672,7 +933,8 @@ size_t tbk_flux_workspace(int32_t nocc, int32_t n, int64_t nslice, int64_t n0, i
   (void)n;
   const long long bx = (n1 - 1 + 255) / 256;
   size_t bytes = align256((size_t)(nslice * (n0 - 1) * (bx > 0 ? bx : 1)) * 8);   // block partial sums
-  bytes += align256((size_t)flux_tiles_bound(nslice, n0, n1) * 8);
+  const long long tb1 = flux_tiles_bound(nslice, n0, n1), tb2 = ring_tiles_bound(nslice, n0, n1);
+  bytes += align256((size_t)(tb1 > tb2 ? tb1 : tb2) * 8);
   if (nocc > 4) {
     const long long nlinks = nslice * ((n0 - 1) * n1 + n0 * (n1 - 1));
     bytes += align256((size_t)nlinks * 16);
@@ -714,6 +976,26 @@ int tbk_flux_plane_x(const tbk_wf_view* view, const int64_t* slice_off_dev, int6
   if (peer && peer->connected && peer->nranks > 1 && total_dev && !(rows_kernel && nslice <= kPeerMaxVals)) {
     set_error("tbk_flux_plane_x: the fused cross-rank sum needs nocc <= 2, n <= 4 and at most %d slices", kPeerMaxVals);
     return TBK_ERR_UNSUPPORTED;
+  }
+  // contiguous mesh columns: the bulk-copy ring kernel is available behind TBK_FLUX_RING=1.  Measured on B200
+  // (profiles/r01/README.md) it streams at the same ~5 TB/s as the register-prefetch kernel while the SMs are
+  // active and pays one halo row per tile, so on the 1024 x 1024 mesh it is 1-2 us slower: not the default.
+  const char* ring_env = getenv("TBK_FLUX_RING");
+  const bool ring_on = ring_env && atoi(ring_env) == 1;
+  if (rows_kernel && ring_on && stride1 == (long long)view->nsta_arr * view->n && n1 >= 64 &&
+      ((uintptr_t)view->wfs_dev & 15) == 0) {
+    double* part2 = (double*)ws;
+    int rc = TBK_OK;
+    const int key = view->nocc * 10 + view->n;
+    switch (key) {
+      case 12: rc = launch_flux_ring<1, 2>(v, off, nslice, n0, stride0, n1, plaq_dev, total_dev, part2, peer, st); break;
+      case 22: rc = launch_flux_ring<2, 2>(v, off, nslice, n0, stride0, n1, plaq_dev, total_dev, part2, peer, st); break;
+      case 13: rc = launch_flux_ring<1, 3>(v, off, nslice, n0, stride0, n1, plaq_dev, total_dev, part2, peer, st); break;
+      case 23: rc = launch_flux_ring<2, 3>(v, off, nslice, n0, stride0, n1, plaq_dev, total_dev, part2, peer, st); break;
+      case 14: rc = launch_flux_ring<1, 4>(v, off, nslice, n0, stride0, n1, plaq_dev, total_dev, part2, peer, st); break;
+      default: rc = launch_flux_ring<2, 4>(v, off, nslice, n0, stride0, n1, plaq_dev, total_dev, part2, peer, st); break;
+    }
+    return rc;
   }
   if (rows_kernel) {
     double* part2 = (double*)ws;

@@ -65,6 +65,39 @@ TBK_HD cplx cdiv(cplx a, cplx b) {
 }
 TBK_HD double cabs_(cplx a) { return hypot(a.re, a.im); }
 
+// a * b with a fixed rounding sequence (no compiler-chosen contraction): used where two code paths
+// must produce bit-identical products (periodic images written by different paths of the mesh kernel).
+TBK_HD cplx mul_fixed(cplx a, cplx b) {
+#if defined(__CUDA_ARCH__)
+  return mk(fma(a.re, b.re, -__dmul_rn(a.im, b.im)), fma(a.re, b.im, __dmul_rn(a.im, b.re)));
+#else
+  return mk(fma(a.re, b.re, -(a.im * b.im)), fma(a.re, b.im, a.im * b.re));
+#endif
+}
+// 1/sqrt(q) for q in the normal range (callers clamp away 0/denormals): hardware seed
+// (MUFU.RSQ64H, ~2^-20) + one cubically convergent step, no range-check branch — the library
+// rsqrt()/sqrt() carry a slow-path branch that splits the basic block of a register-resident
+// solver.  Relative error <= ~2 ulp.  Host emulation: 1/sqrt.
+TBK_HD double rsqrt_fast(double q) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(q));
+  const double e = fma(-q * y, y, 1.0);                 // 1 - q y^2
+  const double t = fma(e, 0.375, 0.5);                  // y' = y + y e (1/2 + 3/8 e)
+  return fma(y * e, t, y);
+#else
+  return 1.0 / sqrt(q);
+#endif
+}
+// sqrt(q) = q * rsqrt(q) with one Newton correction (q normal, > 0); returns the pair (sqrt, rsqrt)
+TBK_HD double sqrt_fast(double q, double* rs_out) {
+  const double y = rsqrt_fast(q);
+  double r = q * y;
+  r = fma(fma(-r, r, q), 0.5 * y, r);                   // r + (q - r^2) / (2 sqrt(q))
+  *rs_out = y;
+  return r;
+}
+
 // exp(2*pi*i*x): x in turns.  Device: sincospi (exact range reduction);
 // host emulation: explicit reduction to [-1/2, 1/2] turns before sin/cos.
 TBK_HD cplx expi_turns(double x) {

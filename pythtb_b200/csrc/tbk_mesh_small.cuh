@@ -21,7 +21,7 @@
 namespace tbk {
 
 constexpr int kMeshThreads = 128;
-constexpr int kMeshMaxRows = 16;
+constexpr int kMeshMaxRows = 32;
 
 struct MeshTiling {
   int nbx;              // 128-wide column blocks along the last axis
@@ -56,7 +56,7 @@ __device__ __noinline__ void mesh_store_images(const EigRows<N>& e, const OutSpe
         for (int o = 0; o < N; ++o) {
           const cplx ph = out.pbc_phase[d * N + o];
 #pragma unroll
-          for (int b = 0; b < N; ++b) im[b][o] = im[b][o] * ph;
+          for (int b = 0; b < N; ++b) im[b][o] = mul_fixed(im[b][o], ph);
         }
       }
     }
@@ -68,20 +68,72 @@ __device__ __noinline__ void mesh_store_images(const EigRows<N>& e, const OutSpe
   }
 }
 
+// 32-byte aligned 256-bit store (STG.E.ENL2.256 on sm_100): one full sector per instruction.
+__device__ __forceinline__ void st256(cplx* p, cplx a, cplx b) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a.re), "d"(a.im), "d"(b.re), "d"(b.im) : "memory");
+}
+// WIDE = false: plain 16-byte stores (cold paths; ptxas 12.9 truncates the v4.f64 asm store to its first
+// element when the operands are reloaded from local memory inside an out-of-line function).
+template <int N, bool WIDE>
+__device__ __forceinline__ void mesh_store_point(cplx* dst, const cplx (&w)[N][N]) {
+  if constexpr (N == 2 && WIDE) {
+    st256(dst, w[0][0], w[0][1]);
+    st256(dst + 2, w[1][0], w[1][1]);
+  } else if constexpr (N == 4 && WIDE) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      st256(dst + 4 * b, w[b][0], w[b][1]);
+      st256(dst + 4 * b + 2, w[b][2], w[b][3]);
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < N; ++b)
+#pragma unroll
+      for (int o = 0; o < N; ++o) dst[b * N + o] = w[b][o];
+  }
+}
+
+// cold path of the store: closing-row pbc factor, the point itself, its periodic images
+template <int N>
+__device__ __noinline__ void mesh_store_special(EigRows<N>& e, const OutSpec& out, const cplx* pbc0, long long at,
+                                                int zero_mask, int closing) {
+  if (closing) {                                    // axis-0 image of global row 0 (pythtb.py:2729); a second
+#pragma unroll                                      // multiply, so the values equal the unsharded image bit for bit
+    for (int o = 0; o < N; ++o) {
+      const cplx ph = pbc0[o];
+#pragma unroll
+      for (int b = 0; b < N; ++b) e.w[b][o] = mul_fixed(e.w[b][o], ph);
+    }
+  }
+  mesh_store_point<N, false>(out.evec + at, e.w);
+  if (zero_mask) mesh_store_images<N>(e, out, at, zero_mask);
+}
+
+struct MeshRow {                                    // per mesh row (outer index), shared memory
+  long long base;                                   // storage offset of the row, complex elements
+  int flags;                                        // bits 0..3 zero_mask, bit 8 closing row
+  int pad;
+};
+
 // Persistent kernel: the grid is one balanced wave (#SM x resident CTAs); CTA c owns the row
 // segments [c*nseg/G, (c+1)*nseg/G) — a contiguous run of rows inside one column block (two at a
-// block boundary), processed in chunks of <= kMeshMaxRows rows.
-template <int N, int NPH, int MINB>
+// block boundary), processed in chunks of <= kMeshMaxRows rows, RPI rows per loop iteration
+// (independent dependency chains in one basic block: the kernel is latency-, not bandwidth-bound).
+//
+// Gauge: the stored Convention-I eigenvector is  d_0(k) * D(k)^H u_II, i.e. component o carries
+// exp(-2 pi i k.(tau_o - tau_0)): the overall phase of an eigenvector is arbitrary (LAPACK's is too),
+// and this choice needs N-1 instead of N phase factors per k-point.
+template <int N, int NPH, int MINB, int RPI>
 __global__ void __launch_bounds__(kMeshThreads, MINB)
 mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__ KSrc ks,
                   const __grid_constant__ OutSpec out, const __grid_constant__ MeshTiling tl, int gauge,
                   double* __restrict__ gap_partial, unsigned* __restrict__ ticket, double* __restrict__ gaps_out,
                   const __grid_constant__ PeerView peer) {
   constexpr int NP = N * (N + 1) / 2;
-  constexpr int NQ = NPH + N;                       // phases, then per-state gauge factors
+  constexpr int NG = N - 1;                         // relative gauge factors of states 1..N-1
+  constexpr int NQ = NPH + NG;
   __shared__ cplx s_out[kMeshMaxRows][NQ];
-  __shared__ long long s_base[kMeshMaxRows];
-  __shared__ int s_flags[kMeshMaxRows];             // bits 0..3 zero_mask, bit 8 closing row
+  __shared__ MeshRow s_row[kMeshMaxRows];
   __shared__ double s_red[kMeshThreads / 32][N];
   __shared__ cplx s_pbc0[N];                        // pbc phase of axis 0 (closing rows of a shard)
   __shared__ int s_last;
@@ -89,8 +141,9 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
   if (threadIdx.x < N) s_pbc0[threadIdx.x] = tl.closing_g >= 0 ? out.pbc_phase[threadIdx.x] : mk(1.0, 0.0);
   const int nd = out.nd;
   const int last = nd - 1;
-  const int nph = ds.nph;   // phases p >= nph are zero-padded in the table: they contribute exactly 0
+  const int nph = ds.nph;   // phases p >= nph are skipped (uniform predicate)
   const int tid = threadIdx.x;
+  const long long gs_last = out.gstride[last];
   double gmin[N - 1];
 #pragma unroll
   for (int b = 0; b < N - 1; ++b) gmin[b] = INFINITY;
@@ -126,13 +179,16 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
         fc[p] = z;
       }
 #pragma unroll
-      for (int o = 0; o < N; ++o) {
-        if (o > 0 && ds.tau[o][last] == ds.tau[o - 1][last]) fc[NPH + o] = fc[NPH + o - 1];
-        else fc[NPH + o] = expi_turns(kl * ds.tau[o][last]);
+      for (int o = 1; o < N; ++o) {
+        const double dt = ds.tau[o][last] - ds.tau[0][last];
+        if (dt == 0.0) fc[NPH + o - 1] = mk(1.0, 0.0);
+        else if (o > 1 && ds.tau[o][last] == ds.tau[o - 1][last]) fc[NPH + o - 1] = fc[NPH + o - 2];
+        else fc[NPH + o - 1] = expi_turns(-kl * dt);
       }
     }
     const int zlast = (j == 0 && out.wrap[last]) ? (1 << last) : 0;
-    cplx* const dst_col = out.evec + (long long)j * out.gstride[last];
+    const int special_j = zlast | (closing_j ? 256 : 0);
+    cplx* const dst_col = out.evec + (long long)j * gs_last;
 
     for (int chunk = row_lo; chunk < row_hi; chunk += kMeshMaxRows) {
       const int nrows = row_hi - chunk < kMeshMaxRows ? row_hi - chunk : kMeshMaxRows;
@@ -155,86 +211,108 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
           int g = (int)idx + (d == 0 ? ks.row0 : 0);
           if (d == 0 && g == tl.closing_g) { g = 0; closing = true; }
           const double kd = ks.start[d] + (double)g / ks.den[d];                   // pythtb.py:2477
-          const double c = q < NPH ? (q < nph ? ds.R[q][d] : 0.0) : ds.tau[q - NPH][d];
+          const double c = q < NPH ? (q < nph ? ds.R[q][d] : 0.0) : -(ds.tau[q - NPH + 1][d] - ds.tau[0][d]);
           x = fma(kd, c, x);
           base += (long long)idx * out.gstride[d];
           if (idx == 0 && out.wrap[d]) zmask |= 1 << d;
         }
         s_out[r][q] = expi_turns(x);
         if (q == 0) {
-          s_base[r] = base;
-          s_flags[r] = zmask | (closing ? 256 : 0);
+          s_row[r].base = base;
+          s_row[r].flags = zmask | (closing ? 256 : 0);
         }
       }
       __syncthreads();
-      if (!active) continue;
-      for (int r = 0; r < nrows; ++r) {
-        // ---- H(k), lower triangle: straight-line over the zero-padded coefficient table
-        cplx acc[NP];
+      if (active)
+      for (int r0 = 0; r0 < nrows; r0 += RPI) {
+        // ---- H(k), lower triangle: straight-line over the coefficient table, RPI rows interleaved
+        cplx acc[RPI][NP];
+        int rr[RPI];
 #pragma unroll
-        for (int e = 0; e < NP; ++e) acc[e] = mk(ds.C[e][0], ds.C[e][1]);
+        for (int u = 0; u < RPI; ++u) {
+          rr[u] = r0 + u < nrows ? r0 + u : nrows - 1;     // tail: recompute the last row (stored once)
+#pragma unroll
+          for (int e = 0; e < NP; ++e) acc[u][e] = mk(ds.C[e][0], ds.C[e][1]);
+        }
 #pragma unroll
         for (int p = 0; p < NPH; ++p) {
-          const cplx z = s_out[r][p] * fc[p];       // exp(2 pi i k.R_p)
+          if (p < nph) {
 #pragma unroll
-          for (int e = 0; e < NP; ++e) {
-            acc[e].re = fma(ds.P[p][e][0], z.re, acc[e].re);
-            acc[e].re = fma(ds.Q[p][e][0], z.im, acc[e].re);
-            acc[e].im = fma(ds.P[p][e][1], z.re, acc[e].im);
-            acc[e].im = fma(ds.Q[p][e][1], z.im, acc[e].im);
+            for (int u = 0; u < RPI; ++u) {
+              const cplx z = s_out[rr[u]][p] * fc[p];      // exp(2 pi i k.R_p)
+#pragma unroll
+              for (int e = 0; e < NP; ++e) {
+                acc[u][e].re = fma(ds.P[p][e][0], z.re, acc[u][e].re);
+                acc[u][e].re = fma(ds.Q[p][e][0], z.im, acc[u][e].re);
+                acc[u][e].im = fma(ds.P[p][e][1], z.re, acc[u][e].im);
+                acc[u][e].im = fma(ds.Q[p][e][1], z.im, acc[u][e].im);
+              }
+            }
           }
         }
         // ---- diagonalise (rows of w = eigenvectors, ascending eigenvalues)
-        double ev[N];
-        cplx w[N][N];
-        if constexpr (N == 2) {
-          eigh2(acc[0].re, acc[2].re, acc[1], ev, w, true);
-        } else {
-          double dg[N];
-          cplx lo[N * (N - 1) / 2];
+        cplx w[RPI][N][N];
 #pragma unroll
-          for (int rr = 0; rr < N; ++rr) {
-            dg[rr] = acc[rr * (rr + 1) / 2 + rr].re;
+        for (int u = 0; u < RPI; ++u) {
+          double ev[N];
+          if constexpr (N == 2) {
+            eigh2_fast(acc[u][0].re, acc[u][2].re, acc[u][1], ev, w[u]);
+          } else {
+            double dg[N];
+            cplx lo[N * (N - 1) / 2];
 #pragma unroll
-            for (int c = 0; c < rr; ++c) lo[rr * (rr - 1) / 2 + c] = acc[rr * (rr + 1) / 2 + c];
+            for (int a = 0; a < N; ++a) {
+              dg[a] = acc[u][a * (a + 1) / 2 + a].re;
+#pragma unroll
+              for (int c = 0; c < a; ++c) lo[a * (a - 1) / 2 + c] = acc[u][a * (a + 1) / 2 + c];
+            }
+            JacobiPacked<N>::solve(dg, lo, w[u], true);
+#pragma unroll
+            for (int b = 0; b < N; ++b) ev[b] = dg[b];
           }
-          JacobiPacked<N>::solve(dg, lo, w, true);
 #pragma unroll
-          for (int b = 0; b < N; ++b) ev[b] = dg[b];
-        }
-#pragma unroll
-        for (int b = 0; b < N - 1; ++b) gmin[b] = fmin(gmin[b], ev[b + 1] - ev[b]);
-        // ---- Convention-I gauge u_I[b][o] = conj(d_o) u_II[b][o] (+ pbc phase on a closing row)
-        const int fl = s_flags[r];
-        const bool closing = (fl & 256) || closing_j;
-#pragma unroll
-        for (int o = 0; o < N; ++o) {
+          for (int b = 0; b < N - 1; ++b) gmin[b] = fmin(gmin[b], ev[b + 1] - ev[b]);
+          // ---- Convention-I gauge relative to state 0
           if (gauge) {
-            const cplx f = conj(s_out[r][NPH + o] * fc[NPH + o]);
 #pragma unroll
-            for (int b = 0; b < N; ++b) w[b][o] = w[b][o] * f;
-          }
-          if (closing) {                            // axis-0 image of global row 0 (pythtb.py:2729); a second
-            const cplx ph = s_pbc0[o];              // multiply, so the values equal the unsharded image bit for bit
+            for (int o = 1; o < N; ++o) {
+              const cplx f = s_out[rr[u]][NPH + o - 1] * fc[NPH + o - 1];
 #pragma unroll
-            for (int b = 0; b < N; ++b) w[b][o] = w[b][o] * ph;
+              for (int b = 0; b < N; ++b) w[u][b][o] = w[u][b][o] * f;
+            }
           }
         }
-        // ---- store (+ periodic images)
-        const long long base = s_base[r];
-        cplx* dst = dst_col + base;
+        // ---- store (+ periodic images / closing-row factor on the cold path)
 #pragma unroll
-        for (int b = 0; b < N; ++b)
+        for (int u = 0; u < RPI; ++u) {
+          if (u > 0 && r0 + u >= nrows) break;
+          const MeshRow mr = s_row[rr[u]];
+          // column 0 of an ordinary row: its image along the fastest axis is written by the whole CTA below
+          const int special = last == 0 ? special_j : (mr.flags ? (mr.flags | zlast) : 0);
+          if (special == 0) {
+            mesh_store_point<N, true>(dst_col + mr.base, w[u]);
+          } else {
+            EigRows<N> eg;
 #pragma unroll
-          for (int o = 0; o < N; ++o) dst[b * N + o] = w[b][o];
-        const int zero_mask = (fl & 15) | zlast;
-        if (zero_mask) {                            // cold: a copy in local memory for the out-of-line call
-          EigRows<N> eg;
+            for (int b = 0; b < N; ++b)
 #pragma unroll
-          for (int b = 0; b < N; ++b)
-#pragma unroll
-            for (int o = 0; o < N; ++o) eg.w[b][o] = w[b][o];
-          mesh_store_images<N>(eg, out, base + (long long)j * out.gstride[last], zero_mask);
+              for (int o = 0; o < N; ++o) eg.w[b][o] = w[u][b][o];
+            mesh_store_special<N>(eg, out, s_pbc0, mr.base + (long long)j * gs_last, special & 15, special & 256);
+          }
+        }
+      }
+      // ---- periodic image of column 0 along the fastest axis (pythtb.py:2729) for the ordinary rows of
+      // this chunk: one element per thread, so that no single warp pays for it (a per-row cold call in
+      // the lane that owns column 0 made the column-block-0 CTAs the tail of the wave)
+      if (bx == 0 && last > 0 && out.wrap[last]) {
+        __syncthreads();                            // the column-0 stores of this chunk are visible CTA-wide
+        const long long img = (long long)(out.full[last] - 1) * gs_last;
+        for (int t = tid; t < nrows * N * N; t += kMeshThreads) {
+          const int r = t / (N * N), e = t - r * (N * N);
+          if (s_row[r].flags != 0) continue;        // rows with their own images went through the cold path
+          cplx* src = out.evec + s_row[r].base + e;
+          const double2 t2 = __ldcg(reinterpret_cast<const double2*>(src));
+          src[img] = mul_fixed(mk(t2.x, t2.y), out.pbc_phase[last * N + (e % N)]);
         }
       }
     }

@@ -655,6 +655,7 @@ int tbk_solve_k(const tbk_model* m, const double* k_dev, int64_t nk, double* eva
 static bool mesh_small_takes(const tbk_model* m, const OutSpec& out) {
   const int n = m->pv.nsta, nd = out.nd;
   if (!m->dense.valid || n < 2 || n > 4) return false;
+  if (((uintptr_t)out.evec & 31) != 0) return false;
   if (nd > 1 && out.cnt[nd - 1] < 48) return false;   // too few points along the fastest axis to fill a CTA row
   long long nseg = (out.cnt[nd - 1] + kMeshThreads - 1) / kMeshThreads;
   for (int d = 0; d < nd - 1; ++d) nseg *= out.cnt[d];
@@ -667,6 +668,7 @@ static int launch_mesh_small(const tbk_model* m, const KSrc& ks, const OutSpec& 
   const int n = m->pv.nsta, nd = out.nd;
   if (!ds.valid || n < 2 || n > 4) return 0;
   if (nd > 1 && out.cnt[nd - 1] < 48) return 0;       // too few points along the fastest axis to fill a CTA row
+  if (((uintptr_t)out.evec & 31) != 0) return 0;      // 256-bit stores need a 32-byte aligned array
   MeshTiling tl;
   long long outer = 1;
   for (int d = 0; d < nd - 1; ++d) outer *= out.cnt[d];
@@ -678,9 +680,14 @@ static int launch_mesh_small(const tbk_model* m, const KSrc& ks, const OutSpec& 
   tl.nseg = (unsigned)nseg;
   tl.closing_g = ks.closing_g;
   const bool p4 = ds.nph <= 4;
-  // one balanced wave: #SM x (CTAs resident per SM) persistent CTAs, each with an equal share of rows
-  int occ = n == 2 ? (p4 ? 6 : 4) : (n == 3 ? 3 : 2);
-  if (n == 2 && p4) { const char* e = getenv("TBK_MESH_OCC"); if (e && atoi(e) == 5) occ = 5; }   // tuning knob
+  // one balanced wave: #SM x (CTAs resident per SM) persistent CTAs, each with an equal share of rows.
+  // n = 2 variants (resident CTAs per SM, rows per loop iteration); TBK_MESH_VARIANT is a tuning knob.
+  int variant = 0;
+  if (n == 2 && p4) { const char* e = getenv("TBK_MESH_VARIANT"); if (e) variant = atoi(e); }
+  static const int kOcc2[] = {4, 6, 5, 4, 3, 5};
+  static const int kVariants2 = 6;
+  if (variant < 0 || variant >= kVariants2) variant = 0;
+  int occ = n == 2 ? (p4 ? kOcc2[variant] : 4) : (n == 3 ? 3 : 2);
   long long want = (long long)kNumSM * occ;
   // at least ~4 rows per CTA so the per-CTA sincospi prologue stays amortised
   if (want > (nseg + 3) / 4) want = (nseg + 3) / 4;
@@ -697,11 +704,22 @@ static int launch_mesh_small(const tbk_model* m, const KSrc& ks, const OutSpec& 
   }
   const int gauge = (m->pv.convention == 1 && m->pv.dim_k > 0) ? 1 : 0;
   const PeerView pview = gaps_dev ? peer_next(peer) : peer_next(nullptr);
-#define TBK_MESH_LAUNCH(NN, PP, MB) \
-  mesh_small_kernel<NN, PP, MB><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview)
-  if (n == 2) { if (p4) { if (occ == 6) TBK_MESH_LAUNCH(2, 4, 6); else TBK_MESH_LAUNCH(2, 4, 5); } else TBK_MESH_LAUNCH(2, 8, 4); }
-  else if (n == 3) { if (p4) TBK_MESH_LAUNCH(3, 4, 3); else TBK_MESH_LAUNCH(3, 8, 3); }
-  else { if (p4) TBK_MESH_LAUNCH(4, 4, 2); else TBK_MESH_LAUNCH(4, 8, 2); }
+#define TBK_MESH_LAUNCH(NN, PP, MB, RP) \
+  mesh_small_kernel<NN, PP, MB, RP><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview)
+  if (n == 2) {
+    if (p4) {
+      switch (variant) {
+        case 1: TBK_MESH_LAUNCH(2, 4, 6, 1); break;
+        case 2: TBK_MESH_LAUNCH(2, 4, 5, 1); break;
+        case 3: TBK_MESH_LAUNCH(2, 4, 4, 1); break;
+        case 4: TBK_MESH_LAUNCH(2, 4, 3, 2); break;
+        case 5: TBK_MESH_LAUNCH(2, 4, 5, 2); break;
+        default: TBK_MESH_LAUNCH(2, 4, 4, 2); break;
+      }
+    } else TBK_MESH_LAUNCH(2, 8, 4, 1);
+  }
+  else if (n == 3) { if (p4) TBK_MESH_LAUNCH(3, 4, 3, 1); else TBK_MESH_LAUNCH(3, 8, 3, 1); }
+  else { if (p4) TBK_MESH_LAUNCH(4, 4, 2, 1); else TBK_MESH_LAUNCH(4, 8, 2, 1); }
 #undef TBK_MESH_LAUNCH
   TBK_LAUNCH_CHECK("mesh_small_kernel");
   note_kernel("mesh_small_kernel");

@@ -250,3 +250,28 @@ def test_shard_slabs_bit_identical(which):
         assert np.array_equal(got2[:-1], ref[sh.row0:sh.row0 + sh.nrows])
         assert np.all(got2[-1] == 0)
     assert np.array_equal(gaps_min, gaps_full)
+
+
+@pytest.mark.parametrize("which,mesh", [("haldane", [300, 200]), ("kane_mele", [70, 161]), ("haldane", [9, 64])])
+def test_flux_ring_kernel_matches_register_kernel(which, mesh):
+    """The cp.async.bulk ring variant of the plaquette kernel (TBK_FLUX_RING=1) against the
+    default register-prefetch kernel and the oracle: per-plaquette phases and totals."""
+    from oracle import pythtb_oracle as orc
+    mod = _mod()
+    m, occ = (M.haldane(mod, 0.0), [0]) if which == "haldane" else (M.kane_mele(mod, "odd"), [0, 1])
+    w = mod.wf_array(m, mesh)
+    w.solve_on_grid([-0.5, -0.5])
+    base_plaq = w.berry_flux(occ, individual_phases=True)
+    base_tot = w.berry_flux(occ)
+    os.environ["TBK_FLUX_RING"] = "1"
+    try:
+        ring_plaq = w.berry_flux(occ, individual_phases=True)
+        ring_tot = w.berry_flux(occ)
+        from pythtb_b200 import _engine, _lib
+        assert _lib.last_kernel(_engine.get_engine().lib) == "flux_ring_kernel"
+    finally:
+        os.environ["TBK_FLUX_RING"] = "0"
+    assert np.max(np.abs(compare.circ_diff(ring_plaq, base_plaq, 2 * np.pi))) < 1e-12
+    assert abs(ring_tot - base_tot) < 1e-9
+    ref = orc.berry_flux(np.array(w._wfs), 2, occ, None, True)
+    assert np.max(np.abs(compare.circ_diff(ring_plaq, ref, 2 * np.pi))) < 1e-8
