@@ -249,6 +249,12 @@ int64_t tbk_launch_count(void);
  * written straight into pinned host memory. */
 int tbk_stream_sync(void* stream);
 
+/* Per-stage cycle counters of the blocked eigensolver, collected when the environment has TBK_PROF=1:
+ * out8[0..3] = SM cycles spent in tridiagonalisation / bisection / inverse iteration / back-transformation
+ * (summed over CTAs), out8[4] = matrices solved, out8[5] = matrices handed to the fallback solver.
+ * Call after synchronising the stream.  Profiling aid, not part of the reference interface. */
+int tbk_debug_profile(uint64_t* out8, int32_t reset);
+
 /* L2 flush helper for benchmarks: overwrites buf_dev[bytes] (bytes > L2 size). */
 int tbk_flush_l2(void* buf_dev, size_t bytes, void* stream);
 

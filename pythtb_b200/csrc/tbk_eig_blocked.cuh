@@ -1,0 +1,623 @@
+// tbk_eig_blocked.cuh — Hermitian eigensolver for the larger supercells / Wannier models
+// (33 <= n <= 512): one matrix per CTA, the matrix itself in an L2/HBM workspace, everything
+// O(n) in shared memory.  Replaces numpy.linalg.eigh/eigvalsh (pythtb.py:939/944) for the
+// BASELINE configs 4 and 5 (ribbons with norb 200-400, the norb-499 slab).
+//
+// Stages (each one O(n^3) pass over the matrix at most):
+//   1. hetrd_blocked   Householder tridiagonalisation in panels of nb columns (LAPACK zhetrd /
+//                      zlatrd, lower): per column ONE matrix-vector product with the stored
+//                      trailing matrix plus O(n nb) panel corrections, and one rank-2nb update
+//                      of the trailing matrix per panel (panels V, W live in shared memory).
+//                      Memory traffic ~ (16/3) n^3 bytes instead of ~16 n^3 for the unblocked
+//                      column-by-column update.
+//   2. tridiag_bisect  all eigenvalues of the real symmetric tridiagonal by Sturm-sequence
+//                      bisection, one eigenvalue per thread (embarrassingly parallel; the QL
+//                      iteration it replaces is a serial chain of n^2 rotations).
+//   3. tridiag_invit   eigenvectors of the tridiagonal by inverse iteration (LAPACK dstein's
+//                      scheme: partially pivoted LU of T - lambda I, perturbed pivots, close
+//                      eigenvalues separated by 10 eps |T|), one eigenvector per thread, then
+//                      modified Gram-Schmidt inside clusters of close eigenvalues, one cluster
+//                      per warp.  O(n^2) per matrix instead of 6 n^3 for rotations applied to Q.
+//   4. backtransform   x = H_0 H_1 ... H_{n-2} z  for every eigenvector, one column per warp held
+//                      in registers, the reflectors streamed from L2 (8 n^3 flops).
+// A cluster vector that loses its norm in the Gram-Schmidt step is regenerated (new random start,
+// orthogonalised before and after every solve, as dstein does); should that fail too, the matrix is
+// reported through the return code and re-solved by the unblocked Householder + implicit-QL solver
+// (tbk_eig_group.cuh).
+//
+// The code is SPMD over the same abstract group as tbk_eig_group.cuh, extended by sub-teams:
+//     g.nsub(), g.sub()        number of sub-teams (warps) and this thread's
+//     g.lane(), g.subsize()    rank inside the sub-team and its size
+//     g.subsum(x)              all-reduce inside the sub-team (no block barrier)
+//     g.subsync()              barrier + memory fence for the sub-team
+// so that the identical source runs as a CTA on the GPU and as a "group" of one host thread in
+// the CPU unit tests (tests/hostemu).
+#pragma once
+#include "tbk_common.cuh"
+
+namespace tbk {
+
+constexpr int kBlkMaxN = 512;
+
+struct BlkWork {
+  int n, lda, nb;
+  cplx* A;         // [n x lda] column-major, lower triangle valid on entry (global)
+  cplx* V;         // [nb][n] reflector panel            (shared memory on the device)
+  cplx* W;         // [nb][n] zlatrd's W panel           (shared)
+  cplx* part;      // [group size] partial sums of the split matrix-vector product (shared)
+  cplx* dots;      // [2 nb] panel dot products           (shared)
+  cplx* tau;       // [n]                                 (shared)
+  double* d;       // [n] diagonal of T                   (shared)
+  double* e;       // [n] sub-diagonal of T               (shared)
+  double* e2;      // [n] e^2                             (shared)
+  double* lam;     // [n] eigenvalues, ascending          (shared)
+  double* lamp;    // [n] perturbed eigenvalues used by the inverse iteration (shared)
+  int* cl;         // [n] first index of the cluster each eigenvalue belongs to (shared)
+  int* ctl;        // [4] status words                    (shared)
+  double* Z;       // [n][n] row-major: Z[i*n + j] = component i of tridiagonal eigenvector j (global)
+  double* lu;      // [4][n][nt] interleaved per-thread LU rows, nt = min(group size, n rounded up) (global)
+  int nt;
+};
+
+TBK_HD size_t blk_shared_bytes(int n, int nb, int nthreads) {
+  return (size_t)2 * nb * n * 16 + (size_t)nthreads * 16 + (size_t)2 * nb * 16 + (size_t)n * 16 + (size_t)5 * n * 8 +
+         (size_t)n * 4 + 64;
+}
+
+// carve the shared part of a BlkWork out of one 16-byte aligned buffer
+TBK_HD void blk_carve_shared(BlkWork& w, void* base, int nthreads) {
+  char* p = (char*)base;
+  const int n = w.n, nb = w.nb;
+  w.V = (cplx*)p;    p += (size_t)nb * n * 16;
+  w.W = (cplx*)p;    p += (size_t)nb * n * 16;
+  w.part = (cplx*)p; p += (size_t)nthreads * 16;
+  w.dots = (cplx*)p; p += (size_t)2 * nb * 16;
+  w.tau = (cplx*)p;  p += (size_t)n * 16;
+  w.d = (double*)p;  p += (size_t)n * 8;
+  w.e = (double*)p;  p += (size_t)n * 8;
+  w.e2 = (double*)p; p += (size_t)n * 8;
+  w.lam = (double*)p;  p += (size_t)n * 8;
+  w.lamp = (double*)p; p += (size_t)n * 8;
+  w.cl = (int*)p;    p += (size_t)n * 4;
+  w.ctl = (int*)p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1. blocked tridiagonalisation.  On exit d, e hold T, the Householder vectors are stored below the
+// first sub-diagonal of A (zhetd2 'L' layout, implicit unit at row j+1) with their scalars in tau.
+// The strict upper triangle is overwritten (it is filled from the lower one first).
+// ---------------------------------------------------------------------------------------------
+template <class G>
+TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
+  const int n = w.n, lda = w.lda, nb = w.nb;
+  const int T = g.size(), tid = g.tid();
+  cplx* A = w.A;
+  cplx* V = w.V;
+  cplx* W = w.W;
+  // full Hermitian storage: upper from lower, real diagonal
+  for (int c = tid; c < n; c += T) A[c + (size_t)c * lda].im = 0.0;
+  for (int r = tid; r < n; r += T)
+    for (int c = r + 1; c < n; ++c) A[r + (size_t)c * lda] = conj(A[c + (size_t)r * lda]);
+  g.sync();
+  for (int j0 = 0; j0 < n - 1; j0 += nb) {
+    const int nbp = n - 1 - j0 < nb ? n - 1 - j0 : nb;
+    // zero the panels (unused panel columns must be exactly zero for the rank-2nb update)
+    for (int q = tid; q < nb * n; q += T) { V[q] = mk(0.0, 0.0); W[q] = mk(0.0, 0.0); }
+    g.sync();
+    for (int i = 0; i < nbp; ++i) {
+      const int j = j0 + i;
+      cplx* col = A + (size_t)j * lda;
+      // ---- (1) bring column j up to date with the reflectors of this panel
+      if (i > 0) {
+        for (int r = j + tid; r < n; r += T) {
+          cplx a = col[r];
+          for (int k = 0; k < i; ++k) {
+            a = a - mulc(V[k * n + r], W[k * n + j]);
+            a = a - mulc(W[k * n + r], V[k * n + j]);
+          }
+          if (r == j) a.im = 0.0;
+          col[r] = a;
+        }
+        g.sync();
+      }
+      // ---- (2) reflector for x = A(j+1:n, j)   (zlarfg)
+      double part = 0.0;
+      for (int r = j + 2 + tid; r < n; r += T) part += norm2(col[r]);
+      const double xnorm2 = g.sum(part);
+      const cplx alpha = col[j + 1];
+      cplx tau = mk(0.0, 0.0);
+      double beta = alpha.re;
+      cplx scal = mk(0.0, 0.0);
+      if (xnorm2 != 0.0 || alpha.im != 0.0) {
+        beta = -copysign(sqrt(alpha.re * alpha.re + alpha.im * alpha.im + xnorm2), alpha.re);
+        tau = mk((beta - alpha.re) / beta, -alpha.im / beta);
+        scal = cdiv(mk(1.0, 0.0), mk(alpha.re - beta, alpha.im));
+      }
+      g.sync();                                   // everyone has read alpha
+      cplx* v = V + i * n;
+      for (int r = j + 2 + tid; r < n; r += T) {
+        const cplx x = col[r] * scal;             // tau == 0: the column is already zero below j+1
+        col[r] = x;
+        v[r] = x;
+      }
+      if (tid == 0) {
+        v[j + 1] = mk(1.0, 0.0);
+        w.e[j] = beta;
+        w.tau[j] = tau;
+        w.d[j] = col[j].re;
+      }
+      g.sync();
+      // ---- (3) w = A22 v with the stored (panel-start) trailing matrix, rows/cols j+1 .. n-1
+      const int m = n - j - 1;
+      {
+        int rw = ((m + 31) / 32) * 32;
+        if (rw > T) rw = T;
+        const int parts = T / rw > 0 ? T / rw : 1;
+        const int pr = tid % rw, pp = tid / rw;
+        if (pp < parts) {
+          for (int rb = 0; rb < m; rb += rw) {    // rb > 0 only when m > T
+            const int r = j + 1 + rb + pr;
+            cplx acc = mk(0.0, 0.0);
+            if (r < n) {
+              // four independent accumulators: four loads in flight per thread, no serial FMA chain
+              const cplx* arow = A + r;
+              cplx a0 = mk(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0;
+              int c = j + 1 + pp;
+              for (; c + 3 * parts < n; c += 4 * parts) {
+                const cplx m0 = arow[(size_t)c * lda], m1 = arow[(size_t)(c + parts) * lda];
+                const cplx m2 = arow[(size_t)(c + 2 * parts) * lda], m3 = arow[(size_t)(c + 3 * parts) * lda];
+                fma_acc(a0, m0, v[c]);
+                fma_acc(a1, m1, v[c + parts]);
+                fma_acc(a2, m2, v[c + 2 * parts]);
+                fma_acc(a3, m3, v[c + 3 * parts]);
+              }
+              for (; c < n; c += parts) fma_acc(a0, arow[(size_t)c * lda], v[c]);
+              acc = (a0 + a1) + (a2 + a3);
+            }
+            if (parts == 1) {
+              if (r < n) W[i * n + r] = acc;
+            } else {                              // parts > 1 implies m <= rw: a single row block
+              w.part[pp * rw + pr] = acc;
+            }
+          }
+        }
+        if (parts > 1) {
+          g.sync();
+          for (int r = tid; r < m; r += T) {
+            cplx acc = w.part[r];
+            for (int q = 1; q < parts; ++q) acc = acc + w.part[q * rw + r];
+            W[i * n + j + 1 + r] = acc;
+          }
+        }
+      }
+      g.sync();
+      // ---- panel corrections: dots[k] = W_k^H v, dots[nb+k] = V_k^H v, one sub-team per dot product
+      if (i > 0) {
+        for (int q = g.sub(); q < 2 * i; q += g.nsub()) {
+          const cplx* src = q < i ? W + q * n : V + (q - i) * n;
+          double sre = 0.0, sim = 0.0;
+          for (int r = j + 1 + g.lane(); r < n; r += g.subsize()) {
+            const cplx t = cmul(src[r], v[r]);
+            sre += t.re; sim += t.im;
+          }
+          sre = g.subsum(sre); sim = g.subsum(sim);
+          if (g.lane() == 0) w.dots[q < i ? q : nb + (q - i)] = mk(sre, sim);
+        }
+        g.sync();
+        for (int r = j + 1 + tid; r < n; r += T) {
+          cplx acc = W[i * n + r];
+          for (int k = 0; k < i; ++k) {
+            acc = acc - V[k * n + r] * w.dots[k];
+            acc = acc - W[k * n + r] * w.dots[nb + k];
+          }
+          W[i * n + r] = acc;
+        }
+        g.sync();
+      }
+      // ---- w = tau w;  w += (-tau/2 (w^H v)) v
+      double dre = 0.0, dim = 0.0;
+      for (int r = j + 1 + tid; r < n; r += T) {
+        const cplx wr = tau * W[i * n + r];
+        W[i * n + r] = wr;
+        const cplx t = cmul(wr, v[r]);
+        dre += t.re; dim += t.im;
+      }
+      dre = g.sum(dre); dim = g.sum(dim);        // g.sum synchronises: the scaled w is visible
+      const cplx a2 = (-0.5) * (tau * mk(dre, dim));
+      for (int r = j + 1 + tid; r < n; r += T) W[i * n + r] = W[i * n + r] + a2 * v[r];
+      g.sync();
+    }
+    // ---- rank-2nb update of the trailing matrix: A22 -= V W^H + W V^H   (rows/cols >= j1)
+    const int j1 = j0 + nbp;
+    const int m = n - j1;
+    if (m > 0) {
+      int rw = ((m + 31) / 32) * 32;
+      if (rw > T) rw = T;
+      const int parts = T / rw > 0 ? T / rw : 1;
+      const int pr = tid % rw, pp = tid / rw;
+      if (pp < parts) {
+        for (int r = j1 + pr; r < n; r += rw) {
+          for (int k0 = 0; k0 < nb; k0 += 8) {    // 8 panel columns at a time in registers
+            if (k0 >= nbp) break;
+            cplx vr[8], wr[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int k = 0; k < 8; ++k) {
+              const bool in = k0 + k < nb;
+              vr[k] = in ? V[(k0 + k) * n + r] : mk(0.0, 0.0);
+              wr[k] = in ? W[(k0 + k) * n + r] : mk(0.0, 0.0);
+            }
+            for (int c = j1 + pp; c < n; c += parts) {
+              cplx a = A[r + (size_t)c * lda];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+              for (int k = 0; k < 8; ++k) {
+                if (k0 + k < nb) {
+                  const cplx wc = W[(k0 + k) * n + c], vc = V[(k0 + k) * n + c];
+                  // a -= vr * conj(wc) + wr * conj(vc)
+                  a.re -= vr[k].re * wc.re + vr[k].im * wc.im + wr[k].re * vc.re + wr[k].im * vc.im;
+                  a.im -= vr[k].im * wc.re - vr[k].re * wc.im + wr[k].im * vc.re - wr[k].re * vc.im;
+                }
+              }
+              A[r + (size_t)c * lda] = a;
+            }
+          }
+        }
+      }
+      g.sync();
+    }
+  }
+  if (tid == 0) {
+    w.d[n - 1] = A[(n - 1) + (size_t)(n - 1) * lda].re;
+    w.e[n - 1] = 0.0;
+    w.tau[n - 1] = mk(0.0, 0.0);
+  }
+  g.sync();
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. eigenvalues of the tridiagonal (d, e) by bisection on the Sturm count; lam ascending.
+// Returns (through every thread) the norm estimate tnorm = max Gershgorin radius.
+// ---------------------------------------------------------------------------------------------
+TBK_HD int sturm_count(int n, const double* d, const double* e2, double x, double pivmin) {
+  int cnt = 0;
+  double q = d[0] - x;
+  if (fabs(q) < pivmin) q = -pivmin;
+  cnt += q < 0.0;
+  for (int i = 1; i < n; ++i) {
+    q = d[i] - x - e2[i - 1] / q;
+    if (fabs(q) < pivmin) q = -pivmin;
+    cnt += q < 0.0;
+  }
+  return cnt;
+}
+
+template <class G>
+TBK_HD double tridiag_bisect(G& g, const BlkWork& w) {
+  const int n = w.n;
+  const double eps = 2.220446049250313e-16, safmin = 2.2250738585072014e-308;
+  for (int i = g.tid(); i < n; i += g.size()) w.e2[i] = i < n - 1 ? w.e[i] * w.e[i] : 0.0;
+  g.sync();
+  // Gershgorin interval and pivmin, computed redundantly by every thread (O(n), shared reads)
+  double gl = w.d[0] - fabs(w.e[0]), gu = w.d[0] + fabs(w.e[0]), emax = 0.0;
+  if (n == 1) { gl = gu = w.d[0]; }
+  for (int i = 1; i < n; ++i) {
+    const double rad = fabs(w.e[i - 1]) + (i < n - 1 ? fabs(w.e[i]) : 0.0);
+    gl = fmin(gl, w.d[i] - rad);
+    gu = fmax(gu, w.d[i] + rad);
+    emax = fmax(emax, w.e2[i - 1]);
+  }
+  const double tnorm = fmax(fabs(gl), fabs(gu));
+  const double pivmin = safmin * fmax(1.0, emax);
+  gl -= 2.1 * tnorm * eps * n + 2.1 * pivmin;
+  gu += 2.1 * tnorm * eps * n + 2.1 * pivmin;
+  const double atol = 0.25 * eps * tnorm + 2.0 * pivmin;
+  for (int j = g.tid(); j < n; j += g.size()) {
+    double lo = gl, hi = gu;
+    for (int it = 0; it < 120; ++it) {
+      const double mid = 0.5 * (lo + hi);
+      if (hi - lo <= atol + eps * (fabs(lo) + fabs(hi)) || mid <= lo || mid >= hi) break;
+      if (sturm_count(n, w.d, w.e2, mid, pivmin) > j) hi = mid; else lo = mid;
+    }
+    w.lam[j] = 0.5 * (lo + hi);
+  }
+  g.sync();
+  return tnorm;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. eigenvectors of the tridiagonal by inverse iteration.  Returns 0, or 1 if the spectrum needs
+// the fallback solver (huge cluster / dependent cluster vectors).
+// ---------------------------------------------------------------------------------------------
+TBK_HD double invit_rand(unsigned& s) {               // uniform in (-1, 1), deterministic
+  s = s * 1664525u + 1013904223u;
+  return ((double)(s >> 8) + 0.5) * (2.0 / 16777216.0) - 1.0;
+}
+
+// One inverse-iteration solve (T - lam I) x = y for the thread that owns column t of the interleaved
+// scratch arrays (element i of a per-thread array lives at [i * nt + t]); y is scaled to max-norm 1
+// first, x overwrites y.  Partially pivoted elimination fused with the forward substitution
+// (LAPACK dlagtf + dlagts), tiny pivots replaced by +-pivtol.
+TBK_HD void tridiag_shifted_solve(int n, const double* d, const double* e, double lam, double pivtol,
+                                  double* U0, double* U1, double* U2, double* Y, int nt, int t) {
+  double mx = 0.0;
+  for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(Y[(size_t)i * nt + t]));
+  const double sc = mx > 0.0 ? 1.0 / mx : 1.0;
+  double ak = d[0] - lam, bk = n > 1 ? e[0] : 0.0, yk = Y[t] * sc;
+  for (int k = 0; k < n - 1; ++k) {
+    const double c = e[k], a1 = d[k + 1] - lam, b1 = k + 1 < n - 1 ? e[k + 1] : 0.0;
+    const double y1 = Y[(size_t)(k + 1) * nt + t] * sc;
+    const size_t at = (size_t)k * nt + t;
+    if (fabs(c) <= fabs(ak)) {
+      const double mult = ak != 0.0 ? c / ak : 0.0;
+      U0[at] = ak; U1[at] = bk; U2[at] = 0.0; Y[at] = yk;
+      ak = a1 - mult * bk; bk = b1; yk = y1 - mult * yk;
+    } else {
+      const double mult = ak / c;
+      U0[at] = c; U1[at] = a1; U2[at] = b1; Y[at] = y1;
+      ak = bk - mult * a1; bk = -mult * b1; yk = yk - mult * y1;
+    }
+  }
+  {
+    const size_t at = (size_t)(n - 1) * nt + t;
+    U0[at] = ak; U1[at] = 0.0; U2[at] = 0.0; Y[at] = yk;
+  }
+  double x1 = 0.0, x2 = 0.0;
+  for (int k = n - 1; k >= 0; --k) {
+    const size_t at = (size_t)k * nt + t;
+    double piv = U0[at];
+    if (fabs(piv) < pivtol) piv = piv < 0.0 ? -pivtol : pivtol;
+    const double x = (Y[at] - U1[at] * x1 - U2[at] * x2) / piv;
+    Y[at] = x;
+    x2 = x1; x1 = x;
+  }
+}
+
+// Returns 0, or 1 if a cluster vector could not be made independent (the caller then uses the
+// unblocked QL solver for this matrix).
+template <class G>
+TBK_HD int tridiag_invit(G& g, const BlkWork& w, double tnorm) {
+  const int n = w.n, nt = w.nt;
+  const double eps = 2.220446049250313e-16;
+  const double scale = tnorm > 0.0 ? tnorm : 1.0;
+  const double pertol = 10.0 * eps * scale;       // minimal separation of the shifts (dstein)
+  const double ortol = 1.0e-4 * scale;            // closer eigenvalues are orthogonalised explicitly
+  const double pivtol = eps * scale;
+  // ---- serial pre-pass: separated shifts and clusters
+  if (g.tid() == 0) {
+    w.lamp[0] = w.lam[0];
+    w.cl[0] = 0;
+    for (int j = 1; j < n; ++j) {
+      double x = w.lam[j];
+      if (x - w.lamp[j - 1] < pertol) x = w.lamp[j - 1] + pertol;
+      w.lamp[j] = x;
+      w.cl[j] = (w.lam[j] - w.lam[j - 1] < ortol) ? w.cl[j - 1] : j;
+    }
+    w.ctl[1] = 0;
+  }
+  g.sync();
+  double* U0 = w.lu;
+  double* U1 = U0 + (size_t)n * nt;
+  double* U2 = U1 + (size_t)n * nt;
+  double* Y = U2 + (size_t)n * nt;
+  // ---- phase 1: every eigenvector independently, one per thread, three solves from a random start
+  for (int j0 = 0; j0 < n; j0 += nt) {
+    const int t = g.tid();
+    const int j = j0 + t;
+    if (t < nt && j < n) {
+      unsigned seed = 0x9E3779B9u * (unsigned)(j + 1) + 12345u;
+      for (int i = 0; i < n; ++i) Y[(size_t)i * nt + t] = invit_rand(seed);
+      for (int it = 0; it < 3; ++it) tridiag_shifted_solve(n, w.d, w.e, w.lamp[j], pivtol, U0, U1, U2, Y, nt, t);
+      // normalise, largest component positive, store as column j of Z
+      double nrm = 0.0, big = 0.0;
+      for (int i = 0; i < n; ++i) {
+        const double x = Y[(size_t)i * nt + t];
+        nrm += x * x;
+        if (fabs(x) > fabs(big)) big = x;
+      }
+      const double sc = (big < 0.0 ? -1.0 : 1.0) / sqrt(nrm);
+      for (int i = 0; i < n; ++i) w.Z[(size_t)i * n + j] = Y[(size_t)i * nt + t] * sc;
+    }
+    g.sync();
+  }
+  // ---- phase 2: modified Gram-Schmidt inside clusters, one cluster per sub-team.  A member that loses
+  // its norm against the earlier members (it converged to the same direction of a degenerate
+  // eigenspace) is regenerated dstein-style: new random start, orthogonalised BEFORE and after
+  // each solve; the solve itself is done by the sub-team's lane 0 in its private scratch column.
+  for (int s = g.sub(); s < n; s += g.nsub()) {
+    if (w.cl[s] != s) continue;                    // s is not the first member of a cluster
+    int last = s;
+    while (last + 1 < n && w.cl[last + 1] == s) ++last;
+    if (last == s) continue;
+    const int L = g.lane(), S = g.subsize();
+    const int t0 = g.tid() - L;                    // scratch column of this sub-team's lane 0
+    const bool have_scratch = t0 < nt;
+    for (int b = s + 1; b <= last; ++b) {
+      int attempt = 0, solves = 0;
+      for (int round = 0; round < 16; ++round) {
+        // project out the earlier members (twice), measuring the norm that survives the first pass
+        double keep = 1.0;
+        for (int pass = 0; pass < 2; ++pass) {
+          double before = 0.0;
+          for (int i = L; i < n; i += S) { const double x = w.Z[(size_t)i * n + b]; before += x * x; }
+          before = sqrt(g.subsum(before));
+          for (int a = s; a < b; ++a) {
+            double dot = 0.0;
+            for (int i = L; i < n; i += S) dot += w.Z[(size_t)i * n + a] * w.Z[(size_t)i * n + b];
+            dot = g.subsum(dot);
+            for (int i = L; i < n; i += S) w.Z[(size_t)i * n + b] -= dot * w.Z[(size_t)i * n + a];
+            g.subsync();
+          }
+          double nrm = 0.0;
+          for (int i = L; i < n; i += S) { const double x = w.Z[(size_t)i * n + b]; nrm += x * x; }
+          nrm = sqrt(g.subsum(nrm));
+          if (pass == 0) keep = before > 0.0 ? nrm / before : 0.0;
+          const double sc = nrm > 0.0 ? 1.0 / nrm : 0.0;
+          for (int i = L; i < n; i += S) w.Z[(size_t)i * n + b] *= sc;
+          g.subsync();
+        }
+        // done when the vector kept a fair share of its norm and (if regenerated) went through three solves
+        if (keep >= 1.0e-2 && (attempt == 0 || solves >= 3)) break;
+        if (!have_scratch || round == 15) {        // cannot iterate here / no independent direction found
+          if (L == 0) w.ctl[1] = 1;
+          break;
+        }
+        if (keep < 1.0e-2) {                        // dependent: restart from a fresh random vector
+          ++attempt;
+          solves = 0;
+          for (int i = L; i < n; i += S) {
+            unsigned seed = 0x85EBCA6Bu * (unsigned)(b + 1) + 0xC2B2AE35u * (unsigned)(i + 1) + 977u * (unsigned)attempt;
+            invit_rand(seed);
+            w.Z[(size_t)i * n + b] = invit_rand(seed);
+          }
+          g.subsync();
+          continue;                                 // orthogonalise the start vector first
+        }
+        // one more solve on the orthogonalised vector
+        ++solves;
+        if (L == 0) {
+          for (int i = 0; i < n; ++i) Y[(size_t)i * nt + t0] = w.Z[(size_t)i * n + b];
+          tridiag_shifted_solve(n, w.d, w.e, w.lamp[b], pivtol, U0, U1, U2, Y, nt, t0);
+          for (int i = 0; i < n; ++i) w.Z[(size_t)i * n + b] = Y[(size_t)i * nt + t0];
+        }
+        g.subsync();
+      }
+    }
+  }
+  g.sync();
+  return w.ctl[1];
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. back-transformation of ONE tridiagonal eigenvector (column c of Z) by a sub-team:
+// x = H_0 H_1 ... H_{n-2} z, reflectors in A (zhetd2 'L' layout).  Element r of x is owned by lane
+// r % subsize, slot r / subsize; MAXM >= ceil(n / subsize).  The result is handed to `store(r, x_r)`.
+// ---------------------------------------------------------------------------------------------
+template <int MAXM, class G, class Store>
+TBK_HD void backtransform_column(G& g, const BlkWork& w, int c, Store store) {
+  const int n = w.n, lda = w.lda;
+  const int L = g.lane(), S = g.subsize();
+  cplx x[MAXM];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int m = 0; m < MAXM; ++m) {
+    const int r = L + S * m;
+    x[m] = mk(r < n ? w.Z[(size_t)r * n + c] : 0.0, 0.0);
+  }
+  for (int j = n - 2; j >= 0; --j) {
+    const cplx tau = w.tau[j];
+    if (tau.re == 0.0 && tau.im == 0.0) continue;
+    const cplx* vcol = w.A + (size_t)j * lda;
+    double dre = 0.0, dim = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int m = 0; m < MAXM; ++m) {
+      const int r = L + S * m;
+      if (r > j && r < n) {
+        const cplx v = r == j + 1 ? mk(1.0, 0.0) : vcol[r];
+        const cplx t = cmul(v, x[m]);             // conj(v) x
+        dre += t.re; dim += t.im;
+      }
+    }
+    dre = g.subsum(dre); dim = g.subsum(dim);
+    const cplx f = tau * mk(dre, dim);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int m = 0; m < MAXM; ++m) {
+      const int r = L + S * m;
+      if (r > j && r < n) {                       // second read of v: an L1 hit, cheaper than MAXM live registers
+        const cplx v = r == j + 1 ? mk(1.0, 0.0) : vcol[r];
+        x[m] = x[m] - f * v;
+      }
+    }
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int m = 0; m < MAXM; ++m) {
+    const int r = L + S * m;
+    if (r < n) store(r, x[m]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4b. back-transformation of ALL tridiagonal eigenvectors by the whole group: every sub-team owns
+// one column of a batch of nsub columns (held in registers as above); the reflectors are staged
+// RB at a time in `stage` (shared memory, [RB][n], zero above the unit element) by all threads,
+// so that the matrix of reflectors is read from L2/HBM once per column batch instead of once per
+// column.  store(c, r, x_r) receives element r of eigenvector c.
+// ---------------------------------------------------------------------------------------------
+template <int MAXM, class G, class Store>
+TBK_HD void backtransform_all(G& g, const BlkWork& w, cplx* stage, int RB, Store store) {
+  const int n = w.n, lda = w.lda;
+  const int L = g.lane(), S = g.subsize(), T = g.size(), tid = g.tid();
+  for (int c0 = 0; c0 < n; c0 += g.nsub()) {
+    const int c = c0 + g.sub();
+    const bool active = c < n;
+    cplx x[MAXM];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int m = 0; m < MAXM; ++m) {
+      const int r = L + S * m;
+      x[m] = mk((active && r < n) ? w.Z[(size_t)r * n + c] : 0.0, 0.0);
+    }
+    for (int jhi = n - 2; jhi >= 0; jhi -= RB) {
+      const int jlo = jhi - RB + 1 > 0 ? jhi - RB + 1 : 0;
+      const int cnt = jhi - jlo + 1;
+      g.sync();                                   // the previous stage has been consumed
+      for (int q = tid; q < cnt * n; q += T) {
+        const int jj = q / n, r = q - jj * n, j = jlo + jj;
+        stage[q] = r > j + 1 ? w.A[r + (size_t)j * lda] : mk(r == j + 1 ? 1.0 : 0.0, 0.0);
+      }
+      g.sync();
+      if (!active) continue;
+      for (int j = jhi; j >= jlo; --j) {
+        const cplx tau = w.tau[j];
+        if (tau.re == 0.0 && tau.im == 0.0) continue;
+        const cplx* v = stage + (size_t)(j - jlo) * n;
+        double dre = 0.0, dim = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int m = 0; m < MAXM; ++m) {
+          if (S * m + S - 1 > j) {                // sub-team-uniform: this slot holds rows > j
+            const int r = L + S * m;
+            if (r < n) {
+              const cplx t = cmul(v[r], x[m]);    // conj(v) x; v is zero for r <= j
+              dre += t.re; dim += t.im;
+            }
+          }
+        }
+        dre = g.subsum(dre); dim = g.subsum(dim);
+        const cplx f = tau * mk(dre, dim);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int m = 0; m < MAXM; ++m) {
+          if (S * m + S - 1 > j) {
+            const int r = L + S * m;
+            if (r < n) x[m] = x[m] - f * v[r];
+          }
+        }
+      }
+    }
+    if (active) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int m = 0; m < MAXM; ++m) {
+        const int r = L + S * m;
+        if (r < n) store(c, r, x[m]);
+      }
+    }
+  }
+  g.sync();
+}
+
+}  // namespace tbk

@@ -62,6 +62,17 @@ struct BlockGroup {
   __device__ int tid() const { return threadIdx.x; }
   __device__ int size() const { return blockDim.x; }
   __device__ void sync() { __syncthreads(); }
+  // sub-teams = warps (tbk_eig_blocked.cuh)
+  __device__ int nsub() const { return blockDim.x >> 5; }
+  __device__ int sub() const { return threadIdx.x >> 5; }
+  __device__ int lane() const { return threadIdx.x & 31; }
+  __device__ int subsize() const { return 32; }
+  __device__ void subsync() { __syncwarp(); }
+  __device__ double subsum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+  }
   __device__ double sum(double x) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);

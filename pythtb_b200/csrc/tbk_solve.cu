@@ -19,6 +19,7 @@
 #include "tbk_internal.cuh"
 #include "tbk_eig_small.cuh"
 #include "tbk_eig_group.cuh"
+#include "tbk_eig_blocked.cuh"
 
 namespace tbk {
 
@@ -419,6 +420,183 @@ solve_block_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long lon
 }
 
 // ===========================================================================
+// nsta > 32, blocked solver (tbk_eig_blocked.cuh): one k-point per CTA, H(k) and the
+// tridiagonal eigenvectors in an L2/HBM workspace, panels and all O(n) data in shared memory
+// ===========================================================================
+struct BlkShape {
+  int n, lda, nb, nt, threads, nph;
+  size_t off_ph, off_gf, off_misc, smem;             // shared-memory layout after the BlkWork part
+  size_t ws_A, ws_Z, ws_lu, ws_block;                // per-CTA global workspace, bytes
+  GroupShape fallback;                               // unblocked solver's layout inside the same shared buffer
+};
+
+static BlkShape blk_shape(int n, int nph) {
+  BlkShape s;
+  s.n = n; s.lda = n | 1; s.nph = nph;
+  s.threads = n <= 256 ? 256 : 512;
+  auto total = [&](int nb) {
+    size_t off = (blk_shared_bytes(n, nb, s.threads) + 15) & ~(size_t)15;
+    off += (size_t)(nph > 0 ? nph : 1) * 16 + (size_t)n * 16 + 128;
+    return off;
+  };
+  // as many resident CTAs as possible matter more than wide panels: nb = 16 only if two CTAs still fit
+  s.nb = total(16) * 2 + 2048 <= (size_t)kMaxSmem ? 16 : 8;
+  size_t off = (blk_shared_bytes(n, s.nb, s.threads) + 15) & ~(size_t)15;
+  s.off_ph = off;   off += (size_t)(nph > 0 ? nph : 1) * 16;
+  s.off_gf = off;   off += (size_t)n * 16;
+  s.off_misc = off; off += 128;
+  s.fallback = group_shape(n, nph, false);
+  s.smem = off > s.fallback.region ? off : s.fallback.region;
+  s.nt = ((n + 31) / 32) * 32;
+  if (s.nt > s.threads) s.nt = s.threads;
+  s.ws_A = ((size_t)n * s.lda * 16 + 255) & ~(size_t)255;
+  s.ws_Z = ((size_t)n * n * 8 + 255) & ~(size_t)255;
+  s.ws_lu = ((size_t)4 * n * s.nt * 8 + 255) & ~(size_t)255;
+  s.ws_block = s.ws_A + s.ws_Z + s.ws_lu;
+  return s;
+}
+
+static long long blk_blocks(const BlkShape& s, long long npts) {
+  int per_sm = (int)((size_t)kMaxSmem / (s.smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  const int by_threads = 2048 / s.threads;
+  if (per_sm > by_threads) per_sm = by_threads;
+  if (per_sm > 4) per_sm = 4;
+  const long long cap = (long long)kNumSM * per_sm;
+  return npts < cap ? npts : cap;
+}
+
+// Optional per-stage cycle counters (TBK_PROF=1): pinned host words the kernel adds clock64 deltas to
+// [0] hetrd [1] bisect [2] invit [3] backtransform [4] matrices [5] fallbacks; read by tbk_debug_profile.
+static unsigned long long* g_blk_prof = nullptr;
+static unsigned long long* blk_prof() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("TBK_PROF"); on = (e && atoi(e) == 1) ? 1 : 0; }
+  if (!on) return nullptr;
+  if (!g_blk_prof) {
+    if (cudaMallocHost((void**)&g_blk_prof, 8 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+    memset(g_blk_prof, 0, 8 * sizeof(unsigned long long));
+  }
+  return g_blk_prof;
+}
+
+template <int MAXM>
+__global__ void __launch_bounds__(512)
+solve_blocked_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long long npts, OutSpec out, int want_vec,
+                     BlkShape shp, char* __restrict__ gws, unsigned long long* prof) {
+  extern __shared__ __align__(16) char smem[];
+  __shared__ double red[32];
+  BlockGroup g(red);
+  const int n = shp.n, lda = shp.lda, tid = threadIdx.x, T = blockDim.x;
+  BlkWork w;
+  w.n = n; w.lda = lda; w.nb = shp.nb; w.nt = shp.nt;
+  blk_carve_shared(w, smem, shp.threads);
+  cplx* ph = (cplx*)(smem + shp.off_ph);
+  cplx* gf = (cplx*)(smem + shp.off_gf);
+  double* kbuf = (double*)(smem + shp.off_misc);
+  int* mibuf = (int*)(kbuf + TBK_MAX_DIM);
+  char* mine = gws + (size_t)blockIdx.x * shp.ws_block;
+  w.A = (cplx*)mine;
+  w.Z = (double*)(mine + shp.ws_A);
+  w.lu = (double*)(mine + shp.ws_A + shp.ws_Z);
+  for (long long idx = blockIdx.x; idx < npts; idx += gridDim.x) {
+    // ---- k-point and the lower triangle of H(k)
+    if (tid == 0) {
+      int mi[TBK_MAX_DIM] = {0, 0, 0, 0};
+      double k[TBK_MAX_DIM];
+      if (out.mode == 1) decode_index(idx, out, mi);
+      load_k(ks, idx, mi, k);
+      for (int d = 0; d < TBK_MAX_DIM; ++d) { kbuf[d] = k[d]; mibuf[d] = mi[d]; }
+    }
+    for (int i = tid; i < n * lda; i += T) w.A[i] = mk(0.0, 0.0);
+    g.sync();
+    if (hsrc != nullptr) {
+      const cplx* h = hsrc + idx * (long long)n * n;
+      for (int q = tid; q < n * n; q += T) {
+        const int r = q / n, c = q - r * n;
+        if (c <= r) w.A[r + (size_t)c * lda] = h[q];
+      }
+    } else {
+      for (int p = tid; p < pv.nph; p += T) {
+        double x = 0.0;
+        for (int d = 0; d < pv.dim_k; ++d) x = fma(kbuf[d], pv.ph_R[p * pv.dim_k + d], x);
+        ph[p] = expi_turns(x);
+      }
+      g.sync();
+      for (int e = tid; e < pv.nel; e += T) w.A[pv.el_row[e] + (size_t)pv.el_col[e] * lda] = plan_element(pv, e, ph, 1);
+    }
+    g.sync();
+    long long t0 = prof ? clock64() : 0;
+#define TBK_PROF_MARK(slot) if (prof && tid == 0) { const long long t1 = clock64(); atomicAdd(prof + slot, (unsigned long long)(t1 - t0)); t0 = t1; }
+    hetrd_blocked(g, w);
+    TBK_PROF_MARK(0)
+    const double tnorm = tridiag_bisect(g, w);
+    TBK_PROF_MARK(1)
+    if (want_vec) {
+      const int fail = tridiag_invit(g, w, tnorm);
+      TBK_PROF_MARK(2)
+      if (fail) {
+        if (prof && tid == 0) atomicAdd(prof + 5, 1ull);
+        // a spectrum the inverse iteration should not be trusted with: unblocked Householder + QL
+        // (rebuilds H(k), writes every output of this k-point)
+        solve_one_matrix(g, pv, ks, hsrc, idx, out, want_vec, shp.fallback, w.A, smem);
+        continue;
+      }
+      for (int o = tid; o < n; o += T) {
+        cplx f = mk(1.0, 0.0);
+        if (hsrc == nullptr && pv.convention == 1 && pv.dim_k > 0) f = conj(plan_gauge(pv, kbuf, o));
+        gf[o] = f;
+      }
+      g.sync();
+      long long base = 0;
+      int zero_mask = 0;
+      bool closing = false;
+      if (out.mode == 1) {
+        closing = is_closing(ks, mibuf);
+        for (int d = 0; d < out.nd; ++d) {
+          base += mibuf[d] * out.gstride[d];
+          if (mibuf[d] == 0 && out.wrap[d]) zero_mask |= 1 << d;
+        }
+      }
+      backtransform_all<MAXM>(g, w, w.V, 2 * w.nb, [&](int c, int o, cplx x) {
+        cplx v = x * gf[o];
+        if (out.mode == 0) {
+          out.evec[c * out.vc_sb + idx * out.vc_sk + o] = v;
+        } else {
+          if (closing) v = v * out.pbc_phase[o];
+          const long long at = (long long)c * n + o;
+          out.evec[base + at] = v;
+          if (zero_mask) {
+            for (int mm = 1; mm < (1 << out.nd); ++mm) {
+              if ((mm & zero_mask) != mm) continue;
+              long long off = base;
+              cplx f = v;
+              for (int d = 0; d < out.nd; ++d)
+                if (mm & (1 << d)) {
+                  off += (long long)(out.full[d] - 1) * out.gstride[d];
+                  f = f * out.pbc_phase[d * n + o];
+                }
+              out.evec[off + at] = f;
+            }
+          }
+        }
+      });
+      g.sync();
+      TBK_PROF_MARK(3)
+    }
+    if (prof && tid == 0) atomicAdd(prof + 4, 1ull);
+#undef TBK_PROF_MARK
+    if (out.mode == 0) {
+      if (out.eval)
+        for (int b = tid; b < n; b += T) out.eval[b * out.ev_sb + idx * out.ev_sk] = w.lam[b];
+    } else if (out.gaps_bits != nullptr) {
+      for (int b = tid; b < n - 1; b += T) atomic_min_nonneg(out.gaps_bits + b, w.lam[b + 1] - w.lam[b]);
+    }
+    g.sync();
+  }
+}
+
+// ===========================================================================
 // Full H(k) output (tb_model._gen_ham)
 // ===========================================================================
 __global__ void __launch_bounds__(128)
@@ -503,6 +681,30 @@ static int launch_solve(const PlanView& pv, const KSrc& ks, const cplx* hsrc, in
     note_kernel("solve_tile_kernel");
     return TBK_OK;
   }
+  // blocked solver (the default for nsta > 32; TBK_BLOCKED=0 keeps the unblocked one-CTA solver)
+  {
+    const char* env = getenv("TBK_BLOCKED");
+    if (n <= kBlkMaxN && !(env && atoi(env) == 0)) {
+      const BlkShape shp = blk_shape(n, nph);
+      if (shp.smem <= (size_t)kMaxSmem) {
+        const long long blocks = blk_blocks(shp, npts);
+        const size_t need = (size_t)blocks * shp.ws_block;
+        if (ws == nullptr || ws_bytes < need) { set_error("workspace too small: need %zu bytes, have %zu", need, ws_bytes); return TBK_ERR_WORKSPACE; }
+#define TBK_BLK_LAUNCH(MM)                                                                                        \
+        do {                                                                                                      \
+          TBK_CUDA(cudaFuncSetAttribute(solve_blocked_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shp.smem)); \
+          solve_blocked_kernel<MM><<<(unsigned)blocks, shp.threads, shp.smem, st>>>(pv, ks, hsrc, npts, out, want_vec, shp, (char*)ws, blk_prof()); \
+        } while (0)
+        if (n <= 128) TBK_BLK_LAUNCH(4);
+        else if (n <= 256) TBK_BLK_LAUNCH(8);
+        else TBK_BLK_LAUNCH(16);
+#undef TBK_BLK_LAUNCH
+        TBK_LAUNCH_CHECK("solve_blocked_kernel");
+        note_kernel("solve_blocked_kernel");
+        return TBK_OK;
+      }
+    }
+  }
   // one matrix per CTA
   GroupShape gs = group_shape(n, nph, true);
   bool in_smem = gs.region <= (size_t)kMaxSmem;
@@ -529,10 +731,18 @@ static int launch_solve(const PlanView& pv, const KSrc& ks, const cplx* hsrc, in
 constexpr int kMeshGridCap = kNumSM * 8;
 static size_t solve_ws_bytes(int n, long long npts) {
   if (n <= 4) return (size_t)kMeshGridCap * 4 * 8;   // per-CTA gap partials of mesh_small_kernel
-  if (n <= 96) return 0;   // always shared-memory resident
+  if (n <= 32) return 0;   // register / tile kernels: shared-memory resident
   long long blocks = npts < (long long)kNumSM * 2 ? npts : (long long)kNumSM * 2;
   if (blocks < 1) blocks = 1;
-  return (size_t)blocks * n * (n | 1) * 16;
+  size_t need = n <= 96 ? 0 : (size_t)blocks * n * (n | 1) * 16;        // unblocked solver with A in the workspace
+  if (n <= kBlkMaxN) {                                                   // blocked solver (nph does not change the workspace)
+    const BlkShape shp = blk_shape(n, 0);
+    long long b2 = blk_blocks(shp, npts < 1 ? 1 : npts);
+    // the shape used at launch may have fewer resident CTAs (phase table in shared memory), never more
+    const size_t n2 = (size_t)b2 * shp.ws_block;
+    if (n2 > need) need = n2;
+  }
+  return need;
 }
 
 // n == 1 is trivial but must work (single-orbital models)
@@ -601,6 +811,13 @@ int tbk_gen_ham(const tbk_model* m, const double* k_dev, int64_t nk, double* ham
   const long long blocks = nk < (long long)kNumSM * 8 ? nk : (long long)kNumSM * 8;
   gen_ham_kernel<<<(unsigned)blocks, 128, dyn, (cudaStream_t)stream>>>(m->pv, k_dev, nk, (cplx*)ham_dev);
   TBK_LAUNCH_CHECK("gen_ham_kernel");
+  return TBK_OK;
+}
+
+int tbk_debug_profile(uint64_t* out8, int32_t reset) {
+  if (!out8) { set_error("tbk_debug_profile: null argument"); return TBK_ERR_ARG; }
+  for (int i = 0; i < 8; ++i) out8[i] = g_blk_prof ? g_blk_prof[i] : 0;
+  if (reset && g_blk_prof) memset(g_blk_prof, 0, 8 * sizeof(unsigned long long));
   return TBK_OK;
 }
 

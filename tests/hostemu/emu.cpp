@@ -10,6 +10,7 @@
 #include "tbk_eig_group.cuh"
 #include "tbk_plan.cuh"
 #include "tbk_berry.cuh"
+#include "tbk_eig_blocked.cuh"
 
 using namespace tbk;
 
@@ -18,6 +19,12 @@ struct HostGroup {
   int size() const { return 1; }
   void sync() {}
   double sum(double x) { return x; }
+  int nsub() const { return 1; }
+  int sub() const { return 0; }
+  int lane() const { return 0; }
+  int subsize() const { return 1; }
+  double subsum(double x) { return x; }
+  void subsync() {}
 };
 
 extern "C" {
@@ -65,6 +72,32 @@ int emu_heev_group(int n, double* A, int lda, int want_vec, double* ev, double* 
       for (int o = 0; o < n; ++o) out[(size_t)rank[i] * n + o] = a[o + (size_t)i * lda];
   }
   return info;
+}
+
+// Blocked solver (tbk_eig_blocked.cuh): A n x n column-major, leading dimension lda, lower triangle valid.
+// Outputs ev[n] ascending, evec[n][n] rows = eigenvectors; returns 0, 1 = the spectrum asks for the fallback.
+int emu_heev_blocked(int n, double* A, int lda, int nb, int want_vec, double* ev, double* evec, double* tri) {
+  HostGroup g;
+  BlkWork w;
+  w.n = n; w.lda = lda; w.nb = nb; w.A = (cplx*)A;
+  std::vector<char> sh(blk_shared_bytes(n, nb, 1) + 64);
+  blk_carve_shared(w, sh.data(), 1);
+  std::vector<double> Z((size_t)n * n), lu((size_t)4 * n);
+  w.Z = Z.data(); w.lu = lu.data(); w.nt = 1;
+  hetrd_blocked(g, w);
+  if (tri) { std::memcpy(tri, w.d, n * 8); std::memcpy(tri + n, w.e, n * 8); }
+  const double tnorm = tridiag_bisect(g, w);
+  std::memcpy(ev, w.lam, n * 8);
+  if (!want_vec) return 0;
+  if (tridiag_invit(g, w, tnorm)) return 1;
+  cplx* out = (cplx*)evec;
+  if (nb % 2) {          // odd panel width: exercise the per-column variant
+    for (int c = 0; c < n; ++c)
+      backtransform_column<kBlkMaxN>(g, w, c, [&](int r, cplx x) { out[(size_t)c * n + r] = x; });
+  } else {
+    backtransform_all<kBlkMaxN>(g, w, w.V, 2 * nb, [&](int c, int r, cplx x) { out[(size_t)c * n + r] = x; });
+  }
+  return 0;
 }
 
 // Hamiltonian assembly from a compiled plan (host pointers), Convention I/II.
