@@ -251,7 +251,8 @@ int tbk_stream_sync(void* stream);
 
 /* Per-stage cycle counters of the blocked eigensolver, collected when the environment has TBK_PROF=1:
  * out8[0..3] = SM cycles spent in tridiagonalisation / bisection / inverse iteration / back-transformation
- * (summed over CTAs), out8[4] = matrices solved, out8[5] = matrices handed to the fallback solver.
+ * (summed over CTAs), out8[4] = matrices solved, out8[5] = matrices handed to the fallback solver,
+ * out8[6] = cycles of the slowest single matrix.
  * Call after synchronising the stream.  Profiling aid, not part of the reference interface. */
 int tbk_debug_profile(uint64_t* out8, int32_t reset);
 

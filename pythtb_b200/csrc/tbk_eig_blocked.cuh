@@ -38,6 +38,7 @@
 namespace tbk {
 
 constexpr int kBlkMaxN = 512;
+constexpr int kWarpCluster = 6;       // clusters up to this size are orthogonalised by one sub-team, larger ones by the group
 
 struct BlkWork {
   int n, lda, nb;
@@ -331,9 +332,13 @@ TBK_HD double tridiag_bisect(G& g, const BlkWork& w) {
 // 3. eigenvectors of the tridiagonal by inverse iteration.  Returns 0, or 1 if the spectrum needs
 // the fallback solver (huge cluster / dependent cluster vectors).
 // ---------------------------------------------------------------------------------------------
-TBK_HD double invit_rand(unsigned& s) {               // uniform in (-1, 1), deterministic
-  s = s * 1664525u + 1013904223u;
-  return ((double)(s >> 8) + 0.5) * (2.0 / 16777216.0) - 1.0;
+// start vectors: a hash of (vector, component, attempt), uniform in (-1, 1).  (A linear congruential stream
+// per vector is NOT good enough: streams seeded j * const differ by an affine function of j, so the
+// start vectors of a degenerate cluster span only a few dimensions and Gram-Schmidt finds them dependent.)
+TBK_HD double invit_rand(unsigned j, unsigned i, unsigned salt) {
+  unsigned x = (j + 1u) * 0x9E3779B1u ^ (i + 1u) * 0x85EBCA77u ^ (salt + 1u) * 0xC2B2AE3Du;
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return ((double)(x >> 8) + 0.5) * (2.0 / 16777216.0) - 1.0;
 }
 
 // One inverse-iteration solve (T - lam I) x = y for the thread that owns column t of the interleaved
@@ -407,8 +412,7 @@ TBK_HD int tridiag_invit(G& g, const BlkWork& w, double tnorm) {
     const int t = g.tid();
     const int j = j0 + t;
     if (t < nt && j < n) {
-      unsigned seed = 0x9E3779B9u * (unsigned)(j + 1) + 12345u;
-      for (int i = 0; i < n; ++i) Y[(size_t)i * nt + t] = invit_rand(seed);
+      for (int i = 0; i < n; ++i) Y[(size_t)i * nt + t] = invit_rand((unsigned)j, (unsigned)i, 0u);
       for (int it = 0; it < 3; ++it) tridiag_shifted_solve(n, w.d, w.e, w.lamp[j], pivtol, U0, U1, U2, Y, nt, t);
       // normalise, largest component positive, store as column j of Z
       double nrm = 0.0, big = 0.0;
@@ -431,6 +435,7 @@ TBK_HD int tridiag_invit(G& g, const BlkWork& w, double tnorm) {
     int last = s;
     while (last + 1 < n && w.cl[last + 1] == s) ++last;
     if (last == s) continue;
+    if (last - s + 1 > kWarpCluster) continue;     // large clusters: whole group, below
     const int L = g.lane(), S = g.subsize();
     const int t0 = g.tid() - L;                    // scratch column of this sub-team's lane 0
     const bool have_scratch = t0 < nt;
@@ -467,11 +472,7 @@ TBK_HD int tridiag_invit(G& g, const BlkWork& w, double tnorm) {
         if (keep < 1.0e-2) {                        // dependent: restart from a fresh random vector
           ++attempt;
           solves = 0;
-          for (int i = L; i < n; i += S) {
-            unsigned seed = 0x85EBCA6Bu * (unsigned)(b + 1) + 0xC2B2AE35u * (unsigned)(i + 1) + 977u * (unsigned)attempt;
-            invit_rand(seed);
-            w.Z[(size_t)i * n + b] = invit_rand(seed);
-          }
+          for (int i = L; i < n; i += S) w.Z[(size_t)i * n + b] = invit_rand((unsigned)b, (unsigned)i, (unsigned)attempt);
           g.subsync();
           continue;                                 // orthogonalise the start vector first
         }
@@ -485,6 +486,48 @@ TBK_HD int tridiag_invit(G& g, const BlkWork& w, double tnorm) {
         g.subsync();
       }
     }
+  }
+  g.sync();
+  // ---- phase 3: large clusters (flat bands, high-symmetry k-points), one after another by the WHOLE
+  // group: classical Gram-Schmidt applied twice.  The members of a cluster are adjacent columns of the
+  // row-major Z, so the projections <z_a, z_b> for all a < b are computed one per thread with coalesced
+  // reads, and the update runs one row per thread.  A single sub-team would need O(c^2) serial
+  // dot products here (measured: one 200-member cluster took 8x the time of the rest of the matrix).
+  for (int s = 0; s < n; ++s) {
+    if (w.cl[s] != s) continue;
+    int last = s;
+    while (last + 1 < n && w.cl[last + 1] == s) ++last;
+    if (last - s + 1 <= kWarpCluster) { s = last; continue; }
+    double* proj = w.e2;                            // free after the bisection
+    for (int b = s + 1; b <= last; ++b) {
+      for (int pass = 0; pass < 2; ++pass) {
+        double before = 0.0;
+        for (int a = s + g.tid(); a < b; a += g.size()) {
+          double dot = 0.0;
+          for (int i = 0; i < n; ++i) dot += w.Z[(size_t)i * n + a] * w.Z[(size_t)i * n + b];
+          proj[a - s] = dot;
+        }
+        for (int i = g.tid(); i < n; i += g.size()) { const double x = w.Z[(size_t)i * n + b]; before += x * x; }
+        before = sqrt(g.sum(before));               // g.sum synchronises: proj is visible
+        double part = 0.0;
+        for (int i = g.tid(); i < n; i += g.size()) {
+          const double* row = w.Z + (size_t)i * n;
+          double acc = row[b];
+          for (int a = s; a < b; ++a) acc -= proj[a - s] * row[a];
+          w.Z[(size_t)i * n + b] = acc;
+          part += acc * acc;
+        }
+        const double nrm = sqrt(g.sum(part));
+        // In a c-fold degenerate eigenspace the last members legitimately keep only ~1/sqrt(c) of their norm
+        // (and with some probability 10-100x less); what survives still lies in the eigenspace, and its error
+        // outside the cluster is amplified by at most 1/keep.  Below 1e-4 the vector is left to the fallback.
+        if (pass == 0 && !(nrm >= 1.0e-4 * before) && g.tid() == 0) w.ctl[1] = 1;
+        const double sc = nrm > 0.0 ? 1.0 / nrm : 0.0;
+        for (int i = g.tid(); i < n; i += g.size()) w.Z[(size_t)i * n + b] *= sc;
+        g.sync();
+      }
+    }
+    s = last;
   }
   g.sync();
   return w.ctl[1];

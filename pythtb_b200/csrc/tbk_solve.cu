@@ -439,7 +439,8 @@ static BlkShape blk_shape(int n, int nph) {
     off += (size_t)(nph > 0 ? nph : 1) * 16 + (size_t)n * 16 + 128;
     return off;
   };
-  // as many resident CTAs as possible matter more than wide panels: nb = 16 only if two CTAs still fit
+  // panel width: 16 if two CTAs still fit an SM, else 8.  (Measured at n = 400: nb = 4 with two resident
+  // CTAs is 15 % slower than nb = 8 with one — the stage is bandwidth-, not latency-bound.)
   s.nb = total(16) * 2 + 2048 <= (size_t)kMaxSmem ? 16 : 8;
   size_t off = (blk_shared_bytes(n, s.nb, s.threads) + 15) & ~(size_t)15;
   s.off_ph = off;   off += (size_t)(nph > 0 ? nph : 1) * 16;
@@ -467,7 +468,8 @@ static long long blk_blocks(const BlkShape& s, long long npts) {
 }
 
 // Optional per-stage cycle counters (TBK_PROF=1): pinned host words the kernel adds clock64 deltas to
-// [0] hetrd [1] bisect [2] invit [3] backtransform [4] matrices [5] fallbacks; read by tbk_debug_profile.
+// [0] hetrd [1] bisect [2] invit [3] backtransform [4] matrices [5] fallbacks [6] slowest matrix;
+// read by tbk_debug_profile.
 static unsigned long long* g_blk_prof = nullptr;
 static unsigned long long* blk_prof() {
   static int on = -1;
@@ -527,6 +529,7 @@ solve_blocked_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long l
     }
     g.sync();
     long long t0 = prof ? clock64() : 0;
+    const long long tstart = t0;
 #define TBK_PROF_MARK(slot) if (prof && tid == 0) { const long long t1 = clock64(); atomicAdd(prof + slot, (unsigned long long)(t1 - t0)); t0 = t1; }
     hetrd_blocked(g, w);
     TBK_PROF_MARK(0)
@@ -584,7 +587,7 @@ solve_blocked_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long l
       g.sync();
       TBK_PROF_MARK(3)
     }
-    if (prof && tid == 0) atomicAdd(prof + 4, 1ull);
+    if (prof && tid == 0) { atomicAdd(prof + 4, 1ull); atomicMax(prof + 6, (unsigned long long)(clock64() - tstart)); }
 #undef TBK_PROF_MARK
     if (out.mode == 0) {
       if (out.eval)

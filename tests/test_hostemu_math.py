@@ -125,6 +125,12 @@ def _blocked_matrix(rng, n, kind):
         h = (q * lam) @ q.conj().T
     elif kind == "diag":
         h = np.diag(rng.randn(n)).astype(complex)
+    elif kind == "flat":                   # two flat bands: every eigenvalue n/2-fold degenerate (slab at k = (1/2, 1/2))
+        q, _ = np.linalg.qr(a)
+        lam = np.where(np.arange(n) % 2 == 0, -1.0, 1.0)
+        h = (q * lam) @ q.conj().T
+    elif kind == "flatdiag":
+        h = np.diag(np.where(np.arange(n) % 2 == 0, -1.0, 1.0)).astype(complex) + 3.7e-17 * (np.eye(n, k=1) + np.eye(n, k=-1))
     elif kind == "ribbon":                 # bipartite chain with a staggered potential (banded, like a ribbon H(k))
         h = np.zeros((n, n), complex)
         for i in range(n - 1):
@@ -140,7 +146,7 @@ def test_blocked_heev(n, nb):
     clustered, diagonal and banded matrices; nb odd exercises the per-column back-transformation."""
     lib = hostemu.lib()
     rng = np.random.RandomState(500 + n)
-    for kind in ("rand", "deg", "cluster", "diag", "ribbon"):
+    for kind in ("rand", "deg", "cluster", "diag", "flat", "flatdiag", "ribbon"):
         h = _blocked_matrix(rng, n, kind)
         lda = n | 1
         a = np.zeros((n, lda), dtype=complex)
