@@ -657,13 +657,163 @@ __device__ inline void link_endpoints(const LinkMap& m, long long l, long long& 
   }
 }
 
+// ---------------------------------------------------------------------------
+// Overlap matrix of one link on the FP64 tensor pipe:  M[m][q] = sum_o conj(A[m][o]) B[q][o]
+// (_wf_dpr, pythtb.py:3793-3796, for all nocc^2 pairs of a link at once).  A, B are the occupied
+// rows (row stride n) of the two mesh points.  One CTA of 8 warps computes M in 64 x 64 output tiles;
+// a warp owns 16 x 32 of it as 2 x 4 fragments of mma.sync.m8n8k4.f64 (DMMA); the K (orbital)
+// dimension is staged 16 orbitals at a time in shared memory as separate re / im planes with a
+// leading dimension of 20 doubles, which makes every 8-byte fragment read conflict-free.  A complex
+// product is four real DMMAs:  re += Ar Br, re += Ai Bi, im += Ar Bi, im += (-Ai) Br.
+// ---------------------------------------------------------------------------
+constexpr int kOvTile = 64, kOvKC = 16, kOvLD = 20;
+struct OvSmem {
+  double are[kOvTile][kOvLD], aim[kOvTile][kOvLD], bre[kOvTile][kOvLD], bim[kOvTile][kOvLD];
+};
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// called by all 256 threads of a CTA; M is row-major [nocc][ld]
+__device__ void cta_overlap_dmma(const WfView& v, const cplx* __restrict__ pa, const cplx* __restrict__ pb,
+                                 cplx* __restrict__ M, int ld, OvSmem& sm) {
+  const int nocc = v.nocc, n = v.n;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wr = warp >> 1, wc = warp & 1;
+  for (int m0 = 0; m0 < nocc; m0 += kOvTile) {
+    for (int q0 = 0; q0 < nocc; q0 += kOvTile) {
+      double cre[2][4][2], cim[2][4][2];
+#pragma unroll
+      for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < 4; ++ct) { cre[rt][ct][0] = cre[rt][ct][1] = 0.0; cim[rt][ct][0] = cim[rt][ct][1] = 0.0; }
+      bool rv[2], cv[4];                         // warp-uniform: does the 8 x 8 fragment touch the matrix at all
+#pragma unroll
+      for (int rt = 0; rt < 2; ++rt) rv[rt] = m0 + wr * 16 + rt * 8 < nocc;
+#pragma unroll
+      for (int ct = 0; ct < 4; ++ct) cv[ct] = q0 + wc * 32 + ct * 8 < nocc;
+      for (int o0 = 0; o0 < n; o0 += kOvKC) {
+        __syncthreads();                         // the previous chunk has been consumed
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int idx = tid + 256 * i;
+          const int row = idx >> 4, oc = idx & 15;
+          const int o = o0 + oc;
+          cplx a = mk(0.0, 0.0), b = mk(0.0, 0.0);
+          if (o < n) {
+            if (m0 + row < nocc) a = pa[(long long)v.occ[m0 + row] * n + o];
+            if (q0 + row < nocc) b = pb[(long long)v.occ[q0 + row] * n + o];
+          }
+          sm.are[row][oc] = a.re; sm.aim[row][oc] = a.im;
+          sm.bre[row][oc] = b.re; sm.bim[row][oc] = b.im;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < kOvKC / 4; ++ks) {
+          double ar[2], ai[2], an[2];
+#pragma unroll
+          for (int rt = 0; rt < 2; ++rt) {
+            const int r = wr * 16 + rt * 8 + g;
+            ar[rt] = sm.are[r][ks * 4 + t];
+            ai[rt] = sm.aim[r][ks * 4 + t];
+            an[rt] = -ai[rt];
+          }
+#pragma unroll
+          for (int ct = 0; ct < 4; ++ct) {
+            if (!cv[ct]) continue;
+            const int c = wc * 32 + ct * 8 + g;
+            const double br = sm.bre[c][ks * 4 + t], bi = sm.bim[c][ks * 4 + t];
+#pragma unroll
+            for (int rt = 0; rt < 2; ++rt) {
+              if (!rv[rt]) continue;
+              dmma884(cre[rt][ct][0], cre[rt][ct][1], ar[rt], br);
+              dmma884(cre[rt][ct][0], cre[rt][ct][1], ai[rt], bi);
+              dmma884(cim[rt][ct][0], cim[rt][ct][1], ar[rt], bi);
+              dmma884(cim[rt][ct][0], cim[rt][ct][1], an[rt], br);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < 4; ++ct) {
+          const int m = m0 + wr * 16 + rt * 8 + g;
+          const int q = q0 + wc * 32 + ct * 8 + 2 * t;
+          if (m < nocc) {
+            if (q < nocc) M[(size_t)m * ld + q] = mk(cre[rt][ct][0], cim[rt][ct][0]);
+            if (q + 1 < nocc) M[(size_t)m * ld + q + 1] = mk(cre[rt][ct][1], cim[rt][ct][1]);
+          }
+        }
+    }
+  }
+  __syncthreads();
+}
+
+// det(M)/|det(M)| of the row-major n x n matrix M (destroyed) by LU with partial pivoting, all threads of
+// the CTA: parallel pivot search, one warp per row in the rank-1 update (coalesced along the row).
+// sred/sidx: [32] shared scratch each; fbuf: [n] shared multipliers.
+__device__ cplx lu_det_phase_cta(cplx* __restrict__ M, int n, int ld, double* sred, int* sidx, cplx* fbuf) {
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  cplx u = mk(1.0, 0.0);
+  for (int k = 0; k < n; ++k) {
+    double best = -1.0;
+    int bi = n;
+    for (int r = k + tid; r < n; r += T) {
+      const double x = norm2(M[(size_t)r * ld + k]);
+      if (x > best) { best = x; bi = r; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { sred[warp] = best; sidx[warp] = bi; }
+    __syncthreads();
+    best = sred[0]; bi = sidx[0];
+    for (int w = 1; w < nw; ++w)
+      if (sred[w] > best || (sred[w] == best && sidx[w] < bi)) { best = sred[w]; bi = sidx[w]; }
+    if (!(best > 0.0)) return mk(0.0, 0.0);
+    const int piv = bi;
+    if (piv != k) {
+      for (int c = k + tid; c < n; c += T) {
+        const cplx tmp = M[(size_t)k * ld + c];
+        M[(size_t)k * ld + c] = M[(size_t)piv * ld + c];
+        M[(size_t)piv * ld + c] = tmp;
+      }
+      u = -u;
+    }
+    __syncthreads();                              // swap done; sred/sidx free for the next step
+    const cplx p = M[(size_t)k * ld + k];
+    const double ap = sqrt(norm2(p));
+    u = u * mk(p.re / ap, p.im / ap);
+    for (int r = k + 1 + tid; r < n; r += T) fbuf[r] = cdiv(M[(size_t)r * ld + k], p);
+    __syncthreads();
+    const cplx* rowk = M + (size_t)k * ld;
+    for (int r = k + 1 + warp; r < n; r += nw) {
+      const cplx f = fbuf[r];
+      cplx* row = M + (size_t)r * ld;
+      for (int c = k + 1 + lane; c < n; c += 32) row[c] = row[c] - f * rowk[c];
+    }
+    __syncthreads();
+  }
+  const double nu = sqrt(norm2(u));
+  return mk(u.re / nu, u.im / nu);
+}
+
 // mode 0: out[l] = det/|det| of the overlap.   mode 1: out[l*nocc*nocc ...] = unitary polar factor.
 __global__ void __launch_bounds__(256)
 link_matrix_kernel(WfView v, LinkMap map, long long nlinks, int mode, cplx* __restrict__ out, cplx* __restrict__ gws) {
+  extern __shared__ __align__(16) char dyn_smem[];
   __shared__ double red[32];
-  __shared__ int ired[4];
-  BlockGroup g(red);
-  const int nocc = v.nocc, n = v.n;
+  __shared__ int ired[32];
+  OvSmem& ov = *reinterpret_cast<OvSmem*>(dyn_smem);
+  cplx* fbuf = reinterpret_cast<cplx*>(dyn_smem + sizeof(OvSmem));
+  const int nocc = v.nocc;
   const int ld = nocc | 1;
   // per-CTA workspace: M [nocc*ld] (+ 2 work matrices for the polar factor)
   cplx* M = gws + (size_t)blockIdx.x * (size_t)nocc * ld * 3;
@@ -672,17 +822,9 @@ link_matrix_kernel(WfView v, LinkMap map, long long nlinks, int mode, cplx* __re
     link_endpoints(map, l, oa, ob);
     const cplx* pa = v.wfs + oa;
     const cplx* pb = v.wfs + ob;
-    for (int idx = threadIdx.x; idx < nocc * nocc; idx += blockDim.x) {
-      const int m = idx / nocc, q = idx - m * nocc;
-      const cplx* ra = pa + (long long)v.occ[m] * n;
-      const cplx* rb = pb + (long long)v.occ[q] * n;
-      cplx acc = mk(0.0, 0.0);
-      for (int o = 0; o < n; ++o) fma_acc_conj(acc, ra[o], rb[o]);
-      M[(size_t)m * ld + q] = acc;
-    }
-    __syncthreads();
+    cta_overlap_dmma(v, pa, pb, M, ld, ov);
     if (mode == 0) {
-      const cplx u = lu_det_phase_g(g, M, nocc, ld, ired);
+      const cplx u = lu_det_phase_cta(M, nocc, ld, red, ired, fbuf);
       if (threadIdx.x == 0) out[l] = u;
       __syncthreads();
     } else {
@@ -893,7 +1035,9 @@ static int launch_links(const WfView& v, const LinkMap& map, long long nlinks, i
     TBK_LAUNCH_CHECK("link_small_kernel");
     return TBK_OK;
   }
-  link_matrix_kernel<<<link_grid(nlinks), 256, 0, st>>>(v, map, nlinks, mode, out, gws);
+  const size_t dyn = sizeof(OvSmem) + (size_t)v.nocc * 16 + 64;
+  TBK_CUDA(cudaFuncSetAttribute(link_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  link_matrix_kernel<<<link_grid(nlinks), 256, dyn, st>>>(v, map, nlinks, mode, out, gws);
   TBK_LAUNCH_CHECK("link_matrix_kernel");
   return TBK_OK;
 }
