@@ -174,4 +174,206 @@ struct JacobiPacked {
   }
 };
 
+#if defined(__CUDA_ARCH__)
+#define TBK_UNROLL _Pragma("unroll")
+#else
+#define TBK_UNROLL
+#endif
+
+// ---------------------------------------------------------------------------
+// 3 <= N <= 4, direct method: Householder tridiagonalisation of the complex Hermitian matrix
+// (N - 1 reflectors, the last one a pure phase), implicit-shift QL on the REAL tridiagonal with the
+// rotations accumulated in a REAL N x N matrix, back-transformation of its columns by the
+// reflectors.  About 3x fewer FP64 operations than the cyclic complex Jacobi above (ncu: the
+// Kane-Mele mesh kernel was bound by the ~2800 FP64 instructions of Jacobi per k-point) and half
+// the live registers during the iteration.  All matrix indices are compile-time constants (loops
+// fully unrolled, data-dependent extents as predicates), so nothing is spilled to local memory.
+//   a[N][N]   Hermitian matrix, only the lower triangle is read; destroyed
+//   ev[N]     ascending eigenvalues
+//   w[N][N]   rows = eigenvectors (not conjugated), H w[b]^T = ev[b] w[b]^T
+// Returns false if the QL iteration did not converge in 30 steps (callers fall back to Jacobi).
+// ---------------------------------------------------------------------------
+template <int N>
+TBK_HD bool eigh_small_ql(cplx a[N][N], double ev[N], cplx w[N][N]) {
+  const double eps = 1.1102230246251565e-16;
+  double d[N], e[N];
+  cplx tau[N];
+  // ---- zhetd2 'L': reflector j annihilates a[j+2..N-1][j]; v_j kept in a[j+2..][j], implicit unit at j+1
+  TBK_UNROLL
+  for (int j = 0; j < N - 1; ++j) {
+    double xnorm2 = 0.0;
+    TBK_UNROLL
+    for (int r = j + 2; r < N; ++r) xnorm2 += norm2(a[r][j]);
+    const cplx alpha = a[j + 1][j];
+    cplx t = mk(0.0, 0.0);
+    double beta = alpha.re;
+    if (xnorm2 != 0.0 || alpha.im != 0.0) {
+      double rs;
+      const double nrm = sqrt_fast(alpha.re * alpha.re + alpha.im * alpha.im + xnorm2 + 1.0e-290, &rs);
+      beta = alpha.re >= 0.0 ? -nrm : nrm;
+      const double ib = 1.0 / beta;
+      t = mk((beta - alpha.re) * ib, -alpha.im * ib);
+      const double dr = alpha.re - beta, di = alpha.im;          // 1 / (alpha - beta)
+      const double idn = 1.0 / (dr * dr + di * di);
+      const cplx scal = mk(dr * idn, -di * idn);
+      TBK_UNROLL
+      for (int r = j + 2; r < N; ++r) a[r][j] = a[r][j] * scal;
+    }
+    d[j] = a[j][j].re;
+    e[j] = beta;
+    tau[j] = t;
+    if (j < N - 2) {
+      // p = tau A22 v, w = p - (tau/2)(p^H v) v, A22 -= v w^H + w v^H   (lower triangle of A22 only)
+      cplx v[N], pv[N];
+      TBK_UNROLL
+      for (int r = j + 1; r < N; ++r) v[r] = r == j + 1 ? mk(1.0, 0.0) : a[r][j];
+      TBK_UNROLL
+      for (int r = j + 1; r < N; ++r) {
+        cplx acc = mk(0.0, 0.0);
+        TBK_UNROLL
+        for (int c = j + 1; c < N; ++c) {
+          const cplx arc = c < r ? a[r][c] : (c == r ? mk(a[r][r].re, 0.0) : conj(a[c][r]));
+          fma_acc(acc, arc, v[c]);
+        }
+        pv[r] = t * acc;
+      }
+      cplx dot = mk(0.0, 0.0);
+      TBK_UNROLL
+      for (int r = j + 1; r < N; ++r) fma_acc_conj(dot, pv[r], v[r]);     // p^H v
+      const cplx a2 = (-0.5) * (t * dot);
+      TBK_UNROLL
+      for (int r = j + 1; r < N; ++r) pv[r] = pv[r] + a2 * v[r];
+      TBK_UNROLL
+      for (int r = j + 1; r < N; ++r) {
+        TBK_UNROLL
+        for (int c = j + 1; c <= r; ++c) a[r][c] = a[r][c] - mulc(v[r], pv[c]) - mulc(pv[r], v[c]);
+      }
+    }
+    // j == N-2: the reflector is the scalar 1 - tau on component N-1; a[N-1][N-1] is unchanged (|1 - tau| = 1)
+  }
+  d[N - 1] = a[N - 1][N - 1].re;
+  e[N - 1] = 0.0;
+  // ---- implicit-shift QL on (d, e); column c of z is the eigenvector of d[c]
+  double z[N][N];
+  TBK_UNROLL
+  for (int r = 0; r < N; ++r) {
+    TBK_UNROLL
+    for (int c = 0; c < N; ++c) z[r][c] = r == c ? 1.0 : 0.0;
+  }
+  bool ok = true;
+  TBK_UNROLL
+  for (int l = 0; l < N - 1; ++l) {
+    for (int iter = 0;; ++iter) {
+      int m = N - 1;
+      TBK_UNROLL
+      for (int mm = N - 2; mm >= l; --mm)
+        if (fabs(e[mm]) <= eps * (fabs(d[mm]) + fabs(d[mm + 1]))) m = mm;
+      if (m == l) break;
+      if (iter == 30) { ok = false; break; }
+      double dm = d[N - 1];
+      TBK_UNROLL
+      for (int mm = l + 1; mm < N - 1; ++mm)
+        if (mm == m) dm = d[mm];
+      double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+      double rs;
+      double r = sqrt_fast(g * g + 1.0, &rs);
+      g = dm - d[l] + e[l] / (g + (g >= 0.0 ? r : -r));
+      double sn = 1.0, cs = 1.0, p = 0.0;
+      bool dead = false;
+      TBK_UNROLL
+      for (int i = N - 2; i >= l; --i) {
+        if (i < m && !dead) {
+          const double f = sn * e[i], b = cs * e[i];
+          const double q2 = f * f + g * g;
+          if (q2 == 0.0) {
+            e[i + 1] = 0.0;
+            d[i + 1] -= p;
+            dead = true;
+          } else {
+            r = sqrt_fast(q2, &rs);
+            e[i + 1] = r;
+            sn = f * rs; cs = g * rs;
+            g = d[i + 1] - p;
+            r = (d[i] - g) * sn + 2.0 * cs * b;
+            p = sn * r;
+            d[i + 1] = g + p;
+            g = cs * r - b;
+            TBK_UNROLL
+            for (int k = 0; k < N; ++k) {
+              const double zf = z[k][i + 1];
+              z[k][i + 1] = sn * z[k][i] + cs * zf;
+              z[k][i] = cs * z[k][i] - sn * zf;
+            }
+          }
+        }
+      }
+      if (!dead) { d[l] -= p; e[l] = g; }
+      TBK_UNROLL
+      for (int mm = l; mm < N; ++mm)
+        if (mm == m) e[mm] = 0.0;
+    }
+  }
+  // ---- ascending order: sort d together with the (real) columns of z
+  TBK_UNROLL
+  for (int x = 0; x < N - 1; ++x) {
+    TBK_UNROLL
+    for (int y = x + 1; y < N; ++y) {
+      if (d[y] < d[x]) {
+        const double td = d[x]; d[x] = d[y]; d[y] = td;
+        TBK_UNROLL
+        for (int k = 0; k < N; ++k) { const double tz = z[k][x]; z[k][x] = z[k][y]; z[k][y] = tz; }
+      }
+    }
+  }
+  // ---- eigenvectors of H: x = H_0 H_1 ... H_{N-2} z_c, row b of w = eigenvector b
+  TBK_UNROLL
+  for (int b = 0; b < N; ++b) {
+    cplx x[N];
+    TBK_UNROLL
+    for (int k = 0; k < N; ++k) x[k] = mk(z[k][b], 0.0);
+    TBK_UNROLL
+    for (int j = N - 2; j >= 0; --j) {
+      cplx dot = x[j + 1];                                   // v^H x with v[j+1] = 1
+      TBK_UNROLL
+      for (int r = j + 2; r < N; ++r) fma_acc_conj(dot, a[r][j], x[r]);
+      const cplx f = tau[j] * dot;
+      x[j + 1] = x[j + 1] - f;
+      TBK_UNROLL
+      for (int r = j + 2; r < N; ++r) x[r] = x[r] - f * a[r][j];
+    }
+    ev[b] = d[b];
+    TBK_UNROLL
+    for (int k = 0; k < N; ++k) w[b][k] = x[k];
+  }
+  return ok;
+}
+
+// cold path, kept out of line so that it does not cost the hot kernels registers
+template <int N>
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+void eigh_small_jacobi_fallback(const double dg_in[N], const cplx lo_in[N * (N - 1) / 2], double ev[N], cplx w[N][N]) {
+  double dg[N];
+  cplx lo[N * (N - 1) / 2];
+  for (int r = 0; r < N; ++r) dg[r] = dg_in[r];
+  for (int q = 0; q < N * (N - 1) / 2; ++q) lo[q] = lo_in[q];
+  JacobiPacked<N>::solve(dg, lo, w, true);
+  for (int r = 0; r < N; ++r) ev[r] = dg[r];
+}
+
+// Solver used by the register kernels for N = 3, 4: direct method, Jacobi if QL ever fails to converge.
+template <int N>
+TBK_HD void eigh_small(const double dg_in[N], const cplx lo_in[N * (N - 1) / 2], double ev[N], cplx w[N][N]) {
+  cplx a[N][N];
+  TBK_UNROLL
+  for (int r = 0; r < N; ++r) {
+    TBK_UNROLL
+    for (int c = 0; c < N; ++c) a[r][c] = c < r ? lo_in[r * (r - 1) / 2 + c] : mk(c == r ? dg_in[r] : 0.0, 0.0);
+  }
+  if (!eigh_small_ql<N>(a, ev, w)) eigh_small_jacobi_fallback<N>(dg_in, lo_in, ev, w);
+}
+
 }  // namespace tbk

@@ -266,9 +266,7 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
 #pragma unroll
               for (int c = 0; c < a; ++c) lo[a * (a - 1) / 2 + c] = acc[u][a * (a + 1) / 2 + c];
             }
-            JacobiPacked<N>::solve(dg, lo, w[u], true);
-#pragma unroll
-            for (int b = 0; b < N; ++b) ev[b] = dg[b];
+            eigh_small<N>(dg, lo, ev, w[u]);
           }
 #pragma unroll
           for (int b = 0; b < N - 1; ++b) gmin[b] = fmin(gmin[b], ev[b + 1] - ev[b]);

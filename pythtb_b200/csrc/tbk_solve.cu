@@ -187,9 +187,7 @@ solve_small_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long lon
 #pragma unroll
         for (int c = 0; c < r; ++c) lo[r * (r - 1) / 2 + c] = acc[r * (r + 1) / 2 + c];
       }
-      JacobiPacked<N>::solve(dg, lo, w, want_vec != 0);
-#pragma unroll
-      for (int b = 0; b < N; ++b) ev[b] = dg[b];
+      eigh_small<N>(dg, lo, ev, w);
     }
     // ---- Convention I gauge: u_I[b][j] = conj(d_j) u_II[b][j], d_j = exp(2 pi i k.tau_j)
     if (want_vec && hsrc == nullptr && pv.convention == 1 && dk > 0) {
@@ -908,6 +906,7 @@ static int launch_mesh_small(const tbk_model* m, const KSrc& ks, const OutSpec& 
   static const int kVariants2 = 6;
   if (variant < 0 || variant >= kVariants2) variant = 0;
   int occ = n == 2 ? (p4 ? kOcc2[variant] : 4) : (n == 3 ? 3 : 2);
+  if (n == 4 && p4) { const char* e = getenv("TBK_MESH_VARIANT4"); const int v4 = e ? atoi(e) : 0; occ = v4 == 1 ? 2 : (v4 == 2 ? 4 : 3); }
   long long want = (long long)kNumSM * occ;
   // at least ~4 rows per CTA so the per-CTA sincospi prologue stays amortised
   if (want > (nseg + 3) / 4) want = (nseg + 3) / 4;
@@ -939,7 +938,12 @@ static int launch_mesh_small(const tbk_model* m, const KSrc& ks, const OutSpec& 
     } else TBK_MESH_LAUNCH(2, 8, 4, 1);
   }
   else if (n == 3) { if (p4) TBK_MESH_LAUNCH(3, 4, 3, 1); else TBK_MESH_LAUNCH(3, 8, 3, 1); }
-  else { if (p4) TBK_MESH_LAUNCH(4, 4, 2, 1); else TBK_MESH_LAUNCH(4, 8, 2, 1); }
+  else {
+    int v4 = 0;
+    { const char* e = getenv("TBK_MESH_VARIANT4"); if (e) v4 = atoi(e); }   // tuning knob: resident CTAs per SM
+    if (p4) { if (v4 == 1) TBK_MESH_LAUNCH(4, 4, 2, 1); else if (v4 == 2) TBK_MESH_LAUNCH(4, 4, 4, 1); else TBK_MESH_LAUNCH(4, 4, 3, 1); }
+    else TBK_MESH_LAUNCH(4, 8, 2, 1);
+  }
 #undef TBK_MESH_LAUNCH
   TBK_LAUNCH_CHECK("mesh_small_kernel");
   note_kernel("mesh_small_kernel");

@@ -55,6 +55,26 @@ int emu_jacobi(int n, const double* H, double* ev, double* w) {
   return -1;
 }
 
+// direct small solver (Householder + QL), n = 3 or 4; returns 1 if the QL iteration converged
+int emu_small_ql(int n, const double* H, double* ev, double* w) {
+  const cplx* h = (const cplx*)H;
+  if (n == 3) {
+    cplx a[3][3]; cplx ww[3][3];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) a[r][c] = h[r * 3 + c];
+    const bool ok = eigh_small_ql<3>(a, ev, ww);
+    std::memcpy(w, ww, sizeof(ww));
+    return ok ? 1 : 0;
+  }
+  if (n == 4) {
+    cplx a[4][4]; cplx ww[4][4];
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) a[r][c] = h[r * 4 + c];
+    const bool ok = eigh_small_ql<4>(a, ev, ww);
+    std::memcpy(w, ww, sizeof(ww));
+    return ok ? 1 : 0;
+  }
+  return -1;
+}
+
 // A: n x n column-major with leading dimension lda (lower triangle valid).
 // Outputs: ev[n] ascending, evec[n][n] rows = eigenvectors (reference layout).
 int emu_heev_group(int n, double* A, int lda, int want_vec, double* ev, double* evec) {

@@ -66,6 +66,26 @@ def test_register_jacobi(n):
         _check_eig(h, ev, w)
 
 
+@pytest.mark.parametrize("n", [3, 4])
+def test_small_direct_solver(n):
+    """Householder + implicit QL in registers (eigh_small_ql), the solver of the n = 3, 4 mesh kernels."""
+    lib = hostemu.lib()
+    rng = np.random.RandomState(30 + n)
+    mats = [_rand_herm(rng, n) for _ in range(400)] + [_rand_herm(rng, n, degenerate=True) for _ in range(100)]
+    mats += [np.diag(rng.randn(n)).astype(complex), np.zeros((n, n), dtype=complex), np.eye(n, dtype=complex) * 3.0]
+    mats += [1e-9 * _rand_herm(rng, n) + np.eye(n), 1e6 * _rand_herm(rng, n)]
+    tri = np.diag(rng.randn(n)).astype(complex) + np.diag(rng.randn(n - 1) + 1j * rng.randn(n - 1), -1)
+    mats.append(tri + np.tril(tri, -1).conj().T)
+    kram = np.kron(_rand_herm(rng, 2), np.eye(2))[:n, :n]          # Kramers-like exact pairs
+    mats.append(kram)
+    for h in mats:
+        ev = np.zeros(n)
+        w = np.zeros((n, n), dtype=complex)
+        hc = np.ascontiguousarray(h)
+        assert lib.emu_small_ql(n, _p(hc.view(np.float64)), _p(ev), _p(w.view(np.float64))) == 1
+        _check_eig(h, ev, w)
+
+
 @pytest.mark.parametrize("n", [1, 2, 5, 8, 17, 32, 40, 64])
 def test_group_heev(n):
     lib = hostemu.lib()
