@@ -51,6 +51,16 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the solve kernel, from the committed
+    `ncu --set full` capture (profiles/traffic.json, written from profiles/rNN/raw_*.csv); None if absent."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return d[workload]["solve_kernel"]["dram_bytes"]
+    except Exception:
+        return None
+
+
 def _build_model(mod, workload):
     from tests import models as M
     if workload == "haldane":
@@ -326,14 +336,27 @@ def run_b200(args):
         gaps_h, flux_h = step_e2e()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # ---- the same step when the caller also wants the whole eigenvector array on the host (the reference keeps
+    # `_wfs` in host memory): solve + flux + D2H of the local `_wfs` slab into its pinned mirror, every step
+    nwf = max(3, min(20, args.steps))
+    w._wfs                                            # allocate the pinned mirror outside the timed region
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(nwf):
+        step_e2e()
+        w._store.state = "device"
+        w._wfs                                        # device -> pinned host copy of the whole slab
+    torch.cuda.synchronize()
+    e2e_wfs_s = (time.perf_counter() - t0) / nwf
+    w._store.state = "device"
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_s, k_ms, f_ms], dtype=torch.float64, device=eng.device)
+        t = torch.tensor([dev_ms, e2e_s, k_ms, f_ms, e2e_wfs_s], dtype=torch.float64, device=eng.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s, k_ms, f_ms = [float(x) for x in t.cpu()]
+        dev_ms, e2e_s, k_ms, f_ms, e2e_wfs_s = [float(x) for x in t.cpu()]
 
     if rank == 0:
         hbm_peak, peak_src = _peaks()
@@ -364,11 +387,15 @@ def run_b200(args):
                     "d2h_bytes_per_step": 8 * (n - 1) + 8,
                     "note": "public API wf_array.solve_on_grid + berry_flux; eigenvectors stay in HBM "
                             "(lazy host mirror), results (gaps, flux) are copied to the host every step"},
+            "e2e_wfs_to_host": {"value": total_k / e2e_wfs_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_wfs_s,
+                                "d2h_bytes_per_step": (ROWS_PER_RANK + 1) * (COLS + 1) * n * n * 16 + 8 * (n - 1) + 8,
+                                "note": "as e2e, plus a device->pinned-host copy of the whole local _wfs slab every step "
+                                        "(what a caller pays who, like the reference, wants the eigenvectors in host memory)"},
             "gpu_launches": launches * args.steps,
             "gpu_launches_per_step": launches,
             "roofline": {"bound": "hbm", "kernel": w._last_solve_kernel(), "achieved": solve_bytes / (k_ms * 1e-3) / 1e9,
                          "peak": hbm_peak, "unit": "GB/s", "frac": solve_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": solve_bytes,
+                         "traffic": _ncu_traffic(args.workload), "peak_source": peak_src, "algorithmic_bytes_per_launch": solve_bytes,
                          "flux_kernel": {"achieved": flux_bytes / (f_ms * 1e-3) / 1e9,
                                          "frac": flux_bytes / (f_ms * 1e-3) / 1e9 / hbm_peak,
                                          "algorithmic_bytes_per_launch": flux_bytes}},
