@@ -676,15 +676,26 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// called by all 256 threads of a CTA; M is row-major [nocc][ld]
-__device__ void cta_overlap_dmma(const WfView& v, const cplx* __restrict__ pa, const cplx* __restrict__ pb,
-                                 cplx* __restrict__ M, int ld, OvSmem& sm) {
-  const int nocc = v.nocc, n = v.n;
+// One operand of the CTA-level complex GEMM: element (row r, contraction index x) lives at
+// p[rowmap ? rowmap[r] : r) * rs + x * xs]; conj != 0 uses its complex conjugate.
+struct GemmSide {
+  const cplx* p;
+  long long rs, xs;
+  const int* rowmap;
+  int conj;
+};
+
+// C[m][q] = sum_x a(m, x) * b(q, x) * (wgt ? wgt[x] : 1),  m < ma, q < nb_, x < kdim;  C row-major [ma][ldc].
+// Called by all 256 threads of a CTA.  The loader picks the thread -> element mapping that makes the global
+// reads contiguous for the operand's unit stride (rows or contraction index).
+__device__ void cta_gemm_dmma(const GemmSide& A, int ma, const GemmSide& B, int nb_, int kdim, const double* __restrict__ wgt,
+                              cplx* __restrict__ C, int ldc, OvSmem& sm) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int wr = warp >> 1, wc = warp & 1;
-  for (int m0 = 0; m0 < nocc; m0 += kOvTile) {
-    for (int q0 = 0; q0 < nocc; q0 += kOvTile) {
+  const double sa = A.conj ? -1.0 : 1.0, sb = B.conj ? -1.0 : 1.0;
+  for (int m0 = 0; m0 < ma; m0 += kOvTile) {
+    for (int q0 = 0; q0 < nb_; q0 += kOvTile) {
       double cre[2][4][2], cim[2][4][2];
 #pragma unroll
       for (int rt = 0; rt < 2; ++rt)
@@ -692,23 +703,33 @@ __device__ void cta_overlap_dmma(const WfView& v, const cplx* __restrict__ pa, c
         for (int ct = 0; ct < 4; ++ct) { cre[rt][ct][0] = cre[rt][ct][1] = 0.0; cim[rt][ct][0] = cim[rt][ct][1] = 0.0; }
       bool rv[2], cv[4];                         // warp-uniform: does the 8 x 8 fragment touch the matrix at all
 #pragma unroll
-      for (int rt = 0; rt < 2; ++rt) rv[rt] = m0 + wr * 16 + rt * 8 < nocc;
+      for (int rt = 0; rt < 2; ++rt) rv[rt] = m0 + wr * 16 + rt * 8 < ma;
 #pragma unroll
-      for (int ct = 0; ct < 4; ++ct) cv[ct] = q0 + wc * 32 + ct * 8 < nocc;
-      for (int o0 = 0; o0 < n; o0 += kOvKC) {
+      for (int ct = 0; ct < 4; ++ct) cv[ct] = q0 + wc * 32 + ct * 8 < nb_;
+      for (int x0 = 0; x0 < kdim; x0 += kOvKC) {
         __syncthreads();                         // the previous chunk has been consumed
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int idx = tid + 256 * i;
-          const int row = idx >> 4, oc = idx & 15;
-          const int o = o0 + oc;
-          cplx a = mk(0.0, 0.0), b = mk(0.0, 0.0);
-          if (o < n) {
-            if (m0 + row < nocc) a = pa[(long long)v.occ[m0 + row] * n + o];
-            if (q0 + row < nocc) b = pb[(long long)v.occ[q0 + row] * n + o];
+          {
+            const int row = A.xs == 1 ? idx >> 4 : idx & 63, xc = A.xs == 1 ? idx & 15 : idx >> 6;
+            cplx a = mk(0.0, 0.0);
+            if (x0 + xc < kdim && m0 + row < ma) {
+              const long long r = A.rowmap ? A.rowmap[m0 + row] : m0 + row;
+              a = A.p[r * A.rs + (long long)(x0 + xc) * A.xs];
+            }
+            sm.are[row][xc] = a.re; sm.aim[row][xc] = sa * a.im;
           }
-          sm.are[row][oc] = a.re; sm.aim[row][oc] = a.im;
-          sm.bre[row][oc] = b.re; sm.bim[row][oc] = b.im;
+          {
+            const int row = B.xs == 1 ? idx >> 4 : idx & 63, xc = B.xs == 1 ? idx & 15 : idx >> 6;
+            cplx b = mk(0.0, 0.0);
+            if (x0 + xc < kdim && q0 + row < nb_) {
+              const long long r = B.rowmap ? B.rowmap[q0 + row] : q0 + row;
+              b = B.p[r * B.rs + (long long)(x0 + xc) * B.xs];
+              if (wgt) { const double f = wgt[x0 + xc]; b.re *= f; b.im *= f; }
+            }
+            sm.bre[row][xc] = b.re; sm.bim[row][xc] = sb * b.im;
+          }
         }
         __syncthreads();
 #pragma unroll
@@ -729,10 +750,10 @@ __device__ void cta_overlap_dmma(const WfView& v, const cplx* __restrict__ pa, c
 #pragma unroll
             for (int rt = 0; rt < 2; ++rt) {
               if (!rv[rt]) continue;
-              dmma884(cre[rt][ct][0], cre[rt][ct][1], ar[rt], br);
-              dmma884(cre[rt][ct][0], cre[rt][ct][1], ai[rt], bi);
+              dmma884(cre[rt][ct][0], cre[rt][ct][1], ar[rt], br);    // (ar + i ai)(br + i bi)
+              dmma884(cre[rt][ct][0], cre[rt][ct][1], an[rt], bi);
               dmma884(cim[rt][ct][0], cim[rt][ct][1], ar[rt], bi);
-              dmma884(cim[rt][ct][0], cim[rt][ct][1], an[rt], br);
+              dmma884(cim[rt][ct][0], cim[rt][ct][1], ai[rt], br);
             }
           }
         }
@@ -743,14 +764,21 @@ __device__ void cta_overlap_dmma(const WfView& v, const cplx* __restrict__ pa, c
         for (int ct = 0; ct < 4; ++ct) {
           const int m = m0 + wr * 16 + rt * 8 + g;
           const int q = q0 + wc * 32 + ct * 8 + 2 * t;
-          if (m < nocc) {
-            if (q < nocc) M[(size_t)m * ld + q] = mk(cre[rt][ct][0], cim[rt][ct][0]);
-            if (q + 1 < nocc) M[(size_t)m * ld + q + 1] = mk(cre[rt][ct][1], cim[rt][ct][1]);
+          if (m < ma) {
+            if (q < nb_) C[(size_t)m * ldc + q] = mk(cre[rt][ct][0], cim[rt][ct][0]);
+            if (q + 1 < nb_) C[(size_t)m * ldc + q + 1] = mk(cre[rt][ct][1], cim[rt][ct][1]);
           }
         }
     }
   }
   __syncthreads();
+}
+
+// overlap of the occupied blocks of two mesh points: M[m][q] = sum_o conj(A[m][o]) B[q][o]
+__device__ __forceinline__ void cta_overlap_dmma(const WfView& v, const cplx* __restrict__ pa, const cplx* __restrict__ pb,
+                                                 cplx* __restrict__ M, int ld, OvSmem& sm) {
+  const GemmSide A{pa, v.n, 1, v.occ, 1}, B{pb, v.n, 1, v.occ, 0};
+  cta_gemm_dmma(A, v.nocc, B, v.nocc, v.n, nullptr, M, ld, sm);
 }
 
 // det(M)/|det(M)| of the row-major n x n matrix M (destroyed) by LU with partial pivoting, all threads of
@@ -999,6 +1027,30 @@ position_matrix_kernel(const cplx* __restrict__ evec, long long batch, int nocc,
   }
 }
 
+// DMMA versions for nocc >= 16: one CTA per k-point
+__global__ void __launch_bounds__(256)
+position_matrix_dmma_kernel(const cplx* __restrict__ evec, long long batch, int nocc, int n, const double* __restrict__ pos,
+                            cplx* __restrict__ xmat) {
+  __shared__ OvSmem sm;
+  for (long long k = blockIdx.x; k < batch; k += gridDim.x) {
+    const cplx* e = evec + k * (long long)nocc * n;
+    const GemmSide A{e, n, 1, nullptr, 1}, B{e, n, 1, nullptr, 0};
+    cta_gemm_dmma(A, nocc, B, nocc, n, pos, xmat + k * (long long)nocc * nocc, nocc, sm);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+hwf_to_orbital_dmma_kernel(const cplx* __restrict__ hwf, const cplx* __restrict__ evec, long long batch, int nocc, int n,
+                           cplx* __restrict__ out) {
+  __shared__ OvSmem sm;
+  for (long long k = blockIdx.x; k < batch; k += gridDim.x) {
+    // out[i][o] = sum_m hwf[i][m] evec[m][o]: B(q = o, x = m) = evec[m][o] -> row stride 1, contraction stride n
+    const GemmSide A{hwf + k * (long long)nocc * nocc, nocc, 1, nullptr, 0};
+    const GemmSide B{evec + k * (long long)nocc * n, 1, n, nullptr, 0};
+    cta_gemm_dmma(A, nocc, B, n, nocc, nullptr, out + k * (long long)nocc * n, n, sm);
+  }
+}
+
 // out[k][i][o] = sum_m hwf[k][i][m] * evec[k][m][o]      (pythtb.py:2262-2274)
 __global__ void __launch_bounds__(256)
 hwf_to_orbital_kernel(const cplx* __restrict__ hwf, const cplx* __restrict__ evec, long long batch, int nocc, int n,
@@ -1235,6 +1287,12 @@ int tbk_position_matrix(const double* evec_dev, int64_t batch, int32_t nocc, int
                         double* xmat_dev, void* stream) {
   if (!evec_dev || !pos_dev || !xmat_dev || batch < 0 || nocc < 1 || n < 1) { set_error("tbk_position_matrix: bad argument"); return TBK_ERR_ARG; }
   if (batch == 0) return TBK_OK;
+  if (nocc >= 16) {
+    const long long blocks = batch < (long long)kNumSM * 4 ? batch : (long long)kNumSM * 4;
+    position_matrix_dmma_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const cplx*)evec_dev, batch, nocc, n, pos_dev, (cplx*)xmat_dev);
+    TBK_LAUNCH_CHECK("position_matrix_dmma_kernel");
+    return TBK_OK;
+  }
   const long long total = batch * nocc * nocc;
   long long blocks = (total + 255) / 256;
   if (blocks > kNumSM * 16) blocks = kNumSM * 16;
@@ -1264,7 +1322,11 @@ int tbk_position_hwf(const double* evec_dev, int64_t batch, int32_t nocc, int32_
   rc = tbk_eigh_batched(xmat, nocc, batch, hwfc_dev, hwf_dev ? (direct ? hwf_dev : vecs) : nullptr, ws,
                         ws_bytes - (size_t)(ws - (char*)ws_dev), stream);
   if (rc) return rc;
-  if (hwf_dev && orbital_basis) {
+  if (hwf_dev && orbital_basis && nocc >= 16) {
+    const long long blocks = batch < (long long)kNumSM * 4 ? batch : (long long)kNumSM * 4;
+    hwf_to_orbital_dmma_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const cplx*)vecs, (const cplx*)evec_dev, batch, nocc, n, (cplx*)hwf_dev);
+    TBK_LAUNCH_CHECK("hwf_to_orbital_dmma_kernel");
+  } else if (hwf_dev && orbital_basis) {
     const long long total = batch * nocc * n;
     long long blocks = (total + 255) / 256;
     if (blocks > kNumSM * 16) blocks = kNumSM * 16;

@@ -275,3 +275,32 @@ def test_flux_ring_kernel_matches_register_kernel(which, mesh):
     assert abs(ring_tot - base_tot) < 1e-9
     ref = orc.berry_flux(np.array(w._wfs), 2, occ, None, True)
     assert np.max(np.abs(compare.circ_diff(ring_plaq, ref, 2 * np.pi))) < 1e-8
+
+
+@pytest.mark.parametrize("ncell", [12, 40])
+def test_position_operator_tensor_path(ncell):
+    """position_matrix / position_hwf with nocc >= 16 (DMMA GEMM kernels; nocc = 40 also takes the blocked
+    eigensolver for the position matrix) against the oracle on the same eigenvectors."""
+    from oracle import pythtb_oracle as orc
+    mod = _mod()
+    rib = M.bn_ribbon(mod, ncell)
+    n = rib._nsta
+    nocc = n // 2
+    ks = [[0.11], [0.37]]
+    ev, evec = rib.solve_all(ks, eig_vectors=True)
+    for i in range(len(ks)):
+        occ = np.ascontiguousarray(evec[:nocc, i])
+        x = rib.position_matrix(occ, 1)
+        x_ref = orc.position_matrix(rib, occ, 1)
+        assert np.max(np.abs(x - x_ref)) < 1e-11
+        hwfc = rib.position_hwf(occ, 1)
+        hwfc_ref = orc.position_hwf(rib, occ, 1)
+        assert np.max(np.abs(hwfc - hwfc_ref)) < 1e-9
+        c2, hwf = rib.position_hwf(occ, 1, hwf_evec=True, basis="orbital")
+        assert np.max(np.abs(c2 - hwfc_ref)) < 1e-9
+        # each hybrid Wannier function is a unit vector in the occupied subspace and an eigenvector of P X P
+        hw = hwf.reshape(nocc, -1)
+        assert np.max(np.abs(np.sum(np.abs(hw) ** 2, axis=1) - 1.0)) < 1e-10
+        pos = np.asarray(rib._orb)[:, 1]
+        xw = np.einsum("io,o,jo->ij", hw.conj(), pos, hw)
+        assert np.max(np.abs(xw - np.diag(c2))) < 1e-9
