@@ -833,6 +833,22 @@ __device__ cplx lu_det_phase_cta(cplx* __restrict__ M, int n, int ld, double* sr
   return mk(u.re / nu, u.im / nu);
 }
 
+constexpr int kWilsonBig = 8;     // from this nocc on the Wilson-loop branch runs on CTA-wide GEMMs
+
+// sum over the CTA (every thread gets it); red: [32] shared doubles
+__device__ __forceinline__ double block_sum(double x, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[w] = x;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  __syncthreads();
+  return t;
+}
+
 // mode 0: out[l] = det/|det| of the overlap.   mode 1: out[l*nocc*nocc ...] = unitary polar factor.
 __global__ void __launch_bounds__(256)
 link_matrix_kernel(WfView v, LinkMap map, long long nlinks, int mode, cplx* __restrict__ out, cplx* __restrict__ gws) {
@@ -856,8 +872,51 @@ link_matrix_kernel(WfView v, LinkMap map, long long nlinks, int mode, cplx* __re
       if (threadIdx.x == 0) out[l] = u;
       __syncthreads();
     } else {
-      // polar factor: serial scaled Newton on a compact copy (thread 0); adequate for
-      // the moderate nocc of Wilson-loop spectra, cooperative version is future work
+      if (nocc >= kWilsonBig) {
+        // unitary polar factor by Newton-Schulz, X <- X (3 I - X^H X) / 2, both products on the DMMA GEMM.
+        // The overlap of two orthonormal sets has singular values in (0, 1], inside the convergence
+        // region |X|_2 < sqrt(3); anything else (user-filled arrays) is scaled by 1 / |X|_F first.
+        cplx* X = M;
+        cplx* G = M + (size_t)nocc * ld;
+        cplx* Xn = G + (size_t)nocc * ld;
+        double fro = 0.0;
+        for (int idx = threadIdx.x; idx < nocc * nocc; idx += blockDim.x) fro += norm2(X[(size_t)(idx / nocc) * ld + idx % nocc]);
+        fro = block_sum(fro, red);
+        if (fro > 1.0001 * nocc) {
+          const double sc = rsqrt(fro);
+          for (int idx = threadIdx.x; idx < nocc * nocc; idx += blockDim.x) {
+            cplx& x = X[(size_t)(idx / nocc) * ld + idx % nocc];
+            x = sc * x;
+          }
+          __syncthreads();
+        }
+        for (int it = 0; it < 100; ++it) {
+          const GemmSide A1{X, 1, ld, nullptr, 1}, B1{X, 1, ld, nullptr, 0};
+          cta_gemm_dmma(A1, nocc, B1, nocc, nocc, nullptr, G, ld, ov);          // G = X^H X
+          double dev = 0.0;
+          for (int idx = threadIdx.x; idx < nocc * nocc; idx += blockDim.x) {
+            const int r = idx / nocc, c = idx - r * nocc;
+            cplx gg = G[(size_t)r * ld + c];
+            if (r == c) gg.re -= 1.0;
+            dev += norm2(gg);
+            G[(size_t)r * ld + c] = mk((r == c ? 1.0 : 0.0) - 0.5 * gg.re, -0.5 * gg.im);   // 1.5 I - 0.5 G
+          }
+          dev = block_sum(dev, red);
+          if (!(dev > 1.0e-28 * nocc)) break;                                     // |X^H X - I|_F <= 1e-14 sqrt(nocc)
+          const GemmSide A2{X, ld, 1, nullptr, 0}, B2{G, 1, ld, nullptr, 0};
+          cta_gemm_dmma(A2, nocc, B2, nocc, nocc, nullptr, Xn, ld, ov);          // Xn = X P
+          for (int idx = threadIdx.x; idx < nocc * nocc; idx += blockDim.x) {
+            const size_t at = (size_t)(idx / nocc) * ld + idx % nocc;
+            X[at] = Xn[at];
+          }
+          __syncthreads();
+        }
+        cplx* dst = out + (size_t)l * nocc * nocc;
+        for (int idx = threadIdx.x; idx < nocc * nocc; idx += blockDim.x) dst[idx] = X[(size_t)(idx / nocc) * ld + idx % nocc];
+        __syncthreads();
+        continue;
+      }
+      // small nocc: serial scaled Newton on a compact copy (thread 0)
       if (threadIdx.x == 0) {
         cplx* X = M + (size_t)nocc * ld;          // compact nocc x nocc
         cplx* w1 = X + (size_t)nocc * nocc;
@@ -984,6 +1043,102 @@ string_wilson_kernel(const cplx* __restrict__ umats, long long nstr, long long n
   }
 }
 
+// ---- Wilson-loop spectra for nocc >= kWilsonBig -------------------------------------------------
+// (a) ordered product of the link matrices of every string as a binary tree: one launch per level,
+//     U[i] <- U[i] U[i + stride] for i = 0, 2 stride, 4 stride, ... (one CTA per product, DMMA GEMM);
+//     after ceil(log2 nlink) levels U[0] holds prod_t U[t]  (pythtb.py:3826, same left-to-right order).
+__global__ void __launch_bounds__(256)
+string_product_kernel(cplx* __restrict__ umats, long long nstr, long long nlink, long long stride, int nocc,
+                      cplx* __restrict__ tmp) {
+  __shared__ OvSmem sm;
+  const size_t nn = (size_t)nocc * nocc;
+  const long long np = (nlink - stride + 2 * stride - 1) / (2 * stride);
+  cplx* T = tmp + (size_t)blockIdx.x * nn;
+  for (long long wk = blockIdx.x; wk < nstr * np; wk += gridDim.x) {
+    const long long s = wk / np, j = wk - s * np;
+    cplx* A = umats + (size_t)(s * nlink + 2 * stride * j) * nn;
+    const cplx* B = A + (size_t)stride * nn;
+    const GemmSide ga{A, nocc, 1, nullptr, 0}, gb{B, 1, nocc, nullptr, 0};
+    cta_gemm_dmma(ga, nocc, gb, nocc, nocc, nullptr, T, nocc, sm);
+    for (size_t i = threadIdx.x; i < nn; i += blockDim.x) A[i] = T[i];
+    __syncthreads();
+  }
+}
+
+// (b) eigenphases of the unitary W = U[0] of every string through the Hermitian solver: W is normal, so
+//     H(phi) = cos(phi) (W + W^H)/2 + sin(phi) (W - W^H)/(2i) has the eigenvectors of W (eigenvalue
+//     cos(theta - phi)); the phases are read off the Rayleigh quotients v^H W v.  Two generic angles are
+//     run and, per string, the one whose quotients are closer to the unit circle is kept: an accidental
+//     collision cos(theta_1 - phi) = cos(theta_2 - phi) with theta_1 != theta_2 mixes eigenvectors for one
+//     angle only.
+__global__ void __launch_bounds__(256)
+unitary_herm_kernel(const cplx* __restrict__ umats, long long nstr, long long nlink, int nocc, double cphi, double sphi,
+                    cplx* __restrict__ H) {
+  const size_t nn = (size_t)nocc * nocc;
+  const long long total = nstr * (long long)nn;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const long long s = q / (long long)nn;
+    const int r = (int)((q - s * (long long)nn) / nocc), c = (int)(q - s * (long long)nn - (long long)r * nocc);
+    const cplx* W = umats + (size_t)s * nlink * nn;
+    const cplx a = W[(size_t)r * nocc + c], b = conj(W[(size_t)c * nocc + r]);
+    const cplx hs = mk(0.5 * (a.re + b.re), 0.5 * (a.im + b.im));             // (W + W^H) / 2
+    const cplx ha = mk(0.5 * (a.im - b.im), -0.5 * (a.re - b.re));            // (W - W^H) / (2i)
+    H[q] = mk(cphi * hs.re + sphi * ha.re, cphi * hs.im + sphi * ha.im);
+  }
+}
+
+// one warp per (string, band): rho = v^H W v with v the eigenvector ROW vec[s][b][:] (H v^T = lambda v^T)
+__global__ void __launch_bounds__(256)
+unitary_rayleigh_kernel(const cplx* __restrict__ umats, const cplx* __restrict__ vec, long long nstr, long long nlink, int nocc,
+                        double* __restrict__ phase, double* __restrict__ modulus) {
+  const size_t nn = (size_t)nocc * nocc;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long wk = warp0; wk < nstr * nocc; wk += nwarp) {
+    const long long s = wk / nocc;
+    const int b = (int)(wk - s * nocc);
+    const cplx* W = umats + (size_t)s * nlink * nn;
+    const cplx* v = vec + ((size_t)s * nocc + b) * nocc;
+    cplx acc = mk(0.0, 0.0);
+    for (int i = 0; i < nocc; ++i) {
+      cplx row = mk(0.0, 0.0);
+      for (int j = lane; j < nocc; j += 32) fma_acc(row, W[(size_t)i * nocc + j], v[j]);
+      fma_acc_conj(acc, v[i], row);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      acc.re += __shfl_xor_sync(0xffffffffu, acc.re, o);
+      acc.im += __shfl_xor_sync(0xffffffffu, acc.im, o);
+    }
+    if (lane == 0) {
+      phase[wk] = neg_arg(acc);
+      modulus[wk] = sqrt(norm2(acc));
+    }
+  }
+}
+
+// per string: pick the better of the two runs, sort its phases ascending (np.sort, pythtb.py:3837)
+__global__ void __launch_bounds__(64)
+unitary_select_kernel(const double* __restrict__ ph0, const double* __restrict__ mod0, const double* __restrict__ ph1,
+                      const double* __restrict__ mod1, long long nstr, int nocc, double* __restrict__ out) {
+  const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (s >= nstr) return;
+  double w0 = 0.0, w1 = 0.0;
+  for (int b = 0; b < nocc; ++b) {
+    w0 = fmax(w0, fabs(mod0[s * nocc + b] - 1.0));
+    w1 = fmax(w1, fabs(mod1[s * nocc + b] - 1.0));
+  }
+  const double* src = (w0 <= w1 ? ph0 : ph1) + s * nocc;
+  double* o = out + s * nocc;
+  for (int i = 0; i < nocc; ++i) o[i] = src[i];
+  for (int i = 1; i < nocc; ++i) {
+    const double x = o[i];
+    int j = i - 1;
+    while (j >= 0 && o[j] > x) { o[j + 1] = o[j]; --j; }
+    o[j + 1] = x;
+  }
+}
+
 // last slice = first slice (* phase[o]) on [outer][len][inner][nsta_arr][n]
 __global__ void __launch_bounds__(256)
 impose_boundary_kernel(cplx* __restrict__ wfs, long long outer, long long len, long long inner, int nsta_arr, int n,
@@ -1069,6 +1224,10 @@ hwf_to_orbital_kernel(const cplx* __restrict__ hwf, const cplx* __restrict__ eve
 }
 
 static long long link_ws_elems(int nocc) { return (long long)nocc * (nocc | 1) * 3; }
+static int product_grid(long long nstr, long long nlink) {
+  const long long work = nstr * ((nlink + 1) / 2), cap = (long long)kNumSM * 4;
+  return (int)(work < cap ? (work > 0 ? work : 1) : cap);
+}
 static int link_grid(long long nlinks) {
   const long long cap = (long long)kNumSM * 4;
   return (int)(nlinks < cap ? (nlinks > 0 ? nlinks : 1) : cap);
@@ -1243,6 +1402,13 @@ size_t tbk_berry_workspace(int32_t nocc, int32_t n, int64_t nstr, int64_t npts, 
     bytes += align256((size_t)nstr * (2 * (size_t)nocc * nocc + nocc) * 16);
   }
   if (nocc > 4) bytes += align256((size_t)link_grid(nlinks) * link_ws_elems(nocc) * 16);
+  if (berry_evals && nocc >= kWilsonBig) {
+    const size_t nn = (size_t)nocc * nocc;
+    bytes += align256((size_t)product_grid(nstr, npts - 1) * nn * 16);      // tree-product temporaries
+    bytes += 2 * align256((size_t)nstr * nn * 16);                          // H, eigenvectors
+    bytes += 5 * align256((size_t)nstr * nocc * 8);                         // eigenvalues, 2 x (phases, moduli)
+    bytes += tbk_eigh_workspace(nocc, nstr, 1) + 256;
+  }
   return bytes;
 }
 
@@ -1276,10 +1442,48 @@ int tbk_berry_strings(const tbk_wf_view* view, const int64_t* string_off_dev, in
   ws += align256((size_t)nlinks * nn * 16);
   cplx* sws = (cplx*)ws;
   ws += align256((size_t)nstr * (2 * nn + view->nocc) * 16);
-  int rc = launch_links(v, map, nlinks, 1, umats, (cplx*)ws, st);
+  cplx* lws = (cplx*)ws;
+  if (view->nocc > 4) ws += align256((size_t)link_grid(nlinks) * link_ws_elems(view->nocc) * 16);
+  int rc = launch_links(v, map, nlinks, 1, umats, lws, st);
   if (rc) return rc;
-  string_wilson_kernel<<<(unsigned)((nstr + 63) / 64), 64, 0, st>>>(umats, nstr, nlink, view->nocc, sws, out_dev);
-  TBK_LAUNCH_CHECK("string_wilson_kernel");
+  if (view->nocc < kWilsonBig) {
+    string_wilson_kernel<<<(unsigned)((nstr + 63) / 64), 64, 0, st>>>(umats, nstr, nlink, view->nocc, sws, out_dev);
+    TBK_LAUNCH_CHECK("string_wilson_kernel");
+    return TBK_OK;
+  }
+  // ---- large nocc: tree product, Hermitian solver on two generic combinations, Rayleigh quotients
+  const int nocc = view->nocc;
+  const int pgrid = product_grid(nstr, nlink);
+  cplx* ptmp = (cplx*)ws;        ws += align256((size_t)pgrid * nn * 16);
+  for (long long stride = 1; stride < nlink; stride *= 2) {
+    string_product_kernel<<<pgrid, 256, 0, st>>>(umats, nstr, nlink, stride, nocc, ptmp);
+    TBK_LAUNCH_CHECK("string_product_kernel");
+  }
+  cplx* H = (cplx*)ws;           ws += align256((size_t)nstr * nn * 16);
+  cplx* vecs = (cplx*)ws;        ws += align256((size_t)nstr * nn * 16);
+  double* evals = (double*)ws;   ws += align256((size_t)nstr * nocc * 8);
+  double* ph[2]; double* md[2];
+  for (int a = 0; a < 2; ++a) {
+    ph[a] = (double*)ws; ws += align256((size_t)nstr * nocc * 8);
+    md[a] = (double*)ws; ws += align256((size_t)nstr * nocc * 8);
+  }
+  const size_t ews = tbk_eigh_workspace(nocc, nstr, 1);
+  void* ews_ptr = ws;
+  const double phis[2] = {0.7390851332151607, 2.0287578381104342};
+  long long eb = (nstr * (long long)nn + 255) / 256;
+  if (eb > kNumSM * 16) eb = kNumSM * 16;
+  long long rb = (nstr * nocc * 32 + 255) / 256;
+  if (rb > kNumSM * 16) rb = kNumSM * 16;
+  for (int a = 0; a < 2; ++a) {
+    unitary_herm_kernel<<<(unsigned)eb, 256, 0, st>>>(umats, nstr, nlink, nocc, cos(phis[a]), sin(phis[a]), H);
+    TBK_LAUNCH_CHECK("unitary_herm_kernel");
+    rc = tbk_eigh_batched((const double*)H, nocc, nstr, evals, (double*)vecs, ews_ptr, ews, stream);
+    if (rc) return rc;
+    unitary_rayleigh_kernel<<<(unsigned)rb, 256, 0, st>>>(umats, vecs, nstr, nlink, nocc, ph[a], md[a]);
+    TBK_LAUNCH_CHECK("unitary_rayleigh_kernel");
+  }
+  unitary_select_kernel<<<(unsigned)((nstr + 63) / 64), 64, 0, st>>>(ph[0], md[0], ph[1], md[1], nstr, nocc, out_dev);
+  TBK_LAUNCH_CHECK("unitary_select_kernel");
   return TBK_OK;
 }
 

@@ -304,3 +304,29 @@ def test_position_operator_tensor_path(ncell):
         pos = np.asarray(rib._orb)[:, 1]
         xw = np.einsum("io,o,jo->ij", hw.conj(), pos, hw)
         assert np.max(np.abs(xw - np.diag(c2))) < 1e-9
+
+
+@pytest.mark.parametrize("which", ["ribbon12", "ribbon40", "slab10"])
+def test_wilson_loop_spectrum_large_nocc(which):
+    """berry_phase(..., berry_evals=True) for nocc >= 8: Newton-Schulz polar factors on the DMMA GEMM, tree
+    product along the string, eigenphases through the Hermitian solver — against the oracle's SVD / eigvals
+    (pythtb.py:3821-3838) on the same wave functions."""
+    from oracle import pythtb_oracle as orc
+    mod = _mod()
+    if which.startswith("ribbon"):
+        m = M.bn_ribbon(mod, int(which[6:]))
+        mesh, start, d = [37], [0.0], 0
+    else:
+        m = M.cubic_slab(mod, 10)
+        mesh, start, d = [9, 11], [0.0, 0.0], 0
+    nocc = m._nsta // 2
+    w = mod.wf_array(m, mesh)
+    w.solve_on_grid(start)
+    got = w.berry_phase(range(nocc), d, contin=False, berry_evals=True)
+    ref = orc.berry_phase(np.array(w._wfs), len(mesh), list(range(nocc)), d, contin=False, berry_evals=True)
+    assert np.shape(got) == np.shape(ref)
+    ok, dev = compare.sets_close(got, ref, 2 * np.pi, 1e-8)
+    assert ok, dev
+    # total phase of the spectrum = Berry phase of the determinant branch
+    tot = w.berry_phase(range(nocc), d, contin=False)
+    assert np.max(np.abs(compare.circ_diff(np.sum(got, axis=-1), tot, 2 * np.pi))) < 1e-7
