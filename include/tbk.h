@@ -238,6 +238,18 @@ int tbk_flux_plane_x(const tbk_wf_view* view, const int64_t* slice_off_dev, int6
                      double* plaq_dev, double* total_dev,
                      void* ws_dev, size_t ws_bytes, tbk_peer* peer, void* stream);
 
+/* Wilson loops split across ranks (wf_array sharded along the string direction, berry_evals=True):
+ * tbk_wilson_products returns, for every local string, the ORDERED product of the unitary (polar) link
+ * matrices of its local links, prod_dev [nstr][nocc][nocc] (pythtb.py:3813-3826 restricted to the local
+ * links; workspace as tbk_berry_workspace(..., berry_evals = 1)).  The host gathers the per-rank products
+ * in rank order and tbk_wilson_phases multiplies mats_dev [nstr][nmat][nocc][nocc] (destroyed) along nmat
+ * and returns the sorted eigenphases -angle(eigvals), out_dev [nstr][nocc] (pythtb.py:3834-3838). */
+int tbk_wilson_products(const tbk_wf_view* view, const int64_t* string_off_dev, int64_t nstr, int64_t npts,
+                        int64_t stride, double* prod_dev, void* ws_dev, size_t ws_bytes, void* stream);
+size_t tbk_wilson_workspace(int32_t nocc, int64_t nstr, int64_t nmat);
+int tbk_wilson_phases(double* mats_dev, int64_t nstr, int64_t nmat, int32_t nocc, double* out_dev,
+                      void* ws_dev, size_t ws_bytes, void* stream);
+
 /* Name of the kernel family the calling thread's last solve call dispatched to
  * (benchmark / profile bookkeeping). */
 const char* tbk_last_kernel(void);

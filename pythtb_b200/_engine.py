@@ -437,6 +437,31 @@ class B200Engine(object):
         res = out.cpu().numpy()
         return res.reshape(oshape + ((nocc,) if berry_evals else ()))
 
+    def wilson_phases_across_ranks(self, store, dim_arr, occ, dir, nranks):
+        """berry_evals=True for strings that run along the sharded axis: every rank forms the ordered product
+        of the polar link matrices of ITS links (tbk_wilson_products), the per-rank products are all-gathered in
+        rank order over NCCL, and tbk_wilson_phases multiplies them and returns the sorted eigenphases
+        (pythtb.py:3813-3838 with the product split by rank).  Shape other_axes + [nocc]."""
+        import torch.distributed as dist
+        torch = self.torch
+        view, strides, keep = self._view(store, dim_arr, occ)
+        mesh = store.shape[:dim_arr]
+        other = [d for d in range(dim_arr) if d != dir]
+        oshape = tuple(mesh[d] for d in other)
+        offs_d = self._offsets(store, dim_arr, other, strides)
+        nstr, npts, nocc = int(offs_d.numel()), mesh[dir], view.nocc
+        prod = torch.empty((nstr, nocc, nocc), dtype=torch.complex128, device=self.device)
+        ws = self.workspace(self.lib.tbk_berry_workspace(nocc, view.n, nstr, npts, 1))
+        _lib.check(self.lib.tbk_wilson_products(ctypes.byref(view), _ptr(offs_d), nstr, npts, strides[dir], _ptr(prod),
+                                                _ptr(ws), ws.numel(), self.stream()))
+        allp = torch.empty((nranks, nstr, nocc, nocc), dtype=torch.complex128, device=self.device)
+        dist.all_gather_into_tensor(torch.view_as_real(allp), torch.view_as_real(prod).unsqueeze(0))
+        mats = allp.permute(1, 0, 2, 3).contiguous()          # [nstr][rank][nocc][nocc]: rank order = link order
+        out = torch.empty((nstr, nocc), dtype=torch.float64, device=self.device)
+        ws = self.workspace(self.lib.tbk_wilson_workspace(nocc, nstr, nranks))
+        _lib.check(self.lib.tbk_wilson_phases(_ptr(mats), nstr, nranks, nocc, _ptr(out), _ptr(ws), ws.numel(), self.stream()))
+        return out.cpu().numpy().reshape(oshape + (nocc,))
+
     def flux(self, store, dim_arr, occ, dirs, individual):
         """_one_flux_plane on every 2-D slice spanned by ``dirs`` (pythtb.py:3133-3202).
         Returns plaquette phases [rest..., n0-1, n1-1] or their sums [rest...]."""

@@ -20,7 +20,7 @@ SYMBOLS = [
     "tbk_impose_boundary", "tbk_flux_workspace", "tbk_flux_plane", "tbk_berry_workspace",
     "tbk_berry_strings", "tbk_position_matrix", "tbk_position_hwf_workspace", "tbk_position_hwf",
     "tbk_flush_l2", "tbk_halo_pack", "tbk_last_kernel", "tbk_launch_count", "tbk_peer_create", "tbk_peer_connect",
-    "tbk_peer_destroy", "tbk_solve_grid_x", "tbk_flux_plane_x", "tbk_stream_sync", "tbk_debug_profile",
+    "tbk_peer_destroy", "tbk_solve_grid_x", "tbk_flux_plane_x", "tbk_stream_sync", "tbk_debug_profile", "tbk_wilson_products", "tbk_wilson_workspace", "tbk_wilson_phases",
 ]
 
 
@@ -81,6 +81,9 @@ def load():
         "tbk_position_hwf": (ctypes.c_int, [V, I64, I32, I32, V, V, V, I32, V, SZ, V]),
         "tbk_flush_l2": (ctypes.c_int, [V, SZ, V]),
         "tbk_stream_sync": (ctypes.c_int, [V]),
+        "tbk_wilson_products": (ctypes.c_int, [ctypes.POINTER(WfView), V, I64, I64, I64, V, V, SZ, V]),
+        "tbk_wilson_workspace": (SZ, [I32, I64, I64]),
+        "tbk_wilson_phases": (ctypes.c_int, [V, I64, I64, I32, V, V, SZ, V]),
         "tbk_debug_profile": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64), I32]),
         "tbk_halo_pack": (ctypes.c_int, [V, V, I64, I32, I32, V, V]),
         "tbk_peer_create": (ctypes.c_int, [I32, I32, ctypes.POINTER(V), V]),

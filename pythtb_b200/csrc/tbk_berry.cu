@@ -1019,7 +1019,7 @@ string_phase_kernel(const cplx* __restrict__ dets, long long nstr, long long nli
 // eigenvalues by complex QR, phases sorted ascending.  One thread per string.
 __global__ void __launch_bounds__(64)
 string_wilson_kernel(const cplx* __restrict__ umats, long long nstr, long long nlink, int nocc,
-                     cplx* __restrict__ gws, double* __restrict__ out) {
+                     cplx* __restrict__ gws, double* __restrict__ out, cplx* __restrict__ prod_out) {
   const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (s >= nstr) return;
   const size_t nn = (size_t)nocc * nocc;
@@ -1031,6 +1031,10 @@ string_wilson_kernel(const cplx* __restrict__ umats, long long nstr, long long n
   for (long long t = 0; t < nlink; ++t) {
     matmul_nn(P, umats + (size_t)(s * nlink + t) * nn, T, nocc);     // prd = prd @ U_t  (pythtb.py:3826)
     for (size_t i = 0; i < nn; ++i) P[i] = T[i];
+  }
+  if (prod_out) {                                // only the ordered product is wanted (sharded strings)
+    for (size_t i = 0; i < nn; ++i) prod_out[(size_t)s * nn + i] = P[i];
+    return;
   }
   comqr_eigvals(P, nocc, nocc, ev);
   double* o = out + s * nocc;
@@ -1233,6 +1237,81 @@ static int link_grid(long long nlinks) {
   return (int)(nlinks < cap ? (nlinks > 0 ? nlinks : 1) : cap);
 }
 
+// prod[s] = umats[s][0]  (the root of the product tree)
+__global__ void __launch_bounds__(256)
+string_root_copy_kernel(const cplx* __restrict__ umats, long long nstr, long long nlink, int nocc, cplx* __restrict__ prod) {
+  const size_t nn = (size_t)nocc * nocc;
+  const long long total = nstr * (long long)nn;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const long long s = q / (long long)nn;
+    prod[q] = umats[(size_t)s * nlink * nn + (size_t)(q - s * (long long)nn)];
+  }
+}
+
+static size_t align256_(size_t x) { return (x + 255) & ~(size_t)255; }
+size_t wilson_tail_bytes(int nocc, long long nstr, long long nlink);
+
+// ordered product of the nlink unitary matrices of every string (umats [nstr][nlink][nocc][nocc], destroyed)
+// and then either its eigenphases (out, sorted ascending) or the product itself (prod_out); ws as sized by
+// wilson_tail_bytes.
+static int wilson_tail(cplx* umats, long long nstr, long long nlink, int nocc, double* out, cplx* prod_out, char* ws,
+                       cudaStream_t st) {
+  const size_t nn = (size_t)nocc * nocc;
+  if (nocc < kWilsonBig) {
+    cplx* sws = (cplx*)ws;
+    string_wilson_kernel<<<(unsigned)((nstr + 63) / 64), 64, 0, st>>>(umats, nstr, nlink, nocc, sws, out, prod_out);
+    TBK_LAUNCH_CHECK("string_wilson_kernel");
+    return TBK_OK;
+  }
+  // large nocc: tree product, Hermitian solver on two generic combinations, Rayleigh quotients
+  const int pgrid = product_grid(nstr, nlink);
+  cplx* ptmp = (cplx*)ws;        ws += align256_((size_t)pgrid * nn * 16);
+  for (long long stride = 1; stride < nlink; stride *= 2) {
+    string_product_kernel<<<pgrid, 256, 0, st>>>(umats, nstr, nlink, stride, nocc, ptmp);
+    TBK_LAUNCH_CHECK("string_product_kernel");
+  }
+  long long eb = (nstr * (long long)nn + 255) / 256;
+  if (eb > kNumSM * 16) eb = kNumSM * 16;
+  if (prod_out) {
+    string_root_copy_kernel<<<(unsigned)eb, 256, 0, st>>>(umats, nstr, nlink, nocc, prod_out);
+    TBK_LAUNCH_CHECK("string_root_copy_kernel");
+    return TBK_OK;
+  }
+  cplx* H = (cplx*)ws;           ws += align256_((size_t)nstr * nn * 16);
+  cplx* vecs = (cplx*)ws;        ws += align256_((size_t)nstr * nn * 16);
+  double* evals = (double*)ws;   ws += align256_((size_t)nstr * nocc * 8);
+  double* ph[2]; double* md[2];
+  for (int a = 0; a < 2; ++a) {
+    ph[a] = (double*)ws; ws += align256_((size_t)nstr * nocc * 8);
+    md[a] = (double*)ws; ws += align256_((size_t)nstr * nocc * 8);
+  }
+  const size_t ews = tbk_eigh_workspace(nocc, nstr, 1);
+  const double phis[2] = {0.7390851332151607, 2.0287578381104342};
+  long long rb = (nstr * nocc * 32 + 255) / 256;
+  if (rb > kNumSM * 16) rb = kNumSM * 16;
+  for (int a = 0; a < 2; ++a) {
+    unitary_herm_kernel<<<(unsigned)eb, 256, 0, st>>>(umats, nstr, nlink, nocc, cos(phis[a]), sin(phis[a]), H);
+    TBK_LAUNCH_CHECK("unitary_herm_kernel");
+    const int rc = tbk_eigh_batched((const double*)H, nocc, nstr, evals, (double*)vecs, ws, ews, (void*)st);
+    if (rc) return rc;
+    unitary_rayleigh_kernel<<<(unsigned)rb, 256, 0, st>>>(umats, vecs, nstr, nlink, nocc, ph[a], md[a]);
+    TBK_LAUNCH_CHECK("unitary_rayleigh_kernel");
+  }
+  unitary_select_kernel<<<(unsigned)((nstr + 63) / 64), 64, 0, st>>>(ph[0], md[0], ph[1], md[1], nstr, nocc, out);
+  TBK_LAUNCH_CHECK("unitary_select_kernel");
+  return TBK_OK;
+}
+
+size_t wilson_tail_bytes(int nocc, long long nstr, long long nlink) {
+  const size_t nn = (size_t)nocc * nocc;
+  if (nocc < kWilsonBig) return align256_((size_t)nstr * (2 * nn + nocc) * 16);
+  size_t bytes = align256_((size_t)product_grid(nstr, nlink) * nn * 16);
+  bytes += 2 * align256_((size_t)nstr * nn * 16);
+  bytes += 5 * align256_((size_t)nstr * nocc * 8);
+  bytes += tbk_eigh_workspace(nocc, nstr, 1) + 256;
+  return bytes;
+}
+
 static int launch_links(const WfView& v, const LinkMap& map, long long nlinks, int mode, cplx* out, cplx* gws, cudaStream_t st) {
   if (nlinks <= 0) return TBK_OK;
   if (v.nocc <= 4) {
@@ -1399,16 +1478,9 @@ size_t tbk_berry_workspace(int32_t nocc, int32_t n, int64_t nstr, int64_t npts, 
   if (!berry_evals) bytes += align256((size_t)nlinks * 16);
   else {
     bytes += align256((size_t)nlinks * nocc * nocc * 16);
-    bytes += align256((size_t)nstr * (2 * (size_t)nocc * nocc + nocc) * 16);
+    bytes += wilson_tail_bytes(nocc, nstr, npts - 1);
   }
   if (nocc > 4) bytes += align256((size_t)link_grid(nlinks) * link_ws_elems(nocc) * 16);
-  if (berry_evals && nocc >= kWilsonBig) {
-    const size_t nn = (size_t)nocc * nocc;
-    bytes += align256((size_t)product_grid(nstr, npts - 1) * nn * 16);      // tree-product temporaries
-    bytes += 2 * align256((size_t)nstr * nn * 16);                          // H, eigenvectors
-    bytes += 5 * align256((size_t)nstr * nocc * 8);                         // eigenvalues, 2 x (phases, moduli)
-    bytes += tbk_eigh_workspace(nocc, nstr, 1) + 256;
-  }
   return bytes;
 }
 
@@ -1440,51 +1512,45 @@ int tbk_berry_strings(const tbk_wf_view* view, const int64_t* string_off_dev, in
   const size_t nn = (size_t)view->nocc * view->nocc;
   cplx* umats = (cplx*)ws;
   ws += align256((size_t)nlinks * nn * 16);
-  cplx* sws = (cplx*)ws;
-  ws += align256((size_t)nstr * (2 * nn + view->nocc) * 16);
   cplx* lws = (cplx*)ws;
   if (view->nocc > 4) ws += align256((size_t)link_grid(nlinks) * link_ws_elems(view->nocc) * 16);
   int rc = launch_links(v, map, nlinks, 1, umats, lws, st);
   if (rc) return rc;
-  if (view->nocc < kWilsonBig) {
-    string_wilson_kernel<<<(unsigned)((nstr + 63) / 64), 64, 0, st>>>(umats, nstr, nlink, view->nocc, sws, out_dev);
-    TBK_LAUNCH_CHECK("string_wilson_kernel");
-    return TBK_OK;
+  return wilson_tail(umats, nstr, nlink, view->nocc, out_dev, nullptr, ws, st);
+}
+
+int tbk_wilson_products(const tbk_wf_view* view, const int64_t* string_off_dev, int64_t nstr, int64_t npts, int64_t stride,
+                        double* prod_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  if (!view || !view->wfs_dev || !view->occ_dev || !string_off_dev || !prod_dev || nstr < 1 || npts < 2 || view->nocc < 1) {
+    set_error("tbk_wilson_products: bad argument");
+    return TBK_ERR_ARG;
   }
-  // ---- large nocc: tree product, Hermitian solver on two generic combinations, Rayleigh quotients
-  const int nocc = view->nocc;
-  const int pgrid = product_grid(nstr, nlink);
-  cplx* ptmp = (cplx*)ws;        ws += align256((size_t)pgrid * nn * 16);
-  for (long long stride = 1; stride < nlink; stride *= 2) {
-    string_product_kernel<<<pgrid, 256, 0, st>>>(umats, nstr, nlink, stride, nocc, ptmp);
-    TBK_LAUNCH_CHECK("string_product_kernel");
+  if (!ws_dev || ws_bytes < tbk_berry_workspace(view->nocc, view->n, nstr, npts, 1)) {
+    set_error("tbk_wilson_products: workspace too small");
+    return TBK_ERR_WORKSPACE;
   }
-  cplx* H = (cplx*)ws;           ws += align256((size_t)nstr * nn * 16);
-  cplx* vecs = (cplx*)ws;        ws += align256((size_t)nstr * nn * 16);
-  double* evals = (double*)ws;   ws += align256((size_t)nstr * nocc * 8);
-  double* ph[2]; double* md[2];
-  for (int a = 0; a < 2; ++a) {
-    ph[a] = (double*)ws; ws += align256((size_t)nstr * nocc * 8);
-    md[a] = (double*)ws; ws += align256((size_t)nstr * nocc * 8);
-  }
-  const size_t ews = tbk_eigh_workspace(nocc, nstr, 1);
-  void* ews_ptr = ws;
-  const double phis[2] = {0.7390851332151607, 2.0287578381104342};
-  long long eb = (nstr * (long long)nn + 255) / 256;
-  if (eb > kNumSM * 16) eb = kNumSM * 16;
-  long long rb = (nstr * nocc * 32 + 255) / 256;
-  if (rb > kNumSM * 16) rb = kNumSM * 16;
-  for (int a = 0; a < 2; ++a) {
-    unitary_herm_kernel<<<(unsigned)eb, 256, 0, st>>>(umats, nstr, nlink, nocc, cos(phis[a]), sin(phis[a]), H);
-    TBK_LAUNCH_CHECK("unitary_herm_kernel");
-    rc = tbk_eigh_batched((const double*)H, nocc, nstr, evals, (double*)vecs, ews_ptr, ews, stream);
-    if (rc) return rc;
-    unitary_rayleigh_kernel<<<(unsigned)rb, 256, 0, st>>>(umats, vecs, nstr, nlink, nocc, ph[a], md[a]);
-    TBK_LAUNCH_CHECK("unitary_rayleigh_kernel");
-  }
-  unitary_select_kernel<<<(unsigned)((nstr + 63) / 64), 64, 0, st>>>(ph[0], md[0], ph[1], md[1], nstr, nocc, out_dev);
-  TBK_LAUNCH_CHECK("unitary_select_kernel");
-  return TBK_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  WfView v{(const cplx*)view->wfs_dev, view->n, view->nsta_arr, view->nocc, view->occ_dev};
+  LinkMap map{(const long long*)string_off_dev, npts, 1, stride, 0, 0};
+  const long long nlink = npts - 1, nlinks = nstr * nlink;
+  const size_t nn = (size_t)view->nocc * view->nocc;
+  char* ws = (char*)ws_dev;
+  cplx* umats = (cplx*)ws;
+  ws += align256((size_t)nlinks * nn * 16);
+  cplx* lws = (cplx*)ws;
+  if (view->nocc > 4) ws += align256((size_t)link_grid(nlinks) * link_ws_elems(view->nocc) * 16);
+  int rc = launch_links(v, map, nlinks, 1, umats, lws, st);
+  if (rc) return rc;
+  return wilson_tail(umats, nstr, nlink, view->nocc, nullptr, (cplx*)prod_dev, ws, st);
+}
+
+size_t tbk_wilson_workspace(int32_t nocc, int64_t nstr, int64_t nmat) { return wilson_tail_bytes(nocc, nstr, nmat) + 256; }
+
+int tbk_wilson_phases(double* mats_dev, int64_t nstr, int64_t nmat, int32_t nocc, double* out_dev, void* ws_dev,
+                      size_t ws_bytes, void* stream) {
+  if (!mats_dev || !out_dev || nstr < 1 || nmat < 1 || nocc < 1) { set_error("tbk_wilson_phases: bad argument"); return TBK_ERR_ARG; }
+  if (!ws_dev || ws_bytes < tbk_wilson_workspace(nocc, nstr, nmat)) { set_error("tbk_wilson_phases: workspace too small"); return TBK_ERR_WORKSPACE; }
+  return wilson_tail((cplx*)mats_dev, nstr, nmat, nocc, out_dev, nullptr, (char*)ws_dev, (cudaStream_t)stream);
 }
 
 int tbk_position_matrix(const double* evec_dev, int64_t batch, int32_t nocc, int32_t n, const double* pos_dev,

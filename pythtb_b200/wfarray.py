@@ -340,17 +340,19 @@ class wf_array(object):
         else:
             raise Exception("\n\nWrong dimensionality!")
         eng = self._model._engine()
-        ret = eng.berry_strings(self._store, self._dim_arr, occ, dir_use, berry_evals)
-        if self._shard is not None:
-            if dir_use == 0:
-                # a string along axis 0 crosses every rank: det(prod M) = prod det(M), so the
-                # phase is the wrapped sum of the per-rank phases
-                if berry_evals:
-                    raise Exception("\n\nberry_evals=True along the sharded mesh axis needs the ordered product of "
-                                    "link matrices across ranks; use dir != 0 or an unsharded wf_array.")
-                ret = self._wrap(eng.allreduce(np.asarray(ret, dtype=float), "sum"))
-            else:
-                ret = self._gather_axis0(ret, 0, with_closing_row=True)
+        if self._shard is not None and dir_use == 0 and berry_evals:
+            # strings along the sharded axis: per-rank ordered products of the unitary link matrices,
+            # gathered in rank order and multiplied before the eigenphases are taken
+            ret = eng.wilson_phases_across_ranks(self._store, self._dim_arr, occ, dir_use, self._shard.nranks)
+        else:
+            ret = eng.berry_strings(self._store, self._dim_arr, occ, dir_use, berry_evals)
+            if self._shard is not None:
+                if dir_use == 0:
+                    # a string along axis 0 crosses every rank: det(prod M) = prod det(M), so the
+                    # phase is the wrapped sum of the per-rank phases
+                    ret = self._wrap(eng.allreduce(np.asarray(ret, dtype=float), "sum"))
+                else:
+                    ret = self._gather_axis0(ret, 0, with_closing_row=True)
         if self._dim_arr == 1 and not berry_evals:
             ret = float(np.asarray(ret).reshape(-1)[0])
         else:

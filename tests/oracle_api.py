@@ -115,6 +115,34 @@ class OracleEngine(object):
     def berry_strings(self, store, dim_arr, occ, dir, berry_evals):
         return np.asarray(orc.berry_phase(store.arr, dim_arr, occ, dir, contin=False, berry_evals=berry_evals))
 
+    def wilson_phases_across_ranks(self, store, dim_arr, occ, dir, nranks):
+        """numpy restatement of the split Wilson loop: local ordered product of the SVD polar factors of the
+        local links (pythtb.py:3813-3826), gathered in rank order, multiplied, eigenphases sorted (3834-3838)."""
+        import torch.distributed as dist
+        wfs = np.moveaxis(store.arr, dir, 0)                      # [npts, other..., state, orb...]
+        npts = wfs.shape[0]
+        other = wfs.shape[1:dim_arr]
+        nsta = wfs.shape[dim_arr]
+        flat = wfs.reshape((npts, int(np.prod(other)) if other else 1, nsta, -1))[:, :, list(occ)]
+        nstr, nocc = flat.shape[1], len(occ)
+        prods = np.zeros((nstr, nocc, nocc), dtype=complex)
+        for s in range(nstr):
+            prd = np.identity(nocc, dtype=complex)
+            for t in range(npts - 1):
+                ovr = flat[t, s].conj() @ flat[t + 1, s].T
+                u, _, vh = np.linalg.svd(ovr)
+                prd = prd @ (u @ vh)
+            prods[s] = prd
+        parts = [None] * nranks
+        dist.all_gather_object(parts, prods)
+        out = np.zeros((nstr, nocc))
+        for s in range(nstr):
+            prd = np.identity(nocc, dtype=complex)
+            for r in range(nranks):
+                prd = prd @ parts[r][s]
+            out[s] = np.sort(-np.angle(np.linalg.eigvals(prd)))
+        return out.reshape(tuple(other) + (nocc,))
+
     def flux(self, store, dim_arr, occ, dirs, individual):
         return np.asarray(orc.berry_flux(store.arr, dim_arr, occ, dirs, individual_phases=individual))
 

@@ -46,6 +46,12 @@ def main():
                     e_ref = full.berry_phase(occ, 1, contin=False, berry_evals=True)
                     e = w.berry_phase(occ, 1, contin=False, berry_evals=True)
                     assert np.max(np.abs(compare.circ_diff(e, e_ref, 2 * np.pi))) < 1e-10
+                    # strings along the sharded axis: ordered product of the per-rank products
+                    e0_ref = full.berry_phase(occ, 0, contin=False, berry_evals=True)
+                    e0 = w.berry_phase(occ, 0, contin=False, berry_evals=True)
+                    assert e0.shape == e0_ref.shape, (e0.shape, e0_ref.shape)
+                    ok, dev = compare.sets_close(e0, e0_ref, 2 * np.pi, 1e-9)
+                    assert ok, dev
         # 3-D mesh: axis 0 sharded, flux on planes that do / do not contain it
         m3 = M.random_model(api, norb=2, dim=3, nhop=6, nspin=1, seed=5)
         full = api.wf_array(m3, [7, 5, 6])

@@ -48,6 +48,26 @@ def main():
                 for d in (0, 1):
                     b_ref, b = full.berry_phase(occ, d, contin=False), w.berry_phase(occ, d, contin=False)
                     assert b.shape == b_ref.shape and np.max(np.abs(compare.circ_diff(b, b_ref, 2 * np.pi))) < 1e-9
+                if len(occ) > 1 and halo == "auto":
+                    # Wilson-loop spectra; d = 0 runs along the sharded axis (ordered product across ranks)
+                    for d in (0, 1):
+                        e_ref = full.berry_phase(occ, d, contin=False, berry_evals=True)
+                        e = w.berry_phase(occ, d, contin=False, berry_evals=True)
+                        assert e.shape == e_ref.shape, (e.shape, e_ref.shape)
+                        ok, dev = compare.sets_close(e, e_ref, 2 * np.pi, 1e-8)
+                        assert ok, (d, dev)
+        # a wider occupied set: the CTA-wide Wilson-loop kernels (nocc >= 8) across ranks
+        rib = M.random_model(tb, norb=20, dim=2, nhop=40, nspin=1, seed=11)
+        full = tb.wf_array(rib, [17, 9])
+        full.solve_on_grid([0.0, 0.0])
+        w = tb.wf_array(rib, [17, 9], shard=(rank, world))
+        w.solve_on_grid([0.0, 0.0])
+        occ = list(range(10))
+        for d in (0, 1):
+            e_ref = full.berry_phase(occ, d, contin=False, berry_evals=True)
+            e = w.berry_phase(occ, d, contin=False, berry_evals=True)
+            ok, dev = compare.sets_close(e, e_ref, 2 * np.pi, 1e-8)
+            assert e.shape == e_ref.shape and ok, (d, dev)
         print("rank %d ok" % rank, flush=True)
     except BaseException:
         # a failed rank must not leave the others waiting inside a collective: report and kill the job
