@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Secondary measurements (not the headline bench): BASELINE configs 3-5 at reduced sizes through the
-public API, with the numpy oracle timed beside each on the host.  Usage: python profiles/bench_configs.py"""
+public API, with the numpy oracle timed beside each on one host core.  Usage: python profiles/bench_configs.py"""
 import json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -11,7 +11,7 @@ from tests import models as M, oracle_api
 from oracle import pythtb_oracle as orc
 
 
-def timeit(fn, reps=3):
+def timeit(fn, reps=2):
     fn(); torch.cuda.synchronize()
     best = 1e30
     for _ in range(reps):
@@ -27,24 +27,29 @@ t = timeit(lambda: m8.solve_all(k))
 m8o = M.random_model(oracle_api, norb=8, dim=3, nhop=300, nspin=1, seed=8)
 t0 = time.perf_counter(); orc.solve_all(m8o, k[:4096]); tc = time.perf_counter() - t0
 out["cfg3_n8_nhop300_solve_all_64^3"] = {"gpu_kpts_per_s": len(k) / t, "cpu1_kpts_per_s": 4096 / tc}
-# config 4: BN ribbon norb=200: solve_on_grid on 2001 k + berry_phase of the lower half
-for ncell in (100, 200):
+# config 4: BN ribbon: solve_on_grid + berry_phase of the lower half (determinant branch)
+for ncell, nk in ((100, 2369), (200, 1185)):
     rib = M.bn_ribbon(tb, ncell)
     n = rib._nsta
-    nk = 1001 if ncell == 100 else 257
     w = tb.wf_array(rib, [nk])
-    t = timeit(lambda: w.solve_on_grid([0.0]), reps=2)
-    tb_ = timeit(lambda: w.berry_phase(range(n // 2), 0), reps=2)
+    t = timeit(lambda: w._solve_on_grid_device(np.array([0.0])))
+    tb_ = timeit(lambda: w.berry_phase(range(n // 2), 0))
     ribo = M.bn_ribbon(oracle_api, ncell)
-    t0 = time.perf_counter(); orc.solve_all(ribo, np.linspace(0, 1, 16)[:, None], eig_vectors=True); tc = time.perf_counter() - t0
-    out["cfg4_ribbon_n%d" % n] = {"gpu_kpts_per_s_eigh": (nk - 1) / t, "gpu_links_per_s_berry": (nk - 1) / tb_,
-                                  "cpu_kpts_per_s_eigh": 16 / tc}
-# config 5: cubic slab norb 99 / 199: solve_on_grid on 17x17 + all-band Wilson loop
-for nl in (50, 100):
+    t0 = time.perf_counter(); orc.solve_all(ribo, np.linspace(0, 1, 8)[:, None], eig_vectors=True); tc = time.perf_counter() - t0
+    out["cfg4_ribbon_n%d" % n] = {"nk": nk - 1, "gpu_kpts_per_s_eigh": (nk - 1) / t, "gpu_links_per_s_berry_nocc%d" % (n // 2): (nk - 1) / tb_,
+                                  "cpu1_kpts_per_s_eigh": 8 / tc}
+# config 5: cubic slab: solve_on_grid, all-band Wilson loop (berry_evals), batched HWF + single-band HWF Berry phases
+for nl, mesh in ((50, [25, 25]), (100, [18, 18]), (250, [9, 9])):
     slab = M.cubic_slab(tb, nl)
     n = slab._nsta
-    w = tb.wf_array(slab, [17, 17])
-    t = timeit(lambda: w.solve_on_grid([0.0, 0.0]), reps=2)
-    tw = timeit(lambda: w.berry_phase(range(nl), 0, contin=False), reps=2)
-    out["cfg5_slab_n%d" % n] = {"gpu_kpts_per_s_eigh": 256 / t, "gpu_links_per_s_berry_nocc%d" % nl: 16 * 17 / tw}
+    w = tb.wf_array(slab, mesh)
+    npts = (mesh[0] - 1) * (mesh[1] - 1)
+    t = timeit(lambda: w._solve_on_grid_device(np.array([0.0, 0.0])), reps=1)
+    tw = timeit(lambda: w.berry_phase(range(nl), 0, contin=False), reps=1)
+    te = timeit(lambda: w.berry_phase(range(nl), 0, contin=False, berry_evals=True), reps=1)
+    th = timeit(lambda: w.position_hwf_all(list(range(nl)), 2, hwf_evec=True), reps=1)
+    nlinks = (mesh[0] - 1) * mesh[1]
+    out["cfg5_slab_n%d" % n] = {"mesh": mesh, "gpu_kpts_per_s_eigh": npts / t, "gpu_links_per_s_det_nocc%d" % nl: nlinks / tw,
+                                "gpu_links_per_s_wilson_evals_nocc%d" % nl: nlinks / te,
+                                "gpu_kpts_per_s_position_hwf_all": mesh[0] * mesh[1] / th}
 print(json.dumps(out, indent=1))

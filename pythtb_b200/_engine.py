@@ -542,6 +542,34 @@ class B200Engine(object):
         _lib.check(self.lib.tbk_position_matrix(_ptr(ed), batch, nocc, n, _ptr(pos), _ptr(x), self.stream()))
         return x.cpu().numpy()
 
+    def position_hwf_store(self, model, store, dim_arr, occ, dir, hwf_evec, out_store=None):
+        """position_hwf at EVERY mesh point of a wf_array in one batched call, device to device
+        (the per-k Python loop of examples/cubic_slab_hwf.py:63-79).  Returns the centres
+        [mesh..., nocc] as a host array; with ``hwf_evec`` the hybrid Wannier functions in the orbital basis are
+        written into ``out_store`` (shape mesh + (nocc, norb(,2))) without leaving the device."""
+        torch = self.torch
+        wfs = store.dev(will_write=False)
+        mesh = store.shape[:dim_arr]
+        nsta = store.shape[dim_arr]
+        n = 1
+        for x in store.shape[dim_arr + 1:]:
+            n *= int(x)
+        occ_t = torch.as_tensor(np.asarray(occ, dtype=np.int64), device=self.device)
+        nocc = int(occ_t.numel())
+        batch = 1
+        for x in mesh:
+            batch *= int(x)
+        ed = wfs.reshape(batch, nsta, n).index_select(1, occ_t).contiguous()      # data movement only
+        pos = self.to_dev(self._pos(model, dir), np.float64)
+        hwfc = torch.empty((batch, nocc), dtype=torch.float64, device=self.device)
+        hwf = None
+        if hwf_evec:
+            hwf = out_store.dev(will_write=True).reshape(batch, nocc, n)
+        ws = self.workspace(self.lib.tbk_position_hwf_workspace(nocc, n, batch))
+        _lib.check(self.lib.tbk_position_hwf(_ptr(ed), batch, nocc, n, _ptr(pos), _ptr(hwfc), _ptr(hwf), 1,
+                                             _ptr(ws), ws.numel(), self.stream()))
+        return hwfc.cpu().numpy().reshape(tuple(mesh) + (nocc,))
+
     def position_hwf(self, model, evec, dir, hwf_evec, orbital_basis):
         """tb_model.position_hwf batched (pythtb.py:2162-2279)."""
         torch = self.torch

@@ -308,6 +308,26 @@ class wf_array(object):
         """pythtb.py:2837-2861."""
         return self._model.position_hwf(self._evec_at(key, occ), dir, hwf_evec, basis)
 
+    def position_hwf_all(self, occ, dir, hwf_evec=False):
+        """Extension of the reference API: ``position_hwf`` (pythtb.py:2837-2861, 2162-2279) at every
+        mesh point in ONE batched launch — the loop of examples/cubic_slab_hwf.py:63-79.
+        Returns ``hwfc[mesh..., nocc]``; with ``hwf_evec`` also a new ``wf_array`` (``nsta_arr = nocc``)
+        holding the hybrid Wannier functions in the orbital basis at every mesh point, ready for
+        ``impose_pbc`` / ``berry_phase`` (device resident; nothing is copied through the host)."""
+        occ = self._occ(occ, allow_none=False)
+        if self._model._assume_position_operator_diagonal == False:  # noqa: E712
+            _offdiag_approximation_warning_and_stop()
+        self._model._position_checks(dir)
+        eng = self._model._engine()
+        out = None
+        if hwf_evec:
+            out = wf_array(self._model, list(self._mesh_arr), nsta_arr=len(occ)) if self._shard is None else \
+                wf_array(self._model, list(self._mesh_arr), nsta_arr=len(occ), shard=(self._shard.rank, self._shard.nranks),
+                         halo=self._halo)
+        hwfc = eng.position_hwf_store(self._model, self._store, self._dim_arr, occ, dir, hwf_evec,
+                                      out._store if out is not None else None)
+        return (hwfc, out) if hwf_evec else hwfc
+
     # ------------------------------------------------------------ Berry phase
     @staticmethod
     def _wrap(x):

@@ -146,6 +146,21 @@ class OracleEngine(object):
     def flux(self, store, dim_arr, occ, dirs, individual):
         return np.asarray(orc.berry_flux(store.arr, dim_arr, occ, dirs, individual_phases=individual))
 
+    def position_hwf_store(self, model, store, dim_arr, occ, dir, hwf_evec, out_store=None):
+        mesh = store.arr.shape[:dim_arr]
+        nocc = len(occ)
+        hwfc = np.zeros(tuple(mesh) + (nocc,))
+        for idx in np.ndindex(*mesh):
+            ev = store.arr[idx][list(occ)]
+            ev = ev.reshape(nocc, -1)
+            if hwf_evec:
+                c, v = orc.position_hwf(model, ev, dir, True, "orbital")
+                out_store.arr[idx] = np.asarray(v).reshape(out_store.arr[idx].shape)
+            else:
+                c = orc.position_hwf(model, ev, dir)
+            hwfc[idx] = c
+        return hwfc
+
     def position_matrix(self, model, evec, dir):
         return np.array([orc.position_matrix(model, e, dir) for e in evec])
 

@@ -330,3 +330,33 @@ def test_wilson_loop_spectrum_large_nocc(which):
     # total phase of the spectrum = Berry phase of the determinant branch
     tot = w.berry_phase(range(nocc), d, contin=False)
     assert np.max(np.abs(compare.circ_diff(np.sum(got, axis=-1), tot, 2 * np.pi))) < 1e-7
+
+
+def test_position_hwf_all_matches_per_point_calls():
+    """wf_array.position_hwf_all (one batched launch, device resident) against the reference-style loop of
+    per-point position_hwf calls that fills a second wf_array (examples/cubic_slab_hwf.py:63-91), including the
+    Berry phases of the individual hybrid Wannier bands."""
+    mod = _mod()
+    nl = 10
+    slab = M.cubic_slab(mod, nl)
+    mesh = [6, 7]
+    bloch = mod.wf_array(slab, mesh)
+    bloch.solve_on_grid([0.0, 0.0])
+    occ = list(range(nl))
+    hwfc_all, hwf_all = bloch.position_hwf_all(occ, 2, hwf_evec=True)
+    manual = mod.wf_array(slab, mesh, nsta_arr=nl)
+    hwfc = np.zeros(tuple(mesh) + (nl,))
+    for ix in range(mesh[0]):
+        for iy in range(mesh[1]):
+            (val, vec) = bloch.position_hwf([ix, iy], occ=occ, dir=2, hwf_evec=True, basis="orbital")
+            hwfc[ix, iy] = val
+            manual[ix, iy] = vec
+    assert np.max(np.abs(hwfc_all - hwfc)) < 1e-10
+    assert np.max(np.abs(bloch.position_hwf_all(occ, 2) - hwfc)) < 1e-10
+    for arr in (hwf_all, manual):
+        arr.impose_pbc(0, 0)
+        arr.impose_pbc(1, 1)
+    for band in (0, nl // 2, nl - 1):
+        a = hwf_all.berry_phase([band], dir=0, contin=False)
+        b = manual.berry_phase([band], dir=0, contin=False)
+        assert np.max(np.abs(compare.circ_diff(a, b, 2 * np.pi))) < 1e-8

@@ -28,3 +28,18 @@ def test_golden_log_pins_reference():
     assert log["pythtb"] == "1.8.0"
     assert log["worst_cross_check_dev"] < 1e-10
     assert len(log["cross_check"]) >= 20
+
+
+def test_position_hwf_all_host_logic():
+    """Host logic of the batched extension wf_array.position_hwf_all, served by the numpy oracle."""
+    from tests import models as M, oracle_api as api
+    nl = 5
+    slab = M.cubic_slab(api, nl)
+    bloch = api.wf_array(slab, [4, 5])
+    bloch.solve_on_grid([0.0, 0.0])
+    occ = list(range(nl))
+    hwfc, hwf = bloch.position_hwf_all(occ, 2, hwf_evec=True)
+    assert hwfc.shape == (4, 5, nl) and hwf._wfs.shape[:3] == (4, 5, nl)
+    val, vec = bloch.position_hwf([1, 2], occ=occ, dir=2, hwf_evec=True, basis="orbital")
+    assert np.max(np.abs(hwfc[1, 2] - val)) < 1e-12
+    assert np.max(np.abs(hwf._wfs[1, 2] - vec)) < 1e-12
