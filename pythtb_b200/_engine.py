@@ -243,6 +243,22 @@ class B200Engine(object):
         wrap0: 1 = write the periodic image of row 0 (single shard), 0 = leave the
         closing row to a halo exchange, 2 = compute the closing row in this launch."""
         torch = self.torch
+        # ---- fast path: the same call as last time on this store (a parameter sweep, the bench loop):
+        # reuse the marshalled arguments as long as every buffer they point to is still the live one
+        fast_key = None
+        if reduce_ranks is None and (host_result or not want_gaps):
+            fast_key = (id(model._plan()), tuple(int(x) for x in mesh_arr), tuple(float(x) for x in start_k), row0, nrows,
+                        wrap0, want_gaps, host_result)
+            hit = store.__dict__.get("_tbk_sg_fast")
+            if hit is not None and hit[0] == fast_key and hit[1] is store._dev and hit[2] is self._ws and \
+                    store.state != "host":
+                store.state = "device"
+                _lib.check(self.lib.tbk_solve_grid(*hit[3], self.stream()))
+                gaps_h = hit[5]
+                if gaps_h is not None:
+                    self.sync()
+                    return gaps_h.copy()
+                return None
         handle, plan = self.model_handle(model)
         nd, n = len(mesh_arr), plan.nsta
         if nrows is None:
@@ -280,6 +296,9 @@ class B200Engine(object):
                     _lib.check(rc)
         if not launched:
             _lib.check(self.lib.tbk_solve_grid(*args, self.stream()))
+            if fast_key is not None and (gaps is None or gaps_h is not None):
+                # keep plan / phase / start / mesh alive with the cached argument tuple
+                store.__dict__["_tbk_sg_fast"] = (fast_key, store._dev, self._ws, args, gaps, gaps_h, (plan, phase, start, mesh))
         if gaps is not None and not reduced:
             # not eligible for the fused reduction: NCCL all-reduce of the per-rank minima
             if gaps_h is not None:
@@ -288,7 +307,7 @@ class B200Engine(object):
             return self.allreduce(gaps, "min")
         if gaps_h is not None:
             self.sync()
-            if not np.all(np.isfinite(gaps_h)):
+            if reduce_ranks is not None and not np.all(np.isfinite(gaps_h)):
                 raise _lib.TbkError("\n\nsolve_on_grid: a peer rank never delivered its gaps (fused reduction timed out)")
             return gaps_h.copy()
         return gaps
@@ -482,6 +501,15 @@ class B200Engine(object):
     def flux_device(self, store, dim_arr, occ, dirs, want_total=True, want_plaq=False, host_result=False,
                     reduce_ranks=None):
         torch = self.torch
+        fast_key = None
+        if reduce_ranks is None and want_total and not want_plaq and host_result:
+            fast_key = (tuple(int(x) for x in occ), tuple(dirs), tuple(store.shape), dim_arr)
+            hit = store.__dict__.get("_tbk_fx_fast")
+            if hit is not None and hit[0] == fast_key and hit[1] is store._dev and hit[2] is self._ws and \
+                    store.state != "host":
+                _lib.check(self.lib.tbk_flux_plane(*hit[3], self.stream()))
+                self.sync()
+                return hit[4].copy(), None
         view, strides, keep = self._view(store, dim_arr, occ)
         mesh = store.shape[:dim_arr]
         rest = [d for d in range(dim_arr) if d not in dirs]
@@ -511,6 +539,8 @@ class B200Engine(object):
                     _lib.check(rc)
         if not launched:
             _lib.check(self.lib.tbk_flux_plane(*args, self.stream()))
+            if fast_key is not None and tot_h is not None and store.state != "host":
+                store.__dict__["_tbk_fx_fast"] = (fast_key, store._dev, self._ws, args, tot_h, (view, keep, offs_d))
         if tot is not None and not reduced:
             # not eligible for the fused reduction: NCCL all-reduce of the per-rank sums
             if tot_h is not None:
@@ -520,7 +550,7 @@ class B200Engine(object):
             return (tot.cpu().numpy() if host_result else tot), plq
         if tot_h is not None:
             self.sync()
-            if not np.all(np.isfinite(tot_h)):
+            if reduce_ranks is not None and not np.all(np.isfinite(tot_h)):
                 raise _lib.TbkError("\n\nberry_flux: a peer rank never delivered its partial sum (fused reduction timed out)")
             return tot_h.copy(), plq
         if host_result and tot is not None:
