@@ -272,7 +272,9 @@ def run_b200(args):
 
     # ---- device-resident step: the two engine calls, results stay on the device
     def step_device():
-        gaps = w._solve_on_grid_device(START_K)
+        # N > 1: the gap minimum over the ranks is posted by the solve kernel and completed inside the flux
+        # kernel, whose own exchange carries both (one exposed NVLink round trip per step instead of two)
+        gaps = w._solve_on_grid_device(START_K, defer_reduce=world > 1)
         flux = w._berry_flux_device(occ)
         return gaps, flux
 
@@ -299,12 +301,14 @@ def run_b200(args):
     barrier()
     for s in range(args.steps):
         flush_l2()
+        eng.peer_barrier()        # N > 1: every timed step starts together on all ranks (device-side, untimed)
         ev0[s].record()
         out = step_device()
         ev1[s].record()
     barrier()
     dev_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
     gaps_d, flux_d = out
+    gaps_dev_host = gaps_d.cpu().numpy() if hasattr(gaps_d, "cpu") else np.asarray(gaps_d)
     flux_val = float(flux_d) if not hasattr(flux_d, "cpu") else float(flux_d.cpu().reshape(-1)[0])
 
     # ---- dominant kernel alone (solve_on_grid's fused assemble+eigh+pbc kernel) for the roofline
@@ -372,7 +376,8 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)",
             "data": "synthetic",
             "config": {"workload": _workload_name(args.workload, world), "norb": model._norb, "nspin": model._nspin,
-                       "occ": occ, "mesh_per_gpu": [ROWS_PER_RANK, COLS], "l2": "256 MiB flush between steps (untimed); events per step, host kept ahead of the device",
+                       "occ": occ, "mesh_per_gpu": [ROWS_PER_RANK, COLS], "l2": "256 MiB flush between steps (untimed); events per step, host kept ahead of the device"
+                             + ("; device-side barrier over the ranks before every timed step (untimed)" if world > 1 else ""),
                        "parallelism": "mesh rows sliced over %d GPU(s)" % world,
                        "halo": (w._halo_mode() if world > 1 else None),
                        "cross_rank_reduction": ("in-kernel over NVLink peer memory" if (world > 1 and eng._peer) else
@@ -381,7 +386,8 @@ def run_b200(args):
                        "kpoints_per_s_solve": kpts_per_step_rank * world / (k_ms * 1e-3),
                        "plaquettes_per_s_flux": kpts_per_step_rank * world / (f_ms * 1e-3)},
             "check": {"chern": chern, "chern_is_integer": bool(abs(chern - round(chern)) < 1e-9),
-                      "e2e_flux_equal": bool(abs(float(flux_h) - flux_val) < 1e-9)},
+                      "e2e_flux_equal": bool(abs(float(flux_h) - flux_val) < 1e-9),
+                      "e2e_gaps_equal": bool(np.array_equal(np.asarray(gaps_h), gaps_dev_host))},
             "e2e": {"value": total_k * args.steps / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / args.steps,
                     "h2d_bytes_per_step": 8 * len(START_K) + 4 * len(mesh),
                     "d2h_bytes_per_step": 8 * (n - 1) + 8,

@@ -153,6 +153,19 @@ typedef struct tbk_peer tbk_peer;
 int tbk_peer_create(int32_t rank, int32_t nranks, tbk_peer** out, void* handle_out);
 int tbk_peer_connect(tbk_peer* peer, const void* handles);
 int tbk_peer_destroy(tbk_peer* peer);
+/* Device-side barrier over the group on `stream` (a one-warp kernel): kernels enqueued after it start
+ * only when every rank has reached the same point of its own stream.  Used by bench.py to start a
+ * timed multi-GPU step together on all ranks (the analogue of torch.distributed.barrier(), but in
+ * stream order and without a host round trip).  No-op for peer == NULL or a single rank. */
+int tbk_peer_barrier(tbk_peer* peer, void* stream);
+/* Deferred reduction.  tbk_peer_defer(peer, 1) makes the NEXT tbk_solve_grid_x only post this rank's
+ * minimal gaps to the peers and return; gaps_dev is completed (minimum over the ranks) by the next
+ * tbk_flux_plane_x issued with the same peer — its exchange carries both, so a solve + flux step exposes
+ * one NVLink round trip instead of two — or by tbk_peer_flush (a one-warp kernel), or implicitly
+ * before any later collective that cannot carry it.  gaps_dev must stay allocated until then.
+ * All ranks must make the same sequence of calls. */
+int tbk_peer_defer(tbk_peer* peer, int32_t on);
+int tbk_peer_flush(tbk_peer* peer, void* stream);
 
 /* Multi-GPU: pack the first local row of a shard ([npoints][nsta_arr][n]
  * complex128) into a contiguous send buffer for the ring shift that closes the
@@ -261,12 +274,32 @@ int64_t tbk_launch_count(void);
  * written straight into pinned host memory. */
 int tbk_stream_sync(void* stream);
 
+/* Prepared calls.  tbk_solve_grid_prepare / tbk_flux_plane_prepare take exactly the arguments of
+ * tbk_solve_grid_x / tbk_flux_plane_x (peer may be NULL) and keep them by value (start_k, mesh and the
+ * view are copied; device buffers, the model and the peer group are referenced and must outlive the
+ * handle).  tbk_prepared_run re-issues that call on `stream`; with sync != 0 it also waits for the
+ * stream, so a repeated host-in / host-out step is one foreign call.  Nothing is launched by *_prepare. */
+typedef struct tbk_prepared tbk_prepared;
+int tbk_solve_grid_prepare(const tbk_model* model, const double* start_k, const int32_t* mesh, int32_t nd,
+                           int32_t row0, int32_t nrows, int32_t wrap0, double* wfs_dev,
+                           const double* pbc_phase_dev, double* gaps_dev, void* ws_dev, size_t ws_bytes,
+                           tbk_peer* peer, tbk_prepared** out);
+int tbk_flux_plane_prepare(const tbk_wf_view* view, const int64_t* slice_off_dev, int64_t nslice, int64_t n0,
+                           int64_t stride0, int64_t n1, int64_t stride1, double* plaq_dev, double* total_dev,
+                           void* ws_dev, size_t ws_bytes, tbk_peer* peer, tbk_prepared** out);
+int tbk_prepared_run(tbk_prepared* call, void* stream, int32_t sync);
+int tbk_prepared_destroy(tbk_prepared* call);
+
 /* Per-stage cycle counters of the blocked eigensolver, collected when the environment has TBK_PROF=1:
  * out8[0..3] = SM cycles spent in tridiagonalisation / bisection / inverse iteration / back-transformation
  * (summed over CTAs), out8[4] = matrices solved, out8[5] = matrices handed to the fallback solver,
  * out8[6] = cycles of the slowest single matrix.
  * Call after synchronising the stream.  Profiling aid, not part of the reference interface. */
 int tbk_debug_profile(uint64_t* out8, int32_t reset);
+/* Profiling aid (TBK_CTA_TRACE=1 in the environment before the first launch): per-CTA timeline of the
+ * last mesh_small_kernel / flux_rows_kernel launch, 4 words per CTA: SM id, begin and end
+ * (%globaltimer, ns), blockIdx.  out: [max_ctas][4].  TBK_ERR_UNSUPPORTED when tracing is off. */
+int tbk_debug_cta_trace(uint64_t* out, int64_t max_ctas, int32_t reset);
 
 /* L2 flush helper for benchmarks: overwrites buf_dev[bytes] (bytes > L2 size). */
 int tbk_flush_l2(void* buf_dev, size_t bytes, void* stream);

@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Per-CTA timeline of the two headline kernels (TBK_CTA_TRACE=1): where the launch ramp, the body and
+the tail of the single wave go.  Usage: TBK_CTA_TRACE=1 python profiles/cta_trace.py [haldane|kane_mele]"""
+import ctypes, json, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ["TBK_CTA_TRACE"] = "1"
+import torch
+import pythtb_b200 as tb
+from pythtb_b200 import _engine, _lib
+from tests import models as M
+
+wl = sys.argv[1] if len(sys.argv) > 1 else "haldane"
+model, occ = (M.haldane(tb, delta=0.0), [0]) if wl == "haldane" else (M.kane_mele(tb, "odd"), [0, 1])
+eng = _engine.get_engine()
+w = tb.wf_array(model, [1025, 1025])
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=eng.device)
+CAP = 4096
+buf = (ctypes.c_uint64 * (CAP * 4))()
+
+
+def grab():
+    _lib.check(eng.lib.tbk_debug_cta_trace(buf, CAP, 1))
+    a = np.ctypeslib.as_array(buf).reshape(CAP, 4).astype(np.int64).copy()
+    return a[a[:, 2] > 0]
+
+
+def summarise(name, a):
+    t0, t1 = a[:, 1].min(), a[:, 2].max()
+    dur = a[:, 2] - a[:, 1]
+    start = a[:, 1] - t0
+    end = a[:, 2] - t0
+    order = np.argsort(-end)
+    per_sm = {}
+    for sm, b, e, _ in a:
+        s = per_sm.setdefault(int(sm), [b, e, 0]); s[0] = min(s[0], b); s[1] = max(s[1], e); s[2] += 1
+    sm_end = np.array([v[1] - t0 for v in per_sm.values()])
+    out = {"kernel": name, "ctas": int(len(a)), "sms": len(per_sm), "span_us": (t1 - t0) / 1e3,
+           "cta_start_us": {"p50": float(np.median(start)) / 1e3, "max": float(start.max()) / 1e3},
+           "cta_dur_us": {"min": float(dur.min()) / 1e3, "p50": float(np.median(dur)) / 1e3,
+                          "p90": float(np.percentile(dur, 90)) / 1e3, "max": float(dur.max()) / 1e3},
+           "cta_end_us": {"p10": float(np.percentile(end, 10)) / 1e3, "p50": float(np.median(end)) / 1e3,
+                          "p90": float(np.percentile(end, 90)) / 1e3, "max": float(end.max()) / 1e3},
+           "sm_end_us": {"min": float(sm_end.min()) / 1e3, "p50": float(np.median(sm_end)) / 1e3, "max": float(sm_end.max()) / 1e3},
+           "ctas_per_sm": sorted(set(v[2] for v in per_sm.values())),
+           "last_ctas(blockIdx,sm,start_us,dur_us)": [(int(a[i, 3]), int(a[i, 0]), round(start[i] / 1e3, 2), round(dur[i] / 1e3, 2)) for i in order[:12]],
+           "first_ctas_to_end(blockIdx,sm,start_us,dur_us)": [(int(a[i, 3]), int(a[i, 0]), round(start[i] / 1e3, 2), round(dur[i] / 1e3, 2)) for i in order[-6:]]}
+    return out
+
+
+res = []
+for rep in range(3):
+    eng.lib.tbk_flush_l2(ctypes.c_void_p(flush.data_ptr()), flush.numel(), eng.stream())
+    w._solve_on_grid_device([-0.5, -0.5])
+    torch.cuda.synchronize()
+    a = grab()
+    eng.lib.tbk_flush_l2(ctypes.c_void_p(flush.data_ptr()), flush.numel(), eng.stream())
+    w._berry_flux_device(occ)
+    torch.cuda.synchronize()
+    b = grab()
+    if rep == 2:
+        res = [summarise("mesh_small_kernel", a), summarise("flux_rows_kernel", b)]
+print(json.dumps(res, indent=1))

@@ -86,6 +86,11 @@ class DeviceStore(object):
         return self._dev
 
 
+class _Prepared(object):
+    """Owner of a ``tbk_prepared`` handle (include/tbk.h): destroyed with the object."""
+    __slots__ = ("handle", "__weakref__")
+
+
 class B200Engine(object):
     def __init__(self):
         self.lib = _lib.load()          # raises if the .so is missing
@@ -99,6 +104,7 @@ class B200Engine(object):
         self._ws = None
         self._host_results = {}
         self._peer = None
+        self._pending_keep = None
         self._dev_index = self.device.index
         self._raw_stream = torch._C._cuda_getCurrentRawStream
 
@@ -126,6 +132,15 @@ class B200Engine(object):
         # cudaStreamSynchronize on torch's current raw stream: one C call
         # (torch.cuda.current_stream(...).synchronize() costs ~10 us of Python on top)
         _lib.check(self.lib.tbk_stream_sync(self.stream()))
+
+    def _prepare(self, fn, args, peer):
+        """Bind the arguments of a solve_grid / flux_plane call in the library (tbk_*_prepare)."""
+        out = ctypes.c_void_p(0)
+        _lib.check(fn(*args, peer, ctypes.byref(out)))
+        h = _Prepared()
+        h.handle = ctypes.c_void_p(out.value)
+        weakref.finalize(h, self.lib.tbk_prepared_destroy, h.handle)
+        return h
 
     def workspace(self, nbytes):
         nbytes = int(nbytes)
@@ -235,28 +250,33 @@ class B200Engine(object):
         return val
 
     def solve_grid(self, model, store, mesh_arr, start_k, row0=0, nrows=None, wrap0=1, want_gaps=True,
-                   host_result=False, reduce_ranks=None):
+                   host_result=False, reduce_ranks=None, defer_reduce=False):
         """wf_array.solve_on_grid + impose_pbc (pythtb.py:2421-2532) into ``store``
         (local rows [row0, row0+nrows] of mesh axis 0); returns the minimal gaps
         over the rows solved here as a device tensor — or, with ``host_result``, as a
         host array (the call then synchronises the stream) — or None.
         wrap0: 1 = write the periodic image of row 0 (single shard), 0 = leave the
-        closing row to a halo exchange, 2 = compute the closing row in this launch."""
+        closing row to a halo exchange, 2 = compute the closing row in this launch.
+        defer_reduce (sharded, device result only): the kernel only posts this rank's gaps to
+        the peers; the returned tensor holds the minimum over the ranks once the next
+        flux_total(..., reduce_ranks=...) kernel — whose exchange then carries both — or
+        peer_flush() has run (include/tbk.h: tbk_peer_defer)."""
         torch = self.torch
         # ---- fast path: the same call as last time on this store (a parameter sweep, the bench loop):
         # reuse the marshalled arguments as long as every buffer they point to is still the live one
         fast_key = None
-        if reduce_ranks is None and (host_result or not want_gaps):
+        if host_result or not want_gaps:
             fast_key = (id(model._plan()), tuple(int(x) for x in mesh_arr), tuple(float(x) for x in start_k), row0, nrows,
-                        wrap0, want_gaps, host_result)
+                        wrap0, want_gaps, host_result, reduce_ranks)
             hit = store.__dict__.get("_tbk_sg_fast")
             if hit is not None and hit[0] == fast_key and hit[1] is store._dev and hit[2] is self._ws and \
                     store.state != "host":
                 store.state = "device"
-                _lib.check(self.lib.tbk_solve_grid(*hit[3], self.stream()))
                 gaps_h = hit[5]
+                _lib.check(self.lib.tbk_prepared_run(hit[3].handle, self.stream(), 1 if gaps_h is not None else 0))
                 if gaps_h is not None:
-                    self.sync()
+                    if reduce_ranks is not None and not np.all(np.isfinite(gaps_h)):
+                        raise _lib.TbkError("\n\nsolve_on_grid: a peer rank never delivered its gaps (fused reduction timed out)")
                     return gaps_h.copy()
                 return None
         handle, plan = self.model_handle(model)
@@ -289,16 +309,29 @@ class B200Engine(object):
             # minimum over the ranks inside the kernel, through NVLink peer memory (csrc/tbk_peer.cuh)
             peer = self.peer_group(*reduce_ranks)
             if peer is not None:
+                deferred = bool(defer_reduce and gaps_h is None)
+                if deferred:
+                    _lib.check(self.lib.tbk_peer_defer(peer, 1))
                 rc = self.lib.tbk_solve_grid_x(*args, peer, self.stream())
+                if deferred:
+                    _lib.check(self.lib.tbk_peer_defer(peer, 0))
                 if rc == 0:
                     reduced = launched = True
+                    if deferred:
+                        self._pending_keep = gaps          # alive until the kernel that completes it is enqueued
+                    if fast_key is not None and gaps_h is not None:
+                        store.__dict__["_tbk_sg_fast"] = (fast_key, store._dev, self._ws,
+                                                          self._prepare(self.lib.tbk_solve_grid_prepare, args, peer),
+                                                          gaps, gaps_h, (plan, phase), peer)
                 elif rc != _lib.ERR_UNSUPPORTED:
                     _lib.check(rc)
         if not launched:
             _lib.check(self.lib.tbk_solve_grid(*args, self.stream()))
-            if fast_key is not None and (gaps is None or gaps_h is not None):
+            if fast_key is not None and reduce_ranks is None and (gaps is None or gaps_h is not None):
                 # keep plan / phase / start / mesh alive with the cached argument tuple
-                store.__dict__["_tbk_sg_fast"] = (fast_key, store._dev, self._ws, args, gaps, gaps_h, (plan, phase, start, mesh))
+                store.__dict__["_tbk_sg_fast"] = (fast_key, store._dev, self._ws,
+                                                  self._prepare(self.lib.tbk_solve_grid_prepare, args, None),
+                                                  gaps, gaps_h, (plan, phase), None)
         if gaps is not None and not reduced:
             # not eligible for the fused reduction: NCCL all-reduce of the per-rank minima
             if gaps_h is not None:
@@ -339,6 +372,18 @@ class B200Engine(object):
         dist.barrier()                      # every mailbox is mapped everywhere before the first collective
         self._peer = peer
         return peer
+
+    def peer_flush(self):
+        """Finish a deferred cross-rank reduction now (tbk_peer_flush); no-op when none is pending."""
+        if self._peer:
+            _lib.check(self.lib.tbk_peer_flush(self._peer, self.stream()))
+        self._pending_keep = None
+
+    def peer_barrier(self):
+        """Device-side barrier over the peer group, in stream order (tbk_peer_barrier): the kernels
+        enqueued after it start together on every rank.  No-op without a peer group."""
+        if self._peer:
+            _lib.check(self.lib.tbk_peer_barrier(self._peer, self.stream()))
 
     def halo_ring_shift(self, store, dim_arr, phase, rank, nranks):
         """Close every rank's slab with the first row of the next rank: one
@@ -502,13 +547,14 @@ class B200Engine(object):
                     reduce_ranks=None):
         torch = self.torch
         fast_key = None
-        if reduce_ranks is None and want_total and not want_plaq and host_result:
-            fast_key = (tuple(int(x) for x in occ), tuple(dirs), tuple(store.shape), dim_arr)
+        if want_total and not want_plaq and host_result:
+            fast_key = (tuple(int(x) for x in occ), tuple(dirs), tuple(store.shape), dim_arr, reduce_ranks)
             hit = store.__dict__.get("_tbk_fx_fast")
             if hit is not None and hit[0] == fast_key and hit[1] is store._dev and hit[2] is self._ws and \
                     store.state != "host":
-                _lib.check(self.lib.tbk_flux_plane(*hit[3], self.stream()))
-                self.sync()
+                _lib.check(self.lib.tbk_prepared_run(hit[3].handle, self.stream(), 1))
+                if reduce_ranks is not None and not np.all(np.isfinite(hit[4])):
+                    raise _lib.TbkError("\n\nberry_flux: a peer rank never delivered its partial sum (fused reduction timed out)")
                 return hit[4].copy(), None
         view, strides, keep = self._view(store, dim_arr, occ)
         mesh = store.shape[:dim_arr]
@@ -535,12 +581,19 @@ class B200Engine(object):
                 rc = self.lib.tbk_flux_plane_x(*args, peer, self.stream())
                 if rc == 0:
                     reduced = launched = True
+                    self._pending_keep = None              # a deferred gap reduction was completed by this kernel
+                    if fast_key is not None and tot_h is not None and store.state != "host":
+                        store.__dict__["_tbk_fx_fast"] = (fast_key, store._dev, self._ws,
+                                                          self._prepare(self.lib.tbk_flux_plane_prepare, args, peer),
+                                                          tot_h, (view, keep, offs_d), peer)
                 elif rc != _lib.ERR_UNSUPPORTED:
                     _lib.check(rc)
         if not launched:
             _lib.check(self.lib.tbk_flux_plane(*args, self.stream()))
-            if fast_key is not None and tot_h is not None and store.state != "host":
-                store.__dict__["_tbk_fx_fast"] = (fast_key, store._dev, self._ws, args, tot_h, (view, keep, offs_d))
+            if fast_key is not None and reduce_ranks is None and tot_h is not None and store.state != "host":
+                store.__dict__["_tbk_fx_fast"] = (fast_key, store._dev, self._ws,
+                                                  self._prepare(self.lib.tbk_flux_plane_prepare, args, None),
+                                                  tot_h, (view, keep, offs_d), None)
         if tot is not None and not reduced:
             # not eligible for the fused reduction: NCCL all-reduce of the per-rank sums
             if tot_h is not None:

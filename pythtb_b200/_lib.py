@@ -20,7 +20,8 @@ SYMBOLS = [
     "tbk_impose_boundary", "tbk_flux_workspace", "tbk_flux_plane", "tbk_berry_workspace",
     "tbk_berry_strings", "tbk_position_matrix", "tbk_position_hwf_workspace", "tbk_position_hwf",
     "tbk_flush_l2", "tbk_halo_pack", "tbk_last_kernel", "tbk_launch_count", "tbk_peer_create", "tbk_peer_connect",
-    "tbk_peer_destroy", "tbk_solve_grid_x", "tbk_flux_plane_x", "tbk_stream_sync", "tbk_debug_profile", "tbk_wilson_products", "tbk_wilson_workspace", "tbk_wilson_phases",
+    "tbk_peer_destroy", "tbk_solve_grid_x", "tbk_flux_plane_x", "tbk_stream_sync", "tbk_debug_profile", "tbk_debug_cta_trace", "tbk_solve_grid_prepare", "tbk_flux_plane_prepare", "tbk_prepared_run", "tbk_prepared_destroy",
+    "tbk_peer_barrier", "tbk_peer_defer", "tbk_peer_flush", "tbk_wilson_products", "tbk_wilson_workspace", "tbk_wilson_phases",
 ]
 
 
@@ -85,6 +86,14 @@ def load():
         "tbk_wilson_workspace": (SZ, [I32, I64, I64]),
         "tbk_wilson_phases": (ctypes.c_int, [V, I64, I64, I32, V, V, SZ, V]),
         "tbk_debug_profile": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64), I32]),
+        "tbk_debug_cta_trace": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64), I64, I32]),
+        "tbk_peer_barrier": (ctypes.c_int, [c_void_p, c_void_p]),
+        "tbk_solve_grid_prepare": (ctypes.c_int, [V, c_double_p, c_int32_p, I32, I32, I32, I32, V, V, V, V, SZ, V, ctypes.POINTER(V)]),
+        "tbk_flux_plane_prepare": (ctypes.c_int, [ctypes.POINTER(WfView), V, I64, I64, I64, I64, I64, V, V, V, SZ, V, ctypes.POINTER(V)]),
+        "tbk_prepared_run": (ctypes.c_int, [V, V, I32]),
+        "tbk_prepared_destroy": (ctypes.c_int, [V]),
+        "tbk_peer_defer": (ctypes.c_int, [c_void_p, c_int32]),
+        "tbk_peer_flush": (ctypes.c_int, [c_void_p, c_void_p]),
         "tbk_halo_pack": (ctypes.c_int, [V, V, I64, I32, I32, V, V]),
         "tbk_peer_create": (ctypes.c_int, [I32, I32, ctypes.POINTER(V), V]),
         "tbk_peer_connect": (ctypes.c_int, [V, V]),

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <atomic>
 #include <mutex>
+#include <functional>
 #include <vector>
 #include "tbk_internal.cuh"
 
@@ -34,6 +35,19 @@ unsigned* take_ticket() {
   return g_tickets[dev] + slot;
 }
 
+unsigned long long* cta_trace_buffer() {
+  static int on = -1;
+  static unsigned long long* buf = nullptr;
+  if (on < 0) { const char* e = getenv("TBK_CTA_TRACE"); on = (e && atoi(e) == 1) ? 1 : 0; }
+  if (!on) return nullptr;
+  if (!buf) {
+    const size_t bytes = (size_t)kCtaTraceCap * 4 * sizeof(unsigned long long);
+    if (cudaMalloc(&buf, bytes) != cudaSuccess) return nullptr;
+    cudaMemset(buf, 0, bytes);
+  }
+  return buf;
+}
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -44,6 +58,36 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
   return TBK_ERR_CUDA;
+}
+
+// device-side barrier over the peer group (one warp): an all-reduce of a dummy value
+__global__ void peer_barrier_kernel(const __grid_constant__ PeerView pv, double* scratch) {
+  __shared__ double s_v[1];
+  __shared__ int s_fail;
+  if (threadIdx.x == 0) s_v[0] = 1.0;
+  __syncthreads();
+  peer_allreduce(pv, s_v, 1, 0, scratch, &s_fail);
+}
+
+// finishes a deferred collective nobody else picked up (one warp)
+__global__ void peer_collect_kernel(const __grid_constant__ PeerView pv) {
+  __shared__ int s_fail;
+  if (threadIdx.x == 0) s_fail = 0;
+  __syncthreads();
+  peer_collect(pv, pv.pend.epoch, pv.pend.nv, pv.pend.op, pv.pend.out, &s_fail);
+}
+
+int peer_flush(tbk_peer* p, cudaStream_t st) {
+  if (!p || !p->connected || p->nranks < 2 || !p->pending.epoch) return TBK_OK;
+  PeerView v;
+  memset(&v, 0, sizeof(v));
+  v.rank = p->rank; v.nranks = p->nranks;
+  for (int r = 0; r < p->nranks; ++r) v.box[r] = p->box[r];
+  v.pend = p->pending;
+  p->pending.epoch = 0;
+  peer_collect_kernel<<<1, 64, 0, st>>>(v);
+  TBK_LAUNCH_CHECK("peer_collect_kernel");
+  return TBK_OK;
 }
 
 __global__ void flush_l2_kernel(double4* __restrict__ buf, size_t n, double v) {
@@ -178,9 +222,9 @@ int tbk_peer_create(int32_t rank, int32_t nranks, tbk_peer** out, void* handle_o
   p->rank = rank; p->nranks = nranks;
   TBK_CUDA(cudaGetDevice(&p->device));
   void* mem = nullptr;
-  cudaError_t e = cudaMalloc(&mem, kPeerMailboxBytes);
+  cudaError_t e = cudaMalloc(&mem, kPeerMailboxBytes + kPeerScratchBytes);
   if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(mailbox)"); }
-  e = cudaMemset(mem, 0, kPeerMailboxBytes);
+  e = cudaMemset(mem, 0, kPeerMailboxBytes + kPeerScratchBytes);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   cudaIpcMemHandle_t h;
   if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, mem);
@@ -212,6 +256,79 @@ int tbk_peer_destroy(tbk_peer* p) {
     if (r == p->rank) cudaFree(p->box[r]);
     else cudaIpcCloseMemHandle(p->box[r]);
   }
+  delete p;
+  return TBK_OK;
+}
+
+int tbk_peer_defer(tbk_peer* p, int32_t on) {
+  if (p) p->defer_next = on != 0;
+  return TBK_OK;
+}
+
+int tbk_peer_flush(tbk_peer* p, void* stream) { return peer_flush(p, (cudaStream_t)stream); }
+
+int tbk_peer_barrier(tbk_peer* p, void* stream) {
+  if (!p || !p->connected || p->nranks < 2) return TBK_OK;
+  if (int rc = peer_flush(p, (cudaStream_t)stream)) return rc;
+  const PeerView pv = peer_next(p);
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pv, (double*)((char*)p->box[p->rank] + kPeerMailboxBytes));
+  TBK_LAUNCH_CHECK("peer_barrier_kernel");
+  return TBK_OK;
+}
+
+int tbk_debug_cta_trace(uint64_t* out, int64_t max_ctas, int32_t reset) {
+  if (!out || max_ctas < 0) { set_error("tbk_debug_cta_trace: bad argument"); return TBK_ERR_ARG; }
+  unsigned long long* buf = cta_trace_buffer();
+  if (!buf) { set_error("tbk_debug_cta_trace: tracing is off (set TBK_CTA_TRACE=1 before the first launch)"); return TBK_ERR_UNSUPPORTED; }
+  const size_t n = (size_t)(max_ctas < kCtaTraceCap ? max_ctas : kCtaTraceCap) * 4 * sizeof(unsigned long long);
+  TBK_CUDA(cudaDeviceSynchronize());
+  TBK_CUDA(cudaMemcpy(out, buf, n, cudaMemcpyDeviceToHost));
+  if (reset) TBK_CUDA(cudaMemset(buf, 0, (size_t)kCtaTraceCap * 4 * sizeof(unsigned long long)));
+  return TBK_OK;
+}
+
+// ---- prepared calls: the arguments of a repeated solve_grid / flux_plane call, kept by value, so that
+// re-issuing it costs the host one 3-argument call (a parameter sweep or a timing loop re-runs the same
+// launch thousands of times and the kernels last ~20 us: the argument marshalling of the host language
+// is then a visible share of the step).
+int tbk_solve_grid_prepare(const tbk_model* m, const double* start_k, const int32_t* mesh, int32_t nd, int32_t row0,
+                           int32_t nrows, int32_t wrap0, double* wfs_dev, const double* pbc_phase_dev, double* gaps_dev,
+                           void* ws_dev, size_t ws_bytes, tbk_peer* peer, tbk_prepared** out) {
+  if (!m || !start_k || !mesh || !out || nd < 1 || nd > TBK_MAX_DIM) { set_error("tbk_solve_grid_prepare: bad argument"); return TBK_ERR_ARG; }
+  std::vector<double> sk(start_k, start_k + nd);
+  std::vector<int32_t> ms(mesh, mesh + nd);
+  tbk_prepared* p = new tbk_prepared();
+  p->run = [=](void* stream) {
+    return tbk_solve_grid_x(m, sk.data(), ms.data(), nd, row0, nrows, wrap0, wfs_dev, pbc_phase_dev, gaps_dev, ws_dev,
+                            ws_bytes, peer, stream);
+  };
+  *out = p;
+  return TBK_OK;
+}
+
+int tbk_flux_plane_prepare(const tbk_wf_view* view, const int64_t* slice_off_dev, int64_t nslice, int64_t n0,
+                           int64_t stride0, int64_t n1, int64_t stride1, double* plaq_dev, double* total_dev,
+                           void* ws_dev, size_t ws_bytes, tbk_peer* peer, tbk_prepared** out) {
+  if (!view || !out) { set_error("tbk_flux_plane_prepare: bad argument"); return TBK_ERR_ARG; }
+  const tbk_wf_view v = *view;
+  tbk_prepared* p = new tbk_prepared();
+  p->run = [=](void* stream) {
+    return tbk_flux_plane_x(&v, slice_off_dev, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, ws_dev, ws_bytes,
+                            peer, stream);
+  };
+  *out = p;
+  return TBK_OK;
+}
+
+int tbk_prepared_run(tbk_prepared* p, void* stream, int32_t sync) {
+  if (!p || !p->run) { set_error("tbk_prepared_run: null handle"); return TBK_ERR_ARG; }
+  const int rc = p->run(stream);
+  if (rc != TBK_OK) return rc;
+  if (sync) TBK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return TBK_OK;
+}
+
+int tbk_prepared_destroy(tbk_prepared* p) {
   delete p;
   return TBK_OK;
 }

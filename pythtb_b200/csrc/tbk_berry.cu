@@ -193,10 +193,11 @@ __global__ void __launch_bounds__(kFluxThreads)
 flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0, long long stride0, long long n1,
                  long long stride1, FluxTiling tl, long long nslice, double* __restrict__ plaq,
                  double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ total,
-                 const __grid_constant__ PeerView peer) {
+                 const __grid_constant__ PeerView peer, unsigned long long* __restrict__ trace) {
   __shared__ double s_red[kFluxThreads / 32];
   __shared__ double s_fin[kPeerMaxVals];
   __shared__ int s_last;
+  const unsigned long long t_begin = cta_trace_begin(trace);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int occ[NOCC];
 #pragma unroll
@@ -287,12 +288,12 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
       }
     }
   }
-  if (!partial) return;
+  if (!partial) { cta_trace_end(trace, t_begin); return; }
   __threadfence();
   __syncthreads();
   if (tid == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
   __syncthreads();
-  if (!s_last) return;
+  if (!s_last) { cta_trace_end(trace, t_begin); return; }
   __threadfence();
   const long long per = tl.nrb * tl.nbx;
   for (long long s = 0; s < nslice; ++s) {
@@ -314,6 +315,7 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
     __syncthreads();
     peer_allreduce(peer, s_fin, (int)nslice, 0, total, &s_last);
   }
+  cta_trace_end(trace, t_begin);
 }
 
 template <int NOCC, int N>
@@ -322,6 +324,10 @@ static int launch_flux_rows(const WfView& v, const long long* off, long long nsl
                             cudaStream_t st) {
   static int occ_plaq = 0, occ_sum = 0;                   // resident CTAs per SM of the two variants
   if (occ_plaq == 0) {
+    if (const char* e = getenv("TBK_L2_FETCH")) {         // experiment knob: DRAM->L2 fetch granularity (32/64/128 B)
+      const int g = atoi(e);
+      if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
+    }
     int a = 0, b = 0;
     TBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, flux_rows_kernel<NOCC, N, true>, kFluxThreads, 0));
     TBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, flux_rows_kernel<NOCC, N, false>, kFluxThreads, 0));
@@ -336,13 +342,14 @@ static int launch_flux_rows(const WfView& v, const long long* off, long long nsl
     if (!ticket) { set_error("tbk_flux_plane: cannot allocate the reduction tickets"); return TBK_ERR_CUDA; }
   }
   const int grid = (int)(tl.ntiles < resident ? tl.ntiles : resident);
-  const PeerView pview = total ? peer_next(peer) : peer_next(nullptr);
+  PeerView pview = total ? peer_next(peer) : peer_next(nullptr);
+  if (total) peer_attach_pending(peer, pview);             // a deferred gap reduction rides on this kernel's exchange
   if (plaq)
     flux_rows_kernel<NOCC, N, true><<<grid, kFluxThreads, 0, st>>>(v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
-                                                                  total ? partial : nullptr, ticket, total, pview);
+                                                                  total ? partial : nullptr, ticket, total, pview, cta_trace_buffer());
   else
     flux_rows_kernel<NOCC, N, false><<<grid, kFluxThreads, 0, st>>>(v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
-                                                                   partial, ticket, total, pview);
+                                                                   partial, ticket, total, pview, cta_trace_buffer());
   TBK_LAUNCH_CHECK("flux_rows_kernel");
   return TBK_OK;
 }
@@ -597,7 +604,8 @@ static int launch_flux_ring(const WfView& v, const long long* off, long long nsl
     if (!ticket) { set_error("tbk_flux_plane: cannot allocate the reduction tickets"); return TBK_ERR_CUDA; }
   }
   const int grid = (int)(tl.ntiles < resident ? tl.ntiles : resident);
-  const PeerView pview = total ? peer_next(peer) : peer_next(nullptr);
+  PeerView pview = total ? peer_next(peer) : peer_next(nullptr);
+  if (total) peer_attach_pending(peer, pview);
   if (plaq)
     kern_p<<<grid, kRingThreads, dyn, st>>>(v, off, n0, stride0, n1, tl, nslice, plaq, total ? partial : nullptr, ticket,
                                             total, pview);

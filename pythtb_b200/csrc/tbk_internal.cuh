@@ -3,6 +3,7 @@
 // eigensolver / LU code, and small launch helpers.
 #pragma once
 #include <cuda_runtime.h>
+#include <functional>
 #include <stdio.h>
 #include <string.h>
 #include "../../include/tbk.h"
@@ -31,6 +32,30 @@ int cuda_fail(cudaError_t e, const char* what);
     if (e__ != cudaSuccess) return cuda_fail(e__, name);     \
     tbk::count_launch();                                     \
   } while (0)
+
+// Optional per-CTA timeline of the two headline kernels (TBK_CTA_TRACE=1, profiling only): a device
+// buffer of (smid, begin ns, end ns, blockIdx) per CTA of the last traced launch; tbk_debug_cta_trace
+// copies it out.  nullptr (one uniform predicate in the kernel) unless enabled.
+constexpr int kCtaTraceCap = 4096;
+unsigned long long* cta_trace_buffer();
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned long long cta_trace_begin(const unsigned long long* trace) {
+  return (trace && threadIdx.x == 0) ? global_ns() : 0ull;
+}
+__device__ __forceinline__ void cta_trace_end(unsigned long long* trace, unsigned long long t0) {
+  if (trace && threadIdx.x == 0 && blockIdx.x < kCtaTraceCap) {
+    unsigned sm;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    unsigned long long* p = trace + 4 * (size_t)blockIdx.x;
+    p[0] = sm; p[1] = t0; p[2] = global_ns(); p[3] = blockIdx.x;
+  }
+}
+#endif
 
 constexpr int kNumSM = 148;           // B200
 constexpr int kMaxSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
@@ -125,12 +150,19 @@ struct tbk_model {
   int max_terms_per_phase;
 };
 
+// The opaque prepared call of tbk.h: the bound arguments of one entry point
+struct tbk_prepared {
+  std::function<int(void*)> run;     // re-issues the call on the given stream
+};
+
 // The opaque peer group of tbk.h: this rank's mailbox and the IPC mappings of the others
 struct tbk_peer {
   int rank, nranks, device;
   unsigned long long epoch;          // advanced by every collective issued through this group
   double* box[tbk::kPeerMaxRanks];   // box[rank] is the local allocation
   bool connected;
+  bool defer_next;                   // tbk_peer_defer: the next tbk_solve_grid_x only posts its reduction
+  tbk::PeerPending pending;          // that posted collective, until a later kernel (or tbk_peer_flush) finishes it
 };
 
 namespace tbk {
@@ -144,4 +176,20 @@ inline PeerView peer_next(tbk_peer* p) {
   }
   return v;
 }
+// ... of which the kernel only posts its contribution: {nv, op, out} stay pending on the host handle
+inline PeerView peer_next_deferred(tbk_peer* p, int nv, int op, double* out) {
+  PeerView v = peer_next(p);
+  if (v.nranks > 1) {
+    v.defer = 1;
+    p->pending.epoch = v.epoch; p->pending.nv = nv; p->pending.op = op; p->pending.out = out;
+  }
+  if (p) p->defer_next = false;
+  return v;
+}
+// hand a pending collective to a view whose kernel finishes it (peer_allreduce does)
+inline void peer_attach_pending(tbk_peer* p, PeerView& v) {
+  if (p && v.nranks > 1 && p->pending.epoch) { v.pend = p->pending; p->pending.epoch = 0; }
+}
+// finish a pending collective with a one-warp kernel (tbk_api.cu); no-op when nothing is pending
+int peer_flush(tbk_peer* p, cudaStream_t st);
 }  // namespace tbk

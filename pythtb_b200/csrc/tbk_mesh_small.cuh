@@ -109,6 +109,17 @@ __device__ __noinline__ void mesh_store_special(EigRows<N>& e, const OutSpec& ou
   if (zero_mask) mesh_store_images<N>(e, out, at, zero_mask);
 }
 
+// periodic image of one point along one axis: every component times that axis' pbc phase, 256-bit stores
+template <int N>
+__device__ __forceinline__ void mesh_store_image(cplx* dst, const cplx (&w)[N][N], const cplx* ph) {
+  cplx im[N][N];
+#pragma unroll
+  for (int b = 0; b < N; ++b)
+#pragma unroll
+    for (int o = 0; o < N; ++o) im[b][o] = mul_fixed(w[b][o], ph[o]);
+  mesh_store_point<N, true>(dst, im);
+}
+
 struct MeshRow {                                    // per mesh row (outer index), shared memory
   long long base;                                   // storage offset of the row, complex elements
   int flags;                                        // bits 0..3 zero_mask, bit 8 closing row
@@ -128,7 +139,7 @@ __global__ void __launch_bounds__(kMeshThreads, MINB)
 mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__ KSrc ks,
                   const __grid_constant__ OutSpec out, const __grid_constant__ MeshTiling tl, int gauge,
                   double* __restrict__ gap_partial, unsigned* __restrict__ ticket, double* __restrict__ gaps_out,
-                  const __grid_constant__ PeerView peer) {
+                  const __grid_constant__ PeerView peer, unsigned long long* __restrict__ trace) {
   constexpr int NP = N * (N + 1) / 2;
   constexpr int NG = N - 1;                         // relative gauge factors of states 1..N-1
   constexpr int NQ = NPH + NG;
@@ -136,9 +147,15 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
   __shared__ MeshRow s_row[kMeshMaxRows];
   __shared__ double s_red[kMeshThreads / 32][N];
   __shared__ cplx s_pbc0[N];                        // pbc phase of axis 0 (closing rows of a shard)
+  __shared__ cplx s_pbc[TBK_MAX_DIM][N];            // pbc phases of every wrapped axis (periodic images)
   __shared__ int s_last;
   __shared__ double s_fin[N];
+  const unsigned long long t_begin = cta_trace_begin(trace);
   if (threadIdx.x < N) s_pbc0[threadIdx.x] = tl.closing_g >= 0 ? out.pbc_phase[threadIdx.x] : mk(1.0, 0.0);
+  if (threadIdx.x < out.nd * N) {
+    const int d = threadIdx.x / N;
+    s_pbc[d][threadIdx.x - d * N] = out.wrap[d] ? out.pbc_phase[threadIdx.x] : mk(1.0, 0.0);
+  }
   const int nd = out.nd;
   const int last = nd - 1;
   const int nph = ds.nph;   // phases p >= nph are skipped (uniform predicate)
@@ -280,43 +297,60 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
             }
           }
         }
-        // ---- store (+ periodic images / closing-row factor on the cold path)
+        // ---- store.  Periodic images (pythtb.py:2729-2747) and the closing-row factor of a shard are
+        // applied INLINE with 256-bit stores: a row at index 0 of one wrapped outer axis writes its image
+        // row (uniform branch), the lane that owns column 0 writes the image along the fastest axis.  The
+        // out-of-line path (local-memory copy + a loop over axis subsets) is left to 1-D meshes and to the
+        // edges of 3-D/4-D meshes where two outer axes wrap at once: taking it for every point of row 0 and
+        // a read-back pass for column 0 made the CTAs that own them the tail of the single wave.
 #pragma unroll
         for (int u = 0; u < RPI; ++u) {
           if (u > 0 && r0 + u >= nrows) break;
           const MeshRow mr = s_row[rr[u]];
-          // column 0 of an ordinary row: its image along the fastest axis is written by the whole CTA below
-          const int special = last == 0 ? special_j : (mr.flags ? (mr.flags | zlast) : 0);
-          if (special == 0) {
-            mesh_store_point<N, true>(dst_col + mr.base, w[u]);
+          const int zm = mr.flags & 15;
+          if (last == 0 || (zm & (zm - 1))) {
+            const int special = last == 0 ? special_j : (mr.flags | zlast);
+            if (special == 0) {
+              mesh_store_point<N, true>(dst_col + mr.base, w[u]);
+            } else {
+              EigRows<N> eg;
+#pragma unroll
+              for (int b = 0; b < N; ++b)
+#pragma unroll
+                for (int o = 0; o < N; ++o) eg.w[b][o] = w[u][b][o];
+              mesh_store_special<N>(eg, out, s_pbc0, mr.base + (long long)j * gs_last, special & 15, special & 256);
+            }
           } else {
-            EigRows<N> eg;
+            if (mr.flags & 256) {                   // closing row of a shard: the axis-0 image of global row 0
 #pragma unroll
-            for (int b = 0; b < N; ++b)
+              for (int o = 0; o < N; ++o) {
+                const cplx ph = s_pbc0[o];
 #pragma unroll
-              for (int o = 0; o < N; ++o) eg.w[b][o] = w[u][b][o];
-            mesh_store_special<N>(eg, out, s_pbc0, mr.base + (long long)j * gs_last, special & 15, special & 256);
+                for (int b = 0; b < N; ++b) w[u][b][o] = mul_fixed(w[u][b][o], ph);
+              }
+            }
+            cplx* const dst = dst_col + mr.base;
+            mesh_store_point<N, true>(dst, w[u]);
+            const long long img_last = (long long)(out.full[last] - 1) * gs_last;
+            if (zlast) mesh_store_image<N>(dst + img_last, w[u], s_pbc[last]);
+            if (zm) {                               // image row along the one wrapped outer axis at index 0
+              const int d = __ffs(zm) - 1;
+              cplx wi[N][N];
+#pragma unroll
+              for (int b = 0; b < N; ++b)
+#pragma unroll
+                for (int o = 0; o < N; ++o) wi[b][o] = mul_fixed(w[u][b][o], s_pbc[d][o]);
+              cplx* const dsti = dst + (long long)(out.full[d] - 1) * out.gstride[d];
+              mesh_store_point<N, true>(dsti, wi);
+              if (zlast) mesh_store_image<N>(dsti + img_last, wi, s_pbc[last]);
+            }
           }
-        }
-      }
-      // ---- periodic image of column 0 along the fastest axis (pythtb.py:2729) for the ordinary rows of
-      // this chunk: one element per thread, so that no single warp pays for it (a per-row cold call in
-      // the lane that owns column 0 made the column-block-0 CTAs the tail of the wave)
-      if (bx == 0 && last > 0 && out.wrap[last]) {
-        __syncthreads();                            // the column-0 stores of this chunk are visible CTA-wide
-        const long long img = (long long)(out.full[last] - 1) * gs_last;
-        for (int t = tid; t < nrows * N * N; t += kMeshThreads) {
-          const int r = t / (N * N), e = t - r * (N * N);
-          if (s_row[r].flags != 0) continue;        // rows with their own images went through the cold path
-          cplx* src = out.evec + s_row[r].base + e;
-          const double2 t2 = __ldcg(reinterpret_cast<const double2*>(src));
-          src[img] = mul_fixed(mk(t2.x, t2.y), out.pbc_phase[last * N + (e % N)]);
         }
       }
     }
   }
   // ---- minimal direct gaps (pythtb.py:2484, 2529-2530): CTA partial, last CTA finishes
-  if (gaps_out == nullptr) return;
+  if (gaps_out == nullptr) { cta_trace_end(trace, t_begin); return; }
 #pragma unroll
   for (int b = 0; b < N - 1; ++b) {
     double g = gmin[b];
@@ -334,7 +368,7 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
   __syncthreads();
   if (tid == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
   __syncthreads();
-  if (!s_last) return;
+  if (!s_last) { cta_trace_end(trace, t_begin); return; }
   __threadfence();
 #pragma unroll
   for (int b = 0; b < N - 1; ++b) {
@@ -356,6 +390,7 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
     __syncthreads();
     peer_allreduce(peer, s_fin, N - 1, 1, gaps_out, &s_last);
   }
+  cta_trace_end(trace, t_begin);
 }
 
 }  // namespace tbk

@@ -2,15 +2,22 @@
 // produced them, over NVLink peer memory (no NCCL launch, no extra kernel).
 //
 // Every rank owns a small "mailbox" in its HBM, mapped into all peers through CUDA IPC
-// (tbk_peer_create / tbk_peer_connect).  The CTA that finishes a rank's local reduction
-//   1. stores its vector into slot [parity][rank] of EVERY rank's mailbox (peer stores over NVLink),
-//      then the call's epoch into the slot's flag word with st.release.sys;
-//   2. spins (ld.acquire.sys) on the nranks flags of its OWN mailbox until all carry this epoch;
+// (tbk_peer_create / tbk_peer_connect).  The protocol is the flag-in-data ("LL") scheme: a double
+// travels as two 8-byte words, each carrying 32 bits of payload and the 32-bit tag of the call's
+// epoch, and an aligned 8-byte store is a single NVLink transaction — so a word is either absent
+// (old tag) or complete, and no release fence / separate flag store is needed (the first version
+// paid a system-scope release per contribution).  The CTA that finishes a rank's local reduction
+//   1. stores its words into slot [parity][rank] of EVERY rank's mailbox (one thread per word);
+//   2. polls the words of its OWN mailbox until each carries this epoch's tag;
 //   3. combines the nranks vectors in rank order (deterministic) and writes the result.
-// Two parities make slot reuse safe: a rank can only be one collective ahead of the slowest rank,
-// because finishing collective e requires everybody's contribution to e.  All ranks must issue the
-// same sequence of collectives (as with NCCL).  A rank that waits longer than ~4 s gives up and
-// returns NaN instead of hanging the GPU.
+// A collective can also be DEFERRED: the producing kernel only posts (step 1) and returns, and the
+// next collective kernel on the stream finishes it (steps 2-3 for the pending epoch, after posting its
+// own words, so the two waits overlap) — one exposed NVLink round trip per step instead of two.
+// Slots are reused every kPeerDepth = 4 epochs: a rank posts epoch e+4 only after it completed e+3,
+// which needs every rank's e+3 words, which a rank posts only after it has (in program order) read
+// everything up to e+1 and collected a pending e.  All ranks must issue the same sequence of
+// collectives (as with NCCL).  A rank that waits longer than ~4 s gives up and returns NaN instead
+// of hanging the GPU.
 #pragma once
 #include "tbk_common.cuh"
 
@@ -18,62 +25,96 @@ namespace tbk {
 
 constexpr int kPeerMaxRanks = 8;
 constexpr int kPeerMaxVals = 16;                     // doubles per contribution
-constexpr int kPeerSlot = 1 + kPeerMaxVals;          // flag + values, in doubles
-constexpr size_t kPeerMailboxBytes = (size_t)2 * kPeerMaxRanks * kPeerSlot * sizeof(double);
+constexpr int kPeerSlotWords = 2 * kPeerMaxVals;     // 8-byte words per (parity, source rank) slot
+constexpr int kPeerDepth = 4;                        // epochs in flight before a slot is reused
+constexpr size_t kPeerMailboxBytes = (size_t)kPeerDepth * kPeerMaxRanks * kPeerSlotWords * sizeof(unsigned long long);
+constexpr size_t kPeerScratchBytes = 256;            // local scratch behind the mailbox (barrier result)
+
+struct PeerPending {                                 // a posted, not yet combined collective (epoch 0: none)
+  unsigned long long epoch;
+  int nv, op;
+  double* out;
+};
 
 struct PeerView {
   int rank, nranks;                                  // nranks <= 1: no exchange
   unsigned long long epoch;                          // > 0, identical on all ranks for one collective
+  int defer;                                         // 1: only post this collective (the host remembers it as pending)
+  PeerPending pend;                                  // an earlier deferred collective this kernel has to finish
   double* box[kPeerMaxRanks];                        // mailbox of every rank (own one included)
 };
 
 #if defined(__CUDACC__)
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_sys(double* p, double v) {
-  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 
-// Called by ALL threads of ONE CTA per rank (blockDim >= nranks).  vals[nv] (shared or global,
-// written before a __syncthreads by the caller) -> out[nv] = sum / min over ranks.
-// op: 0 = sum (rank order), 1 = min.
-__device__ inline void peer_allreduce(const PeerView& pv, const double* vals, int nv, int op, double* out, int* s_fail) {
+__device__ __forceinline__ unsigned peer_tag(unsigned long long epoch) {
+  return (unsigned)epoch | 0x80000000u;              // never the zero of a fresh mailbox, never the tag this
+}                                                    // slot carried kPeerDepth collectives ago
+
+// Step 1, by ALL threads of ONE CTA per rank: vals[nv] (shared or global, written before a __syncthreads
+// by the caller), nv <= kPeerMaxVals, one word per thread to every rank.
+__device__ inline void peer_post(const PeerView& pv, unsigned long long epoch, const double* vals, int nv) {
+  const unsigned tag = peer_tag(epoch);
+  const int nw = 2 * nv;
+  const size_t slot = (size_t)((int)(epoch % kPeerDepth) * pv.nranks + pv.rank) * kPeerSlotWords;
+  for (int t = threadIdx.x; t < pv.nranks * nw; t += blockDim.x) {
+    const int r = t / nw, w = t - r * nw;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[w >> 1]);
+    const unsigned half = (w & 1) ? (unsigned)(bits >> 32) : (unsigned)bits;
+    st_relaxed_sys_u64(reinterpret_cast<unsigned long long*>(pv.box[r]) + slot + w, ((unsigned long long)tag << 32) | half);
+  }
+}
+
+// Steps 2-3, by ALL threads of the CTA: wait for every rank's words of `epoch`, combine in rank order.
+// op: 0 = sum, 1 = min.  *s_fail (shared) must have been zeroed before a __syncthreads; it is set when a
+// peer never arrived, and out[] is then NaN.
+__device__ inline void peer_collect(const PeerView& pv, unsigned long long epoch, int nv, int op, double* out, int* s_fail) {
+  __shared__ unsigned s_half[kPeerMaxRanks * kPeerSlotWords];
   const int tid = threadIdx.x;
-  if (tid == 0) *s_fail = 0;
-  __syncthreads();
-  const int parity = (int)(pv.epoch & 1ull);
-  if (tid < pv.nranks) {
-    double* dst = pv.box[tid] + (size_t)(parity * pv.nranks + pv.rank) * kPeerSlot;
-    for (int v = 0; v < nv; ++v) st_relaxed_sys(dst + 1 + v, vals[v]);
-    st_release_sys(reinterpret_cast<unsigned long long*>(dst), pv.epoch);
-    const unsigned long long* flag =
-        reinterpret_cast<const unsigned long long*>(pv.box[pv.rank] + (size_t)(parity * pv.nranks + tid) * kPeerSlot);
+  const unsigned tag = peer_tag(epoch);
+  const int nw = 2 * nv;
+  const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(pv.box[pv.rank]) +
+                                   (size_t)((int)(epoch % kPeerDepth) * pv.nranks) * kPeerSlotWords;
+  for (int t = tid; t < pv.nranks * nw; t += blockDim.x) {
+    const int r = t / nw, w = t - r * nw;
+    const unsigned long long* src = mine + (size_t)r * kPeerSlotWords + w;
     const long long t0 = clock64();
-    while (ld_acquire_sys(flag) != pv.epoch) {
+    unsigned long long x = ld_relaxed_sys_u64(src);
+    while ((unsigned)(x >> 32) != tag) {
       if (clock64() - t0 > 8000000000LL) { *s_fail = 1; break; }     // ~4 s at 2 GHz: a peer never arrived
-      __nanosleep(64);
+      x = ld_relaxed_sys_u64(src);
     }
+    s_half[r * kPeerSlotWords + w] = (unsigned)x;
   }
   __syncthreads();
   if (tid < nv) {
     double acc = op == 0 ? 0.0 : INFINITY;
     for (int r = 0; r < pv.nranks; ++r) {
-      const double x = ld_relaxed_sys(pv.box[pv.rank] + (size_t)(parity * pv.nranks + r) * kPeerSlot + 1 + tid);
+      const unsigned long long bits = ((unsigned long long)s_half[r * kPeerSlotWords + 2 * tid + 1] << 32) |
+                                      (unsigned long long)s_half[r * kPeerSlotWords + 2 * tid];
+      const double x = __longlong_as_double((long long)bits);
       acc = op == 0 ? acc + x : fmin(acc, x);
     }
     out[tid] = *s_fail ? NAN : acc;
   }
+  __syncthreads();                                            // s_half may be reused by a second collect
+}
+
+// The whole collective, called by ALL threads of ONE CTA per rank: post (or only post, when the view
+// says defer), finish an attached pending collective while the words travel, then wait and combine.
+__device__ inline void peer_allreduce(const PeerView& pv, const double* vals, int nv, int op, double* out, int* s_fail) {
+  if (threadIdx.x == 0) *s_fail = 0;
+  __syncthreads();
+  peer_post(pv, pv.epoch, vals, nv);
+  if (pv.pend.epoch) peer_collect(pv, pv.pend.epoch, pv.pend.nv, pv.pend.op, pv.pend.out, s_fail);
+  if (!pv.defer) peer_collect(pv, pv.epoch, nv, op, out, s_fail);
 }
 #endif
 

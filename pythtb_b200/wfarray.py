@@ -13,6 +13,7 @@ import copy
 
 import numpy as np
 
+from . import _lib
 from .model import _is_int, _offdiag_approximation_warning_and_stop
 
 __all__ = ["wf_array"]
@@ -114,6 +115,7 @@ class wf_array(object):
             raise Exception("\n\nhalo must be 'auto', 'exchange' or 'recompute'")
         self._halo = halo
         self._store = self._model._engine().new_store(self._wfs_shape(self._nsta_arr))
+        self._rp_sg = self._rp_fx = None    # replay records of the last solve_on_grid / berry_flux call
 
     def _local_mesh(self):
         mesh = [int(m) for m in self._mesh_arr]
@@ -132,6 +134,9 @@ class wf_array(object):
         memo[id(self)] = new
         for k, v in self.__dict__.items():
             if k == "_store":
+                continue
+            if k in ("_rp_sg", "_rp_fx"):
+                setattr(new, k, None)
                 continue
             setattr(new, k, copy.deepcopy(v, memo))
         new._store = self._model._engine().new_store(self._store.shape)
@@ -153,6 +158,21 @@ class wf_array(object):
         """pythtb.py:2421-2532: solve on k = start_k + i/(N-1), i < N-1, impose
         the periodic images on every axis, return the minimal direct gaps.
         One fused kernel launch for the whole mesh."""
+        # ---- replay: the same call as last time on this array (a parameter sweep, a timing loop) re-issues
+        # the bound launch in the library (tbk_prepared_run) as long as the model, the device array and the
+        # workspace are still the ones it was bound to — one foreign call, no argument marshalling
+        rp = self._rp_sg
+        if rp is not None and type(start_k) is list and start_k == rp[0] and self._model._plan_cache is rp[1]:
+            st, eng = self._store, rp[2]
+            if st._dev is rp[3] and eng._ws is rp[4] and st.state != "host":
+                st.state = "device"
+                rc = eng.lib.tbk_prepared_run(rp[5], eng.stream(), 1)
+                if rc:
+                    _lib.check(rc)
+                self._start_k = start_k
+                if rp[7] and not np.all(np.isfinite(rp[6])):
+                    raise _lib.TbkError("\n\nsolve_on_grid: a peer rank never delivered its gaps (fused reduction timed out)")
+                return rp[6].copy()
         if self._dim_arr != self._model._dim_k:
             raise Exception("\n\nIf using solve_on_grid method, dimension of wf_array must equal"
                             "\ndim_k of the tight-binding model!")
@@ -170,6 +190,13 @@ class wf_array(object):
         gaps = self._solve_on_grid_device(start, host_result=True)
         if self._nsta_arr <= 1:
             return None
+        hit = self._store.__dict__.get("_tbk_sg_fast")
+        self._rp_sg = None
+        if hit is not None and hit[5] is not None and type(start_k) is list and hit[1] is self._store._dev:
+            eng = self._model._engine()
+            if hasattr(eng, "lib"):
+                self._rp_sg = (list(start_k), self._model._plan_cache, eng, hit[1], hit[2], hit[3].handle, hit[5],
+                               self._shard is not None, hit[3])
         return self._gaps_to_host(gaps)
 
     def _halo_mode(self):
@@ -181,10 +208,12 @@ class wf_array(object):
             return self._halo
         return "recompute" if self._model._nsta <= 16 else "exchange"
 
-    def _solve_on_grid_device(self, start, want_gaps=True, host_result=False):
+    def _solve_on_grid_device(self, start, want_gaps=True, host_result=False, defer_reduce=False):
         """Launch the fused grid solve (and, when sharded, close the slab and
         reduce the gaps over ranks); results stay engine-resident unless
-        ``host_result`` asks for a host array (unsharded: zero-copy)."""
+        ``host_result`` asks for a host array (unsharded: zero-copy).
+        ``defer_reduce`` (sharded, device result): the minimum over the ranks is
+        completed by the next ``_berry_flux_device`` launch or ``engine.peer_flush()``."""
         eng = self._model._engine()
         start = np.array(start, dtype=float).reshape(-1)
         sh = self._shard
@@ -196,7 +225,8 @@ class wf_array(object):
         # memory where the kernel family supports it, NCCL all-reduce otherwise)
         gaps = eng.solve_grid(self._model, self._store, self._mesh_arr, start, row0=sh.row0, nrows=sh.nrows,
                               wrap0=(2 if mode == "recompute" else 0), want_gaps=want_gaps,
-                              host_result=host_result, reduce_ranks=(sh.rank, sh.nranks))
+                              host_result=host_result, reduce_ranks=(sh.rank, sh.nranks),
+                              defer_reduce=defer_reduce and mode == "recompute")
         if mode == "exchange":
             # rank r needs the first row of rank r+1; rank 0's row reaches the last
             # rank multiplied by the pbc phase (pythtb.py:2729, 2740-2741)
@@ -423,11 +453,33 @@ class wf_array(object):
     def berry_flux(self, occ="All", dirs=None, individual_phases=False):
         """pythtb.py:3068-3205: plaquette phases / integrated Berry curvature on
         every 2-D slice spanned by ``dirs``; one fused launch for all plaquettes."""
+        rp = self._rp_fx                    # replay of the previous identical call (see solve_on_grid)
+        if rp is not None and not individual_phases and type(occ) is list and occ == rp[0] and dirs == rp[1] and \
+                self._model._assume_position_operator_diagonal != False:  # noqa: E712
+            st, eng = self._store, rp[2]
+            if st._dev is rp[3] and eng._ws is rp[4] and st.state != "host":
+                rc = eng.lib.tbk_prepared_run(rp[5], eng.stream(), 1)
+                if rc:
+                    _lib.check(rc)
+                tot = rp[6]
+                if rp[7] and not np.all(np.isfinite(tot)):
+                    raise _lib.TbkError("\n\nberry_flux: a peer rank never delivered its partial sum (fused reduction timed out)")
+                if self._dim_arr == 2:
+                    return np.float64(tot[0])
+                return tot.copy().reshape(rp[8])
+        occ_arg, dirs_arg = occ, dirs
         occ, dirs = self._check_flux_args(occ, dirs)
         eng = self._model._engine()
         sh = self._shard
         if not individual_phases and (sh is None or 0 in dirs):
             res = self._berry_flux_device(occ, dirs, host_result=True)
+            hit = self._store.__dict__.get("_tbk_fx_fast")
+            self._rp_fx = None
+            if hit is not None and type(occ_arg) is list and hasattr(eng, "lib") and hit[1] is self._store._dev and \
+                    hit[0][0] == tuple(int(x) for x in occ) and hit[0][1] == tuple(dirs) and isinstance(res, np.ndarray):
+                rshape = tuple(int(self._mesh_arr[d]) for d in range(self._dim_arr) if d not in dirs)
+                self._rp_fx = (list(occ_arg), (None if dirs_arg is None else list(dirs_arg)), eng, hit[1], hit[2],
+                               hit[3].handle, hit[4], sh is not None, rshape, hit[3])
             res = res if isinstance(res, np.ndarray) else res.cpu().numpy()
             rest = [d for d in range(self._dim_arr) if d not in dirs]
             res = res.reshape(tuple(int(self._mesh_arr[d]) for d in rest))

@@ -54,7 +54,7 @@ class OracleEngine(object):
         return np.array([np.repeat(np.exp(-2.0j * np.pi * np.asarray(orb)[:, kd]), nspin) for kd in k_dirs])
 
     def solve_grid(self, model, store, mesh_arr, start_k, row0=0, nrows=None, wrap0=1, want_gaps=True, host_result=False,
-                   reduce_ranks=None):
+                   reduce_ranks=None, defer_reduce=False):
         """Same contract as B200Engine.solve_grid: fills the local rows
         [row0, row0+nrows] of a shard (the closing row only for wrap0 in (1, 2))."""
         wfs, _ = orc.solve_on_grid(model, mesh_arr, start_k)

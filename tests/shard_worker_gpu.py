@@ -56,6 +56,26 @@ def main():
                         assert e.shape == e_ref.shape, (e.shape, e_ref.shape)
                         ok, dev = compare.sets_close(e, e_ref, 2 * np.pi, 1e-8)
                         assert ok, (d, dev)
+        # deferred gap reduction (tbk_peer_defer): posted by the solve kernel, completed by the flux kernel's
+        # exchange, by an explicit flush, or implicitly by the next solve; repeated calls exercise slot reuse
+        for model, occ, mesh in cases[:2]:
+            full = tb.wf_array(model, mesh)
+            gaps_ref = full.solve_on_grid([-0.5, -0.5])
+            f_ref = full.berry_flux(occ)
+            w = tb.wf_array(model, mesh, shard=(rank, world), halo="recompute")
+            eng = model._engine()
+            for rep in range(7):
+                g = w._solve_on_grid_device([-0.5, -0.5], defer_reduce=True)
+                if rep % 3 == 0:
+                    f = w._berry_flux_device(occ)
+                    assert abs(float(f.cpu().reshape(-1)[0]) - f_ref) < 1e-9
+                elif rep % 3 == 1:
+                    eng.peer_flush()
+                else:
+                    g2 = w._solve_on_grid_device([-0.5, -0.5], defer_reduce=True)   # flushes the first implicitly
+                    eng.peer_barrier()                                                # ... and the barrier the second
+                    assert np.array_equal(g2.cpu().numpy(), gaps_ref), (rep, g2, gaps_ref)
+                assert np.array_equal(g.cpu().numpy(), gaps_ref), (rep, g, gaps_ref)
         # a wider occupied set: the CTA-wide Wilson-loop kernels (nocc >= 8) across ranks
         rib = M.random_model(tb, norb=20, dim=2, nhop=40, nspin=1, seed=11)
         full = tb.wf_array(rib, [17, 9])
