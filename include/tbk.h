@@ -158,12 +158,12 @@ int tbk_peer_destroy(tbk_peer* peer);
  * timed multi-GPU step together on all ranks (the analogue of torch.distributed.barrier(), but in
  * stream order and without a host round trip).  No-op for peer == NULL or a single rank. */
 int tbk_peer_barrier(tbk_peer* peer, void* stream);
-/* Deferred reduction.  tbk_peer_defer(peer, 1) makes the NEXT tbk_solve_grid_x only post this rank's
- * minimal gaps to the peers and return; gaps_dev is completed (minimum over the ranks) by the next
- * tbk_flux_plane_x issued with the same peer — its exchange carries both, so a solve + flux step exposes
- * one NVLink round trip instead of two — or by tbk_peer_flush (a one-warp kernel), or implicitly
- * before any later collective that cannot carry it.  gaps_dev must stay allocated until then.
- * All ranks must make the same sequence of calls. */
+/* Deferred reduction.  tbk_peer_defer(peer, 1) makes the NEXT tbk_solve_grid_x keep this rank's minimal
+ * gaps in its own memory (no exchange, no NVLink traffic) and return; gaps_dev is completed (minimum over
+ * the ranks) by the next tbk_flux_plane_x issued with the same peer — the gaps travel in the same message as
+ * the flux sums, so a solve + flux step is ONE exchange instead of two — or by tbk_peer_flush (a one-CTA
+ * kernel), or implicitly before a later collective that cannot carry it.  gaps_dev must stay allocated
+ * until then.  All ranks must make the same sequence of calls. */
 int tbk_peer_defer(tbk_peer* peer, int32_t on);
 int tbk_peer_flush(tbk_peer* peer, void* stream);
 

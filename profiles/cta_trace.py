@@ -11,10 +11,15 @@ import pythtb_b200 as tb
 from pythtb_b200 import _engine, _lib
 from tests import models as M
 
+world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+if world > 1:
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
 wl = sys.argv[1] if len(sys.argv) > 1 else "haldane"
 model, occ = (M.haldane(tb, delta=0.0), [0]) if wl == "haldane" else (M.kane_mele(tb, "odd"), [0, 1])
 eng = _engine.get_engine()
-w = tb.wf_array(model, [1025, 1025])
+w = tb.wf_array(model, [1024 * world + 1, 1025], shard=(rank, world)) if world > 1 else tb.wf_array(model, [1025, 1025])
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=eng.device)
 CAP = 4096
 buf = (ctypes.c_uint64 * (CAP * 4))()
@@ -50,15 +55,29 @@ def summarise(name, a):
 
 
 res = []
-for rep in range(3):
+spans = []
+for rep in range(12):
     eng.lib.tbk_flush_l2(ctypes.c_void_p(flush.data_ptr()), flush.numel(), eng.stream())
-    w._solve_on_grid_device([-0.5, -0.5])
+    eng.peer_barrier()
+    w._solve_on_grid_device([-0.5, -0.5], defer_reduce=world > 1)
     torch.cuda.synchronize()
     a = grab()
+    if world > 1:
+        dist.barrier()
     eng.lib.tbk_flush_l2(ctypes.c_void_p(flush.data_ptr()), flush.numel(), eng.stream())
+    eng.peer_barrier()
     w._berry_flux_device(occ)
     torch.cuda.synchronize()
     b = grab()
-    if rep == 2:
+    if world > 1:
+        dist.barrier()
+    if rep >= 2:
+        spans.append(((a[:, 2].max() - a[:, 1].min()) / 1e3, (b[:, 2].max() - b[:, 1].min()) / 1e3,
+                      float(np.sort(b[:, 2])[-2] - b[:, 1].min()) / 1e3))
+    if rep == 11:
         res = [summarise("mesh_small_kernel", a), summarise("flux_rows_kernel", b)]
-print(json.dumps(res, indent=1))
+print("rank %d world %d spans us (mesh, flux, flux without its last CTA): %s" % (rank, world, np.round(np.median(np.array(spans), axis=0), 2)))
+if rank == 0:
+    print(json.dumps(res, indent=1))
+if world > 1:
+    dist.barrier(); dist.destroy_process_group()

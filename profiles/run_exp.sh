@@ -15,6 +15,6 @@ PY
 }
 for w in haldane kane_mele; do
   timeout 300 python bench.py --workload $w --steps 200 --warmup 5 --no-cpu > $OUT/bench_$w.json 2>$OUT/bench_$w.err; show $OUT/bench_$w.json
-  TBK_L2_FETCH=32 timeout 300 python bench.py --workload $w --steps 200 --warmup 5 --no-cpu > $OUT/bench_${w}_l2f32.json 2>$OUT/bench_${w}_l2f32.err; show $OUT/bench_${w}_l2f32.json
+  TBK_PDL=0 timeout 300 python bench.py --workload $w --steps 200 --warmup 5 --no-cpu > $OUT/bench_${w}_nopdl.json 2>$OUT/bench_${w}_nopdl.err; show $OUT/bench_${w}_nopdl.json
 done
 TBK_CTA_TRACE=1 timeout 300 python profiles/cta_trace.py haldane > $OUT/cta_trace_haldane.json 2>$OUT/cta_trace_haldane.err; cat $OUT/cta_trace_haldane.json | head -120

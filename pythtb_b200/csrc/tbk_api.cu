@@ -69,22 +69,16 @@ __global__ void peer_barrier_kernel(const __grid_constant__ PeerView pv, double*
   peer_allreduce(pv, s_v, 1, 0, scratch, &s_fail);
 }
 
-// finishes a deferred collective nobody else picked up (one warp)
+// exchanges a deferred collective nobody else picked up (one CTA)
 __global__ void peer_collect_kernel(const __grid_constant__ PeerView pv) {
   __shared__ int s_fail;
-  if (threadIdx.x == 0) s_fail = 0;
-  __syncthreads();
-  peer_collect(pv, pv.pend.epoch, pv.pend.nv, pv.pend.op, pv.pend.out, &s_fail);
+  peer_allreduce(pv, nullptr, 0, 0, nullptr, &s_fail);
 }
 
 int peer_flush(tbk_peer* p, cudaStream_t st) {
-  if (!p || !p->connected || p->nranks < 2 || !p->pending.epoch) return TBK_OK;
-  PeerView v;
-  memset(&v, 0, sizeof(v));
-  v.rank = p->rank; v.nranks = p->nranks;
-  for (int r = 0; r < p->nranks; ++r) v.box[r] = p->box[r];
-  v.pend = p->pending;
-  p->pending.epoch = 0;
+  if (!p || !p->connected || p->nranks < 2 || p->pending.nv <= 0) return TBK_OK;
+  PeerView v = peer_next(p);
+  peer_attach_pending(p, v);
   peer_collect_kernel<<<1, 64, 0, st>>>(v);
   TBK_LAUNCH_CHECK("peer_collect_kernel");
   return TBK_OK;
@@ -271,7 +265,7 @@ int tbk_peer_barrier(tbk_peer* p, void* stream) {
   if (!p || !p->connected || p->nranks < 2) return TBK_OK;
   if (int rc = peer_flush(p, (cudaStream_t)stream)) return rc;
   const PeerView pv = peer_next(p);
-  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pv, (double*)((char*)p->box[p->rank] + kPeerMailboxBytes));
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pv, (double*)((char*)p->box[p->rank] + kPeerMailboxBytes) + kPeerMaxVals);
   TBK_LAUNCH_CHECK("peer_barrier_kernel");
   return TBK_OK;
 }

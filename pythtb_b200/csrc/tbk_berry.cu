@@ -199,6 +199,10 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
   __shared__ int s_last;
   const unsigned long long t_begin = cta_trace_begin(trace);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // Programmatic dependent launch: this grid may have been scheduled while the previous kernel on the
+  // stream (typically the grid solve that writes the array read here) was still draining; everything it
+  // wrote is visible after this wait.  A no-op when launched without the attribute.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   int occ[NOCC];
 #pragma unroll
   for (int m = 0; m < NOCC; ++m) occ[m] = v.occ[m];
@@ -324,10 +328,6 @@ static int launch_flux_rows(const WfView& v, const long long* off, long long nsl
                             cudaStream_t st) {
   static int occ_plaq = 0, occ_sum = 0;                   // resident CTAs per SM of the two variants
   if (occ_plaq == 0) {
-    if (const char* e = getenv("TBK_L2_FETCH")) {         // experiment knob: DRAM->L2 fetch granularity (32/64/128 B)
-      const int g = atoi(e);
-      if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
-    }
     int a = 0, b = 0;
     TBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, flux_rows_kernel<NOCC, N, true>, kFluxThreads, 0));
     TBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, flux_rows_kernel<NOCC, N, false>, kFluxThreads, 0));
@@ -343,13 +343,29 @@ static int launch_flux_rows(const WfView& v, const long long* off, long long nsl
   }
   const int grid = (int)(tl.ntiles < resident ? tl.ntiles : resident);
   PeerView pview = total ? peer_next(peer) : peer_next(nullptr);
-  if (total) peer_attach_pending(peer, pview);             // a deferred gap reduction rides on this kernel's exchange
+  if (total && peer && peer->pending.nv > 0) {             // a deferred gap reduction rides on this kernel's exchange
+    if (peer_can_attach(peer, (int)nslice)) peer_attach_pending(peer, pview);
+  }
+  // launched as a programmatic dependent of the previous kernel on the stream: its CTAs are scheduled as that
+  // kernel's CTAs retire and wait at griddepcontrol.wait, which hides this kernel's launch latency and ramp
+  // behind the predecessor's tail (TBK_PDL=0 turns it off)
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("TBK_PDL"); pdl = (e && atoi(e) == 0) ? 0 : 1; }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kFluxThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  double* part_arg = plaq ? (total ? partial : nullptr) : partial;
+  unsigned long long* trace = cta_trace_buffer();
   if (plaq)
-    flux_rows_kernel<NOCC, N, true><<<grid, kFluxThreads, 0, st>>>(v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
-                                                                  total ? partial : nullptr, ticket, total, pview, cta_trace_buffer());
+    TBK_CUDA(cudaLaunchKernelEx(&cfg, flux_rows_kernel<NOCC, N, true>, v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
+                                part_arg, ticket, total, pview, trace));
   else
-    flux_rows_kernel<NOCC, N, false><<<grid, kFluxThreads, 0, st>>>(v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
-                                                                   partial, ticket, total, pview, cta_trace_buffer());
+    TBK_CUDA(cudaLaunchKernelEx(&cfg, flux_rows_kernel<NOCC, N, false>, v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
+                                part_arg, ticket, total, pview, trace));
   TBK_LAUNCH_CHECK("flux_rows_kernel");
   return TBK_OK;
 }
@@ -605,7 +621,7 @@ static int launch_flux_ring(const WfView& v, const long long* off, long long nsl
   }
   const int grid = (int)(tl.ntiles < resident ? tl.ntiles : resident);
   PeerView pview = total ? peer_next(peer) : peer_next(nullptr);
-  if (total) peer_attach_pending(peer, pview);
+  if (total && peer_can_attach(peer, (int)nslice)) peer_attach_pending(peer, pview);
   if (plaq)
     kern_p<<<grid, kRingThreads, dyn, st>>>(v, off, n0, stride0, n1, tl, nslice, plaq, total ? partial : nullptr, ticket,
                                             total, pview);

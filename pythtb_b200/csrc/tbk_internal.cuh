@@ -161,8 +161,8 @@ struct tbk_peer {
   unsigned long long epoch;          // advanced by every collective issued through this group
   double* box[tbk::kPeerMaxRanks];   // box[rank] is the local allocation
   bool connected;
-  bool defer_next;                   // tbk_peer_defer: the next tbk_solve_grid_x only posts its reduction
-  tbk::PeerPending pending;          // that posted collective, until a later kernel (or tbk_peer_flush) finishes it
+  bool defer_next;                   // tbk_peer_defer: the next tbk_solve_grid_x keeps its reduction local
+  tbk::PeerPending pending;          // that deferred collective, until a later kernel (or tbk_peer_flush) exchanges it
 };
 
 namespace tbk {
@@ -176,19 +176,24 @@ inline PeerView peer_next(tbk_peer* p) {
   }
   return v;
 }
-// ... of which the kernel only posts its contribution: {nv, op, out} stay pending on the host handle
+// no collective now: the kernel stores its local result in this rank's scratch, {nv, op, out} stay pending
+// on the host handle until the next collective carries them (peer_attach_pending) or peer_flush runs
 inline PeerView peer_next_deferred(tbk_peer* p, int nv, int op, double* out) {
-  PeerView v = peer_next(p);
-  if (v.nranks > 1) {
+  PeerView v;
+  memset(&v, 0, sizeof(v));
+  if (p && p->connected && p->nranks > 1) {
+    v.rank = p->rank; v.nranks = p->nranks; v.epoch = p->epoch;
     v.defer = 1;
-    p->pending.epoch = v.epoch; p->pending.nv = nv; p->pending.op = op; p->pending.out = out;
+    v.local = (double*)((char*)p->box[p->rank] + kPeerMailboxBytes);
+    p->pending.nv = nv; p->pending.op = op; p->pending.out = out; p->pending.local = v.local;
   }
   if (p) p->defer_next = false;
   return v;
 }
-// hand a pending collective to a view whose kernel finishes it (peer_allreduce does)
+// hand a pending collective to a view whose kernel exchanges it together with its own values
+inline bool peer_can_attach(const tbk_peer* p, int nv) { return p && p->pending.nv > 0 && nv + p->pending.nv <= kPeerMaxVals; }
 inline void peer_attach_pending(tbk_peer* p, PeerView& v) {
-  if (p && v.nranks > 1 && p->pending.epoch) { v.pend = p->pending; p->pending.epoch = 0; }
+  if (p && v.nranks > 1 && p->pending.nv > 0) { v.pend = p->pending; p->pending.nv = 0; }
 }
 // finish a pending collective with a one-warp kernel (tbk_api.cu); no-op when nothing is pending
 int peer_flush(tbk_peer* p, cudaStream_t st);

@@ -151,6 +151,9 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
   __shared__ int s_last;
   __shared__ double s_fin[N];
   const unsigned long long t_begin = cta_trace_begin(trace);
+  // let a programmatic dependent (the flux kernel) be scheduled as soon as this grid's CTAs retire: the whole
+  // grid is resident from the start (one wave), so the dependent can never take a slot a CTA of this grid needs
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (threadIdx.x < N) s_pbc0[threadIdx.x] = tl.closing_g >= 0 ? out.pbc_phase[threadIdx.x] : mk(1.0, 0.0);
   if (threadIdx.x < out.nd * N) {
     const int d = threadIdx.x / N;
@@ -386,9 +389,10 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
       else gaps_out[b] = t;
     }
   }
-  if (peer.nranks > 1) {                            // minimum over the ranks, through the peers' mailboxes
-    __syncthreads();
-    peer_allreduce(peer, s_fin, N - 1, 1, gaps_out, &s_last);
+  if (peer.nranks > 1) {                            // minimum over the ranks, through the peers' mailboxes —
+    __syncthreads();                                // or deferred: kept local until the next exchange carries it
+    if (peer.defer) { if (tid < N - 1) peer.local[tid] = s_fin[tid]; }
+    else peer_allreduce(peer, s_fin, N - 1, 1, gaps_out, &s_last);
   }
   cta_trace_end(trace, t_begin);
 }

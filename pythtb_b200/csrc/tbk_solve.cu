@@ -922,7 +922,7 @@ static int launch_mesh_small(const tbk_model* m, const KSrc& ks, const OutSpec& 
     if (!ticket) { set_error("tbk_solve_grid: cannot allocate the reduction tickets"); return TBK_ERR_CUDA; }
   }
   const int gauge = (m->pv.convention == 1 && m->pv.dim_k > 0) ? 1 : 0;
-  if (peer && peer->pending.epoch) { if (int rc = peer_flush(peer, st)) return rc; }   // an unclaimed deferred reduction
+  if (peer && peer->pending.nv > 0) { if (int rc = peer_flush(peer, st)) return rc; }   // an unclaimed deferred reduction
   const PeerView pview = !gaps_dev ? peer_next(nullptr)
                          : (peer && peer->defer_next ? peer_next_deferred(peer, n - 1, 1, gaps_dev) : peer_next(peer));
 #define TBK_MESH_LAUNCH(NN, PP, MB, RP) \

@@ -400,12 +400,18 @@ def test_replayed_calls_follow_their_arguments():
     host[5, 6, 0] = (host[5, 6, 0] + 0.5 * host[5, 6, 2]) / np.sqrt(1.25)   # a real change: it must
     f1 = w.berry_flux([0, 1])
     ref = orc.berry_flux(np.array(w._wfs), 2, [0, 1])
-    assert abs(compare.circ_diff(f1, ref, 2 * np.pi)) < 1e-8 and abs(compare.circ_diff(f1, f0, 2 * np.pi)) > 1e-6
+    assert abs(compare.circ_diff(f1, ref, 2 * np.pi)) < 1e-8        # (the total is 2 pi C whatever was written:
+    p1 = w.berry_flux([0, 1], individual_phases=True)               #  the edit shows in the plaquettes around it)
+    pref = orc.berry_flux(np.array(w._wfs), 2, [0, 1], None, True)
+    assert np.max(np.abs(compare.circ_diff(p1, pref, 2 * np.pi))) < 1e-8
+    w2 = mod.wf_array(m, mesh)
+    w2.solve_on_grid([-0.5, -0.5])
+    assert np.max(np.abs(compare.circ_diff(p1, w2.berry_flux([0, 1], individual_phases=True), 2 * np.pi))) > 1e-3
     # a model edit rebuilds the plan: the solve must follow it
     h = M.haldane(mod, delta=0.0)
     wh = mod.wf_array(h, mesh)
     a = wh.solve_on_grid([-0.5, -0.5]); wh.solve_on_grid([-0.5, -0.5])
-    wh._model.set_onsite([-0.7, 0.7], mode="set")
+    wh._model.set_onsite([-0.7, 0.7], mode="reset")
     b = wh.solve_on_grid([-0.5, -0.5])
     _, gaps_ref = orc.solve_on_grid(wh._model, mesh, [-0.5, -0.5])
     assert np.max(np.abs(b - gaps_ref)) < 1e-10 and abs(a[0] - b[0]) > 1e-3
