@@ -7,7 +7,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libtbk_b200.so")
+# PYTHTB_B200_LIB: an alternative build of the same library (A/B experiments under profiles/)
+SO_PATH = os.environ.get("PYTHTB_B200_LIB") or os.path.join(HERE, "libtbk_b200.so")
 
 c_int32, c_int64, c_size_t, c_void_p = ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t, ctypes.c_void_p
 c_double_p = ctypes.POINTER(ctypes.c_double)

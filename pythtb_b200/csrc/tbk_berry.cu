@@ -122,45 +122,59 @@ flux_small_kernel(WfView v, const long long* __restrict__ slice_off, long long n
 // |sum of args| < pi and arg(prod) = sum(arg) exactly — and ONE atan2 is taken per thread per tile;
 // any other plaquette gets its own atan2.  The plane sum is finished by the last CTA (ticket) in a
 // fixed order: one launch, deterministic.
+// Work is dealt out per WARP, not per CTA: the plane is cut into column strips of (nearly) equal width
+// <= 31 and row blocks of (nearly) equal height such that strips x blocks fills the resident warps of one
+// wave.  (CTA-sized tiles of 4 x 31 columns left the last column block of a 1024-wide mesh with one busy
+// warp in four and 711 tiles for 740 CTA slots: the per-CTA timeline showed CTA times from 14.3 to 18.3 us.)
 // ---------------------------------------------------------------------------
 constexpr int kFluxThreads = 128;
 constexpr int kFluxWarpCols = 31;
 constexpr int kFluxCols = kFluxWarpCols * (kFluxThreads / 32);
 constexpr int kFluxMaxRows = 24;
 
+constexpr int kFluxWarps = kFluxThreads / 32;
+
 struct FluxTiling {
-  int ti;                 // plaquette rows per tile
-  long long nbx, nrb;     // column blocks, row blocks per slice
-  long long ntiles;       // nslice * nrb * nbx
+  long long nstrip;       // column strips per slice: widths wc or wc + 1 (<= 31), the first cx strips the wider ones
+  int wc, cx;
+  long long nrb;          // row blocks per slice: heights hr or hr + 1, the first rx blocks the taller ones
+  int hr, rx;
+  long long nitems;       // nslice * nrb * nstrip warp work items (strip index fastest)
 };
 
-// One balanced wave: as many tiles as CTAs can be resident (`resident` = #SM x CTAs per SM), all of
-// (nearly) the same height; more column blocks than resident CTAs -> full-height tiles, grid-stride.
+// One balanced wave of warp items: `resident` = #SM x CTAs per SM CTAs of kFluxWarps warps.
 static FluxTiling flux_tiling(long long nslice, long long n0, long long n1, long long resident) {
   FluxTiling t;
-  t.nbx = (n1 - 1 + kFluxCols - 1) / kFluxCols;
-  const long long p0 = n0 - 1;
-  long long per_col = resident / (nslice * t.nbx);       // tiles per column block
-  if (per_col < 1) per_col = 1;
-  if (per_col > p0) per_col = p0;
-  long long ti = (p0 + per_col - 1) / per_col;
-  if (ti < 4 && p0 >= 4) ti = 4;                          // keep the per-tile first-row loads amortised
-  t.ti = (int)ti;
-  t.nrb = (p0 + ti - 1) / ti;
-  t.ntiles = nslice * t.nrb * t.nbx;
+  const long long p0 = n0 - 1, p1 = n1 - 1;
+  t.nstrip = (p1 + kFluxWarpCols - 1) / kFluxWarpCols;
+  t.wc = (int)(p1 / t.nstrip);
+  t.cx = (int)(p1 - t.wc * t.nstrip);
+  long long nrb = resident * kFluxWarps / (nslice * t.nstrip);   // row blocks per strip
+  if (nrb > p0 / 4) nrb = p0 / 4;                                // keep the per-item first-row loads amortised
+  if (nrb < 1) nrb = 1;
+  t.nrb = nrb;
+  t.hr = (int)(p0 / nrb);
+  t.rx = (int)(p0 - t.hr * nrb);
+  t.nitems = nslice * t.nrb * t.nstrip;
   return t;
 }
-// upper bound of ntiles over every `resident` the launcher may use (workspace sizing)
+// upper bound of nitems over every `resident` the launcher may use (workspace sizing)
 static long long flux_tiles_bound(long long nslice, long long n0, long long n1) {
-  const long long nbx = (n1 - 1 + kFluxCols - 1) / kFluxCols;
-  const long long a = nslice * nbx * ((n0 - 1 + 3) / 4 + 3);
-  const long long b = (long long)kNumSM * 16 + nslice * nbx;
+  const long long nstrip = (n1 - 1 + kFluxWarpCols - 1) / kFluxWarpCols;
+  const long long a = nslice * nstrip * ((n0 - 1) / 4 + 1);
+  const long long b = (long long)kNumSM * 16 * kFluxWarps + nslice * nstrip;
   return a < b ? a : b;
 }
 
 template <int NOCC, int N>
 struct OccState {
   cplx u[NOCC][N];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int m = 0; m < NOCC; ++m)
+#pragma unroll
+      for (int o = 0; o < N; ++o) u[m][o] = mk(0.0, 0.0);
+  }
   __device__ __forceinline__ void load(const cplx* __restrict__ p, const int* occ) {
 #pragma unroll
     for (int m = 0; m < NOCC; ++m) {
@@ -188,8 +202,22 @@ __device__ __forceinline__ cplx link_det(const OccState<NOCC, N>& a, const OccSt
   else return M[0][0] * M[1][1] - M[0][1] * M[1][0];
 }
 
+// the state held by the next lane
+template <int NOCC, int N>
+__device__ __forceinline__ OccState<NOCC, N> shfl_down_state(const OccState<NOCC, N>& a) {
+  OccState<NOCC, N> r;
+#pragma unroll
+  for (int m = 0; m < NOCC; ++m)
+#pragma unroll
+    for (int o = 0; o < N; ++o) {
+      r.u[m][o].re = __shfl_down_sync(0xffffffffu, a.u[m][o].re, 1);
+      r.u[m][o].im = __shfl_down_sync(0xffffffffu, a.u[m][o].im, 1);
+    }
+  return r;
+}
+
 template <int NOCC, int N, bool WANT_PLAQ>
-__global__ void __launch_bounds__(kFluxThreads)
+__global__ void __launch_bounds__(kFluxThreads, (NOCC == 1 && N == 2) ? 5 : 1)   // 5 CTAs / SM for the Haldane case (<= 102 registers)
 flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0, long long stride0, long long n1,
                  long long stride1, FluxTiling tl, long long nslice, double* __restrict__ plaq,
                  double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ total,
@@ -207,16 +235,85 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
 #pragma unroll
   for (int m = 0; m < NOCC; ++m) occ[m] = v.occ[m];
   const long long p0 = n0 - 1, p1 = n1 - 1;
-  for (long long tile = blockIdx.x; tile < tl.ntiles; tile += gridDim.x) {
-    const long long s = tile / (tl.nrb * tl.nbx);
-    const long long rem = tile - s * tl.nrb * tl.nbx;
-    const long long rb = rem / tl.nbx, bx = rem - rb * tl.nbx;
-    const long long col = bx * kFluxCols + warp * kFluxWarpCols + lane;   // mesh column of this lane's vertical link
-    const bool has_col = col < n1;
-    const bool owner = lane < kFluxWarpCols && col < p1;                  // owns plaquette column `col`
-    const long long i0 = rb * tl.ti;
-    const int nrow = (int)((i0 + tl.ti < p0 ? i0 + tl.ti : p0) - i0);
+  const long long per_slice = tl.nrb * tl.nstrip;
+  // one slice (the usual 2-D mesh): a warp keeps adding its items up and the CTA writes ONE partial, so the
+  // last CTA has gridDim.x values to sum instead of one per item; several slices: one partial per item
+  const bool cta_partial = nslice == 1;
+  double wacc = 0.0;
+  for (long long item = (long long)blockIdx.x * kFluxWarps + warp; item < tl.nitems; item += (long long)gridDim.x * kFluxWarps) {
+    const long long s = item / per_slice;
+    const long long rem = item - s * per_slice;
+    const long long rb = rem / tl.nstrip, strip = rem - rb * tl.nstrip;
+    const int width = tl.wc + (strip < tl.cx ? 1 : 0);                    // plaquette columns of this strip
+    const long long col = strip * tl.wc + (strip < tl.cx ? strip : tl.cx) + lane;   // mesh column of this lane's vertical link
+    const bool has_col = lane <= width;                                   // col <= strip end <= p1 < n1
+    const bool owner = lane < width;                                      // owns plaquette column `col`
+    const long long i0 = rb * tl.hr + (rb < tl.rx ? rb : tl.rx);
+    const int nrow = tl.hr + (rb < tl.rx ? 1 : 0);
     const cplx* pa = v.wfs + slice_off[s] + col * stride1 + i0 * stride0;  // u(i0, col)
+    double acc = 0.0;
+    if constexpr (NOCC * N <= 4) {
+      // ---- small states: every lane loads ONLY its own column, two rows ahead (a rotation of four
+      // register slots: rows i, i+1, and i+2, i+3 in flight), and takes the right-hand neighbour's
+      // state for the horizontal link by shuffle.  The kernel is bound by the bytes a warp keeps in
+      // flight (per-CTA timeline + Little's law: one row ahead = 2 KB per warp = ~40 KB per SM gave
+      // ~3.9 TB/s); dropping the neighbour-column registers pays for the deeper prefetch.
+      OccState<NOCC, N> X[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) X[q].zero();             // lanes past the strip carry zeros, never garbage
+      if (has_col) {
+        X[0].load(pa, occ);
+        X[1].load(pa + stride0, occ);
+        if (nrow >= 2) X[2].load(pa + 2 * stride0, occ);
+      }
+      cplx hda;                                            // L(d,a) = conj(H(i,col))
+      {
+        const OccState<NOCC, N> d = shfl_down_state(X[0]);
+        hda = conj(link_det<NOCC, N>(X[0], d));
+      }
+      cplx prod = mk(1.0, 0.0);
+      double* pq = WANT_PLAQ ? plaq + (s * p0 + i0) * p1 + col : nullptr;
+      const cplx* pf = pa + 3 * stride0;                   // row i0 + r + 3 at step r
+#pragma unroll 1
+      for (int r = 0; r < nrow; r += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (r + u < nrow) {
+            if (has_col && r + u + 3 <= nrow) X[(u + 3) & 3].load(pf, occ);
+            pf += stride0;
+            const OccState<NOCC, N>& A = X[u];
+            const OccState<NOCC, N>& B = X[(u + 1) & 3];
+            const cplx lab = link_det<NOCC, N>(A, B);      // V(i, col); junk in lanes without a column
+            cplx right;                                    // V(i, col+1) from the next lane
+            right.re = __shfl_down_sync(0xffffffffu, lab.re, 1);
+            right.im = __shfl_down_sync(0xffffffffu, lab.im, 1);
+            const OccState<NOCC, N> C = shfl_down_state(B);
+            const cplx lbc = link_det<NOCC, N>(B, C);      // H(i+1, col)
+            cplx z = lab * lbc;
+            z = mulc(z, right);                            // L(c,d) = conj(V(i, col+1))
+            z = z * hda;
+            hda = conj(lbc);
+            if (owner) {
+              if (WANT_PLAQ) {
+                const double phase = neg_arg(z);
+                pq[0] = phase;
+                pq += p1;
+                acc += phase;
+              } else if (z.re > 0.5 && z.re > 8.0 * fabs(z.im)) {
+                prod = prod * z;
+              } else {
+                acc += neg_arg(z);
+              }
+            }
+          }
+        }
+        if (!WANT_PLAQ && ((r + 4) % 24) == 0) {           // at most 24 small angles per product
+          if (owner) acc += neg_arg(prod);
+          prod = mk(1.0, 0.0);
+        }
+      }
+      if (!WANT_PLAQ && owner) acc += neg_arg(prod);
+    } else {
     // Register rotation instead of copies: (s0,s1,s2) take the roles (a, b, prefetch of next b) and
     // (c0,c1) the roles (c, prefetch of next c); the roles advance every row, period 6.
     OccState<NOCC, N> s0, s1, s2, c0, c1;
@@ -227,7 +324,6 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
       hda = conj(link_det<NOCC, N>(s0, c1));
       c0.load(pa + stride0 + stride1, occ);
     }
-    double acc = 0.0;
     cplx prod = mk(1.0, 0.0);
     double* pq = WANT_PLAQ ? plaq + (s * p0 + i0) * p1 + col : nullptr;
     int r = 0;
@@ -277,19 +373,23 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
     }
 #undef TBK_FLUX_STEP
     if (!WANT_PLAQ && owner) acc += neg_arg(prod);
+    }
     if (partial) {
-      // fixed-order CTA sum -> partial[tile]
+      // fixed-order warp sum -> partial[item]
       double x = acc;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-      __syncthreads();
-      if (lane == 0) s_red[warp] = x;
-      __syncthreads();
-      if (tid == 0) {
-        double t = 0.0;
-        for (int w = 0; w < kFluxThreads / 32; ++w) t += s_red[w];
-        partial[tile] = t;
-      }
+      if (cta_partial) wacc += x;
+      else if (lane == 0) partial[item] = x;
+    }
+  }
+  if (partial && cta_partial) {
+    if (lane == 0) s_red[warp] = wacc;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < kFluxWarps; ++w) t += s_red[w];
+      partial[blockIdx.x] = t;
     }
   }
   if (!partial) { cta_trace_end(trace, t_begin); return; }
@@ -299,10 +399,10 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
   __syncthreads();
   if (!s_last) { cta_trace_end(trace, t_begin); return; }
   __threadfence();
-  const long long per = tl.nrb * tl.nbx;
+  const long long count = cta_partial ? (long long)gridDim.x : per_slice;
   for (long long s = 0; s < nslice; ++s) {
     double x = 0.0;
-    for (long long i = tid; i < per; i += kFluxThreads) x += __ldcg(partial + s * per + i);
+    for (long long i = tid; i < count; i += kFluxThreads) x += __ldcg(partial + s * count + i);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
     __syncthreads();
@@ -341,7 +441,8 @@ static int launch_flux_rows(const WfView& v, const long long* off, long long nsl
     ticket = take_ticket();
     if (!ticket) { set_error("tbk_flux_plane: cannot allocate the reduction tickets"); return TBK_ERR_CUDA; }
   }
-  const int grid = (int)(tl.ntiles < resident ? tl.ntiles : resident);
+  const long long ctas = (tl.nitems + kFluxWarps - 1) / kFluxWarps;
+  const int grid = (int)(ctas < resident ? ctas : resident);
   PeerView pview = total ? peer_next(peer) : peer_next(nullptr);
   if (total && peer && peer->pending.nv > 0) {             // a deferred gap reduction rides on this kernel's exchange
     if (peer_can_attach(peer, (int)nslice)) peer_attach_pending(peer, pview);
@@ -415,6 +516,12 @@ struct RingTiling {
 template <int NOCC, int N>
 struct RingState {
   cplx u[NOCC][N];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int m = 0; m < NOCC; ++m)
+#pragma unroll
+      for (int o = 0; o < N; ++o) u[m][o] = mk(0.0, 0.0);
+  }
   __device__ __forceinline__ void load(const cplx* p, const int (&occ)[NOCC]) {     // shared memory
 #pragma unroll
     for (int m = 0; m < NOCC; ++m)

@@ -28,7 +28,8 @@ struct MeshTiling {
   int outer;            // product of cnt[d], d < nd-1  ("rows")
   unsigned nseg;        // outer * nbx row segments (< 2^31, checked by the launcher), column block major
   int closing_g;        // global axis-0 index that is the periodic image of row 0 (wrap0 == 2), else -1
-};
+  int cpb;              // > 0: CTAs per column block, each with an equal run of rows of ONE block (grid = cpb * nbx);
+};                      // 0: flat split of the nseg segments over the grid (a CTA may straddle two blocks)
 
 template <int N>
 struct EigRows {
@@ -168,10 +169,20 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
 #pragma unroll
   for (int b = 0; b < N - 1; ++b) gmin[b] = INFINITY;
 
-  // balanced split: the first (nseg % G) CTAs take one segment more (32-bit arithmetic only)
-  const unsigned per = tl.nseg / gridDim.x, extra = tl.nseg - per * gridDim.x;
-  unsigned seg = per * blockIdx.x + (blockIdx.x < extra ? blockIdx.x : extra);
-  const unsigned seg_end = seg + per + (blockIdx.x < extra ? 1u : 0u);
+  // balanced split (32-bit arithmetic only).  cpb > 0: the CTA owns rows [i outer/cpb, (i+1) outer/cpb) of column
+  // block bx — a CTA that straddled two column blocks paid the per-block prologue (sincospi, phase powers, the
+  // per-row phase table) twice and was the tail of the wave.  cpb == 0: the first (nseg % G) CTAs take one segment more.
+  unsigned seg, seg_end;
+  if (tl.cpb > 0) {
+    const unsigned bxi = blockIdx.x / (unsigned)tl.cpb, i = blockIdx.x - bxi * (unsigned)tl.cpb;
+    const unsigned per = (unsigned)tl.outer / (unsigned)tl.cpb, extra = (unsigned)tl.outer - per * (unsigned)tl.cpb;
+    seg = bxi * (unsigned)tl.outer + per * i + (i < extra ? i : extra);
+    seg_end = seg + per + (i < extra ? 1u : 0u);
+  } else {
+    const unsigned per = tl.nseg / gridDim.x, extra = tl.nseg - per * gridDim.x;
+    seg = per * blockIdx.x + (blockIdx.x < extra ? blockIdx.x : extra);
+    seg_end = seg + per + (blockIdx.x < extra ? 1u : 0u);
+  }
   while (seg < seg_end) {
     const int bx = (int)(seg / (unsigned)tl.outer);
     const int row_lo = (int)(seg - (unsigned)bx * (unsigned)tl.outer);
