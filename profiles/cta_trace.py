@@ -76,6 +76,21 @@ for rep in range(12):
                       float(np.sort(b[:, 2])[-2] - b[:, 1].min()) / 1e3))
     if rep == 11:
         res = [summarise("mesh_small_kernel", a), summarise("flux_rows_kernel", b)]
+# the flux kernel inside a step: launched right behind the grid solve (programmatic dependent launch, array still in L2)
+instep = []
+for rep in range(10):
+    eng.lib.tbk_flush_l2(ctypes.c_void_p(flush.data_ptr()), flush.numel(), eng.stream())
+    eng.peer_barrier()
+    w._solve_on_grid_device([-0.5, -0.5], defer_reduce=world > 1)
+    w._berry_flux_device(occ)
+    torch.cuda.synchronize()
+    b = grab()
+    if world > 1:
+        dist.barrier()
+    if rep >= 2:
+        instep.append(((b[:, 2].max() - b[:, 1].min()) / 1e3, float(np.sort(b[:, 2])[-2] - b[:, 1].min()) / 1e3,
+                       float(np.median(b[:, 2] - b[:, 1])) / 1e3))
+print("rank %d world %d flux kernel inside a step, us (span, span without its last CTA, median CTA): %s" % (rank, world, np.round(np.median(np.array(instep), axis=0), 2)))
 print("rank %d world %d spans us (mesh, flux, flux without its last CTA): %s" % (rank, world, np.round(np.median(np.array(spans), axis=0), 2)))
 if rank == 0:
     print(json.dumps(res, indent=1))

@@ -321,19 +321,19 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
         for (int u = 0; u < RPI; ++u) {
           if (u > 0 && r0 + u >= nrows) break;
           const MeshRow mr = s_row[rr[u]];
+          const int special = last == 0 ? special_j : (mr.flags | zlast);
+          if (special == 0) {                       // the common case: one test, two 256-bit stores
+            mesh_store_point<N, true>(dst_col + mr.base, w[u]);
+            continue;
+          }
           const int zm = mr.flags & 15;
           if (last == 0 || (zm & (zm - 1))) {
-            const int special = last == 0 ? special_j : (mr.flags | zlast);
-            if (special == 0) {
-              mesh_store_point<N, true>(dst_col + mr.base, w[u]);
-            } else {
-              EigRows<N> eg;
+            EigRows<N> eg;
 #pragma unroll
-              for (int b = 0; b < N; ++b)
+            for (int b = 0; b < N; ++b)
 #pragma unroll
-                for (int o = 0; o < N; ++o) eg.w[b][o] = w[u][b][o];
-              mesh_store_special<N>(eg, out, s_pbc0, mr.base + (long long)j * gs_last, special & 15, special & 256);
-            }
+              for (int o = 0; o < N; ++o) eg.w[b][o] = w[u][b][o];
+            mesh_store_special<N>(eg, out, s_pbc0, mr.base + (long long)j * gs_last, special & 15, special & 256);
           } else {
             if (mr.flags & 256) {                   // closing row of a shard: the axis-0 image of global row 0
 #pragma unroll
