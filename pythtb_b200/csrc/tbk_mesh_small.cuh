@@ -135,7 +135,9 @@ struct MeshRow {                                    // per mesh row (outer index
 // Gauge: the stored Convention-I eigenvector is  d_0(k) * D(k)^H u_II, i.e. component o carries
 // exp(-2 pi i k.(tau_o - tau_0)): the overall phase of an eigenvector is arbitrary (LAPACK's is too),
 // and this choice needs N-1 instead of N phase factors per k-point.
-template <int N, int NPH, int MINB, int RPI>
+// EXACT: the model has exactly NPH phases (compile-time trip count: no per-phase test splits the basic block in
+// which the RPI independent rows interleave).
+template <int N, int NPH, int MINB, int RPI, bool EXACT = false>
 __global__ void __launch_bounds__(kMeshThreads, MINB)
 mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__ KSrc ks,
                   const __grid_constant__ OutSpec out, const __grid_constant__ MeshTiling tl, int gauge,
@@ -162,7 +164,7 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
   }
   const int nd = out.nd;
   const int last = nd - 1;
-  const int nph = ds.nph;   // phases p >= nph are skipped (uniform predicate)
+  const int nph = EXACT ? NPH : ds.nph;   // phases p >= nph are skipped (uniform predicate)
   const int tid = threadIdx.x;
   const long long gs_last = out.gstride[last];
   double gmin[N - 1];

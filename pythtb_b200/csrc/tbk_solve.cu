@@ -899,13 +899,8 @@ static int launch_mesh_small(const tbk_model* m, const KSrc& ks, const OutSpec& 
   tl.closing_g = ks.closing_g;
   const bool p4 = ds.nph <= 4;
   // one balanced wave: #SM x (CTAs resident per SM) persistent CTAs, each with an equal share of rows.
-  // n = 2 variants (resident CTAs per SM, rows per loop iteration); TBK_MESH_VARIANT is a tuning knob.
-  int variant = 0;
-  if (n == 2 && p4) { const char* e = getenv("TBK_MESH_VARIANT"); if (e) variant = atoi(e); }
-  static const int kOcc2[] = {4, 6, 5, 4, 3, 5};
-  static const int kVariants2 = 6;
-  if (variant < 0 || variant >= kVariants2) variant = 0;
-  int occ = n == 2 ? (p4 ? kOcc2[variant] : 4) : (n == 3 ? 3 : 2);
+  // resident CTAs per SM: n = 2: 4 (x 2 rows in flight per thread; 3, 5 and 6 CTAs and 1 row measured slower, profiles/README.md r02)
+  int occ = n == 2 ? 4 : (n == 3 ? 3 : 2);
   if (n == 4 && p4) { const char* e = getenv("TBK_MESH_VARIANT4"); const int v4 = e ? atoi(e) : 0; occ = v4 == 1 ? 2 : (v4 == 2 ? 4 : 3); }
   long long want = (long long)kNumSM * occ;
   // at least ~4 rows per CTA so the per-CTA sincospi prologue stays amortised
@@ -937,16 +932,13 @@ static int launch_mesh_small(const tbk_model* m, const KSrc& ks, const OutSpec& 
 #define TBK_MESH_LAUNCH(NN, PP, MB, RP) \
   mesh_small_kernel<NN, PP, MB, RP><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview, cta_trace_buffer())
   if (n == 2) {
-    if (p4) {
-      switch (variant) {
-        case 1: TBK_MESH_LAUNCH(2, 4, 6, 1); break;
-        case 2: TBK_MESH_LAUNCH(2, 4, 5, 1); break;
-        case 3: TBK_MESH_LAUNCH(2, 4, 4, 1); break;
-        case 4: TBK_MESH_LAUNCH(2, 4, 3, 2); break;
-        case 5: TBK_MESH_LAUNCH(2, 4, 5, 2); break;
-        default: TBK_MESH_LAUNCH(2, 4, 4, 2); break;
-      }
-    } else TBK_MESH_LAUNCH(2, 8, 4, 1);
+    switch (ds.nph) {                               // exact phase counts for the headline case (Haldane: 3)
+      case 1: mesh_small_kernel<2, 1, 4, 2, true><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview, cta_trace_buffer()); break;
+      case 2: mesh_small_kernel<2, 2, 4, 2, true><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview, cta_trace_buffer()); break;
+      case 3: mesh_small_kernel<2, 3, 4, 2, true><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview, cta_trace_buffer()); break;
+      case 4: mesh_small_kernel<2, 4, 4, 2, true><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview, cta_trace_buffer()); break;
+      default: TBK_MESH_LAUNCH(2, 8, 4, 1); break;
+    }
   }
   else if (n == 3) { if (p4) TBK_MESH_LAUNCH(3, 4, 3, 1); else TBK_MESH_LAUNCH(3, 8, 3, 1); }
   else {
