@@ -35,6 +35,11 @@ unsigned* take_ticket() {
   return g_tickets[dev] + slot;
 }
 
+static thread_local DoneSignal g_done_req = {nullptr, 0};
+void post_done_request(const DoneSignal& d) { g_done_req = d; }
+DoneSignal take_done_request() { const DoneSignal d = g_done_req; g_done_req.flag = nullptr; return d; }
+bool done_request_pending() { return g_done_req.flag != nullptr; }
+
 unsigned long long* cta_trace_buffer() {
   static int on = -1;
   static unsigned long long* buf = nullptr;
@@ -292,6 +297,7 @@ int tbk_solve_grid_prepare(const tbk_model* m, const double* start_k, const int3
   std::vector<double> sk(start_k, start_k + nd);
   std::vector<int32_t> ms(mesh, mesh + nd);
   tbk_prepared* p = new tbk_prepared();
+  p->done_flag = nullptr; p->done_seq = 0;
   p->run = [=](void* stream) {
     return tbk_solve_grid_x(m, sk.data(), ms.data(), nd, row0, nrows, wrap0, wfs_dev, pbc_phase_dev, gaps_dev, ws_dev,
                             ws_bytes, peer, stream);
@@ -306,6 +312,7 @@ int tbk_flux_plane_prepare(const tbk_wf_view* view, const int64_t* slice_off_dev
   if (!view || !out) { set_error("tbk_flux_plane_prepare: bad argument"); return TBK_ERR_ARG; }
   const tbk_wf_view v = *view;
   tbk_prepared* p = new tbk_prepared();
+  p->done_flag = nullptr; p->done_seq = 0;
   p->run = [=](void* stream) {
     return tbk_flux_plane_x(&v, slice_off_dev, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, ws_dev, ws_bytes,
                             peer, stream);
@@ -316,13 +323,48 @@ int tbk_flux_plane_prepare(const tbk_wf_view* view, const int64_t* slice_off_dev
 
 int tbk_prepared_run(tbk_prepared* p, void* stream, int32_t sync) {
   if (!p || !p->run) { set_error("tbk_prepared_run: null handle"); return TBK_ERR_ARG; }
+  static int spin = -1;                 // TBK_SPIN_SYNC=0: always wait with cudaStreamSynchronize (A/B knob)
+  if (spin < 0) { const char* e = getenv("TBK_SPIN_SYNC"); spin = (e && atoi(e) == 0) ? 0 : 1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (sync && spin) {
+    if (!p->done_flag) {
+      if (cudaHostAlloc((void**)&p->done_flag, sizeof(unsigned long long), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+        cudaGetLastError();
+        p->done_flag = nullptr;
+      } else {
+        *p->done_flag = 0;
+      }
+    }
+    if (p->done_flag) post_done_request(DoneSignal{p->done_flag, ++p->done_seq});
+  }
   const int rc = p->run(stream);
+  const bool signalled = sync && spin && p->done_flag && !done_request_pending();   // a launcher took the request
+  take_done_request();
   if (rc != TBK_OK) return rc;
-  if (sync) TBK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (!sync) return TBK_OK;
+  if (signalled) {
+    // spin on the pinned word; every few thousand polls make sure the stream is still alive (a failed
+    // kernel would never write it)
+    volatile unsigned long long* f = p->done_flag;
+    const unsigned long long want = p->done_seq;
+    for (unsigned n = 1; *f != want; ++n) {
+      if ((n & 0x3fff) == 0) {
+        const cudaError_t q = cudaStreamQuery(st);
+        if (q == cudaSuccess) break;                         // finished (the word is written by now or never)
+        if (q != cudaErrorNotReady) return cuda_fail(q, "cudaStreamQuery");
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    if (*f == want) return TBK_OK;
+  }
+  TBK_CUDA(cudaStreamSynchronize(st));
   return TBK_OK;
 }
 
 int tbk_prepared_destroy(tbk_prepared* p) {
+  if (p && p->done_flag) cudaFreeHost(p->done_flag);
   delete p;
   return TBK_OK;
 }

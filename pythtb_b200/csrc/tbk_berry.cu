@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kFluxThreads, (NOCC == 1 && N == 2) ? 5 : 1)  
 flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0, long long stride0, long long n1,
                  long long stride1, FluxTiling tl, long long nslice, double* __restrict__ plaq,
                  double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ total,
-                 const __grid_constant__ PeerView peer, unsigned long long* __restrict__ trace) {
+                 const __grid_constant__ PeerView peer, unsigned long long* __restrict__ trace, const DoneSignal done) {
   __shared__ double s_red[kFluxThreads / 32];
   __shared__ double s_fin[kPeerMaxVals];
   __shared__ int s_last;
@@ -418,7 +418,9 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
   if (peer.nranks > 1) {                                  // sum over the ranks, through the peers' mailboxes
     __syncthreads();
     peer_allreduce(peer, s_fin, (int)nslice, 0, total, &s_last);
+    __syncthreads();                                      // total[] was written by threads 0 .. nslice-1
   }
+  if (tid == 0) signal_done(done);                        // single rank: thread 0 wrote total[] itself
   cta_trace_end(trace, t_begin);
 }
 
@@ -461,12 +463,14 @@ static int launch_flux_rows(const WfView& v, const long long* off, long long nsl
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
   double* part_arg = plaq ? (total ? partial : nullptr) : partial;
   unsigned long long* trace = cta_trace_buffer();
+  // a synchronous prepared call waits on a pinned word the last CTA writes after the totals
+  const DoneSignal done = total ? take_done_request() : DoneSignal{nullptr, 0};
   if (plaq)
     TBK_CUDA(cudaLaunchKernelEx(&cfg, flux_rows_kernel<NOCC, N, true>, v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
-                                part_arg, ticket, total, pview, trace));
+                                part_arg, ticket, total, pview, trace, done));
   else
     TBK_CUDA(cudaLaunchKernelEx(&cfg, flux_rows_kernel<NOCC, N, false>, v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
-                                part_arg, ticket, total, pview, trace));
+                                part_arg, ticket, total, pview, trace, done));
   TBK_LAUNCH_CHECK("flux_rows_kernel");
   return TBK_OK;
 }

@@ -57,6 +57,28 @@ __device__ __forceinline__ void cta_trace_end(unsigned long long* trace, unsigne
 }
 #endif
 
+// Completion signal for a synchronous prepared call: the kernel that writes the call's (pinned-host) results
+// also writes `seq` to a pinned host word after them (system-scope fence in between), and the host spins on
+// that word instead of on cudaStreamSynchronize — the results are usable ~1 us after the last store instead of
+// after the stream's completion semaphore has made its way through the driver.  tbk_prepared_run posts a
+// request (thread-local); a launcher whose kernel supports the signal takes it.
+struct DoneSignal {
+  unsigned long long* flag;           // nullptr: no signal
+  unsigned long long seq;
+};
+void post_done_request(const DoneSignal& d);
+DoneSignal take_done_request();        // returns the pending request (flag == nullptr if none) and clears it
+bool done_request_pending();
+#if defined(__CUDACC__)
+// by ONE thread, after the results it (or, behind a __syncthreads, its CTA) wrote
+__device__ __forceinline__ void signal_done(const DoneSignal& d) {
+  if (d.flag) {
+    __threadfence_system();
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(d.flag), "l"(d.seq) : "memory");
+  }
+}
+#endif
+
 constexpr int kNumSM = 148;           // B200
 constexpr int kMaxSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
 
@@ -153,6 +175,8 @@ struct tbk_model {
 // The opaque prepared call of tbk.h: the bound arguments of one entry point
 struct tbk_prepared {
   std::function<int(void*)> run;     // re-issues the call on the given stream
+  unsigned long long* done_flag;     // pinned host word of the completion signal (allocated on first synchronous run)
+  unsigned long long done_seq;
 };
 
 // The opaque peer group of tbk.h: this rank's mailbox and the IPC mappings of the others

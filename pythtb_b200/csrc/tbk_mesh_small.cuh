@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kMeshThreads, MINB)
 mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__ KSrc ks,
                   const __grid_constant__ OutSpec out, const __grid_constant__ MeshTiling tl, int gauge,
                   double* __restrict__ gap_partial, unsigned* __restrict__ ticket, double* __restrict__ gaps_out,
-                  const __grid_constant__ PeerView peer, unsigned long long* __restrict__ trace) {
+                  const __grid_constant__ PeerView peer, unsigned long long* __restrict__ trace, const DoneSignal done) {
   constexpr int NP = N * (N + 1) / 2;
   constexpr int NG = N - 1;                         // relative gauge factors of states 1..N-1
   constexpr int NQ = NPH + NG;
@@ -406,7 +406,9 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
     __syncthreads();                                // or deferred: kept local until the next exchange carries it
     if (peer.defer) { if (tid < N - 1) peer.local[tid] = s_fin[tid]; }
     else peer_allreduce(peer, s_fin, N - 1, 1, gaps_out, &s_last);
+    __syncthreads();                                // gaps_out was written by threads 0 .. N-2
   }
+  if (tid == 0) signal_done(done);                  // single rank: thread 0 wrote gaps_out itself
   cta_trace_end(trace, t_begin);
 }
 

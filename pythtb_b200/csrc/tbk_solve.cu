@@ -929,14 +929,17 @@ static int launch_mesh_small(const tbk_model* m, const KSrc& ks, const OutSpec& 
   if (peer && peer->pending.nv > 0) { if (int rc = peer_flush(peer, st)) return rc; }   // an unclaimed deferred reduction
   const PeerView pview = !gaps_dev ? peer_next(nullptr)
                          : (peer && peer->defer_next ? peer_next_deferred(peer, n - 1, 1, gaps_dev) : peer_next(peer));
+  // a synchronous prepared call waits on a pinned word this kernel's last CTA writes after the gaps
+  // (not for a deferred reduction: the gaps are then completed by a later kernel)
+  const DoneSignal done = (gaps_dev && !pview.defer) ? take_done_request() : DoneSignal{nullptr, 0};
 #define TBK_MESH_LAUNCH(NN, PP, MB, RP) \
-  mesh_small_kernel<NN, PP, MB, RP><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview, cta_trace_buffer())
+  mesh_small_kernel<NN, PP, MB, RP><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview, cta_trace_buffer(), done)
   if (n == 2) {
     switch (ds.nph) {                               // exact phase counts for the headline case (Haldane: 3)
-      case 1: mesh_small_kernel<2, 1, 4, 2, true><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview, cta_trace_buffer()); break;
-      case 2: mesh_small_kernel<2, 2, 4, 2, true><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview, cta_trace_buffer()); break;
-      case 3: mesh_small_kernel<2, 3, 4, 2, true><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview, cta_trace_buffer()); break;
-      case 4: mesh_small_kernel<2, 4, 4, 2, true><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview, cta_trace_buffer()); break;
+      case 1: mesh_small_kernel<2, 1, 4, 2, true><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview, cta_trace_buffer(), done); break;
+      case 2: mesh_small_kernel<2, 2, 4, 2, true><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview, cta_trace_buffer(), done); break;
+      case 3: mesh_small_kernel<2, 3, 4, 2, true><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview, cta_trace_buffer(), done); break;
+      case 4: mesh_small_kernel<2, 4, 4, 2, true><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview, cta_trace_buffer(), done); break;
       default: TBK_MESH_LAUNCH(2, 8, 4, 1); break;
     }
   }
