@@ -111,6 +111,12 @@ int tbk_solve_k(const tbk_model* model, const double* k_dev, int64_t nk,
                 double* evec_dev, int64_t vc_sb, int64_t vc_sk,
                 void* ws_dev, size_t ws_bytes, void* stream);
 
+/* tb_model.k_uniform_mesh (pythtb.py:1792-1861) on the device: k_dev[nk][nd], nk = prod(mesh), point
+ * (i_0/mesh[0], i_1/mesh[1], ...) at the C-order index of (i_0, i_1, ...) — the same doubles as numpy's
+ * arange(n)/float(n).  Lets solve_all run on a dense mesh (256^3 = 16.8 M points = 403 MB of k) without
+ * building the list on the host and shipping it over PCIe. */
+int tbk_kmesh_uniform(const int32_t* mesh_host, int32_t nd, double* k_dev, void* stream);
+
 /* ------------------------------------------------------------------------
  * wf_array.solve_on_grid + impose_pbc (pythtb.py:2421-2532, 2674-2749).
  * k = start_k[d] + i_d/(mesh[d]-1) is generated on the device

@@ -27,6 +27,14 @@ t = timeit(lambda: m8.solve_all(k))
 m8o = M.random_model(oracle_api, norb=8, dim=3, nhop=300, nspin=1, seed=8)
 t0 = time.perf_counter(); orc.solve_all(m8o, k[:4096]); tc = time.perf_counter() - t0
 out["cfg3_n8_nhop300_solve_all_64^3"] = {"gpu_kpts_per_s": len(k) / t, "cpu1_kpts_per_s": 4096 / tc}
+# config 3 at full scale: the same model on the 256^3 mesh of BASELINE configs[2] (16.8 M k-points), k generated on the device
+for nhop, tag in ((300, "nhop300"), (2972, "nhop2972_silicon_size")):
+    mm = M.random_model(tb, norb=8, dim=3, nhop=nhop, nspin=1, seed=8)
+    lazy = mm.k_uniform_mesh([256, 256, 256], lazy=True)
+    td = timeit(lambda: mm.solve_all(lazy, device_result=True), reps=2)
+    th = timeit(lambda: mm.solve_all(lazy), reps=1)
+    out["cfg3_n8_%s_solve_all_256^3" % tag] = {"nk": len(lazy), "gpu_kpts_per_s_device_result": len(lazy) / td,
+                                                "gpu_kpts_per_s_host_result": len(lazy) / th, "seconds_device_result": td}
 # config 4: BN ribbon: solve_on_grid + berry_phase of the lower half (determinant branch)
 for ncell, nk in ((100, 2369), (200, 1185)):
     rib = M.bn_ribbon(tb, ncell)

@@ -210,6 +210,25 @@ class B200Engine(object):
                                         _ptr(ws), ws.numel(), self.stream()))
         return ev, vec
 
+    def solve_all_mesh(self, model, mesh_size, eig_vectors, device_result=False):
+        """solve_all on tb_model.k_uniform_mesh(mesh_size) with the k-points generated on the device
+        (tbk_kmesh_uniform): nothing but the results crosses PCIe — and not even those with
+        ``device_result`` (torch tensors in the reference layouts)."""
+        torch = self.torch
+        nd = len(mesh_size)
+        nk = int(np.prod(mesh_size))
+        kd = torch.empty((nk, nd), dtype=torch.float64, device=self.device)
+        mesh = (ctypes.c_int32 * nd)(*[int(x) for x in mesh_size])
+        _lib.check(self.lib.tbk_kmesh_uniform(mesh, nd, _ptr(kd), self.stream()))
+        ev, vec = self.solve_all_device(model, kd, nk, eig_vectors)
+        if vec is not None and model._nspin == 2:
+            vec = vec.reshape(model._nsta, nk, model._norb, 2)
+        if device_result:
+            return (ev, vec) if eig_vectors else ev
+        if not eig_vectors:
+            return ev.cpu().numpy()
+        return ev.cpu().numpy(), vec.cpu().numpy()
+
     def solve_all(self, model, klist, eig_vectors):
         nk = klist.shape[0]
         if nk == 0:      # empty k-list: nothing to launch (reference returns empty arrays)

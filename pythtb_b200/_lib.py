@@ -21,7 +21,7 @@ SYMBOLS = [
     "tbk_impose_boundary", "tbk_flux_workspace", "tbk_flux_plane", "tbk_berry_workspace",
     "tbk_berry_strings", "tbk_position_matrix", "tbk_position_hwf_workspace", "tbk_position_hwf",
     "tbk_flush_l2", "tbk_halo_pack", "tbk_last_kernel", "tbk_launch_count", "tbk_peer_create", "tbk_peer_connect",
-    "tbk_peer_destroy", "tbk_solve_grid_x", "tbk_flux_plane_x", "tbk_stream_sync", "tbk_debug_profile", "tbk_debug_cta_trace", "tbk_solve_grid_prepare", "tbk_flux_plane_prepare", "tbk_prepared_run", "tbk_prepared_destroy",
+    "tbk_peer_destroy", "tbk_solve_grid_x", "tbk_flux_plane_x", "tbk_stream_sync", "tbk_debug_profile", "tbk_debug_cta_trace", "tbk_kmesh_uniform", "tbk_solve_grid_prepare", "tbk_flux_plane_prepare", "tbk_prepared_run", "tbk_prepared_destroy",
     "tbk_peer_barrier", "tbk_peer_defer", "tbk_peer_flush", "tbk_wilson_products", "tbk_wilson_workspace", "tbk_wilson_phases",
 ]
 
@@ -92,6 +92,7 @@ def load():
         "tbk_solve_grid_prepare": (ctypes.c_int, [V, c_double_p, c_int32_p, I32, I32, I32, I32, V, V, V, V, SZ, V, ctypes.POINTER(V)]),
         "tbk_flux_plane_prepare": (ctypes.c_int, [ctypes.POINTER(WfView), V, I64, I64, I64, I64, I64, V, V, V, SZ, V, ctypes.POINTER(V)]),
         "tbk_prepared_run": (ctypes.c_int, [V, V, I32]),
+        "tbk_kmesh_uniform": (ctypes.c_int, [c_int32_p, I32, V, V]),
         "tbk_prepared_destroy": (ctypes.c_int, [V]),
         "tbk_peer_defer": (ctypes.c_int, [c_void_p, c_int32]),
         "tbk_peer_flush": (ctypes.c_int, [c_void_p, c_void_p]),

@@ -45,6 +45,30 @@ struct OutSpec {
   unsigned long long* gaps_bits;   // [n-1] running min of non-negative doubles, or null
 };
 
+// tb_model.k_uniform_mesh (pythtb.py:1848-1857): point (i_0/n_0, i_1/n_1, ...) at C-order index of (i_0, i_1, ...)
+struct KMeshDesc {
+  int nd;
+  int n[TBK_MAX_DIM];
+};
+__global__ void __launch_bounds__(256)
+kmesh_uniform_kernel(const KMeshDesc md, long long nk, double* __restrict__ k) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nk) return;
+  long long rem = idx;
+  double v[TBK_MAX_DIM];
+#pragma unroll
+  for (int d = TBK_MAX_DIM - 1; d >= 0; --d) {
+    if (d < md.nd) {
+      const long long q = rem / md.n[d];
+      v[d] = (double)(rem - q * md.n[d]) / (double)md.n[d];
+      rem = q;
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < TBK_MAX_DIM; ++d)
+    if (d < md.nd) k[idx * md.nd + d] = v[d];
+}
+
 __device__ __forceinline__ void decode_index(long long idx, const OutSpec& o, int mi[TBK_MAX_DIM]) {
 #pragma unroll
   for (int d = TBK_MAX_DIM - 1; d >= 0; --d) {
@@ -812,6 +836,21 @@ int tbk_gen_ham(const tbk_model* m, const double* k_dev, int64_t nk, double* ham
   const long long blocks = nk < (long long)kNumSM * 8 ? nk : (long long)kNumSM * 8;
   gen_ham_kernel<<<(unsigned)blocks, 128, dyn, (cudaStream_t)stream>>>(m->pv, k_dev, nk, (cplx*)ham_dev);
   TBK_LAUNCH_CHECK("gen_ham_kernel");
+  return TBK_OK;
+}
+
+int tbk_kmesh_uniform(const int32_t* mesh, int32_t nd, double* k_dev, void* stream) {
+  if (!mesh || !k_dev || nd < 1 || nd > TBK_MAX_DIM) { set_error("tbk_kmesh_uniform: bad argument"); return TBK_ERR_ARG; }
+  KMeshDesc md;
+  long long nk = 1;
+  for (int d = 0; d < TBK_MAX_DIM; ++d) {
+    md.n[d] = d < nd ? mesh[d] : 1;
+    if (md.n[d] < 1) { set_error("tbk_kmesh_uniform: mesh sizes must be positive"); return TBK_ERR_ARG; }
+    nk *= md.n[d];
+  }
+  md.nd = nd;
+  kmesh_uniform_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, (cudaStream_t)stream>>>(md, nk, k_dev);
+  TBK_LAUNCH_CHECK("kmesh_uniform_kernel");
   return TBK_OK;
 }
 

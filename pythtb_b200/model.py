@@ -46,6 +46,27 @@ def _offdiag_approximation_warning_and_stop():
 """)
 
 
+class KMesh(object):
+    """A uniform k-mesh kept as its descriptor (``tb_model.k_uniform_mesh(mesh, lazy=True)``):
+    ``solve_all`` generates the points on the device instead of receiving a host
+    list (256^3 points are 403 MB of k-vectors).  ``np.asarray(kmesh)`` gives
+    exactly the array the reference's ``k_uniform_mesh`` returns (pythtb.py:1848-1857)."""
+
+    def __init__(self, mesh_size):
+        self.mesh_size = tuple(int(n) for n in mesh_size)
+        self.shape = (int(np.prod(self.mesh_size)), len(self.mesh_size))
+        self.ndim = 2
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __array__(self, dtype=None, copy=None):
+        axes = [np.arange(n) / float(n) for n in self.mesh_size]
+        grids = np.meshgrid(*axes, indexing="ij")
+        out = np.stack([g.reshape(-1) for g in grids], axis=-1)
+        return out if dtype is None else out.astype(dtype)
+
+
 class tb_model(object):
     """Tight-binding model; same constructor as pythtb.tb_model
     (pythtb.py:94-185): ``tb_model(dim_k, dim_r, lat=None, orb=None, per=None, nspin=1)``."""
@@ -343,10 +364,21 @@ class tb_model(object):
             out = out.reshape(self._nsta, self._norb, 2)
         return ev[0], out
 
-    def solve_all(self, k_list=None, eig_vectors=False):
+    def solve_all(self, k_list=None, eig_vectors=False, device_result=False):
         """pythtb.py:955-1079: ``eval[band,k]`` and ``evec[band,k,orb(,spin)]``
         (k axis dropped for dim_k == 0).  One fused assemble+diagonalise launch
-        for the whole list."""
+        for the whole list.  Extensions: ``k_list`` may be a ``KMesh`` descriptor
+        (``k_uniform_mesh(mesh, lazy=True)``; the points are generated on the device),
+        and with it ``device_result=True`` returns torch tensors instead of host arrays."""
+        if isinstance(k_list, KMesh):
+            if self._dim_k == 0 or k_list.shape[1] != self._dim_k:
+                raise Exception("\n\nk-vector of wrong shape!")
+            eng = self._engine()
+            if hasattr(eng, "solve_all_mesh"):
+                return eng.solve_all_mesh(self, k_list.mesh_size, eig_vectors, device_result)
+            k_list = np.asarray(k_list)
+        if device_result:
+            raise Exception("\n\ndevice_result needs a KMesh descriptor (k_uniform_mesh(mesh, lazy=True))")
         if k_list is None:
             if self._dim_k != 0:
                 raise Exception("\n\nHave to provide a k-vector!")
@@ -613,8 +645,10 @@ class tb_model(object):
         return ret
 
     # ------------------------------------------------------------ k-list helpers
-    def k_uniform_mesh(self, mesh_size):
-        """pythtb.py:1792-1861: all points (i/N1, j/N2, ...) in C order."""
+    def k_uniform_mesh(self, mesh_size, lazy=False):
+        """pythtb.py:1792-1861: all points (i/N1, j/N2, ...) in C order.
+        ``lazy=True`` (extension) returns a ``KMesh`` descriptor that ``solve_all``
+        expands on the device."""
         use = np.array(list(map(round, mesh_size)), dtype=int)
         if use.shape != (self._dim_k,):
             print(use.shape)
@@ -623,9 +657,9 @@ class tb_model(object):
             raise Exception("\n\nMesh must have positive non-zero number of elements.")
         if self._dim_k not in (1, 2, 3):
             raise Exception("\n\nUnsupported dim_k!")
-        axes = [np.arange(n) / float(n) for n in use]
-        grids = np.meshgrid(*axes, indexing="ij")
-        return np.stack([g.reshape(-1) for g in grids], axis=-1)
+        if lazy:
+            return KMesh(use)
+        return np.asarray(KMesh(use))
 
     def k_path(self, kpts, nk, report=True):
         """pythtb.py:1863-2026: piecewise-linear path with nearly equidistant

@@ -47,6 +47,35 @@ def test_host_argument_validation_without_gpu():
     assert lib.tbk_model_destroy(None) == 0
 
 
+def test_new_entry_points_validate_arguments_without_gpu():
+    """Prepared calls, the device k-mesh and the peer helpers reject bad arguments / are no-ops on NULL."""
+    from pythtb_b200 import _lib
+    lib = _lib.load()
+    out = ctypes.c_void_p(0)
+    assert lib.tbk_solve_grid_prepare(None, None, None, 2, 0, 4, 1, None, None, None, None, 0, None, ctypes.byref(out)) == -1
+    assert lib.tbk_flux_plane_prepare(None, None, 1, 4, 4, 4, 1, None, None, None, 0, None, ctypes.byref(out)) == -1
+    assert lib.tbk_prepared_run(None, None, 0) == -1
+    assert lib.tbk_prepared_destroy(None) == 0
+    assert lib.tbk_kmesh_uniform(None, 2, None, None) == -1
+    assert lib.tbk_peer_barrier(None, None) == 0 and lib.tbk_peer_flush(None, None) == 0 and lib.tbk_peer_defer(None, 1) == 0
+
+
+def test_lazy_k_mesh_is_the_reference_mesh():
+    """KMesh (k_uniform_mesh(..., lazy=True)) materialises to exactly the eager array (pythtb.py:1848-1857)."""
+    import numpy as np
+    import pythtb_b200
+    from pythtb_b200.model import KMesh
+    from tests import models as M
+    m = M.haldane(pythtb_b200)
+    eager = m.k_uniform_mesh([5, 7])
+    lazy = m.k_uniform_mesh([5, 7], lazy=True)
+    assert isinstance(lazy, KMesh) and lazy.shape == eager.shape == (35, 2) and len(lazy) == 35
+    assert np.array_equal(np.asarray(lazy), eager)
+    assert np.array_equal(eager[8], [1 / 5.0, 1 / 7.0])
+    with pytest.raises(Exception, match="Incorrect size"):
+        m.k_uniform_mesh([5, 7, 3], lazy=True)
+
+
 def test_product_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():

@@ -415,3 +415,24 @@ def test_replayed_calls_follow_their_arguments():
     b = wh.solve_on_grid([-0.5, -0.5])
     _, gaps_ref = orc.solve_on_grid(wh._model, mesh, [-0.5, -0.5])
     assert np.max(np.abs(b - gaps_ref)) < 1e-10 and abs(a[0] - b[0]) > 1e-3
+
+
+def test_solve_all_on_a_device_generated_mesh():
+    """solve_all(k_uniform_mesh(mesh, lazy=True)): k-points generated on the device (tbk_kmesh_uniform) give
+    exactly what the host list gives, for values, vectors (spinor layout included) and device-resident results."""
+    from oracle import pythtb_oracle as orc
+    mod = _mod()
+    for model, mesh in ((M.haldane(mod, delta=0.2), [12, 9]), (M.kane_mele(mod, "odd"), [7, 8]),
+                        (M.random_model(mod, norb=8, dim=3, nhop=40, nspin=1, seed=5), [5, 4, 6]),
+                        (M.random_model(mod, norb=3, dim=1, nhop=5, nspin=1, seed=22), [33])):
+        eager = model.k_uniform_mesh(mesh)
+        lazy = model.k_uniform_mesh(mesh, lazy=True)
+        ev_e, vec_e = model.solve_all(eager, eig_vectors=True)
+        ev_l, vec_l = model.solve_all(lazy, eig_vectors=True)
+        assert np.array_equal(ev_e, ev_l) and np.array_equal(vec_e, vec_l) and vec_l.shape == vec_e.shape
+        assert np.max(np.abs(model.solve_all(lazy) - orc.solve_all(model, eager))) < 1e-10
+        ev_d = model.solve_all(lazy, device_result=True)
+        assert ev_d.is_cuda and np.array_equal(ev_d.cpu().numpy(), ev_e)
+    with pytest.raises(Exception, match="wrong shape"):
+        M.haldane(mod).solve_all(M.kane_mele(mod, "odd").k_uniform_mesh([3, 3], lazy=True)[:0] if False else
+                                 M.random_model(mod, norb=3, dim=1, nhop=5, nspin=1, seed=22).k_uniform_mesh([4], lazy=True))
