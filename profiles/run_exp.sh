@@ -15,6 +15,5 @@ PY
 }
 for w in haldane kane_mele; do
   timeout 300 python bench.py --workload $w --steps 200 --warmup 5 --no-cpu > $OUT/bench_$w.json 2>$OUT/bench_$w.err; show $OUT/bench_$w.json
-  TBK_SPIN_SYNC=0 timeout 300 python bench.py --workload $w --steps 200 --warmup 5 --no-cpu > $OUT/bench_${w}_nospin.json 2>$OUT/bench_${w}_nospin.err; show $OUT/bench_${w}_nospin.json
 done
 TBK_CTA_TRACE=1 timeout 300 python profiles/cta_trace.py haldane > $OUT/cta_trace_haldane.json 2>$OUT/cta_trace_haldane.err; cat $OUT/cta_trace_haldane.json | head -120

@@ -112,11 +112,11 @@ flux_small_kernel(WfView v, const long long* __restrict__ slice_off, long long n
 // d=(i,j+1) and L(x,y) = det <x|y>,
 //     phase(i,j) = -arg[ L(a,b) L(b,c) L(c,d) L(d,a) ]
 // and L(c,d) = conj(V(i,j+1)), L(d,a) = conj(H(i,j)) where V(i,j) = L((i,j),(i+1,j)) is the
-// vertical and H(i,j) = L((i,j),(i,j+1)) the horizontal link.  A WARP owns 31 plaquette columns
-// and marches down `ti` rows: lane t computes V(i, col0+t) (32 of them; the right neighbour's comes
-// by shuffle) and H(i+1, col), which it keeps in a register for the next row, so each plaquette
-// costs two link determinants, there is no block barrier in the row loop, and the loads of row
-// i+2 are in flight while row i+1 is being reduced.
+// vertical and H(i,j) = L((i,j),(i,j+1)) the horizontal link.  A WARP owns up to 31 plaquette columns
+// and marches down its rows: lane t loads only ITS column's occupied states, computes V(i, col0+t)
+// (the right neighbour's comes by shuffle) and H(i+1, col) against the right neighbour's state (also by
+// shuffle), which it keeps in a register for the next row — two link determinants per plaquette, no
+// block barrier in the row loop, one or two rows of loads in flight while a row is being reduced.
 // When only the plane sum is wanted, plaquettes whose loop product z has Re z > 1/2 and
 // Re z > 8 |Im z| (|arg z| < 0.125) are multiplied together — at most 24 per product, so
 // |sum of args| < pi and arg(prod) = sum(arg) exactly — and ONE atan2 is taken per thread per tile;
@@ -217,7 +217,7 @@ __device__ __forceinline__ OccState<NOCC, N> shfl_down_state(const OccState<NOCC
 }
 
 template <int NOCC, int N, bool WANT_PLAQ>
-__global__ void __launch_bounds__(kFluxThreads, (NOCC == 1 && N == 2) ? 5 : 1)   // 5 CTAs / SM for the Haldane case (<= 102 registers)
+__global__ void __launch_bounds__(kFluxThreads, (NOCC == 1 && N == 2) ? 5 : (NOCC * N >= 6 ? 3 : 1))   // 5 CTAs / SM for the Haldane case (<= 102 registers), 3 for the 6- and 8-component states (<= 168)
 flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0, long long stride0, long long n1,
                  long long stride1, FluxTiling tl, long long nslice, double* __restrict__ plaq,
                  double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ total,
@@ -252,19 +252,21 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
     const int nrow = tl.hr + (rb < tl.rx ? 1 : 0);
     const cplx* pa = v.wfs + slice_off[s] + col * stride1 + i0 * stride0;  // u(i0, col)
     double acc = 0.0;
-    if constexpr (NOCC * N <= 4) {
-      // ---- small states: every lane loads ONLY its own column, two rows ahead (a rotation of four
-      // register slots: rows i, i+1, and i+2, i+3 in flight), and takes the right-hand neighbour's
-      // state for the horizontal link by shuffle.  The kernel is bound by the bytes a warp keeps in
-      // flight (per-CTA timeline + Little's law: one row ahead = 2 KB per warp = ~40 KB per SM gave
-      // ~3.9 TB/s); dropping the neighbour-column registers pays for the deeper prefetch.
-      OccState<NOCC, N> X[4];
+    {
+      // ---- every lane loads ONLY its own column, kSlots - 2 rows ahead (a rotation of kSlots register
+      // slots: rows i, i+1 and the rows in flight), and takes the right-hand neighbour's state for the
+      // horizontal link by shuffle.  The kernel is bound by the bytes a warp keeps in flight (per-CTA
+      // timeline + Little's law: one row ahead = 2 KB per warp = ~40 KB per SM gave ~3.9 TB/s for the
+      // 2-component state); dropping the neighbour-column registers pays for the deeper prefetch.
+      // Small states (nocc x n <= 4): two rows ahead; larger ones: one row ahead, the registers go to occupancy.
+      constexpr int kSlots = (NOCC * N <= 4) ? 4 : 3;
+      OccState<NOCC, N> X[kSlots];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) X[q].zero();             // lanes past the strip carry zeros, never garbage
+      for (int q = 0; q < kSlots; ++q) X[q].zero();        // lanes past the strip carry zeros, never garbage
       if (has_col) {
         X[0].load(pa, occ);
         X[1].load(pa + stride0, occ);
-        if (nrow >= 2) X[2].load(pa + 2 * stride0, occ);
+        if (kSlots == 4 && nrow >= 2) X[2].load(pa + 2 * stride0, occ);
       }
       cplx hda;                                            // L(d,a) = conj(H(i,col))
       {
@@ -273,16 +275,16 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
       }
       cplx prod = mk(1.0, 0.0);
       double* pq = WANT_PLAQ ? plaq + (s * p0 + i0) * p1 + col : nullptr;
-      const cplx* pf = pa + 3 * stride0;                   // row i0 + r + 3 at step r
+      const cplx* pf = pa + (kSlots - 1) * stride0;        // row i0 + r + kSlots - 1 at step r
 #pragma unroll 1
-      for (int r = 0; r < nrow; r += 4) {
+      for (int r = 0; r < nrow; r += kSlots) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kSlots; ++u) {
           if (r + u < nrow) {
-            if (has_col && r + u + 3 <= nrow) X[(u + 3) & 3].load(pf, occ);
+            if (has_col && r + u + kSlots - 1 <= nrow) X[(u + kSlots - 1) % kSlots].load(pf, occ);
             pf += stride0;
             const OccState<NOCC, N>& A = X[u];
-            const OccState<NOCC, N>& B = X[(u + 1) & 3];
+            const OccState<NOCC, N>& B = X[(u + 1) % kSlots];
             const cplx lab = link_det<NOCC, N>(A, B);      // V(i, col); junk in lanes without a column
             cplx right;                                    // V(i, col+1) from the next lane
             right.re = __shfl_down_sync(0xffffffffu, lab.re, 1);
@@ -307,72 +309,12 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
             }
           }
         }
-        if (!WANT_PLAQ && ((r + 4) % 24) == 0) {           // at most 24 small angles per product
+        if (!WANT_PLAQ && ((r + kSlots) % 24) == 0) {      // at most 24 small angles per product
           if (owner) acc += neg_arg(prod);
           prod = mk(1.0, 0.0);
         }
       }
       if (!WANT_PLAQ && owner) acc += neg_arg(prod);
-    } else {
-    // Register rotation instead of copies: (s0,s1,s2) take the roles (a, b, prefetch of next b) and
-    // (c0,c1) the roles (c, prefetch of next c); the roles advance every row, period 6.
-    OccState<NOCC, N> s0, s1, s2, c0, c1;
-    cplx hda = mk(1.0, 0.0);                               // L(d,a) = conj(H(i,col))
-    if (has_col) { s0.load(pa, occ); s1.load(pa + stride0, occ); }
-    if (owner) {
-      c1.load(pa + stride1, occ);                          // d of the first row
-      hda = conj(link_det<NOCC, N>(s0, c1));
-      c0.load(pa + stride0 + stride1, occ);
-    }
-    cplx prod = mk(1.0, 0.0);
-    double* pq = WANT_PLAQ ? plaq + (s * p0 + i0) * p1 + col : nullptr;
-    int r = 0;
-#define TBK_FLUX_STEP(A, B, BN, C, CN)                                                            \
-    {                                                                                             \
-      if (r >= nrow) break;                                                                       \
-      pa += stride0;                                       /* now u(i0+r+1, col) */               \
-      if (r + 1 < nrow) {                                  /* prefetch the next row */            \
-        if (has_col) BN.load(pa + stride0, occ);                                                  \
-        if (owner) CN.load(pa + stride0 + stride1, occ);                                          \
-      }                                                                                           \
-      cplx lab = mk(0.0, 0.0);                                                                    \
-      if (has_col) lab = link_det<NOCC, N>(A, B);          /* V(i, col) */                        \
-      cplx right;                                          /* V(i, col+1) from the next lane */   \
-      right.re = __shfl_down_sync(0xffffffffu, lab.re, 1);                                        \
-      right.im = __shfl_down_sync(0xffffffffu, lab.im, 1);                                        \
-      if (owner) {                                                                                \
-        const cplx lbc = link_det<NOCC, N>(B, C);          /* H(i+1, col) */                      \
-        cplx z = lab * lbc;                                                                       \
-        z = mulc(z, right);                                /* L(c,d) = conj(V(i, col+1)) */       \
-        z = z * hda;                                                                              \
-        hda = conj(lbc);                                                                          \
-        if (WANT_PLAQ) {                                                                          \
-          const double phase = neg_arg(z);                                                        \
-          pq[0] = phase;                                                                          \
-          pq += p1;                                                                               \
-          acc += phase;                                                                           \
-        } else if (z.re > 0.5 && z.re > 8.0 * fabs(z.im)) {                                       \
-          prod = prod * z;                                                                        \
-        } else {                                                                                  \
-          acc += neg_arg(z);                                                                      \
-        }                                                                                         \
-      }                                                                                           \
-      ++r;                                                                                        \
-    }
-    for (;;) {
-      TBK_FLUX_STEP(s0, s1, s2, c0, c1)
-      TBK_FLUX_STEP(s1, s2, s0, c1, c0)
-      TBK_FLUX_STEP(s2, s0, s1, c0, c1)
-      TBK_FLUX_STEP(s0, s1, s2, c1, c0)
-      TBK_FLUX_STEP(s1, s2, s0, c0, c1)
-      TBK_FLUX_STEP(s2, s0, s1, c1, c0)
-      if (!WANT_PLAQ && (r % 24) == 0) {                   // at most 24 small angles per product
-        if (owner) acc += neg_arg(prod);
-        prod = mk(1.0, 0.0);
-      }
-    }
-#undef TBK_FLUX_STEP
-    if (!WANT_PLAQ && owner) acc += neg_arg(prod);
     }
     if (partial) {
       // fixed-order warp sum -> partial[item]
