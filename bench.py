@@ -157,7 +157,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": _workload_name(args.workload, 1), "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
@@ -373,9 +373,9 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": total_k * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": _workload_name(args.workload, world), "norb": model._norb, "nspin": model._nspin,
+            "config": {"workload": _workload_name(args.workload, world), "arithmetic": "complex128 = pairs of f64", "norb": model._norb, "nspin": model._nspin,
                        "occ": occ, "mesh_per_gpu": [ROWS_PER_RANK, COLS], "l2": "256 MiB flush between steps (untimed); events per step, host kept ahead of the device"
                              + ("; device-side barrier over the ranks before every timed step (untimed)" if world > 1 else ""),
                        "parallelism": "mesh rows sliced over %d GPU(s)" % world,
