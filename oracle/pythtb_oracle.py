@@ -29,7 +29,7 @@ __all__ = [
     "solve_on_grid", "impose_pbc", "impose_loop", "one_berry_loop",
     "one_flux_plane", "berry_phase", "berry_flux", "no_2pi",
     "one_phase_cont", "array_phases_cont", "position_matrix",
-    "position_expectation", "position_hwf",
+    "position_expectation", "position_hwf", "convention_gauge",
 ]
 
 
@@ -38,7 +38,13 @@ __all__ = [
 # ----------------------------------------------------------------------------
 def gen_ham(model, k_list=None):
     """H(k) for a list of k-points; restates ``tb_model._gen_ham``
-    (pythtb.py:874-925), Convention I.
+    (pythtb.py:874-925), Convention I.  A model carrying ``_convention == 2``
+    (the ``pythtb_b200`` extension ``set_convention``; the reference has no
+    such attribute) gets the Convention-II matrix of
+    doc/formalism/pythtb-formalism.tex:341-344, i.e. the same sum without the
+    orbital positions in the phase.  UNPINNED by reference fixtures (1.8.0 does
+    not implement it); pinned instead on the identity tex:355-364 against the
+    Convention-I result, see ``convention_gauge``.
 
     Returns complex128 ``[nk, nsta, nsta]`` (spinor index = 2*orb+spin, the
     reshape of pythtb.py:933).  For dim_k == 0 pass ``k_list=None`` and get
@@ -65,6 +71,8 @@ def gen_ham(model, k_list=None):
         if model._dim_k > 0:
             ind_R = np.array(hop[3], dtype=float)
             rv = -model._orb[i, :] + model._orb[j, :] + ind_R   # :912
+            if getattr(model, "_convention", 1) == 2:
+                rv = ind_R                                      # tex:341-344
             rv = rv[per]                                        # :914
             phase = np.exp((2.0j) * np.pi * (kpts @ rv))        # :916
         else:
@@ -73,6 +81,17 @@ def gen_ham(model, k_list=None):
         ham[:, i, :, j, :] += blk                               # :920/:923
         ham[:, j, :, i, :] += blk.conj().transpose(0, 2, 1)     # :921/:924
     return ham.reshape(nk, nsta, nsta)
+
+
+def convention_gauge(model, k_list):
+    """D[k, j] = exp(2 pi i k.tau_j) per state (both spin components of an
+    orbital share tau_j): H~ = D H D^H element-wise H~_ij = D_i H_ij conj(D_j)
+    and C~_j = D_j C_j (doc/formalism/pythtb-formalism.tex:355-364) relate
+    Convention II (tilde) to the reference's Convention I."""
+    kpts = np.asarray(k_list, dtype=float).reshape(-1, model._dim_k)
+    tau = np.asarray(model._orb, dtype=float)[:, list(model._per)]
+    d = np.exp(2.0j * np.pi * (kpts @ tau.T))
+    return np.repeat(d, model._nspin, axis=1)
 
 
 def sol_ham(ham, eig_vectors=False):
@@ -158,7 +177,10 @@ def solve_on_grid(model, mesh_arr, start_k):
     if nsta > 1:
         gaps = (ev[:, 1:] - ev[:, :-1]).min(axis=0)             # :2484, :2529-2530
     for d in range(dim):                                        # :2486, :2496-2497
-        impose_pbc(wfs, model._orb, model._nspin, d, model._per[d])
+        if getattr(model, "_convention", 1) == 2:
+            impose_loop(wfs, d)                                 # C~(k+G) = C~(k), tex:341-364
+        else:
+            impose_pbc(wfs, model._orb, model._nspin, d, model._per[d])
     return wfs, gaps
 
 

@@ -251,11 +251,14 @@ class B200Engine(object):
     def new_store(self, shape):
         return DeviceStore(self, shape)
 
-    def pbc_phases(self, orb, nspin, k_dirs):
-        """exp(-2 pi i tau_j[k_dir]) per state (pythtb.py:2729-2736), [len(k_dirs), nsta]."""
+    def pbc_phases(self, orb, nspin, k_dirs, convention=1):
+        """exp(-2 pi i tau_j[k_dir]) per state (pythtb.py:2729-2736), [len(k_dirs), nsta];
+        Convention II eigenvectors are periodic in k (formalism tex:341-364): factor 1."""
         out = []
         for kd in k_dirs:
             ffac = np.exp(-2.0j * np.pi * np.asarray(orb)[:, kd])
+            if convention == 2:
+                ffac = np.ones_like(ffac)
             out.append(np.repeat(ffac, nspin))
         return np.array(out, dtype=complex)
 
@@ -307,7 +310,7 @@ class B200Engine(object):
         phase = cache.get(("pbc", nd))
         if phase is None:
             phase = cache[("pbc", nd)] = self.to_dev(
-                self.pbc_phases(model._orb, model._nspin, [model._per[d] for d in range(nd)]))
+                self.pbc_phases(model._orb, model._nspin, [model._per[d] for d in range(nd)], model._convention))
         gaps = gaps_h = None
         if n > 1 and want_gaps:
             if host_result:

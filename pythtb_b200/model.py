@@ -123,6 +123,7 @@ class tb_model(object):
             raise Exception("\n\nWrong value of nspin, must be 1 or 2!")
         self._nspin = nspin
         self._assume_position_operator_diagonal = True
+        self._convention = 1
         self._nsta = self._norb * self._nspin
         if nspin == 1:
             self._site_energies = np.zeros(self._norb, dtype=float)
@@ -323,8 +324,28 @@ class tb_model(object):
                                   "(SURVEY.md §2: out of scope); use the reference for plotting")
 
     # ------------------------------------------------------------- the hot path
-    def _plan(self, convention=1):
+    def set_convention(self, convention):
+        """Extension (not in PythTB 1.8.0, which implements Convention I only):
+        choose the Bloch-phase convention of doc/formalism/pythtb-formalism.tex.
+        1 = H_ij(k) = sum_R e^{ik.(R+tau_j-tau_i)} H_ij(R)   (tex:300-304, pythtb.py:912-916),
+        2 = H~_ij(k) = sum_R e^{ik.R} H_ij(R)                 (tex:341-344).
+        Eigenvalues are the same; eigenvectors are related by C~_j = e^{ik.tau_j} C_j
+        (tex:355-364) and are periodic in k, so ``wf_array`` closes a periodic
+        mesh direction with a plain copy instead of the e^{-iG.tau_j} factor of
+        tex:688-691 / pythtb.py:2729."""
+        if convention not in (1, 2):
+            raise Exception("\n\nconvention must be 1 (PythTB, orbital positions in the phase) or 2")
+        if convention != self._convention:
+            self._convention = convention
+            self._touch()
+
+    def get_convention(self):
+        return self._convention
+
+    def _plan(self, convention=None):
         from ._plan import compile_plan
+        if convention is None:
+            convention = self._convention
         if self._plan_cache is None or self._plan_cache[0] != convention:
             self._plan_cache = (convention, compile_plan(self, convention))
         return self._plan_cache[1]
@@ -429,6 +450,7 @@ class tb_model(object):
         fin_per = [p for p in self._per if p != fin_dir]
         fin = self.__class__(self._dim_k - 1, self._dim_r, copy.deepcopy(self._lat), fin_orb, fin_per, self._nspin)
         fin._assume_position_operator_diagonal = self._assume_position_operator_diagonal
+        fin._convention = self._convention
         fin.set_onsite(onsite, mode="reset")
         ntot = self._norb * num
         for c in range(num):
@@ -558,6 +580,7 @@ class tb_model(object):
                 sc_orb.append(to_sc(o + np.array(cur, dtype=float)))
         sc = self.__class__(self._dim_k, self._dim_r, sc_cart_lat, sc_orb, per=self._per, nspin=self._nspin)
         sc._assume_position_operator_diagonal = self._assume_position_operator_diagonal
+        sc._convention = self._convention
         lookup = {tuple(int(x) for x in v): n for n, v in enumerate(sc_vec)}
         for icur, cur in enumerate(sc_vec):
             for i in range(self._norb):

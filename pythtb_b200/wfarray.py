@@ -232,7 +232,7 @@ class wf_array(object):
             # rank multiplied by the pbc phase (pythtb.py:2729, 2740-2741)
             phase = None
             if sh.rank == 0:
-                phase = eng.pbc_phases(self._orb, self._nspin, [self._model._per[0]])[0]
+                phase = eng.pbc_phases(self._orb, self._nspin, [self._model._per[0]], self._model._convention)[0]
             eng.halo_ring_shift(self._store, self._dim_arr, phase, sh.rank, sh.nranks)
         return gaps
 
@@ -296,13 +296,14 @@ class wf_array(object):
 
     # --------------------------------------------------- boundary conditions
     def impose_pbc(self, mesh_dir, k_dir):
-        """pythtb.py:2674-2749: last slice := first slice * exp(-2 pi i tau_j[k_dir])."""
+        """pythtb.py:2674-2749: last slice := first slice * exp(-2 pi i tau_j[k_dir])
+        (a plain copy for a Convention-II model, ``tb_model.set_convention``)."""
         if k_dir not in self._model._per:
             raise Exception("Periodic boundary condition can be specified only along periodic directions!")
         if mesh_dir < 0 or mesh_dir >= self._dim_arr or mesh_dir > 3:
             raise Exception("\n\nWrong value of mesh_dir.")
         eng = self._model._engine()
-        phase = eng.pbc_phases(self._orb, self._nspin, [k_dir])[0]
+        phase = eng.pbc_phases(self._orb, self._nspin, [k_dir], self._model._convention)[0]
         eng.impose_boundary(self._store, self._dim_arr, mesh_dir, phase)
 
     def impose_loop(self, mesh_dir):

@@ -50,7 +50,9 @@ class OracleEngine(object):
             return res[0][:, None], res[1][:, None]
         return orc.solve_all(model, klist, eig_vectors)
 
-    def pbc_phases(self, orb, nspin, k_dirs):
+    def pbc_phases(self, orb, nspin, k_dirs, convention=1):
+        if convention == 2:
+            return np.ones((len(k_dirs), np.asarray(orb).shape[0] * nspin), dtype=complex)
         return np.array([np.repeat(np.exp(-2.0j * np.pi * np.asarray(orb)[:, kd]), nspin) for kd in k_dirs])
 
     def solve_grid(self, model, store, mesh_arr, start_k, row0=0, nrows=None, wrap0=1, want_gaps=True, host_result=False,
