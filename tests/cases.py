@@ -260,6 +260,139 @@ def case_position(mod):
     return out
 
 
+def case_more_bands(mod):
+    """The remaining band-structure regression scripts of the reference:
+    tests/test_examples/buckling/buckled_layer/run.py:21-40 (dim_k 2 of dim_r 3),
+    buckling/trestle/run.py:17-35 (per=[0], complex hoppings, k_path("fullc")),
+    graphene/graphene/run.py:17-34 (touching bands at K),
+    supercell/supercell/run.py:8-27 (make_supercell + cut_piece, k_path("full")),
+    zero_dim/0dim/run.py:8-33 (0-D, four orbitals)."""
+    out = {}
+    m = mod.tb_model(2, 3, [[1.0, 0.0, 0.0], [0.0, 1.25, 0.0], [0.0, 0.0, 3.0]],
+                     [[0.0, 0.0, -0.15], [0.5, 0.5, 0.15]])
+    m.set_onsite([-1.1, 1.1])
+    for R in ([0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]):
+        m.set_hop(0.6, 1, 0, R)
+    k_vec, _, _ = m.k_path([[0.0, 0.0], [0.0, 0.5], [0.5, 0.5], [0.0, 0.0]], 81, report=False)
+    out["evals_buckled"] = m.solve_all(k_vec)
+    m = mod.tb_model(1, 2, [[2.0, 0.0], [0.0, 1.0]], [[0.0, 0.0], [0.5, 1.0]], per=[0])
+    m.set_hop(2.0, 0, 0, [1, 0])
+    m.set_hop(2.0, 1, 1, [1, 0])
+    m.set_hop(0.8 + 0.6j, 0, 1, [0, 0])
+    m.set_hop(0.8 + 0.6j, 1, 0, [1, 0])
+    k_vec, _, _ = m.k_path("fullc", 100, report=False)
+    out["evals_trestle"] = m.solve_all(k_vec)
+    g = M.graphene(mod, delta=0.0)
+    k_vec, _, _ = g.k_path([[0.0, 0.0], [2.0 / 3.0, 1.0 / 3.0], [0.5, 0.5], [0.0, 0.0]], 121, report=False)
+    out["evals_graphene"] = g.solve_all(k_vec)
+    sc = g.make_supercell([[2, 1], [-1, 2]], to_home=True)
+    slab = sc.cut_piece(6, 1, glue_edgs=False)
+    k_vec, _, _ = slab.k_path("full", 100, report=False)
+    out["evals_supercell"] = slab.solve_all(k_vec)
+    sq32 = np.sqrt(3.0) / 2.0
+    m = mod.tb_model(0, 3, np.identity(3).tolist(),
+                     [[(2.0 / 3.0) * sq32, 0.0, 0.0], [(-1.0 / 3.0) * sq32, 0.5, 0.0],
+                      [(-1.0 / 3.0) * sq32, -0.5, 0.0], [0.0, 0.0, 1.0]])
+    m.set_onsite([-0.5, -0.5, -0.5, 0.5])
+    for i, j in ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)):
+        m.set_hop(1.0, i, j)
+    out["evals_0dim"] = m.solve_all()
+    return out
+
+
+def case_haldane_finite(mod):
+    """Finite Haldane flakes, 0-D models of 200 and 800 orbitals:
+    tests/test_examples/haldane/edge/run.py:35-50 (10x10, with eigenvectors) and
+    haldane/haldane_fin/run.py:37-52 (20x20, glued or not).  The raw eigenvectors of
+    the reference golden are gauge dependent; the projector on the lower half of the
+    spectrum stands in for them."""
+    hal = M.haldane(mod, delta=0.0)
+    out = {}
+    # occupied sets end below a real gap: the glued flake has its two mid-gap levels 5.7e-6 apart
+    # (levels 99, 100), so the projector on 100 states would amplify rounding by 1e5
+    for tag, glue, nocc in (("", False, 100), ("_half", True, 99)):
+        fin = hal.cut_piece(10, 0, glue_edgs=glue).cut_piece(10, 1, glue_edgs=False)
+        ev, evec = fin.solve_all(eig_vectors=True)
+        out["evals_edge" + tag] = ev
+        out["proj_edge" + tag] = _projector(evec, list(range(nocc)))[:48, :48]    # a corner block keeps the fixture small
+    out["evals_fin_false"] = hal.cut_piece(20, 0, glue_edgs=False).cut_piece(20, 1, glue_edgs=False).solve_all().flatten()
+    out["evals_fin_true"] = hal.cut_piece(20, 0, glue_edgs=True).cut_piece(20, 1, glue_edgs=True).solve_all().flatten()
+    return out
+
+
+def _mask_close(vals, evals, tol=1.0e-3):
+    """Per-state expectation values are only defined up to the mixing inside a
+    (near-)degenerate level: zero the entries whose level has a neighbour closer than tol
+    (the reference's own test_spin fails for exactly this reason)."""
+    ev = np.asarray(evals, dtype=float)
+    gap = np.full(ev.shape, np.inf)
+    d = np.diff(ev, axis=0)
+    gap[1:] = np.minimum(gap[1:], d)
+    gap[:-1] = np.minimum(gap[:-1], d)
+    return np.where(gap > tol, np.asarray(vals, dtype=float), 0.0)
+
+
+def case_haldane_hwf(mod):
+    """tests/test_examples/haldane/haldane_hwf/run.py:37-94: Berry phase flow of the bulk
+    against the hybrid Wannier centres / position expectations of a ribbon, with an occupied
+    set that changes along k (the edge state crosses the Fermi level)."""
+    m = mod.tb_model(2, 2, M._HEX_LAT, M._HEX_ORB)
+    delta, t, t2 = -0.2, -1.0, 0.05 - 0.15j
+    m.set_onsite([-delta, delta])
+    m.set_hop(t, 0, 1, [0, 0])
+    m.set_hop(t, 1, 0, [1, 0])
+    m.set_hop(t, 1, 0, [0, 1])
+    for amp, i, R in ((t2, 0, [1, 0]), (t2, 1, [1, -1]), (t2, 1, [0, 1]),
+                      (t2.conjugate(), 1, [1, 0]), (t2.conjugate(), 0, [1, -1]), (t2.conjugate(), 0, [0, 1])):
+        m.set_hop(amp, i, i, R)
+    len_0, len_1, efermi = 100, 10, 0.25
+    w = mod.wf_array(m, [len_0, len_1])
+    out = dict(gaps=w.solve_on_grid([0.0, 0.0]))
+    out["phi1"] = w.berry_phase(occ=[0], dir=1, contin=True)
+    rib = m.cut_piece(len_1, fin_dir=1, glue_edgs=False)
+    k_vec, _, _ = rib.k_path([0.0, 0.5, 1.0], len_0, report=False)
+    rib_eval, rib_evec = rib.solve_all(k_vec, eig_vectors=True)
+    rib_eval = rib_eval - efermi
+    out["rib_eval"] = rib_eval
+    nocc = np.sum(rib_eval < 0.0, axis=0)
+    out["jump_k"] = np.array([i for i in range(len_0 - 1) if nocc[i] != nocc[i + 1]], dtype=float)
+    pos = np.array([rib.position_expectation(rib_evec[:, i], dir=1) for i in range(len_0)]).T
+    out["pos_exp_sum"] = pos.sum(axis=0)
+    out["pos_exp_masked"] = _mask_close(pos, rib_eval)
+    out["hwfc_flat"] = np.concatenate([rib.position_hwf(rib_evec[rib_eval[:, i] < 0.0, i], 1) for i in range(len_0)])
+    return out
+
+
+def case_three_site_fin(mod):
+    """tests/test_examples/three_site/3site_cycle_fin/run.py:35-79 with t=-1.3, delta=2
+    (regen_golden_data.py:22):
+    Berry fluxes on a (lambda, k) array filled by hand (parametric axis, no pbc imposed),
+    and the finite chain of 10 cells along the cycle (every 4th of the 241 lambda steps)."""
+    nl, nk = 21, 31
+    lam = np.linspace(0.0, 1.0, nl, endpoint=True)
+    t = -1.3
+    m0 = M.three_site(mod, 0.0, t=t)
+    k_vec, _, _ = m0.k_path([[-0.5], [0.5]], nk, report=False)
+    w = mod.wf_array(m0, [nl, nk])
+    for il in range(nl):
+        _, evec = M.three_site(mod, lam[il], t=t).solve_all(k_vec, eig_vectors=True)
+        for ik in range(nk):
+            w[il, ik] = evec[:, ik, :]
+    out = dict(fluxes=np.array([w.berry_flux(o) for o in ([0], [1], [2], [0, 1], [0, 1, 2])]))
+    lam2 = np.linspace(0.0, 1.0, 241)[::4]
+    ch_eval = np.zeros((30, len(lam2)))
+    ch_xexp = np.zeros((30, len(lam2)))
+    for i, lmbd in enumerate(lam2):
+        fin = M.three_site(mod, lmbd, t=t).cut_piece(10, 0)
+        ev, evec = fin.solve_all(eig_vectors=True)
+        ch_eval[:, i] = ev
+        ch_xexp[:, i] = fin.position_expectation(evec, 0)
+    out["evals_chain"] = ch_eval
+    out["pos_exp_sum"] = ch_xexp.sum(axis=0)
+    out["pos_exp_masked"] = _mask_close(ch_xexp, ch_eval)
+    return out
+
+
 ALL_CASES = {
     "haldane_bands": case_haldane_bands,
     "haldane_bp": case_haldane_bp,
@@ -272,4 +405,8 @@ ALL_CASES = {
     "random": case_random,
     "grid3d": case_grid3d,
     "position": case_position,
+    "more_bands": case_more_bands,
+    "haldane_finite": case_haldane_finite,
+    "haldane_hwf": case_haldane_hwf,
+    "three_site_fin": case_three_site_fin,
 }

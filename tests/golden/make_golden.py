@@ -60,6 +60,28 @@ CROSS = [
     ("cubic_slab", "px", "slab/cubic_slab_hwf/golden_outputs/px.npy"),
     ("three_site", "wann_center", "three_site/3site_cycle/golden_outputs/3site_cycle_wann_centers.npy"),
     ("three_site", "final", "three_site/3site_cycle/golden_outputs/3site_cycle_final.npy"),
+    ("misc_bands", "checkerboard", "checkerboard/checkerboard/golden_outputs/evals.npy"),
+    ("more_bands", "evals_buckled", "buckling/buckled_layer/golden_outputs/evals.npy"),
+    ("more_bands", "evals_trestle", "buckling/trestle/golden_outputs/evals.npy"),
+    ("more_bands", "evals_graphene", "graphene/graphene/golden_outputs/evals.npy"),
+    ("more_bands", "evals_supercell", "supercell/supercell/golden_outputs/evals.py.npy"),
+    ("more_bands", "evals_0dim", "zero_dim/0dim/golden_outputs/evals.npy"),
+    ("haldane_finite", "evals_edge", "haldane/edge/golden_outputs/evals.npy"),
+    ("haldane_finite", "evals_edge_half", "haldane/edge/golden_outputs/evals_half.npy"),
+    ("haldane_finite", "evals_fin_false", "haldane/haldane_fin/golden_outputs/evals_false.npy"),
+    ("haldane_finite", "evals_fin_true", "haldane/haldane_fin/golden_outputs/evals_true.npy"),
+    ("haldane_hwf", "phi1", "haldane/haldane_hwf/golden_outputs/phi1.npy"),
+    ("haldane_hwf", "rib_eval", "haldane/haldane_hwf/golden_outputs/rib_eval.npy"),
+    ("haldane_hwf", "jump_k", "haldane/haldane_hwf/golden_outputs/jump_k.npy"),
+    ("haldane_hwf", "hwfc_flat", "haldane/haldane_hwf/golden_outputs/hwfcs.npy",
+     lambda g: np.concatenate([np.asarray(x, dtype=float).reshape(-1) for x in g])),
+    ("haldane_hwf", "pos_exp_sum", "haldane/haldane_hwf/golden_outputs/pos_exps.npy",
+     lambda g: np.array([np.sum(np.asarray(x, dtype=float)) for x in g])),
+    ("three_site_fin", "fluxes", "three_site/3site_cycle_fin/golden_outputs/3site_cycle_fluxes.npy"),
+    ("three_site_fin", "evals_chain", "three_site/3site_cycle_fin/golden_outputs/3site_cycle_fin_evals.npy",
+     lambda g: g[:, ::4]),
+    ("three_site_fin", "pos_exp_sum", "three_site/3site_cycle_fin/golden_outputs/3site_cycle_fin_xexp.npy",
+     lambda g: g[:, ::4].sum(axis=0)),
 ]
 
 
@@ -130,10 +152,13 @@ def main():
         log["cases"][name] = {k: list(v.shape) for k, v in res.items()}
         print("case %-16s %d arrays" % (name, len(res)))
     worst = 0.0
-    for case, key, rel in CROSS:
-        gold = np.load(os.path.join(REF_GOLD, rel))
+    for case, key, rel, *post in CROSS:
+        gold = np.load(os.path.join(REF_GOLD, rel), allow_pickle=True)
+        if post:
+            gold = post[0](gold)
+        gold = np.asarray(gold, dtype=float)
         ours = results[case][key]
-        dev = float(np.max(np.abs(np.asarray(ours).reshape(gold.shape) - gold)))
+        dev = float(np.max(np.abs(np.asarray(ours, dtype=float).reshape(gold.shape) - gold)))
         log["cross_check"]["%s.%s" % (case, key)] = dict(reference_golden=rel, max_abs_dev=dev)
         worst = max(worst, dev)
         print("cross-check %-28s vs %-70s max|dev| = %.2e" % (case + "." + key, rel, dev))
