@@ -36,12 +36,20 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
-    objs = []
-    logs = []
-    for src in SOURCES:
+    # the three translation units are independent: compile them side by side
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        return src, obj, res
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        done = list(pool.map(compile_one, SOURCES))
+    objs = []
+    logs = []
+    for src, obj, res in done:
         logs.append(res.stdout)
         if res.returncode != 0:
             sys.stderr.write(res.stdout)
