@@ -210,6 +210,33 @@ class B200Engine(object):
                                         _ptr(ws), ws.numel(), self.stream()))
         return ev, vec
 
+    def solve_slice(self, model, store, dim_arr, fixed, free, kpts):
+        """wf_array.solve_on_slice: eigenvectors of ``model`` at ``kpts[free..., dim_k]`` written straight
+        into the slice ``store[fixed]`` of the device array through tbk_solve_k's output strides (one fused
+        assemble + diagonalise launch per run of the last free axis); returns eval[free..., nsta] (host)."""
+        torch = self.torch
+        handle, plan = self.model_handle(model)
+        n = plan.nsta
+        wfs = store.dev(will_write=True)            # uploads the host mirror first if that is the newer copy
+        stride = [int(x) for x in wfs.stride()]     # in complex elements
+        base = sum(int(fixed[d]) * stride[d] for d in fixed)
+        fshape = [int(store.shape[d]) for d in free]
+        nk = fshape[-1]
+        outer = fshape[:-1]
+        kd = self.to_dev(kpts.reshape(-1, plan.dim_k), np.float64)
+        ev = torch.empty((int(np.prod(fshape)), n), dtype=torch.float64, device=self.device)
+        ws = self.workspace(self.lib.tbk_solve_workspace(n, nk, 1))
+        run = 0
+        for idx in np.ndindex(*outer):
+            off = base + sum(int(i) * stride[d] for i, d in zip(idx, free[:-1]))
+            _lib.check(self.lib.tbk_solve_k(
+                handle, ctypes.c_void_p(kd.data_ptr() + run * nk * plan.dim_k * 8), nk,
+                ctypes.c_void_p(ev.data_ptr() + run * nk * n * 8), 1, n,
+                ctypes.c_void_p(wfs.data_ptr() + off * 16), stride[dim_arr], stride[free[-1]],
+                _ptr(ws), ws.numel(), self.stream()))
+            run += 1
+        return ev.cpu().numpy().reshape(tuple(fshape) + (n,))
+
     def solve_all_mesh(self, model, mesh_size, eig_vectors, device_result=False):
         """solve_all on tb_model.k_uniform_mesh(mesh_size) with the k-points generated on the device
         (tbk_kmesh_uniform): nothing but the results crosses PCIe — and not even those with

@@ -249,6 +249,43 @@ class wf_array(object):
         key = (mesh_indices,) if _is_int(mesh_indices) else tuple(mesh_indices)
         self._wfs[key] = evec
 
+    def solve_on_slice(self, fixed, k_list, model=None):
+        """Extension for parametric axes (the pattern of examples/3site_cycle.py:48-90
+        and tests/test_examples/three_site/*/run.py): solve ``model`` — by default the array's own model, in
+        a sweep the model at one value of the parameter — at the k-points ``k_list[free..., dim_k]`` and
+        store the eigenvectors in ``self[fixed]``, where ``fixed = {mesh_axis: index}`` pins some axes and
+        the remaining ("free") axes, in order, index ``k_list``.  Equivalent to
+
+            (_, evec) = model.solve_all(k_list, eig_vectors=True)
+            for i in ...: self[..., i, ...] = evec[:, i]              # pythtb.py:2662-2672
+
+        but the eigenvectors are written by the solve kernel directly into the device array (no host
+        round trip, one launch per run of the last free axis).  Returns ``eval[free..., band]``."""
+        model = self._model if model is None else model
+        if model._nsta != self._nsta_arr or model._norb != self._norb or model._nspin != self._nspin:
+            raise Exception("\n\nsolve_on_slice: the model does not have the orbitals / states of this wf_array")
+        if model._dim_k == 0:
+            raise Exception("\n\nsolve_on_slice needs a periodic model (dim_k > 0)")
+        if self._shard is not None:
+            raise Exception("\n\nsolve_on_slice is not available on a sharded wf_array")
+        fix = {}
+        for d, i in dict(fixed).items():
+            if not _is_int(d) or d < 0 or d >= self._dim_arr:
+                raise Exception("\n\nWrong value of mesh axis in fixed.")
+            if not _is_int(i) or i < -self._mesh_arr[d] or i >= self._mesh_arr[d]:
+                raise IndexError("Key outside the range!")
+            fix[int(d)] = int(i) % int(self._mesh_arr[d])
+        free = [d for d in range(self._dim_arr) if d not in fix]
+        if not free:
+            raise Exception("\n\nsolve_on_slice: no free mesh axis left; use solve_on_one_point")
+        kpts = np.array(k_list, dtype=float)
+        want = tuple(int(self._mesh_arr[d]) for d in free) + (model._dim_k,)
+        if kpts.ndim == len(want) - 1 and model._dim_k == 1:
+            kpts = kpts.reshape(kpts.shape + (1,))
+        if kpts.shape != want:
+            raise Exception("\n\nk-vector of wrong shape!")
+        return self._model._engine().solve_slice(model, self._store, self._dim_arr, fix, free, kpts)
+
     def choose_states(self, subset):
         """pythtb.py:2568-2607."""
         subset = np.array(subset, dtype=int)

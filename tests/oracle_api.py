@@ -50,6 +50,15 @@ class OracleEngine(object):
             return res[0][:, None], res[1][:, None]
         return orc.solve_all(model, klist, eig_vectors)
 
+    def solve_slice(self, model, store, dim_arr, fixed, free, kpts):
+        """Same contract as B200Engine.solve_slice."""
+        fshape = tuple(store.arr.shape[d] for d in free)
+        ev, vec = orc.solve_all(model, kpts.reshape(-1, model._dim_k), True)
+        key = tuple(fixed[d] if d in fixed else slice(None) for d in range(dim_arr))
+        tail = store.arr.shape[dim_arr:]
+        store.arr[key] = np.swapaxes(vec, 0, 1).reshape(fshape + tuple(tail))
+        return ev.T.reshape(fshape + (model._nsta,))
+
     def pbc_phases(self, orb, nspin, k_dirs, convention=1):
         if convention == 2:
             return np.ones((len(k_dirs), np.asarray(orb).shape[0] * nspin), dtype=complex)
