@@ -160,10 +160,25 @@ TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
             const int r = j + 1 + rb + pr;
             cplx acc = mk(0.0, 0.0);
             if (r < n) {
-              // four independent accumulators: four loads in flight per thread, no serial FMA chain
+              // eight independent accumulators: eight 16-byte loads in flight per thread, no serial FMA chain
+              // (the product is latency-bound: one 512-thread CTA per SM has only its own loads to hide them)
               const cplx* arow = A + r;
-              cplx a0 = mk(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0;
+              cplx a0 = mk(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0, a7 = a0;
               int c = j + 1 + pp;
+              for (; c + 7 * parts < n; c += 8 * parts) {
+                const cplx m0 = arow[(size_t)c * lda], m1 = arow[(size_t)(c + parts) * lda];
+                const cplx m2 = arow[(size_t)(c + 2 * parts) * lda], m3 = arow[(size_t)(c + 3 * parts) * lda];
+                const cplx m4 = arow[(size_t)(c + 4 * parts) * lda], m5 = arow[(size_t)(c + 5 * parts) * lda];
+                const cplx m6 = arow[(size_t)(c + 6 * parts) * lda], m7 = arow[(size_t)(c + 7 * parts) * lda];
+                fma_acc(a0, m0, v[c]);
+                fma_acc(a1, m1, v[c + parts]);
+                fma_acc(a2, m2, v[c + 2 * parts]);
+                fma_acc(a3, m3, v[c + 3 * parts]);
+                fma_acc(a4, m4, v[c + 4 * parts]);
+                fma_acc(a5, m5, v[c + 5 * parts]);
+                fma_acc(a6, m6, v[c + 6 * parts]);
+                fma_acc(a7, m7, v[c + 7 * parts]);
+              }
               for (; c + 3 * parts < n; c += 4 * parts) {
                 const cplx m0 = arow[(size_t)c * lda], m1 = arow[(size_t)(c + parts) * lda];
                 const cplx m2 = arow[(size_t)(c + 2 * parts) * lda], m3 = arow[(size_t)(c + 3 * parts) * lda];
@@ -173,7 +188,7 @@ TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
                 fma_acc(a3, m3, v[c + 3 * parts]);
               }
               for (; c < n; c += parts) fma_acc(a0, arow[(size_t)c * lda], v[c]);
-              acc = (a0 + a1) + (a2 + a3);
+              acc = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
             }
             if (parts == 1) {
               if (r < n) W[i * n + r] = acc;
