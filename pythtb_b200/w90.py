@@ -65,22 +65,28 @@ class w90(object):
             if len(deg) > num_ws:
                 raise Exception("Too many degeneracies for WS points!")
         deg = np.array(deg, dtype=int)
-        rows = np.array([l.split() for l in ln[last + 1:] if l.strip()], dtype=float)
+        # one C-level parse of the whole body; the rows of one R form a block of num_wan^2 lines, but nothing
+        # below relies on it: rows are grouped by R vector in first-seen order (dict order = the order the
+        # reference's loop at pythtb.py:3532 visits them)
+        rows = np.loadtxt(ln[last + 1:], dtype=float, ndmin=2)
+        if rows.shape[1] != 7:
+            raise Exception("Unexpected row format in the _hr.dat file.")
         rvec = rows[:, :3].astype(int)
         ii = rows[:, 3].astype(int) - 1
         jj = rows[:, 4].astype(int) - 1
         val = rows[:, 5] + 1.0j * rows[:, 6]
+        uniq, first, inv = np.unique(rvec, axis=0, return_index=True, return_inverse=True)
+        inv = np.asarray(inv).reshape(-1)
+        order = np.argsort(first, kind="stable")              # unique R vectors in first-seen order
+        rank = np.empty(len(order), dtype=int)
+        rank[order] = np.arange(len(order))
+        if len(order) > num_ws:
+            raise Exception("More R vectors in the file than Wigner-Seitz points announced!")
+        ham = np.zeros((len(order), self.num_wan, self.num_wan), dtype=complex)
+        ham[rank[inv], ii, jj] = val                          # a repeated (R, i, j) row: the last one wins, as in the reference
         self.ham_r = {}
-        ind_R = 0
-        # group by R in first-seen order
-        keys = [tuple(r) for r in rvec.tolist()]
-        for n, key in enumerate(keys):
-            ent = self.ham_r.get(key)
-            if ent is None:
-                ent = {"h": np.zeros((self.num_wan, self.num_wan), dtype=complex), "deg": deg[ind_R]}
-                self.ham_r[key] = ent
-                ind_R += 1
-            ent["h"][ii[n], jj[n]] = val[n]
+        for pos, u in enumerate(order):
+            self.ham_r[tuple(int(x) for x in uniq[u])] = {"h": ham[pos], "deg": deg[pos]}
         for R in self.ham_r:
             if R != (0, 0, 0) and tuple(-x for x in R) not in self.ham_r:
                 raise Exception("Did not find negative R for R = " + str(R) + "!")
