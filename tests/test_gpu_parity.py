@@ -114,6 +114,34 @@ def test_chern_number_full_mesh():
     assert abs(wk.berry_flux([0, 1])) < 1e-7
 
 
+def test_full_mesh_eigenvectors_satisfy_the_eigenproblem():
+    """BASELINE config 2 at full size, both models: at 4000 random mesh points (images included) the stored
+    rows are orthonormal eigenvectors of the oracle's H(k) — a size-independent property of every point —
+    and the band gaps of those points are bounded below by the minimal gaps the kernel reduced."""
+    from oracle import pythtb_oracle as orc
+    mod = _mod()
+    rng = np.random.RandomState(12)
+    for m in (M.haldane(mod, delta=0.0), M.kane_mele(mod, "odd")):
+        n = m._nsta
+        w = mod.wf_array(m, [1025, 1025])
+        gaps = w.solve_on_grid([-0.5, -0.5])
+        wfs = w._wfs.reshape(1025, 1025, n, n)
+        ij = rng.randint(0, 1025, size=(4000, 2))
+        ij[:40, 0] = 1024                                   # rows / columns written as periodic images
+        ij[40:80, 1] = 1024
+        k = -0.5 + ij / 1024.0
+        ham = orc.gen_ham(m, k)
+        u = wfs[ij[:, 0], ij[:, 1]]                         # [pts, band, orb]
+        hu = np.einsum("pij,pbj->pbi", ham, u)
+        ev = np.einsum("pbi,pbi->pb", u.conj(), hu).real
+        assert np.max(np.abs(hu - ev[:, :, None] * u)) < 1e-11
+        assert np.max(np.abs(np.einsum("pbi,pci->pbc", u.conj(), u) - np.eye(n))) < 1e-12
+        assert np.all(np.diff(ev, axis=1) >= -1e-12)        # ascending
+        ev_ref = orc.sol_ham(ham, False)
+        assert np.max(np.abs(ev - ev_ref)) < 1e-10 * max(1.0, np.max(np.abs(ev_ref)))
+        assert np.all((ev[:, 1:] - ev[:, :-1]).min(axis=0) >= gaps - 1e-12)
+
+
 def test_solve_on_grid_subsample_vs_oracle():
     """129x129 Haldane / Kane-Mele grids against the oracle (gauge-invariant)."""
     from oracle import pythtb_oracle as orc
