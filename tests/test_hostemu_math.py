@@ -184,3 +184,77 @@ def test_blocked_heev(n, nb):
         ev2 = np.zeros(n)
         assert lib.emu_heev_blocked(n, _p(a.view(np.float64)), lda, nb, 0, _p(ev2), None, None) == 0
         assert np.array_equal(ev2, ev)
+
+
+# ---------------------------------------------------------------------------------------------
+# Hamiltonian assembly: the model compiler (pythtb_b200/_plan.py) + the device arithmetic of
+# csrc/tbk_plan.cuh (phase table, element-major accumulation, Convention-I gauge), emulated on
+# the host, against the oracle's restatement of tb_model._gen_ham (pythtb.py:874-925).
+# ---------------------------------------------------------------------------------------------
+class _PlanView(ctypes.Structure):
+    _fields_ = [("dim_k", ctypes.c_int), ("nsta", ctypes.c_int), ("nph", ctypes.c_int), ("nel", ctypes.c_int),
+                ("nterm", ctypes.c_int), ("convention", ctypes.c_int),
+                ("ph_R", ctypes.c_void_p), ("tau", ctypes.c_void_p), ("el_ptr", ctypes.c_void_p),
+                ("el_row", ctypes.c_void_p), ("el_col", ctypes.c_void_p), ("t_ph", ctypes.c_void_p),
+                ("t_amp", ctypes.c_void_p), ("pm_ptr", ctypes.c_void_p), ("pm_el", ctypes.c_void_p),
+                ("pm_amp", ctypes.c_void_p)]
+
+
+def _emu_gen_ham(model, k):
+    plan = model._plan()
+    pv = _PlanView(plan.dim_k, plan.nsta, plan.nph, plan.nel, plan.nterm, plan.convention)
+    for name in ("ph_R", "tau", "el_ptr", "el_row", "el_col", "t_ph", "t_amp", "pm_ptr", "pm_el", "pm_amp"):
+        setattr(pv, name, getattr(plan, name).ctypes.data)
+    k = np.ascontiguousarray(k, dtype=float).reshape(-1, max(plan.dim_k, 1))
+    nk = k.shape[0]
+    ham = np.zeros((nk, plan.nsta, plan.nsta), dtype=complex)
+    fn = hostemu.lib().emu_gen_ham
+    fn.restype = None
+    fn.argtypes = [ctypes.POINTER(_PlanView), DP, ctypes.c_int64, DP]
+    fn(ctypes.byref(pv), _p(k), nk, _p(ham.view(np.float64)))
+    return ham, plan
+
+
+def _phase_major_ham(plan, k):
+    """The same H_II from the phase-major CSR the mesh kernels stream (numpy, Convention II)."""
+    nk = k.shape[0]
+    ham = np.zeros((nk, plan.nsta, plan.nsta), dtype=complex)
+    amp = plan.pm_amp[:, 0] + 1j * plan.pm_amp[:, 1]
+    for p in range(plan.nph + 1):
+        ph = np.exp(2j * np.pi * (k @ plan.ph_R[p, :plan.dim_k])) if p < plan.nph else np.ones(nk)
+        for t in range(plan.pm_ptr[p], plan.pm_ptr[p + 1]):
+            e = int(plan.pm_el[t]) & ((1 << 30) - 1)
+            z = ph.conj() if int(plan.pm_el[t]) & (1 << 30) else ph
+            ham[:, plan.el_row[e], plan.el_col[e]] += amp[t] * z
+    low = np.tril(np.ones((plan.nsta, plan.nsta), dtype=bool), -1)
+    ham = ham + np.where(low, ham, 0).conj().transpose(0, 2, 1)
+    idx = np.arange(plan.nsta)
+    ham[:, idx, idx] = ham[:, idx, idx].real
+    return ham
+
+
+@pytest.mark.parametrize("convention", [1, 2])
+def test_plan_compiler_and_device_assembly(convention):
+    from oracle import pythtb_oracle as orc
+    from tests import models as M, oracle_api as api
+    zoo = [M.haldane(api, 0.2), M.kane_mele(api, "odd"), M.bn_ribbon(api, 7), M.cubic_slab(api, 5),
+           M.three_site(api, 0.3), M.checkerboard(api), M.cubic_bulk(api),
+           M.random_model(api, norb=5, dim=3, nhop=24, nspin=1, seed=3),
+           M.random_model(api, norb=4, dim=3, nhop=15, nspin=2, seed=5),
+           M.random_model(api, norb=9, dim=1, nhop=30, nspin=2, seed=8)]
+    rng = np.random.RandomState(40 + convention)
+    for m in zoo:
+        m.set_convention(convention)
+        k = rng.rand(11, m._dim_k) * 4.0 - 2.0
+        got, plan = _emu_gen_ham(m, k)
+        want = orc.gen_ham(m, k)
+        scale = max(1.0, np.max(np.abs(want)))
+        assert plan.convention == convention
+        assert np.max(np.abs(got - want)) < 1e-13 * scale
+        assert np.max(np.abs(got - got.conj().transpose(0, 2, 1))) < 1e-15 * scale   # the kernels also zero Im H_ii
+        # the phase-major list is the same operator (always Convention II: the gauge is applied afterwards)
+        m.set_convention(2)
+        assert np.max(np.abs(_phase_major_ham(plan, k) - orc.gen_ham(m, k))) < 1e-13 * scale
+    mol = M.molecule(api)                                     # dim_k = 0: no phases at all
+    got, _ = _emu_gen_ham(mol, np.zeros((1, 1)))
+    assert np.max(np.abs(got[0] - orc.gen_ham(mol, None)[0])) < 1e-14
