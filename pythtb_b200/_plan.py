@@ -32,6 +32,55 @@ def _canon(rper):
     return None, False
 
 
+# spinless models with at least this many hoppings take the array-native term builder (large Wannier models)
+VECTORISE_FROM = 4096
+
+
+def _terms_vectorised(model):
+    """The term list of ``compile_plan`` for a spinless periodic model, built with array operations:
+    the same terms in the same order as the loop (on-site first, then per hopping its (i,j) term followed
+    by the conjugate (j,i) term; upper-triangle and zero entries dropped; lattice vectors numbered in
+    first-seen order, canonical sign = first non-zero component positive)."""
+    norb = model._norb
+    per = list(model._per)
+    hops = model._hoppings
+    nhop = len(hops)
+    amp = np.fromiter((complex(h[0]) for h in hops), dtype=complex, count=nhop)
+    hi = np.fromiter((h[1] for h in hops), dtype=np.int64, count=nhop)
+    hj = np.fromiter((h[2] for h in hops), dtype=np.int64, count=nhop)
+    rper = np.array([h[3] for h in hops], dtype=np.int64).reshape(nhop, -1)[:, per]
+    nz = rper != 0
+    has = nz.any(axis=1)
+    first = np.argmax(nz, axis=1)
+    sgn = np.sign(rper[np.arange(nhop), first])              # 0 for R = 0
+    canon = rper * np.where(sgn < 0, -1, 1)[:, None]
+    idx = np.full(nhop, -1, dtype=np.int64)
+    table = {}
+    if has.any():
+        uniq, first_seen, inv = np.unique(canon[has], axis=0, return_index=True, return_inverse=True)
+        order = np.argsort(first_seen, kind="stable")
+        rank = np.empty(len(order), dtype=np.int64)
+        rank[order] = np.arange(len(order))
+        idx[has] = rank[np.asarray(inv).reshape(-1)]
+        for pos, u in enumerate(order):
+            table[tuple(int(x) for x in uniq[u])] = pos
+    ph_f = np.where(has, idx | np.where(sgn < 0, PH_CONJ, 0), -1)
+    ph_c = np.where(has, idx | np.where(sgn > 0, PH_CONJ, 0), -1)
+    site = np.array([complex(x).real for x in model._site_energies], dtype=float)
+    on = np.nonzero(site != 0.0)[0]
+    # interleave forward / conjugate terms per hopping, then drop upper-triangle and zero entries
+    rows = np.stack([hi, hj], axis=1).reshape(-1)
+    cols = np.stack([hj, hi], axis=1).reshape(-1)
+    amps = np.stack([amp, amp.conj()], axis=1).reshape(-1)
+    phs = np.stack([ph_f, ph_c], axis=1).reshape(-1)
+    keep = (rows >= cols) & (amps != 0.0)
+    rows = np.concatenate([on, rows[keep]])
+    cols = np.concatenate([on, cols[keep]])
+    amps = np.concatenate([site[on].astype(complex), amps[keep]])
+    phs = np.concatenate([np.full(len(on), -1, dtype=np.int64), phs[keep]])
+    return rows, cols, amps, phs, table
+
+
 def compile_plan(model, convention=1):
     """Build the plan from any object exposing the reference's attribute names
     (``_dim_k,_nspin,_norb,_nsta,_per,_orb,_site_energies,_hoppings``)."""
@@ -63,8 +112,11 @@ def compile_plan(model, convention=1):
         amps.append(val)
         phs.append(ph)
 
+    vectorised = nspin == 1 and dim_k > 0 and len(model._hoppings) >= VECTORISE_FROM
+    if vectorised:
+        rows, cols, amps, phs, table = _terms_vectorised(model)
     # on-site block, pythtb.py:894-898
-    for i in range(norb):
+    for i in range(norb if not vectorised else 0):
         if nspin == 1:
             add(i, i, complex(model._site_energies[i]).real, -1)
         else:
@@ -76,7 +128,7 @@ def compile_plan(model, convention=1):
                         val = val.real      # LAPACK ignores the imaginary part of the diagonal
                     add(2 * i + s, 2 * i + sp, val, -1)
     # hoppings in list order, pythtb.py:900-924
-    for hop in model._hoppings:
+    for hop in (model._hoppings if not vectorised else ()):
         blk = np.array(hop[0], dtype=complex).reshape(nspin, nspin)
         i, j = int(hop[1]), int(hop[2])
         if dim_k > 0:

@@ -278,9 +278,17 @@ class tb_model(object):
 
     def _bulk_set_hops(self, amps, ii, jj, RR):
         """O(nhop) insertion of hoppings known to be distinct (used by w90.model)."""
-        for a, i, j, R in zip(amps, ii, jj, RR):
-            self._hop_index[(int(i), int(j), self._rper(R))] = len(self._hoppings)
-            self._hoppings.append([self._val_to_block(a), int(i), int(j), np.array(R)])
+        n = len(ii)
+        if n == 0:
+            return
+        ii = np.asarray(ii, dtype=int).tolist()
+        jj = np.asarray(jj, dtype=int).tolist()
+        RR = np.asarray(RR, dtype=int).reshape(n, -1)
+        keys = RR[:, list(self._per)].tolist() if self._dim_k > 0 else [[]] * n      # _rper of every row at once
+        base = len(self._hoppings)
+        for pos in range(n):
+            self._hop_index[(ii[pos], jj[pos], tuple(keys[pos]))] = base + pos
+            self._hoppings.append([self._val_to_block(amps[pos]), ii[pos], jj[pos], RR[pos].copy()])
         self._touch()
 
     # ------------------------------------------------------------------ queries

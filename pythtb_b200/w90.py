@@ -137,11 +137,14 @@ class w90(object):
             if ignorable_imaginary_part is not None:
                 ham = np.where(np.abs(ham.imag) < ignorable_imaginary_part, ham.real + 0.0j, ham)
             idx_i, idx_j = np.nonzero(keep)     # row-major: i outer, j inner, as the reference loops
-            for i, j in zip(idx_i.tolist(), idx_j.tolist()):
-                amps.append(complex(ham[i, j]))
-                hi.append(i)
-                hj.append(j)
-                hR.append(list(R))
+            if len(idx_i):
+                amps.append(ham[idx_i, idx_j])
+                hi.append(idx_i)
+                hj.append(idx_j)
+                hR.append(np.tile(np.array(R, dtype=int), (len(idx_i), 1)))
+        if amps:
+            amps, hi, hj, hR = (np.concatenate(x) for x in (amps, hi, hj, hR))
+            amps = amps.tolist()                # Python complex, as set_hop would store them
         tb._bulk_set_hops(amps, hi, hj, hR)
         return tb
 

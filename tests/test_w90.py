@@ -70,3 +70,22 @@ def test_gpu_w90_parsed_model_eigenvalues(tmp_path):
     assert np.max(np.abs(ev - z["synth_all_evals"])) <= 1e-10 * max(1.0, np.max(np.abs(ev)))
     m = w.model(**CUT)
     assert np.max(np.abs(m.solve_all(z["synth_k"]) - orc.solve_all(m, z["synth_k"]))) <= 1e-10 * max(1.0, np.max(np.abs(ev)))
+
+
+def test_array_native_plan_builder_equals_the_loop(tmp_path):
+    """Large spinless models compile their plan with array operations (pythtb_b200/_plan.py): same terms, same
+    order, same lattice-vector table as the per-hopping loop."""
+    from pythtb_b200 import _plan
+    m = _parse(tmp_path).model()
+    assert len(m._hoppings) > 500
+    old = _plan.VECTORISE_FROM
+    try:
+        _plan.VECTORISE_FROM = 10 ** 9
+        a = _plan.compile_plan(m)
+        _plan.VECTORISE_FROM = 1
+        b = _plan.compile_plan(m)
+    finally:
+        _plan.VECTORISE_FROM = old
+    assert (a.nph, a.nel, a.nterm) == (b.nph, b.nel, b.nterm)
+    for name in ("ph_R", "tau", "el_ptr", "el_row", "el_col", "t_ph", "t_amp", "pm_ptr", "pm_el", "pm_amp"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
