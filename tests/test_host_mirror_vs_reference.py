@@ -207,3 +207,36 @@ def test_wf_array_error_behaviour_matches_the_reference():
         assert (x is None) == (y is None), (n, x, y)
         if x is not None:
             assert x == y, (n, x, y)
+
+
+@pytest.mark.parametrize("spec", [dict(norb=3, dim=2, nhop=8, nspin=1, seed=31), dict(norb=2, dim=2, nhop=6, nspin=2, seed=32),
+                                  dict(norb=5, dim=2, nhop=14, nspin=1, seed=33), dict(norb=3, dim=3, nhop=12, nspin=1, seed=34),
+                                  dict(norb=4, dim=1, nhop=7, nspin=2, seed=35)])
+def test_random_models_berry_quantities_oracle_vs_live_reference(spec):
+    """The oracle (through the product's host classes) against the live reference on seeded random models:
+    every wf_array result the goldens pin on physical models, here on generic ones — gaps, Berry phases in
+    both branches along every axis, fluxes over every pair of axes, per plaquette and summed."""
+    ref, _ = _mods()
+    from tests import compare, models as M, oracle_api
+    res = []
+    for mod in (ref, oracle_api):
+        m = _quiet(M.random_model, mod, **spec)
+        dim = spec["dim"]
+        mesh = [6, 5, 4][:dim]
+        w = mod.wf_array(m, mesh)
+        out = dict(gaps=_quiet(w.solve_on_grid, [0.1, -0.2, 0.3][:dim]))
+        nocc = max(1, m._nsta // 2)
+        for occ in ([0], list(range(nocc))):
+            tag = "_%d" % len(occ)
+            for d in range(dim):
+                out["phase%d%s" % (d, tag)] = w.berry_phase(occ, d, contin=False)
+                if len(occ) > 1:
+                    out["wilson%d%s" % (d, tag)] = w.berry_phase(occ, d, contin=False, berry_evals=True)
+            for d0 in range(dim):
+                for d1 in range(dim):
+                    if d0 != d1:
+                        out["plaq%d%d%s" % (d0, d1, tag)] = w.berry_flux(occ, dirs=[d0, d1], individual_phases=True)
+                        out["flux%d%d%s" % (d0, d1, tag)] = np.array(w.berry_flux(occ, dirs=[d0, d1]))
+        res.append(out)
+    bad = compare.compare_case("random_live", res[1], res[0])
+    assert not bad, "\n".join(bad)
