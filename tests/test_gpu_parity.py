@@ -73,6 +73,39 @@ def test_random_models_against_oracle(spec):
     assert np.max(np.abs(ham - orc.gen_ham(m, k[:3]))) <= compare.TOL_HAM * scale
 
 
+@pytest.mark.parametrize("spec", [dict(norb=3, dim=2, nhop=8, nspin=1, seed=31), dict(norb=2, dim=2, nhop=6, nspin=2, seed=32),
+                                  dict(norb=5, dim=2, nhop=14, nspin=1, seed=33), dict(norb=3, dim=3, nhop=12, nspin=1, seed=34),
+                                  dict(norb=4, dim=1, nhop=7, nspin=2, seed=35), dict(norb=12, dim=2, nhop=40, nspin=1, seed=36)])
+def test_random_models_berry_quantities_against_oracle(spec):
+    """Generic (random, complex, non-symmetric) models through solve_on_grid + berry_phase (both branches, every
+    axis) + berry_flux (every ordered pair of axes, per plaquette and summed) against the oracle; the same specs
+    are checked oracle-vs-live-reference in tests/test_host_mirror_vs_reference.py."""
+    from tests import oracle_api
+    res = []
+    for mod in (oracle_api, _mod()):
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = M.random_model(mod, **spec)
+        dim = spec["dim"]
+        mesh = [6, 5, 4][:dim]
+        w = mod.wf_array(m, mesh)
+        out = dict(gaps=w.solve_on_grid([0.1, -0.2, 0.3][:dim]))
+        nocc = max(1, m._nsta // 2)
+        for occ in ([0], list(range(nocc))):
+            tag = "_%d" % len(occ)
+            for d in range(dim):
+                out["phase%d%s" % (d, tag)] = w.berry_phase(occ, d, contin=False)
+                if len(occ) > 1:
+                    out["wilson%d%s" % (d, tag)] = w.berry_phase(occ, d, contin=False, berry_evals=True)
+            for d0 in range(dim):
+                for d1 in range(dim):
+                    if d0 != d1:
+                        out["plaq%d%d%s" % (d0, d1, tag)] = w.berry_flux(occ, dirs=[d0, d1], individual_phases=True)
+                        out["flux%d%d%s" % (d0, d1, tag)] = np.array(w.berry_flux(occ, dirs=[d0, d1]))
+        res.append(out)
+    bad = compare.compare_case("random_berry", res[1], res[0])
+    assert not bad, "\n".join(bad)
+
+
 def test_large_ribbon_and_slab_eigenvalues():
     """Configs 4/5 sizes on a few k-points: norb 200 ribbon, norb 499 slab."""
     from oracle import pythtb_oracle as orc
