@@ -97,3 +97,20 @@ def test_no_oracle_in_product():
             if f.endswith((".py", ".cu", ".cuh")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "hostemu" not in txt.replace("tests/hostemu", ""), f
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    """include/tbk.h compiles as strict C99 and a pure-C program links against the library and gets the
+    argument-check answers of the entry points without a GPU (tests/cabi/abi_smoke.c)."""
+    import shutil
+    import subprocess
+    so = _lib_path()
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the toolchain of this image"
+    exe = str(tmp_path / "abi_smoke")
+    src = os.path.join(ROOT, "tests", "cabi", "abi_smoke.c")
+    subprocess.check_call([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           src, "-o", exe, so, "-Wl,-rpath," + os.path.dirname(so)])
+    res = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout
+    assert "abi_smoke: ok" in res.stdout
