@@ -52,6 +52,21 @@ def main():
                     assert e0.shape == e0_ref.shape, (e0.shape, e0_ref.shape)
                     ok, dev = compare.sets_close(e0, e0_ref, 2 * np.pi, 1e-9)
                     assert ok, dev
+        # Convention II (tb_model.set_convention): the closing row of the last rank is a plain copy of row 0
+        m2 = M.haldane(api, 0.0)
+        m2.set_convention(2)
+        full = api.wf_array(m2, [11, 7])
+        gaps_ref = full.solve_on_grid([-0.5, -0.5])
+        for halo in ("exchange", "recompute"):
+            w = api.wf_array(m2, [11, 7], shard=(rank, world), halo=halo)
+            assert np.max(np.abs(w.solve_on_grid([-0.5, -0.5]) - gaps_ref)) < 1e-12
+            sh = w._shard
+            assert np.max(np.abs(w._wfs - full._wfs[sh.row0:sh.row0 + sh.nrows + 1])) < 1e-12
+            if sh.is_last:
+                assert np.array_equal(w._wfs[-1], full._wfs[0])
+            assert abs(w.berry_flux([0]) - full.berry_flux([0])) < 1e-10
+            b, b_ref = w.berry_phase([0], 0, contin=False), full.berry_phase([0], 0, contin=False)
+            assert np.max(np.abs(compare.circ_diff(b, b_ref, 2 * np.pi))) < 1e-10
         # 3-D mesh: axis 0 sharded, flux on planes that do / do not contain it
         m3 = M.random_model(api, norb=2, dim=3, nhop=6, nspin=1, seed=5)
         full = api.wf_array(m3, [7, 5, 6])
