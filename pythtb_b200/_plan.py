@@ -32,20 +32,20 @@ def _canon(rper):
     return None, False
 
 
-# spinless models with at least this many hoppings take the array-native term builder (large Wannier models)
+# models with at least this many hoppings take the array-native term builder (large Wannier models)
 VECTORISE_FROM = 4096
 
 
 def _terms_vectorised(model):
-    """The term list of ``compile_plan`` for a spinless periodic model, built with array operations:
-    the same terms in the same order as the loop (on-site first, then per hopping its (i,j) term followed
-    by the conjugate (j,i) term; upper-triangle and zero entries dropped; lattice vectors numbered in
-    first-seen order, canonical sign = first non-zero component positive)."""
-    norb = model._norb
+    """The term list of ``compile_plan`` for a periodic model, built with array operations: the same terms in
+    the same order as the loop (on-site blocks first, then per hopping and per spin pair (s, s') its
+    (i s, j s') term followed by the conjugate (j s', i s) term; upper-triangle and zero entries dropped;
+    lattice vectors numbered in first-seen order, canonical sign = first non-zero component positive)."""
+    norb, ns = model._norb, model._nspin
     per = list(model._per)
     hops = model._hoppings
     nhop = len(hops)
-    amp = np.fromiter((complex(h[0]) for h in hops), dtype=complex, count=nhop)
+    amp = np.array([np.asarray(h[0], dtype=complex).reshape(ns, ns) for h in hops], dtype=complex).reshape(nhop, ns, ns)
     hi = np.fromiter((h[1] for h in hops), dtype=np.int64, count=nhop)
     hj = np.fromiter((h[2] for h in hops), dtype=np.int64, count=nhop)
     rper = np.array([h[3] for h in hops], dtype=np.int64).reshape(nhop, -1)[:, per]
@@ -66,19 +66,31 @@ def _terms_vectorised(model):
             table[tuple(int(x) for x in uniq[u])] = pos
     ph_f = np.where(has, idx | np.where(sgn < 0, PH_CONJ, 0), -1)
     ph_c = np.where(has, idx | np.where(sgn > 0, PH_CONJ, 0), -1)
-    site = np.array([complex(x).real for x in model._site_energies], dtype=float)
-    on = np.nonzero(site != 0.0)[0]
-    # interleave forward / conjugate terms per hopping, then drop upper-triangle and zero entries
-    rows = np.stack([hi, hj], axis=1).reshape(-1)
-    cols = np.stack([hj, hi], axis=1).reshape(-1)
-    amps = np.stack([amp, amp.conj()], axis=1).reshape(-1)
-    phs = np.stack([ph_f, ph_c], axis=1).reshape(-1)
+    # on-site blocks, pythtb.py:894-898 (LAPACK ignores the imaginary part of the diagonal)
+    if ns == 1:
+        site = np.array([complex(x).real for x in model._site_energies], dtype=complex).reshape(norb, 1, 1)
+    else:
+        site = np.array(model._site_energies, dtype=complex).reshape(norb, 2, 2).copy()
+        site[:, 0, 0] = site[:, 0, 0].real
+        site[:, 1, 1] = site[:, 1, 1].real
+    sgrid, spgrid = np.meshgrid(np.arange(ns), np.arange(ns), indexing="ij")
+    o_rows = (np.arange(norb)[:, None, None] * ns + sgrid[None]).reshape(-1)
+    o_cols = (np.arange(norb)[:, None, None] * ns + spgrid[None]).reshape(-1)
+    o_amps = site.reshape(-1)
+    # hoppings: [hop, s, s', forward/conjugate] in C order = the loop's order
+    f_rows = hi[:, None, None] * ns + sgrid[None]
+    f_cols = hj[:, None, None] * ns + spgrid[None]
+    rows = np.stack([f_rows, f_cols], axis=-1).reshape(-1)
+    cols = np.stack([f_cols, f_rows], axis=-1).reshape(-1)
+    amps = np.stack([amp, amp.conj()], axis=-1).reshape(-1)
+    phs = np.stack([np.broadcast_to(ph_f[:, None, None], amp.shape), np.broadcast_to(ph_c[:, None, None], amp.shape)],
+                   axis=-1).reshape(-1)
+    rows = np.concatenate([o_rows, rows])
+    cols = np.concatenate([o_cols, cols])
+    amps = np.concatenate([o_amps, amps])
+    phs = np.concatenate([np.full(len(o_rows), -1, dtype=np.int64), phs])
     keep = (rows >= cols) & (amps != 0.0)
-    rows = np.concatenate([on, rows[keep]])
-    cols = np.concatenate([on, cols[keep]])
-    amps = np.concatenate([site[on].astype(complex), amps[keep]])
-    phs = np.concatenate([np.full(len(on), -1, dtype=np.int64), phs[keep]])
-    return rows, cols, amps, phs, table
+    return rows[keep], cols[keep], amps[keep], phs[keep], table
 
 
 def compile_plan(model, convention=1):
@@ -112,7 +124,7 @@ def compile_plan(model, convention=1):
         amps.append(val)
         phs.append(ph)
 
-    vectorised = nspin == 1 and dim_k > 0 and len(model._hoppings) >= VECTORISE_FROM
+    vectorised = dim_k > 0 and len(model._hoppings) >= VECTORISE_FROM
     if vectorised:
         rows, cols, amps, phs, table = _terms_vectorised(model)
     # on-site block, pythtb.py:894-898

@@ -73,19 +73,31 @@ def test_gpu_w90_parsed_model_eigenvalues(tmp_path):
 
 
 def test_array_native_plan_builder_equals_the_loop(tmp_path):
-    """Large spinless models compile their plan with array operations (pythtb_b200/_plan.py): same terms, same
-    order, same lattice-vector table as the per-hopping loop."""
+    """Large models compile their plan with array operations (pythtb_b200/_plan.py): same terms, same order,
+    same lattice-vector table as the per-hopping loop — spinless Wannier model, spinor models (2x2 blocks,
+    complex on-site blocks), dim_k < dim_r, zero amplitudes and R = 0 hoppings included."""
+    import io
+    import contextlib
+    import pythtb_b200
     from pythtb_b200 import _plan
-    m = _parse(tmp_path).model()
-    assert len(m._hoppings) > 500
+    from tests import models as M
+    zoo = [_parse(tmp_path).model()]
+    assert len(zoo[0]._hoppings) > 500
+    with contextlib.redirect_stdout(io.StringIO()):
+        zoo += [M.random_model(pythtb_b200, norb=6, dim=3, nhop=60, nspin=2, seed=2),
+                M.random_model(pythtb_b200, norb=9, dim=2, nhop=80, nspin=1, seed=3),
+                M.kane_mele(pythtb_b200, "odd"), M.bn_ribbon(pythtb_b200, 9), M.cubic_slab(pythtb_b200, 6),
+                M.haldane(pythtb_b200, 0.0)]
+    zoo[1].set_hop(0.0, 0, 1, [0, 0, 0], mode="reset", allow_conjugate_pair=True)      # an explicit zero amplitude
     old = _plan.VECTORISE_FROM
     try:
-        _plan.VECTORISE_FROM = 10 ** 9
-        a = _plan.compile_plan(m)
-        _plan.VECTORISE_FROM = 1
-        b = _plan.compile_plan(m)
+        for m in zoo:
+            _plan.VECTORISE_FROM = 10 ** 9
+            a = _plan.compile_plan(m)
+            _plan.VECTORISE_FROM = 1
+            b = _plan.compile_plan(m)
+            assert (a.nph, a.nel, a.nterm) == (b.nph, b.nel, b.nterm)
+            for name in ("ph_R", "tau", "el_ptr", "el_row", "el_col", "t_ph", "t_amp", "pm_ptr", "pm_el", "pm_amp"):
+                assert np.array_equal(getattr(a, name), getattr(b, name)), name
     finally:
         _plan.VECTORISE_FROM = old
-    assert (a.nph, a.nel, a.nterm) == (b.nph, b.nel, b.nterm)
-    for name in ("ph_R", "tau", "el_ptr", "el_row", "el_col", "t_ph", "t_amp", "pm_ptr", "pm_el", "pm_amp"):
-        assert np.array_equal(getattr(a, name), getattr(b, name)), name
