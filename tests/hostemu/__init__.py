@@ -20,7 +20,7 @@ def build(force=False):
     deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
         return SO
-    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I", CSRC, "-x", "c++", src, "-o", SO]
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-I", CSRC, "-x", "c++", src, "-o", SO]
     subprocess.check_call(cmd)
     return SO
 

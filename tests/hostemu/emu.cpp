@@ -5,6 +5,8 @@
 // product package.
 #include <vector>
 #include <cstring>
+#include <thread>
+#include <pthread.h>
 #include "tbk_common.cuh"
 #include "tbk_eig_small.cuh"
 #include "tbk_eig_group.cuh"
@@ -27,7 +29,88 @@ struct HostGroup {
   void subsync() {}
 };
 
+// A CTA emulated by T host threads: the same SPMD code the kernels run, barriers for __syncthreads /
+// __syncwarp, "warps" (sub-teams) of S consecutive threads.  Verifies the PARALLEL decomposition of the
+// group algorithms (which element each thread owns, what is visible after which barrier), not only their
+// arithmetic; a missing barrier shows up as a wrong result or as a ThreadSanitizer report.
+struct TeamShared {
+  int T, S;
+  pthread_barrier_t all;
+  std::vector<pthread_barrier_t> sub;
+  std::vector<double> red;
+  TeamShared(int T_, int S_) : T(T_), S(S_), sub(T_ / S_), red(T_) {
+    pthread_barrier_init(&all, nullptr, T);
+    for (auto& b : sub) pthread_barrier_init(&b, nullptr, S);
+  }
+  ~TeamShared() {
+    pthread_barrier_destroy(&all);
+    for (auto& b : sub) pthread_barrier_destroy(&b);
+  }
+};
+struct TeamGroup {
+  TeamShared* sh;
+  int t;
+  int tid() const { return t; }
+  int size() const { return sh->T; }
+  void sync() { pthread_barrier_wait(&sh->all); }
+  double sum(double x) {
+    sh->red[t] = x;
+    sync();
+    double s = 0.0;
+    for (int i = 0; i < sh->T; ++i) s += sh->red[i];
+    sync();
+    return s;
+  }
+  int nsub() const { return sh->T / sh->S; }
+  int sub() const { return t / sh->S; }
+  int lane() const { return t % sh->S; }
+  int subsize() const { return sh->S; }
+  void subsync() { pthread_barrier_wait(&sh->sub[sub()]); }
+  double subsum(double x) {
+    sh->red[t] = x;
+    subsync();
+    double s = 0.0;
+    for (int i = sub() * sh->S; i < (sub() + 1) * sh->S; ++i) s += sh->red[i];
+    subsync();
+    return s;
+  }
+};
+
 extern "C" {
+
+// The blocked solver run by a team of T threads in sub-teams of S (T a multiple of S), as solve_blocked_kernel
+// runs it with T = 256 / 512 and S = 32.  Same contract as emu_heev_blocked.
+int emu_heev_blocked_team(int n, double* A, int lda, int nb, int want_vec, double* ev, double* evec, int T, int S) {
+  if (T < 1 || S < 1 || T % S) return -1;
+  TeamShared shd(T, S);
+  BlkWork w;
+  w.n = n; w.lda = lda; w.nb = nb; w.A = (cplx*)A;
+  std::vector<char> sh(blk_shared_bytes(n, nb, T) + 64);
+  blk_carve_shared(w, sh.data(), T);
+  int nt = ((n + S - 1) / S) * S;
+  if (nt > T) nt = T;
+  std::vector<double> Z((size_t)n * n), lu((size_t)4 * n * nt);
+  w.Z = Z.data(); w.lu = lu.data(); w.nt = nt;
+  cplx* out = (cplx*)evec;
+  std::vector<int> fail(T, 0);
+  auto body = [&](int t) {
+    TeamGroup g{&shd, t};
+    hetrd_blocked(g, w);
+    const double tnorm = tridiag_bisect(g, w);
+    if (t == 0) std::memcpy(ev, w.lam, n * 8);
+    if (!want_vec) return;
+    fail[t] = tridiag_invit(g, w, tnorm);
+    if (fail[t]) return;                         // uniform across the team by construction
+    backtransform_all<kBlkMaxN>(g, w, w.V, 2 * nb, [&](int c, int r, cplx x) { out[(size_t)c * n + r] = x; });
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; ++t) th.emplace_back(body, t);
+  body(0);
+  for (auto& x : th) x.join();
+  for (int t = 1; t < T; ++t)
+    if (fail[t] != fail[0]) return -2;           // the fallback decision must not diverge inside a CTA
+  return fail[0];
+}
 
 void emu_eigh2(double h00, double h11, double h10re, double h10im, double* ev, double* w) {
   cplx ww[2][2];
@@ -92,6 +175,36 @@ int emu_heev_group(int n, double* A, int lda, int want_vec, double* ev, double* 
       for (int o = 0; o < n; ++o) out[(size_t)rank[i] * n + o] = a[o + (size_t)i * lda];
   }
   return info;
+}
+
+// The group solver run by a team of T threads (solve_tile_kernel: T = 8 / 16 / 32 lanes of a warp;
+// solve_block_kernel: a whole CTA).  Same contract as emu_heev_group.
+int emu_heev_group_team(int n, double* A, int lda, int want_vec, double* ev, double* evec, int T) {
+  if (T < 1) return -1;
+  TeamShared shd(T, T);
+  std::vector<char> buf(eig_scratch_bytes(n));
+  EigScratch s = eig_scratch_carve(buf.data(), n);
+  cplx* a = (cplx*)A;
+  std::vector<int> rank(n), info(T, 0);
+  auto body = [&](int t) {
+    TeamGroup g{&shd, t};
+    info[t] = heev_group(g, n, a, lda, s, want_vec != 0);
+    eig_rank(g, n, s.d, rank.data());
+    g.sync();
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; ++t) th.emplace_back(body, t);
+  body(0);
+  for (auto& x : th) x.join();
+  cplx* out = (cplx*)evec;
+  for (int i = 0; i < n; ++i) {
+    ev[rank[i]] = s.d[i];
+    if (want_vec)
+      for (int o = 0; o < n; ++o) out[(size_t)rank[i] * n + o] = a[o + (size_t)i * lda];
+  }
+  for (int t = 1; t < T; ++t)
+    if (info[t] != info[0]) return -2;
+  return info[0];
 }
 
 // Blocked solver (tbk_eig_blocked.cuh): A n x n column-major, leading dimension lda, lower triangle valid.

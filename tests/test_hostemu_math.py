@@ -258,3 +258,66 @@ def test_plan_compiler_and_device_assembly(convention):
     mol = M.molecule(api)                                     # dim_k = 0: no phases at all
     got, _ = _emu_gen_ham(mol, np.zeros((1, 1)))
     assert np.max(np.abs(got[0] - orc.gen_ham(mol, None)[0])) < 1e-14
+
+
+# ---------------------------------------------------------------------------------------------
+# The PARALLEL decomposition of the group algorithms: a CTA emulated by T host threads (one per CUDA
+# thread, pthread barriers for __syncthreads / __syncwarp, sub-teams of S threads as warps) runs the
+# same SPMD code as solve_blocked_kernel / solve_tile_kernel / solve_block_kernel.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,nb,T,S", [(24, 4, 16, 8), (45, 8, 64, 32), (33, 16, 32, 8), (70, 8, 96, 32)])
+def test_blocked_heev_by_a_team_of_threads(n, nb, T, S):
+    lib = hostemu.lib()
+    rng = np.random.RandomState(900 + n)
+    for kind in ("rand", "deg", "cluster", "flat", "ribbon"):
+        h = _blocked_matrix(rng, n, kind)
+        lda = n | 1
+        a = np.zeros((n, lda), dtype=complex)
+        a[:, :n] = np.tril(h).T
+        ev = np.zeros(n)
+        vec = np.zeros((n, n), dtype=complex)
+        rc = lib.emu_heev_blocked_team(n, _p(a.view(np.float64)), lda, nb, 1, _p(ev), _p(vec.view(np.float64)), T, S)
+        assert rc == 0, (kind, rc)
+        scale = max(1.0, np.max(np.abs(h)))
+        assert np.max(np.abs(ev - np.linalg.eigvalsh(h))) < 2e-13 * scale, kind
+        assert np.max(np.abs(h @ vec.T - vec.T * ev[None, :])) < 5e-14 * scale, kind
+        assert np.max(np.abs(vec.conj() @ vec.T - np.eye(n))) < 5e-12, kind
+
+
+@pytest.mark.parametrize("n,T", [(5, 8), (13, 16), (32, 32), (48, 64)])
+def test_group_heev_by_a_team_of_threads(n, T):
+    lib = hostemu.lib()
+    rng = np.random.RandomState(950 + n)
+    for degenerate in (False, True):
+        h = _rand_herm(rng, n, degenerate)
+        lda = n | 1
+        a = np.zeros((n, lda), dtype=complex)
+        a[:, :n] = np.tril(h).T
+        ev = np.zeros(n)
+        vec = np.zeros((n, n), dtype=complex)
+        assert lib.emu_heev_group_team(n, _p(a.view(np.float64)), lda, 1, _p(ev), _p(vec.view(np.float64)), T) == 0
+        _check_eig(h, ev, vec)
+
+
+def test_solvers_have_no_unsynchronised_accesses(tmp_path):
+    """The same team emulation under ThreadSanitizer (tests/hostemu/tsan_driver.cpp): an access to the shared
+    panels / workspace that no barrier orders — a missing __syncthreads() or __syncwarp() in the kernels — is a
+    reported data race.  Random, exactly degenerate, banded and flat-band spectra; blocked and group solvers."""
+    import os
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    src = os.path.join(os.path.dirname(hostemu.__file__), "tsan_driver.cpp")
+    exe = str(tmp_path / "tsan_driver")
+    build = subprocess.run([gxx, "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-pthread", "-ffp-contract=off",
+                            "-I", hostemu.CSRC, src, "-o", exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if build.returncode != 0 and "tsan" in build.stdout.lower():
+        pytest.skip("ThreadSanitizer runtime not available: " + build.stdout[-200:])
+    assert build.returncode == 0, build.stdout
+    runs = ["24 4 16 8 0 1", "30 8 32 8 1 2", "41 8 32 16 2 3", "36 8 32 8 3 4", "70 8 64 32 0 5", "50 16 64 32 3 6",
+            "7 0 8 8 0 1", "12 0 16 16 1 2", "31 0 32 32 2 4", "40 0 64 64 3 5"]
+    for args in runs:
+        res = subprocess.run([exe] + args.split(), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                             env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=66"))
+        assert "ThreadSanitizer" not in res.stdout, args + "\n" + res.stdout[:3000]
+        assert res.returncode == 0, args + "\n" + res.stdout[-500:]
