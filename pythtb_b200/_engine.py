@@ -548,6 +548,9 @@ class B200Engine(object):
         _lib.check(self.lib.tbk_berry_strings(ctypes.byref(view), _ptr(offs_d), nstr, npts, strides[dir],
                                               int(berry_evals), _ptr(out), _ptr(ws), ws.numel(), self.stream()))
         res = out.cpu().numpy()
+        if berry_evals and not np.all(np.isfinite(res)):
+            raise Exception("\n\nberry_phase(berry_evals=True): the overlap matrix of a link is singular (or not finite); "
+                            "its unitary polar factor is undefined.")
         return res.reshape(oshape + ((nocc,) if berry_evals else ()))
 
     def wilson_phases_across_ranks(self, store, dim_arr, occ, dir, nranks):
@@ -573,7 +576,11 @@ class B200Engine(object):
         out = torch.empty((nstr, nocc), dtype=torch.float64, device=self.device)
         ws = self.workspace(self.lib.tbk_wilson_workspace(nocc, nstr, nranks))
         _lib.check(self.lib.tbk_wilson_phases(_ptr(mats), nstr, nranks, nocc, _ptr(out), _ptr(ws), ws.numel(), self.stream()))
-        return out.cpu().numpy().reshape(oshape + (nocc,))
+        res = out.cpu().numpy()
+        if not np.all(np.isfinite(res)):
+            raise Exception("\n\nberry_phase(berry_evals=True): the overlap matrix of a link is singular (or not finite); "
+                            "its unitary polar factor is undefined.")
+        return res.reshape(oshape + (nocc,))
 
     def flux(self, store, dim_arr, occ, dirs, individual):
         """_one_flux_plane on every 2-D slice spanned by ``dirs`` (pythtb.py:3133-3202).

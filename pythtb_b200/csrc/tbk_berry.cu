@@ -926,6 +926,19 @@ __device__ __forceinline__ double block_sum(double x, double* red) {
   return t;
 }
 
+__device__ __forceinline__ double block_max(double x, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+  const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[w] = x;
+  __syncthreads();
+  double t = red[0];
+  for (int i = 1; i < nw; ++i) t = fmax(t, red[i]);
+  __syncthreads();
+  return t;
+}
+
 // mode 0: out[l] = det/|det| of the overlap.   mode 1: out[l*nocc*nocc ...] = unitary polar factor.
 __global__ void __launch_bounds__(256)
 link_matrix_kernel(WfView v, LinkMap map, long long nlinks, int mode, cplx* __restrict__ out, cplx* __restrict__ gws) {
@@ -951,22 +964,35 @@ link_matrix_kernel(WfView v, LinkMap map, long long nlinks, int mode, cplx* __re
     } else {
       if (nocc >= kWilsonBig) {
         // unitary polar factor by Newton-Schulz, X <- X (3 I - X^H X) / 2, both products on the DMMA GEMM.
-        // The overlap of two orthonormal sets has singular values in (0, 1], inside the convergence
-        // region |X|_2 < sqrt(3); anything else (user-filled arrays) is scaled by 1 / |X|_F first.
+        // The iteration converges for |X|_2 < sqrt(3).  The overlap of two orthonormal sets has singular values
+        // in (0, 1]; whatever else is in the array (user-filled, not normalised) is first scaled by the
+        // spectral-norm bound sqrt(|X|_1 |X|_inf) >= |X|_2 whenever that bound exceeds 1.7.  A (nearly)
+        // singular overlap does not converge: the result is then poisoned with NaN instead of returning the
+        // phases of a non-unitary product (the host raises).
         cplx* X = M;
         cplx* G = M + (size_t)nocc * ld;
         cplx* Xn = G + (size_t)nocc * ld;
-        double fro = 0.0;
-        for (int idx = threadIdx.x; idx < nocc * nocc; idx += blockDim.x) fro += norm2(X[(size_t)(idx / nocc) * ld + idx % nocc]);
-        fro = block_sum(fro, red);
-        if (fro > 1.0001 * nocc) {
-          const double sc = rsqrt(fro);
+        double rmax = 0.0, cmax = 0.0;
+        for (int r = threadIdx.x; r < nocc; r += blockDim.x) {
+          double rs = 0.0, cs = 0.0;
+          for (int c = 0; c < nocc; ++c) {
+            rs += sqrt(norm2(X[(size_t)r * ld + c]));
+            cs += sqrt(norm2(X[(size_t)c * ld + r]));
+          }
+          rmax = fmax(rmax, rs); cmax = fmax(cmax, cs);
+        }
+        rmax = block_max(rmax, red);
+        cmax = block_max(cmax, red);
+        const double bound = sqrt(rmax * cmax);
+        if (bound > 1.7) {
+          const double sc = 1.0 / bound;
           for (int idx = threadIdx.x; idx < nocc * nocc; idx += blockDim.x) {
             cplx& x = X[(size_t)(idx / nocc) * ld + idx % nocc];
             x = sc * x;
           }
           __syncthreads();
         }
+        bool converged = false;
         for (int it = 0; it < 100; ++it) {
           const GemmSide A1{X, 1, ld, nullptr, 1}, B1{X, 1, ld, nullptr, 0};
           cta_gemm_dmma(A1, nocc, B1, nocc, nocc, nullptr, G, ld, ov);          // G = X^H X
@@ -979,13 +1005,17 @@ link_matrix_kernel(WfView v, LinkMap map, long long nlinks, int mode, cplx* __re
             G[(size_t)r * ld + c] = mk((r == c ? 1.0 : 0.0) - 0.5 * gg.re, -0.5 * gg.im);   // 1.5 I - 0.5 G
           }
           dev = block_sum(dev, red);
-          if (!(dev > 1.0e-28 * nocc)) break;                                     // |X^H X - I|_F <= 1e-14 sqrt(nocc)
+          if (!(dev > 1.0e-28 * nocc)) { converged = dev == dev; break; }          // |X^H X - I|_F <= 1e-14 sqrt(nocc)
           const GemmSide A2{X, ld, 1, nullptr, 0}, B2{G, 1, ld, nullptr, 0};
           cta_gemm_dmma(A2, nocc, B2, nocc, nocc, nullptr, Xn, ld, ov);          // Xn = X P
           for (int idx = threadIdx.x; idx < nocc * nocc; idx += blockDim.x) {
             const size_t at = (size_t)(idx / nocc) * ld + idx % nocc;
             X[at] = Xn[at];
           }
+          __syncthreads();
+        }
+        if (!converged) {
+          for (int idx = threadIdx.x; idx < nocc * nocc; idx += blockDim.x) X[(size_t)(idx / nocc) * ld + idx % nocc] = mk(NAN, NAN);
           __syncthreads();
         }
         cplx* dst = out + (size_t)l * nocc * nocc;

@@ -62,7 +62,9 @@ TBK_HD void eigh2_fast(double h00, double h11, cplx h10, double ev[2], cplx w[2]
   ev[0] = mean - r;
   ev[1] = mean + r;
   const double big = fabs(delta) + r;                       // > 0
-  const double inv = rsqrt_fast(fma(big, big, b2) + tiny);
+  // big >= sqrt(tiny) = 1e-145, so big^2 + b2 >= 1e-290 is a normal number without a further offset (adding
+  // `tiny` again halved the norm of both vectors when H is exactly proportional to the identity)
+  const double inv = rsqrt_fast(fma(big, big, b2));
   const double x = big * inv;
   const cplx y = mk(h10.re * inv, -h10.im * inv);           // inv * H[0][1]
   const bool pos = delta >= 0.0;

@@ -551,9 +551,11 @@ class tb_model(object):
         """pythtb.py:1440-1637: arbitrary integer supercell of the periodic directions."""
         if self._dim_r == 0:
             raise Exception("\n\nMust have at least one periodic direction to make a super-cell")
-        use = np.array(sc_red_lat, dtype=int)
+        use = np.array(sc_red_lat)
         if use.shape != (self._dim_r, self._dim_r):
             raise Exception("\n\nDimension of sc_red_lat array must be dim_r*dim_r")
+        if use.dtype != int:                # pythtb.py:1508-1509: no silent truncation of 2.5 -> 2
+            raise Exception("\n\nsc_red_lat array elements must be integers")
         for i in range(self._dim_r):
             for j in range(self._dim_r):
                 if i == j:

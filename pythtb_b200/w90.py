@@ -151,11 +151,18 @@ class w90(object):
     def dist_hop(self):
         """Distances and |H| of all matrix elements (pythtb.py:3590-3645)."""
         ret_ham, ret_dist = [], []
+        nw = self.num_wan
+        offdiag = ~np.eye(nw, dtype=bool)
         for R, ent in self.ham_r.items():
             vecR = R[0] * self.lat[0] + R[1] * self.lat[1] + R[2] * self.lat[2]
             dvec = -self.xyz_cen[:, None, :] + self.xyz_cen[None, :, :] + vecR
-            ret_dist.append(np.sqrt(np.sum(dvec * dvec, axis=-1)).reshape(-1))
-            ret_ham.append((ent["h"] / float(ent["deg"])).reshape(-1))
+            dist = np.sqrt(np.sum(dvec * dvec, axis=-1))
+            ham = ent["h"] / float(ent["deg"])
+            if R[0] == 0 and R[1] == 0 and R[2] == 0:
+                # the on-site energies of the home cell are not hoppings (pythtb.py:3624-3636, avoid_diagonal)
+                dist, ham = dist[offdiag], ham[offdiag]
+            ret_dist.append(dist.reshape(-1))
+            ret_ham.append(ham.reshape(-1))
         return (np.concatenate(ret_dist), np.concatenate(ret_ham))
 
     def shells(self, num_digits=2):

@@ -192,7 +192,10 @@ class wf_array(object):
             return None
         hit = self._store.__dict__.get("_tbk_sg_fast")
         self._rp_sg = None
-        if hit is not None and hit[5] is not None and type(start_k) is list and hit[1] is self._store._dev:
+        # (a shard closed by a halo exchange is never replayed: the replay re-issues the kernel only, and the
+        # ring shift that fills the closing row — a collective every rank must take part in — would be skipped)
+        exchange = self._shard is not None and self._halo_mode() == "exchange"
+        if hit is not None and hit[5] is not None and type(start_k) is list and hit[1] is self._store._dev and not exchange:
             eng = self._model._engine()
             if hasattr(eng, "lib"):
                 self._rp_sg = (list(start_k), self._model._plan_cache, eng, hit[1], hit[2], hit[3].handle, hit[5],

@@ -135,6 +135,9 @@ def w90_fixtures():
         k2 = np.random.RandomState(8).rand(9, 3)
         out["synth_k"] = k2
         out["synth_all_evals"] = syn.model().solve_all(k2)
+        (dd, hh) = syn.dist_hop()                      # pythtb.py:3590-3645 (no i == j entries at R = 0)
+        out["synth_dist_hop_dist"], out["synth_dist_hop_ham"] = dd, hh
+        out["synth_shells"] = syn.shells()
     return out, float(dev)
 
 

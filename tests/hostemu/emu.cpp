@@ -112,6 +112,12 @@ int emu_heev_blocked_team(int n, double* A, int lda, int nb, int want_vec, doubl
   return fail[0];
 }
 
+void emu_eigh2_fast(double h00, double h11, double h10re, double h10im, double* ev, double* w) {
+  cplx ww[2][2];
+  eigh2_fast(h00, h11, mk(h10re, h10im), ev, ww);
+  std::memcpy(w, ww, sizeof(ww));
+}
+
 void emu_eigh2(double h00, double h11, double h10re, double h10im, double* ev, double* w) {
   cplx ww[2][2];
   eigh2(h00, h11, mk(h10re, h10im), ev, ww, true);

@@ -104,6 +104,9 @@ def test_model_definition_and_surgery_match_the_reference():
                     _same(_state(_quiet(a.make_supercell, sc, to_home=home, to_home_suppress_warning=True)),
                           _state(_quiet(b.make_supercell, sc, to_home=home, to_home_suppress_warning=True)),
                           (name, "make_supercell", sc, home))
+            for who in (a, b):                          # non-integer super-lattice: both refuse (pythtb.py:1508-1509)
+                with pytest.raises(Exception, match="must be integers"):
+                    _quiet(who.make_supercell, [[2.5, 0], [0, 1]])
         if a._dim_k == a._dim_r == 3:
             sc = [[1, 1, 0], [0, 2, 0], [0, 1, 2]]
             _same(_state(_quiet(a.make_supercell, sc, to_home=True, to_home_suppress_warning=True)),

@@ -52,6 +52,26 @@ def test_eigh2_closed_form():
         _check_eig(h, ev, w)
 
 
+def test_eigh2_fast_branch_free_variant():
+    """The mesh kernels' branch-free 2x2 solver (tbk_eig_small.cuh: eigh2_fast) on generic, diagonal and
+    EXACTLY degenerate matrices — H proportional to the identity is reachable on a mesh because the phases come
+    from sincospi (cospi(0.5) == 0 at k = 0.5 of a two-site chain, a Dirac point of graphene on the mesh)."""
+    lib = hostemu.lib()
+    rng = np.random.RandomState(2)
+    cases = [(rng.randn(), rng.randn(), complex(rng.randn(), rng.randn())) for _ in range(200)]
+    cases += [(1.0, 1.0, 0j), (0.0, 0.0, 0j), (-3.5, -3.5, 0j), (2.0, -1.0, 0j), (-1.0, 2.0, 0j), (0.3, 0.3, 1e-9 + 0j),
+              (1.0, 1.0 + 1e-13, 1e-3j), (1e8, -1e8, 1.0 + 1j), (0.0, 0.0, 1e-140 + 0j), (1.0, 1.0, 1e-200 + 0j),
+              (1.0 + 1e-200, 1.0, 0j)]
+    for h00, h11, h10 in cases:
+        ev = np.zeros(2)
+        w = np.zeros((2, 2), dtype=complex)
+        lib.emu_eigh2_fast(ctypes.c_double(h00), ctypes.c_double(h11), ctypes.c_double(h10.real), ctypes.c_double(h10.imag),
+                           _p(ev), _p(w.view(np.float64)))
+        h = np.array([[h00, np.conj(h10)], [h10, h11]])
+        _check_eig(h, ev, w)
+        assert np.max(np.abs(np.sum(np.abs(w) ** 2, axis=1) - 1.0)) < 1e-14, (h00, h11, h10)
+
+
 @pytest.mark.parametrize("n", [3, 4])
 def test_register_jacobi(n):
     lib = hostemu.lib()

@@ -50,7 +50,9 @@ def test_parser_and_model_match_the_reference_parse(tmp_path):
     assert np.max(np.abs(ev - z["synth_all_evals"])) < 1e-10
     # helper methods keep the reference's shapes (pythtb.py:3590-3685)
     dist, ham = w.dist_hop()
-    assert dist.shape == ham.shape == (len(w.ham_r) * 25,)
+    assert dist.shape == ham.shape == (len(w.ham_r) * 25 - 5,)      # R = 0 contributes no i == j entries (:3624-3636)
+    if "synth_dist_hop_dist" in z.files:
+        assert np.allclose(dist, z["synth_dist_hop_dist"], atol=1e-12) and np.allclose(ham, z["synth_dist_hop_ham"], atol=1e-12)
     assert np.all(np.diff(w.shells()) > 0)
 
 
