@@ -12,5 +12,11 @@ from .model import tb_model
 from .wfarray import wf_array
 from .w90 import w90
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 __all__ = ["tb_model", "wf_array", "w90"]
+
+
+def get_backend():
+    """Always 'b200' here; ``shim/pythtb`` (``import pythtb`` with PYTHTB_BACKEND=b200|reference, or
+    ``pythtb.set_backend``) is the switch for unmodified scripts."""
+    return "b200"
