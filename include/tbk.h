@@ -269,6 +269,13 @@ size_t tbk_wilson_workspace(int32_t nocc, int64_t nstr, int64_t nmat);
 int tbk_wilson_phases(double* mats_dev, int64_t nstr, int64_t nmat, int32_t nocc, double* out_dev,
                       void* ws_dev, size_t ws_bytes, void* stream);
 
+/* The ordered product alone: prod_dev [nstr][nocc][nocc] = mats[s][0] mats[s][1] ... mats[s][nmat-1] (mats_dev
+ * destroyed; workspace as tbk_wilson_workspace).  Used by the streamed 1-D Berry phase (config 4: a string of
+ * 1e5 k-points is processed in chunks that never coexist in memory; every chunk contributes the ordered
+ * product of its unitary link matrices, pythtb.py:3821-3826, and the chunk products are chained here). */
+int tbk_wilson_chain(double* mats_dev, int64_t nstr, int64_t nmat, int32_t nocc, double* prod_dev,
+                     void* ws_dev, size_t ws_bytes, void* stream);
+
 /* Name of the kernel family the calling thread's last solve call dispatched to
  * (benchmark / profile bookkeeping). */
 const char* tbk_last_kernel(void);

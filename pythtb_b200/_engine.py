@@ -570,17 +570,131 @@ class B200Engine(object):
         ws = self.workspace(self.lib.tbk_berry_workspace(nocc, view.n, nstr, npts, 1))
         _lib.check(self.lib.tbk_wilson_products(ctypes.byref(view), _ptr(offs_d), nstr, npts, strides[dir], _ptr(prod),
                                                 _ptr(ws), ws.numel(), self.stream()))
-        allp = torch.empty((nranks, nstr, nocc, nocc), dtype=torch.complex128, device=self.device)
-        dist.all_gather_into_tensor(torch.view_as_real(allp), torch.view_as_real(prod).unsqueeze(0))
-        mats = allp.permute(1, 0, 2, 3).contiguous()          # [nstr][rank][nocc][nocc]: rank order = link order
+        return self.wilson_finish(prod, nranks).reshape(oshape + (nocc,))
+
+    def wilson_finish(self, prod, nranks):
+        """Per-rank ordered products prod[nstr, nocc, nocc] (device) -> sorted eigenphases [nstr, nocc] of
+        prod_rank0 @ prod_rank1 @ ... (pythtb.py:3834-3838): one NCCL all-gather in rank order when nranks > 1,
+        then tbk_wilson_phases."""
+        torch = self.torch
+        nstr, nocc = int(prod.shape[0]), int(prod.shape[1])
+        if nranks > 1:
+            import torch.distributed as dist
+            allp = torch.empty((nranks, nstr, nocc, nocc), dtype=torch.complex128, device=self.device)
+            dist.all_gather_into_tensor(torch.view_as_real(allp), torch.view_as_real(prod.contiguous()).unsqueeze(0))
+            mats = allp.permute(1, 0, 2, 3).contiguous()      # [nstr][rank][nocc][nocc]: rank order = link order
+        else:
+            mats = prod.reshape(nstr, 1, nocc, nocc).clone()
         out = torch.empty((nstr, nocc), dtype=torch.float64, device=self.device)
-        ws = self.workspace(self.lib.tbk_wilson_workspace(nocc, nstr, nranks))
-        _lib.check(self.lib.tbk_wilson_phases(_ptr(mats), nstr, nranks, nocc, _ptr(out), _ptr(ws), ws.numel(), self.stream()))
+        ws = self.workspace(self.lib.tbk_wilson_workspace(nocc, nstr, max(nranks, 1)))
+        _lib.check(self.lib.tbk_wilson_phases(_ptr(mats), nstr, max(nranks, 1), nocc, _ptr(out), _ptr(ws), ws.numel(), self.stream()))
         res = out.cpu().numpy()
         if not np.all(np.isfinite(res)):
             raise Exception("\n\nberry_phase(berry_evals=True): the overlap matrix of a link is singular (or not finite); "
                             "its unitary polar factor is undefined.")
-        return res.reshape(oshape + (nocc,))
+        return res
+
+    # ------------------------------------------------- streamed 1-D strings (BASELINE config 4)
+    def stream_chunk(self, n):
+        """Links per chunk of the streamed string: whole waves of the solver that takes matrices of this size
+        (one 512-thread CTA per SM above n = 256, two 256-thread CTAs below), capped at ~1 GiB of eigenvectors."""
+        if n > 256:
+            c = 148 * 2
+        elif n > 32:
+            c = 148 * 4
+        else:
+            c = 1 << 16
+        cap = max(8, (1 << 30) // (16 * n * n))
+        return int(min(c, cap))
+
+    def stream_links(self, model, npts, start_k, occ, l0, l1, berry_evals, want_gaps=False, chunk=None):
+        """Links l0 .. l1-1 of the closed 1-D string k_g = start_k + g / (npts - 1), g = 0 .. npts-1 (the last point
+        is the periodic image of the first, pythtb.py:2472-2486 + 2729) WITHOUT materialising the wave functions:
+        chunks of <= `chunk` links go through assemble + diagonalise (tbk_solve_grid into a chunk buffer whose
+        first row is the carried last point of the previous chunk) and straight into the link overlaps
+        (pythtb.py:3813-3831).  Returns (result, gaps):
+          berry_evals False: result = sum over the chunks of -arg det prod M (a float, NOT wrapped),
+          berry_evals True : result = ordered product of the unitary link matrices, device tensor [1, nocc, nocc];
+          gaps = minimal direct gaps over the points l0 .. l1 (host array) or None."""
+        torch = self.torch
+        handle, plan = self.model_handle(model)
+        n = plan.nsta
+        occ = np.asarray(occ, dtype=np.int64).reshape(-1)
+        occ = np.where(occ < 0, occ + n, occ)
+        if occ.size == 0:
+            raise Exception("\n\nNo states selected.")
+        if occ.min() < 0 or occ.max() >= n:
+            raise IndexError("index in occ out of bounds")
+        nocc = int(occ.size)
+        l0, l1, npts = int(l0), int(l1), int(npts)
+        if not (0 <= l0 < l1 <= npts - 1):
+            raise Exception("\n\nstream_links: empty or out-of-range link interval")
+        C = int(min(chunk or self.stream_chunk(n), l1 - l0))
+        buf = torch.empty((C + 1, n, n), dtype=torch.complex128, device=self.device)
+        cache = plan.__dict__.setdefault("_tbk_dev_cache", {})
+        phase = cache.get(("pbc", 1))
+        if phase is None:
+            phase = cache[("pbc", 1)] = self.to_dev(self.pbc_phases(model._orb, model._nspin, [model._per[0]], model._convention))
+        occ_d = self.to_dev(occ.astype(np.int32))
+        off_d = self.to_dev(np.zeros(1, dtype=np.int64))
+        nch = (l1 - l0 + C - 1) // C
+        ws = self.workspace(max(self.lib.tbk_solve_workspace(n, C + 1, 1),
+                                self.lib.tbk_berry_workspace(nocc, n, 1, C + 1, int(bool(berry_evals))),
+                                self.lib.tbk_wilson_workspace(nocc, 1, nch)))
+        gaps = gaps_run = None
+        if want_gaps and n > 1:
+            gaps = torch.empty(n - 1, dtype=torch.float64, device=self.device)
+        if berry_evals:
+            acc = torch.empty((nch, nocc, nocc), dtype=torch.complex128, device=self.device)
+        else:
+            acc = torch.empty(nch, dtype=torch.float64, device=self.device)
+        start = (ctypes.c_double * 1)(float(np.asarray(start_k, dtype=float).reshape(-1)[0]))
+        mesh = (ctypes.c_int32 * 1)(npts)
+        blk = n * n                                   # complex elements per k-point
+        lo, ci, prev = l0, 0, 0
+        while lo < l1:
+            c = min(C, l1 - lo)
+            if ci == 0:                               # points lo .. lo+c
+                dst, row0, nrows = buf.data_ptr(), lo, c
+            else:                                     # carry the closing point of the previous chunk; points lo+1 .. lo+c
+                buf[0].copy_(buf[prev])
+                dst, row0, nrows = buf.data_ptr() + 16 * blk, lo + 1, c - 1
+            _lib.check(self.lib.tbk_solve_grid(handle, start, mesh, 1, row0, nrows, 2, ctypes.c_void_p(dst), _ptr(phase),
+                                               _ptr(gaps), _ptr(ws), ws.numel(), self.stream()))
+            if gaps is not None:
+                gaps_run = gaps.clone() if gaps_run is None else torch.minimum(gaps_run, gaps)
+            view = _lib.WfView(buf.data_ptr(), n, n, nocc, occ_d.data_ptr())
+            if berry_evals:
+                _lib.check(self.lib.tbk_wilson_products(ctypes.byref(view), _ptr(off_d), 1, c + 1, blk, _ptr(acc[ci]),
+                                                        _ptr(ws), ws.numel(), self.stream()))
+            else:
+                _lib.check(self.lib.tbk_berry_strings(ctypes.byref(view), _ptr(off_d), 1, c + 1, blk, 0,
+                                                      ctypes.c_void_p(acc.data_ptr() + 8 * ci), _ptr(ws), ws.numel(), self.stream()))
+            lo, ci, prev = lo + c, ci + 1, c
+        gaps_h = gaps_run.cpu().numpy() if gaps_run is not None else None
+        if not berry_evals:
+            return float(acc.cpu().numpy().sum()), gaps_h
+        prod = torch.empty((1, nocc, nocc), dtype=torch.complex128, device=self.device)
+        _lib.check(self.lib.tbk_wilson_chain(_ptr(acc), 1, nch, nocc, _ptr(prod), _ptr(ws), ws.numel(), self.stream()))
+        return prod, gaps_h
+
+    def stream_gaps(self, model, npts, start_k, l0, l1):
+        """Minimal direct gaps over the points l0 .. l1-1 of the 1-D mesh (pythtb.py:2484, 2529-2530) from an
+        eigenvalue-only pass; nothing but [nsta, chunk] eigenvalues is ever stored."""
+        n = model._nsta
+        if n <= 1:
+            return None
+        den = float(npts - 1)
+        s0 = float(np.asarray(start_k, dtype=float).reshape(-1)[0])
+        best = None
+        step = 1 << 16
+        for a in range(int(l0), int(l1), step):
+            g = np.arange(a, min(int(l1), a + step), dtype=float)
+            kd = self.to_dev((s0 + g / den).reshape(-1, 1), np.float64)           # pythtb.py:2477, same doubles as the kernels
+            ev, _ = self.solve_all_device(model, kd, int(g.size), False)
+            d = (ev[1:] - ev[:-1]).min(dim=1).values
+            best = d if best is None else self.torch.minimum(best, d)
+        return best.cpu().numpy()
 
     def flux(self, store, dim_arr, occ, dirs, individual):
         """_one_flux_plane on every 2-D slice spanned by ``dirs`` (pythtb.py:3133-3202).

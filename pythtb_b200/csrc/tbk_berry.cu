@@ -1660,6 +1660,13 @@ int tbk_wilson_phases(double* mats_dev, int64_t nstr, int64_t nmat, int32_t nocc
   return wilson_tail((cplx*)mats_dev, nstr, nmat, nocc, out_dev, nullptr, (char*)ws_dev, (cudaStream_t)stream);
 }
 
+int tbk_wilson_chain(double* mats_dev, int64_t nstr, int64_t nmat, int32_t nocc, double* prod_dev, void* ws_dev,
+                     size_t ws_bytes, void* stream) {
+  if (!mats_dev || !prod_dev || nstr < 1 || nmat < 1 || nocc < 1) { set_error("tbk_wilson_chain: bad argument"); return TBK_ERR_ARG; }
+  if (!ws_dev || ws_bytes < tbk_wilson_workspace(nocc, nstr, nmat)) { set_error("tbk_wilson_chain: workspace too small"); return TBK_ERR_WORKSPACE; }
+  return wilson_tail((cplx*)mats_dev, nstr, nmat, nocc, nullptr, (cplx*)prod_dev, (char*)ws_dev, (cudaStream_t)stream);
+}
+
 int tbk_position_matrix(const double* evec_dev, int64_t batch, int32_t nocc, int32_t n, const double* pos_dev,
                         double* xmat_dev, void* stream) {
   if (!evec_dev || !pos_dev || !xmat_dev || batch < 0 || nocc < 1 || n < 1) { set_error("tbk_position_matrix: bad argument"); return TBK_ERR_ARG; }

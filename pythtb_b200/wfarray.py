@@ -89,9 +89,19 @@ class wf_array(object):
     holds rows ``[row0, row0+nrows]`` only, ``solve_on_grid`` closes the slab
     with the neighbour's first row (NCCL ring shift over NVLink, or an in-kernel
     recomputation for tiny matrices), and ``berry_flux``/``berry_phase``/the
-    gaps are reduced over the ranks so every rank returns the global result."""
+    gaps are reduced over the ranks so every rank returns the global result.
 
-    def __init__(self, model, mesh_arr, nsta_arr=None, shard=None, halo="auto"):
+    ``stream=True`` (extension, 1-D meshes): the wave functions are never
+    materialised.  ``solve_on_grid`` returns the minimal gaps from an
+    eigenvalue-only pass, ``berry_phase`` streams the string in chunks —
+    assemble + diagonalise a chunk, overlap it link by link with the carried
+    last point of the previous chunk, keep only the chunk's determinant phase
+    (or ordered unitary product) — so a string of 1e5 k-points of a norb-400
+    ribbon (256 GB of eigenvectors, BASELINE config 4) runs in ~1 GB.  With
+    ``shard`` the links are dealt to the ranks in contiguous runs; every rank
+    returns the global result."""
+
+    def __init__(self, model, mesh_arr, nsta_arr=None, shard=None, halo="auto", stream=False):
         if nsta_arr is None:
             self._nsta_arr = model._nsta
         else:
@@ -114,8 +124,22 @@ class wf_array(object):
         if halo not in ("auto", "exchange", "recompute"):
             raise Exception("\n\nhalo must be 'auto', 'exchange' or 'recompute'")
         self._halo = halo
+        self._stream = bool(stream)
+        if self._stream:
+            if self._dim_arr != 1 or model._dim_k != 1 or self._nsta_arr != model._nsta:
+                raise Exception("\n\nstream=True needs a one-dimensional wf_array of a model with one periodic direction"
+                                "\n(and no nsta_arr): it streams a single closed string of k-points.")
+            self._store = None
+            self._start_k = None
+            self._rp_sg = self._rp_fx = None
+            return
         self._store = self._model._engine().new_store(self._wfs_shape(self._nsta_arr))
         self._rp_sg = self._rp_fx = None    # replay records of the last solve_on_grid / berry_flux call
+
+    def _need_store(self, what):
+        if self._store is None:
+            raise Exception("\n\n" + what + " is not available on a wf_array created with stream=True"
+                            "\n(its wave functions are never stored).")
 
     def _local_mesh(self):
         mesh = [int(m) for m in self._mesh_arr]
@@ -133,12 +157,14 @@ class wf_array(object):
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k == "_store":
+            if k == "_store" and v is not None:
                 continue
             if k in ("_rp_sg", "_rp_fx"):
                 setattr(new, k, None)
                 continue
             setattr(new, k, copy.deepcopy(v, memo))
+        if self._store is None:
+            return new
         new._store = self._model._engine().new_store(self._store.shape)
         if self._store.state != "empty":
             new._store.replace_host(np.array(self._store.host(), copy=True))
@@ -147,6 +173,9 @@ class wf_array(object):
     # the reference's host array (pythtb.py:2419); handing it out makes it authoritative
     @property
     def _wfs(self):
+        if self._store is None:
+            raise Exception("\n\nThis wf_array was created with stream=True: its wave functions are never stored."
+                            "\nUse solve_on_grid / berry_phase, or create the array without stream=True.")
         return self._store.host()
 
     @_wfs.setter
@@ -158,6 +187,8 @@ class wf_array(object):
         """pythtb.py:2421-2532: solve on k = start_k + i/(N-1), i < N-1, impose
         the periodic images on every axis, return the minimal direct gaps.
         One fused kernel launch for the whole mesh."""
+        if self._stream:
+            return self._stream_solve(start_k)
         # ---- replay: the same call as last time on this array (a parameter sweep, a timing loop) re-issues
         # the bound launch in the library (tbk_prepared_run) as long as the model, the device array and the
         # workspace are still the ones it was bound to — one foreign call, no argument marshalling
@@ -264,6 +295,7 @@ class wf_array(object):
 
         but the eigenvectors are written by the solve kernel directly into the device array (no host
         round trip, one launch per run of the last free axis).  Returns ``eval[free..., band]``."""
+        self._need_store("solve_on_slice")
         model = self._model if model is None else model
         if model._nsta != self._nsta_arr or model._norb != self._norb or model._nspin != self._nspin:
             raise Exception("\n\nsolve_on_slice: the model does not have the orbitals / states of this wf_array")
@@ -338,6 +370,7 @@ class wf_array(object):
     def impose_pbc(self, mesh_dir, k_dir):
         """pythtb.py:2674-2749: last slice := first slice * exp(-2 pi i tau_j[k_dir])
         (a plain copy for a Convention-II model, ``tb_model.set_convention``)."""
+        self._need_store("impose_pbc")
         if k_dir not in self._model._per:
             raise Exception("Periodic boundary condition can be specified only along periodic directions!")
         if mesh_dir < 0 or mesh_dir >= self._dim_arr or mesh_dir > 3:
@@ -348,6 +381,7 @@ class wf_array(object):
 
     def impose_loop(self, mesh_dir):
         """pythtb.py:2751-2791: last slice := first slice."""
+        self._need_store("impose_loop")
         if mesh_dir < 0 or mesh_dir >= self._dim_arr or mesh_dir > 3:
             raise Exception("\n\nWrong value of mesh_dir.")
         self._model._engine().impose_boundary(self._store, self._dim_arr, mesh_dir, None)
@@ -385,6 +419,7 @@ class wf_array(object):
         Returns ``hwfc[mesh..., nocc]``; with ``hwf_evec`` also a new ``wf_array`` (``nsta_arr = nocc``)
         holding the hybrid Wannier functions in the orbital basis at every mesh point, ready for
         ``impose_pbc`` / ``berry_phase`` (device resident; nothing is copied through the host)."""
+        self._need_store("position_hwf_all")
         occ = self._occ(occ, allow_none=False)
         if self._model._assume_position_operator_diagonal == False:  # noqa: E712
             _offdiag_approximation_warning_and_stop()
@@ -422,6 +457,10 @@ class wf_array(object):
         occ = self._occ(occ)
         if self._model._assume_position_operator_diagonal == False:  # noqa: E712
             _offdiag_approximation_warning_and_stop()
+        if self._stream:
+            if self._start_k is None:
+                raise Exception("\n\nCall solve_on_grid(start_k) before berry_phase on a streamed wf_array.")
+            return self.berry_phase_stream(self._start_k, occ, berry_evals=berry_evals)
         if self._dim_arr == 1:
             dir_use = 0
         elif self._dim_arr in (2, 3):
@@ -465,6 +504,59 @@ class wf_array(object):
                         ret[:, i] = _array_phases_cont(ret[:, i], clos)
         return ret
 
+    # ---------------------------------------------------- streamed 1-D strings
+    def _stream_links_range(self):
+        n0 = int(self._mesh_arr[0])
+        if self._shard is None:
+            return 0, n0 - 1, 1
+        return self._shard.row0, self._shard.row0 + self._shard.nrows, self._shard.nranks
+
+    def _stream_solve(self, start_k):
+        """solve_on_grid of a streamed array: remembers start_k and returns the minimal direct gaps
+        (pythtb.py:2484, 2529-2530) from an eigenvalue-only pass over this rank's points."""
+        start = np.array(start_k, dtype=float).reshape(-1)
+        if start.shape[0] != 1:
+            raise Exception("\n\nk-vector of wrong shape!")
+        self._start_k = [float(start[0])]
+        if self._nsta_arr <= 1:
+            return None
+        eng = self._model._engine()
+        l0, l1, nranks = self._stream_links_range()
+        gaps = eng.stream_gaps(self._model, int(self._mesh_arr[0]), self._start_k, l0, l1)
+        return eng.allreduce(np.asarray(gaps, dtype=float), "min") if nranks > 1 else gaps
+
+    def berry_phase_stream(self, start_k, occ="All", berry_evals=False, want_gaps=False, chunk=None):
+        """Berry phase of the closed string ``k = start_k + i / (N - 1)`` in ONE streamed pass — what
+        ``solve_on_grid(start_k)`` followed by ``berry_phase(occ, 0, berry_evals=...)`` returns on a 1-D array
+        (pythtb.py:2472-2486, 2729, 3813-3838), without storing the N x nsta x nsta eigenvector array.
+        ``berry_evals=False``: det(prod_links M) = prod_links det(M), so every chunk (and every rank)
+        contributes the phase of its own links and the sum is wrapped into [-pi, pi).  ``berry_evals=True``: every
+        chunk contributes the ordered product of its unitary link matrices; the products are chained in link order
+        (over the ranks too) and the sorted eigenphases returned.  ``want_gaps``: also return the minimal direct
+        gaps, as ``(phase, gaps)``."""
+        if self._dim_arr != 1 or self._model._dim_k != 1 or self._nsta_arr != self._model._nsta:
+            raise Exception("\n\nberry_phase_stream needs a one-dimensional wf_array of a model with one periodic direction.")
+        occ = self._occ(occ)
+        if self._model._assume_position_operator_diagonal == False:  # noqa: E712
+            _offdiag_approximation_warning_and_stop()
+        start = np.array(start_k, dtype=float).reshape(-1)
+        if start.shape[0] != 1:
+            raise Exception("\n\nk-vector of wrong shape!")
+        eng = self._model._engine()
+        l0, l1, nranks = self._stream_links_range()
+        res, gaps = eng.stream_links(self._model, int(self._mesh_arr[0]), [float(start[0])], occ, l0, l1, bool(berry_evals),
+                                     want_gaps=want_gaps, chunk=chunk)
+        if berry_evals:
+            ret = np.array(eng.wilson_finish(res, nranks), dtype=float).reshape(-1)
+        else:
+            tot = float(eng.allreduce(np.array([res], dtype=float), "sum")[0]) if nranks > 1 else float(res)
+            ret = float(self._wrap(tot))
+        if want_gaps:
+            if gaps is not None and nranks > 1:
+                gaps = eng.allreduce(np.asarray(gaps, dtype=float), "min")
+            return ret, gaps
+        return ret
+
     # ------------------------------------------------------------- Berry flux
     def _check_flux_args(self, occ, dirs):
         occ = self._occ(occ)
@@ -494,6 +586,7 @@ class wf_array(object):
     def berry_flux(self, occ="All", dirs=None, individual_phases=False):
         """pythtb.py:3068-3205: plaquette phases / integrated Berry curvature on
         every 2-D slice spanned by ``dirs``; one fused launch for all plaquettes."""
+        self._need_store("berry_flux")
         rp = self._rp_fx                    # replay of the previous identical call (see solve_on_grid)
         if rp is not None and not individual_phases and type(occ) is list and occ == rp[0] and dirs == rp[1] and \
                 self._model._assume_position_operator_diagonal != False:  # noqa: E712

@@ -154,6 +154,49 @@ class OracleEngine(object):
             out[s] = np.sort(-np.angle(np.linalg.eigvals(prd)))
         return out.reshape(tuple(other) + (nocc,))
 
+    # ---- streamed 1-D strings (same contract as B200Engine.stream_links / stream_gaps / wilson_finish)
+    def _string_points(self, model, npts, start_k, l0, l1):
+        """Eigenvector blocks of the points l0 .. l1 of the closed string (the last mesh point is the image of the first)."""
+        wfs, _ = orc.solve_on_grid(model, [npts], start_k)
+        return wfs[l0:l1 + 1].reshape(l1 - l0 + 1, model._nsta, -1)
+
+    def stream_links(self, model, npts, start_k, occ, l0, l1, berry_evals, want_gaps=False, chunk=None):
+        pts = self._string_points(model, npts, start_k, l0, l1)[:, list(occ)]
+        gaps = self.stream_gaps(model, npts, start_k, l0, l1 + 1 if l1 < npts - 1 else l1) if want_gaps else None
+        nocc = len(occ)
+        if not berry_evals:
+            tot = 0.0
+            for t in range(pts.shape[0] - 1):
+                tot += -np.angle(np.linalg.det(pts[t].conj() @ pts[t + 1].T))
+            return float(tot), gaps
+        prd = np.identity(nocc, dtype=complex)
+        for t in range(pts.shape[0] - 1):
+            u, _, vh = np.linalg.svd(pts[t].conj() @ pts[t + 1].T)
+            prd = prd @ (u @ vh)
+        return prd.reshape(1, nocc, nocc), gaps
+
+    def stream_gaps(self, model, npts, start_k, l0, l1):
+        if model._nsta <= 1:
+            return None
+        k = float(np.asarray(start_k, dtype=float).reshape(-1)[0]) + np.arange(l0, l1, dtype=float) / float(npts - 1)
+        ev = orc.sol_ham(orc.gen_ham(model, k.reshape(-1, 1)), False)
+        return (ev[:, 1:] - ev[:, :-1]).min(axis=0)
+
+    def wilson_finish(self, prod, nranks):
+        parts = [np.asarray(prod)]
+        if nranks > 1:
+            import torch.distributed as dist
+            parts = [None] * nranks
+            dist.all_gather_object(parts, np.asarray(prod))
+        nstr, nocc = parts[0].shape[0], parts[0].shape[1]
+        out = np.zeros((nstr, nocc))
+        for s in range(nstr):
+            prd = np.identity(nocc, dtype=complex)
+            for part in parts:
+                prd = prd @ part[s]
+            out[s] = np.sort(-np.angle(np.linalg.eigvals(prd)))
+        return out
+
     def flux(self, store, dim_arr, occ, dirs, individual):
         return np.asarray(orc.berry_flux(store.arr, dim_arr, occ, dirs, individual_phases=individual))
 

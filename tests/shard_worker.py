@@ -52,6 +52,24 @@ def main():
                     assert e0.shape == e0_ref.shape, (e0.shape, e0_ref.shape)
                     ok, dev = compare.sets_close(e0, e0_ref, 2 * np.pi, 1e-9)
                     assert ok, dev
+        # streamed 1-D string (BASELINE config 4 in miniature): links dealt to the ranks, never materialised
+        rib = M.bn_ribbon(api, 5)
+        occ_r = list(range(rib._nsta // 2))
+        full = api.wf_array(rib, [23])
+        gaps_ref = full.solve_on_grid([0.05])
+        for kw in (dict(stream=True), dict()):
+            ws = api.wf_array(rib, [23], shard=(rank, world), **kw)
+            if kw:
+                assert np.max(np.abs(ws.solve_on_grid([0.05]) - gaps_ref)) < 1e-12
+                ph = ws.berry_phase(occ_r)
+                ev = ws.berry_phase(occ_r, berry_evals=True)
+            else:
+                ph, gp = ws.berry_phase_stream([0.05], occ_r, want_gaps=True)
+                assert np.max(np.abs(gp - gaps_ref)) < 1e-12
+                ev = ws.berry_phase_stream([0.05], occ_r, berry_evals=True)
+            assert abs(compare.circ_diff(ph, full.berry_phase(occ_r), 2 * np.pi)) < 1e-10
+            ok, dev = compare.sets_close(ev, full.berry_phase(occ_r, berry_evals=True), 2 * np.pi, 1e-9)
+            assert ok, dev
         # Convention II (tb_model.set_convention): the closing row of the last rank is a plain copy of row 0
         m2 = M.haldane(api, 0.0)
         m2.set_convention(2)
