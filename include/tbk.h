@@ -314,6 +314,13 @@ int tbk_debug_profile(uint64_t* out8, int32_t reset);
  * (%globaltimer, ns), blockIdx.  out: [max_ctas][4].  TBK_ERR_UNSUPPORTED when tracing is off. */
 int tbk_debug_cta_trace(uint64_t* out, int64_t max_ctas, int32_t reset);
 
+/* FP64 peak microkernels for the benchmark harness: one launch of a register-resident kernel that issues only
+ * independent DFMA chains (kind 0, the FP64 FMA pipe) or independent mma.sync.m8n8k4.f64 (kind 1, the DMMA path
+ * the overlap GEMMs use) on every SM.  tbk_bench_fp64_flops returns the flops of one such launch; the caller
+ * times it with CUDA events: achieved flop/s = the FP64 roofline denominator MEASURED on this box in this run. */
+int tbk_bench_fp64(int32_t kind, int32_t iters, double* sink_dev, void* stream);
+double tbk_bench_fp64_flops(int32_t kind, int32_t iters);
+
 /* L2 flush helper for benchmarks: overwrites buf_dev[bytes] (bytes > L2 size). */
 int tbk_flush_l2(void* buf_dev, size_t bytes, void* stream);
 

@@ -9,6 +9,7 @@ The engine methods mirror the seams of the reference
 (``_gen_ham``/``_sol_ham``/``solve_all``/``solve_on_grid``/``_one_berry_loop``/
 ``_one_flux_plane``/``position_*``; file:line in the docstrings).
 """
+import collections
 import ctypes
 import os
 import weakref
@@ -104,7 +105,7 @@ class B200Engine(object):
         self._ws = None
         self._host_results = {}
         self._peer = None
-        self._pending_keep = None
+        self._pending_keep = collections.deque(maxlen=16)   # result tensors of posted, not yet completed reductions
         self._dev_index = self.device.index
         self._raw_stream = torch._C._cuda_getCurrentRawStream
 
@@ -306,10 +307,10 @@ class B200Engine(object):
         host array (the call then synchronises the stream) — or None.
         wrap0: 1 = write the periodic image of row 0 (single shard), 0 = leave the
         closing row to a halo exchange, 2 = compute the closing row in this launch.
-        defer_reduce (sharded, device result only): the kernel only posts this rank's gaps to
-        the peers; the returned tensor holds the minimum over the ranks once the next
-        flux_total(..., reduce_ranks=...) kernel — whose exchange then carries both — or
-        peer_flush() has run (include/tbk.h: tbk_peer_defer)."""
+        defer_reduce (sharded, device result only): the kernel only POSTS this rank's gaps to
+        the peers; the returned tensor holds the minimum over the ranks once a later kernel has
+        completed the reduction — a synchronous collective, a deferred flux_total at least one
+        step later, or peer_flush() (include/tbk.h: tbk_peer_defer)."""
         torch = self.torch
         # ---- fast path: the same call as last time on this store (a parameter sweep, the bench loop):
         # reuse the marshalled arguments as long as every buffer they point to is still the live one
@@ -367,7 +368,7 @@ class B200Engine(object):
                 if rc == 0:
                     reduced = launched = True
                     if deferred:
-                        self._pending_keep = gaps          # alive until the kernel that completes it is enqueued
+                        self._pending_keep.append(gaps)    # alive until the kernel that completes it has been enqueued
                     if fast_key is not None and gaps_h is not None:
                         store.__dict__["_tbk_sg_fast"] = (fast_key, store._dev, self._ws,
                                                           self._prepare(self.lib.tbk_solve_grid_prepare, args, peer),
@@ -426,7 +427,6 @@ class B200Engine(object):
         """Finish a deferred cross-rank reduction now (tbk_peer_flush); no-op when none is pending."""
         if self._peer:
             _lib.check(self.lib.tbk_peer_flush(self._peer, self.stream()))
-        self._pending_keep = None
 
     def peer_barrier(self):
         """Device-side barrier over the peer group, in stream order (tbk_peer_barrier): the kernels
@@ -707,14 +707,17 @@ class B200Engine(object):
             return plq.cpu().numpy().reshape(rshape + (mesh[dirs[0]] - 1, mesh[dirs[1]] - 1))
         return tot.cpu().numpy().reshape(rshape)
 
-    def flux_total(self, store, dim_arr, occ, dirs, host_result=False, reduce_ranks=None):
+    def flux_total(self, store, dim_arr, occ, dirs, host_result=False, reduce_ranks=None, defer_reduce=False):
         """Sum of the plaquette phases of every local 2-D slice: a device tensor [nslice], or with
-        ``host_result`` a host array (written by the kernel into pinned memory; the call synchronises)."""
+        ``host_result`` a host array (written by the kernel into pinned memory; the call synchronises).
+        defer_reduce (sharded, device result): the sum over the ranks is only posted by this kernel (which
+        completes the deferred reductions of EARLIER steps); the tensor holds the global sum once a later
+        collective kernel or peer_flush() has completed it."""
         return self.flux_device(store, dim_arr, occ, dirs, want_total=True, want_plaq=False, host_result=host_result,
-                                reduce_ranks=reduce_ranks)[0]
+                                reduce_ranks=reduce_ranks, defer_reduce=defer_reduce)[0]
 
     def flux_device(self, store, dim_arr, occ, dirs, want_total=True, want_plaq=False, host_result=False,
-                    reduce_ranks=None):
+                    reduce_ranks=None, defer_reduce=False):
         torch = self.torch
         fast_key = None
         if want_total and not want_plaq and host_result:
@@ -748,10 +751,16 @@ class B200Engine(object):
             # sum over the ranks inside the kernel, through NVLink peer memory (csrc/tbk_peer.cuh)
             peer = self.peer_group(*reduce_ranks)
             if peer is not None:
+                deferred = bool(defer_reduce and tot_h is None)
+                if deferred:
+                    _lib.check(self.lib.tbk_peer_defer(peer, 1))
                 rc = self.lib.tbk_flux_plane_x(*args, peer, self.stream())
+                if deferred:
+                    _lib.check(self.lib.tbk_peer_defer(peer, 0))
                 if rc == 0:
                     reduced = launched = True
-                    self._pending_keep = None              # a deferred gap reduction was completed by this kernel
+                    if deferred:
+                        self._pending_keep.append(tot)
                     if fast_key is not None and tot_h is not None and store.state != "host":
                         store.__dict__["_tbk_fx_fast"] = (fast_key, store._dev, self._ws,
                                                           self._prepare(self.lib.tbk_flux_plane_prepare, args, peer),

@@ -22,7 +22,7 @@ SYMBOLS = [
     "tbk_berry_strings", "tbk_position_matrix", "tbk_position_hwf_workspace", "tbk_position_hwf",
     "tbk_flush_l2", "tbk_halo_pack", "tbk_last_kernel", "tbk_launch_count", "tbk_peer_create", "tbk_peer_connect",
     "tbk_peer_destroy", "tbk_solve_grid_x", "tbk_flux_plane_x", "tbk_stream_sync", "tbk_debug_profile", "tbk_debug_cta_trace", "tbk_kmesh_uniform", "tbk_solve_grid_prepare", "tbk_flux_plane_prepare", "tbk_prepared_run", "tbk_prepared_destroy",
-    "tbk_peer_barrier", "tbk_peer_defer", "tbk_peer_flush", "tbk_wilson_products", "tbk_wilson_workspace", "tbk_wilson_phases", "tbk_wilson_chain",
+    "tbk_peer_barrier", "tbk_peer_defer", "tbk_peer_flush", "tbk_wilson_products", "tbk_wilson_workspace", "tbk_wilson_phases", "tbk_wilson_chain", "tbk_bench_fp64", "tbk_bench_fp64_flops",
 ]
 
 
@@ -87,6 +87,8 @@ def load():
         "tbk_wilson_workspace": (SZ, [I32, I64, I64]),
         "tbk_wilson_phases": (ctypes.c_int, [V, I64, I64, I32, V, V, SZ, V]),
         "tbk_wilson_chain": (ctypes.c_int, [V, I64, I64, I32, V, V, SZ, V]),
+        "tbk_bench_fp64": (ctypes.c_int, [I32, I32, V, V]),
+        "tbk_bench_fp64_flops": (ctypes.c_double, [I32, I32]),
         "tbk_debug_profile": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64), I32]),
         "tbk_debug_cta_trace": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64), I64, I32]),
         "tbk_peer_barrier": (ctypes.c_int, [c_void_p, c_void_p]),

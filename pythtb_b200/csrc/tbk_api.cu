@@ -65,33 +65,76 @@ int cuda_fail(cudaError_t e, const char* what) {
   return TBK_ERR_CUDA;
 }
 
-// device-side barrier over the peer group (one warp): an all-reduce of a dummy value
+// device-side barrier over the peer group (one warp): a synchronous all-reduce of a dummy value
 __global__ void peer_barrier_kernel(const __grid_constant__ PeerView pv, double* scratch) {
   __shared__ double s_v[1];
   __shared__ int s_fail;
   if (threadIdx.x == 0) s_v[0] = 1.0;
   __syncthreads();
-  peer_allreduce(pv, s_v, 1, 0, scratch, &s_fail);
+  peer_collective(pv, s_v, 1, 0, scratch, &s_fail);
 }
 
-// exchanges a deferred collective nobody else picked up (one CTA)
+// completes deferred collectives nobody else picked up (one CTA, posts nothing)
 __global__ void peer_collect_kernel(const __grid_constant__ PeerView pv) {
   __shared__ int s_fail;
-  peer_allreduce(pv, nullptr, 0, 0, nullptr, &s_fail);
+  peer_collective(pv, nullptr, 0, 0, nullptr, &s_fail);
 }
 
 int peer_flush(tbk_peer* p, cudaStream_t st) {
-  if (!p || !p->connected || p->nranks < 2 || p->pending.nv <= 0) return TBK_OK;
-  PeerView v = peer_next(p);
-  peer_attach_pending(p, v);
-  peer_collect_kernel<<<1, 64, 0, st>>>(v);
-  TBK_LAUNCH_CHECK("peer_collect_kernel");
+  if (!peer_active(p)) return TBK_OK;
+  while (p->npending > 0) {
+    PeerView v = peer_none();
+    v.rank = p->rank; v.nranks = p->nranks; v.epoch = 0;
+    for (int r = 0; r < p->nranks; ++r) v.box[r] = p->box[r];
+    peer_take_pending(p, v, p->npending < kPeerMaxPend ? p->npending : kPeerMaxPend);
+    peer_collect_kernel<<<1, 64, 0, st>>>(v);
+    TBK_LAUNCH_CHECK("peer_collect_kernel");
+  }
   return TBK_OK;
 }
 
 __global__ void flush_l2_kernel(double4* __restrict__ buf, size_t n, double v) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     buf[i] = make_double4(v, v, v, v);
+}
+
+// ---- FP64 peak microkernels: the denominators of the FP64 rooflines are MEASURED in the run that reports them
+// (MEASURED_PEAKS.json has no FP64 figure).  kind 0: 16 independent DFMA chains per thread (FMA pipe);
+// kind 1: 8 independent mma.sync.m8n8k4.f64 accumulator pairs per warp (the DMMA path of the overlap GEMMs).
+constexpr int kPeakThreads = 256, kPeakCtasPerSm = 4;
+__global__ void __launch_bounds__(kPeakThreads)
+fp64_peak_dfma_kernel(int iters, double seed, double* __restrict__ sink) {
+  double a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = seed + 1.0e-3 * (double)(threadIdx.x + i);
+  const double m = 1.0 - 1.0e-9, c = 1.0e-9 * seed;
+#pragma unroll 4
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fma(a[i], m, c);
+  }
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) t += a[i];
+  if (t == 123.456) sink[0] = t;                  // never true: keeps the chains alive
+}
+__global__ void __launch_bounds__(kPeakThreads)
+fp64_peak_dmma_kernel(int iters, double seed, double* __restrict__ sink) {
+  double d0[8], d1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { d0[i] = 0.0; d1[i] = 0.0; }
+  const double a = 1.0e-3 * seed + 1.0e-6 * (double)(threadIdx.x & 31), b = 1.0e-3 - 1.0e-6 * (double)(threadIdx.x & 31);
+#pragma unroll 4
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(d0[i]), "+d"(d1[i]) : "d"(a), "d"(b));
+  }
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += d0[i] + d1[i];
+  if (t == 123.456) sink[0] = t;
 }
 
 }  // namespace tbk
@@ -105,6 +148,7 @@ int tbk_version(void) { return 100; }
 const char* tbk_last_error(void) { return g_err; }
 
 int tbk_model_create(const tbk_model_desc* d, tbk_model** out) {
+  TBK_NVTX("tbk_model_create");
   if (!d || !out) { set_error("tbk_model_create: null argument"); return TBK_ERR_ARG; }
   if (d->dim_k < 0 || d->dim_k > TBK_MAX_DIM || d->nsta < 1 || d->nph < 0 || d->nel < 0 || d->nterm < 0 ||
       (d->convention != 1 && d->convention != 2)) {
@@ -267,10 +311,18 @@ int tbk_peer_defer(tbk_peer* p, int32_t on) {
 int tbk_peer_flush(tbk_peer* p, void* stream) { return peer_flush(p, (cudaStream_t)stream); }
 
 int tbk_peer_barrier(tbk_peer* p, void* stream) {
-  if (!p || !p->connected || p->nranks < 2) return TBK_OK;
-  if (int rc = peer_flush(p, (cudaStream_t)stream)) return rc;
-  const PeerView pv = peer_next(p);
-  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pv, (double*)((char*)p->box[p->rank] + kPeerMailboxBytes) + kPeerMaxVals);
+  TBK_NVTX("tbk_peer_barrier");
+  if (!peer_active(p)) return TBK_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  // a barrier is a synchronous collective of its own; it leaves deferred collectives alone (tbk_peer_flush
+  // completes those) unless the slot-reuse rule forces them out first
+  if (p->npending > 0 && p->epoch + 1 - p->pending[0].epoch > (unsigned long long)kPeerMaxLag) {
+    if (int rc = peer_flush(p, st)) return rc;
+  }
+  PeerView v = peer_none();
+  v.rank = p->rank; v.nranks = p->nranks; v.epoch = ++p->epoch; v.complete_self = 1;
+  for (int r = 0; r < p->nranks; ++r) v.box[r] = p->box[r];
+  peer_barrier_kernel<<<1, 32, 0, st>>>(v, (double*)((char*)p->box[p->rank] + kPeerMailboxBytes));
   TBK_LAUNCH_CHECK("peer_barrier_kernel");
   return TBK_OK;
 }
@@ -322,6 +374,7 @@ int tbk_flux_plane_prepare(const tbk_wf_view* view, const int64_t* slice_off_dev
 }
 
 int tbk_prepared_run(tbk_prepared* p, void* stream, int32_t sync) {
+  TBK_NVTX("tbk_prepared_run");
   if (!p || !p->run) { set_error("tbk_prepared_run: null handle"); return TBK_ERR_ARG; }
   static int spin = -1;                 // TBK_SPIN_SYNC=0: always wait with cudaStreamSynchronize (A/B knob)
   if (spin < 0) { const char* e = getenv("TBK_SPIN_SYNC"); spin = (e && atoi(e) == 0) ? 0 : 1; }
@@ -366,6 +419,21 @@ int tbk_prepared_run(tbk_prepared* p, void* stream, int32_t sync) {
 int tbk_prepared_destroy(tbk_prepared* p) {
   if (p && p->done_flag) cudaFreeHost(p->done_flag);
   delete p;
+  return TBK_OK;
+}
+
+double tbk_bench_fp64_flops(int32_t kind, int32_t iters) {
+  const double threads = (double)kNumSM * kPeakCtasPerSm * kPeakThreads;
+  if (kind == 0) return threads * (double)iters * 16.0 * 2.0;              // 16 FMA per thread per iteration
+  return (threads / 32.0) * (double)iters * 8.0 * 512.0;                   // 8 m8n8k4 DMMA (2*8*8*4 flops) per warp per iteration
+}
+
+int tbk_bench_fp64(int32_t kind, int32_t iters, double* sink_dev, void* stream) {
+  if (!sink_dev || iters < 1 || kind < 0 || kind > 1) { set_error("tbk_bench_fp64: bad argument"); return TBK_ERR_ARG; }
+  const int grid = kNumSM * kPeakCtasPerSm;
+  if (kind == 0) fp64_peak_dfma_kernel<<<grid, kPeakThreads, 0, (cudaStream_t)stream>>>(iters, 1.0, sink_dev);
+  else fp64_peak_dmma_kernel<<<grid, kPeakThreads, 0, (cudaStream_t)stream>>>(iters, 1.0, sink_dev);
+  TBK_LAUNCH_CHECK("fp64_peak_kernel");
   return TBK_OK;
 }
 

@@ -357,10 +357,9 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
       else total[s] = t;
     }
   }
-  if (peer.nranks > 1) {                                  // sum over the ranks, through the peers' mailboxes
-    __syncthreads();
-    peer_allreduce(peer, s_fin, (int)nslice, 0, total, &s_last);
-    __syncthreads();                                      // total[] was written by threads 0 .. nslice-1
+  if (peer.nranks > 1) {                                  // sum over the ranks through the peers' mailboxes (posted; completed
+    __syncthreads();                                      // here when synchronous), plus the older deferred collectives
+    peer_collective(peer, s_fin, (int)nslice, 0, total, &s_last);
   }
   if (tid == 0) signal_done(done);                        // single rank: thread 0 wrote total[] itself
   cta_trace_end(trace, t_begin);
@@ -387,10 +386,8 @@ static int launch_flux_rows(const WfView& v, const long long* off, long long nsl
   }
   const long long ctas = (tl.nitems + kFluxWarps - 1) / kFluxWarps;
   const int grid = (int)(ctas < resident ? ctas : resident);
-  PeerView pview = total ? peer_next(peer) : peer_next(nullptr);
-  if (total && peer && peer->pending.nv > 0) {             // a deferred gap reduction rides on this kernel's exchange
-    if (peer_can_attach(peer, (int)nslice)) peer_attach_pending(peer, pview);
-  }
+  PeerView pview = peer_none();                             // cross-rank sum: synchronous or posted (tbk_peer_defer); either way
+  if (total) { if (int rc = peer_next(peer, (int)nslice, 0, total, true, st, &pview)) return rc; }   // it completes older deferred ones
   // launched as a programmatic dependent of the previous kernel on the stream: its CTAs are scheduled as that
   // kernel's CTAs retire and wait at griddepcontrol.wait, which hides this kernel's launch latency and ramp
   // behind the predecessor's tail (TBK_PDL=0 turns it off)
@@ -406,7 +403,7 @@ static int launch_flux_rows(const WfView& v, const long long* off, long long nsl
   double* part_arg = plaq ? (total ? partial : nullptr) : partial;
   unsigned long long* trace = cta_trace_buffer();
   // a synchronous prepared call waits on a pinned word the last CTA writes after the totals
-  const DoneSignal done = total ? take_done_request() : DoneSignal{nullptr, 0};
+  const DoneSignal done = (total && (pview.nranks <= 1 || pview.complete_self)) ? take_done_request() : DoneSignal{nullptr, 0};
   if (plaq)
     TBK_CUDA(cudaLaunchKernelEx(&cfg, flux_rows_kernel<NOCC, N, true>, v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
                                 part_arg, ticket, total, pview, trace, done));
@@ -616,7 +613,7 @@ flux_ring_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
   }
   if (peer.nranks > 1) {                                  // sum over the ranks, through the peers' mailboxes
     __syncthreads();
-    peer_allreduce(peer, s_fin, (int)nslice, 0, total, &s_last);
+    peer_collective(peer, s_fin, (int)nslice, 0, total, &s_last);
   }
 }
 
@@ -673,8 +670,8 @@ static int launch_flux_ring(const WfView& v, const long long* off, long long nsl
     if (!ticket) { set_error("tbk_flux_plane: cannot allocate the reduction tickets"); return TBK_ERR_CUDA; }
   }
   const int grid = (int)(tl.ntiles < resident ? tl.ntiles : resident);
-  PeerView pview = total ? peer_next(peer) : peer_next(nullptr);
-  if (total && peer_can_attach(peer, (int)nslice)) peer_attach_pending(peer, pview);
+  PeerView pview = peer_none();
+  if (total) { if (int rc = peer_next(peer, (int)nslice, 0, total, true, st, &pview)) return rc; }
   if (plaq)
     kern_p<<<grid, kRingThreads, dyn, st>>>(v, off, n0, stride0, n1, tl, nslice, plaq, total ? partial : nullptr, ticket,
                                             total, pview);
@@ -1449,6 +1446,7 @@ extern "C" {
 
 int tbk_impose_boundary(double* wfs_dev, int64_t outer, int64_t len, int64_t inner, int32_t nsta_arr, int32_t n,
                         const double* phase_dev, void* stream) {
+  TBK_NVTX("tbk_impose_boundary");
   if (!wfs_dev || outer < 1 || len < 2 || inner < 1 || nsta_arr < 1 || n < 1) { set_error("tbk_impose_boundary: bad argument"); return TBK_ERR_ARG; }
   const long long total = outer * inner * nsta_arr * n;
   long long blocks = (total + 255) / 256;
@@ -1460,6 +1458,7 @@ int tbk_impose_boundary(double* wfs_dev, int64_t outer, int64_t len, int64_t inn
 
 int tbk_halo_pack(const double* row_dev, double* dst_dev, int64_t npoints, int32_t nsta_arr, int32_t n,
                   const double* phase_dev, void* stream) {
+  TBK_NVTX("tbk_halo_pack");
   if (!row_dev || !dst_dev || npoints < 0 || nsta_arr < 1 || n < 1) { set_error("tbk_halo_pack: bad argument"); return TBK_ERR_ARG; }
   const long long total = npoints * nsta_arr * n;
   if (total == 0) return TBK_OK;
@@ -1494,6 +1493,7 @@ int tbk_flux_plane(const tbk_wf_view* view, const int64_t* slice_off_dev, int64_
 int tbk_flux_plane_x(const tbk_wf_view* view, const int64_t* slice_off_dev, int64_t nslice, int64_t n0, int64_t stride0,
                      int64_t n1, int64_t stride1, double* plaq_dev, double* total_dev, void* ws_dev, size_t ws_bytes,
                      tbk_peer* peer, void* stream) {
+  TBK_NVTX("tbk_flux_plane_x");
   if (!view || !view->wfs_dev || !view->occ_dev || !slice_off_dev || nslice < 1 || n0 < 2 || n1 < 2 || view->nocc < 1 ||
       (!plaq_dev && !total_dev)) {
     set_error("tbk_flux_plane: bad argument");
@@ -1593,6 +1593,7 @@ size_t tbk_berry_workspace(int32_t nocc, int32_t n, int64_t nstr, int64_t npts, 
 
 int tbk_berry_strings(const tbk_wf_view* view, const int64_t* string_off_dev, int64_t nstr, int64_t npts, int64_t stride,
                       int32_t berry_evals, double* out_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  TBK_NVTX("tbk_berry_strings");
   if (!view || !view->wfs_dev || !view->occ_dev || !string_off_dev || !out_dev || nstr < 1 || npts < 2 || view->nocc < 1) {
     set_error("tbk_berry_strings: bad argument");
     return TBK_ERR_ARG;
@@ -1628,6 +1629,7 @@ int tbk_berry_strings(const tbk_wf_view* view, const int64_t* string_off_dev, in
 
 int tbk_wilson_products(const tbk_wf_view* view, const int64_t* string_off_dev, int64_t nstr, int64_t npts, int64_t stride,
                         double* prod_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  TBK_NVTX("tbk_wilson_products");
   if (!view || !view->wfs_dev || !view->occ_dev || !string_off_dev || !prod_dev || nstr < 1 || npts < 2 || view->nocc < 1) {
     set_error("tbk_wilson_products: bad argument");
     return TBK_ERR_ARG;
@@ -1655,6 +1657,7 @@ size_t tbk_wilson_workspace(int32_t nocc, int64_t nstr, int64_t nmat) { return w
 
 int tbk_wilson_phases(double* mats_dev, int64_t nstr, int64_t nmat, int32_t nocc, double* out_dev, void* ws_dev,
                       size_t ws_bytes, void* stream) {
+  TBK_NVTX("tbk_wilson_phases");
   if (!mats_dev || !out_dev || nstr < 1 || nmat < 1 || nocc < 1) { set_error("tbk_wilson_phases: bad argument"); return TBK_ERR_ARG; }
   if (!ws_dev || ws_bytes < tbk_wilson_workspace(nocc, nstr, nmat)) { set_error("tbk_wilson_phases: workspace too small"); return TBK_ERR_WORKSPACE; }
   return wilson_tail((cplx*)mats_dev, nstr, nmat, nocc, out_dev, nullptr, (char*)ws_dev, (cudaStream_t)stream);
@@ -1662,6 +1665,7 @@ int tbk_wilson_phases(double* mats_dev, int64_t nstr, int64_t nmat, int32_t nocc
 
 int tbk_wilson_chain(double* mats_dev, int64_t nstr, int64_t nmat, int32_t nocc, double* prod_dev, void* ws_dev,
                      size_t ws_bytes, void* stream) {
+  TBK_NVTX("tbk_wilson_chain");
   if (!mats_dev || !prod_dev || nstr < 1 || nmat < 1 || nocc < 1) { set_error("tbk_wilson_chain: bad argument"); return TBK_ERR_ARG; }
   if (!ws_dev || ws_bytes < tbk_wilson_workspace(nocc, nstr, nmat)) { set_error("tbk_wilson_chain: workspace too small"); return TBK_ERR_WORKSPACE; }
   return wilson_tail((cplx*)mats_dev, nstr, nmat, nocc, nullptr, (cplx*)prod_dev, (char*)ws_dev, (cudaStream_t)stream);
@@ -1669,6 +1673,7 @@ int tbk_wilson_chain(double* mats_dev, int64_t nstr, int64_t nmat, int32_t nocc,
 
 int tbk_position_matrix(const double* evec_dev, int64_t batch, int32_t nocc, int32_t n, const double* pos_dev,
                         double* xmat_dev, void* stream) {
+  TBK_NVTX("tbk_position_matrix");
   if (!evec_dev || !pos_dev || !xmat_dev || batch < 0 || nocc < 1 || n < 1) { set_error("tbk_position_matrix: bad argument"); return TBK_ERR_ARG; }
   if (batch == 0) return TBK_OK;
   if (nocc >= 16) {
@@ -1692,6 +1697,7 @@ size_t tbk_position_hwf_workspace(int32_t nocc, int32_t n, int64_t batch) {
 
 int tbk_position_hwf(const double* evec_dev, int64_t batch, int32_t nocc, int32_t n, const double* pos_dev,
                      double* hwfc_dev, double* hwf_dev, int32_t orbital_basis, void* ws_dev, size_t ws_bytes, void* stream) {
+  TBK_NVTX("tbk_position_hwf");
   if (!evec_dev || !pos_dev || !hwfc_dev || batch < 0 || nocc < 1 || n < 1) { set_error("tbk_position_hwf: bad argument"); return TBK_ERR_ARG; }
   if (!ws_dev || ws_bytes < tbk_position_hwf_workspace(nocc, n, batch)) { set_error("tbk_position_hwf: workspace too small"); return TBK_ERR_WORKSPACE; }
   if (batch == 0) return TBK_OK;

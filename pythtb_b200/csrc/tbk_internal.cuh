@@ -3,6 +3,7 @@
 // eigensolver / LU code, and small launch helpers.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <functional>
 #include <stdio.h>
 #include <string.h>
@@ -78,6 +79,13 @@ __device__ __forceinline__ void signal_done(const DoneSignal& d) {
   }
 }
 #endif
+
+// NVTX range around a C-ABI entry point (header-only NVTX3: a no-op unless a profiler injects itself)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define TBK_NVTX(name) tbk::NvtxRange nvtx_range__(name)
 
 constexpr int kNumSM = 148;           // B200
 constexpr int kMaxSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
@@ -185,40 +193,61 @@ struct tbk_peer {
   unsigned long long epoch;          // advanced by every collective issued through this group
   double* box[tbk::kPeerMaxRanks];   // box[rank] is the local allocation
   bool connected;
-  bool defer_next;                   // tbk_peer_defer: the next tbk_solve_grid_x keeps its reduction local
-  tbk::PeerPending pending;          // that deferred collective, until a later kernel (or tbk_peer_flush) exchanges it
+  bool defer_next;                   // tbk_peer_defer: the next *_x collective is only POSTED by its kernel
+  int npending;                      // posted, not yet completed collectives (oldest first)
+  tbk::PeerPending pending[2 * tbk::kPeerMaxPend];
 };
 
 namespace tbk {
-// PeerView for the next collective (advances the epoch); nranks = 0 view when peer is null
-inline PeerView peer_next(tbk_peer* p) {
-  PeerView v;
-  memset(&v, 0, sizeof(v));
-  if (p && p->connected && p->nranks > 1) {
-    v.rank = p->rank; v.nranks = p->nranks; v.epoch = ++p->epoch;
-    for (int r = 0; r < p->nranks; ++r) v.box[r] = p->box[r];
-  }
-  return v;
-}
-// no collective now: the kernel stores its local result in this rank's scratch, {nv, op, out} stay pending
-// on the host handle until the next collective carries them (peer_attach_pending) or peer_flush runs
-inline PeerView peer_next_deferred(tbk_peer* p, int nv, int op, double* out) {
-  PeerView v;
-  memset(&v, 0, sizeof(v));
-  if (p && p->connected && p->nranks > 1) {
-    v.rank = p->rank; v.nranks = p->nranks; v.epoch = p->epoch;
-    v.defer = 1;
-    v.local = (double*)((char*)p->box[p->rank] + kPeerMailboxBytes);
-    p->pending.nv = nv; p->pending.op = op; p->pending.out = out; p->pending.local = v.local;
-  }
-  if (p) p->defer_next = false;
-  return v;
-}
-// hand a pending collective to a view whose kernel exchanges it together with its own values
-inline bool peer_can_attach(const tbk_peer* p, int nv) { return p && p->pending.nv > 0 && nv + p->pending.nv <= kPeerMaxVals; }
-inline void peer_attach_pending(tbk_peer* p, PeerView& v) {
-  if (p && v.nranks > 1 && p->pending.nv > 0) { v.pend = p->pending; p->pending.nv = 0; }
-}
-// finish a pending collective with a one-warp kernel (tbk_api.cu); no-op when nothing is pending
+// completes every pending collective with one-CTA kernels (tbk_api.cu); no-op when nothing is pending
 int peer_flush(tbk_peer* p, cudaStream_t st);
+
+inline PeerView peer_none() {
+  PeerView v;
+  memset(&v, 0, sizeof(v));
+  return v;
+}
+inline bool peer_active(const tbk_peer* p) { return p && p->connected && p->nranks > 1; }
+
+// moves the oldest `count` pending collectives into the view
+inline void peer_take_pending(tbk_peer* p, PeerView& v, int count) {
+  for (int i = 0; i < count; ++i) v.pend[v.npend++] = p->pending[i];
+  for (int i = count; i < p->npending; ++i) p->pending[i - count] = p->pending[i];
+  p->npending -= count;
+}
+
+// PeerView for the next collective of nv values (advances the epoch).
+//   completer: a kernel that may complete older deferred collectives (the flux kernels, the flush / barrier
+//   kernels); the grid-solve kernel only posts when deferred, so that nothing but a few stores sits between its
+//   last CTA and the dependent flux kernel.
+// A synchronous collective (defer_next not set) completes everything pending together with its own result; a
+// deferred one is queued on the handle and completes only the queue entries that are >= 2 epochs old (the previous
+// step's).  rc != 0: launching a flush failed.
+inline int peer_next(tbk_peer* p, int nv, int op, double* out, bool completer, cudaStream_t st, PeerView* view) {
+  PeerView v = peer_none();
+  if (!peer_active(p)) { if (p) p->defer_next = false; *view = v; return 0; }
+  const bool defer = p->defer_next;
+  p->defer_next = false;
+  // slot-reuse safety / queue capacity: never let a posted epoch lag more than kPeerMaxLag, never overflow the view
+  if (p->npending > 0 && (p->epoch + 1 - p->pending[0].epoch > (unsigned long long)kPeerMaxLag ||
+                          (!defer && p->npending > kPeerMaxPend) || p->npending >= 2 * kPeerMaxPend - 1)) {
+    if (int rc = peer_flush(p, st)) return rc;
+  }
+  v.rank = p->rank; v.nranks = p->nranks; v.epoch = ++p->epoch;
+  for (int r = 0; r < p->nranks; ++r) v.box[r] = p->box[r];
+  v.complete_self = defer ? 0 : 1;
+  if (!defer) {
+    peer_take_pending(p, v, p->npending);                     // <= kPeerMaxPend by the check above
+  } else {
+    if (completer) {
+      int old = 0;
+      while (old < p->npending && old < kPeerMaxPend && p->pending[old].epoch + 2 <= v.epoch) ++old;
+      peer_take_pending(p, v, old);
+    }
+    PeerPending& q = p->pending[p->npending++];
+    q.epoch = v.epoch; q.nv = nv; q.op = op; q.out = out;
+  }
+  *view = v;
+  return 0;
+}
 }  // namespace tbk

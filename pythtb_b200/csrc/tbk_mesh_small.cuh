@@ -402,11 +402,9 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
       else gaps_out[b] = t;
     }
   }
-  if (peer.nranks > 1) {                            // minimum over the ranks, through the peers' mailboxes —
-    __syncthreads();                                // or deferred: kept local until the next exchange carries it
-    if (peer.defer) { if (tid < N - 1) peer.local[tid] = s_fin[tid]; }
-    else peer_allreduce(peer, s_fin, N - 1, 1, gaps_out, &s_last);
-    __syncthreads();                                // gaps_out was written by threads 0 .. N-2
+  if (peer.nranks > 1) {                            // minimum over the ranks through the peers' mailboxes: posted here,
+    __syncthreads();                                // completed here (synchronous) or by a later kernel (deferred)
+    peer_collective(peer, s_fin, N - 1, 1, gaps_out, &s_last);
   }
   if (tid == 0) signal_done(done);                  // single rank: thread 0 wrote gaps_out itself
   cta_trace_end(trace, t_begin);

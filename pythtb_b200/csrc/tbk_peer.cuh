@@ -5,17 +5,26 @@
 // (tbk_peer_create / tbk_peer_connect).  The protocol is the flag-in-data ("LL") scheme: a double
 // travels as two 8-byte words, each carrying 32 bits of payload and the 32-bit tag of the call's
 // epoch, and an aligned 8-byte store is a single NVLink transaction — so a word is either absent
-// (old tag) or complete, and no release fence / separate flag store is needed (the first version
-// paid a system-scope release per contribution).  The CTA that finishes a rank's local reduction
-//   1. stores its words into slot [parity][rank] of EVERY rank's mailbox (one thread per word);
-//   2. polls the words of its OWN mailbox until each carries this epoch's tag;
-//   3. combines the nranks vectors in rank order (deterministic) and writes the result.
-// A collective can also be DEFERRED: the producing kernel keeps its local result in this rank's own
-// memory (no NVLink traffic at all) and the host handle remembers it as pending; the next collective
-// kernel on the stream appends the pending values to its own message, so a solve + flux step is ONE
-// exchange (one exposed NVLink round trip, one kernel that has to drain remote stores) instead of two.
-// Slots are reused every kPeerDepth = 4 epochs: a rank posts epoch e+4 only after it completed e+3,
-// which needs every rank's e+3 words, which a rank posts only after it has read everything up to e+2.
+// (old tag) or complete, and no release fence / separate flag store is needed.
+//
+// A collective has two halves that need not run in the same kernel:
+//   POST      the CTA that finishes a rank's local reduction stores its words into slot
+//             [epoch % depth][rank] of EVERY rank's mailbox (one thread per word, fire and forget);
+//   COMPLETE  some CTA polls the words of its OWN mailbox until each carries that epoch's tag,
+//             combines the nranks vectors in rank order (deterministic) and writes the result.
+// A synchronous collective (the public API returns the number to the caller) does both in the
+// producing kernel's last CTA: one exposed NVLink round trip plus the skew between the ranks.
+// A DEFERRED collective (tbk_peer_defer) is only posted by its kernel; it is completed by a later
+// kernel on the stream — the next flux kernel completes the collectives that are at least two epochs
+// old, i.e. those of the PREVIOUS solve + flux step, whose words arrived tens of microseconds ago —
+// or by tbk_peer_flush.  A device-resident pipeline (a parameter sweep that reads its Chern numbers
+// at the end) therefore never waits for a peer inside a step: no exposed round trip, no skew.
+//
+// Slot reuse: epoch e and e + kPeerDepth share a slot.  The host handle never lets a posted epoch
+// lag more than kPeerMaxLag behind (it inserts a completing kernel first), and a rank posts e only
+// after completing everything up to e - kPeerMaxLag; rank r posting e + D has therefore completed
+// e + D - L, which needed q's words of e + D - L, which q posted after completing e + D - 2L >= e
+// for D >= 2L: the receiver has read a slot before anybody overwrites it.
 // All ranks must issue the same sequence of collectives (as with NCCL).  A rank that waits longer
 // than ~4 s gives up and returns NaN instead of hanging the GPU.
 #pragma once
@@ -25,23 +34,25 @@ namespace tbk {
 
 constexpr int kPeerMaxRanks = 8;
 constexpr int kPeerMaxVals = 16;                     // doubles per contribution
-constexpr int kPeerSlotWords = 2 * kPeerMaxVals;     // 8-byte words per (parity, source rank) slot
-constexpr int kPeerDepth = 4;                        // epochs in flight before a slot is reused
+constexpr int kPeerSlotWords = 2 * kPeerMaxVals;     // 8-byte words per (epoch slot, source rank)
+constexpr int kPeerDepth = 8;                        // epochs before a slot is reused
+constexpr int kPeerMaxLag = 4;                       // a posted collective is completed at most this many epochs later
+constexpr int kPeerMaxPend = 4;                      // deferred collectives one kernel can complete
 constexpr size_t kPeerMailboxBytes = (size_t)kPeerDepth * kPeerMaxRanks * kPeerSlotWords * sizeof(unsigned long long);
-constexpr size_t kPeerScratchBytes = 512;            // local scratch behind the mailbox: [0,16) deferred values, [16] barrier result
+constexpr size_t kPeerScratchBytes = 512;            // local scratch behind the mailbox (barrier result)
 
-struct PeerPending {                                 // a deferred collective (nv 0: none): the local values wait in
-  int nv, op;                                        // `local` (this rank's memory) for the next exchange
+struct PeerPending {                                 // a posted, not yet completed collective
+  unsigned long long epoch;
+  int nv, op;                                        // op 0: sum in rank order, 1: min
   double* out;
-  const double* local;
 };
 
 struct PeerView {
   int rank, nranks;                                  // nranks <= 1: no exchange
-  unsigned long long epoch;                          // > 0, identical on all ranks for one collective
-  int defer;                                         // 1: no exchange now, the kernel stores its local result to `local`
-  double* local;                                     // (the host handle remembers it as pending)
-  PeerPending pend;                                  // an earlier deferred collective that rides on this one
+  unsigned long long epoch;                          // of this kernel's own post (0: it posts nothing)
+  int complete_self;                                 // 1: also wait for the peers' words of `epoch` and write the result
+  int npend;
+  PeerPending pend[kPeerMaxPend];                    // older collectives this kernel completes
   double* box[kPeerMaxRanks];                        // mailbox of every rank (own one included)
 };
 
@@ -59,32 +70,28 @@ __device__ __forceinline__ unsigned peer_tag(unsigned long long epoch) {
   return (unsigned)epoch | 0x80000000u;              // never the zero of a fresh mailbox, never the tag this
 }                                                    // slot carried kPeerDepth collectives ago
 
-// The collective, called by ALL threads of ONE CTA per rank.  vals[nv] (shared or global, written before
-// a __syncthreads by the caller) -> out[nv] = sum (op 0, rank order) / min (op 1) over the ranks; a pending
-// deferred collective attached to the view travels in the same message and is combined into pv.pend.out.
-// nv + pv.pend.nv <= kPeerMaxVals.  *s_fail (shared) is set when a peer never arrived; the outputs are then NaN.
-__device__ inline void peer_allreduce(const PeerView& pv, const double* vals, int nv, int op, double* out, int* s_fail) {
-  __shared__ double s_vals[kPeerMaxVals];
-  __shared__ unsigned s_half[kPeerMaxRanks * kPeerSlotWords];
-  const int tid = threadIdx.x;
-  const int np = pv.pend.nv, nt = nv + np;
-  if (tid == 0) *s_fail = 0;
-  if (tid < nv) s_vals[tid] = vals[tid];
-  else if (tid < nt) s_vals[tid] = pv.pend.local[tid - nv];
-  __syncthreads();
+// POST: s_vals[nv] (shared memory, visible to the CTA) -> every rank's mailbox.  All threads of one CTA.
+__device__ __forceinline__ void peer_post(const PeerView& pv, const double* s_vals, int nv) {
   const unsigned tag = peer_tag(pv.epoch);
-  const int nw = 2 * nt;
-  const int depth = (int)(pv.epoch % kPeerDepth);
-  const size_t slot = (size_t)(depth * pv.nranks + pv.rank) * kPeerSlotWords;
-  for (int t = tid; t < pv.nranks * nw; t += blockDim.x) {    // 1. one word per thread, to every rank
+  const int nw = 2 * nv;
+  const size_t slot = (size_t)((int)(pv.epoch % kPeerDepth) * pv.nranks + pv.rank) * kPeerSlotWords;
+  for (int t = threadIdx.x; t < pv.nranks * nw; t += blockDim.x) {
     const int r = t / nw, w = t - r * nw;
     const unsigned long long bits = (unsigned long long)__double_as_longlong(s_vals[w >> 1]);
     const unsigned half = (w & 1) ? (unsigned)(bits >> 32) : (unsigned)bits;
     st_relaxed_sys_u64(reinterpret_cast<unsigned long long*>(pv.box[r]) + slot + w, ((unsigned long long)tag << 32) | half);
   }
+}
+
+// COMPLETE: wait for every rank's words of `epoch`, combine in rank order, write out[nv].  All threads of one CTA;
+// s_half: [kPeerMaxRanks * kPeerSlotWords] shared words; *s_fail (shared) is set when a peer never arrived.
+__device__ inline void peer_complete(const PeerView& pv, unsigned long long epoch, int nv, int op, double* out,
+                                     unsigned* s_half, int* s_fail) {
+  const unsigned tag = peer_tag(epoch);
+  const int nw = 2 * nv, tid = threadIdx.x;
   const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(pv.box[pv.rank]) +
-                                   (size_t)(depth * pv.nranks) * kPeerSlotWords;
-  for (int t = tid; t < pv.nranks * nw; t += blockDim.x) {    // 2. wait for every rank's words
+                                   (size_t)((int)(epoch % kPeerDepth) * pv.nranks) * kPeerSlotWords;
+  for (int t = tid; t < pv.nranks * nw; t += blockDim.x) {
     const int r = t / nw, w = t - r * nw;
     const unsigned long long* src = mine + (size_t)r * kPeerSlotWords + w;
     const long long t0 = clock64();
@@ -96,19 +103,34 @@ __device__ inline void peer_allreduce(const PeerView& pv, const double* vals, in
     s_half[r * kPeerSlotWords + w] = (unsigned)x;
   }
   __syncthreads();
-  if (tid < nt) {                                             // 3. rank order
-    const int o = tid < nv ? op : pv.pend.op;
-    double acc = o == 0 ? 0.0 : INFINITY;
+  if (tid < nv) {
+    double acc = op == 0 ? 0.0 : INFINITY;
     for (int r = 0; r < pv.nranks; ++r) {
       const unsigned long long bits = ((unsigned long long)s_half[r * kPeerSlotWords + 2 * tid + 1] << 32) |
                                       (unsigned long long)s_half[r * kPeerSlotWords + 2 * tid];
       const double x = __longlong_as_double((long long)bits);
-      acc = o == 0 ? acc + x : fmin(acc, x);
+      acc = op == 0 ? acc + x : fmin(acc, x);
     }
     if (*s_fail) acc = NAN;
-    if (tid < nv) out[tid] = acc;
-    else pv.pend.out[tid - nv] = acc;
+    out[tid] = acc;
   }
+  __syncthreads();                                   // s_half is free again; out[] is written
+}
+
+// The collective as one kernel sees it, called by ALL threads of ONE CTA per rank: post vals[nv] (if this
+// kernel has an epoch of its own), complete the older collectives attached to the view, and — for a synchronous
+// collective — complete its own: out[nv] = sum (op 0, rank order) / min (op 1) over the ranks.  The post goes
+// first: the peers' waits then overlap this rank's completions.
+__device__ inline void peer_collective(const PeerView& pv, const double* vals, int nv, int op, double* out, int* s_fail) {
+  __shared__ double s_vals[kPeerMaxVals];
+  __shared__ unsigned s_half[kPeerMaxRanks * kPeerSlotWords];
+  const int tid = threadIdx.x;
+  if (tid == 0) *s_fail = 0;
+  if (pv.epoch != 0 && tid < nv) s_vals[tid] = vals[tid];
+  __syncthreads();
+  if (pv.epoch != 0) peer_post(pv, s_vals, nv);
+  for (int i = 0; i < pv.npend; ++i) peer_complete(pv, pv.pend[i].epoch, pv.pend[i].nv, pv.pend[i].op, pv.pend[i].out, s_half, s_fail);
+  if (pv.epoch != 0 && pv.complete_self) peer_complete(pv, pv.epoch, nv, op, out, s_half, s_fail);
 }
 #endif
 

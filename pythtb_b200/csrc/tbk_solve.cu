@@ -828,6 +828,7 @@ using namespace tbk;
 extern "C" {
 
 int tbk_gen_ham(const tbk_model* m, const double* k_dev, int64_t nk, double* ham_dev, void* stream) {
+  TBK_NVTX("tbk_gen_ham");
   if (!m || !ham_dev || nk < 0 || (m->pv.dim_k > 0 && !k_dev)) { set_error("tbk_gen_ham: bad argument"); return TBK_ERR_ARG; }
   if (nk == 0) return TBK_OK;
   const size_t dyn = (size_t)((m->pv.nph > 0 ? m->pv.nph : 1) + m->pv.nsta) * 16;
@@ -840,6 +841,7 @@ int tbk_gen_ham(const tbk_model* m, const double* k_dev, int64_t nk, double* ham
 }
 
 int tbk_kmesh_uniform(const int32_t* mesh, int32_t nd, double* k_dev, void* stream) {
+  TBK_NVTX("tbk_kmesh_uniform");
   if (!mesh || !k_dev || nd < 1 || nd > TBK_MAX_DIM) { set_error("tbk_kmesh_uniform: bad argument"); return TBK_ERR_ARG; }
   KMeshDesc md;
   long long nk = 1;
@@ -865,6 +867,7 @@ size_t tbk_eigh_workspace(int32_t n, int64_t batch, int32_t) { return solve_ws_b
 
 int tbk_eigh_batched(const double* ham_dev, int32_t n, int64_t batch, double* eval_dev, double* evec_dev,
                      void* ws_dev, size_t ws_bytes, void* stream) {
+  TBK_NVTX("tbk_eigh_batched");
   if (!ham_dev || !eval_dev || n < 1 || batch < 0) { set_error("tbk_eigh_batched: bad argument"); return TBK_ERR_ARG; }
   PlanView pv;
   memset(&pv, 0, sizeof(pv));
@@ -890,6 +893,7 @@ size_t tbk_solve_workspace(int32_t nsta, int64_t nk, int32_t) { return solve_ws_
 
 int tbk_solve_k(const tbk_model* m, const double* k_dev, int64_t nk, double* eval_dev, int64_t ev_sb, int64_t ev_sk,
                 double* evec_dev, int64_t vc_sb, int64_t vc_sk, void* ws_dev, size_t ws_bytes, void* stream) {
+  TBK_NVTX("tbk_solve_k");
   if (!m || nk < 0 || (!eval_dev && !evec_dev) || (m->pv.dim_k > 0 && !k_dev)) { set_error("tbk_solve_k: bad argument"); return TBK_ERR_ARG; }
   KSrc ks;
   memset(&ks, 0, sizeof(ks));
@@ -965,12 +969,14 @@ static int launch_mesh_small(const tbk_model* m, const KSrc& ks, const OutSpec& 
     if (!ticket) { set_error("tbk_solve_grid: cannot allocate the reduction tickets"); return TBK_ERR_CUDA; }
   }
   const int gauge = (m->pv.convention == 1 && m->pv.dim_k > 0) ? 1 : 0;
-  if (peer && peer->pending.nv > 0) { if (int rc = peer_flush(peer, st)) return rc; }   // an unclaimed deferred reduction
-  const PeerView pview = !gaps_dev ? peer_next(nullptr)
-                         : (peer && peer->defer_next ? peer_next_deferred(peer, n - 1, 1, gaps_dev) : peer_next(peer));
+  // cross-rank minimum of the gaps: synchronous, or (tbk_peer_defer) only posted by this kernel — the grid solve
+  // never completes older collectives itself, so that nothing but a few stores sits between its last CTA and
+  // the dependent flux kernel
+  PeerView pview = peer_none();
+  if (gaps_dev) { if (int rc = peer_next(peer, n - 1, 1, gaps_dev, false, st, &pview)) return rc; }
   // a synchronous prepared call waits on a pinned word this kernel's last CTA writes after the gaps
   // (not for a deferred reduction: the gaps are then completed by a later kernel)
-  const DoneSignal done = (gaps_dev && !pview.defer) ? take_done_request() : DoneSignal{nullptr, 0};
+  const DoneSignal done = (gaps_dev && (pview.nranks <= 1 || pview.complete_self)) ? take_done_request() : DoneSignal{nullptr, 0};
 #define TBK_MESH_LAUNCH(NN, PP, MB, RP) \
   mesh_small_kernel<NN, PP, MB, RP><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview, cta_trace_buffer(), done)
   if (n == 2) {
@@ -1005,6 +1011,7 @@ int tbk_solve_grid(const tbk_model* m, const double* start_k, const int32_t* mes
 int tbk_solve_grid_x(const tbk_model* m, const double* start_k, const int32_t* mesh, int32_t nd, int32_t row0,
                      int32_t nrows, int32_t wrap0, double* wfs_dev, const double* pbc_phase_dev, double* gaps_dev,
                      void* ws_dev, size_t ws_bytes, tbk_peer* peer, void* stream) {
+  TBK_NVTX("tbk_solve_grid_x");
   if (!m || !start_k || !mesh || !wfs_dev || !pbc_phase_dev || nd < 1 || nd > TBK_MAX_DIM || nd != m->pv.dim_k ||
       nrows < 0 || row0 < 0 || wrap0 < 0 || wrap0 > 2) {
     set_error("tbk_solve_grid: bad argument (nd=%d dim_k=%d)", nd, m ? m->pv.dim_k : -1);

@@ -246,8 +246,8 @@ class wf_array(object):
         """Launch the fused grid solve (and, when sharded, close the slab and
         reduce the gaps over ranks); results stay engine-resident unless
         ``host_result`` asks for a host array (unsharded: zero-copy).
-        ``defer_reduce`` (sharded, device result): the minimum over the ranks is
-        completed by the next ``_berry_flux_device`` launch or ``engine.peer_flush()``."""
+        ``defer_reduce`` (sharded, device result): the minimum over the ranks is only posted by
+        this launch; a later collective launch or ``engine.peer_flush()`` completes it."""
         eng = self._model._engine()
         start = np.array(start, dtype=float).reshape(-1)
         sh = self._shard
@@ -572,16 +572,19 @@ class wf_array(object):
             raise Exception("\n\nWrong dimensionality!")
         return occ, [int(dirs[0]), int(dirs[1])]
 
-    def _berry_flux_device(self, occ, dirs=None, local_only=False, host_result=False):
+    def _berry_flux_device(self, occ, dirs=None, local_only=False, host_result=False, defer_reduce=False):
         """Total flux per 2-D slice, engine-resident (summed over ranks unless
-        ``local_only``); ``host_result`` returns a host array (unsharded: zero-copy)."""
+        ``local_only``); ``host_result`` returns a host array (unsharded: zero-copy).
+        ``defer_reduce`` (sharded, device result): the sum over the ranks is posted by this launch and
+        completed by a later one (or ``engine.peer_flush()``) — see ``_solve_on_grid_device``."""
         occ, dirs = self._check_flux_args(occ, dirs)
         eng = self._model._engine()
         if self._shard is None:
             return eng.flux_total(self._store, self._dim_arr, occ, dirs, host_result=host_result)
         sh = self._shard
         reduce_ranks = (sh.rank, sh.nranks) if (not local_only and 0 in dirs) else None
-        return eng.flux_total(self._store, self._dim_arr, occ, dirs, host_result=host_result, reduce_ranks=reduce_ranks)
+        return eng.flux_total(self._store, self._dim_arr, occ, dirs, host_result=host_result, reduce_ranks=reduce_ranks,
+                              defer_reduce=defer_reduce)
 
     def berry_flux(self, occ="All", dirs=None, individual_phases=False):
         """pythtb.py:3068-3205: plaquette phases / integrated Berry curvature on

@@ -110,7 +110,7 @@ class OracleEngine(object):
         dist.all_gather_object(parts, np.asarray(local))
         return parts
 
-    def flux_total(self, store, dim_arr, occ, dirs, host_result=False, reduce_ranks=None):
+    def flux_total(self, store, dim_arr, occ, dirs, host_result=False, reduce_ranks=None, defer_reduce=False):
         tot = np.asarray(orc.berry_flux(store.arr, dim_arr, occ, dirs, individual_phases=False)).reshape(-1)
         return self.allreduce(tot, "sum") if reduce_ranks is not None else tot
 

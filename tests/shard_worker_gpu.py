@@ -56,8 +56,9 @@ def main():
                         assert e.shape == e_ref.shape, (e.shape, e_ref.shape)
                         ok, dev = compare.sets_close(e, e_ref, 2 * np.pi, 1e-8)
                         assert ok, (d, dev)
-        # deferred gap reduction (tbk_peer_defer): posted by the solve kernel, completed by the flux kernel's
-        # exchange, by an explicit flush, or implicitly by the next solve; repeated calls exercise slot reuse
+        # deferred reductions (tbk_peer_defer): POSTED by the producing kernel, completed by a later collective
+        # kernel (a synchronous one completes everything pending; a deferred flux kernel the ones of EARLIER
+        # steps) or by an explicit flush; repeated calls exercise the slot reuse and the forced flush
         for model, occ, mesh in cases[:2]:
             full = tb.wf_array(model, mesh)
             gaps_ref = full.solve_on_grid([-0.5, -0.5])
@@ -67,15 +68,37 @@ def main():
             for rep in range(7):
                 g = w._solve_on_grid_device([-0.5, -0.5], defer_reduce=True)
                 if rep % 3 == 0:
-                    f = w._berry_flux_device(occ)
+                    f = w._berry_flux_device(occ)                                    # synchronous: completes g as well
                     assert abs(float(f.cpu().reshape(-1)[0]) - f_ref) < 1e-9
                 elif rep % 3 == 1:
                     eng.peer_flush()
                 else:
-                    g2 = w._solve_on_grid_device([-0.5, -0.5], defer_reduce=True)   # flushes the first implicitly
-                    eng.peer_barrier()                                                # ... and the barrier the second
+                    g2 = w._solve_on_grid_device([-0.5, -0.5], defer_reduce=True)   # two posted reductions in flight
+                    eng.peer_barrier()                                                # a barrier leaves them alone ...
+                    eng.peer_flush()                                                  # ... the flush completes both
                     assert np.array_equal(g2.cpu().numpy(), gaps_ref), (rep, g2, gaps_ref)
                 assert np.array_equal(g.cpu().numpy(), gaps_ref), (rep, g, gaps_ref)
+            # the pipelined step of bench.py: both reductions of a step only posted; step i's flux kernel completes
+            # the reductions of step i-1; one flush at the end.  33 steps: every mailbox slot is reused 8 times.
+            keep = []
+            for step in range(33):
+                eng.peer_barrier()
+                g = w._solve_on_grid_device([-0.5, -0.5], defer_reduce=True)
+                f = w._berry_flux_device(occ, defer_reduce=True)
+                keep.append((g, f))
+                if step >= 2:                       # results of step - 2 were completed by the flux kernel of step - 1
+                    g_old, f_old = keep[step - 2]
+                    assert np.array_equal(g_old.cpu().numpy(), gaps_ref), (step, g_old)
+                    assert abs(float(f_old.cpu().reshape(-1)[0]) - f_ref) < 1e-9, (step, f_old)
+            eng.peer_flush()
+            for g, f in keep[-2:]:
+                assert np.array_equal(g.cpu().numpy(), gaps_ref)
+                assert abs(float(f.cpu().reshape(-1)[0]) - f_ref) < 1e-9
+            # many posted solves in a row without a completer: the library flushes by itself before a slot is reused
+            gs = [w._solve_on_grid_device([-0.5, -0.5], defer_reduce=True) for _ in range(11)]
+            eng.peer_flush()
+            for g in gs:
+                assert np.array_equal(g.cpu().numpy(), gaps_ref)
         # a wider occupied set: the CTA-wide Wilson-loop kernels (nocc >= 8) across ranks
         rib = M.random_model(tb, norb=20, dim=2, nhop=40, nspin=1, seed=11)
         full = tb.wf_array(rib, [17, 9])
