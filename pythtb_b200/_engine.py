@@ -152,6 +152,17 @@ class B200Engine(object):
             self._ws = self.torch.empty(nbytes, dtype=self.torch.uint8, device=self.device)
         return self._ws
 
+    def to_host(self, t):
+        """Device tensor -> numpy array backed by PINNED host memory from torch's caching host allocator: the
+        copy runs at PCIe rate instead of through the driver's pageable staging (~2 GB/s for a 1 GB result), and a
+        sweep that drops its previous result gets the same pinned block back without paying for the pinning."""
+        if t.numel() * t.element_size() < (1 << 20):
+            return t.cpu().numpy()
+        h = self.torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        self.sync()
+        return h.numpy()
+
     def to_dev(self, arr, dtype=None):
         t = self.torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype))
         return t.to(self.device, non_blocking=False)
@@ -254,8 +265,8 @@ class B200Engine(object):
         if device_result:
             return (ev, vec) if eig_vectors else ev
         if not eig_vectors:
-            return ev.cpu().numpy()
-        return ev.cpu().numpy(), vec.cpu().numpy()
+            return self.to_host(ev)
+        return self.to_host(ev), self.to_host(vec)
 
     def solve_all(self, model, klist, eig_vectors):
         nk = klist.shape[0]
@@ -267,10 +278,10 @@ class B200Engine(object):
             return ev_h, np.zeros((model._nsta, 0) + tail, dtype=complex)
         kd = self.to_dev(klist, np.float64) if model._dim_k > 0 else None
         ev, vec = self.solve_all_device(model, kd, nk, eig_vectors)
-        ev_h = ev.cpu().numpy()
+        ev_h = self.to_host(ev)
         if not eig_vectors:
             return ev_h
-        vec_h = vec.cpu().numpy()
+        vec_h = self.to_host(vec)
         if model._nspin == 2:
             vec_h = vec_h.reshape(model._nsta, nk, model._norb, 2)
         return ev_h, vec_h
@@ -821,15 +832,24 @@ class B200Engine(object):
         batch = 1
         for x in mesh:
             batch *= int(x)
-        ed = wfs.reshape(batch, nsta, n).index_select(1, occ_t).contiguous()      # data movement only
         pos = self.to_dev(self._pos(model, dir), np.float64)
         hwfc = torch.empty((batch, nocc), dtype=torch.float64, device=self.device)
         hwf = None
         if hwf_evec:
             hwf = out_store.dev(will_write=True).reshape(batch, nocc, n)
-        ws = self.workspace(self.lib.tbk_position_hwf_workspace(nocc, n, batch))
-        _lib.check(self.lib.tbk_position_hwf(_ptr(ed), batch, nocc, n, _ptr(pos), _ptr(hwfc), _ptr(hwf), 1,
-                                             _ptr(ws), ws.numel(), self.stream()))
+        flat = wfs.reshape(batch, nsta, n)
+        # mesh points in chunks: the gathered occupied blocks and the position / eigenvector workspaces of a
+        # chunk stay below ~2 GiB each (a [129, 129] mesh of the norb-499 slab would otherwise need 3 x 33 GB
+        # of temporaries next to the 66 GB array)
+        per = max(1, nocc * max(n, nocc) * 16)
+        step = int(max(1, min(batch, (2 << 30) // per)))
+        ws = self.workspace(self.lib.tbk_position_hwf_workspace(nocc, n, step))
+        for a in range(0, batch, step):
+            b = min(batch, a + step)
+            ed = flat[a:b].index_select(1, occ_t).contiguous()                    # data movement only
+            _lib.check(self.lib.tbk_position_hwf(_ptr(ed), b - a, nocc, n, _ptr(pos), _ptr(hwfc[a:b]),
+                                                 _ptr(hwf[a:b]) if hwf is not None else ctypes.c_void_p(0), 1,
+                                                 _ptr(ws), ws.numel(), self.stream()))
         return hwfc.cpu().numpy().reshape(tuple(mesh) + (nocc,))
 
     def position_hwf(self, model, evec, dir, hwf_evec, orbital_basis):

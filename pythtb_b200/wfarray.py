@@ -377,6 +377,12 @@ class wf_array(object):
             raise Exception("\n\nWrong value of mesh_dir.")
         eng = self._model._engine()
         phase = eng.pbc_phases(self._orb, self._nspin, [k_dir], self._model._convention)[0]
+        if self._shard is not None and mesh_dir == 0:
+            # the sharded axis: every slab is closed by the first row of the next rank, the last one by rank 0's
+            # row times the phase — one ring shift (pythtb.py:2729, 2740-2741 across ranks)
+            sh = self._shard
+            eng.halo_ring_shift(self._store, self._dim_arr, phase if sh.rank == 0 else None, sh.rank, sh.nranks)
+            return
         eng.impose_boundary(self._store, self._dim_arr, mesh_dir, phase)
 
     def impose_loop(self, mesh_dir):
@@ -384,6 +390,10 @@ class wf_array(object):
         self._need_store("impose_loop")
         if mesh_dir < 0 or mesh_dir >= self._dim_arr or mesh_dir > 3:
             raise Exception("\n\nWrong value of mesh_dir.")
+        if self._shard is not None and mesh_dir == 0:
+            sh = self._shard
+            self._model._engine().halo_ring_shift(self._store, self._dim_arr, None, sh.rank, sh.nranks)
+            return
         self._model._engine().impose_boundary(self._store, self._dim_arr, mesh_dir, None)
 
     # ----------------------------------------------------- position operator

@@ -52,6 +52,24 @@ def main():
                     assert e0.shape == e0_ref.shape, (e0.shape, e0_ref.shape)
                     ok, dev = compare.sets_close(e0, e0_ref, 2 * np.pi, 1e-9)
                     assert ok, dev
+        # impose_pbc / impose_loop along the sharded axis on a manually filled array: a ring shift, not a local copy
+        mh = M.haldane(api, 0.0)
+        full = api.wf_array(mh, [9, 6])
+        full.solve_on_grid([-0.5, -0.5])
+        fa = api.wf_array(mh, [9, 6])
+        fa._wfs[...] = full._wfs
+        fa._wfs[-1] = 0.0
+        fa.impose_pbc(0, 0)
+        ws = api.wf_array(mh, [9, 6], shard=(rank, world))
+        sh = ws._shard
+        ws._wfs[...] = full._wfs[sh.row0:sh.row0 + sh.nrows + 1]
+        ws._wfs[-1] = 0.0
+        ws.impose_pbc(0, 0)
+        assert np.max(np.abs(ws._wfs - fa._wfs[sh.row0:sh.row0 + sh.nrows + 1])) < 1e-14
+        ws._wfs[-1] = 0.0
+        ws.impose_loop(0)
+        want = full._wfs[0] if sh.is_last else full._wfs[sh.row0 + sh.nrows]
+        assert np.max(np.abs(ws._wfs[-1] - want)) < 1e-14
         # streamed 1-D string (BASELINE config 4 in miniature): links dealt to the ranks, never materialised
         rib = M.bn_ribbon(api, 5)
         occ_r = list(range(rib._nsta // 2))
