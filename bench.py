@@ -421,7 +421,7 @@ def measure_mesh(tb, eng, args, workload, world, rank, local, with_cpu, cpu_seco
     ri, ci = rng.randint(0, nloc, 64), rng.randint(0, COLS, 64)
     ri[:4], ci[:4] = [0, nloc - 1, 0, nloc - 1], [0, 0, COLS - 1, COLS - 1]       # slab corners: halo row / periodic images
     got = plq[0][torch.as_tensor(ri, device=eng.device), torch.as_tensor(ci, device=eng.device)].cpu().numpy()
-    ref = _oracle_plaquettes(model, world * ROWS_PER_RANK, row0 + ri, ci)
+    ref = _oracle_plaquettes(model, occ, world * ROWS_PER_RANK, row0 + ri, ci)
     pdev = float(np.max(np.abs((got - ref + np.pi) % (2 * np.pi) - np.pi)))
     sub = _oracle_gaps(model, world * ROWS_PER_RANK, row0, row0 + nloc, 16)
     loc_gaps = eng.solve_grid(model, w._store, w._mesh_arr, np.array(START_K), row0=row0, nrows=nloc,

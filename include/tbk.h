@@ -196,6 +196,11 @@ typedef struct {
   int32_t nsta_arr;       /* states stored per mesh point (stride n between states) */
   int32_t nocc;           /* number of selected states */
   const int32_t* occ_dev; /* [nocc] indices of the selected states */
+  int64_t state_stride;   /* complex elements between consecutive states of one mesh point; 0 = n (the reference's
+                           * [k..., state, orb] layout).  A STATE-MAJOR array [state][k...][orb] has
+                           * state_stride = n * (number of mesh points) and point strides that are multiples of n:
+                           * a kernel that needs one band of a two-band model then fetches half the bytes
+                           * (64-byte DRAM lines would otherwise hold both bands of a k-point). */
 } tbk_wf_view;
 
 /* wf_array.berry_flux / _one_flux_plane (pythtb.py:3068-3205, 3840-3865).
@@ -248,10 +253,13 @@ int tbk_position_hwf(const double* evec_dev, int64_t batch, int32_t nocc, int32_
  * the row-marching flux kernel (nocc <= 2, n <= 4) and nslice <= 16; otherwise
  * TBK_ERR_UNSUPPORTED is returned before anything is launched and the caller reduces
  * with NCCL.  peer == NULL behaves exactly like the plain entry points. */
+/* state_stride (tbk_solve_grid_x / tbk_solve_grid_prepare): 0 = the slab is stored [row][i_1]..[state][orb] as
+ * described at tbk_solve_grid; > 0 = STATE-MAJOR slab [state][row][i_1]..[orb] with that many complex elements
+ * between the states of a mesh point (= n * number of local mesh points for a compact array); see tbk_wf_view. */
 int tbk_solve_grid_x(const tbk_model* model, const double* start_k_host, const int32_t* mesh_host,
                      int32_t nd, int32_t row0, int32_t nrows, int32_t wrap0,
                      double* wfs_dev, const double* pbc_phase_dev, double* gaps_dev,
-                     void* ws_dev, size_t ws_bytes, tbk_peer* peer, void* stream);
+                     void* ws_dev, size_t ws_bytes, int64_t state_stride, tbk_peer* peer, void* stream);
 int tbk_flux_plane_x(const tbk_wf_view* view, const int64_t* slice_off_dev, int64_t nslice,
                      int64_t n0, int64_t stride0, int64_t n1, int64_t stride1,
                      double* plaq_dev, double* total_dev,
@@ -296,7 +304,7 @@ typedef struct tbk_prepared tbk_prepared;
 int tbk_solve_grid_prepare(const tbk_model* model, const double* start_k, const int32_t* mesh, int32_t nd,
                            int32_t row0, int32_t nrows, int32_t wrap0, double* wfs_dev,
                            const double* pbc_phase_dev, double* gaps_dev, void* ws_dev, size_t ws_bytes,
-                           tbk_peer* peer, tbk_prepared** out);
+                           int64_t state_stride, tbk_peer* peer, tbk_prepared** out);
 int tbk_flux_plane_prepare(const tbk_wf_view* view, const int64_t* slice_off_dev, int64_t nslice, int64_t n0,
                            int64_t stride0, int64_t n1, int64_t stride1, double* plaq_dev, double* total_dev,
                            void* ws_dev, size_t ws_bytes, tbk_peer* peer, tbk_prepared** out);

@@ -42,13 +42,31 @@ class DeviceStore(object):
            'device' the device tensor is authoritative
     """
 
-    def __init__(self, engine, shape):
+    def __init__(self, engine, shape, state_axis=None):
+        """state_axis: index of the state (band) axis of `shape` when the DEVICE copy is to be stored state-major,
+        [state][mesh...][orb(,spin)] — the layout the mesh kernels of 2..4-band models write and the Berry kernels
+        read (a band's data is then contiguous: berry_flux([0]) of a two-band model fetches half the bytes).  The
+        host mirror and the tensor `dev()` returns always have the reference's logical shape; `dev()` is then a
+        permuted view of the state-major allocation."""
         self.engine = engine
         self.shape = tuple(int(x) for x in shape)
+        self.state_axis = state_axis
         self._host_t = None
         self._host = None
         self._dev = None
+        self._phys = None
         self.state = "empty"
+
+    def _alloc_dev(self):
+        torch = self.engine.torch
+        ax = self.state_axis
+        if ax is None:
+            self._phys = torch.zeros(self.shape, dtype=torch.complex128, device=self.engine.device)
+            return self._phys
+        phys_shape = (self.shape[ax],) + self.shape[:ax] + self.shape[ax + 1:]
+        self._phys = torch.zeros(phys_shape, dtype=torch.complex128, device=self.engine.device)
+        perm = list(range(1, ax + 1)) + [0] + list(range(ax + 1, len(self.shape)))
+        return self._phys.permute(perm)               # logical shape, state-major strides
 
     def host(self):
         """Host ndarray (a view the caller may mutate)."""
@@ -68,14 +86,14 @@ class DeviceStore(object):
         self._host_t = torch.empty(self.shape, dtype=torch.complex128, pin_memory=True)
         self._host = self._host_t.numpy()
         self._host[...] = arr
-        self._dev = None
+        self._dev = self._phys = None
         self.state = "host"
 
     def dev(self, will_write):
         """Device tensor, uploaded if the host mirror is newer."""
         torch = self.engine.torch
         if self._dev is None or tuple(self._dev.shape) != self.shape:
-            self._dev = torch.zeros(self.shape, dtype=torch.complex128, device=self.engine.device)
+            self._dev = self._alloc_dev()
             if self.state == "device":
                 self.state = "empty"
         if self.state == "host":
@@ -287,8 +305,8 @@ class B200Engine(object):
         return ev_h, vec_h
 
     # ------------------------------------------------------------ wf_array ops
-    def new_store(self, shape):
-        return DeviceStore(self, shape)
+    def new_store(self, shape, state_axis=None):
+        return DeviceStore(self, shape, state_axis)
 
     def pbc_phases(self, orb, nspin, k_dirs, convention=1):
         """exp(-2 pi i tau_j[k_dir]) per state (pythtb.py:2729-2736), [len(k_dirs), nsta];
@@ -362,8 +380,10 @@ class B200Engine(object):
         ws = self.workspace(self.lib.tbk_solve_workspace(n, npts, 1))
         start = (ctypes.c_double * nd)(*[float(x) for x in start_k])
         mesh = (ctypes.c_int32 * nd)(*[int(x) for x in mesh_arr])
+        # a state-major store (DeviceStore.state_axis) is told to the kernels by its state stride
+        sstride = int(wfs.stride(nd)) if store.state_axis is not None else 0
         args = (handle, start, mesh, nd, int(row0), int(nrows), int(wrap0), _ptr(wfs), _ptr(phase), _ptr(gaps),
-                _ptr(ws), ws.numel())
+                _ptr(ws), ws.numel(), sstride)
         reduced = reduce_ranks is None
         launched = False
         if gaps is not None and reduce_ranks is not None:
@@ -387,7 +407,7 @@ class B200Engine(object):
                 elif rc != _lib.ERR_UNSUPPORTED:
                     _lib.check(rc)
         if not launched:
-            _lib.check(self.lib.tbk_solve_grid(*args, self.stream()))
+            _lib.check(self.lib.tbk_solve_grid_x(*args, None, self.stream()))
             if fast_key is not None and reduce_ranks is None and (gaps is None or gaps_h is not None):
                 # keep plan / phase / start / mesh alive with the cached argument tuple
                 store.__dict__["_tbk_sg_fast"] = (fast_key, store._dev, self._ws,
@@ -451,17 +471,20 @@ class B200Engine(object):
         row goes to the last rank multiplied by the pbc phase, pythtb.py:2729)."""
         import torch.distributed as dist
         wfs = store.dev(will_write=True)
-        row = wfs[0]
+        row = wfs[0].contiguous()                 # (a copy only for a state-major store, whose rows are strided)
         nsta_arr = store.shape[dim_arr]
         n = int(np.prod(store.shape[dim_arr + 1:]))
         send = self.torch.empty_like(row)
         ph = self.to_dev(phase) if phase is not None else None
         _lib.check(self.lib.tbk_halo_pack(_ptr(row), _ptr(send), row.numel() // (nsta_arr * n), nsta_arr, n,
                                           _ptr(ph), self.stream()))
-        recv = wfs[wfs.shape[0] - 1]
+        last = wfs[wfs.shape[0] - 1]
+        recv = last if last.is_contiguous() else self.torch.empty_like(send)
         ops = [dist.P2POp(dist.isend, send, (rank - 1) % nranks), dist.P2POp(dist.irecv, recv, (rank + 1) % nranks)]
         for req in dist.batch_isend_irecv(ops):
             req.wait()
+        if recv is not last:
+            last.copy_(recv)
 
     def allreduce(self, x, op):
         """Sum / min of a small result vector over the ranks (NCCL)."""
@@ -498,6 +521,9 @@ class B200Engine(object):
         inner = int(np.prod(shape[mesh_dir + 1:dim_arr])) if mesh_dir + 1 < dim_arr else 1
         nsta_arr = shape[dim_arr]
         n = int(np.prod(shape[dim_arr + 1:]))
+        if store.state_axis is not None:
+            # state-major allocation [state][mesh...][orb]: every state plane is an array of single-state points
+            outer, nsta_arr = outer * nsta_arr, 1
         ph = self.to_dev(phase) if phase is not None else None
         _lib.check(self.lib.tbk_impose_boundary(_ptr(wfs), outer, length, inner, nsta_arr, n, _ptr(ph), self.stream()))
 
@@ -519,15 +545,11 @@ class B200Engine(object):
             if occ.min() < 0 or occ.max() >= nsta_arr:
                 raise IndexError("index in occ out of bounds")
             occ_d = self.to_dev(occ.astype(np.int32))
-            strides = []
-            for d in range(dim_arr):
-                st = nsta_arr * n
-                for x in shape[d + 1:dim_arr]:
-                    st *= int(x)
-                strides.append(st)
-            hit = cache[key] = (n, nsta_arr, len(occ), occ_d, strides)
-        n, nsta_arr, nocc, occ_d, strides = hit
-        view = _lib.WfView(wfs.data_ptr(), n, nsta_arr, nocc, occ_d.data_ptr())
+            strides = [int(wfs.stride(d)) for d in range(dim_arr)]      # mesh-axis strides, complex elements
+            sstride = int(wfs.stride(dim_arr))                          # n, or the state-major plane size
+            hit = cache[key] = (n, nsta_arr, len(occ), occ_d, strides, sstride)
+        n, nsta_arr, nocc, occ_d, strides, sstride = hit
+        view = _lib.WfView(wfs.data_ptr(), n, nsta_arr, nocc, occ_d.data_ptr(), sstride)
         return view, strides, (wfs, occ_d)
 
     def _offsets(self, store, dim_arr, axes, strides):
@@ -560,8 +582,8 @@ class B200Engine(object):
                                               int(berry_evals), _ptr(out), _ptr(ws), ws.numel(), self.stream()))
         res = out.cpu().numpy()
         if berry_evals and not np.all(np.isfinite(res)):
-            raise Exception("\n\nberry_phase(berry_evals=True): the overlap matrix of a link is singular (or not finite); "
-                            "its unitary polar factor is undefined.")
+            raise Exception("\n\nberry_phase(berry_evals=True): the wave functions of a link are not finite (NaN / Inf); "
+                            "the unitary polar factor of their overlap is undefined.")
         return res.reshape(oshape + ((nocc,) if berry_evals else ()))
 
     def wilson_phases_across_ranks(self, store, dim_arr, occ, dir, nranks):
@@ -601,8 +623,8 @@ class B200Engine(object):
         _lib.check(self.lib.tbk_wilson_phases(_ptr(mats), nstr, max(nranks, 1), nocc, _ptr(out), _ptr(ws), ws.numel(), self.stream()))
         res = out.cpu().numpy()
         if not np.all(np.isfinite(res)):
-            raise Exception("\n\nberry_phase(berry_evals=True): the overlap matrix of a link is singular (or not finite); "
-                            "its unitary polar factor is undefined.")
+            raise Exception("\n\nberry_phase(berry_evals=True): the wave functions of a link are not finite (NaN / Inf); "
+                            "the unitary polar factor of their overlap is undefined.")
         return res
 
     # ------------------------------------------------- streamed 1-D strings (BASELINE config 4)
@@ -674,7 +696,7 @@ class B200Engine(object):
                                                _ptr(gaps), _ptr(ws), ws.numel(), self.stream()))
             if gaps is not None:
                 gaps_run = gaps.clone() if gaps_run is None else torch.minimum(gaps_run, gaps)
-            view = _lib.WfView(buf.data_ptr(), n, n, nocc, occ_d.data_ptr())
+            view = _lib.WfView(buf.data_ptr(), n, n, nocc, occ_d.data_ptr(), 0)
             if berry_evals:
                 _lib.check(self.lib.tbk_wilson_products(ctypes.byref(view), _ptr(off_d), 1, c + 1, blk, _ptr(acc[ci]),
                                                         _ptr(ws), ws.numel(), self.stream()))
@@ -834,9 +856,12 @@ class B200Engine(object):
             batch *= int(x)
         pos = self.to_dev(self._pos(model, dir), np.float64)
         hwfc = torch.empty((batch, nocc), dtype=torch.float64, device=self.device)
-        hwf = None
+        hwf = hwf_log = None
         if hwf_evec:
-            hwf = out_store.dev(will_write=True).reshape(batch, nocc, n)
+            hwf_log = out_store.dev(will_write=True)
+            # (a state-major output store is filled through a contiguous staging tensor)
+            hwf = hwf_log.reshape(batch, nocc, n) if hwf_log.is_contiguous() else \
+                torch.empty((batch, nocc, n), dtype=torch.complex128, device=self.device)
         flat = wfs.reshape(batch, nsta, n)
         # mesh points in chunks: the gathered occupied blocks and the position / eigenvector workspaces of a
         # chunk stay below ~2 GiB each (a [129, 129] mesh of the norb-499 slab would otherwise need 3 x 33 GB
@@ -850,6 +875,8 @@ class B200Engine(object):
             _lib.check(self.lib.tbk_position_hwf(_ptr(ed), b - a, nocc, n, _ptr(pos), _ptr(hwfc[a:b]),
                                                  _ptr(hwf[a:b]) if hwf is not None else ctypes.c_void_p(0), 1,
                                                  _ptr(ws), ws.numel(), self.stream()))
+        if hwf_log is not None and not hwf_log.is_contiguous():
+            hwf_log.copy_(hwf.reshape(hwf_log.shape))
         return hwfc.cpu().numpy().reshape(tuple(mesh) + (nocc,))
 
     def position_hwf(self, model, evec, dir, hwf_evec, orbital_basis):

@@ -38,7 +38,7 @@ class ModelDesc(ctypes.Structure):
 class WfView(ctypes.Structure):
     """``tbk_wf_view``"""
     _fields_ = [("wfs_dev", c_void_p), ("n", c_int32), ("nsta_arr", c_int32), ("nocc", c_int32),
-                ("occ_dev", c_void_p)]
+                ("occ_dev", c_void_p), ("state_stride", c_int64)]
 
 
 class TbkError(Exception):
@@ -92,7 +92,7 @@ def load():
         "tbk_debug_profile": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64), I32]),
         "tbk_debug_cta_trace": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64), I64, I32]),
         "tbk_peer_barrier": (ctypes.c_int, [c_void_p, c_void_p]),
-        "tbk_solve_grid_prepare": (ctypes.c_int, [V, c_double_p, c_int32_p, I32, I32, I32, I32, V, V, V, V, SZ, V, ctypes.POINTER(V)]),
+        "tbk_solve_grid_prepare": (ctypes.c_int, [V, c_double_p, c_int32_p, I32, I32, I32, I32, V, V, V, V, SZ, I64, V, ctypes.POINTER(V)]),
         "tbk_flux_plane_prepare": (ctypes.c_int, [ctypes.POINTER(WfView), V, I64, I64, I64, I64, I64, V, V, V, SZ, V, ctypes.POINTER(V)]),
         "tbk_prepared_run": (ctypes.c_int, [V, V, I32]),
         "tbk_kmesh_uniform": (ctypes.c_int, [c_int32_p, I32, V, V]),
@@ -103,7 +103,7 @@ def load():
         "tbk_peer_create": (ctypes.c_int, [I32, I32, ctypes.POINTER(V), V]),
         "tbk_peer_connect": (ctypes.c_int, [V, V]),
         "tbk_peer_destroy": (ctypes.c_int, [V]),
-        "tbk_solve_grid_x": (ctypes.c_int, [V, c_double_p, c_int32_p, I32, I32, I32, I32, V, V, V, V, SZ, V, V]),
+        "tbk_solve_grid_x": (ctypes.c_int, [V, c_double_p, c_int32_p, I32, I32, I32, I32, V, V, V, V, SZ, I64, V, V]),
         "tbk_flux_plane_x": (ctypes.c_int, [ctypes.POINTER(WfView), V, I64, I64, I64, I64, I64, V, V, V, SZ, V, V]),
         "tbk_last_kernel": (ctypes.c_char_p, []),
         "tbk_launch_count": (c_int64, []),

@@ -344,7 +344,7 @@ int tbk_debug_cta_trace(uint64_t* out, int64_t max_ctas, int32_t reset) {
 // is then a visible share of the step).
 int tbk_solve_grid_prepare(const tbk_model* m, const double* start_k, const int32_t* mesh, int32_t nd, int32_t row0,
                            int32_t nrows, int32_t wrap0, double* wfs_dev, const double* pbc_phase_dev, double* gaps_dev,
-                           void* ws_dev, size_t ws_bytes, tbk_peer* peer, tbk_prepared** out) {
+                           void* ws_dev, size_t ws_bytes, int64_t state_stride, tbk_peer* peer, tbk_prepared** out) {
   if (!m || !start_k || !mesh || !out || nd < 1 || nd > TBK_MAX_DIM) { set_error("tbk_solve_grid_prepare: bad argument"); return TBK_ERR_ARG; }
   std::vector<double> sk(start_k, start_k + nd);
   std::vector<int32_t> ms(mesh, mesh + nd);
@@ -352,7 +352,7 @@ int tbk_solve_grid_prepare(const tbk_model* m, const double* start_k, const int3
   p->done_flag = nullptr; p->done_seq = 0;
   p->run = [=](void* stream) {
     return tbk_solve_grid_x(m, sk.data(), ms.data(), nd, row0, nrows, wrap0, wfs_dev, pbc_phase_dev, gaps_dev, ws_dev,
-                            ws_bytes, peer, stream);
+                            ws_bytes, state_stride, peer, stream);
   };
   *out = p;
   return TBK_OK;

@@ -22,6 +22,7 @@ struct WfView {
   const cplx* wfs;
   int n, nsta_arr, nocc;
   const int* occ;
+  long long ss;          // elements between the states of one mesh point (n for the reference layout)
 };
 
 // unit-modulus (or zero) determinant of the overlap between the occupied blocks at two mesh points
@@ -35,7 +36,7 @@ __device__ __forceinline__ cplx link_det_small(const WfView& v, const cplx* __re
     cplx a[NOCC], b[NOCC];
 #pragma unroll
     for (int m = 0; m < NOCC; ++m) {
-      const long long so = (long long)v.occ[m] * n + o;
+      const long long so = (long long)v.occ[m] * v.ss + o;
       a[m] = pa[so];
       b[m] = pb[so];
     }
@@ -175,10 +176,10 @@ struct OccState {
 #pragma unroll
       for (int o = 0; o < N; ++o) u[m][o] = mk(0.0, 0.0);
   }
-  __device__ __forceinline__ void load(const cplx* __restrict__ p, const int* occ) {
+  __device__ __forceinline__ void load(const cplx* __restrict__ p, const long long* occ) {   // occ[m]: element offset of state m
 #pragma unroll
     for (int m = 0; m < NOCC; ++m) {
-      const double2* src = reinterpret_cast<const double2*>(p + occ[m] * N);
+      const double2* src = reinterpret_cast<const double2*>(p + occ[m]);
 #pragma unroll
       for (int o = 0; o < N; ++o) { const double2 t = __ldg(src + o); u[m][o] = mk(t.x, t.y); }
     }
@@ -231,9 +232,9 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
   // stream (typically the grid solve that writes the array read here) was still draining; everything it
   // wrote is visible after this wait.  A no-op when launched without the attribute.
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  int occ[NOCC];
+  long long occ[NOCC];
 #pragma unroll
-  for (int m = 0; m < NOCC; ++m) occ[m] = v.occ[m];
+  for (int m = 0; m < NOCC; ++m) occ[m] = (long long)v.occ[m] * v.ss;
   const long long p0 = n0 - 1, p1 = n1 - 1;
   const long long per_slice = tl.nrb * tl.nstrip;
   // one slice (the usual 2-D mesh): a warp keeps adding its items up and the CTA writes ONE partial, so the
@@ -851,7 +852,7 @@ __device__ void cta_gemm_dmma(const GemmSide& A, int ma, const GemmSide& B, int 
 // overlap of the occupied blocks of two mesh points: M[m][q] = sum_o conj(A[m][o]) B[q][o]
 __device__ __forceinline__ void cta_overlap_dmma(const WfView& v, const cplx* __restrict__ pa, const cplx* __restrict__ pb,
                                                  cplx* __restrict__ M, int ld, OvSmem& sm) {
-  const GemmSide A{pa, v.n, 1, v.occ, 1}, B{pb, v.n, 1, v.occ, 0};
+  const GemmSide A{pa, v.ss, 1, v.occ, 1}, B{pb, v.ss, 1, v.occ, 0};
   cta_gemm_dmma(A, v.nocc, B, v.nocc, v.n, nullptr, M, ld, sm);
 }
 
@@ -963,9 +964,11 @@ link_matrix_kernel(WfView v, LinkMap map, long long nlinks, int mode, cplx* __re
         // unitary polar factor by Newton-Schulz, X <- X (3 I - X^H X) / 2, both products on the DMMA GEMM.
         // The iteration converges for |X|_2 < sqrt(3).  The overlap of two orthonormal sets has singular values
         // in (0, 1]; whatever else is in the array (user-filled, not normalised) is first scaled by the
-        // spectral-norm bound sqrt(|X|_1 |X|_inf) >= |X|_2 whenever that bound exceeds 1.7.  A (nearly)
-        // singular overlap does not converge: the result is then poisoned with NaN instead of returning the
-        // phases of a non-unitary product (the host raises).
+        // spectral-norm bound sqrt(|X|_1 |X|_inf) >= |X|_2 whenever that bound exceeds 1.7, so the iteration cannot
+        // diverge.  Singular directions of an overlap (sigma = 0: symmetry-enforced orthogonality between the two
+        // occupied sets, e.g. a surface band crossing the chosen filling at a high-symmetry k) stay zero: the result
+        // is the partial isometry sum_{sigma > 0} u v^H, where the reference's SVD puts an arbitrary unitary
+        // completion of the null spaces.  Only a non-finite iterate (NaN / Inf in the array) is poisoned with NaN.
         cplx* X = M;
         cplx* G = M + (size_t)nocc * ld;
         cplx* Xn = G + (size_t)nocc * ld;
@@ -1002,7 +1005,9 @@ link_matrix_kernel(WfView v, LinkMap map, long long nlinks, int mode, cplx* __re
             G[(size_t)r * ld + c] = mk((r == c ? 1.0 : 0.0) - 0.5 * gg.re, -0.5 * gg.im);   // 1.5 I - 0.5 G
           }
           dev = block_sum(dev, red);
-          if (!(dev > 1.0e-28 * nocc)) { converged = dev == dev; break; }          // |X^H X - I|_F <= 1e-14 sqrt(nocc)
+          if (!(dev == dev) || dev > 1.0e300) break;                              // NaN / Inf in the input
+          converged = true;                                                       // finite: X is the best iterate so far
+          if (!(dev > 1.0e-28 * nocc)) break;                                     // |X^H X - I|_F <= 1e-14 sqrt(nocc)
           const GemmSide A2{X, ld, 1, nullptr, 0}, B2{G, 1, ld, nullptr, 0};
           cta_gemm_dmma(A2, nocc, B2, nocc, nocc, nullptr, Xn, ld, ov);          // Xn = X P
           for (int idx = threadIdx.x; idx < nocc * nocc; idx += blockDim.x) {
@@ -1054,8 +1059,8 @@ link_small_kernel(WfView v, LinkMap map, long long nlinks, int mode, cplx* __res
   for (int m = 0; m < NOCC; ++m)
     for (int q = 0; q < NOCC; ++q) {
       cplx acc = mk(0.0, 0.0);
-      const cplx* ra = pa + (long long)v.occ[m] * v.n;
-      const cplx* rb = pb + (long long)v.occ[q] * v.n;
+      const cplx* ra = pa + (long long)v.occ[m] * v.ss;
+      const cplx* rb = pb + (long long)v.occ[q] * v.ss;
       for (int o = 0; o < v.n; ++o) fma_acc_conj(acc, ra[o], rb[o]);
       M[m * NOCC + q] = acc;
     }
@@ -1504,7 +1509,8 @@ int tbk_flux_plane_x(const tbk_wf_view* view, const int64_t* slice_off_dev, int6
     return TBK_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  WfView v{(const cplx*)view->wfs_dev, view->n, view->nsta_arr, view->nocc, view->occ_dev};
+  WfView v{(const cplx*)view->wfs_dev, view->n, view->nsta_arr, view->nocc, view->occ_dev,
+           view->state_stride > 0 ? (long long)view->state_stride : (long long)view->n};
   const long long p0 = n0 - 1, p1 = n1 - 1;
   const long long bx = (p1 + 255) / 256;
   if (p0 > 65535 || nslice > 65535) { set_error("tbk_flux_plane: mesh too large for one launch"); return TBK_ERR_UNSUPPORTED; }
@@ -1523,7 +1529,7 @@ int tbk_flux_plane_x(const tbk_wf_view* view, const int64_t* slice_off_dev, int6
   // active and pays one halo row per tile, so on the 1024 x 1024 mesh it is 1-2 us slower: not the default.
   const char* ring_env = getenv("TBK_FLUX_RING");
   const bool ring_on = ring_env && atoi(ring_env) == 1;
-  if (rows_kernel && ring_on && stride1 == (long long)view->nsta_arr * view->n && n1 >= 64 &&
+  if (rows_kernel && ring_on && v.ss == view->n && stride1 == (long long)view->nsta_arr * view->n && n1 >= 64 &&
       ((uintptr_t)view->wfs_dev & 15) == 0) {
     double* part2 = (double*)ws;
     int rc = TBK_OK;
@@ -1603,7 +1609,8 @@ int tbk_berry_strings(const tbk_wf_view* view, const int64_t* string_off_dev, in
     return TBK_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  WfView v{(const cplx*)view->wfs_dev, view->n, view->nsta_arr, view->nocc, view->occ_dev};
+  WfView v{(const cplx*)view->wfs_dev, view->n, view->nsta_arr, view->nocc, view->occ_dev,
+           view->state_stride > 0 ? (long long)view->state_stride : (long long)view->n};
   LinkMap map{(const long long*)string_off_dev, npts, 1, stride, 0, 0};
   const long long nlink = npts - 1, nlinks = nstr * nlink;
   char* ws = (char*)ws_dev;
@@ -1639,7 +1646,8 @@ int tbk_wilson_products(const tbk_wf_view* view, const int64_t* string_off_dev, 
     return TBK_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  WfView v{(const cplx*)view->wfs_dev, view->n, view->nsta_arr, view->nocc, view->occ_dev};
+  WfView v{(const cplx*)view->wfs_dev, view->n, view->nsta_arr, view->nocc, view->occ_dev,
+           view->state_stride > 0 ? (long long)view->state_stride : (long long)view->n};
   LinkMap map{(const long long*)string_off_dev, npts, 1, stride, 0, 0};
   const long long nlink = npts - 1, nlinks = nstr * nlink;
   const size_t nn = (size_t)view->nocc * view->nocc;

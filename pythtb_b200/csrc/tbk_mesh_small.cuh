@@ -65,7 +65,7 @@ __device__ __noinline__ void mesh_store_images(const EigRows<N>& e, const OutSpe
 #pragma unroll
     for (int b = 0; b < N; ++b)
 #pragma unroll
-      for (int o = 0; o < N; ++o) dsti[b * N + o] = im[b][o];
+      for (int o = 0; o < N; ++o) dsti[b * out.sstride + o] = im[b][o];
   }
 }
 
@@ -75,22 +75,23 @@ __device__ __forceinline__ void st256(cplx* p, cplx a, cplx b) {
 }
 // WIDE = false: plain 16-byte stores (cold paths; ptxas 12.9 truncates the v4.f64 asm store to its first
 // element when the operands are reloaded from local memory inside an out-of-line function).
+// ss: elements between the states of the point (N for the reference layout; a multiple of 2 for WIDE)
 template <int N, bool WIDE>
-__device__ __forceinline__ void mesh_store_point(cplx* dst, const cplx (&w)[N][N]) {
+__device__ __forceinline__ void mesh_store_point(cplx* dst, const cplx (&w)[N][N], long long ss) {
   if constexpr (N == 2 && WIDE) {
     st256(dst, w[0][0], w[0][1]);
-    st256(dst + 2, w[1][0], w[1][1]);
+    st256(dst + ss, w[1][0], w[1][1]);
   } else if constexpr (N == 4 && WIDE) {
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      st256(dst + 4 * b, w[b][0], w[b][1]);
-      st256(dst + 4 * b + 2, w[b][2], w[b][3]);
+      st256(dst + ss * b, w[b][0], w[b][1]);
+      st256(dst + ss * b + 2, w[b][2], w[b][3]);
     }
   } else {
 #pragma unroll
     for (int b = 0; b < N; ++b)
 #pragma unroll
-      for (int o = 0; o < N; ++o) dst[b * N + o] = w[b][o];
+      for (int o = 0; o < N; ++o) dst[b * ss + o] = w[b][o];
   }
 }
 
@@ -106,19 +107,19 @@ __device__ __noinline__ void mesh_store_special(EigRows<N>& e, const OutSpec& ou
       for (int b = 0; b < N; ++b) e.w[b][o] = mul_fixed(e.w[b][o], ph);
     }
   }
-  mesh_store_point<N, false>(out.evec + at, e.w);
+  mesh_store_point<N, false>(out.evec + at, e.w, out.sstride);
   if (zero_mask) mesh_store_images<N>(e, out, at, zero_mask);
 }
 
 // periodic image of one point along one axis: every component times that axis' pbc phase, 256-bit stores
 template <int N>
-__device__ __forceinline__ void mesh_store_image(cplx* dst, const cplx (&w)[N][N], const cplx* ph) {
+__device__ __forceinline__ void mesh_store_image(cplx* dst, const cplx (&w)[N][N], const cplx* ph, long long ss) {
   cplx im[N][N];
 #pragma unroll
   for (int b = 0; b < N; ++b)
 #pragma unroll
     for (int o = 0; o < N; ++o) im[b][o] = mul_fixed(w[b][o], ph[o]);
-  mesh_store_point<N, true>(dst, im);
+  mesh_store_point<N, true>(dst, im, ss);
 }
 
 struct MeshRow {                                    // per mesh row (outer index), shared memory
@@ -167,6 +168,7 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
   const int nph = EXACT ? NPH : ds.nph;   // phases p >= nph are skipped (uniform predicate)
   const int tid = threadIdx.x;
   const long long gs_last = out.gstride[last];
+  const long long ss = out.sstride;
   double gmin[N - 1];
 #pragma unroll
   for (int b = 0; b < N - 1; ++b) gmin[b] = INFINITY;
@@ -325,7 +327,7 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
           const MeshRow mr = s_row[rr[u]];
           const int special = last == 0 ? special_j : (mr.flags | zlast);
           if (special == 0) {                       // the common case: one test, two 256-bit stores
-            mesh_store_point<N, true>(dst_col + mr.base, w[u]);
+            mesh_store_point<N, true>(dst_col + mr.base, w[u], ss);
             continue;
           }
           const int zm = mr.flags & 15;
@@ -346,9 +348,9 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
               }
             }
             cplx* const dst = dst_col + mr.base;
-            mesh_store_point<N, true>(dst, w[u]);
+            mesh_store_point<N, true>(dst, w[u], ss);
             const long long img_last = (long long)(out.full[last] - 1) * gs_last;
-            if (zlast) mesh_store_image<N>(dst + img_last, w[u], s_pbc[last]);
+            if (zlast) mesh_store_image<N>(dst + img_last, w[u], s_pbc[last], ss);
             if (zm) {                               // image row along the one wrapped outer axis at index 0
               const int d = __ffs(zm) - 1;
               cplx wi[N][N];
@@ -357,8 +359,8 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
 #pragma unroll
                 for (int o = 0; o < N; ++o) wi[b][o] = mul_fixed(w[u][b][o], s_pbc[d][o]);
               cplx* const dsti = dst + (long long)(out.full[d] - 1) * out.gstride[d];
-              mesh_store_point<N, true>(dsti, wi);
-              if (zlast) mesh_store_image<N>(dsti + img_last, wi, s_pbc[last]);
+              mesh_store_point<N, true>(dsti, wi, ss);
+              if (zlast) mesh_store_image<N>(dsti + img_last, wi, s_pbc[last], ss);
             }
           }
         }

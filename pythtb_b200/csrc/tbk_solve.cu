@@ -40,6 +40,7 @@ struct OutSpec {
   int cnt[TBK_MAX_DIM];            // solved points per axis
   int full[TBK_MAX_DIM];           // storage extent per axis
   long long gstride[TBK_MAX_DIM];  // storage stride per axis, complex elements
+  long long sstride;               // storage stride between the states (bands) of one mesh point (n: [k..., state, orb])
   int wrap[TBK_MAX_DIM];           // write the periodic image along this axis
   const cplx* pbc_phase;           // [nd][n]
   unsigned long long* gaps_bits;   // [n-1] running min of non-negative doubles, or null
@@ -253,7 +254,7 @@ solve_small_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long lon
 #pragma unroll
       for (int b = 0; b < N; ++b)
 #pragma unroll
-        for (int o = 0; o < N; ++o) dst[b * N + o] = w[b][o];
+        for (int o = 0; o < N; ++o) dst[b * out.sstride + o] = w[b][o];
       // periodic images (impose_pbc, pythtb.py:2729-2747), every subset of the
       // axes on which this point sits at index 0
       int zero_mask = 0;
@@ -281,7 +282,7 @@ solve_small_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long lon
 #pragma unroll
           for (int b = 0; b < N; ++b)
 #pragma unroll
-            for (int o = 0; o < N; ++o) dsti[b * N + o] = im[b][o];
+            for (int o = 0; o < N; ++o) dsti[b * out.sstride + o] = im[b][o];
         }
       }
     }
@@ -394,7 +395,7 @@ __device__ void solve_one_matrix(G& g, const PlanView& pv, const KSrc& ks, const
       const int i = q / n, o = q - i * n;
       cplx v = A[o + (size_t)i * lda] * s.work[o];
       if (closing) v = v * out.pbc_phase[o];      // image of global row 0 (same two-step rounding as the unsharded image)
-      const long long at = (long long)rank[i] * n + o;
+      const long long at = (long long)rank[i] * out.sstride + o;
       out.evec[base + at] = v;
       if (zero_mask) {
         for (int m = 1; m < (1 << out.nd); ++m) {
@@ -589,7 +590,7 @@ solve_blocked_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long l
           out.evec[c * out.vc_sb + idx * out.vc_sk + o] = v;
         } else {
           if (closing) v = v * out.pbc_phase[o];
-          const long long at = (long long)c * n + o;
+          const long long at = (long long)c * out.sstride + o;
           out.evec[base + at] = v;
           if (zero_mask) {
             for (int mm = 1; mm < (1 << out.nd); ++mm) {
@@ -916,7 +917,7 @@ int tbk_solve_k(const tbk_model* m, const double* k_dev, int64_t nk, double* eva
 static bool mesh_small_takes(const tbk_model* m, const OutSpec& out) {
   const int n = m->pv.nsta, nd = out.nd;
   if (!m->dense.valid || n < 2 || n > 4) return false;
-  if (((uintptr_t)out.evec & 31) != 0) return false;
+  if (((uintptr_t)out.evec & 31) != 0 || ((out.sstride * 16) & 31) != 0) return false;
   if (nd > 1 && out.cnt[nd - 1] < 48) return false;   // too few points along the fastest axis to fill a CTA row
   long long nseg = (out.cnt[nd - 1] + kMeshThreads - 1) / kMeshThreads;
   for (int d = 0; d < nd - 1; ++d) nseg *= out.cnt[d];
@@ -929,7 +930,7 @@ static int launch_mesh_small(const tbk_model* m, const KSrc& ks, const OutSpec& 
   const int n = m->pv.nsta, nd = out.nd;
   if (!ds.valid || n < 2 || n > 4) return 0;
   if (nd > 1 && out.cnt[nd - 1] < 48) return 0;       // too few points along the fastest axis to fill a CTA row
-  if (((uintptr_t)out.evec & 31) != 0) return 0;      // 256-bit stores need a 32-byte aligned array
+  if (((uintptr_t)out.evec & 31) != 0 || ((out.sstride * 16) & 31) != 0) return 0;      // 256-bit stores need a 32-byte aligned array
   MeshTiling tl;
   long long outer = 1;
   for (int d = 0; d < nd - 1; ++d) outer *= out.cnt[d];
@@ -1005,15 +1006,15 @@ int tbk_solve_grid(const tbk_model* m, const double* start_k, const int32_t* mes
                    int32_t nrows, int32_t wrap0, double* wfs_dev, const double* pbc_phase_dev, double* gaps_dev,
                    void* ws_dev, size_t ws_bytes, void* stream) {
   return tbk_solve_grid_x(m, start_k, mesh, nd, row0, nrows, wrap0, wfs_dev, pbc_phase_dev, gaps_dev, ws_dev, ws_bytes,
-                          nullptr, stream);
+                          0, nullptr, stream);
 }
 
 int tbk_solve_grid_x(const tbk_model* m, const double* start_k, const int32_t* mesh, int32_t nd, int32_t row0,
                      int32_t nrows, int32_t wrap0, double* wfs_dev, const double* pbc_phase_dev, double* gaps_dev,
-                     void* ws_dev, size_t ws_bytes, tbk_peer* peer, void* stream) {
+                     void* ws_dev, size_t ws_bytes, int64_t state_stride, tbk_peer* peer, void* stream) {
   TBK_NVTX("tbk_solve_grid_x");
   if (!m || !start_k || !mesh || !wfs_dev || !pbc_phase_dev || nd < 1 || nd > TBK_MAX_DIM || nd != m->pv.dim_k ||
-      nrows < 0 || row0 < 0 || wrap0 < 0 || wrap0 > 2) {
+      nrows < 0 || row0 < 0 || wrap0 < 0 || wrap0 > 2 || state_stride < 0) {
     set_error("tbk_solve_grid: bad argument (nd=%d dim_k=%d)", nd, m ? m->pv.dim_k : -1);
     return TBK_ERR_ARG;
   }
@@ -1037,8 +1038,12 @@ int tbk_solve_grid_x(const tbk_model* m, const double* start_k, const int32_t* m
     out.wrap[d] = d == 0 ? (wrap0 == 1) : 1;
     npts *= out.cnt[d];
   }
-  long long stride = (long long)n * n;
+  // k-major [row][i_1]..[state][orb]: a mesh point is n*n contiguous elements; state-major [state][row][i_1]..[orb]:
+  // a mesh point is n elements per state, the states state_stride apart
+  long long stride = state_stride > 0 ? (long long)n : (long long)n * n;
   for (int d = nd - 1; d >= 0; --d) { out.gstride[d] = stride; stride *= out.full[d]; }
+  out.sstride = state_stride > 0 ? (long long)state_stride : (long long)n;
+  if (state_stride > 0 && state_stride < stride) { set_error("tbk_solve_grid: state_stride smaller than one state plane"); return TBK_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 1) {
     if (npts > 0) solve_n1_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(m->pv, ks, nullptr, npts, out, 1);

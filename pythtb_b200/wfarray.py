@@ -133,13 +133,23 @@ class wf_array(object):
             self._start_k = None
             self._rp_sg = self._rp_fx = None
             return
-        self._store = self._model._engine().new_store(self._wfs_shape(self._nsta_arr))
+        self._store = self._new_store(self._nsta_arr)
         self._rp_sg = self._rp_fx = None    # replay records of the last solve_on_grid / berry_flux call
 
     def _need_store(self, what):
         if self._store is None:
             raise Exception("\n\n" + what + " is not available on a wf_array created with stream=True"
                             "\n(its wave functions are never stored).")
+
+    def _new_store(self, nsta):
+        """Storage for `nsta` states per mesh point.  Models whose states fit the register-resident kernels
+        (nsta * nspin components <= 4, 2-D and higher meshes) keep their DEVICE copy state-major — a band's data
+        contiguous — which halves what `berry_flux([0])` of a two-band model has to fetch; `_wfs` on the host has
+        the reference's shape either way."""
+        shape = self._wfs_shape(nsta)
+        eng = self._model._engine()
+        small = int(nsta) <= 4 and self._norb * self._nspin <= 4 and self._dim_arr >= 2
+        return eng.new_store(shape, state_axis=(self._dim_arr if small else None))
 
     def _local_mesh(self):
         mesh = [int(m) for m in self._mesh_arr]
@@ -165,7 +175,7 @@ class wf_array(object):
             setattr(new, k, copy.deepcopy(v, memo))
         if self._store is None:
             return new
-        new._store = self._model._engine().new_store(self._store.shape)
+        new._store = self._model._engine().new_store(self._store.shape, state_axis=getattr(self._store, "state_axis", None))
         if self._store.state != "empty":
             new._store.replace_host(np.array(self._store.host(), copy=True))
         return new
@@ -339,7 +349,7 @@ class wf_array(object):
         new = copy.deepcopy(self)
         if nsta_arr is not None:
             new._nsta_arr = nsta_arr
-            new._store = self._model._engine().new_store(self._wfs_shape(nsta_arr))
+            new._store = new._new_store(nsta_arr)
         return new
 
     # -------------------------------------------------------------- indexing

@@ -31,8 +31,8 @@ class _HostStore(object):
 class OracleEngine(object):
     """Same method set as pythtb_b200._engine.B200Engine, numpy arithmetic."""
 
-    def new_store(self, shape):
-        return _HostStore(shape)
+    def new_store(self, shape, state_axis=None):
+        return _HostStore(shape)                  # (the device layout option of the product engine does not apply)
 
     def gen_ham(self, model, klist):
         return orc.gen_ham(model, klist if model._dim_k > 0 else None)

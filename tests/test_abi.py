@@ -52,7 +52,7 @@ def test_new_entry_points_validate_arguments_without_gpu():
     from pythtb_b200 import _lib
     lib = _lib.load()
     out = ctypes.c_void_p(0)
-    assert lib.tbk_solve_grid_prepare(None, None, None, 2, 0, 4, 1, None, None, None, None, 0, None, ctypes.byref(out)) == -1
+    assert lib.tbk_solve_grid_prepare(None, None, None, 2, 0, 4, 1, None, None, None, None, 0, 0, None, ctypes.byref(out)) == -1
     assert lib.tbk_flux_plane_prepare(None, None, 1, 4, 4, 4, 1, None, None, None, 0, None, ctypes.byref(out)) == -1
     assert lib.tbk_prepared_run(None, None, 0) == -1
     assert lib.tbk_prepared_destroy(None) == 0
