@@ -250,7 +250,7 @@ class B200Engine(object):
         wfs = store.dev(will_write=True)            # uploads the host mirror first if that is the newer copy
         stride = [int(x) for x in wfs.stride()]     # in complex elements
         base = sum(int(fixed[d]) * stride[d] for d in fixed)
-        fshape = [int(store.shape[d]) for d in free]
+        fshape = [int(store.shape[d]) for d in free]        # (a shard's store has its local extents)
         nk = fshape[-1]
         outer = fshape[:-1]
         kd = self.to_dev(kpts.reshape(-1, plan.dim_k), np.float64)

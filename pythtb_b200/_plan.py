@@ -155,6 +155,17 @@ def compile_plan(model, convention=1):
                 add(i * nspin + s, j * nspin + sp, blk[s, sp], ph_f)
                 add(j * nspin + sp, i * nspin + s, np.conj(blk[s, sp]), ph_c)
 
+    table_R = np.zeros((len(table), max(dim_k, 1)), dtype=np.float64)
+    for key, idx in table.items():
+        table_R[idx, :dim_k] = key
+    tau = np.zeros((max(nsta, 1), max(dim_k, 1)), dtype=np.float64)
+    if dim_k > 0:
+        tau[:nsta, :dim_k] = np.repeat(np.asarray(model._orb, dtype=float)[:, per], nspin, axis=0)
+    return _finish_plan(rows, cols, amps, phs, table_R, tau, dim_k, nsta, norb, nspin, convention)
+
+
+def _finish_plan(rows, cols, amps, phs, table_R, tau, dim_k, nsta, norb, nspin, convention):
+    """Term lists (reference accumulation order) -> Plan with its two CSR orderings."""
     nterm = len(rows)
     rows = np.array(rows, dtype=np.int64)
     cols = np.array(cols, dtype=np.int64)
@@ -162,14 +173,10 @@ def compile_plan(model, convention=1):
     phs = np.array(phs, dtype=np.int64)
     p = Plan()
     p.dim_k, p.nsta, p.norb, p.nspin, p.convention = dim_k, nsta, norb, nspin, convention
-    p.nph = len(table)
+    p.nph = int(table_R.shape[0])
     p.ph_R = np.zeros((max(p.nph, 1), max(dim_k, 1)), dtype=np.float64)
-    for key, idx in table.items():
-        p.ph_R[idx, :dim_k] = key
-    tau = np.zeros((max(nsta, 1), max(dim_k, 1)), dtype=np.float64)
-    if dim_k > 0:
-        tau[:nsta, :dim_k] = np.repeat(np.asarray(model._orb, dtype=float)[:, per], nspin, axis=0)
-    p.tau = tau
+    p.ph_R[:p.nph, :dim_k] = table_R[:, :dim_k]
+    p.tau = np.ascontiguousarray(tau, dtype=np.float64)
     # ---- element-major CSR (stable: keeps the reference's accumulation order)
     key = rows * nsta + cols
     order = np.argsort(key, kind="stable")
@@ -201,3 +208,59 @@ def compile_plan(model, convention=1):
         p.el_row = np.zeros(1, dtype=np.int32)
         p.el_col = np.zeros(1, dtype=np.int32)
     return p
+
+
+def reduce_plan(p, axis, value):
+    """Plan of ``model.reduce_dim(per[axis], value)`` (pythtb.py:1233-1311) obtained from the PARENT's plan with
+    array operations — no Python model is rebuilt, no hopping list is walked:
+
+        H_red(k') = H(k', k_axis = value).
+
+    The factor exp(+-2 pi i value R_axis) of every term moves from the phase into its amplitude, the phase table
+    loses a column (vectors that coincide afterwards are merged, vectors that vanish turn their terms into
+    constants), and for Convention I the constant diagonal gauge Phi = diag(exp(2 pi i value tau_o[axis])) is
+    folded in as Phi^H H Phi, so that the kernels' eigenvectors carry exactly the phases of the reduced reference
+    model (whose hopping amplitudes contain exp(2 pi i value (tau_j - tau_i + R)[axis]))."""
+    if p.dim_k < 1 or not (0 <= axis < p.dim_k):
+        raise Exception("\n\nSpecified wrong dimension to reduce!")
+    nterm, nel, nph, dk = p.nterm, p.nel, p.nph, p.dim_k
+    counts = np.diff(p.el_ptr[:nel + 1].astype(np.int64)) if nel else np.zeros(0, dtype=np.int64)
+    rows = np.repeat(p.el_row[:nel].astype(np.int64), counts)
+    cols = np.repeat(p.el_col[:nel].astype(np.int64), counts)
+    phs = p.t_ph[:nterm].astype(np.int64)
+    amps = np.ascontiguousarray(p.t_amp[:nterm]).view(complex).reshape(-1).copy()
+    has = phs >= 0
+    idx = np.where(has, phs & (PH_CONJ - 1), 0)
+    cj = has & ((phs & PH_CONJ) != 0)
+    R = p.ph_R[:nph, :dk] if nph else np.zeros((0, dk))
+    r_axis = np.where(has, R[idx, axis] if nph else 0.0, 0.0)
+    r_axis = np.where(cj, -r_axis, r_axis)
+    fac = np.exp(2.0j * np.pi * value * r_axis)
+    if p.convention == 1:
+        phi = np.exp(2.0j * np.pi * value * p.tau[:p.nsta, axis])
+        fac = fac * np.conj(phi[rows]) * phi[cols]
+    amps = amps * fac
+    # ---- the phase table without the fixed component: canonical sign, merged duplicates, first-seen order
+    Rn = np.rint(np.delete(R, axis, axis=1)).astype(np.int64)              # [nph, dk-1]
+    new_id = np.full(nph, -1, dtype=np.int64)
+    flip = np.zeros(nph, dtype=bool)
+    table_R = np.zeros((0, max(dk - 1, 1)))
+    if dk - 1 > 0 and nph > 0:
+        nz = Rn != 0
+        hasnz = nz.any(axis=1)
+        first = np.argmax(nz, axis=1)
+        sgn = np.sign(Rn[np.arange(nph), first])
+        flip = sgn < 0
+        canon = Rn * np.where(flip, -1, 1)[:, None]
+        if hasnz.any():
+            uniq, first_seen, inv = np.unique(canon[hasnz], axis=0, return_index=True, return_inverse=True)
+            order = np.argsort(first_seen, kind="stable")                  # ids in first-seen order
+            rank = np.empty(len(order), dtype=np.int64)
+            rank[order] = np.arange(len(order))
+            new_id[hasnz] = rank[np.asarray(inv).reshape(-1)]
+            table_R = uniq[order].astype(np.float64)
+    nid = np.where(has, new_id[idx] if nph else -1, -1)
+    ncj = cj ^ (flip[idx] if nph else False)
+    phs2 = np.where(nid >= 0, nid | np.where(ncj, PH_CONJ, 0), -1)
+    tau = np.delete(p.tau, axis, axis=1) if dk - 1 > 0 else np.zeros((max(p.nsta, 1), 1))
+    return _finish_plan(rows, cols, amps, phs2, table_R, tau, dk - 1, p.nsta, p.norb, p.nspin, p.convention)

@@ -20,6 +20,22 @@ import numpy as np
 __all__ = ["tb_model"]
 
 
+class _LazyAttr(object):
+    """Data descriptor: an attribute of a lazily reduced model that triggers the materialisation when read."""
+
+    def __init__(self, name):
+        self.slot = "_lazy_" + name
+
+    def __get__(self, obj, objtype=None):
+        if obj is None:
+            return self
+        obj._materialise()
+        return obj.__dict__[self.slot]
+
+    def __set__(self, obj, value):
+        obj.__dict__[self.slot] = value
+
+
 def _is_int(a):
     return np.issubdtype(type(a), np.integer)
 
@@ -137,6 +153,7 @@ class tb_model(object):
     # ------------------------------------------------------------------ helpers
     def _touch(self):
         self._plan_cache = None
+        self.__dict__["_version"] = self.__dict__.get("_version", 0) + 1     # witnessed by lazily reduced views
 
     def _rper(self, ind_R):
         if self._dim_k == 0:
@@ -479,10 +496,20 @@ class tb_model(object):
                     fin.set_hop(h[0], hi, hj, ind_R, mode="add", allow_conjugate_pair=True)
         return fin
 
-    def reduce_dim(self, remove_k, value_k):
-        """pythtb.py:1233-1311: fix one k component, fold its phase into the amplitudes."""
+    def reduce_dim(self, remove_k, value_k, lazy=False):
+        """pythtb.py:1233-1311: fix one k component, fold its phase into the amplitudes.
+
+        ``lazy=True`` (extension, SURVEY.md section 8f: parameter sweeps ``for kx in ...: model.reduce_dim(0, kx)``):
+        the reduced model is obtained from THIS model's compiled plan with array operations
+        (``_plan.reduce_plan``: H_red(k') = H(k', k_remove = value)) — no hopping list is walked and no Python
+        model is rebuilt per value; ``_hoppings`` / ``_site_energies`` of the returned model are materialised with
+        the reference algorithm only if something reads them."""
+        if lazy:
+            return _ReducedMixin._make(self, remove_k, value_k)
         if self._dim_k == 0:
             raise Exception("\n\nCan not reduce dimensionality even further!")
+        if hasattr(self, "_materialise"):
+            self._materialise()                     # a lazily reduced model: from here on it is an ordinary one
         red = copy.deepcopy(self)
         red._per.remove(remove_k)
         red._dim_k = len(red._per)
@@ -789,3 +816,72 @@ class tb_model(object):
         if b == "orbital" and self._nspin == 2:
             out = out.reshape(out.shape[0], self._norb, 2)
         return hwfc[0], out
+
+
+class _ReducedMixin(object):
+    """``parent.reduce_dim(remove_k, value_k, lazy=True)``: a ``tb_model`` of one dimension less whose compiled plan
+    is derived from the parent's plan (``_plan.reduce_plan``); everything numerical (``solve_all``, ``wf_array``)
+    runs from that plan.  The Python-level description (``_hoppings``, ``_site_energies``) is built by the
+    reference algorithm (pythtb.py:1268-1310) on first access; a model that is edited afterwards behaves like any
+    other ``tb_model``."""
+    _hoppings = _LazyAttr("hoppings")
+    _site_energies = _LazyAttr("site_energies")
+    _site_energies_specified = _LazyAttr("site_energies_specified")
+    _hop_index = _LazyAttr("hop_index")
+
+    _classes = {}
+
+    @classmethod
+    def _make(cls, parent, remove_k, value_k):
+        base = type(parent)
+        if not issubclass(base, _ReducedMixin):            # keep the parent's class (and engine) underneath
+            if base not in _ReducedMixin._classes:
+                _ReducedMixin._classes[base] = type(base.__name__ + "_reduced", (_ReducedMixin, base), {})
+            base = _ReducedMixin._classes[base]
+        cls = base
+        if parent._dim_k == 0:
+            raise Exception("\n\nCan not reduce dimensionality even further!")
+        if list(parent._per).count(remove_k) != 1:
+            raise Exception("\n\nSpecified wrong dimension to reduce!")
+        from ._plan import reduce_plan
+        snap = parent._plan()
+        new = cls.__new__(cls)
+        for k, v in parent.__dict__.items():
+            if k in ("_hoppings", "_site_energies", "_site_energies_specified", "_hop_index", "_plan_cache") or k.startswith("_lazy_"):
+                continue
+            new.__dict__[k] = copy.copy(v) if isinstance(v, (list, np.ndarray)) else v
+        new._per = [p for p in parent._per if p != remove_k]
+        new._dim_k = len(new._per)
+        new._lazy = (parent, parent.__dict__.get("_version", 0), remove_k, float(value_k))
+        new._red_plan = reduce_plan(snap, list(parent._per).index(remove_k), float(value_k))
+        new._plan_cache = None
+        return new
+
+    def _materialise(self):
+        lazy = self.__dict__.get("_lazy")
+        if lazy is None:
+            return
+        parent, version, remove_k, value_k = lazy
+        if parent.__dict__.get("_version", 0) != version:
+            raise Exception("\n\nThe model this lazily reduced model was derived from has been modified since;"
+                            "\ncall reduce_dim again.")
+        self.__dict__["_lazy"] = None
+        eager = tb_model.reduce_dim(parent, remove_k, value_k)
+        for name in ("hoppings", "site_energies", "site_energies_specified", "hop_index"):
+            self.__dict__["_lazy_" + name] = getattr(eager, "_" + name)
+        self.__dict__["_red_plan"] = None
+
+    def _plan(self, convention=None):
+        red = self.__dict__.get("_red_plan")
+        if red is not None and self.__dict__.get("_lazy") is not None and convention in (None, red.convention):
+            return red
+        return tb_model._plan(self, convention)
+
+    def __deepcopy__(self, memo):
+        if self.__dict__.get("_lazy") is None:
+            return tb_model.__deepcopy__(self, memo)
+        new = self.__class__.__new__(self.__class__)          # the plan is immutable and the parent only a witness:
+        memo[id(self)] = new                                  # a copy (wf_array takes one) shares both
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = v if k in ("_lazy", "_red_plan") else copy.deepcopy(v, memo)
+        return new

@@ -311,8 +311,6 @@ class wf_array(object):
             raise Exception("\n\nsolve_on_slice: the model does not have the orbitals / states of this wf_array")
         if model._dim_k == 0:
             raise Exception("\n\nsolve_on_slice needs a periodic model (dim_k > 0)")
-        if self._shard is not None:
-            raise Exception("\n\nsolve_on_slice is not available on a sharded wf_array")
         fix = {}
         for d, i in dict(fixed).items():
             if not _is_int(d) or d < 0 or d >= self._dim_arr:
@@ -329,7 +327,25 @@ class wf_array(object):
             kpts = kpts.reshape(kpts.shape + (1,))
         if kpts.shape != want:
             raise Exception("\n\nk-vector of wrong shape!")
-        return self._model._engine().solve_slice(model, self._store, self._dim_arr, fix, free, kpts)
+        eng = self._model._engine()
+        sh = self._shard
+        if sh is None:
+            return eng.solve_slice(model, self._store, self._dim_arr, fix, free, kpts)
+        # ---- sharded array (mesh axis 0 sliced over the ranks; every slab carries its closing row)
+        if 0 in fix:
+            # a fixed GLOBAL row: stored by the rank(s) whose slab holds it (its owner, and the previous rank as
+            # its closing row); every rank returns the eigenvalues
+            g = fix[0]
+            if sh.row0 <= g <= sh.row0 + sh.nrows:
+                loc = dict(fix)
+                loc[0] = g - sh.row0
+                return eng.solve_slice(model, self._store, self._dim_arr, loc, free, kpts)
+            ev = model.solve_all(kpts.reshape(-1, model._dim_k))                 # eval[band, k]
+            return np.ascontiguousarray(ev.T).reshape(kpts.shape[:-1] + (model._nsta,))
+        # axis 0 is free: every rank fills its rows (closing row included) from its part of the k-list
+        ev_loc = eng.solve_slice(model, self._store, self._dim_arr, fix, free,
+                                 np.ascontiguousarray(kpts[sh.row0:sh.row0 + sh.nrows + 1]))
+        return self._gather_axis0(ev_loc, 0, with_closing_row=True)
 
     def choose_states(self, subset):
         """pythtb.py:2568-2607."""

@@ -70,6 +70,28 @@ def main():
         ws.impose_loop(0)
         want = full._wfs[0] if sh.is_last else full._wfs[sh.row0 + sh.nrows]
         assert np.max(np.abs(ws._wfs[-1] - want)) < 1e-14
+        # solve_on_slice on a sharded array (parametric axis along the sharded direction and across it)
+        lam = np.linspace(0.0, 1.0, 9)
+        kx = np.linspace(0.0, 1.0, 6)
+        full = api.wf_array(M.three_site(api, 0.0), [9, 6])
+        ws = api.wf_array(M.three_site(api, 0.0), [9, 6], shard=(rank, world))
+        for il, lm in enumerate(lam):                                   # axis 0 fixed: one global row per call
+            mdl = M.three_site(api, lm)
+            e_f = full.solve_on_slice({0: il}, kx.reshape(-1, 1), model=mdl)
+            e_s = ws.solve_on_slice({0: il}, kx.reshape(-1, 1), model=mdl)
+            assert np.max(np.abs(e_f - e_s)) < 1e-12
+        sh = ws._shard
+        assert np.max(np.abs(np.abs(ws._wfs) - np.abs(full._wfs[sh.row0:sh.row0 + sh.nrows + 1]))) < 1e-12
+        m2 = M.haldane(api, 0.2)
+        full2 = api.wf_array(m2, [7, 5])
+        ws2 = api.wf_array(m2, [7, 5], shard=(rank, world))
+        kk = np.stack(np.meshgrid(np.linspace(0, 1, 7), np.linspace(0, 1, 5), indexing="ij"), axis=-1)
+        for j in range(5):                                              # axis 0 free: every rank fills its rows
+            e_f = full2.solve_on_slice({1: j}, kk[:, j])
+            e_s = ws2.solve_on_slice({1: j}, kk[:, j])
+            assert e_s.shape == e_f.shape and np.max(np.abs(e_f - e_s)) < 1e-12
+        sh = ws2._shard
+        assert np.max(np.abs(np.abs(ws2._wfs) - np.abs(full2._wfs[sh.row0:sh.row0 + sh.nrows + 1]))) < 1e-12
         # streamed 1-D string (BASELINE config 4 in miniature): links dealt to the ranks, never materialised
         rib = M.bn_ribbon(api, 5)
         occ_r = list(range(rib._nsta // 2))

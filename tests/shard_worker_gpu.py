@@ -99,6 +99,37 @@ def main():
             eng.peer_flush()
             for g in gs:
                 assert np.array_equal(g.cpu().numpy(), gaps_ref)
+        # solve_on_slice on a sharded array: a fixed global row per call / every rank fills its rows
+        lam = np.linspace(0.0, 1.0, 9)
+        kx = np.linspace(0.0, 1.0, 6).reshape(-1, 1)
+        full = tb.wf_array(M.three_site(tb, 0.0), [9, 6])
+        ws = tb.wf_array(M.three_site(tb, 0.0), [9, 6], shard=(rank, world))
+        for il, lm in enumerate(lam):
+            mdl = M.three_site(tb, lm)
+            assert np.max(np.abs(full.solve_on_slice({0: il}, kx, model=mdl) - ws.solve_on_slice({0: il}, kx, model=mdl))) < 1e-12
+        sh = ws._shard
+        assert np.array_equal(np.array(ws._wfs), np.array(full._wfs)[sh.row0:sh.row0 + sh.nrows + 1])
+        for arr in (full, ws):
+            arr.impose_loop(0)
+        assert abs(compare.circ_diff(ws.berry_flux([0]), full.berry_flux([0]), 2 * np.pi)) < 1e-9
+        m2 = M.haldane(tb, 0.2)
+        full2, ws2 = tb.wf_array(m2, [7, 5]), tb.wf_array(m2, [7, 5], shard=(rank, world))
+        kk = np.stack(np.meshgrid(np.linspace(0, 1, 7), np.linspace(0, 1, 5), indexing="ij"), axis=-1)
+        for j in range(5):
+            assert np.max(np.abs(full2.solve_on_slice({1: j}, kk[:, j]) - ws2.solve_on_slice({1: j}, kk[:, j]))) < 1e-12
+        sh = ws2._shard
+        assert np.array_equal(np.array(ws2._wfs), np.array(full2._wfs)[sh.row0:sh.row0 + sh.nrows + 1])
+        # streamed 1-D string dealt to the ranks (BASELINE config 4 in miniature), both branches
+        rib = M.bn_ribbon(tb, 20)
+        occ_r = list(range(rib._nsta // 2))
+        fullr = tb.wf_array(rib, [101])
+        gaps_ref = fullr.solve_on_grid([0.05])
+        wsr = tb.wf_array(rib, [101], shard=(rank, world), stream=True)
+        assert np.max(np.abs(wsr.solve_on_grid([0.05]) - gaps_ref)) < 1e-12
+        assert abs(compare.circ_diff(wsr.berry_phase(occ_r), fullr.berry_phase(occ_r), 2 * np.pi)) < 1e-9
+        ok, dev = compare.sets_close(wsr.berry_phase_stream([0.05], occ_r, berry_evals=True, chunk=17),
+                                     fullr.berry_phase(occ_r, berry_evals=True), 2 * np.pi, 1e-8)
+        assert ok, dev
         # a wider occupied set: the CTA-wide Wilson-loop kernels (nocc >= 8) across ranks
         rib = M.random_model(tb, norb=20, dim=2, nhop=40, nspin=1, seed=11)
         full = tb.wf_array(rib, [17, 9])

@@ -101,3 +101,62 @@ def test_solve_on_slice_argument_checks(get):
         w.solve_on_slice({0: 1, 1: 1}, np.zeros((2,)))         # nothing left free
     with pytest.raises(Exception):
         w.solve_on_slice({0: 1}, np.zeros((5, 2)), model=M.kane_mele(mod))   # other state count
+
+
+@pytest.mark.parametrize("get", MODS)
+def test_lazy_reduce_dim_matches_the_reference_algorithm(get):
+    """``reduce_dim(remove_k, value, lazy=True)`` (the reduced model's plan derived from the parent's plan,
+    pythtb_b200/_plan.py::reduce_plan) against the eager reference algorithm (pythtb.py:1233-1311) and the oracle:
+    eigenvalues, gauge-invariant projectors, a Berry phase along the remaining direction — for scalar, spinor and
+    3-D models, both phase conventions, nested reductions, and the materialised Python description."""
+    from oracle import pythtb_oracle as orc
+    mod = get()
+    k1 = np.linspace(-0.5, 0.5, 13)[:, None]
+    specs = [(M.haldane(mod, 0.2), 1, 0.37), (M.haldane(mod, 0.2), 0, -0.12), (M.kane_mele(mod, "odd"), 0, 0.21),
+             (M.random_model(mod, norb=3, dim=2, nhop=8, nspin=1, seed=31), 1, 0.4),
+             (M.random_model(mod, norb=7, dim=2, nhop=20, nspin=1, seed=25), 0, 0.77)]
+    for model, rk, val in specs:
+        for conv in (1, 2):
+            model.set_convention(conv)
+            lazy = model.reduce_dim(rk, val, lazy=True)
+            eager = model.reduce_dim(rk, val)
+            assert lazy._dim_k == eager._dim_k == 1 and list(lazy._per) == list(eager._per)
+            on_gpu = mod.__name__ == "pythtb_b200"                 # (the oracle engine reads _hoppings: it materialises)
+            assert lazy.__dict__.get("_lazy") is not None          # nothing has been materialised so far
+            ev_l, vec_l = lazy.solve_all(k1, eig_vectors=True)
+            ev_ref = orc.solve_all(eager, k1)
+            vec_ref = eager.solve_all(k1, eig_vectors=True)[1]     # same engine, eagerly reduced model (either convention)
+            scale = max(1.0, np.max(np.abs(ev_ref)))
+            assert np.max(np.abs(ev_l - ev_ref)) <= compare.TOL_EVAL * scale
+            n = model._nsta
+            gaps = np.min(np.diff(ev_ref, axis=0))
+            if gaps > 1e-3:
+                a = vec_l.reshape(n, len(k1), n)
+                b = np.asarray(vec_ref).reshape(n, len(k1), n)
+                pa = np.einsum("bki,bkj->bkij", a, a.conj())
+                pb = np.einsum("bki,bkj->bkij", b, b.conj())
+                assert np.max(np.abs(pa - pb)) < compare.TOL_PROJ
+            # a Berry phase of the reduced model (examples/haldane_hwf-style sweeps)
+            wl = mod.wf_array(lazy, [21])
+            we = mod.wf_array(eager, [21])
+            wl.solve_on_grid([0.0])
+            we.solve_on_grid([0.0])
+            assert abs(compare.circ_diff(wl.berry_phase([0]), we.berry_phase([0]), 2 * np.pi)) < compare.TOL_PHASE
+            assert lazy.__dict__.get("_lazy") is not None or not on_gpu
+            # the Python description, on demand, is the reference algorithm's
+            assert len(lazy._hoppings) == len(eager._hoppings) and lazy.__dict__.get("_lazy") is None
+            assert np.allclose(np.asarray(lazy._site_energies), np.asarray(eager._site_energies))
+        model.set_convention(1)
+    # nested: 3-D -> 1-D, and down to 0-D
+    m3 = M.random_model(mod, norb=3, dim=3, nhop=9, nspin=1, seed=2)
+    lz = m3.reduce_dim(2, 0.3, lazy=True).reduce_dim(0, -0.2, lazy=True)
+    eg = m3.reduce_dim(2, 0.3).reduce_dim(0, -0.2)
+    assert np.max(np.abs(lz.solve_all(k1) - orc.solve_all(eg, k1))) < 1e-10
+    lz0 = lz.reduce_dim(1, 0.45, lazy=True)
+    assert lz0._dim_k == 0 and np.max(np.abs(lz0.solve_all() - orc.solve_all(eg.reduce_dim(1, 0.45)))) < 1e-10
+    # a parent edited after the reduction is detected when the Python description is asked for
+    h = M.haldane(mod, 0.2)
+    lz = h.reduce_dim(0, 0.2, lazy=True)
+    h.set_onsite([0.1, -0.1], mode="reset")
+    with pytest.raises(Exception, match="modified since"):
+        lz._hoppings
