@@ -65,12 +65,21 @@ def _max_over_ranks(torch, world, vals):
     return [float(x) for x in t.cpu()]
 
 
+def _single_thread_blas():
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+
+
 def _pool_rate(fn, args_list, procs, min_seconds=4.0):
-    """units/s of `fn` over a process pool: passes repeated for >= min_seconds, best pass reported."""
+    """units/s of `fn` over a process pool (one single-threaded BLAS process per core): passes repeated for
+    >= min_seconds, best pass reported."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
     times = []
-    with ctx.Pool(procs) as pool:
+    with ctx.Pool(procs, initializer=_single_thread_blas) as pool:
         pool.map(fn, args_list[:procs])
         t_all = time.perf_counter()
         while (time.perf_counter() - t_all) < min_seconds and len(times) < 50:
@@ -283,7 +292,7 @@ def config5(tb, eng, world, rank, peaks, with_cpu, nl=250, mesh=129, budget_s=1e
     nlinks_tot = nstr_tot * (mesh - 1)
     wil = None
     left = budget_s - (time.perf_counter() - t_start)
-    est = nlinks_tot / world / 380.0 + 5.0
+    est = nlinks_tot / world / 4000.0 + 5.0
     if left > est:
         with Timer(torch) as t:
             wil = w.berry_phase(occ, 0, contin=False, berry_evals=True)

@@ -134,6 +134,7 @@ constexpr int kFluxCols = kFluxWarpCols * (kFluxThreads / 32);
 constexpr int kFluxMaxRows = 24;
 
 constexpr int kFluxWarps = kFluxThreads / 32;
+constexpr int kFluxDefaultSlots12 = 4;   // default prefetch rotation of flux_rows_kernel<1, 2> (measured, profiles/README.md)
 
 struct FluxTiling {
   long long nstrip;       // column strips per slice: widths wc or wc + 1 (<= 31), the first cx strips the wider ones
@@ -217,8 +218,11 @@ __device__ __forceinline__ OccState<NOCC, N> shfl_down_state(const OccState<NOCC
   return r;
 }
 
-template <int NOCC, int N, bool WANT_PLAQ>
-__global__ void __launch_bounds__(kFluxThreads, (NOCC == 1 && N == 2) ? 5 : (NOCC * N >= 6 ? 3 : 1))   // 5 CTAs / SM for the Haldane case (<= 102 registers), 3 for the 6- and 8-component states (<= 168)
+// SLOTS: register slots of the row rotation (rows i, i+1 and SLOTS - 2 rows of loads in flight); 0 = the default
+// (4 for states of <= 4 components, 3 above).  With a state-major array a row of the one-band, two-orbital case is
+// 32 useful bytes per lane, and deeper rotations (6, 8 slots: 4 / 6 rows in flight) trade occupancy for bytes in flight.
+template <int NOCC, int N, bool WANT_PLAQ, int SLOTS = 0>
+__global__ void __launch_bounds__(kFluxThreads, (NOCC == 1 && N == 2) ? (SLOTS > 4 ? 4 : 5) : (NOCC * N >= 6 ? 3 : 1))   // 5 CTAs / SM for the Haldane case (<= 102 registers), 3 for the 6- and 8-component states (<= 168)
 flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0, long long stride0, long long n1,
                  long long stride1, FluxTiling tl, long long nslice, double* __restrict__ plaq,
                  double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ total,
@@ -260,14 +264,16 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
       // timeline + Little's law: one row ahead = 2 KB per warp = ~40 KB per SM gave ~3.9 TB/s for the
       // 2-component state); dropping the neighbour-column registers pays for the deeper prefetch.
       // Small states (nocc x n <= 4): two rows ahead; larger ones: one row ahead, the registers go to occupancy.
-      constexpr int kSlots = (NOCC * N <= 4) ? 4 : 3;
+      constexpr int kSlots = SLOTS > 0 ? SLOTS : ((NOCC * N <= 4) ? 4 : 3);
       OccState<NOCC, N> X[kSlots];
 #pragma unroll
       for (int q = 0; q < kSlots; ++q) X[q].zero();        // lanes past the strip carry zeros, never garbage
       if (has_col) {
         X[0].load(pa, occ);
         X[1].load(pa + stride0, occ);
-        if (kSlots == 4 && nrow >= 2) X[2].load(pa + 2 * stride0, occ);
+#pragma unroll
+        for (int q = 2; q <= kSlots - 2; ++q)              // rows 0 .. kSlots - 2 are in flight before the first step
+          if (nrow >= q) X[q].load(pa + q * stride0, occ);
       }
       cplx hda;                                            // L(d,a) = conj(H(i,col))
       {
@@ -366,15 +372,15 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
   cta_trace_end(trace, t_begin);
 }
 
-template <int NOCC, int N>
+template <int NOCC, int N, int SLOTS = 0>
 static int launch_flux_rows(const WfView& v, const long long* off, long long nslice, long long n0, long long stride0,
                             long long n1, long long stride1, double* plaq, double* total, double* partial, tbk_peer* peer,
                             cudaStream_t st) {
   static int occ_plaq = 0, occ_sum = 0;                   // resident CTAs per SM of the two variants
   if (occ_plaq == 0) {
     int a = 0, b = 0;
-    TBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, flux_rows_kernel<NOCC, N, true>, kFluxThreads, 0));
-    TBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, flux_rows_kernel<NOCC, N, false>, kFluxThreads, 0));
+    TBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, flux_rows_kernel<NOCC, N, true, SLOTS>, kFluxThreads, 0));
+    TBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, flux_rows_kernel<NOCC, N, false, SLOTS>, kFluxThreads, 0));
     occ_sum = b > 0 ? (b > 16 ? 16 : b) : 1;
     occ_plaq = a > 0 ? (a > 16 ? 16 : a) : 1;
   }
@@ -406,10 +412,10 @@ static int launch_flux_rows(const WfView& v, const long long* off, long long nsl
   // a synchronous prepared call waits on a pinned word the last CTA writes after the totals
   const DoneSignal done = (total && (pview.nranks <= 1 || pview.complete_self)) ? take_done_request() : DoneSignal{nullptr, 0};
   if (plaq)
-    TBK_CUDA(cudaLaunchKernelEx(&cfg, flux_rows_kernel<NOCC, N, true>, v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
+    TBK_CUDA(cudaLaunchKernelEx(&cfg, flux_rows_kernel<NOCC, N, true, SLOTS>, v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
                                 part_arg, ticket, total, pview, trace, done));
   else
-    TBK_CUDA(cudaLaunchKernelEx(&cfg, flux_rows_kernel<NOCC, N, false>, v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
+    TBK_CUDA(cudaLaunchKernelEx(&cfg, flux_rows_kernel<NOCC, N, false, SLOTS>, v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
                                 part_arg, ticket, total, pview, trace, done));
   TBK_LAUNCH_CHECK("flux_rows_kernel");
   return TBK_OK;
@@ -1549,7 +1555,16 @@ int tbk_flux_plane_x(const tbk_wf_view* view, const int64_t* slice_off_dev, int6
     int rc = TBK_OK;
     const int key = view->nocc * 10 + view->n;
     switch (key) {
-      case 12: rc = launch_flux_rows<1, 2>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, peer, st); break;
+      case 12: {
+        // prefetch depth of the one-band / two-orbital case (TBK_FLUX_SLOTS = 4 | 6 | 8; A/B knob, see profiles/README.md)
+        static int slots = -1;
+        if (slots < 0) { const char* e = getenv("TBK_FLUX_SLOTS"); slots = e ? atoi(e) : kFluxDefaultSlots12; }
+        const bool deep_ok = v.ss != view->n;              // deeper rotations pay only when a row is one band (state-major)
+        if (slots == 8 && deep_ok) rc = launch_flux_rows<1, 2, 8>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, peer, st);
+        else if (slots == 6 && deep_ok) rc = launch_flux_rows<1, 2, 6>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, peer, st);
+        else rc = launch_flux_rows<1, 2>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, peer, st);
+        break;
+      }
       case 22: rc = launch_flux_rows<2, 2>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, peer, st); break;
       case 13: rc = launch_flux_rows<1, 3>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, peer, st); break;
       case 23: rc = launch_flux_rows<2, 3>(v, off, nslice, n0, stride0, n1, stride1, plaq_dev, total_dev, part2, peer, st); break;

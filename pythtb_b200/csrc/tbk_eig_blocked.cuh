@@ -45,7 +45,9 @@ struct BlkWork {
   cplx* A;         // [n x lda] column-major, lower triangle valid on entry (global)
   cplx* V;         // [nb][n] reflector panel            (shared memory on the device)
   cplx* W;         // [nb][n] zlatrd's W panel           (shared)
-  cplx* part;      // [group size] partial sums of the split matrix-vector product (shared)
+  cplx* wcol;      // [n] column part of the symmetric matrix-vector product          (shared)
+  cplx* racc;      // [nred][n] row partials of the sub-teams, nred sub-teams per round (shared)
+  int nred;
   cplx* dots;      // [2 nb] panel dot products           (shared)
   cplx* tau;       // [n]                                 (shared)
   double* d;       // [n] diagonal of T                   (shared)
@@ -60,18 +62,19 @@ struct BlkWork {
   int nt;
 };
 
-TBK_HD size_t blk_shared_bytes(int n, int nb, int nthreads) {
-  return (size_t)2 * nb * n * 16 + (size_t)nthreads * 16 + (size_t)2 * nb * 16 + (size_t)n * 16 + (size_t)5 * n * 8 +
+TBK_HD size_t blk_shared_bytes(int n, int nb, int nred) {
+  return (size_t)2 * nb * n * 16 + (size_t)(1 + nred) * n * 16 + (size_t)2 * nb * 16 + (size_t)n * 16 + (size_t)5 * n * 8 +
          (size_t)n * 4 + 64;
 }
 
-// carve the shared part of a BlkWork out of one 16-byte aligned buffer
-TBK_HD void blk_carve_shared(BlkWork& w, void* base, int nthreads) {
+// carve the shared part of a BlkWork (n, nb, nred set) out of one 16-byte aligned buffer
+TBK_HD void blk_carve_shared(BlkWork& w, void* base) {
   char* p = (char*)base;
   const int n = w.n, nb = w.nb;
   w.V = (cplx*)p;    p += (size_t)nb * n * 16;
   w.W = (cplx*)p;    p += (size_t)nb * n * 16;
-  w.part = (cplx*)p; p += (size_t)nthreads * 16;
+  w.wcol = (cplx*)p; p += (size_t)n * 16;
+  w.racc = (cplx*)p; p += (size_t)w.nred * n * 16;
   w.dots = (cplx*)p; p += (size_t)2 * nb * 16;
   w.tau = (cplx*)p;  p += (size_t)n * 16;
   w.d = (double*)p;  p += (size_t)n * 8;
@@ -86,19 +89,18 @@ TBK_HD void blk_carve_shared(BlkWork& w, void* base, int nthreads) {
 // ---------------------------------------------------------------------------------------------
 // 1. blocked tridiagonalisation.  On exit d, e hold T, the Householder vectors are stored below the
 // first sub-diagonal of A (zhetd2 'L' layout, implicit unit at row j+1) with their scalars in tau.
-// The strict upper triangle is overwritten (it is filled from the lower one first).
+// Only the lower triangle of A is ever read or written: the trailing matrix is streamed from L2 / HBM once per
+// column, and the Hermitian product w = A22 v takes both contributions of an element a_rc (to w_r and,
+// conjugated, to w_c) from ONE load — half the bytes of a product with the full matrix.  MAXM >= ceil(n / subsize).
 // ---------------------------------------------------------------------------------------------
-template <class G>
+template <int MAXM, class G>
 TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
   const int n = w.n, lda = w.lda, nb = w.nb;
   const int T = g.size(), tid = g.tid();
   cplx* A = w.A;
   cplx* V = w.V;
   cplx* W = w.W;
-  // full Hermitian storage: upper from lower, real diagonal
-  for (int c = tid; c < n; c += T) A[c + (size_t)c * lda].im = 0.0;
-  for (int r = tid; r < n; r += T)
-    for (int c = r + 1; c < n; ++c) A[r + (size_t)c * lda] = conj(A[c + (size_t)r * lda]);
+  for (int c = tid; c < n; c += T) A[c + (size_t)c * lda].im = 0.0;       // real diagonal
   g.sync();
   for (int j0 = 0; j0 < n - 1; j0 += nb) {
     const int nbp = n - 1 - j0 < nb ? n - 1 - j0 : nb;
@@ -148,65 +150,65 @@ TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
         w.d[j] = col[j].re;
       }
       g.sync();
-      // ---- (3) w = A22 v with the stored (panel-start) trailing matrix, rows/cols j+1 .. n-1
-      const int m = n - j - 1;
+      // ---- (3) w = A22 v with the stored (panel-start) trailing matrix, rows/cols j+1 .. n-1, LOWER TRIANGLE ONLY.
+      // A sub-team (warp) owns the columns c = j+1+sub, j+1+sub+nsub, ...; it streams column c from the diagonal
+      // down (contiguous: 512-byte warp loads), lane L holding the rows r = L + S t.  An element a_rc gives
+      //   w_r += a_rc v_c            (row part, accumulated in the lane's registers over all its columns) and
+      //   w_c += conj(a_rc) v_r      (column part, one reduction over the sub-team per column).
+      // The sub-teams' row partials are then summed through shared memory, nred sub-teams per round.
       {
-        int rw = ((m + 31) / 32) * 32;
-        if (rw > T) rw = T;
-        const int parts = T / rw > 0 ? T / rw : 1;
-        const int pr = tid % rw, pp = tid / rw;
-        if (pp < parts) {
-          for (int rb = 0; rb < m; rb += rw) {    // rb > 0 only when m > T
-            const int r = j + 1 + rb + pr;
-            cplx acc = mk(0.0, 0.0);
-            if (r < n) {
-              // eight independent accumulators: eight 16-byte loads in flight per thread, no serial FMA chain
-              // (the product is latency-bound: one 512-thread CTA per SM has only its own loads to hide them)
-              const cplx* arow = A + r;
-              cplx a0 = mk(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0, a7 = a0;
-              int c = j + 1 + pp;
-              for (; c + 7 * parts < n; c += 8 * parts) {
-                const cplx m0 = arow[(size_t)c * lda], m1 = arow[(size_t)(c + parts) * lda];
-                const cplx m2 = arow[(size_t)(c + 2 * parts) * lda], m3 = arow[(size_t)(c + 3 * parts) * lda];
-                const cplx m4 = arow[(size_t)(c + 4 * parts) * lda], m5 = arow[(size_t)(c + 5 * parts) * lda];
-                const cplx m6 = arow[(size_t)(c + 6 * parts) * lda], m7 = arow[(size_t)(c + 7 * parts) * lda];
-                fma_acc(a0, m0, v[c]);
-                fma_acc(a1, m1, v[c + parts]);
-                fma_acc(a2, m2, v[c + 2 * parts]);
-                fma_acc(a3, m3, v[c + 3 * parts]);
-                fma_acc(a4, m4, v[c + 4 * parts]);
-                fma_acc(a5, m5, v[c + 5 * parts]);
-                fma_acc(a6, m6, v[c + 6 * parts]);
-                fma_acc(a7, m7, v[c + 7 * parts]);
+        const int S = g.subsize(), L = g.lane(), nsub = g.nsub(), sub = g.sub();
+        cplx acc[MAXM];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int t = 0; t < MAXM; ++t) acc[t] = mk(0.0, 0.0);
+        for (int c = j + 1 + sub; c < n; c += nsub) {
+          const cplx vc = v[c];
+          const cplx* acol = A + (size_t)c * lda;
+          double sre = 0.0, sim = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+          for (int t = 0; t < MAXM; ++t) {
+            if (S * t + S - 1 >= c) {                 // sub-team-uniform: this slot reaches the diagonal of column c
+              const int r = L + S * t;
+              if (r >= c && r < n) {
+                cplx a = acol[r];
+                if (r == c) a.im = 0.0;
+                fma_acc(acc[t], a, vc);
+                if (r > c) {
+                  const cplx tt = cmul(a, v[r]);      // conj(a_rc) v_r
+                  sre += tt.re; sim += tt.im;
+                }
               }
-              for (; c + 3 * parts < n; c += 4 * parts) {
-                const cplx m0 = arow[(size_t)c * lda], m1 = arow[(size_t)(c + parts) * lda];
-                const cplx m2 = arow[(size_t)(c + 2 * parts) * lda], m3 = arow[(size_t)(c + 3 * parts) * lda];
-                fma_acc(a0, m0, v[c]);
-                fma_acc(a1, m1, v[c + parts]);
-                fma_acc(a2, m2, v[c + 2 * parts]);
-                fma_acc(a3, m3, v[c + 3 * parts]);
-              }
-              for (; c < n; c += parts) fma_acc(a0, arow[(size_t)c * lda], v[c]);
-              acc = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-            }
-            if (parts == 1) {
-              if (r < n) W[i * n + r] = acc;
-            } else {                              // parts > 1 implies m <= rw: a single row block
-              w.part[pp * rw + pr] = acc;
             }
           }
+          sre = g.subsum(sre); sim = g.subsum(sim);
+          if (L == 0) w.wcol[c] = mk(sre, sim);
         }
-        if (parts > 1) {
-          g.sync();
-          for (int r = tid; r < m; r += T) {
-            cplx acc = w.part[r];
-            for (int q = 1; q < parts; ++q) acc = acc + w.part[q * rw + r];
-            W[i * n + j + 1 + r] = acc;
+        g.sync();                                     // wcol complete
+        for (int w0 = 0; w0 < nsub; w0 += w.nred) {
+          if (sub >= w0 && sub < w0 + w.nred) {
+            cplx* dst = w.racc + (size_t)(sub - w0) * n;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int t = 0; t < MAXM; ++t) {
+              const int r = L + S * t;
+              if (r > j && r < n) dst[r] = acc[t];
+            }
           }
+          g.sync();
+          const int cnt = nsub - w0 < w.nred ? nsub - w0 : w.nred;
+          for (int r = j + 1 + tid; r < n; r += T) {
+            cplx sacc = w0 == 0 ? w.wcol[r] : W[i * n + r];
+            for (int q = 0; q < cnt; ++q) sacc = sacc + w.racc[(size_t)q * n + r];
+            W[i * n + r] = sacc;
+          }
+          g.sync();
         }
       }
-      g.sync();
       // ---- panel corrections: dots[k] = W_k^H v, dots[nb+k] = V_k^H v, one sub-team per dot product
       if (i > 0) {
         for (int q = g.sub(); q < 2 * i; q += g.nsub()) {
@@ -243,41 +245,48 @@ TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
       for (int r = j + 1 + tid; r < n; r += T) W[i * n + r] = W[i * n + r] + a2 * v[r];
       g.sync();
     }
-    // ---- rank-2nb update of the trailing matrix: A22 -= V W^H + W V^H   (rows/cols >= j1)
+    // ---- rank-2nb update of the trailing matrix, lower triangle only: a_rc -= sum_k (V_kr conj(W_kc) + W_kr conj(V_kc)),
+    // c <= r.  A thread takes the row pair (j1 + q, n - 1 - q): together they always have m + 1 columns, so every
+    // thread of the group streams the same number of elements (rows alone would leave the last warp with twice the mean).
     const int j1 = j0 + nbp;
     const int m = n - j1;
     if (m > 0) {
-      int rw = ((m + 31) / 32) * 32;
+      const int half = (m + 1) / 2;
+      int rw = ((half + 31) / 32) * 32;
       if (rw > T) rw = T;
       const int parts = T / rw > 0 ? T / rw : 1;
       const int pr = tid % rw, pp = tid / rw;
       if (pp < parts) {
-        for (int r = j1 + pr; r < n; r += rw) {
-          for (int k0 = 0; k0 < nb; k0 += 8) {    // 8 panel columns at a time in registers
-            if (k0 >= nbp) break;
-            cplx vr[8], wr[8];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (int k = 0; k < 8; ++k) {
-              const bool in = k0 + k < nb;
-              vr[k] = in ? V[(k0 + k) * n + r] : mk(0.0, 0.0);
-              wr[k] = in ? W[(k0 + k) * n + r] : mk(0.0, 0.0);
-            }
-            for (int c = j1 + pp; c < n; c += parts) {
-              cplx a = A[r + (size_t)c * lda];
+        for (int q = pr; q < half; q += rw) {
+          for (int side = 0; side < 2; ++side) {
+            const int r = side == 0 ? j1 + q : n - 1 - q;
+            if (side == 1 && r <= j1 + q) break;  // the middle row of an odd m is its own partner
+            for (int k0 = 0; k0 < nb; k0 += 8) {  // 8 panel columns at a time in registers
+              if (k0 >= nbp) break;
+              cplx vr[8], wr[8];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
               for (int k = 0; k < 8; ++k) {
-                if (k0 + k < nb) {
-                  const cplx wc = W[(k0 + k) * n + c], vc = V[(k0 + k) * n + c];
-                  // a -= vr * conj(wc) + wr * conj(vc)
-                  a.re -= vr[k].re * wc.re + vr[k].im * wc.im + wr[k].re * vc.re + wr[k].im * vc.im;
-                  a.im -= vr[k].im * wc.re - vr[k].re * wc.im + wr[k].im * vc.re - wr[k].re * vc.im;
-                }
+                const bool in = k0 + k < nb;
+                vr[k] = in ? V[(k0 + k) * n + r] : mk(0.0, 0.0);
+                wr[k] = in ? W[(k0 + k) * n + r] : mk(0.0, 0.0);
               }
-              A[r + (size_t)c * lda] = a;
+              for (int c = j1 + pp; c <= r; c += parts) {
+                cplx a = A[r + (size_t)c * lda];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int k = 0; k < 8; ++k) {
+                  if (k0 + k < nb) {
+                    const cplx wc = W[(k0 + k) * n + c], vc = V[(k0 + k) * n + c];
+                    // a -= vr * conj(wc) + wr * conj(vc)
+                    a.re -= vr[k].re * wc.re + vr[k].im * wc.im + wr[k].re * vc.re + wr[k].im * vc.im;
+                    a.im -= vr[k].im * wc.re - vr[k].re * wc.im + wr[k].im * vc.re - wr[k].re * vc.im;
+                  }
+                }
+                A[r + (size_t)c * lda] = a;
+              }
             }
           }
         }

@@ -447,7 +447,7 @@ solve_block_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long lon
 // tridiagonal eigenvectors in an L2/HBM workspace, panels and all O(n) data in shared memory
 // ===========================================================================
 struct BlkShape {
-  int n, lda, nb, nt, threads, nph;
+  int n, lda, nb, nt, threads, nph, nred;
   size_t off_ph, off_gf, off_misc, smem;             // shared-memory layout after the BlkWork part
   size_t ws_A, ws_Z, ws_lu, ws_block;                // per-CTA global workspace, bytes
   GroupShape fallback;                               // unblocked solver's layout inside the same shared buffer
@@ -457,15 +457,22 @@ static BlkShape blk_shape(int n, int nph) {
   BlkShape s;
   s.n = n; s.lda = n | 1; s.nph = nph;
   s.threads = n <= 256 ? 256 : 512;
-  auto total = [&](int nb) {
-    size_t off = (blk_shared_bytes(n, nb, s.threads) + 15) & ~(size_t)15;
+  const int nwarps = s.threads / 32;
+  auto total = [&](int nb, int nred) {
+    size_t off = (blk_shared_bytes(n, nb, nred) + 15) & ~(size_t)15;
     off += (size_t)(nph > 0 ? nph : 1) * 16 + (size_t)n * 16 + 128;
     return off;
   };
   // panel width: 16 if two CTAs still fit an SM, else 8.  (Measured at n = 400: nb = 4 with two resident
   // CTAs is 15 % slower than nb = 8 with one — the stage is bandwidth-, not latency-bound.)
-  s.nb = total(16) * 2 + 2048 <= (size_t)kMaxSmem ? 16 : 8;
-  size_t off = (blk_shared_bytes(n, s.nb, s.threads) + 15) & ~(size_t)15;
+  // nred: how many warps' row partials of the symmetric matrix-vector product are summed per round through shared
+  // memory — all of them when they fit, fewer (more rounds) for the largest matrices.
+  if (total(16, nwarps) * 2 + 2048 <= (size_t)kMaxSmem) { s.nb = 16; s.nred = nwarps; }
+  else {
+    s.nb = 8; s.nred = nwarps;
+    while (s.nred > 1 && total(8, s.nred) + 1024 > (size_t)kMaxSmem) --s.nred;
+  }
+  size_t off = (blk_shared_bytes(n, s.nb, s.nred) + 15) & ~(size_t)15;
   s.off_ph = off;   off += (size_t)(nph > 0 ? nph : 1) * 16;
   s.off_gf = off;   off += (size_t)n * 16;
   s.off_misc = off; off += 128;
@@ -514,8 +521,8 @@ solve_blocked_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long l
   BlockGroup g(red);
   const int n = shp.n, lda = shp.lda, tid = threadIdx.x, T = blockDim.x;
   BlkWork w;
-  w.n = n; w.lda = lda; w.nb = shp.nb; w.nt = shp.nt;
-  blk_carve_shared(w, smem, shp.threads);
+  w.n = n; w.lda = lda; w.nb = shp.nb; w.nt = shp.nt; w.nred = shp.nred;
+  blk_carve_shared(w, smem);
   cplx* ph = (cplx*)(smem + shp.off_ph);
   cplx* gf = (cplx*)(smem + shp.off_gf);
   double* kbuf = (double*)(smem + shp.off_misc);
@@ -554,7 +561,7 @@ solve_blocked_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long l
     long long t0 = prof ? clock64() : 0;
     const long long tstart = t0;
 #define TBK_PROF_MARK(slot) if (prof && tid == 0) { const long long t1 = clock64(); atomicAdd(prof + slot, (unsigned long long)(t1 - t0)); t0 = t1; }
-    hetrd_blocked(g, w);
+    hetrd_blocked<MAXM>(g, w);
     TBK_PROF_MARK(0)
     const double tnorm = tridiag_bisect(g, w);
     TBK_PROF_MARK(1)

@@ -85,8 +85,9 @@ int emu_heev_blocked_team(int n, double* A, int lda, int nb, int want_vec, doubl
   TeamShared shd(T, S);
   BlkWork w;
   w.n = n; w.lda = lda; w.nb = nb; w.A = (cplx*)A;
-  std::vector<char> sh(blk_shared_bytes(n, nb, T) + 64);
-  blk_carve_shared(w, sh.data(), T);
+  w.nred = T / S > 3 ? 3 : T / S;                // fewer slots than sub-teams: several reduction rounds
+  std::vector<char> sh(blk_shared_bytes(n, nb, w.nred) + 64);
+  blk_carve_shared(w, sh.data());
   int nt = ((n + S - 1) / S) * S;
   if (nt > T) nt = T;
   std::vector<double> Z((size_t)n * n), lu((size_t)4 * n * nt);
@@ -95,7 +96,7 @@ int emu_heev_blocked_team(int n, double* A, int lda, int nb, int want_vec, doubl
   std::vector<int> fail(T, 0);
   auto body = [&](int t) {
     TeamGroup g{&shd, t};
-    hetrd_blocked(g, w);
+    hetrd_blocked<kBlkMaxN>(g, w);
     const double tnorm = tridiag_bisect(g, w);
     if (t == 0) std::memcpy(ev, w.lam, n * 8);
     if (!want_vec) return;
@@ -219,11 +220,12 @@ int emu_heev_blocked(int n, double* A, int lda, int nb, int want_vec, double* ev
   HostGroup g;
   BlkWork w;
   w.n = n; w.lda = lda; w.nb = nb; w.A = (cplx*)A;
+  w.nred = 1;
   std::vector<char> sh(blk_shared_bytes(n, nb, 1) + 64);
-  blk_carve_shared(w, sh.data(), 1);
+  blk_carve_shared(w, sh.data());
   std::vector<double> Z((size_t)n * n), lu((size_t)4 * n);
   w.Z = Z.data(); w.lu = lu.data(); w.nt = 1;
-  hetrd_blocked(g, w);
+  hetrd_blocked<kBlkMaxN>(g, w);
   if (tri) { std::memcpy(tri, w.d, n * 8); std::memcpy(tri + n, w.e, n * 8); }
   const double tnorm = tridiag_bisect(g, w);
   std::memcpy(ev, w.lam, n * 8);

@@ -321,6 +321,9 @@ def test_flux_ring_kernel_matches_register_kernel(which, mesh):
     mod = _mod()
     m, occ = (M.haldane(mod, 0.0), [0]) if which == "haldane" else (M.kane_mele(mod, "odd"), [0, 1])
     w = mod.wf_array(m, mesh)
+    # the ring kernel streams whole rows of k-points ([k..., state, orb] storage): give this array the reference
+    # layout on the device instead of the state-major default of 2..4-band arrays
+    w._store = w._model._engine().new_store(w._store.shape)
     w.solve_on_grid([-0.5, -0.5])
     base_plaq = w.berry_flux(occ, individual_phases=True)
     base_tot = w.berry_flux(occ)
