@@ -218,9 +218,9 @@ def reduce_plan(p, axis, value):
 
     The factor exp(+-2 pi i value R_axis) of every term moves from the phase into its amplitude, the phase table
     loses a column (vectors that coincide afterwards are merged, vectors that vanish turn their terms into
-    constants), and for Convention I the constant diagonal gauge Phi = diag(exp(2 pi i value tau_o[axis])) is
-    folded in as Phi^H H Phi, so that the kernels' eigenvectors carry exactly the phases of the reduced reference
-    model (whose hopping amplitudes contain exp(2 pi i value (tau_j - tau_i + R)[axis]))."""
+    constants), and the constant diagonal gauge Phi = diag(exp(2 pi i value tau_o[axis])) is folded in as
+    Phi^H H Phi, so that the kernels' eigenvectors carry exactly the phases of the reduced reference model
+    (whose hopping amplitudes contain exp(2 pi i value (tau_j - tau_i + R)[axis]))."""
     if p.dim_k < 1 or not (0 <= axis < p.dim_k):
         raise Exception("\n\nSpecified wrong dimension to reduce!")
     nterm, nel, nph, dk = p.nterm, p.nel, p.nph, p.dim_k
@@ -236,9 +236,10 @@ def reduce_plan(p, axis, value):
     r_axis = np.where(has, R[idx, axis] if nph else 0.0, 0.0)
     r_axis = np.where(cj, -r_axis, r_axis)
     fac = np.exp(2.0j * np.pi * value * r_axis)
-    if p.convention == 1:
-        phi = np.exp(2.0j * np.pi * value * p.tau[:p.nsta, axis])
-        fac = fac * np.conj(phi[rows]) * phi[cols]
+    # (either convention: the reference algorithm puts the orbital positions along the removed direction into the
+    #  amplitudes, so the reduced model's Convention-II matrix is Phi^H H_II(k', value) Phi as well)
+    phi = np.exp(2.0j * np.pi * value * p.tau[:p.nsta, axis])
+    fac = fac * np.conj(phi[rows]) * phi[cols]
     amps = amps * fac
     # ---- the phase table without the fixed component: canonical sign, merged duplicates, first-seen order
     Rn = np.rint(np.delete(R, axis, axis=1)).astype(np.int64)              # [nph, dk-1]

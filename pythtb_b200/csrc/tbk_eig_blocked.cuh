@@ -303,6 +303,219 @@ TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// 1'. blocked tridiagonalisation, FULL-MATRIX variant (the round-1 kernel, kept selectable: TBK_HETRD=full).  On exit d, e hold T, the Householder vectors are stored below the
+// first sub-diagonal of A (zhetd2 'L' layout, implicit unit at row j+1) with their scalars in tau.
+// The strict upper triangle is overwritten (it is filled from the lower one first).
+// ---------------------------------------------------------------------------------------------
+template <class G>
+TBK_HD void hetrd_blocked_full(G& g, const BlkWork& w) {
+  const int n = w.n, lda = w.lda, nb = w.nb;
+  const int T = g.size(), tid = g.tid();
+  cplx* A = w.A;
+  cplx* V = w.V;
+  cplx* W = w.W;
+  // full Hermitian storage: upper from lower, real diagonal
+  for (int c = tid; c < n; c += T) A[c + (size_t)c * lda].im = 0.0;
+  for (int r = tid; r < n; r += T)
+    for (int c = r + 1; c < n; ++c) A[r + (size_t)c * lda] = conj(A[c + (size_t)r * lda]);
+  g.sync();
+  for (int j0 = 0; j0 < n - 1; j0 += nb) {
+    const int nbp = n - 1 - j0 < nb ? n - 1 - j0 : nb;
+    // zero the panels (unused panel columns must be exactly zero for the rank-2nb update)
+    for (int q = tid; q < nb * n; q += T) { V[q] = mk(0.0, 0.0); W[q] = mk(0.0, 0.0); }
+    g.sync();
+    for (int i = 0; i < nbp; ++i) {
+      const int j = j0 + i;
+      cplx* col = A + (size_t)j * lda;
+      // ---- (1) bring column j up to date with the reflectors of this panel
+      if (i > 0) {
+        for (int r = j + tid; r < n; r += T) {
+          cplx a = col[r];
+          for (int k = 0; k < i; ++k) {
+            a = a - mulc(V[k * n + r], W[k * n + j]);
+            a = a - mulc(W[k * n + r], V[k * n + j]);
+          }
+          if (r == j) a.im = 0.0;
+          col[r] = a;
+        }
+        g.sync();
+      }
+      // ---- (2) reflector for x = A(j+1:n, j)   (zlarfg)
+      double part = 0.0;
+      for (int r = j + 2 + tid; r < n; r += T) part += norm2(col[r]);
+      const double xnorm2 = g.sum(part);
+      const cplx alpha = col[j + 1];
+      cplx tau = mk(0.0, 0.0);
+      double beta = alpha.re;
+      cplx scal = mk(0.0, 0.0);
+      if (xnorm2 != 0.0 || alpha.im != 0.0) {
+        beta = -copysign(sqrt(alpha.re * alpha.re + alpha.im * alpha.im + xnorm2), alpha.re);
+        tau = mk((beta - alpha.re) / beta, -alpha.im / beta);
+        scal = cdiv(mk(1.0, 0.0), mk(alpha.re - beta, alpha.im));
+      }
+      g.sync();                                   // everyone has read alpha
+      cplx* v = V + i * n;
+      for (int r = j + 2 + tid; r < n; r += T) {
+        const cplx x = col[r] * scal;             // tau == 0: the column is already zero below j+1
+        col[r] = x;
+        v[r] = x;
+      }
+      if (tid == 0) {
+        v[j + 1] = mk(1.0, 0.0);
+        w.e[j] = beta;
+        w.tau[j] = tau;
+        w.d[j] = col[j].re;
+      }
+      g.sync();
+      // ---- (3) w = A22 v with the stored (panel-start) trailing matrix, rows/cols j+1 .. n-1
+      const int m = n - j - 1;
+      {
+        int rw = ((m + 31) / 32) * 32;
+        if (rw > T) rw = T;
+        const int parts = T / rw > 0 ? T / rw : 1;
+        const int pr = tid % rw, pp = tid / rw;
+        if (pp < parts) {
+          for (int rb = 0; rb < m; rb += rw) {    // rb > 0 only when m > T
+            const int r = j + 1 + rb + pr;
+            cplx acc = mk(0.0, 0.0);
+            if (r < n) {
+              // eight independent accumulators: eight 16-byte loads in flight per thread, no serial FMA chain
+              // (the product is latency-bound: one 512-thread CTA per SM has only its own loads to hide them)
+              const cplx* arow = A + r;
+              cplx a0 = mk(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0, a7 = a0;
+              int c = j + 1 + pp;
+              for (; c + 7 * parts < n; c += 8 * parts) {
+                const cplx m0 = arow[(size_t)c * lda], m1 = arow[(size_t)(c + parts) * lda];
+                const cplx m2 = arow[(size_t)(c + 2 * parts) * lda], m3 = arow[(size_t)(c + 3 * parts) * lda];
+                const cplx m4 = arow[(size_t)(c + 4 * parts) * lda], m5 = arow[(size_t)(c + 5 * parts) * lda];
+                const cplx m6 = arow[(size_t)(c + 6 * parts) * lda], m7 = arow[(size_t)(c + 7 * parts) * lda];
+                fma_acc(a0, m0, v[c]);
+                fma_acc(a1, m1, v[c + parts]);
+                fma_acc(a2, m2, v[c + 2 * parts]);
+                fma_acc(a3, m3, v[c + 3 * parts]);
+                fma_acc(a4, m4, v[c + 4 * parts]);
+                fma_acc(a5, m5, v[c + 5 * parts]);
+                fma_acc(a6, m6, v[c + 6 * parts]);
+                fma_acc(a7, m7, v[c + 7 * parts]);
+              }
+              for (; c + 3 * parts < n; c += 4 * parts) {
+                const cplx m0 = arow[(size_t)c * lda], m1 = arow[(size_t)(c + parts) * lda];
+                const cplx m2 = arow[(size_t)(c + 2 * parts) * lda], m3 = arow[(size_t)(c + 3 * parts) * lda];
+                fma_acc(a0, m0, v[c]);
+                fma_acc(a1, m1, v[c + parts]);
+                fma_acc(a2, m2, v[c + 2 * parts]);
+                fma_acc(a3, m3, v[c + 3 * parts]);
+              }
+              for (; c < n; c += parts) fma_acc(a0, arow[(size_t)c * lda], v[c]);
+              acc = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+            }
+            if (parts == 1) {
+              if (r < n) W[i * n + r] = acc;
+            } else {                              // parts > 1 implies m <= rw: a single row block
+              w.wcol[pp * rw + pr] = acc;
+            }
+          }
+        }
+        if (parts > 1) {
+          g.sync();
+          for (int r = tid; r < m; r += T) {
+            cplx acc = w.wcol[r];
+            for (int q = 1; q < parts; ++q) acc = acc + w.wcol[q * rw + r];
+            W[i * n + j + 1 + r] = acc;
+          }
+        }
+      }
+      g.sync();
+      // ---- panel corrections: dots[k] = W_k^H v, dots[nb+k] = V_k^H v, one sub-team per dot product
+      if (i > 0) {
+        for (int q = g.sub(); q < 2 * i; q += g.nsub()) {
+          const cplx* src = q < i ? W + q * n : V + (q - i) * n;
+          double sre = 0.0, sim = 0.0;
+          for (int r = j + 1 + g.lane(); r < n; r += g.subsize()) {
+            const cplx t = cmul(src[r], v[r]);
+            sre += t.re; sim += t.im;
+          }
+          sre = g.subsum(sre); sim = g.subsum(sim);
+          if (g.lane() == 0) w.dots[q < i ? q : nb + (q - i)] = mk(sre, sim);
+        }
+        g.sync();
+        for (int r = j + 1 + tid; r < n; r += T) {
+          cplx acc = W[i * n + r];
+          for (int k = 0; k < i; ++k) {
+            acc = acc - V[k * n + r] * w.dots[k];
+            acc = acc - W[k * n + r] * w.dots[nb + k];
+          }
+          W[i * n + r] = acc;
+        }
+        g.sync();
+      }
+      // ---- w = tau w;  w += (-tau/2 (w^H v)) v
+      double dre = 0.0, dim = 0.0;
+      for (int r = j + 1 + tid; r < n; r += T) {
+        const cplx wr = tau * W[i * n + r];
+        W[i * n + r] = wr;
+        const cplx t = cmul(wr, v[r]);
+        dre += t.re; dim += t.im;
+      }
+      dre = g.sum(dre); dim = g.sum(dim);        // g.sum synchronises: the scaled w is visible
+      const cplx a2 = (-0.5) * (tau * mk(dre, dim));
+      for (int r = j + 1 + tid; r < n; r += T) W[i * n + r] = W[i * n + r] + a2 * v[r];
+      g.sync();
+    }
+    // ---- rank-2nb update of the trailing matrix: A22 -= V W^H + W V^H   (rows/cols >= j1)
+    const int j1 = j0 + nbp;
+    const int m = n - j1;
+    if (m > 0) {
+      int rw = ((m + 31) / 32) * 32;
+      if (rw > T) rw = T;
+      const int parts = T / rw > 0 ? T / rw : 1;
+      const int pr = tid % rw, pp = tid / rw;
+      if (pp < parts) {
+        for (int r = j1 + pr; r < n; r += rw) {
+          for (int k0 = 0; k0 < nb; k0 += 8) {    // 8 panel columns at a time in registers
+            if (k0 >= nbp) break;
+            cplx vr[8], wr[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int k = 0; k < 8; ++k) {
+              const bool in = k0 + k < nb;
+              vr[k] = in ? V[(k0 + k) * n + r] : mk(0.0, 0.0);
+              wr[k] = in ? W[(k0 + k) * n + r] : mk(0.0, 0.0);
+            }
+            for (int c = j1 + pp; c < n; c += parts) {
+              cplx a = A[r + (size_t)c * lda];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+              for (int k = 0; k < 8; ++k) {
+                if (k0 + k < nb) {
+                  const cplx wc = W[(k0 + k) * n + c], vc = V[(k0 + k) * n + c];
+                  // a -= vr * conj(wc) + wr * conj(vc)
+                  a.re -= vr[k].re * wc.re + vr[k].im * wc.im + wr[k].re * vc.re + wr[k].im * vc.im;
+                  a.im -= vr[k].im * wc.re - vr[k].re * wc.im + wr[k].im * vc.re - wr[k].re * vc.im;
+                }
+              }
+              A[r + (size_t)c * lda] = a;
+            }
+          }
+        }
+      }
+      g.sync();
+    }
+  }
+  if (tid == 0) {
+    w.d[n - 1] = A[(n - 1) + (size_t)(n - 1) * lda].re;
+    w.e[n - 1] = 0.0;
+    w.tau[n - 1] = mk(0.0, 0.0);
+  }
+  g.sync();
+}
+// Both variants are kept because neither dominates (profiles/README.md r09): the full-matrix product (a thread per
+// row, eight independent loads in flight per thread, no shuffle) is latency-friendlier, the lower-triangle one moves
+// half the bytes.  w.wcol .. w.racc (>= group size complex numbers) serves as the split-product scratch here.
+
+// ---------------------------------------------------------------------------------------------
 // 2. eigenvalues of the tridiagonal (d, e) by bisection on the Sturm count; lam ascending.
 // Returns (through every thread) the norm estimate tnorm = max Gershgorin radius.
 // ---------------------------------------------------------------------------------------------
@@ -614,25 +827,33 @@ TBK_HD void backtransform_column(G& g, const BlkWork& w, int c, Store store) {
 
 // ---------------------------------------------------------------------------------------------
 // 4b. back-transformation of ALL tridiagonal eigenvectors by the whole group: every sub-team owns
-// one column of a batch of nsub columns (held in registers as above); the reflectors are staged
+// CB columns of a batch of nsub * CB columns (held in registers as above); the reflectors are staged
 // RB at a time in `stage` (shared memory, [RB][n], zero above the unit element) by all threads,
 // so that the matrix of reflectors is read from L2/HBM once per column batch instead of once per
-// column.  store(c, r, x_r) receives element r of eigenvector c.
+// column.  A reflector element read from shared memory serves all CB columns of the sub-team: with
+// one column the loop is bound by those reads (two 16-byte reads per 8 FMAs), with two or four it is
+// bound by the FP64 pipe.  CB is limited by the registers (CB * MAXM complex numbers per thread).
+// store(c, r, x_r) receives element r of eigenvector c.
 // ---------------------------------------------------------------------------------------------
-template <int MAXM, class G, class Store>
+template <int MAXM, int CB, class G, class Store>
 TBK_HD void backtransform_all(G& g, const BlkWork& w, cplx* stage, int RB, Store store) {
   const int n = w.n, lda = w.lda;
   const int L = g.lane(), S = g.subsize(), T = g.size(), tid = g.tid();
-  for (int c0 = 0; c0 < n; c0 += g.nsub()) {
-    const int c = c0 + g.sub();
-    const bool active = c < n;
-    cplx x[MAXM];
+  for (int c0 = 0; c0 < n; c0 += g.nsub() * CB) {
+    const int cbase = c0 + g.sub() * CB;
+    const bool active = cbase < n;
+    cplx x[CB][MAXM];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int m = 0; m < MAXM; ++m) {
-      const int r = L + S * m;
-      x[m] = mk((active && r < n) ? w.Z[(size_t)r * n + c] : 0.0, 0.0);
+    for (int q = 0; q < CB; ++q) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int m = 0; m < MAXM; ++m) {
+        const int r = L + S * m;
+        x[q][m] = mk((cbase + q < n && r < n) ? w.Z[(size_t)r * n + cbase + q] : 0.0, 0.0);
+      }
     }
     for (int jhi = n - 2; jhi >= 0; jhi -= RB) {
       const int jlo = jhi - RB + 1 > 0 ? jhi - RB + 1 : 0;
@@ -648,7 +869,11 @@ TBK_HD void backtransform_all(G& g, const BlkWork& w, cplx* stage, int RB, Store
         const cplx tau = w.tau[j];
         if (tau.re == 0.0 && tau.im == 0.0) continue;
         const cplx* v = stage + (size_t)(j - jlo) * n;
-        double dre = 0.0, dim = 0.0;
+        double dre[CB], dim[CB];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < CB; ++q) { dre[q] = 0.0; dim[q] = 0.0; }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -656,20 +881,38 @@ TBK_HD void backtransform_all(G& g, const BlkWork& w, cplx* stage, int RB, Store
           if (S * m + S - 1 > j) {                // sub-team-uniform: this slot holds rows > j
             const int r = L + S * m;
             if (r < n) {
-              const cplx t = cmul(v[r], x[m]);    // conj(v) x; v is zero for r <= j
-              dre += t.re; dim += t.im;
+              const cplx vr = v[r];               // zero for r <= j
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+              for (int q = 0; q < CB; ++q) {
+                const cplx t = cmul(vr, x[q][m]); // conj(v) x
+                dre[q] += t.re; dim[q] += t.im;
+              }
             }
           }
         }
-        dre = g.subsum(dre); dim = g.subsum(dim);
-        const cplx f = tau * mk(dre, dim);
+        cplx f[CB];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < CB; ++q) {
+          const double a = g.subsum(dre[q]), b = g.subsum(dim[q]);
+          f[q] = tau * mk(a, b);
+        }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int m = 0; m < MAXM; ++m) {
           if (S * m + S - 1 > j) {
             const int r = L + S * m;
-            if (r < n) x[m] = x[m] - f * v[r];
+            if (r < n) {
+              const cplx vr = v[r];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+              for (int q = 0; q < CB; ++q) x[q][m] = x[q][m] - f[q] * vr;
+            }
           }
         }
       }
@@ -678,9 +921,16 @@ TBK_HD void backtransform_all(G& g, const BlkWork& w, cplx* stage, int RB, Store
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-      for (int m = 0; m < MAXM; ++m) {
-        const int r = L + S * m;
-        if (r < n) store(c, r, x[m]);
+      for (int q = 0; q < CB; ++q) {
+        if (cbase + q < n) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+          for (int m = 0; m < MAXM; ++m) {
+            const int r = L + S * m;
+            if (r < n) store(cbase + q, r, x[q][m]);
+          }
+        }
       }
     }
   }

@@ -447,7 +447,7 @@ solve_block_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long lon
 // tridiagonal eigenvectors in an L2/HBM workspace, panels and all O(n) data in shared memory
 // ===========================================================================
 struct BlkShape {
-  int n, lda, nb, nt, threads, nph, nred;
+  int n, lda, nb, nt, threads, nph, nred, sym;
   size_t off_ph, off_gf, off_misc, smem;             // shared-memory layout after the BlkWork part
   size_t ws_A, ws_Z, ws_lu, ws_block;                // per-CTA global workspace, bytes
   GroupShape fallback;                               // unblocked solver's layout inside the same shared buffer
@@ -471,6 +471,13 @@ static BlkShape blk_shape(int n, int nph) {
   else {
     s.nb = 8; s.nred = nwarps;
     while (s.nred > 1 && total(8, s.nred) + 1024 > (size_t)kMaxSmem) --s.nred;
+  }
+  // tridiagonalisation variant: TBK_HETRD=sym reads / updates the lower triangle only (half the DRAM traffic),
+  // TBK_HETRD=full (default: measured faster on B200, profiles/README.md r09) streams the full trailing matrix
+  {
+    static int sym = -1;
+    if (sym < 0) { const char* e = getenv("TBK_HETRD"); sym = (e && strcmp(e, "sym") == 0) ? 1 : 0; }
+    s.sym = sym;
   }
   size_t off = (blk_shared_bytes(n, s.nb, s.nred) + 15) & ~(size_t)15;
   s.off_ph = off;   off += (size_t)(nph > 0 ? nph : 1) * 16;
@@ -561,7 +568,8 @@ solve_blocked_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long l
     long long t0 = prof ? clock64() : 0;
     const long long tstart = t0;
 #define TBK_PROF_MARK(slot) if (prof && tid == 0) { const long long t1 = clock64(); atomicAdd(prof + slot, (unsigned long long)(t1 - t0)); t0 = t1; }
-    hetrd_blocked<MAXM>(g, w);
+    if (shp.sym) hetrd_blocked<MAXM>(g, w);
+    else hetrd_blocked_full(g, w);
     TBK_PROF_MARK(0)
     const double tnorm = tridiag_bisect(g, w);
     TBK_PROF_MARK(1)
@@ -591,7 +599,7 @@ solve_blocked_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long l
           if (mibuf[d] == 0 && out.wrap[d]) zero_mask |= 1 << d;
         }
       }
-      backtransform_all<MAXM>(g, w, w.V, 2 * w.nb, [&](int c, int o, cplx x) {
+      backtransform_all<MAXM, (MAXM <= 4 ? 4 : (MAXM <= 8 ? 2 : 1))>(g, w, w.V, 2 * w.nb, [&](int c, int o, cplx x) {
         cplx v = x * gf[o];
         if (out.mode == 0) {
           out.evec[c * out.vc_sb + idx * out.vc_sk + o] = v;

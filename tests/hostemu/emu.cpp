@@ -76,7 +76,12 @@ struct TeamGroup {
   }
 };
 
+static int g_hetrd_sym = 1;
+
 extern "C" {
+
+// which tridiagonalisation the emu_heev_blocked* entry points run: 1 = lower triangle only, 0 = full matrix
+void emu_set_hetrd_sym(int on) { g_hetrd_sym = on; }
 
 // The blocked solver run by a team of T threads in sub-teams of S (T a multiple of S), as solve_blocked_kernel
 // runs it with T = 256 / 512 and S = 32.  Same contract as emu_heev_blocked.
@@ -96,13 +101,14 @@ int emu_heev_blocked_team(int n, double* A, int lda, int nb, int want_vec, doubl
   std::vector<int> fail(T, 0);
   auto body = [&](int t) {
     TeamGroup g{&shd, t};
-    hetrd_blocked<kBlkMaxN>(g, w);
+    if (g_hetrd_sym) hetrd_blocked<kBlkMaxN>(g, w);
+    else hetrd_blocked_full(g, w);
     const double tnorm = tridiag_bisect(g, w);
     if (t == 0) std::memcpy(ev, w.lam, n * 8);
     if (!want_vec) return;
     fail[t] = tridiag_invit(g, w, tnorm);
     if (fail[t]) return;                         // uniform across the team by construction
-    backtransform_all<kBlkMaxN>(g, w, w.V, 2 * nb, [&](int c, int r, cplx x) { out[(size_t)c * n + r] = x; });
+    backtransform_all<kBlkMaxN, 2>(g, w, w.V, 2 * nb, [&](int c, int r, cplx x) { out[(size_t)c * n + r] = x; });
   };
   std::vector<std::thread> th;
   for (int t = 1; t < T; ++t) th.emplace_back(body, t);
@@ -225,7 +231,8 @@ int emu_heev_blocked(int n, double* A, int lda, int nb, int want_vec, double* ev
   blk_carve_shared(w, sh.data());
   std::vector<double> Z((size_t)n * n), lu((size_t)4 * n);
   w.Z = Z.data(); w.lu = lu.data(); w.nt = 1;
-  hetrd_blocked<kBlkMaxN>(g, w);
+  if (g_hetrd_sym) hetrd_blocked<kBlkMaxN>(g, w);
+  else hetrd_blocked_full(g, w);
   if (tri) { std::memcpy(tri, w.d, n * 8); std::memcpy(tri + n, w.e, n * 8); }
   const double tnorm = tridiag_bisect(g, w);
   std::memcpy(ev, w.lam, n * 8);
@@ -236,7 +243,8 @@ int emu_heev_blocked(int n, double* A, int lda, int nb, int want_vec, double* ev
     for (int c = 0; c < n; ++c)
       backtransform_column<kBlkMaxN>(g, w, c, [&](int r, cplx x) { out[(size_t)c * n + r] = x; });
   } else {
-    backtransform_all<kBlkMaxN>(g, w, w.V, 2 * nb, [&](int c, int r, cplx x) { out[(size_t)c * n + r] = x; });
+    if (nb % 3 == 1) backtransform_all<kBlkMaxN, 3>(g, w, w.V, 2 * nb, [&](int c, int r, cplx x) { out[(size_t)c * n + r] = x; });
+    else backtransform_all<kBlkMaxN, 1>(g, w, w.V, 2 * nb, [&](int c, int r, cplx x) { out[(size_t)c * n + r] = x; });
   }
   return 0;
 }
