@@ -77,16 +77,20 @@ __global__ void peer_barrier_kernel(const __grid_constant__ PeerView pv, double*
 // completes deferred collectives nobody else picked up (one CTA, posts nothing)
 __global__ void peer_collect_kernel(const __grid_constant__ PeerView pv) {
   __shared__ int s_fail;
+  peer_prologue(pv);
+  __syncthreads();
   peer_collective(pv, nullptr, 0, 0, nullptr, &s_fail);
 }
 
 int peer_flush(tbk_peer* p, cudaStream_t st) {
   if (!peer_active(p)) return TBK_OK;
-  while (p->npending > 0) {
+  while (p->nqueue > 0) {
     PeerView v = peer_none();
-    v.rank = p->rank; v.nranks = p->nranks; v.epoch = 0;
-    for (int r = 0; r < p->nranks; ++r) v.box[r] = p->box[r];
-    peer_take_pending(p, v, p->npending < kPeerMaxPend ? p->npending : kPeerMaxPend);
+    peer_view_base(p, v);
+    v.epoch = 0;
+    peer_attach_posts(p, v);                  // its first (only) CTA posts what nobody posted yet ...
+    peer_attach_pends(p, v, true);            // ... and completes everything that is posted, up to the view's capacity
+    peer_age_posts(p);
     peer_collect_kernel<<<1, 64, 0, st>>>(v);
     TBK_LAUNCH_CHECK("peer_collect_kernel");
   }
@@ -316,13 +320,13 @@ int tbk_peer_barrier(tbk_peer* p, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   // a barrier is a synchronous collective of its own; it leaves deferred collectives alone (tbk_peer_flush
   // completes those) unless the slot-reuse rule forces them out first
-  if (p->npending > 0 && p->epoch + 1 - p->pending[0].epoch > (unsigned long long)kPeerMaxLag) {
+  if (p->nqueue > 0 && p->epoch + 1 - p->queue[0].epoch > (unsigned long long)kPeerMaxLag) {
     if (int rc = peer_flush(p, st)) return rc;
   }
   PeerView v = peer_none();
-  v.rank = p->rank; v.nranks = p->nranks; v.epoch = ++p->epoch; v.complete_self = 1;
-  for (int r = 0; r < p->nranks; ++r) v.box[r] = p->box[r];
-  peer_barrier_kernel<<<1, 32, 0, st>>>(v, (double*)((char*)p->box[p->rank] + kPeerMailboxBytes));
+  peer_view_base(p, v);
+  v.epoch = ++p->epoch; v.mode = 1;
+  peer_barrier_kernel<<<1, 32, 0, st>>>(v, (double*)((char*)p->box[p->rank] + kPeerMailboxBytes + kPeerLocalBytes));
   TBK_LAUNCH_CHECK("peer_barrier_kernel");
   return TBK_OK;
 }

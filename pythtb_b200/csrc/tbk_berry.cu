@@ -236,6 +236,7 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
   // stream (typically the grid solve that writes the array read here) was still draining; everything it
   // wrote is visible after this wait.  A no-op when launched without the attribute.
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  peer_prologue(peer);                              // first CTA: post what an earlier kernel of this step kept locally (N > 1)
   long long occ[NOCC];
 #pragma unroll
   for (int m = 0; m < NOCC; ++m) occ[m] = (long long)v.occ[m] * v.ss;
@@ -410,7 +411,7 @@ static int launch_flux_rows(const WfView& v, const long long* off, long long nsl
   double* part_arg = plaq ? (total ? partial : nullptr) : partial;
   unsigned long long* trace = cta_trace_buffer();
   // a synchronous prepared call waits on a pinned word the last CTA writes after the totals
-  const DoneSignal done = (total && (pview.nranks <= 1 || pview.complete_self)) ? take_done_request() : DoneSignal{nullptr, 0};
+  const DoneSignal done = (total && (pview.nranks <= 1 || pview.mode == 1)) ? take_done_request() : DoneSignal{nullptr, 0};
   if (plaq)
     TBK_CUDA(cudaLaunchKernelEx(&cfg, flux_rows_kernel<NOCC, N, true, SLOTS>, v, off, n0, stride0, n1, stride1, tl, nslice, plaq,
                                 part_arg, ticket, total, pview, trace, done));
@@ -516,6 +517,7 @@ flux_ring_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  peer_prologue(peer);
   const long long p0 = n0 - 1, p1 = n1 - 1;
   unsigned q_cons = 0;                                      // rows consumed so far by this CTA (stage = q % D)
   for (long long tile = blockIdx.x; tile < tl.ntiles; tile += gridDim.x) {

@@ -193,13 +193,13 @@ struct tbk_peer {
   unsigned long long epoch;          // advanced by every collective issued through this group
   double* box[tbk::kPeerMaxRanks];   // box[rank] is the local allocation
   bool connected;
-  bool defer_next;                   // tbk_peer_defer: the next *_x collective is only POSTED by its kernel
-  int npending;                      // posted, not yet completed collectives (oldest first)
-  tbk::PeerPending pending[2 * tbk::kPeerMaxPend];
+  bool defer_next;                   // tbk_peer_defer: the next *_x collective is a deferred one
+  int nqueue;                        // deferred collectives on their way (oldest first)
+  tbk::PeerPending queue[tbk::kPeerQueue];
 };
 
 namespace tbk {
-// completes every pending collective with one-CTA kernels (tbk_api.cu); no-op when nothing is pending
+// posts and completes every deferred collective with one-CTA kernels (tbk_api.cu); no-op when the queue is empty
 int peer_flush(tbk_peer* p, cudaStream_t st);
 
 inline PeerView peer_none() {
@@ -208,45 +208,64 @@ inline PeerView peer_none() {
   return v;
 }
 inline bool peer_active(const tbk_peer* p) { return p && p->connected && p->nranks > 1; }
-
-// moves the oldest `count` pending collectives into the view
-inline void peer_take_pending(tbk_peer* p, PeerView& v, int count) {
-  for (int i = 0; i < count; ++i) v.pend[v.npend++] = p->pending[i];
-  for (int i = count; i < p->npending; ++i) p->pending[i - count] = p->pending[i];
-  p->npending -= count;
+inline void peer_view_base(const tbk_peer* p, PeerView& v) {
+  v.rank = p->rank; v.nranks = p->nranks;
+  for (int r = 0; r < p->nranks; ++r) v.box[r] = p->box[r];
+}
+inline double* peer_local_slot(const tbk_peer* p, unsigned long long epoch) {
+  return (double*)((char*)p->box[p->rank] + kPeerMailboxBytes) + (size_t)(epoch % kPeerDepth) * kPeerMaxVals;
+}
+// attach every not yet posted queue entry to the view's post list (the kernel's first CTA posts them)
+inline void peer_attach_posts(tbk_peer* p, PeerView& v) {
+  for (int i = 0; i < p->nqueue && v.npost < kPeerMaxPost; ++i)
+    if (!p->queue[i].posted) { v.post[v.npost++] = p->queue[i]; p->queue[i].posted = 2; }     // 2: posted by THIS kernel
+}
+// move queue entries to the view's completion list: all of them, or only those a PREVIOUS kernel posted
+inline void peer_attach_pends(tbk_peer* p, PeerView& v, bool also_fresh) {
+  int keep = 0;
+  for (int i = 0; i < p->nqueue; ++i) {
+    const bool take = (p->queue[i].posted == 1 || (also_fresh && p->queue[i].posted == 2)) && v.npend < kPeerMaxPend;
+    if (take) v.pend[v.npend++] = p->queue[i];
+    else p->queue[keep++] = p->queue[i];
+  }
+  p->nqueue = keep;
+}
+// what this kernel posts counts as "posted by an earlier kernel" from the next kernel on
+inline void peer_age_posts(tbk_peer* p) {
+  for (int i = 0; i < p->nqueue; ++i)
+    if (p->queue[i].posted == 2) p->queue[i].posted = 1;
 }
 
 // PeerView for the next collective of nv values (advances the epoch).
-//   completer: a kernel that may complete older deferred collectives (the flux kernels, the flush / barrier
-//   kernels); the grid-solve kernel only posts when deferred, so that nothing but a few stores sits between its
-//   last CTA and the dependent flux kernel.
-// A synchronous collective (defer_next not set) completes everything pending together with its own result; a
-// deferred one is queued on the handle and completes only the queue entries that are >= 2 epochs old (the previous
-// step's).  rc != 0: launching a flush failed.
+//   completer: a kernel whose last CTA may complete older deferred collectives (the flux kernels, the flush
+//   kernel); the grid-solve kernel never does, so that nothing sits between its last CTA and the dependent flux kernel.
+// Every collective-capable kernel posts (from its FIRST CTA) whatever the queue holds unposted.  A synchronous
+// collective (defer_next not set) also completes the whole queue together with its own result; a deferred one is
+// queued and its kernel completes only what an EARLIER kernel posted.  rc != 0: launching a flush failed.
 inline int peer_next(tbk_peer* p, int nv, int op, double* out, bool completer, cudaStream_t st, PeerView* view) {
   PeerView v = peer_none();
   if (!peer_active(p)) { if (p) p->defer_next = false; *view = v; return 0; }
   const bool defer = p->defer_next;
   p->defer_next = false;
-  // slot-reuse safety / queue capacity: never let a posted epoch lag more than kPeerMaxLag, never overflow the view
-  if (p->npending > 0 && (p->epoch + 1 - p->pending[0].epoch > (unsigned long long)kPeerMaxLag ||
-                          (!defer && p->npending > kPeerMaxPend) || p->npending >= 2 * kPeerMaxPend - 1)) {
+  // slot-reuse safety / capacities: never run more than kPeerMaxLag epochs ahead of the oldest uncompleted one
+  if (p->nqueue > 0 && (p->epoch + 1 - p->queue[0].epoch > (unsigned long long)kPeerMaxLag || p->nqueue >= kPeerQueue - 1 ||
+                        (!defer && p->nqueue > kPeerMaxPend) )) {
     if (int rc = peer_flush(p, st)) return rc;
   }
-  v.rank = p->rank; v.nranks = p->nranks; v.epoch = ++p->epoch;
-  for (int r = 0; r < p->nranks; ++r) v.box[r] = p->box[r];
-  v.complete_self = defer ? 0 : 1;
+  peer_view_base(p, v);
+  v.epoch = ++p->epoch;
+  peer_attach_posts(p, v);
   if (!defer) {
-    peer_take_pending(p, v, p->npending);                     // <= kPeerMaxPend by the check above
+    v.mode = 1;
+    peer_attach_pends(p, v, true);
   } else {
-    if (completer) {
-      int old = 0;
-      while (old < p->npending && old < kPeerMaxPend && p->pending[old].epoch + 2 <= v.epoch) ++old;
-      peer_take_pending(p, v, old);
-    }
-    PeerPending& q = p->pending[p->npending++];
-    q.epoch = v.epoch; q.nv = nv; q.op = op; q.out = out;
+    v.mode = 2;
+    v.local = peer_local_slot(p, v.epoch);
+    if (completer) peer_attach_pends(p, v, false);
+    PeerPending& q = p->queue[p->nqueue++];
+    q.epoch = v.epoch; q.nv = nv; q.op = op; q.out = out; q.local = v.local; q.posted = 0;
   }
+  peer_age_posts(p);
   *view = v;
   return 0;
 }

@@ -158,6 +158,7 @@ mesh_small_kernel(const __grid_constant__ DenseSmall ds, const __grid_constant__
   // let a programmatic dependent (the flux kernel) be scheduled as soon as this grid's CTAs retire: the whole
   // grid is resident from the start (one wave), so the dependent can never take a slot a CTA of this grid needs
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  peer_prologue(peer);                              // first CTA: post the deferred reductions of the previous step (N > 1)
   if (threadIdx.x < N) s_pbc0[threadIdx.x] = tl.closing_g >= 0 ? out.pbc_phase[threadIdx.x] : mk(1.0, 0.0);
   if (threadIdx.x < out.nd * N) {
     const int d = threadIdx.x / N;

@@ -7,24 +7,27 @@
 // epoch, and an aligned 8-byte store is a single NVLink transaction — so a word is either absent
 // (old tag) or complete, and no release fence / separate flag store is needed.
 //
-// A collective has two halves that need not run in the same kernel:
-//   POST      the CTA that finishes a rank's local reduction stores its words into slot
-//             [epoch % depth][rank] of EVERY rank's mailbox (one thread per word, fire and forget);
-//   COMPLETE  some CTA polls the words of its OWN mailbox until each carries that epoch's tag,
-//             combines the nranks vectors in rank order (deterministic) and writes the result.
-// A synchronous collective (the public API returns the number to the caller) does both in the
+// A collective has three steps that need not run in the same kernel:
+//   STORE     (deferred collectives only) the CTA that finishes a rank's local reduction keeps the values in a
+//             LOCAL scratch slot — no NVLink traffic at the end of the producing kernel;
+//   POST      some CTA stores the values into slot [epoch % depth][rank] of EVERY rank's mailbox (one thread
+//             per word, fire and forget);
+//   COMPLETE  some CTA polls the words of its OWN mailbox until each carries that epoch's tag, combines the
+//             nranks vectors in rank order (deterministic) and writes the result.
+// A synchronous collective (the public API returns the number to the caller) posts and completes in the
 // producing kernel's last CTA: one exposed NVLink round trip plus the skew between the ranks.
-// A DEFERRED collective (tbk_peer_defer) is only posted by its kernel; it is completed by a later
-// kernel on the stream — the next flux kernel completes the collectives that are at least two epochs
-// old, i.e. those of the PREVIOUS solve + flux step, whose words arrived tens of microseconds ago —
-// or by tbk_peer_flush.  A device-resident pipeline (a parameter sweep that reads its Chern numbers
-// at the end) therefore never waits for a peer inside a step: no exposed round trip, no skew.
+// A DEFERRED collective (tbk_peer_defer) is stored locally by its kernel, posted by the FIRST CTA of the next
+// collective-capable kernel on the stream at its START, and completed by the last CTA of a later flux kernel (or
+// tbk_peer_flush).  Remote stores at the END of a kernel are what costs: the grid does not complete (and a
+// programmatic dependent does not pass griddepcontrol.wait) before they are acknowledged over NVLink, ~2 us
+// measured per kernel (profiles/README.md r09: N = 2 efficiency 0.876 with posts at the kernel ends).  Posted from
+// a kernel's first CTA they drain under the kernel's body, and a device-resident pipeline (a parameter sweep that
+// reads its Chern numbers at the end) never waits for a peer inside a step.
 //
-// Slot reuse: epoch e and e + kPeerDepth share a slot.  The host handle never lets a posted epoch
-// lag more than kPeerMaxLag behind (it inserts a completing kernel first), and a rank posts e only
-// after completing everything up to e - kPeerMaxLag; rank r posting e + D has therefore completed
-// e + D - L, which needed q's words of e + D - L, which q posted after completing e + D - 2L >= e
-// for D >= 2L: the receiver has read a slot before anybody overwrites it.
+// Slot reuse: epoch e and e + kPeerDepth share a slot.  The host handle never lets the newest epoch run more than
+// kPeerMaxLag ahead of the oldest uncompleted one (it inserts a flush kernel first); rank r posting e + D has
+// therefore completed e + D - L, which needed q's words of e + D - L, which q posted after completing
+// e + D - 2L >= e for D >= 2L: the receiver has read a slot before anybody overwrites it.
 // All ranks must issue the same sequence of collectives (as with NCCL).  A rank that waits longer
 // than ~4 s gives up and returns NaN instead of hanging the GPU.
 #pragma once
@@ -35,24 +38,31 @@ namespace tbk {
 constexpr int kPeerMaxRanks = 8;
 constexpr int kPeerMaxVals = 16;                     // doubles per contribution
 constexpr int kPeerSlotWords = 2 * kPeerMaxVals;     // 8-byte words per (epoch slot, source rank)
-constexpr int kPeerDepth = 8;                        // epochs before a slot is reused
-constexpr int kPeerMaxLag = 4;                       // a posted collective is completed at most this many epochs later
-constexpr int kPeerMaxPend = 4;                      // deferred collectives one kernel can complete
+constexpr int kPeerDepth = 16;                       // epochs before a slot is reused
+constexpr int kPeerMaxLag = 7;                       // the newest epoch runs at most this far ahead of the oldest uncompleted one
+constexpr int kPeerMaxPend = 6;                      // deferred collectives one kernel can complete
+constexpr int kPeerMaxPost = 4;                      // deferred collectives one kernel can post
+constexpr int kPeerQueue = 8;                        // deferred collectives in flight on the host handle
 constexpr size_t kPeerMailboxBytes = (size_t)kPeerDepth * kPeerMaxRanks * kPeerSlotWords * sizeof(unsigned long long);
-constexpr size_t kPeerScratchBytes = 512;            // local scratch behind the mailbox (barrier result)
+constexpr size_t kPeerLocalBytes = (size_t)kPeerDepth * kPeerMaxVals * sizeof(double);   // local slots of deferred values
+constexpr size_t kPeerScratchBytes = kPeerLocalBytes + 256;   // behind the mailbox: local slots, then the barrier result
 
-struct PeerPending {                                 // a posted, not yet completed collective
+struct PeerPending {                                 // a deferred collective on its way
   unsigned long long epoch;
   int nv, op;                                        // op 0: sum in rank order, 1: min
-  double* out;
+  double* out;                                       // where the combined result goes
+  double* local;                                     // this rank's values (local scratch slot of the epoch)
+  int posted;                                        // host bookkeeping: a kernel that posts it has been enqueued
 };
 
 struct PeerView {
   int rank, nranks;                                  // nranks <= 1: no exchange
-  unsigned long long epoch;                          // of this kernel's own post (0: it posts nothing)
-  int complete_self;                                 // 1: also wait for the peers' words of `epoch` and write the result
-  int npend;
-  PeerPending pend[kPeerMaxPend];                    // older collectives this kernel completes
+  unsigned long long epoch;                          // of this kernel's own collective (0: none)
+  int mode;                                          // own collective: 1 synchronous (post + complete here), 2 deferred (store locally)
+  double* local;                                     // mode 2: the local slot of `epoch`
+  int npost, npend;
+  PeerPending post[kPeerMaxPost];                    // deferred collectives this kernel's FIRST CTA posts at its start
+  PeerPending pend[kPeerMaxPend];                    // deferred collectives this kernel's last CTA completes
   double* box[kPeerMaxRanks];                        // mailbox of every rank (own one included)
 };
 
@@ -70,11 +80,11 @@ __device__ __forceinline__ unsigned peer_tag(unsigned long long epoch) {
   return (unsigned)epoch | 0x80000000u;              // never the zero of a fresh mailbox, never the tag this
 }                                                    // slot carried kPeerDepth collectives ago
 
-// POST: s_vals[nv] (shared memory, visible to the CTA) -> every rank's mailbox.  All threads of one CTA.
-__device__ __forceinline__ void peer_post(const PeerView& pv, const double* s_vals, int nv) {
-  const unsigned tag = peer_tag(pv.epoch);
+// POST: vals[nv] (shared or global memory, visible to the CTA) of `epoch` -> every rank's mailbox.  All threads of one CTA.
+__device__ __forceinline__ void peer_post(const PeerView& pv, unsigned long long epoch, const double* s_vals, int nv) {
+  const unsigned tag = peer_tag(epoch);
   const int nw = 2 * nv;
-  const size_t slot = (size_t)((int)(pv.epoch % kPeerDepth) * pv.nranks + pv.rank) * kPeerSlotWords;
+  const size_t slot = (size_t)((int)(epoch % kPeerDepth) * pv.nranks + pv.rank) * kPeerSlotWords;
   for (int t = threadIdx.x; t < pv.nranks * nw; t += blockDim.x) {
     const int r = t / nw, w = t - r * nw;
     const unsigned long long bits = (unsigned long long)__double_as_longlong(s_vals[w >> 1]);
@@ -117,20 +127,35 @@ __device__ inline void peer_complete(const PeerView& pv, unsigned long long epoc
   __syncthreads();                                   // s_half is free again; out[] is written
 }
 
-// The collective as one kernel sees it, called by ALL threads of ONE CTA per rank: post vals[nv] (if this
-// kernel has an epoch of its own), complete the older collectives attached to the view, and — for a synchronous
-// collective — complete its own: out[nv] = sum (op 0, rank order) / min (op 1) over the ranks.  The post goes
-// first: the peers' waits then overlap this rank's completions.
+// Kernel prologue, called by ALL threads of the kernel right at its start (after griddepcontrol.wait where the
+// kernel is a programmatic dependent): the first CTA posts the deferred collectives attached to the view from
+// their local slots.  The remote stores drain under the kernel's body.
+__device__ __forceinline__ void peer_prologue(const PeerView& pv) {
+  if (pv.nranks > 1 && pv.npost > 0 && blockIdx.x == 0) {
+    for (int i = 0; i < pv.npost; ++i) peer_post(pv, pv.post[i].epoch, pv.post[i].local, pv.post[i].nv);
+  }
+}
+
+// The collective as the LAST CTA of a kernel sees it, called by all its threads: vals[nv] are this rank's values.
+//   mode 1 (synchronous): post them, complete the deferred collectives attached to the view, complete the own one:
+//          out[nv] = sum (op 0, rank order) / min (op 1) over the ranks.  The post goes first: the peers' waits
+//          then overlap this rank's completions.
+//   mode 2 (deferred): keep them in the local slot (a later kernel posts them), complete the attached ones.
+//   epoch 0: only complete the attached ones (flush kernel).
 __device__ inline void peer_collective(const PeerView& pv, const double* vals, int nv, int op, double* out, int* s_fail) {
   __shared__ double s_vals[kPeerMaxVals];
   __shared__ unsigned s_half[kPeerMaxRanks * kPeerSlotWords];
   const int tid = threadIdx.x;
   if (tid == 0) *s_fail = 0;
-  if (pv.epoch != 0 && tid < nv) s_vals[tid] = vals[tid];
+  if (pv.epoch != 0 && tid < nv) {
+    const double x = vals[tid];
+    if (pv.mode == 2) pv.local[tid] = x;
+    else s_vals[tid] = x;
+  }
   __syncthreads();
-  if (pv.epoch != 0) peer_post(pv, s_vals, nv);
+  if (pv.epoch != 0 && pv.mode == 1) peer_post(pv, pv.epoch, s_vals, nv);
   for (int i = 0; i < pv.npend; ++i) peer_complete(pv, pv.pend[i].epoch, pv.pend[i].nv, pv.pend[i].op, pv.pend[i].out, s_half, s_fail);
-  if (pv.epoch != 0 && pv.complete_self) peer_complete(pv, pv.epoch, nv, op, out, s_half, s_fail);
+  if (pv.epoch != 0 && pv.mode == 1) peer_complete(pv, pv.epoch, nv, op, out, s_half, s_fail);
 }
 #endif
 

@@ -992,7 +992,7 @@ static int launch_mesh_small(const tbk_model* m, const KSrc& ks, const OutSpec& 
   if (gaps_dev) { if (int rc = peer_next(peer, n - 1, 1, gaps_dev, false, st, &pview)) return rc; }
   // a synchronous prepared call waits on a pinned word this kernel's last CTA writes after the gaps
   // (not for a deferred reduction: the gaps are then completed by a later kernel)
-  const DoneSignal done = (gaps_dev && (pview.nranks <= 1 || pview.complete_self)) ? take_done_request() : DoneSignal{nullptr, 0};
+  const DoneSignal done = (gaps_dev && (pview.nranks <= 1 || pview.mode == 1)) ? take_done_request() : DoneSignal{nullptr, 0};
 #define TBK_MESH_LAUNCH(NN, PP, MB, RP) \
   mesh_small_kernel<NN, PP, MB, RP><<<grid, kMeshThreads, 0, st>>>(ds, ks, out, tl, gauge, partial, ticket, gaps_dev, pview, cta_trace_buffer(), done)
   if (n == 2) {
