@@ -318,8 +318,9 @@ int tbk_prepared_destroy(tbk_prepared* call);
  * Call after synchronising the stream.  Profiling aid, not part of the reference interface. */
 int tbk_debug_profile(uint64_t* out8, int32_t reset);
 /* Profiling aid (TBK_CTA_TRACE=1 in the environment before the first launch): per-CTA timeline of the
- * last mesh_small_kernel / flux_rows_kernel launch, 4 words per CTA: SM id, begin and end
- * (%globaltimer, ns), blockIdx.  out: [max_ctas][4].  TBK_ERR_UNSUPPORTED when tracing is off. */
+ * last mesh_small_kernel launch (entries [0, 4096)) and the last flux_rows_kernel launch (entries [4096, 8192)),
+ * 4 words per CTA: SM id, begin and end (%globaltimer, ns), blockIdx.  out: [max_ctas][4], max_ctas <= 8192.
+ * TBK_ERR_UNSUPPORTED when tracing is off. */
 int tbk_debug_cta_trace(uint64_t* out, int64_t max_ctas, int32_t reset);
 
 /* FP64 peak microkernels for the benchmark harness: one launch of a register-resident kernel that issues only

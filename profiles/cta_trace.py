@@ -22,13 +22,23 @@ eng = _engine.get_engine()
 w = tb.wf_array(model, [1024 * world + 1, 1025], shard=(rank, world)) if world > 1 else tb.wf_array(model, [1025, 1025])
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=eng.device)
 CAP = 4096
-buf = (ctypes.c_uint64 * (CAP * 4))()
+buf = (ctypes.c_uint64 * (2 * CAP * 4))()
 
 
-def grab():
-    _lib.check(eng.lib.tbk_debug_cta_trace(buf, CAP, 1))
-    a = np.ctypeslib.as_array(buf).reshape(CAP, 4).astype(np.int64).copy()
-    return a[a[:, 2] > 0]
+def grab(which=None):
+    """Timeline of the last traced launch: the solve kernel's half of the buffer, the flux kernel's, or (which=None)
+    whichever was launched last in the calls this script makes one at a time."""
+    _lib.check(eng.lib.tbk_debug_cta_trace(buf, 2 * CAP, 1))
+    a = np.ctypeslib.as_array(buf).reshape(2 * CAP, 4).astype(np.int64).copy()
+    lo, hi = a[:CAP], a[CAP:]
+    lo, hi = lo[lo[:, 2] > 0], hi[hi[:, 2] > 0]
+    if which == "solve":
+        return lo
+    if which == "flux":
+        return hi
+    if which == "both":
+        return lo, hi
+    return hi if len(hi) else lo
 
 
 def summarise(name, a):
@@ -82,15 +92,23 @@ for rep in range(10):
     eng.lib.tbk_flush_l2(ctypes.c_void_p(flush.data_ptr()), flush.numel(), eng.stream())
     eng.peer_barrier()
     w._solve_on_grid_device([-0.5, -0.5], defer_reduce=world > 1)
-    w._berry_flux_device(occ)
+    w._berry_flux_device(occ, defer_reduce=world > 1)
     torch.cuda.synchronize()
-    b = grab()
+    a, b = grab("both")
     if world > 1:
         dist.barrier()
     if rep >= 2:
+        t0 = a[:, 1].min()
         instep.append(((b[:, 2].max() - b[:, 1].min()) / 1e3, float(np.sort(b[:, 2])[-2] - b[:, 1].min()) / 1e3,
-                       float(np.median(b[:, 2] - b[:, 1])) / 1e3))
-print("rank %d world %d flux kernel inside a step, us (span, span without its last CTA, median CTA): %s" % (rank, world, np.round(np.median(np.array(instep), axis=0), 2)))
+                       float(np.median(b[:, 2] - b[:, 1])) / 1e3,
+                       # the step on one clock, relative to the first solve CTA: solve body end (all but the last CTA), solve end,
+                       # first / median / last flux CTA start, flux body end, flux end
+                       float(np.sort(a[:, 2])[-2] - t0) / 1e3, float(a[:, 2].max() - t0) / 1e3, float(b[:, 1].min() - t0) / 1e3,
+                       float(np.median(b[:, 1]) - t0) / 1e3, float(b[:, 1].max() - t0) / 1e3, float(np.sort(b[:, 2])[-2] - t0) / 1e3,
+                       float(b[:, 2].max() - t0) / 1e3))
+med = np.round(np.median(np.array(instep), axis=0), 2)
+print("rank %d world %d flux kernel inside a step, us (span, span without its last CTA, median CTA): %s" % (rank, world, med[:3]))
+print("rank %d world %d step timeline us from the first solve CTA (solve body end, solve end, flux first/median/last CTA start, flux body end, flux end): %s" % (rank, world, med[3:]))
 print("rank %d world %d spans us (mesh, flux, flux without its last CTA): %s" % (rank, world, np.round(np.median(np.array(spans), axis=0), 2)))
 if rank == 0:
     print(json.dumps(res, indent=1))

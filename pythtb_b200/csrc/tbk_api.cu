@@ -46,7 +46,7 @@ unsigned long long* cta_trace_buffer() {
   if (on < 0) { const char* e = getenv("TBK_CTA_TRACE"); on = (e && atoi(e) == 1) ? 1 : 0; }
   if (!on) return nullptr;
   if (!buf) {
-    const size_t bytes = (size_t)kCtaTraceCap * 4 * sizeof(unsigned long long);
+    const size_t bytes = (size_t)2 * kCtaTraceCap * 4 * sizeof(unsigned long long);   // [0, cap): solve kernel, [cap, 2 cap): flux kernel
     if (cudaMalloc(&buf, bytes) != cudaSuccess) return nullptr;
     cudaMemset(buf, 0, bytes);
   }
@@ -335,10 +335,10 @@ int tbk_debug_cta_trace(uint64_t* out, int64_t max_ctas, int32_t reset) {
   if (!out || max_ctas < 0) { set_error("tbk_debug_cta_trace: bad argument"); return TBK_ERR_ARG; }
   unsigned long long* buf = cta_trace_buffer();
   if (!buf) { set_error("tbk_debug_cta_trace: tracing is off (set TBK_CTA_TRACE=1 before the first launch)"); return TBK_ERR_UNSUPPORTED; }
-  const size_t n = (size_t)(max_ctas < kCtaTraceCap ? max_ctas : kCtaTraceCap) * 4 * sizeof(unsigned long long);
+  const size_t n = (size_t)(max_ctas < 2 * kCtaTraceCap ? max_ctas : 2 * kCtaTraceCap) * 4 * sizeof(unsigned long long);
   TBK_CUDA(cudaDeviceSynchronize());
   TBK_CUDA(cudaMemcpy(out, buf, n, cudaMemcpyDeviceToHost));
-  if (reset) TBK_CUDA(cudaMemset(buf, 0, (size_t)kCtaTraceCap * 4 * sizeof(unsigned long long)));
+  if (reset) TBK_CUDA(cudaMemset(buf, 0, (size_t)2 * kCtaTraceCap * 4 * sizeof(unsigned long long)));
   return TBK_OK;
 }
 

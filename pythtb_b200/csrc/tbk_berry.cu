@@ -345,9 +345,13 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
   if (!partial) { cta_trace_end(trace, t_begin); return; }
   __threadfence();
   __syncthreads();
-  if (tid == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+  if (tid == 0) s_last = (int)atomicInc(ticket, gridDim.x - 1);          // order of finishing
   __syncthreads();
-  if (!s_last) { cta_trace_end(trace, t_begin); return; }
+  const int tick = s_last;
+  __syncthreads();
+  // the FIRST CTA to finish completes the older deferred cross-rank reductions (N > 1) while the wave drains
+  if (tick == 0) peer_complete_pending(peer, &s_last);
+  if (tick != (int)gridDim.x - 1) { cta_trace_end(trace, t_begin); return; }
   __threadfence();
   const long long count = cta_partial ? (long long)gridDim.x : per_slice;
   for (long long s = 0; s < nslice; ++s) {
@@ -365,9 +369,9 @@ flux_rows_kernel(WfView v, const long long* __restrict__ slice_off, long long n0
       else total[s] = t;
     }
   }
-  if (peer.nranks > 1) {                                  // sum over the ranks through the peers' mailboxes (posted; completed
-    __syncthreads();                                      // here when synchronous), plus the older deferred collectives
-    peer_collective(peer, s_fin, (int)nslice, 0, total, &s_last);
+  if (peer.nranks > 1) {                                  // sum over the ranks: synchronous (post + complete here) or
+    __syncthreads();                                      // deferred (kept locally, posted by the next kernel's first CTA)
+    peer_own(peer, s_fin, (int)nslice, 0, total, &s_last);
   }
   if (tid == 0) signal_done(done);                        // single rank: thread 0 wrote total[] itself
   cta_trace_end(trace, t_begin);
@@ -410,6 +414,7 @@ static int launch_flux_rows(const WfView& v, const long long* off, long long nsl
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
   double* part_arg = plaq ? (total ? partial : nullptr) : partial;
   unsigned long long* trace = cta_trace_buffer();
+  if (trace) trace += (size_t)4 * kCtaTraceCap;          // the flux kernel's half of the trace buffer
   // a synchronous prepared call waits on a pinned word the last CTA writes after the totals
   const DoneSignal done = (total && (pview.nranks <= 1 || pview.mode == 1)) ? take_done_request() : DoneSignal{nullptr, 0};
   if (plaq)

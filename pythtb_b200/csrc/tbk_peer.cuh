@@ -93,36 +93,46 @@ __device__ __forceinline__ void peer_post(const PeerView& pv, unsigned long long
   }
 }
 
-// COMPLETE: wait for every rank's words of `epoch`, combine in rank order, write out[nv].  All threads of one CTA;
-// s_half: [kPeerMaxRanks * kPeerSlotWords] shared words; *s_fail (shared) is set when a peer never arrived.
-__device__ inline void peer_complete(const PeerView& pv, unsigned long long epoch, int nv, int op, double* out,
-                                     unsigned* s_half, int* s_fail) {
-  const unsigned tag = peer_tag(epoch);
-  const int nw = 2 * nv, tid = threadIdx.x;
-  const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(pv.box[pv.rank]) +
-                                   (size_t)((int)(epoch % kPeerDepth) * pv.nranks) * kPeerSlotWords;
-  for (int t = tid; t < pv.nranks * nw; t += blockDim.x) {
-    const int r = t / nw, w = t - r * nw;
-    const unsigned long long* src = mine + (size_t)r * kPeerSlotWords + w;
+// COMPLETE a list of collectives at once: wait for every rank's words of every entry (ONE round of polling loads for
+// all of them: the entries are usually long there, and what is paid is a load latency, not a wait), combine in
+// rank order, write out[].  All threads of one CTA.  *s_fail (shared) is set when a peer never arrived (~4 s).
+__device__ inline void peer_complete_list(const PeerView& pv, const PeerPending* list, int count, int* s_fail) {
+  __shared__ unsigned s_half[kPeerMaxPend + 1][kPeerMaxRanks * kPeerSlotWords];
+  const int tid = threadIdx.x;
+  int total = 0;
+  for (int i = 0; i < count; ++i) total += pv.nranks * 2 * list[i].nv;
+  for (int t = tid; t < total; t += blockDim.x) {     // one word per thread: a single round of loads in the usual case
+    int i = 0, q = t;
+    while (q >= pv.nranks * 2 * list[i].nv) { q -= pv.nranks * 2 * list[i].nv; ++i; }
+    const int nw = 2 * list[i].nv;
+    const int r = q / nw, w = q - r * nw;
+    q = r * kPeerSlotWords + w;
+    const unsigned long long epoch = list[i].epoch;
+    const unsigned tag = peer_tag(epoch);
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(pv.box[pv.rank]) +
+                                    (size_t)((int)(epoch % kPeerDepth) * pv.nranks + r) * kPeerSlotWords + w;
     const long long t0 = clock64();
     unsigned long long x = ld_relaxed_sys_u64(src);
     while ((unsigned)(x >> 32) != tag) {
       if (clock64() - t0 > 8000000000LL) { *s_fail = 1; break; }     // ~4 s at 2 GHz: a peer never arrived
       x = ld_relaxed_sys_u64(src);
     }
-    s_half[r * kPeerSlotWords + w] = (unsigned)x;
+    s_half[i][q] = (unsigned)x;
   }
   __syncthreads();
-  if (tid < nv) {
+  for (int t = tid; t < count * kPeerMaxVals; t += blockDim.x) {
+    const int i = t / kPeerMaxVals, k = t - i * kPeerMaxVals;
+    if (k >= list[i].nv) continue;
+    const int op = list[i].op;
     double acc = op == 0 ? 0.0 : INFINITY;
     for (int r = 0; r < pv.nranks; ++r) {
-      const unsigned long long bits = ((unsigned long long)s_half[r * kPeerSlotWords + 2 * tid + 1] << 32) |
-                                      (unsigned long long)s_half[r * kPeerSlotWords + 2 * tid];
+      const unsigned long long bits = ((unsigned long long)s_half[i][r * kPeerSlotWords + 2 * k + 1] << 32) |
+                                      (unsigned long long)s_half[i][r * kPeerSlotWords + 2 * k];
       const double x = __longlong_as_double((long long)bits);
       acc = op == 0 ? acc + x : fmin(acc, x);
     }
     if (*s_fail) acc = NAN;
-    out[tid] = acc;
+    list[i].out[k] = acc;
   }
   __syncthreads();                                   // s_half is free again; out[] is written
 }
@@ -136,26 +146,47 @@ __device__ __forceinline__ void peer_prologue(const PeerView& pv) {
   }
 }
 
-// The collective as the LAST CTA of a kernel sees it, called by all its threads: vals[nv] are this rank's values.
-//   mode 1 (synchronous): post them, complete the deferred collectives attached to the view, complete the own one:
-//          out[nv] = sum (op 0, rank order) / min (op 1) over the ranks.  The post goes first: the peers' waits
-//          then overlap this rank's completions.
-//   mode 2 (deferred): keep them in the local slot (a later kernel posts them), complete the attached ones.
-//   epoch 0: only complete the attached ones (flush kernel).
-__device__ inline void peer_collective(const PeerView& pv, const double* vals, int nv, int op, double* out, int* s_fail) {
+// The older deferred collectives attached to the view, completed by all threads of ONE CTA.  The flux kernel hands
+// this to the FIRST CTA that finishes its work (ticket 0): the polls then run while the rest of the wave is still
+// finishing, instead of after the last CTA's own reduction (measured: 2.3 us at the end of every step, N = 2).
+__device__ inline void peer_complete_pending(const PeerView& pv, int* s_fail) {
+  if (pv.nranks > 1 && pv.npend > 0) {
+    if (threadIdx.x == 0) *s_fail = 0;
+    __syncthreads();
+    peer_complete_list(pv, pv.pend, pv.npend, s_fail);
+  }
+}
+
+// The kernel's OWN collective as its LAST CTA sees it, called by all its threads: vals[nv] are this rank's values.
+//   mode 1 (synchronous): post them and complete: out[nv] = sum (op 0, rank order) / min (op 1) over the ranks.
+//   mode 2 (deferred): keep them in the local slot (a later kernel's first CTA posts them).
+__device__ inline void peer_own(const PeerView& pv, const double* vals, int nv, int op, double* out, int* s_fail) {
   __shared__ double s_vals[kPeerMaxVals];
-  __shared__ unsigned s_half[kPeerMaxRanks * kPeerSlotWords];
   const int tid = threadIdx.x;
+  if (pv.epoch == 0) return;
   if (tid == 0) *s_fail = 0;
-  if (pv.epoch != 0 && tid < nv) {
+  if (tid < nv) {
     const double x = vals[tid];
     if (pv.mode == 2) pv.local[tid] = x;
     else s_vals[tid] = x;
   }
   __syncthreads();
-  if (pv.epoch != 0 && pv.mode == 1) peer_post(pv, pv.epoch, s_vals, nv);
-  for (int i = 0; i < pv.npend; ++i) peer_complete(pv, pv.pend[i].epoch, pv.pend[i].nv, pv.pend[i].op, pv.pend[i].out, s_half, s_fail);
-  if (pv.epoch != 0 && pv.mode == 1) peer_complete(pv, pv.epoch, nv, op, out, s_half, s_fail);
+  if (pv.mode == 1) {
+    peer_post(pv, pv.epoch, s_vals, nv);
+    PeerPending self;
+    self.epoch = pv.epoch; self.nv = nv; self.op = op; self.out = out; self.local = nullptr; self.posted = 1;
+    __shared__ PeerPending s_self;
+    if (tid == 0) s_self = self;
+    __syncthreads();
+    peer_complete_list(pv, &s_self, 1, s_fail);
+  }
+}
+
+// Both in one CTA (kernels with a single finishing CTA: the grid solve's last CTA — which has no pending list —,
+// the flush and barrier kernels).
+__device__ inline void peer_collective(const PeerView& pv, const double* vals, int nv, int op, double* out, int* s_fail) {
+  peer_own(pv, vals, nv, op, out, s_fail);
+  peer_complete_pending(pv, s_fail);
 }
 #endif
 
