@@ -62,19 +62,26 @@ struct BlkWork {
   int nt;
 };
 
-TBK_HD size_t blk_shared_bytes(int n, int nb, int nred) {
-  return (size_t)2 * nb * n * 16 + (size_t)(1 + nred) * n * 16 + (size_t)2 * nb * 16 + (size_t)n * 16 + (size_t)5 * n * 8 +
-         (size_t)n * 4 + 64;
+// wcol + racc: (1 + nred) n complex numbers for the lower-triangle product, and never fewer than `nthreads` (the
+// full-matrix variant uses the same region as its per-thread split-product scratch; it needs no racc: nred = 0)
+TBK_HD size_t blk_scratch_elems(int n, int nred, int nthreads) {
+  const size_t a = (size_t)(1 + nred) * n;
+  return a > (size_t)nthreads ? a : (size_t)nthreads;
+}
+TBK_HD size_t blk_shared_bytes(int n, int nb, int nred, int nthreads) {
+  return (size_t)2 * nb * n * 16 + blk_scratch_elems(n, nred, nthreads) * 16 + (size_t)2 * nb * 16 + (size_t)n * 16 +
+         (size_t)5 * n * 8 + (size_t)n * 4 + 64;
 }
 
 // carve the shared part of a BlkWork (n, nb, nred set) out of one 16-byte aligned buffer
-TBK_HD void blk_carve_shared(BlkWork& w, void* base) {
+TBK_HD void blk_carve_shared(BlkWork& w, void* base, int nthreads) {
   char* p = (char*)base;
   const int n = w.n, nb = w.nb;
   w.V = (cplx*)p;    p += (size_t)nb * n * 16;
   w.W = (cplx*)p;    p += (size_t)nb * n * 16;
-  w.wcol = (cplx*)p; p += (size_t)n * 16;
-  w.racc = (cplx*)p; p += (size_t)w.nred * n * 16;
+  w.wcol = (cplx*)p;
+  w.racc = w.wcol + n;
+  p += blk_scratch_elems(n, w.nred, nthreads) * 16;
   w.dots = (cplx*)p; p += (size_t)2 * nb * 16;
   w.tau = (cplx*)p;  p += (size_t)n * 16;
   w.d = (double*)p;  p += (size_t)n * 8;

@@ -458,20 +458,6 @@ static BlkShape blk_shape(int n, int nph) {
   s.n = n; s.lda = n | 1; s.nph = nph;
   s.threads = n <= 256 ? 256 : 512;
   const int nwarps = s.threads / 32;
-  auto total = [&](int nb, int nred) {
-    size_t off = (blk_shared_bytes(n, nb, nred) + 15) & ~(size_t)15;
-    off += (size_t)(nph > 0 ? nph : 1) * 16 + (size_t)n * 16 + 128;
-    return off;
-  };
-  // panel width: 16 if two CTAs still fit an SM, else 8.  (Measured at n = 400: nb = 4 with two resident
-  // CTAs is 15 % slower than nb = 8 with one — the stage is bandwidth-, not latency-bound.)
-  // nred: how many warps' row partials of the symmetric matrix-vector product are summed per round through shared
-  // memory — all of them when they fit, fewer (more rounds) for the largest matrices.
-  if (total(16, nwarps) * 2 + 2048 <= (size_t)kMaxSmem) { s.nb = 16; s.nred = nwarps; }
-  else {
-    s.nb = 8; s.nred = nwarps;
-    while (s.nred > 1 && total(8, s.nred) + 1024 > (size_t)kMaxSmem) --s.nred;
-  }
   // tridiagonalisation variant: TBK_HETRD=sym reads / updates the lower triangle only (half the DRAM traffic),
   // TBK_HETRD=full (default: measured faster on B200, profiles/README.md r09) streams the full trailing matrix
   {
@@ -479,7 +465,22 @@ static BlkShape blk_shape(int n, int nph) {
     if (sym < 0) { const char* e = getenv("TBK_HETRD"); sym = (e && strcmp(e, "sym") == 0) ? 1 : 0; }
     s.sym = sym;
   }
-  size_t off = (blk_shared_bytes(n, s.nb, s.nred) + 15) & ~(size_t)15;
+  auto total = [&](int nb, int nred) {
+    size_t off = (blk_shared_bytes(n, nb, nred, s.threads) + 15) & ~(size_t)15;
+    off += (size_t)(nph > 0 ? nph : 1) * 16 + (size_t)n * 16 + 128;
+    return off;
+  };
+  // panel width: 16 if two CTAs still fit an SM, else 8.  (Measured at n = 400: nb = 4 with two resident
+  // CTAs is 15 % slower than nb = 8 with one — the stage is bandwidth-, not latency-bound.)
+  // nred (lower-triangle variant only): how many warps' row partials of the symmetric matrix-vector product are
+  // summed per round through shared memory — all of them when they fit, fewer (more rounds) for the largest matrices.
+  const int want_red = s.sym ? nwarps : 0;
+  if (total(16, want_red) * 2 + 2048 <= (size_t)kMaxSmem) { s.nb = 16; s.nred = want_red; }
+  else {
+    s.nb = 8; s.nred = want_red;
+    while (s.nred > 1 && total(8, s.nred) + 1024 > (size_t)kMaxSmem) --s.nred;
+  }
+  size_t off = (blk_shared_bytes(n, s.nb, s.nred, s.threads) + 15) & ~(size_t)15;
   s.off_ph = off;   off += (size_t)(nph > 0 ? nph : 1) * 16;
   s.off_gf = off;   off += (size_t)n * 16;
   s.off_misc = off; off += 128;
@@ -529,7 +530,7 @@ solve_blocked_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long l
   const int n = shp.n, lda = shp.lda, tid = threadIdx.x, T = blockDim.x;
   BlkWork w;
   w.n = n; w.lda = lda; w.nb = shp.nb; w.nt = shp.nt; w.nred = shp.nred;
-  blk_carve_shared(w, smem);
+  blk_carve_shared(w, smem, shp.threads);
   cplx* ph = (cplx*)(smem + shp.off_ph);
   cplx* gf = (cplx*)(smem + shp.off_gf);
   double* kbuf = (double*)(smem + shp.off_misc);

@@ -91,8 +91,8 @@ int emu_heev_blocked_team(int n, double* A, int lda, int nb, int want_vec, doubl
   BlkWork w;
   w.n = n; w.lda = lda; w.nb = nb; w.A = (cplx*)A;
   w.nred = T / S > 3 ? 3 : T / S;                // fewer slots than sub-teams: several reduction rounds
-  std::vector<char> sh(blk_shared_bytes(n, nb, w.nred) + 64);
-  blk_carve_shared(w, sh.data());
+  std::vector<char> sh(blk_shared_bytes(n, nb, w.nred, T) + 64);
+  blk_carve_shared(w, sh.data(), T);
   int nt = ((n + S - 1) / S) * S;
   if (nt > T) nt = T;
   std::vector<double> Z((size_t)n * n), lu((size_t)4 * n * nt);
@@ -227,8 +227,8 @@ int emu_heev_blocked(int n, double* A, int lda, int nb, int want_vec, double* ev
   BlkWork w;
   w.n = n; w.lda = lda; w.nb = nb; w.A = (cplx*)A;
   w.nred = 1;
-  std::vector<char> sh(blk_shared_bytes(n, nb, 1) + 64);
-  blk_carve_shared(w, sh.data());
+  std::vector<char> sh(blk_shared_bytes(n, nb, 1, 1) + 64);
+  blk_carve_shared(w, sh.data(), 1);
   std::vector<double> Z((size_t)n * n), lu((size_t)4 * n);
   w.Z = Z.data(); w.lu = lu.data(); w.nt = 1;
   if (g_hetrd_sym) hetrd_blocked<kBlkMaxN>(g, w);
