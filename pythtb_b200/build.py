@@ -33,15 +33,23 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=None, out=None):
+    """extra_flags / out: an A/B variant of the library (profiles/build_variant.py) — object files go to a scratch
+    directory and the default in-tree library is left alone."""
+    if extra_flags is None and out is None and not force and not needs_build():
         return SO
+    objdir = CSRC
+    so = SO
+    if out is not None:
+        import tempfile
+        objdir = tempfile.mkdtemp(prefix="tbk_variant_")
+        so = out
     # the three translation units are independent: compile them side by side
     from concurrent.futures import ThreadPoolExecutor
 
     def compile_one(src):
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags or []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         return src, obj, res
 
@@ -55,16 +63,16 @@ def build(force=False, verbose=False):
             sys.stderr.write(res.stdout)
             raise RuntimeError("nvcc failed on " + src)
         objs.append(obj)
-    cmd = [_nvcc(), "-shared", "-o", SO] + objs + ["-lcudart"]
+    cmd = [_nvcc(), "-shared", "-o", so] + objs + ["-lcudart"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout)
         raise RuntimeError("link failed")
-    with open(os.path.join(CSRC, "ptxas_info.log"), "w") as f:
+    with open(os.path.join(objdir, "ptxas_info.log"), "w") as f:
         f.write("\n".join(logs))
     if verbose:
         print("\n".join(logs))
-    return SO
+    return so
 
 
 if __name__ == "__main__":

@@ -776,8 +776,69 @@ struct GemmSide {
 // C[m][q] = sum_x a(m, x) * b(q, x) * (wgt ? wgt[x] : 1),  m < ma, q < nb_, x < kdim;  C row-major [ma][ldc].
 // Called by all 256 threads of a CTA.  The loader picks the thread -> element mapping that makes the global
 // reads contiguous for the operand's unit stride (rows or contraction index).
-__device__ void cta_gemm_dmma(const GemmSide& A, int ma, const GemmSide& B, int nb_, int kdim, const double* __restrict__ wgt,
-                              cplx* __restrict__ C, int ldc, OvSmem& sm) {
+// Software pipeline: the global loads of K-chunk i + 1 are issued into registers BEFORE the DMMAs of chunk i and
+// written to shared memory after them, so a chunk's ~1 us of L2 / HBM latency hides under the previous chunk's
+// tensor-pipe work (the single-stage version waited for every chunk: DMMA pipe 18-65 % busy, profiles/README.md r06).
+// Not inlined: the callers (link overlap + LU, Newton-Schulz, tree products, position matrices) would otherwise each
+// carry the 64 accumulator registers through their own code (254 registers, one CTA per SM).
+// A/B knobs (profiles/build_variant.py): resident CTAs per SM the DMMA kernels are compiled for, and the software
+// pipeline of the GEMM (0 = the single-stage loop of round 1: load, barrier, DMMAs, barrier)
+#ifndef TBK_GEMM_MINB
+#define TBK_GEMM_MINB 2
+#endif
+#ifndef TBK_GEMM_PIPELINE
+#define TBK_GEMM_PIPELINE 1
+#endif
+struct GemmStage {
+  cplx a[4], b[4];
+};
+
+__device__ __forceinline__ void gemm_stage_load(GemmStage& st, const GemmSide& A, int ma, int m0, const GemmSide& B, int nb_, int q0,
+                                                int kdim, int x0, const double* __restrict__ wgt) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = tid + 256 * i;
+    {
+      const int row = A.xs == 1 ? idx >> 4 : idx & 63, xc = A.xs == 1 ? idx & 15 : idx >> 6;
+      cplx a = mk(0.0, 0.0);
+      if (x0 + xc < kdim && m0 + row < ma) {
+        const long long r = A.rowmap ? A.rowmap[m0 + row] : m0 + row;
+        a = A.p[r * A.rs + (long long)(x0 + xc) * A.xs];
+      }
+      st.a[i] = a;
+    }
+    {
+      const int row = B.xs == 1 ? idx >> 4 : idx & 63, xc = B.xs == 1 ? idx & 15 : idx >> 6;
+      cplx b = mk(0.0, 0.0);
+      if (x0 + xc < kdim && q0 + row < nb_) {
+        const long long r = B.rowmap ? B.rowmap[q0 + row] : q0 + row;
+        b = B.p[r * B.rs + (long long)(x0 + xc) * B.xs];
+        if (wgt) { const double f = wgt[x0 + xc]; b.re *= f; b.im *= f; }
+      }
+      st.b[i] = b;
+    }
+  }
+}
+
+__device__ __forceinline__ void gemm_stage_store(const GemmStage& st, const GemmSide& A, const GemmSide& B, double sa, double sb, OvSmem& sm) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = tid + 256 * i;
+    {
+      const int row = A.xs == 1 ? idx >> 4 : idx & 63, xc = A.xs == 1 ? idx & 15 : idx >> 6;
+      sm.are[row][xc] = st.a[i].re; sm.aim[row][xc] = sa * st.a[i].im;
+    }
+    {
+      const int row = B.xs == 1 ? idx >> 4 : idx & 63, xc = B.xs == 1 ? idx & 15 : idx >> 6;
+      sm.bre[row][xc] = st.b[i].re; sm.bim[row][xc] = sb * st.b[i].im;
+    }
+  }
+}
+
+__device__ __noinline__ void cta_gemm_dmma(const GemmSide& A, int ma, const GemmSide& B, int nb_, int kdim, const double* __restrict__ wgt,
+                                           cplx* __restrict__ C, int ldc, OvSmem& sm) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int wr = warp >> 1, wc = warp & 1;
@@ -794,32 +855,20 @@ __device__ void cta_gemm_dmma(const GemmSide& A, int ma, const GemmSide& B, int 
       for (int rt = 0; rt < 2; ++rt) rv[rt] = m0 + wr * 16 + rt * 8 < ma;
 #pragma unroll
       for (int ct = 0; ct < 4; ++ct) cv[ct] = q0 + wc * 32 + ct * 8 < nb_;
+      GemmStage st;
+#if TBK_GEMM_PIPELINE
+      gemm_stage_load(st, A, ma, m0, B, nb_, q0, kdim, 0, wgt);
+#endif
       for (int x0 = 0; x0 < kdim; x0 += kOvKC) {
+#if !TBK_GEMM_PIPELINE
+        gemm_stage_load(st, A, ma, m0, B, nb_, q0, kdim, x0, wgt);
+#endif
         __syncthreads();                         // the previous chunk has been consumed
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int idx = tid + 256 * i;
-          {
-            const int row = A.xs == 1 ? idx >> 4 : idx & 63, xc = A.xs == 1 ? idx & 15 : idx >> 6;
-            cplx a = mk(0.0, 0.0);
-            if (x0 + xc < kdim && m0 + row < ma) {
-              const long long r = A.rowmap ? A.rowmap[m0 + row] : m0 + row;
-              a = A.p[r * A.rs + (long long)(x0 + xc) * A.xs];
-            }
-            sm.are[row][xc] = a.re; sm.aim[row][xc] = sa * a.im;
-          }
-          {
-            const int row = B.xs == 1 ? idx >> 4 : idx & 63, xc = B.xs == 1 ? idx & 15 : idx >> 6;
-            cplx b = mk(0.0, 0.0);
-            if (x0 + xc < kdim && q0 + row < nb_) {
-              const long long r = B.rowmap ? B.rowmap[q0 + row] : q0 + row;
-              b = B.p[r * B.rs + (long long)(x0 + xc) * B.xs];
-              if (wgt) { const double f = wgt[x0 + xc]; b.re *= f; b.im *= f; }
-            }
-            sm.bre[row][xc] = b.re; sm.bim[row][xc] = sb * b.im;
-          }
-        }
+        gemm_stage_store(st, A, B, sa, sb, sm);
         __syncthreads();
+#if TBK_GEMM_PIPELINE
+        if (x0 + kOvKC < kdim) gemm_stage_load(st, A, ma, m0, B, nb_, q0, kdim, x0 + kOvKC, wgt);   // in flight under the DMMAs below
+#endif
 #pragma unroll
         for (int ks = 0; ks < kOvKC / 4; ++ks) {
           double ar[2], ai[2], an[2];
@@ -951,7 +1000,7 @@ __device__ __forceinline__ double block_max(double x, double* red) {
 }
 
 // mode 0: out[l] = det/|det| of the overlap.   mode 1: out[l*nocc*nocc ...] = unitary polar factor.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, TBK_GEMM_MINB)
 link_matrix_kernel(WfView v, LinkMap map, long long nlinks, int mode, cplx* __restrict__ out, cplx* __restrict__ gws) {
   extern __shared__ __align__(16) char dyn_smem[];
   __shared__ double red[32];
@@ -1173,7 +1222,7 @@ string_wilson_kernel(const cplx* __restrict__ umats, long long nstr, long long n
 // (a) ordered product of the link matrices of every string as a binary tree: one launch per level,
 //     U[i] <- U[i] U[i + stride] for i = 0, 2 stride, 4 stride, ... (one CTA per product, DMMA GEMM);
 //     after ceil(log2 nlink) levels U[0] holds prod_t U[t]  (pythtb.py:3826, same left-to-right order).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, TBK_GEMM_MINB)
 string_product_kernel(cplx* __restrict__ umats, long long nstr, long long nlink, long long stride, int nocc,
                       cplx* __restrict__ tmp) {
   __shared__ OvSmem sm;
@@ -1309,7 +1358,7 @@ position_matrix_kernel(const cplx* __restrict__ evec, long long batch, int nocc,
 }
 
 // DMMA versions for nocc >= 16: one CTA per k-point
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, TBK_GEMM_MINB)
 position_matrix_dmma_kernel(const cplx* __restrict__ evec, long long batch, int nocc, int n, const double* __restrict__ pos,
                             cplx* __restrict__ xmat) {
   __shared__ OvSmem sm;
@@ -1320,7 +1369,7 @@ position_matrix_dmma_kernel(const cplx* __restrict__ evec, long long batch, int 
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, TBK_GEMM_MINB)
 hwf_to_orbital_dmma_kernel(const cplx* __restrict__ hwf, const cplx* __restrict__ evec, long long batch, int nocc, int n,
                            cplx* __restrict__ out) {
   __shared__ OvSmem sm;
