@@ -793,47 +793,61 @@ struct GemmStage {
   cplx a[4], b[4];
 };
 
-__device__ __forceinline__ void gemm_stage_load(GemmStage& st, const GemmSide& A, int ma, int m0, const GemmSide& B, int nb_, int q0,
-                                                int kdim, int x0, const double* __restrict__ wgt) {
+// Loader mapping (element idx = tid + 256 i of a 64 x 16 chunk, i < 4): unit contraction stride -> row = idx / 16,
+// xc = idx % 16 (16 lanes read 256 contiguous bytes of a row, and the shared-memory stores are conflict-free);
+// unit row stride -> row = idx % 64, xc = idx / 64.  Everything that does not depend on the K chunk — the four rows, their
+// bounds test, the row map (occupied-state index) and the base pointers — is computed once per output tile (GemmTile),
+// not once per loaded element: in the first version that index arithmetic was ~45 % of the kernel's instructions and
+// the DMMAs 2 % (ncu source page, profiles/r11/lines_large.txt).
+struct GemmTile {
+  const cplx* pa[4];    // element i of A at chunk 0, nullptr if its row is outside the matrix
+  const cplx* pb[4];
+  int xa0, dxa, xb0, dxb;   // contraction index of element i inside the chunk: x0 + i * dx
+  int ra0, dra, rb0, drb;   // row of element i inside the tile
+};
+
+__device__ __forceinline__ GemmTile gemm_tile_setup(const GemmSide& A, int ma, int m0, const GemmSide& B, int nb_, int q0) {
   const int tid = threadIdx.x;
+  GemmTile t;
+  if (A.xs == 1) { t.ra0 = tid >> 4; t.dra = 16; t.xa0 = tid & 15; t.dxa = 0; }
+  else { t.ra0 = tid & 63; t.dra = 0; t.xa0 = tid >> 6; t.dxa = 4; }
+  if (B.xs == 1) { t.rb0 = tid >> 4; t.drb = 16; t.xb0 = tid & 15; t.dxb = 0; }
+  else { t.rb0 = tid & 63; t.drb = 0; t.xb0 = tid >> 6; t.dxb = 4; }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int idx = tid + 256 * i;
-    {
-      const int row = A.xs == 1 ? idx >> 4 : idx & 63, xc = A.xs == 1 ? idx & 15 : idx >> 6;
-      cplx a = mk(0.0, 0.0);
-      if (x0 + xc < kdim && m0 + row < ma) {
-        const long long r = A.rowmap ? A.rowmap[m0 + row] : m0 + row;
-        a = A.p[r * A.rs + (long long)(x0 + xc) * A.xs];
-      }
-      st.a[i] = a;
+    const int ra = m0 + t.ra0 + i * t.dra, rb = q0 + t.rb0 + i * t.drb;
+    t.pa[i] = t.pb[i] = nullptr;
+    if (ra < ma) {
+      const long long r = A.rowmap ? A.rowmap[ra] : ra;
+      t.pa[i] = A.p + r * A.rs + (long long)(t.xa0 + i * t.dxa) * A.xs;
     }
-    {
-      const int row = B.xs == 1 ? idx >> 4 : idx & 63, xc = B.xs == 1 ? idx & 15 : idx >> 6;
-      cplx b = mk(0.0, 0.0);
-      if (x0 + xc < kdim && q0 + row < nb_) {
-        const long long r = B.rowmap ? B.rowmap[q0 + row] : q0 + row;
-        b = B.p[r * B.rs + (long long)(x0 + xc) * B.xs];
-        if (wgt) { const double f = wgt[x0 + xc]; b.re *= f; b.im *= f; }
-      }
-      st.b[i] = b;
+    if (rb < nb_) {
+      const long long r = B.rowmap ? B.rowmap[rb] : rb;
+      t.pb[i] = B.p + r * B.rs + (long long)(t.xb0 + i * t.dxb) * B.xs;
     }
+  }
+  return t;
+}
+
+__device__ __forceinline__ void gemm_stage_load(GemmStage& st, const GemmTile& t, long long xsa, long long xsb, int kdim, int x0,
+                                                const double* __restrict__ wgt) {
+  const cplx zero = mk(0.0, 0.0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int xa = x0 + t.xa0 + i * t.dxa, xb = x0 + t.xb0 + i * t.dxb;
+    st.a[i] = (t.pa[i] && xa < kdim) ? t.pa[i][(long long)x0 * xsa] : zero;
+    cplx b = (t.pb[i] && xb < kdim) ? t.pb[i][(long long)x0 * xsb] : zero;
+    if (wgt && xb < kdim) { const double f = wgt[xb]; b.re *= f; b.im *= f; }
+    st.b[i] = b;
   }
 }
 
-__device__ __forceinline__ void gemm_stage_store(const GemmStage& st, const GemmSide& A, const GemmSide& B, double sa, double sb, OvSmem& sm) {
-  const int tid = threadIdx.x;
+__device__ __forceinline__ void gemm_stage_store(const GemmStage& st, const GemmTile& t, double sa, double sb, OvSmem& sm) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int idx = tid + 256 * i;
-    {
-      const int row = A.xs == 1 ? idx >> 4 : idx & 63, xc = A.xs == 1 ? idx & 15 : idx >> 6;
-      sm.are[row][xc] = st.a[i].re; sm.aim[row][xc] = sa * st.a[i].im;
-    }
-    {
-      const int row = B.xs == 1 ? idx >> 4 : idx & 63, xc = B.xs == 1 ? idx & 15 : idx >> 6;
-      sm.bre[row][xc] = st.b[i].re; sm.bim[row][xc] = sb * st.b[i].im;
-    }
+    const int ra = t.ra0 + i * t.dra, xa = t.xa0 + i * t.dxa, rb = t.rb0 + i * t.drb, xb = t.xb0 + i * t.dxb;
+    sm.are[ra][xa] = st.a[i].re; sm.aim[ra][xa] = sa * st.a[i].im;
+    sm.bre[rb][xb] = st.b[i].re; sm.bim[rb][xb] = sb * st.b[i].im;
   }
 }
 
@@ -856,18 +870,19 @@ __device__ __noinline__ void cta_gemm_dmma(const GemmSide& A, int ma, const Gemm
 #pragma unroll
       for (int ct = 0; ct < 4; ++ct) cv[ct] = q0 + wc * 32 + ct * 8 < nb_;
       GemmStage st;
+      const GemmTile tile = gemm_tile_setup(A, ma, m0, B, nb_, q0);
 #if TBK_GEMM_PIPELINE
-      gemm_stage_load(st, A, ma, m0, B, nb_, q0, kdim, 0, wgt);
+      gemm_stage_load(st, tile, A.xs, B.xs, kdim, 0, wgt);
 #endif
       for (int x0 = 0; x0 < kdim; x0 += kOvKC) {
 #if !TBK_GEMM_PIPELINE
-        gemm_stage_load(st, A, ma, m0, B, nb_, q0, kdim, x0, wgt);
+        gemm_stage_load(st, tile, A.xs, B.xs, kdim, x0, wgt);
 #endif
         __syncthreads();                         // the previous chunk has been consumed
-        gemm_stage_store(st, A, B, sa, sb, sm);
+        gemm_stage_store(st, tile, sa, sb, sm);
         __syncthreads();
 #if TBK_GEMM_PIPELINE
-        if (x0 + kOvKC < kdim) gemm_stage_load(st, A, ma, m0, B, nb_, q0, kdim, x0 + kOvKC, wgt);   // in flight under the DMMAs below
+        if (x0 + kOvKC < kdim) gemm_stage_load(st, tile, A.xs, B.xs, kdim, x0 + kOvKC, wgt);   // in flight under the DMMAs below
 #endif
 #pragma unroll
         for (int ks = 0; ks < kOvKC / 4; ++ks) {
@@ -958,11 +973,35 @@ __device__ cplx lu_det_phase_cta(cplx* __restrict__ M, int n, int ld, double* sr
     u = u * mk(p.re / ap, p.im / ap);
     for (int r = k + 1 + tid; r < n; r += T) fbuf[r] = cdiv(M[(size_t)r * ld + k], p);
     __syncthreads();
+    // rank-1 update of the trailing block, one warp per pair of rows.  M lives in global memory (L2): written as a plain
+    // `row[c] -= f * rowk[c]` loop, a warp had ONE load in flight and paid an L2 round trip per 32 elements — at n = 200
+    // that was 7 of the 10 ms of a link determinant (profiles/README.md r11).  Here a lane keeps its four pivot-row
+    // elements of a 128-column chunk in registers and issues the eight loads of two rows before it uses any of them.
     const cplx* rowk = M + (size_t)k * ld;
-    for (int r = k + 1 + warp; r < n; r += nw) {
-      const cplx f = fbuf[r];
-      cplx* row = M + (size_t)r * ld;
-      for (int c = k + 1 + lane; c < n; c += 32) row[c] = row[c] - f * rowk[c];
+    for (int cb = k + 1; cb < n; cb += 128) {
+      cplx rk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int c = cb + lane + 32 * u; rk[u] = c < n ? rowk[c] : mk(0.0, 0.0); }
+      for (int r = k + 1 + 2 * warp; r < n; r += 2 * nw) {
+        const bool two = r + 1 < n;
+        cplx* row0 = M + (size_t)r * ld;
+        cplx* row1 = M + (size_t)(two ? r + 1 : r) * ld;
+        const cplx f0 = fbuf[r], f1 = fbuf[two ? r + 1 : r];
+        cplx v0[4], v1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = cb + lane + 32 * u;
+          if (c < n) { v0[u] = row0[c]; v1[u] = row1[c]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = cb + lane + 32 * u;
+          if (c < n) {
+            row0[c] = v0[u] - f0 * rk[u];
+            if (two) row1[c] = v1[u] - f1 * rk[u];
+          }
+        }
+      }
     }
     __syncthreads();
   }
