@@ -532,7 +532,7 @@ TBK_HD int sturm_count(int n, const double* d, const double* e2, double x, doubl
   if (fabs(q) < pivmin) q = -pivmin;
   cnt += q < 0.0;
   for (int i = 1; i < n; ++i) {
-    q = d[i] - x - e2[i - 1] / q;
+    q = d[i] - x - e2[i - 1] * rcp_fast(q);        // |q| >= pivmin (a normal number): no IEEE-division slow path in the n-step chain
     if (fabs(q) < pivmin) q = -pivmin;
     cnt += q < 0.0;
   }

@@ -213,10 +213,10 @@ TBK_HD bool eigh_small_ql(cplx a[N][N], double ev[N], cplx w[N][N]) {
       double rs;
       const double nrm = sqrt_fast(alpha.re * alpha.re + alpha.im * alpha.im + xnorm2 + 1.0e-290, &rs);
       beta = alpha.re >= 0.0 ? -nrm : nrm;
-      const double ib = 1.0 / beta;
+      const double ib = rcp_fast(beta);                          // |beta| >= 1e-145
       t = mk((beta - alpha.re) * ib, -alpha.im * ib);
       const double dr = alpha.re - beta, di = alpha.im;          // 1 / (alpha - beta)
-      const double idn = 1.0 / (dr * dr + di * di);
+      const double idn = rcp_fast(dr * dr + di * di);           // |alpha - beta|^2 >= beta^2 >= 1e-290
       const cplx scal = mk(dr * idn, -di * idn);
       TBK_UNROLL
       for (int r = j + 2; r < N; ++r) a[r][j] = a[r][j] * scal;
@@ -276,10 +276,13 @@ TBK_HD bool eigh_small_ql(cplx a[N][N], double ev[N], cplx w[N][N]) {
       TBK_UNROLL
       for (int mm = l + 1; mm < N - 1; ++mm)
         if (mm == m) dm = d[mm];
-      double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+      // e[l] != 0 here (m != l).  The shift only steers the convergence: a reciprocal good to an ulp is plenty.
+      // Tiny |e[l]| (the quotient overflows) just gives the shift d[l] - as the IEEE division would.
+      const double el = fabs(e[l]) < 1.0e-290 ? (e[l] < 0.0 ? -1.0e-290 : 1.0e-290) : e[l];   // keep the reciprocal finite
+      double g = (d[l + 1] - d[l]) * (0.5 * rcp_fast(el));
       double rs;
       double r = sqrt_fast(g * g + 1.0, &rs);
-      g = dm - d[l] + e[l] / (g + (g >= 0.0 ? r : -r));
+      g = dm - d[l] + e[l] * rcp_fast(g + (g >= 0.0 ? r : -r));
       double sn = 1.0, cs = 1.0, p = 0.0;
       bool dead = false;
       TBK_UNROLL
