@@ -40,8 +40,12 @@ namespace tbk {
 constexpr int kBlkMaxN = 512;
 constexpr int kWarpCluster = 6;       // clusters up to this size are orthogonalised by one sub-team, larger ones by the group
 
+// leading dimension of the shared-memory panels V, W: the smallest value >= n that is 2 mod 8, so that the 16-byte
+// fragment reads of the tensor-pipe rank-2nb update (lane -> row g of panel column q) hit eight distinct bank groups
+TBK_HD int blk_ldp(int n) { return ((n + 5) / 8) * 8 + 2; }
+
 struct BlkWork {
-  int n, lda, nb;
+  int n, lda, nb, ldp;
   cplx* A;         // [n x lda] column-major, lower triangle valid on entry (global)
   cplx* V;         // [nb][n] reflector panel            (shared memory on the device)
   cplx* W;         // [nb][n] zlatrd's W panel           (shared)
@@ -60,7 +64,20 @@ struct BlkWork {
   double* Z;       // [n][n] row-major: Z[i*n + j] = component i of tridiagonal eigenvector j (global)
   double* lu;      // [4][n][nt] interleaved per-thread LU rows, nt = min(group size, n rounded up) (global)
   int nt;
+  unsigned long long* prof;   // -DTBK_HETRD_PROF builds only: cycle counters of the tridiagonalisation's phases
 };
+
+// phase counters of the tridiagonalisation (profiles/build_variant.py hetrd_prof -DTBK_HETRD_PROF=1): slot 0 = the
+// matrix-vector products, 3 = the rank-2nb updates, 7 = everything else (column update, reflector, corrections)
+#if defined(TBK_HETRD_PROF) && defined(__CUDA_ARCH__)
+#define TBK_HP_BEGIN long long hp_t0 = (w.prof && g.tid() == 0) ? clock64() : 0; long long hp_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define TBK_HP(slot) if (w.prof && g.tid() == 0) { const long long hp_t1 = clock64(); hp_acc[slot] += hp_t1 - hp_t0; hp_t0 = hp_t1; }
+#define TBK_HP_END if (w.prof && g.tid() == 0) { atomicAdd(w.prof + 0, (unsigned long long)hp_acc[0]); atomicAdd(w.prof + 3, (unsigned long long)hp_acc[3]); atomicAdd(w.prof + 7, (unsigned long long)hp_acc[7]); }
+#else
+#define TBK_HP_BEGIN
+#define TBK_HP(slot)
+#define TBK_HP_END
+#endif
 
 // wcol + racc: (1 + nred) n complex numbers for the lower-triangle product, and never fewer than `nthreads` (the
 // full-matrix variant uses the same region as its per-thread split-product scratch; it needs no racc: nred = 0)
@@ -69,7 +86,7 @@ TBK_HD size_t blk_scratch_elems(int n, int nred, int nthreads) {
   return a > (size_t)nthreads ? a : (size_t)nthreads;
 }
 TBK_HD size_t blk_shared_bytes(int n, int nb, int nred, int nthreads) {
-  return (size_t)2 * nb * n * 16 + blk_scratch_elems(n, nred, nthreads) * 16 + (size_t)2 * nb * 16 + (size_t)n * 16 +
+  return (size_t)2 * nb * blk_ldp(n) * 16 + blk_scratch_elems(n, nred, nthreads) * 16 + (size_t)2 * nb * 16 + (size_t)n * 16 +
          (size_t)5 * n * 8 + (size_t)n * 4 + 64;
 }
 
@@ -77,8 +94,9 @@ TBK_HD size_t blk_shared_bytes(int n, int nb, int nred, int nthreads) {
 TBK_HD void blk_carve_shared(BlkWork& w, void* base, int nthreads) {
   char* p = (char*)base;
   const int n = w.n, nb = w.nb;
-  w.V = (cplx*)p;    p += (size_t)nb * n * 16;
-  w.W = (cplx*)p;    p += (size_t)nb * n * 16;
+  w.ldp = blk_ldp(n);
+  w.V = (cplx*)p;    p += (size_t)nb * w.ldp * 16;
+  w.W = (cplx*)p;    p += (size_t)nb * w.ldp * 16;
   w.wcol = (cplx*)p;
   w.racc = w.wcol + n;
   p += blk_scratch_elems(n, w.nred, nthreads) * 16;
@@ -93,6 +111,93 @@ TBK_HD void blk_carve_shared(BlkWork& w, void* base, int nthreads) {
   w.ctl = (int*)p;
 }
 
+#if defined(__CUDACC__)
+__device__ __forceinline__ void blk_dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// Rank-2nb update of the full trailing matrix on the FP64 tensor pipe (all threads of the CTA):
+//   A[r][c] -= sum_kk P[r][kk] conj(Q[c][kk]),  P = [V | W], Q = [W | V]  (K = 2 nb),  j1 <= r, c < n.
+// A warp owns 16 x 16 tiles (2 x 2 fragments of mma.sync.m8n8k4.f64, fragment layouts in tbk_eig_wy.cuh); the old
+// values of a tile are requested from L2 / HBM first and the DMMAs run while they are on their way.  Operands come
+// straight from the shared-memory panels ([k][ldp], ldp == 2 mod 8: conflict-free 16-byte fragment reads); row / column
+// indices past n - 1 are clamped for the operand reads and masked for the tile itself.  The scalar version of this
+// update (one element per thread: 16-byte load -> 64 FMAs -> store) ran at ~9 % of the FP64 rate.
+template <bool LOWER>
+__device__ __forceinline__ void blk_rank2k_dmma(cplx* __restrict__ A, int lda, int n, int j1, const cplx* __restrict__ V,
+                                                const cplx* __restrict__ W, int ldp, int nb) {
+  const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const int m = n - j1;
+  const int nt = (m + 15) >> 4;
+  const int ksteps = nb >> 1;                         // 2 nb / 4
+  // LOWER: only the tiles on and below the diagonal, and of those only the elements r >= c (tile column tc has nt - tc tiles)
+  const int ntile = LOWER ? nt * (nt + 1) / 2 : nt * nt;
+  for (int t = warp; t < ntile; t += nwarp) {
+    int tc, tr;
+    if (LOWER) {
+      // t = tc nt - tc (tc - 1) / 2 + (tr - tc): invert by a float estimate and one correction either way
+      tc = (int)((2.0f * nt + 1.0f - sqrtf((2.0f * nt + 1.0f) * (2.0f * nt + 1.0f) - 8.0f * (float)t)) * 0.5f);
+      if (tc < 0) tc = 0;
+      while (tc > 0 && tc * nt - tc * (tc - 1) / 2 > t) --tc;
+      while ((tc + 1) * nt - (tc + 1) * tc / 2 <= t) ++tc;
+      tr = tc + (t - (tc * nt - tc * (tc - 1) / 2));
+    } else {
+      tc = t / nt; tr = t - tc * nt;
+    }
+    const int r0 = j1 + tr * 16, c0 = j1 + tc * 16;
+    cplx old[2][2][2];
+#pragma unroll
+    for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+      for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int r = r0 + rt * 8 + g, c = c0 + ct * 8 + 2 * q + e;
+          old[rt][ct][e] = (r < n && c < n && (!LOWER || r >= c)) ? A[r + (size_t)c * lda] : mk(0.0, 0.0);
+        }
+    double are[2][2][2], aim[2][2][2];
+#pragma unroll
+    for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+      for (int ct = 0; ct < 2; ++ct) { are[rt][ct][0] = are[rt][ct][1] = 0.0; aim[rt][ct][0] = aim[rt][ct][1] = 0.0; }
+    int rr[2], cc[2];
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+      rr[x] = r0 + x * 8 + g < n ? r0 + x * 8 + g : n - 1;
+      cc[x] = c0 + x * 8 + g < n ? c0 + x * 8 + g : n - 1;
+    }
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const int kk = ks * 4 + q;
+      const cplx* Pp = kk < nb ? V + kk * ldp : W + (kk - nb) * ldp;
+      const cplx* Qp = kk < nb ? W + kk * ldp : V + (kk - nb) * ldp;
+      const cplx p0 = Pp[rr[0]], p1 = Pp[rr[1]], q0 = Qp[cc[0]], q1 = Qp[cc[1]];
+#pragma unroll
+      for (int rt = 0; rt < 2; ++rt) {
+        const cplx pv = rt ? p1 : p0;
+#pragma unroll
+        for (int ct = 0; ct < 2; ++ct) {
+          const cplx qv = ct ? q1 : q0;             // p conj(q) = (pr qr + pi qi) + i (pi qr - pr qi)
+          blk_dmma(are[rt][ct][0], are[rt][ct][1], pv.re, qv.re);
+          blk_dmma(are[rt][ct][0], are[rt][ct][1], pv.im, qv.im);
+          blk_dmma(aim[rt][ct][0], aim[rt][ct][1], pv.im, qv.re);
+          blk_dmma(aim[rt][ct][0], aim[rt][ct][1], -pv.re, qv.im);
+        }
+      }
+    }
+#pragma unroll
+    for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+      for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int r = r0 + rt * 8 + g, c = c0 + ct * 8 + 2 * q + e;
+          if (r < n && c < n && (!LOWER || r >= c))
+            A[r + (size_t)c * lda] = mk(old[rt][ct][e].re - are[rt][ct][e], old[rt][ct][e].im - aim[rt][ct][e]);
+        }
+  }
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // 1. blocked tridiagonalisation.  On exit d, e hold T, the Householder vectors are stored below the
 // first sub-diagonal of A (zhetd2 'L' layout, implicit unit at row j+1) with their scalars in tau.
@@ -102,17 +207,18 @@ TBK_HD void blk_carve_shared(BlkWork& w, void* base, int nthreads) {
 // ---------------------------------------------------------------------------------------------
 template <int MAXM, class G>
 TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
-  const int n = w.n, lda = w.lda, nb = w.nb;
+  const int n = w.n, lda = w.lda, nb = w.nb, ldp = w.ldp;
   const int T = g.size(), tid = g.tid();
   cplx* A = w.A;
   cplx* V = w.V;
   cplx* W = w.W;
+  TBK_HP_BEGIN
   for (int c = tid; c < n; c += T) A[c + (size_t)c * lda].im = 0.0;       // real diagonal
   g.sync();
   for (int j0 = 0; j0 < n - 1; j0 += nb) {
     const int nbp = n - 1 - j0 < nb ? n - 1 - j0 : nb;
     // zero the panels (unused panel columns must be exactly zero for the rank-2nb update)
-    for (int q = tid; q < nb * n; q += T) { V[q] = mk(0.0, 0.0); W[q] = mk(0.0, 0.0); }
+    for (int q = tid; q < nb * ldp; q += T) { V[q] = mk(0.0, 0.0); W[q] = mk(0.0, 0.0); }
     g.sync();
     for (int i = 0; i < nbp; ++i) {
       const int j = j0 + i;
@@ -122,8 +228,8 @@ TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
         for (int r = j + tid; r < n; r += T) {
           cplx a = col[r];
           for (int k = 0; k < i; ++k) {
-            a = a - mulc(V[k * n + r], W[k * n + j]);
-            a = a - mulc(W[k * n + r], V[k * n + j]);
+            a = a - mulc(V[k * ldp + r], W[k * ldp + j]);
+            a = a - mulc(W[k * ldp + r], V[k * ldp + j]);
           }
           if (r == j) a.im = 0.0;
           col[r] = a;
@@ -144,7 +250,7 @@ TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
         scal = cdiv(mk(1.0, 0.0), mk(alpha.re - beta, alpha.im));
       }
       g.sync();                                   // everyone has read alpha
-      cplx* v = V + i * n;
+      cplx* v = V + i * ldp;
       for (int r = j + 2 + tid; r < n; r += T) {
         const cplx x = col[r] * scal;             // tau == 0: the column is already zero below j+1
         col[r] = x;
@@ -157,6 +263,7 @@ TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
         w.d[j] = col[j].re;
       }
       g.sync();
+      TBK_HP(7)
       // ---- (3) w = A22 v with the stored (panel-start) trailing matrix, rows/cols j+1 .. n-1, LOWER TRIANGLE ONLY.
       // A sub-team (warp) owns the columns c = j+1+sub, j+1+sub+nsub, ...; it streams column c from the diagonal
       // down (contiguous: 512-byte warp loads), lane L holding the rows r = L + S t.  An element a_rc gives
@@ -170,13 +277,74 @@ TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
 #pragma unroll
 #endif
         for (int t = 0; t < MAXM; ++t) acc[t] = mk(0.0, 0.0);
+#if defined(__CUDA_ARCH__)
+        // Device: FOUR adjacent columns per warp step.  Their loads (one coalesced 512-byte warp load per column and row
+        // slot) are independent and issued together — with one column at a time a warp had ~6 loads in flight and then
+        // waited for a 10-shuffle reduction before it touched the next column (the product ran at half the speed of the
+        // full-matrix one although it moves half the bytes) — and the eight column sums (re, im of four columns) are
+        // reduced over the lanes by ONE transposing butterfly: 4 + 2 + 1 + 1 + 1 = 9 shuffles instead of 40.
+        for (int c0 = j + 1 + 4 * sub; c0 < n; c0 += 4 * nsub) {
+          cplx vc[4];
+          const cplx* acol[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int c = c0 + q < n ? c0 + q : n - 1;
+            vc[q] = c0 + q < n ? v[c] : mk(0.0, 0.0);
+            acol[q] = A + (size_t)c * lda;
+          }
+          double s8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+          for (int t = 0; t < MAXM; ++t) {
+            if (32 * t + 31 >= c0) {                  // warp-uniform: this slot reaches the diagonal of the first column
+              const int r = L + 32 * t;
+              const int rc = r < n ? r : n - 1;
+              const cplx vr = v[rc];
+              cplx a[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) a[q] = acol[q][rc];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int c = c0 + q;
+                const bool on = r >= c && r < n && c < n;
+                cplx x = on ? a[q] : mk(0.0, 0.0);
+                if (r == c) x.im = 0.0;
+                fma_acc(acc[t], x, vc[q]);
+                const cplx tt = cmul(r > c ? x : mk(0.0, 0.0), vr);      // conj(a_rc) v_r, strictly below the diagonal
+                s8[2 * q] += tt.re; s8[2 * q + 1] += tt.im;
+              }
+            }
+          }
+          {
+            const bool b0 = L & 1, b1 = L & 2, b2 = L & 4;
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              const double send = b0 ? s8[x] : s8[x + 4], keep = b0 ? s8[x + 4] : s8[x];
+              s8[x] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            }
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+              const double send = b1 ? s8[x] : s8[x + 2], keep = b1 ? s8[x + 2] : s8[x];
+              s8[x] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            {
+              const double send = b2 ? s8[0] : s8[1], keep = b2 ? s8[1] : s8[0];
+              s8[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            s8[0] += __shfl_xor_sync(0xffffffffu, s8[0], 8);
+            s8[0] += __shfl_xor_sync(0xffffffffu, s8[0], 16);
+            // lane L (< 8) now holds entry (L & 1) * 4 + ((L >> 1) & 1) * 2 + ((L >> 2) & 1) of the eight sums
+            if (L < 8) {
+              const int idx = (L & 1) * 4 + ((L >> 1) & 1) * 2 + ((L >> 2) & 1);
+              const int c = c0 + (idx >> 1);
+              if (c < n) { double* dst = (double*)(w.wcol + c); dst[idx & 1] = s8[0]; }
+            }
+          }
+        }
+#else
         for (int c = j + 1 + sub; c < n; c += nsub) {
           const cplx vc = v[c];
           const cplx* acol = A + (size_t)c * lda;
           double sre = 0.0, sim = 0.0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
           for (int t = 0; t < MAXM; ++t) {
             if (S * t + S - 1 >= c) {                 // sub-team-uniform: this slot reaches the diagonal of column c
               const int r = L + S * t;
@@ -194,6 +362,7 @@ TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
           sre = g.subsum(sre); sim = g.subsum(sim);
           if (L == 0) w.wcol[c] = mk(sre, sim);
         }
+#endif
         g.sync();                                     // wcol complete
         for (int w0 = 0; w0 < nsub; w0 += w.nred) {
           if (sub >= w0 && sub < w0 + w.nred) {
@@ -209,17 +378,18 @@ TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
           g.sync();
           const int cnt = nsub - w0 < w.nred ? nsub - w0 : w.nred;
           for (int r = j + 1 + tid; r < n; r += T) {
-            cplx sacc = w0 == 0 ? w.wcol[r] : W[i * n + r];
+            cplx sacc = w0 == 0 ? w.wcol[r] : W[i * ldp + r];
             for (int q = 0; q < cnt; ++q) sacc = sacc + w.racc[(size_t)q * n + r];
-            W[i * n + r] = sacc;
+            W[i * ldp + r] = sacc;
           }
           g.sync();
         }
       }
+      TBK_HP(0)
       // ---- panel corrections: dots[k] = W_k^H v, dots[nb+k] = V_k^H v, one sub-team per dot product
       if (i > 0) {
         for (int q = g.sub(); q < 2 * i; q += g.nsub()) {
-          const cplx* src = q < i ? W + q * n : V + (q - i) * n;
+          const cplx* src = q < i ? W + q * ldp : V + (q - i) * ldp;
           double sre = 0.0, sim = 0.0;
           for (int r = j + 1 + g.lane(); r < n; r += g.subsize()) {
             const cplx t = cmul(src[r], v[r]);
@@ -230,33 +400,40 @@ TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
         }
         g.sync();
         for (int r = j + 1 + tid; r < n; r += T) {
-          cplx acc = W[i * n + r];
+          cplx acc = W[i * ldp + r];
           for (int k = 0; k < i; ++k) {
-            acc = acc - V[k * n + r] * w.dots[k];
-            acc = acc - W[k * n + r] * w.dots[nb + k];
+            acc = acc - V[k * ldp + r] * w.dots[k];
+            acc = acc - W[k * ldp + r] * w.dots[nb + k];
           }
-          W[i * n + r] = acc;
+          W[i * ldp + r] = acc;
         }
         g.sync();
       }
       // ---- w = tau w;  w += (-tau/2 (w^H v)) v
       double dre = 0.0, dim = 0.0;
       for (int r = j + 1 + tid; r < n; r += T) {
-        const cplx wr = tau * W[i * n + r];
-        W[i * n + r] = wr;
+        const cplx wr = tau * W[i * ldp + r];
+        W[i * ldp + r] = wr;
         const cplx t = cmul(wr, v[r]);
         dre += t.re; dim += t.im;
       }
       dre = g.sum(dre); dim = g.sum(dim);        // g.sum synchronises: the scaled w is visible
       const cplx a2 = (-0.5) * (tau * mk(dre, dim));
-      for (int r = j + 1 + tid; r < n; r += T) W[i * n + r] = W[i * n + r] + a2 * v[r];
+      for (int r = j + 1 + tid; r < n; r += T) W[i * ldp + r] = W[i * ldp + r] + a2 * v[r];
       g.sync();
     }
+    TBK_HP(7)
     // ---- rank-2nb update of the trailing matrix, lower triangle only: a_rc -= sum_k (V_kr conj(W_kc) + W_kr conj(V_kc)),
     // c <= r.  A thread takes the row pair (j1 + q, n - 1 - q): together they always have m + 1 columns, so every
     // thread of the group streams the same number of elements (rows alone would leave the last warp with twice the mean).
     const int j1 = j0 + nbp;
     const int m = n - j1;
+#if defined(__CUDA_ARCH__)
+    if (m > 0) {
+      blk_rank2k_dmma<true>(A, lda, n, j1, V, W, ldp, nb);
+      g.sync();
+    }
+#else
     if (m > 0) {
       const int half = (m + 1) / 2;
       int rw = ((half + 31) / 32) * 32;
@@ -276,8 +453,8 @@ TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
 #endif
               for (int k = 0; k < 8; ++k) {
                 const bool in = k0 + k < nb;
-                vr[k] = in ? V[(k0 + k) * n + r] : mk(0.0, 0.0);
-                wr[k] = in ? W[(k0 + k) * n + r] : mk(0.0, 0.0);
+                vr[k] = in ? V[(k0 + k) * ldp + r] : mk(0.0, 0.0);
+                wr[k] = in ? W[(k0 + k) * ldp + r] : mk(0.0, 0.0);
               }
               for (int c = j1 + pp; c <= r; c += parts) {
                 cplx a = A[r + (size_t)c * lda];
@@ -286,7 +463,7 @@ TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
 #endif
                 for (int k = 0; k < 8; ++k) {
                   if (k0 + k < nb) {
-                    const cplx wc = W[(k0 + k) * n + c], vc = V[(k0 + k) * n + c];
+                    const cplx wc = W[(k0 + k) * ldp + c], vc = V[(k0 + k) * ldp + c];
                     // a -= vr * conj(wc) + wr * conj(vc)
                     a.re -= vr[k].re * wc.re + vr[k].im * wc.im + wr[k].re * vc.re + wr[k].im * vc.im;
                     a.im -= vr[k].im * wc.re - vr[k].re * wc.im + wr[k].im * vc.re - wr[k].re * vc.im;
@@ -300,12 +477,16 @@ TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
       }
       g.sync();
     }
+#endif
+    TBK_HP(3)
   }
   if (tid == 0) {
     w.d[n - 1] = A[(n - 1) + (size_t)(n - 1) * lda].re;
     w.e[n - 1] = 0.0;
     w.tau[n - 1] = mk(0.0, 0.0);
   }
+  TBK_HP(7)
+  TBK_HP_END
   g.sync();
 }
 
@@ -316,11 +497,12 @@ TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
 // ---------------------------------------------------------------------------------------------
 template <class G>
 TBK_HD void hetrd_blocked_full(G& g, const BlkWork& w) {
-  const int n = w.n, lda = w.lda, nb = w.nb;
+  const int n = w.n, lda = w.lda, nb = w.nb, ldp = w.ldp;
   const int T = g.size(), tid = g.tid();
   cplx* A = w.A;
   cplx* V = w.V;
   cplx* W = w.W;
+  TBK_HP_BEGIN
   // full Hermitian storage: upper from lower, real diagonal
   for (int c = tid; c < n; c += T) A[c + (size_t)c * lda].im = 0.0;
   for (int r = tid; r < n; r += T)
@@ -329,7 +511,7 @@ TBK_HD void hetrd_blocked_full(G& g, const BlkWork& w) {
   for (int j0 = 0; j0 < n - 1; j0 += nb) {
     const int nbp = n - 1 - j0 < nb ? n - 1 - j0 : nb;
     // zero the panels (unused panel columns must be exactly zero for the rank-2nb update)
-    for (int q = tid; q < nb * n; q += T) { V[q] = mk(0.0, 0.0); W[q] = mk(0.0, 0.0); }
+    for (int q = tid; q < nb * ldp; q += T) { V[q] = mk(0.0, 0.0); W[q] = mk(0.0, 0.0); }
     g.sync();
     for (int i = 0; i < nbp; ++i) {
       const int j = j0 + i;
@@ -339,8 +521,8 @@ TBK_HD void hetrd_blocked_full(G& g, const BlkWork& w) {
         for (int r = j + tid; r < n; r += T) {
           cplx a = col[r];
           for (int k = 0; k < i; ++k) {
-            a = a - mulc(V[k * n + r], W[k * n + j]);
-            a = a - mulc(W[k * n + r], V[k * n + j]);
+            a = a - mulc(V[k * ldp + r], W[k * ldp + j]);
+            a = a - mulc(W[k * ldp + r], V[k * ldp + j]);
           }
           if (r == j) a.im = 0.0;
           col[r] = a;
@@ -361,7 +543,7 @@ TBK_HD void hetrd_blocked_full(G& g, const BlkWork& w) {
         scal = cdiv(mk(1.0, 0.0), mk(alpha.re - beta, alpha.im));
       }
       g.sync();                                   // everyone has read alpha
-      cplx* v = V + i * n;
+      cplx* v = V + i * ldp;
       for (int r = j + 2 + tid; r < n; r += T) {
         const cplx x = col[r] * scal;             // tau == 0: the column is already zero below j+1
         col[r] = x;
@@ -374,6 +556,7 @@ TBK_HD void hetrd_blocked_full(G& g, const BlkWork& w) {
         w.d[j] = col[j].re;
       }
       g.sync();
+      TBK_HP(7)
       // ---- (3) w = A22 v with the stored (panel-start) trailing matrix, rows/cols j+1 .. n-1
       const int m = n - j - 1;
       {
@@ -387,7 +570,8 @@ TBK_HD void hetrd_blocked_full(G& g, const BlkWork& w) {
             cplx acc = mk(0.0, 0.0);
             if (r < n) {
               // eight independent accumulators: eight 16-byte loads in flight per thread, no serial FMA chain
-              // (the product is latency-bound: one 512-thread CTA per SM has only its own loads to hide them)
+              // (measured r13: the product runs AT the HBM bound of the concurrently resident matrices — 16 n^3 / 3 bytes
+              // each — so deeper software pipelining buys nothing; it only spills at the 128-register cap)
               const cplx* arow = A + r;
               cplx a0 = mk(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0, a7 = a0;
               int c = j + 1 + pp;
@@ -417,7 +601,7 @@ TBK_HD void hetrd_blocked_full(G& g, const BlkWork& w) {
               acc = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
             }
             if (parts == 1) {
-              if (r < n) W[i * n + r] = acc;
+              if (r < n) W[i * ldp + r] = acc;
             } else {                              // parts > 1 implies m <= rw: a single row block
               w.wcol[pp * rw + pr] = acc;
             }
@@ -428,15 +612,16 @@ TBK_HD void hetrd_blocked_full(G& g, const BlkWork& w) {
           for (int r = tid; r < m; r += T) {
             cplx acc = w.wcol[r];
             for (int q = 1; q < parts; ++q) acc = acc + w.wcol[q * rw + r];
-            W[i * n + j + 1 + r] = acc;
+            W[i * ldp + j + 1 + r] = acc;
           }
         }
       }
       g.sync();
+      TBK_HP(0)
       // ---- panel corrections: dots[k] = W_k^H v, dots[nb+k] = V_k^H v, one sub-team per dot product
       if (i > 0) {
         for (int q = g.sub(); q < 2 * i; q += g.nsub()) {
-          const cplx* src = q < i ? W + q * n : V + (q - i) * n;
+          const cplx* src = q < i ? W + q * ldp : V + (q - i) * ldp;
           double sre = 0.0, sim = 0.0;
           for (int r = j + 1 + g.lane(); r < n; r += g.subsize()) {
             const cplx t = cmul(src[r], v[r]);
@@ -447,75 +632,66 @@ TBK_HD void hetrd_blocked_full(G& g, const BlkWork& w) {
         }
         g.sync();
         for (int r = j + 1 + tid; r < n; r += T) {
-          cplx acc = W[i * n + r];
+          cplx acc = W[i * ldp + r];
           for (int k = 0; k < i; ++k) {
-            acc = acc - V[k * n + r] * w.dots[k];
-            acc = acc - W[k * n + r] * w.dots[nb + k];
+            acc = acc - V[k * ldp + r] * w.dots[k];
+            acc = acc - W[k * ldp + r] * w.dots[nb + k];
           }
-          W[i * n + r] = acc;
+          W[i * ldp + r] = acc;
         }
         g.sync();
       }
       // ---- w = tau w;  w += (-tau/2 (w^H v)) v
       double dre = 0.0, dim = 0.0;
       for (int r = j + 1 + tid; r < n; r += T) {
-        const cplx wr = tau * W[i * n + r];
-        W[i * n + r] = wr;
+        const cplx wr = tau * W[i * ldp + r];
+        W[i * ldp + r] = wr;
         const cplx t = cmul(wr, v[r]);
         dre += t.re; dim += t.im;
       }
       dre = g.sum(dre); dim = g.sum(dim);        // g.sum synchronises: the scaled w is visible
       const cplx a2 = (-0.5) * (tau * mk(dre, dim));
-      for (int r = j + 1 + tid; r < n; r += T) W[i * n + r] = W[i * n + r] + a2 * v[r];
+      for (int r = j + 1 + tid; r < n; r += T) W[i * ldp + r] = W[i * ldp + r] + a2 * v[r];
       g.sync();
     }
+    TBK_HP(7)
     // ---- rank-2nb update of the trailing matrix: A22 -= V W^H + W V^H   (rows/cols >= j1)
     const int j1 = j0 + nbp;
     const int m = n - j1;
     if (m > 0) {
+#if defined(__CUDA_ARCH__)
+      blk_rank2k_dmma<false>(A, lda, n, j1, V, W, ldp, nb);
+#else
       int rw = ((m + 31) / 32) * 32;
       if (rw > T) rw = T;
       const int parts = T / rw > 0 ? T / rw : 1;
       const int pr = tid % rw, pp = tid / rw;
       if (pp < parts) {
         for (int r = j1 + pr; r < n; r += rw) {
-          for (int k0 = 0; k0 < nb; k0 += 8) {    // 8 panel columns at a time in registers
-            if (k0 >= nbp) break;
-            cplx vr[8], wr[8];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (int k = 0; k < 8; ++k) {
-              const bool in = k0 + k < nb;
-              vr[k] = in ? V[(k0 + k) * n + r] : mk(0.0, 0.0);
-              wr[k] = in ? W[(k0 + k) * n + r] : mk(0.0, 0.0);
+          for (int c = j1 + pp; c < n; c += parts) {
+            cplx a = A[r + (size_t)c * lda];
+            for (int k = 0; k < nb; ++k) {
+              const cplx vr = V[k * ldp + r], wr = W[k * ldp + r], wc = W[k * ldp + c], vc = V[k * ldp + c];
+              // a -= vr * conj(wc) + wr * conj(vc)
+              a.re -= vr.re * wc.re + vr.im * wc.im + wr.re * vc.re + wr.im * vc.im;
+              a.im -= vr.im * wc.re - vr.re * wc.im + wr.im * vc.re - wr.re * vc.im;
             }
-            for (int c = j1 + pp; c < n; c += parts) {
-              cplx a = A[r + (size_t)c * lda];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-              for (int k = 0; k < 8; ++k) {
-                if (k0 + k < nb) {
-                  const cplx wc = W[(k0 + k) * n + c], vc = V[(k0 + k) * n + c];
-                  // a -= vr * conj(wc) + wr * conj(vc)
-                  a.re -= vr[k].re * wc.re + vr[k].im * wc.im + wr[k].re * vc.re + wr[k].im * vc.im;
-                  a.im -= vr[k].im * wc.re - vr[k].re * wc.im + wr[k].im * vc.re - wr[k].re * vc.im;
-                }
-              }
-              A[r + (size_t)c * lda] = a;
-            }
+            A[r + (size_t)c * lda] = a;
           }
         }
       }
+#endif
       g.sync();
     }
+    TBK_HP(3)
   }
   if (tid == 0) {
     w.d[n - 1] = A[(n - 1) + (size_t)(n - 1) * lda].re;
     w.e[n - 1] = 0.0;
     w.tau[n - 1] = mk(0.0, 0.0);
   }
+  TBK_HP(7)
+  TBK_HP_END
   g.sync();
 }
 // Both variants are kept because neither dominates (profiles/README.md r09): the full-matrix product (a thread per

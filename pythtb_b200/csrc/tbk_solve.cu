@@ -114,6 +114,7 @@ __global__ void fill_u64_kernel(unsigned long long* p, int n, unsigned long long
 
 }  // namespace tbk
 #include "tbk_mesh_small.cuh"
+#include "tbk_eig_wy.cuh"
 namespace tbk {
 
 // ===========================================================================
@@ -505,6 +506,43 @@ static long long blk_blocks(const BlkShape& s, long long npts) {
   return npts < cap ? npts : cap;
 }
 
+// Staged solver (eigenvectors wanted): the matrices of a chunk keep their reflectors (A, tau), tridiagonal eigenvectors
+// (Z) and compact-WY T factors in per-matrix SLOTS of the workspace; solve_blocked_kernel fills the slots (H build,
+// tridiagonalisation, bisection, inverse iteration), blk_wy_kernel and blk_backtransform_kernel (tbk_eig_wy.cuh) finish
+// the chunk on the FP64 tensor pipe.  The inverse-iteration scratch stays per resident CTA.
+constexpr int kBlkSlotsPerSM = 4;
+struct BlkStage {
+  WyArgs wy;            // slot layout (ws filled in at launch)
+  long long slots;      // matrices per chunk
+  long long ctas;       // resident CTAs of the front kernel
+  size_t lu_bytes;      // inverse-iteration scratch per front-kernel CTA
+  size_t total;
+};
+static BlkStage blk_stage_layout(const BlkShape& shp, long long npts) {
+  BlkStage s;
+  memset(&s, 0, sizeof(s));
+  const int n = shp.n;
+  s.wy.n = n; s.wy.lda = shp.lda; s.wy.nblk = wy_nblk(n);
+  auto r256 = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t off = 0;
+  s.wy.off_A = off;    off += shp.ws_A;
+  s.wy.off_Z = off;    off += shp.ws_Z;
+  s.wy.off_tau = off;  off += r256((size_t)n * 16);
+  s.wy.off_T = off;    off += r256((size_t)s.wy.nblk * kWyNB * kWyNB * 16);
+  s.wy.off_flag = off; off += 256;
+  s.wy.slot_bytes = off;
+  s.slots = npts < (long long)kNumSM * kBlkSlotsPerSM ? (npts < 1 ? 1 : npts) : (long long)kNumSM * kBlkSlotsPerSM;
+  s.ctas = blk_blocks(shp, s.slots);
+  s.lu_bytes = shp.ws_lu;
+  s.total = (size_t)s.slots * s.wy.slot_bytes + (size_t)s.ctas * s.lu_bytes;
+  return s;
+}
+static bool blk_staged_enabled() {
+  static int on = -1;                                   // TBK_BACKTR=legacy: the one-kernel solver of rounds 1-2 (A/B knob)
+  if (on < 0) { const char* e = getenv("TBK_BACKTR"); on = (e && strcmp(e, "legacy") == 0) ? 0 : 1; }
+  return on == 1;
+}
+
 // Optional per-stage cycle counters (TBK_PROF=1): pinned host words the kernel adds clock64 deltas to
 // [0] hetrd [1] bisect [2] invit [3] backtransform [4] matrices [5] fallbacks [6] slowest matrix;
 // read by tbk_debug_profile.
@@ -523,23 +561,39 @@ static unsigned long long* blk_prof() {
 template <int MAXM>
 __global__ void __launch_bounds__(512)
 solve_blocked_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long long npts, OutSpec out, int want_vec,
-                     BlkShape shp, char* __restrict__ gws, unsigned long long* prof) {
+                     BlkShape shp, char* __restrict__ gws, unsigned long long* prof, const WyArgs stg, const long long idx0) {
   extern __shared__ __align__(16) char smem[];
   __shared__ double red[32];
   BlockGroup g(red);
   const int n = shp.n, lda = shp.lda, tid = threadIdx.x, T = blockDim.x;
   BlkWork w;
   w.n = n; w.lda = lda; w.nb = shp.nb; w.nt = shp.nt; w.nred = shp.nred;
+  w.prof = prof;
   blk_carve_shared(w, smem, shp.threads);
   cplx* ph = (cplx*)(smem + shp.off_ph);
   cplx* gf = (cplx*)(smem + shp.off_gf);
   double* kbuf = (double*)(smem + shp.off_misc);
   int* mibuf = (int*)(kbuf + TBK_MAX_DIM);
-  char* mine = gws + (size_t)blockIdx.x * shp.ws_block;
-  w.A = (cplx*)mine;
-  w.Z = (double*)(mine + shp.ws_A);
-  w.lu = (double*)(mine + shp.ws_A + shp.ws_Z);
-  for (long long idx = blockIdx.x; idx < npts; idx += gridDim.x) {
+  // stg.ws == nullptr: one kernel does everything, the CTA's private workspace block holds A, Z and the
+  // inverse-iteration scratch.  Otherwise (staged, eigenvectors wanted): this kernel handles the matrices
+  // idx0 .. idx0 + npts - 1 of a chunk, A / Z / tau / the fallback flag go to the matrix' slot, gws holds the per-CTA scratch.
+  const bool staged = stg.ws != nullptr;
+  char* mine = gws + (size_t)blockIdx.x * (staged ? shp.ws_lu : shp.ws_block);
+  if (staged) {
+    w.lu = (double*)mine;
+  } else {
+    w.A = (cplx*)mine;
+    w.Z = (double*)(mine + shp.ws_A);
+    w.lu = (double*)(mine + shp.ws_A + shp.ws_Z);
+  }
+  for (long long it = blockIdx.x; it < npts; it += gridDim.x) {
+    const long long idx = idx0 + it;
+    char* slot = nullptr;
+    if (staged) {
+      slot = stg.ws + (size_t)it * stg.slot_bytes;
+      w.A = (cplx*)(slot + stg.off_A);
+      w.Z = (double*)(slot + stg.off_Z);
+    }
     // ---- k-point and the lower triangle of H(k)
     if (tid == 0) {
       int mi[TBK_MAX_DIM] = {0, 0, 0, 0};
@@ -571,17 +625,36 @@ solve_blocked_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long l
 #define TBK_PROF_MARK(slot) if (prof && tid == 0) { const long long t1 = clock64(); atomicAdd(prof + slot, (unsigned long long)(t1 - t0)); t0 = t1; }
     if (shp.sym) hetrd_blocked<MAXM>(g, w);
     else hetrd_blocked_full(g, w);
+#if defined(TBK_HETRD_PROF)
+    if (prof && tid == 0) t0 = clock64();       // the phases of the tridiagonalisation were counted inside (slots 0, 3, 7)
+#else
     TBK_PROF_MARK(0)
+#endif
     const double tnorm = tridiag_bisect(g, w);
     TBK_PROF_MARK(1)
     if (want_vec) {
       const int fail = tridiag_invit(g, w, tnorm);
       TBK_PROF_MARK(2)
+      if (staged && tid == 0) *(int*)(slot + stg.off_flag) = fail ? 1 : 0;
       if (fail) {
         if (prof && tid == 0) atomicAdd(prof + 5, 1ull);
         // a spectrum the inverse iteration should not be trusted with: unblocked Householder + QL
         // (rebuilds H(k), writes every output of this k-point)
         solve_one_matrix(g, pv, ks, hsrc, idx, out, want_vec, shp.fallback, w.A, smem);
+        continue;
+      }
+      if (staged) {
+        // the back-transformation is left to blk_wy_kernel / blk_backtransform_kernel
+        cplx* tau_g = (cplx*)(slot + stg.off_tau);
+        for (int o = tid; o < n; o += T) tau_g[o] = w.tau[o];
+        if (prof && tid == 0) { atomicAdd(prof + 4, 1ull); atomicMax(prof + 6, (unsigned long long)(clock64() - tstart)); }
+        if (out.mode == 0) {
+          if (out.eval)
+            for (int b = tid; b < n; b += T) out.eval[b * out.ev_sb + idx * out.ev_sk] = w.lam[b];
+        } else if (out.gaps_bits != nullptr) {
+          for (int b = tid; b < n - 1; b += T) atomic_min_nonneg(out.gaps_bits + b, w.lam[b + 1] - w.lam[b]);
+        }
+        g.sync();
         continue;
       }
       for (int o = tid; o < n; o += T) {
@@ -729,17 +802,47 @@ static int launch_solve(const PlanView& pv, const KSrc& ks, const cplx* hsrc, in
     if (n <= kBlkMaxN && !(env && atoi(env) == 0)) {
       const BlkShape shp = blk_shape(n, nph);
       if (shp.smem <= (size_t)kMaxSmem) {
+        WyArgs stg;
+        memset(&stg, 0, sizeof(stg));
+#define TBK_BLK_LAUNCH(MM, BLOCKS, COUNT, GWS, IDX0)                                                              \
+        do {                                                                                                      \
+          TBK_CUDA(cudaFuncSetAttribute(solve_blocked_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shp.smem)); \
+          solve_blocked_kernel<MM><<<(unsigned)(BLOCKS), shp.threads, shp.smem, st>>>(pv, ks, hsrc, COUNT, out, want_vec, shp, GWS, blk_prof(), stg, IDX0); \
+        } while (0)
+#define TBK_BLK_DISPATCH(BLOCKS, COUNT, GWS, IDX0)                                                                \
+        do {                                                                                                      \
+          if (n <= 128) TBK_BLK_LAUNCH(4, BLOCKS, COUNT, GWS, IDX0);                                              \
+          else if (n <= 256) TBK_BLK_LAUNCH(8, BLOCKS, COUNT, GWS, IDX0);                                         \
+          else TBK_BLK_LAUNCH(16, BLOCKS, COUNT, GWS, IDX0);                                                      \
+        } while (0)
+        if (want_vec && blk_staged_enabled()) {
+          BlkStage sg = blk_stage_layout(shp, npts);
+          if (ws == nullptr || ws_bytes < sg.total) { set_error("workspace too small: need %zu bytes, have %zu", sg.total, ws_bytes); return TBK_ERR_WORKSPACE; }
+          stg = sg.wy;
+          stg.ws = (char*)ws;
+          char* lu_base = (char*)ws + (size_t)sg.slots * sg.wy.slot_bytes;
+          const size_t smem_t = wy_t_smem(), smem_b = wy_bt_smem(n);
+          TBK_CUDA(cudaFuncSetAttribute(blk_wy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+          TBK_CUDA(cudaFuncSetAttribute(blk_backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+          for (long long base = 0; base < npts; base += sg.slots) {
+            const long long cnt = npts - base < sg.slots ? npts - base : sg.slots;
+            const long long blocks = cnt < sg.ctas ? cnt : sg.ctas;
+            TBK_BLK_DISPATCH(blocks, cnt, lu_base, base);
+            TBK_LAUNCH_CHECK("solve_blocked_kernel");
+            blk_wy_kernel<<<dim3((unsigned)stg.nblk, (unsigned)cnt), kWyThreads, smem_t, st>>>(stg);
+            TBK_LAUNCH_CHECK("blk_wy_kernel");
+            blk_backtransform_kernel<<<dim3((unsigned)((n + kWyNC - 1) / kWyNC), (unsigned)cnt), kWyThreads, smem_b, st>>>(
+                stg, pv, ks, out, hsrc != nullptr ? 1 : 0, base);
+            TBK_LAUNCH_CHECK("blk_backtransform_kernel");
+          }
+          note_kernel("solve_blocked_kernel");
+          return TBK_OK;
+        }
         const long long blocks = blk_blocks(shp, npts);
         const size_t need = (size_t)blocks * shp.ws_block;
         if (ws == nullptr || ws_bytes < need) { set_error("workspace too small: need %zu bytes, have %zu", need, ws_bytes); return TBK_ERR_WORKSPACE; }
-#define TBK_BLK_LAUNCH(MM)                                                                                        \
-        do {                                                                                                      \
-          TBK_CUDA(cudaFuncSetAttribute(solve_blocked_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shp.smem)); \
-          solve_blocked_kernel<MM><<<(unsigned)blocks, shp.threads, shp.smem, st>>>(pv, ks, hsrc, npts, out, want_vec, shp, (char*)ws, blk_prof()); \
-        } while (0)
-        if (n <= 128) TBK_BLK_LAUNCH(4);
-        else if (n <= 256) TBK_BLK_LAUNCH(8);
-        else TBK_BLK_LAUNCH(16);
+        TBK_BLK_DISPATCH(blocks, npts, (char*)ws, 0LL);
+#undef TBK_BLK_DISPATCH
 #undef TBK_BLK_LAUNCH
         TBK_LAUNCH_CHECK("solve_blocked_kernel");
         note_kernel("solve_blocked_kernel");
@@ -783,6 +886,8 @@ static size_t solve_ws_bytes(int n, long long npts) {
     // the shape used at launch may have fewer resident CTAs (phase table in shared memory), never more
     const size_t n2 = (size_t)b2 * shp.ws_block;
     if (n2 > need) need = n2;
+    const size_t n3 = blk_stage_layout(shp, npts < 1 ? 1 : npts).total;   // staged solver (eigenvectors wanted)
+    if (n3 > need) need = n3;
   }
   return need;
 }
