@@ -277,74 +277,13 @@ TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
 #pragma unroll
 #endif
         for (int t = 0; t < MAXM; ++t) acc[t] = mk(0.0, 0.0);
-#if defined(__CUDA_ARCH__)
-        // Device: FOUR adjacent columns per warp step.  Their loads (one coalesced 512-byte warp load per column and row
-        // slot) are independent and issued together — with one column at a time a warp had ~6 loads in flight and then
-        // waited for a 10-shuffle reduction before it touched the next column (the product ran at half the speed of the
-        // full-matrix one although it moves half the bytes) — and the eight column sums (re, im of four columns) are
-        // reduced over the lanes by ONE transposing butterfly: 4 + 2 + 1 + 1 + 1 = 9 shuffles instead of 40.
-        for (int c0 = j + 1 + 4 * sub; c0 < n; c0 += 4 * nsub) {
-          cplx vc[4];
-          const cplx* acol[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int c = c0 + q < n ? c0 + q : n - 1;
-            vc[q] = c0 + q < n ? v[c] : mk(0.0, 0.0);
-            acol[q] = A + (size_t)c * lda;
-          }
-          double s8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-          for (int t = 0; t < MAXM; ++t) {
-            if (32 * t + 31 >= c0) {                  // warp-uniform: this slot reaches the diagonal of the first column
-              const int r = L + 32 * t;
-              const int rc = r < n ? r : n - 1;
-              const cplx vr = v[rc];
-              cplx a[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) a[q] = acol[q][rc];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int c = c0 + q;
-                const bool on = r >= c && r < n && c < n;
-                cplx x = on ? a[q] : mk(0.0, 0.0);
-                if (r == c) x.im = 0.0;
-                fma_acc(acc[t], x, vc[q]);
-                const cplx tt = cmul(r > c ? x : mk(0.0, 0.0), vr);      // conj(a_rc) v_r, strictly below the diagonal
-                s8[2 * q] += tt.re; s8[2 * q + 1] += tt.im;
-              }
-            }
-          }
-          {
-            const bool b0 = L & 1, b1 = L & 2, b2 = L & 4;
-#pragma unroll
-            for (int x = 0; x < 4; ++x) {
-              const double send = b0 ? s8[x] : s8[x + 4], keep = b0 ? s8[x + 4] : s8[x];
-              s8[x] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-            }
-#pragma unroll
-            for (int x = 0; x < 2; ++x) {
-              const double send = b1 ? s8[x] : s8[x + 2], keep = b1 ? s8[x + 2] : s8[x];
-              s8[x] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-            }
-            {
-              const double send = b2 ? s8[0] : s8[1], keep = b2 ? s8[1] : s8[0];
-              s8[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-            s8[0] += __shfl_xor_sync(0xffffffffu, s8[0], 8);
-            s8[0] += __shfl_xor_sync(0xffffffffu, s8[0], 16);
-            // lane L (< 8) now holds entry (L & 1) * 4 + ((L >> 1) & 1) * 2 + ((L >> 2) & 1) of the eight sums
-            if (L < 8) {
-              const int idx = (L & 1) * 4 + ((L >> 1) & 1) * 2 + ((L >> 2) & 1);
-              const int c = c0 + (idx >> 1);
-              if (c < n) { double* dst = (double*)(w.wcol + c); dst[idx & 1] = s8[0]; }
-            }
-          }
-        }
-#else
         for (int c = j + 1 + sub; c < n; c += nsub) {
           const cplx vc = v[c];
           const cplx* acol = A + (size_t)c * lda;
           double sre = 0.0, sim = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
           for (int t = 0; t < MAXM; ++t) {
             if (S * t + S - 1 >= c) {                 // sub-team-uniform: this slot reaches the diagonal of column c
               const int r = L + S * t;
@@ -362,7 +301,6 @@ TBK_HD void hetrd_blocked(G& g, const BlkWork& w) {
           sre = g.subsum(sre); sim = g.subsum(sim);
           if (L == 0) w.wcol[c] = mk(sre, sim);
         }
-#endif
         g.sync();                                     // wcol complete
         for (int w0 = 0; w0 < nsub; w0 += w.nred) {
           if (sub >= w0 && sub < w0 + w.nred) {
@@ -570,8 +508,10 @@ TBK_HD void hetrd_blocked_full(G& g, const BlkWork& w) {
             cplx acc = mk(0.0, 0.0);
             if (r < n) {
               // eight independent accumulators: eight 16-byte loads in flight per thread, no serial FMA chain
-              // (measured r13: the product runs AT the HBM bound of the concurrently resident matrices — 16 n^3 / 3 bytes
-              // each — so deeper software pipelining buys nothing; it only spills at the 128-register cap)
+              // (measured r13: with one matrix per SM the product moves 16 n^3 / 3 bytes per matrix at 5.7-6 TB/s in
+              // aggregate — the HBM rate; a two-deep register pipeline only spilled at the 128-register cap and a TMA ring
+              // (cp.async.bulk per column + mbarriers, all free shared memory in flight) was 4x slower: one 16-byte
+              // element per thread per column cannot amortise a barrier wait and a slot release)
               const cplx* arow = A + r;
               cplx a0 = mk(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0, a7 = a0;
               int c = j + 1 + pp;

@@ -558,8 +558,12 @@ static unsigned long long* blk_prof() {
   return g_blk_prof;
 }
 
+// resident CTAs per SM the 256-thread instantiations (n <= 256) are compiled for (A/B knob, profiles/build_variant.py)
+#ifndef TBK_BLK_MINB_SMALL
+#define TBK_BLK_MINB_SMALL 2
+#endif
 template <int MAXM>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(MAXM <= 8 ? 256 : 512, MAXM <= 8 ? TBK_BLK_MINB_SMALL : 1)
 solve_blocked_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long long npts, OutSpec out, int want_vec,
                      BlkShape shp, char* __restrict__ gws, unsigned long long* prof, const WyArgs stg, const long long idx0) {
   extern __shared__ __align__(16) char smem[];
