@@ -305,7 +305,10 @@ def config5(tb, eng, world, rank, peaks, with_cpu, nl=250, mesh=129, budget_s=1e
         stages[k] = v
     fl_solve = f_eigh(n, True)
     fl_hwf = 2 * f_overlap(nl, n) + f_eigh(nl, True)
-    fl_link = f_overlap(nl, n) + 20 * 2 * 8.0 * nl ** 3          # overlap + ~20 Newton-Schulz iterations of two nl^3 complex GEMMs
+    # Wilson links: only the overlap GEMM is counted.  The polar factors (Newton-Schulz on the DMMA GEMM, 2 x 8 nl^3 flops
+    # per iteration) take a data-dependent number of iterations that the library does not report; round 2's first lines
+    # assumed 20 of them and showed an "achieved" rate above the measured DMMA peak.  links/s is the figure to read.
+    fl_link = f_overlap(nl, n)
     solve_s = stages["solve_on_grid_s"]
     out = dict(workload="cubic slab nl = %d (norb %d) on a [%d, %d] mesh%s: solve_on_grid, position_hwf at every k-point (hwf_evec, orbital basis), Berry phases of hybrid Wannier bands, all-band Wilson loops"
                         % (nl, n, mesh, mesh, " sharded over %d GPUs" % world if world > 1 else ""),
@@ -320,7 +323,8 @@ def config5(tb, eng, world, rank, peaks, with_cpu, nl=250, mesh=129, budget_s=1e
                              frac=npts * fl_solve / solve_s / 1e12 / peaks["dfma_tflops"], flops_per_kpoint=fl_solve,
                              peak_source="measured in this run (DFMA microkernel)",
                              hwf=dict(flops_per_kpoint=fl_hwf, achieved=mesh * mesh * fl_hwf / stages["position_hwf_all_s"] / 1e12),
-                             wilson=(dict(flops_per_link=fl_link, achieved=nlinks_tot * fl_link / stages["wilson_all_bands_s"] / 1e12,
+                             wilson=(dict(flops_per_link_counted=fl_link, counted="overlap GEMM only (lower bound: polar factors, products and eigenphases not counted)",
+                                          achieved_lower_bound=nlinks_tot * fl_link / stages["wilson_all_bands_s"] / 1e12,
                                           peak=peaks["dmma_tflops"], peak_source="measured in this run (DMMA microkernel)")
                                      if stages["wilson_all_bands_s"] else None)),
                check=dict(golden_cubic_slab_nl9=("ok" if not bad else bad), min_gap=float(np.min(gaps)),

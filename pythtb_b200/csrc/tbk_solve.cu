@@ -481,6 +481,17 @@ static BlkShape blk_shape(int n, int nph) {
     s.nb = 8; s.nred = want_red;
     while (s.nred > 1 && total(8, s.nred) + 1024 > (size_t)kMaxSmem) --s.nred;
   }
+  {
+    // A/B knob TBK_BLK_SHAPE="threads,nb" (n > 256 only), e.g. "256,4": two 256-thread CTAs per SM with half-width
+    // panels, so that one matrix' latency-bound stages overlap the other's HBM-bound matrix-vector products
+    static int kt = -1, knb = 0;
+    if (kt < 0) {
+      kt = 0;
+      const char* e = getenv("TBK_BLK_SHAPE");
+      if (e) { int a = 0, b = 0; if (sscanf(e, "%d,%d", &a, &b) == 2 && (a == 256 || a == 512) && (b == 4 || b == 8 || b == 16)) { kt = a; knb = b; } }
+    }
+    if (kt > 0 && n > 256 && !s.sym) { s.threads = kt; s.nb = knb; s.nred = 0; }
+  }
   size_t off = (blk_shared_bytes(n, s.nb, s.nred, s.threads) + 15) & ~(size_t)15;
   s.off_ph = off;   off += (size_t)(nph > 0 ? nph : 1) * 16;
   s.off_gf = off;   off += (size_t)n * 16;
@@ -565,7 +576,8 @@ static unsigned long long* blk_prof() {
 template <int MAXM>
 __global__ void __launch_bounds__(MAXM <= 8 ? 256 : 512, MAXM <= 8 ? TBK_BLK_MINB_SMALL : 1)
 solve_blocked_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long long npts, OutSpec out, int want_vec,
-                     BlkShape shp, char* __restrict__ gws, unsigned long long* prof, const WyArgs stg, const long long idx0) {
+                     BlkShape shp, char* __restrict__ gws, unsigned long long* prof, const WyArgs stg, const long long idx0,
+                     unsigned* __restrict__ work) {
   extern __shared__ __align__(16) char smem[];
   __shared__ double red[32];
   BlockGroup g(red);
@@ -590,7 +602,18 @@ solve_blocked_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long l
     w.Z = (double*)(mine + shp.ws_A);
     w.lu = (double*)(mine + shp.ws_A + shp.ws_Z);
   }
-  for (long long it = blockIdx.x; it < npts; it += gridDim.x) {
+  // work distribution: static stride, or (staged chunks) a self-resetting device counter — matrices with large
+  // eigenvalue clusters take up to 3x the mean, and with 4 matrices per CTA a static split made the unlucky CTA the
+  // tail of every chunk.  atomicInc wraps to 0 after npts successful + gridDim failing fetches: ready for the next launch.
+  __shared__ long long s_next;
+  auto fetch = [&](long long cur) -> long long {
+    if (work == nullptr) return cur < 0 ? (long long)blockIdx.x : cur + gridDim.x;
+    __syncthreads();
+    if (tid == 0) s_next = (long long)atomicInc(work, (unsigned)(npts + gridDim.x - 1));
+    __syncthreads();
+    return s_next;
+  };
+  for (long long it = fetch(-1); it < npts; it = fetch(it)) {
     const long long idx = idx0 + it;
     char* slot = nullptr;
     if (staged) {
@@ -808,10 +831,11 @@ static int launch_solve(const PlanView& pv, const KSrc& ks, const cplx* hsrc, in
       if (shp.smem <= (size_t)kMaxSmem) {
         WyArgs stg;
         memset(&stg, 0, sizeof(stg));
+        unsigned* work = nullptr;
 #define TBK_BLK_LAUNCH(MM, BLOCKS, COUNT, GWS, IDX0)                                                              \
         do {                                                                                                      \
           TBK_CUDA(cudaFuncSetAttribute(solve_blocked_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shp.smem)); \
-          solve_blocked_kernel<MM><<<(unsigned)(BLOCKS), shp.threads, shp.smem, st>>>(pv, ks, hsrc, COUNT, out, want_vec, shp, GWS, blk_prof(), stg, IDX0); \
+          solve_blocked_kernel<MM><<<(unsigned)(BLOCKS), shp.threads, shp.smem, st>>>(pv, ks, hsrc, COUNT, out, want_vec, shp, GWS, blk_prof(), stg, IDX0, work); \
         } while (0)
 #define TBK_BLK_DISPATCH(BLOCKS, COUNT, GWS, IDX0)                                                                \
         do {                                                                                                      \
@@ -831,6 +855,7 @@ static int launch_solve(const PlanView& pv, const KSrc& ks, const cplx* hsrc, in
           for (long long base = 0; base < npts; base += sg.slots) {
             const long long cnt = npts - base < sg.slots ? npts - base : sg.slots;
             const long long blocks = cnt < sg.ctas ? cnt : sg.ctas;
+            work = cnt > blocks ? take_ticket() : nullptr;       // more matrices than CTAs: dynamic distribution
             TBK_BLK_DISPATCH(blocks, cnt, lu_base, base);
             TBK_LAUNCH_CHECK("solve_blocked_kernel");
             blk_wy_kernel<<<dim3((unsigned)stg.nblk, (unsigned)cnt), kWyThreads, smem_t, st>>>(stg);

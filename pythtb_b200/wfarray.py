@@ -205,7 +205,9 @@ class wf_array(object):
         rp = self._rp_sg
         if rp is not None and type(start_k) is list and start_k == rp[0] and self._model._plan_cache is rp[1]:
             st, eng = self._store, rp[2]
-            if st._dev is rp[3] and eng._ws is rp[4] and st.state != "host":
+            # (a grid solve overwrites every element of the array: a host mirror that was handed out in between
+            # — state "host" — need not be uploaded first, and does not invalidate the replay)
+            if st._dev is rp[3] and eng._ws is rp[4]:
                 st.state = "device"
                 rc = eng.lib.tbk_prepared_run(rp[5], eng.stream(), 1)
                 if rc:

@@ -471,6 +471,15 @@ def test_replayed_calls_follow_their_arguments():
     w2 = mod.wf_array(m, mesh)
     w2.solve_on_grid([-0.5, -0.5])
     assert np.max(np.abs(compare.circ_diff(p1, w2.berry_flux([0, 1], individual_phases=True), 2 * np.pi))) > 1e-3
+    # a grid solve overwrites every element: it neither uploads nor is misled by a host mirror that was handed
+    # out (and scribbled on) since the last solve — replayed or not
+    fresh = np.array(w2._wfs)
+    for _ in range(2):
+        host = w._wfs
+        host[...] = 0.0
+        w.solve_on_grid([-0.5, -0.5])
+        assert w._store.state == "device"
+        assert np.array_equal(np.array(w._wfs), fresh)
     # a model edit rebuilds the plan: the solve must follow it
     h = M.haldane(mod, delta=0.0)
     wh = mod.wf_array(h, mesh)
