@@ -195,11 +195,9 @@ struct JacobiPacked {
 //   w[N][N]   rows = eigenvectors (not conjugated), H w[b]^T = ev[b] w[b]^T
 // Returns false if the QL iteration did not converge in 30 steps (callers fall back to Jacobi).
 // ---------------------------------------------------------------------------
+// (1) zhetd2 'L': a -> real tridiagonal (d, e), reflectors left in a / tau
 template <int N>
-TBK_HD bool eigh_small_ql(cplx a[N][N], double ev[N], cplx w[N][N]) {
-  const double eps = 1.1102230246251565e-16;
-  double d[N], e[N];
-  cplx tau[N];
+TBK_HD void small_hetd2(cplx a[N][N], double d[N], double e[N], cplx tau[N]) {
   // ---- zhetd2 'L': reflector j annihilates a[j+2..N-1][j]; v_j kept in a[j+2..][j], implicit unit at j+1
   TBK_UNROLL
   for (int j = 0; j < N - 1; ++j) {
@@ -255,8 +253,12 @@ TBK_HD bool eigh_small_ql(cplx a[N][N], double ev[N], cplx w[N][N]) {
   }
   d[N - 1] = a[N - 1][N - 1].re;
   e[N - 1] = 0.0;
-  // ---- implicit-shift QL on (d, e); column c of z is the eigenvector of d[c]
-  double z[N][N];
+}
+
+// (2) implicit-shift QL on (d, e): on exit d ascending, column c of z the eigenvector of d[c]; false = not converged
+template <int N>
+TBK_HD bool small_tridiag_ql(double d[N], double e[N], double z[N][N]) {
+  const double eps = 1.1102230246251565e-16;
   TBK_UNROLL
   for (int r = 0; r < N; ++r) {
     TBK_UNROLL
@@ -330,7 +332,12 @@ TBK_HD bool eigh_small_ql(cplx a[N][N], double ev[N], cplx w[N][N]) {
       }
     }
   }
-  // ---- eigenvectors of H: x = H_0 H_1 ... H_{N-2} z_c, row b of w = eigenvector b
+  return ok;
+}
+
+// (3) eigenvectors of H: x = H_0 H_1 ... H_{N-2} z_c, row b of w = eigenvector b
+template <int N>
+TBK_HD void small_backtransform(const cplx a[N][N], const cplx tau[N], const double d[N], const double z[N][N], double ev[N], cplx w[N][N]) {
   TBK_UNROLL
   for (int b = 0; b < N; ++b) {
     cplx x[N];
@@ -350,6 +357,167 @@ TBK_HD bool eigh_small_ql(cplx a[N][N], double ev[N], cplx w[N][N]) {
     TBK_UNROLL
     for (int k = 0; k < N; ++k) w[b][k] = x[k];
   }
+}
+
+template <int N>
+TBK_HD bool eigh_small_ql(cplx a[N][N], double ev[N], cplx w[N][N]) {
+  double d[N], e[N];
+  cplx tau[N];
+  small_hetd2<N>(a, d, e, tau);
+  double z[N][N];
+  const bool ok = small_tridiag_ql<N>(d, e, z);
+  small_backtransform<N>(a, tau, d, z, ev, w);
+  return ok;
+}
+
+// ---------------------------------------------------------------------------
+// N = 4, direct solver of the real symmetric tridiagonal (d, e) — the hot path of the Kane-Mele mesh kernel.
+// The implicit-QL iteration above is a serial dependency chain (shift, rotation, rotation, ... ~7 iterations per
+// matrix): ncu r11 showed 56 % of the kernel's FP64 instructions in it at an ILP of about one.  Here instead:
+//   eigenvalues   roots of the characteristic quartic in closed form (Ferrari: largest root of the resolvent cubic by
+//                 the trigonometric formula — float acos / cos, ~1e-7, is plenty because —) two Newton steps per root
+//                 on the Sturm recurrence p_k = (d_k - x) p_{k-1} - e_{k-1}^2 p_{k-2} restore full accuracy
+//                 (four independent chains);
+//   eigenvectors  the column of adj(T - lambda) with the largest diagonal entry (the twisted factorisation's choice
+//                 of the twist index, written with leading / trailing minors: no divisions).
+// Valid while the roots are simple and not too close: the function returns false — and the caller takes the QL lane —
+// unless min gap > 1e-3 x (largest - smallest root) and everything is finite.  (Kramers pairs at the TRIM points, band
+// crossings, diagonal / zero matrices go there; on the 1024 x 1024 Kane-Mele mesh that is ~50 of 10^6 points.)
+// Measured on random, clustered and decoupled spectra (tests/test_hostemu_math.py): eigenvalues to 2e-15 x |T|,
+// residuals 1e-15, orthogonality <= 2e-13 at the gap threshold (~ eps / relative gap).
+// lam ascending; column c of z = eigenvector of lam[c], as small_tridiag_ql returns them.
+// ---------------------------------------------------------------------------
+TBK_HD bool small_tridiag4_direct(const double d[4], const double e[4], double lam[4], double z[4][4]) {
+  const double mu = 0.25 * ((d[0] + d[1]) + (d[2] + d[3]));
+  const double t0 = d[0] - mu, t1 = d[1] - mu, t2 = d[2] - mu, t3 = d[3] - mu;
+  const double e0 = e[0], e1 = e[1], e2 = e[2];
+  const double f0 = e0 * e0, f1 = e1 * e1, f2 = e2 * e2;
+  // x^4 + a2 x^2 + a1 x + a0 (the shift by the mean removes the cubic term)
+  const double s01 = t0 * t1, s23 = t2 * t3, u01 = t0 + t1, u23 = t2 + t3;
+  const double a2 = s01 + s23 + u01 * u23 - (f0 + f1 + f2);
+  const double a1 = f0 * u23 + f1 * (t0 + t3) + f2 * u01 - (s01 * u23 + s23 * u01);
+  const double a0 = s01 * s23 - f0 * s23 - f1 * (t0 * t3) - f2 * s01 + f0 * f2;
+  // resolvent cubic  zz^3 + 2 a2 zz^2 + (a2^2 - 4 a0) zz - a1^2 = 0, largest root: zz = 2 r cos(theta / 3) - 2 a2 / 3
+  const double pp = a2 * a2 * (1.0 / 9.0) + a0 * (4.0 / 3.0);                 // -P/3 of the depressed cubic
+  const double qq = a1 * a1 + a2 * a2 * a2 * (2.0 / 27.0) - a2 * a0 * (8.0 / 3.0);   // -Q
+  if (!(pp > 1.0e-290)) return false;
+  double rs;
+  const double r = sqrt_fast(pp, &rs);
+  double c = 0.5 * qq * rs * rs * rs;                                          // cos(theta) = -Q / (2 r^3)
+  c = c > 1.0 ? 1.0 : (c < -1.0 ? -1.0 : c);
+  double y = (double)cosf(acosf((float)c) * (1.0f / 3.0f));                    // in [1/2, 1]
+  {
+    // one Newton step on 4 y^3 - 3 y = c (denominator 12 y^2 - 3 >= 0, = 0 only at the double root y = 1/2)
+    const double den = fma(12.0 * y, y, -3.0);
+    if (den > 1.0e-3) y -= (fma(4.0 * y * y, y, -3.0 * y) - c) * rcp_fast(den);
+  }
+  const double zz = fma(2.0 * r, y, a2 * (-2.0 / 3.0));
+  if (!(zz > 1.0e-290)) return false;
+  // x^4 + a2 x^2 + a1 x + a0 = (x^2 + s x + tt)(x^2 - s x + uu),  s^2 = zz, tt + uu = a2 + zz, s (uu - tt) = a1
+  double rsz;
+  const double sgm = sqrt_fast(zz, &rsz);
+  const double qd = a1 * rsz;
+  const double tt = 0.5 * (a2 + zz - qd), uu = 0.5 * (a2 + zz + qd);
+  const double D1 = fma(-4.0, tt, zz), D2 = fma(-4.0, uu, zz);
+  const double q1 = sqrt(D1 > 0.0 ? D1 : 0.0), q2 = sqrt(D2 > 0.0 ? D2 : 0.0);
+  double x[4] = {0.5 * (-sgm - q1), 0.5 * (-sgm + q1), 0.5 * (sgm - q2), 0.5 * (sgm + q2)};
+  // ascending (x[0] <= x[1], x[2] <= x[3] already): three compare-exchanges
+  { const double lo = fmin(x[0], x[2]), hi = fmax(x[0], x[2]); x[0] = lo; x[2] = hi; }
+  { const double lo = fmin(x[1], x[3]), hi = fmax(x[1], x[3]); x[1] = lo; x[3] = hi; }
+  { const double lo = fmin(x[1], x[2]), hi = fmax(x[1], x[2]); x[1] = lo; x[2] = hi; }
+  // two Newton steps per root on the Sturm recurrence (p_4 and its derivative).  The size of the SECOND step is the
+  // convergence test: at a simple, separated root the first step leaves ~1e-10 and the second is ~1e-18 of the
+  // spectrum's width; near a (nearly) multiple root the closed form is only good to ~sqrt(eps), Newton converges
+  // linearly, the step stays large — and the roots it would return can be split far enough to pass the gap test below.
+  double worst = 0.0;
+  TBK_UNROLL
+  for (int it = 0; it < 2; ++it) {
+    TBK_UNROLL
+    for (int b = 0; b < 4; ++b) {
+      const double l = x[b];
+      const double g0 = t0 - l, g1 = t1 - l, g2 = t2 - l, g3 = t3 - l;
+      const double p1 = g0;
+      const double p2 = fma(g1, p1, -f0), dp2 = -(p1 + g1);
+      const double p3 = fma(g2, p2, -f1 * p1), dp3 = fma(g2, dp2, f1 - p2);
+      const double p4 = fma(g3, p3, -f2 * p2), dp4 = fma(g3, dp3, -(p3 + f2 * dp2));
+      const double ad = fabs(dp4);
+      const double step = ad > 1.0e-290 ? p4 * rcp_fast(dp4) : INFINITY;
+      x[b] = l - step;
+      if (it == 1) worst = fmax(worst, fabs(step));
+    }
+  }
+  const double spread = x[3] - x[0];
+  const double g01 = x[1] - x[0], g12 = x[2] - x[1], g23 = x[3] - x[2];
+  const double mingap = fmin(g01, fmin(g12, g23));
+  if (!(mingap > 1.0e-3 * spread) || !(spread < 1.0e150) || !(worst < 1.0e-8 * spread)) return false;   // (NaN anywhere: false)
+  // eigenvectors: column k of adj(T - lambda), k = argmax |P_k Q_{k+1}| (P: leading, Q: trailing principal minors)
+  const double e01 = e0 * e1, e12 = e1 * e2, e012 = e01 * e2;
+  TBK_UNROLL
+  for (int b = 0; b < 4; ++b) {
+    const double l = x[b];
+    const double g0 = t0 - l, g1 = t1 - l, g2 = t2 - l, g3 = t3 - l;
+    const double p1 = g0, p2 = fma(g1, p1, -f0), p3 = fma(g2, p2, -f1 * p1);
+    const double r4 = g3, r3 = fma(g2, r4, -f2), r2 = fma(g1, r3, -f1 * r4);   // trailing minors Q_3, Q_2, Q_1
+    const double c0 = r2, c1 = p1 * r3, c2 = p2 * r4, c3 = p3;
+    const double m0 = fabs(c0), m1 = fabs(c1), m2 = fabs(c2), m3 = fabs(c3);
+    const bool hi = fmax(m2, m3) > fmax(m0, m1);
+    const bool odd = hi ? (m3 > m2) : (m1 > m0);
+    // candidates: k = 0: ( r2, -e0 r3, e01 r4, -e012 )   k = 1: ( -e0 r3, p1 r3, -p1 e1 r4, p1 e12 )
+    //             k = 2: ( e01 r4, -p1 e1 r4, p2 r4, -p2 e2 )   k = 3: ( -e012, p1 e12, -p2 e2, p3 )
+    const double v0 = hi ? (odd ? -e012 : e01 * r4) : (odd ? -e0 * r3 : r2);
+    const double v1 = hi ? (odd ? p1 * e12 : -p1 * e1 * r4) : (odd ? c1 : -e0 * r3);
+    const double v2 = hi ? (odd ? -p2 * e2 : c2) : (odd ? -p1 * e1 * r4 : e01 * r4);
+    const double v3 = hi ? (odd ? p3 : -p2 * e2) : (odd ? p1 * e12 : -e012);
+    const double n2 = (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
+    if (!(n2 > 1.0e-280) || !(n2 < 1.0e280)) return false;
+    const double inv = rsqrt_fast(n2);
+    z[0][b] = v0 * inv; z[1][b] = v1 * inv; z[2][b] = v2 * inv; z[3][b] = v3 * inv;
+    lam[b] = l + mu;
+  }
+  return true;
+}
+
+// the QL lane of the N = 4 solver, out of line (cold): arrays through local memory
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+bool small_tridiag_ql4_cold(double* d, double* e, double* zflat) {
+  double dd[4], ee[4], zz[4][4];
+  for (int i = 0; i < 4; ++i) { dd[i] = d[i]; ee[i] = e[i]; }
+  const bool ok = small_tridiag_ql<4>(dd, ee, zz);
+  for (int i = 0; i < 4; ++i) {
+    d[i] = dd[i];
+    for (int j = 0; j < 4; ++j) zflat[4 * i + j] = zz[i][j];
+  }
+  return ok;
+}
+
+// N = 4 direct solver: Householder, closed-form tridiagonal solver with the QL lane behind it, back-transformation
+TBK_HD bool eigh4_direct(cplx a[4][4], double ev[4], cplx w[4][4], int* lane_taken = nullptr) {
+  double d[4], e[4];
+  cplx tau[4];
+  small_hetd2<4>(a, d, e, tau);
+  double lam[4], z[4][4];
+  bool ok = true;
+  const bool fast = small_tridiag4_direct(d, e, lam, z);
+  if (lane_taken) *lane_taken = fast ? 0 : 1;
+  if (!fast) {
+    // (every index below must be a compile-time constant: a rolled loop would index d / z dynamically and move them —
+    // and with them the hot path's working set — to local memory)
+    double dc[4], ec[4], zc[16];
+    TBK_UNROLL
+    for (int i = 0; i < 4; ++i) { dc[i] = d[i]; ec[i] = e[i]; }
+    ok = small_tridiag_ql4_cold(dc, ec, zc);
+    TBK_UNROLL
+    for (int i = 0; i < 4; ++i) {
+      lam[i] = dc[i];
+      TBK_UNROLL
+      for (int j = 0; j < 4; ++j) z[i][j] = zc[4 * i + j];
+    }
+  }
+  small_backtransform<4>(a, tau, lam, z, ev, w);
   return ok;
 }
 
@@ -378,7 +546,10 @@ TBK_HD void eigh_small(const double dg_in[N], const cplx lo_in[N * (N - 1) / 2],
     TBK_UNROLL
     for (int c = 0; c < N; ++c) a[r][c] = c < r ? lo_in[r * (r - 1) / 2 + c] : mk(c == r ? dg_in[r] : 0.0, 0.0);
   }
-  if (!eigh_small_ql<N>(a, ev, w)) eigh_small_jacobi_fallback<N>(dg_in, lo_in, ev, w);
+  bool ok;
+  if constexpr (N == 4) ok = eigh4_direct(a, ev, w);
+  else ok = eigh_small_ql<N>(a, ev, w);
+  if (!ok) eigh_small_jacobi_fallback<N>(dg_in, lo_in, ev, w);
 }
 
 }  // namespace tbk

@@ -171,6 +171,18 @@ int emu_small_ql(int n, const double* H, double* ev, double* w) {
   return -1;
 }
 
+// the N = 4 solver of the mesh kernels (closed-form tridiagonal solver + QL lane): returns 0 = fast lane, 1 = QL lane,
+// -1 = the QL lane did not converge
+int emu_eigh4_direct(const double* H, double* ev, double* w) {
+  const cplx* h = (const cplx*)H;
+  cplx a[4][4]; cplx ww[4][4];
+  for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) a[r][c] = h[r * 4 + c];
+  int lane = 0;
+  const bool ok = eigh4_direct(a, ev, ww, &lane);
+  std::memcpy(w, ww, sizeof(ww));
+  return ok ? lane : -1;
+}
+
 // A: n x n column-major with leading dimension lda (lower triangle valid).
 // Outputs: ev[n] ascending, evec[n][n] rows = eigenvectors (reference layout).
 int emu_heev_group(int n, double* A, int lda, int want_vec, double* ev, double* evec) {

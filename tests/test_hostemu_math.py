@@ -106,6 +106,59 @@ def test_small_direct_solver(n):
         _check_eig(h, ev, w)
 
 
+def test_small_direct_solver_n4():
+    """eigh4_direct, the n = 4 solver of the mesh kernels: closed-form roots of the tridiagonal's quartic + Newton on the
+    Sturm recurrence + adjugate-column eigenvectors, with the implicit-QL lane behind it for close or multiple roots.
+    Both lanes must meet the same tolerances; generic spectra must stay on the fast lane."""
+    lib = hostemu.lib()
+    rng = np.random.RandomState(44)
+
+    def with_spectrum(lam):
+        a = rng.randn(4, 4) + 1j * rng.randn(4, 4)
+        q, _ = np.linalg.qr(a)
+        h = (q * np.asarray(lam)) @ q.conj().T
+        return 0.5 * (h + h.conj().T)
+
+    def run(h):
+        ev = np.zeros(4)
+        w = np.zeros((4, 4), dtype=complex)
+        hc = np.ascontiguousarray(h, dtype=complex)
+        lane = lib.emu_eigh4_direct(_p(hc.view(np.float64)), _p(ev), _p(w.view(np.float64)))
+        assert lane in (0, 1)
+        _check_eig(h, ev, w)
+        return lane
+
+    generic = [_rand_herm(rng, 4) for _ in range(2000)]
+    lanes = [run(h) for h in generic]
+    assert np.mean(lanes) < 0.03                                   # almost always the fast lane
+    for gap in (1e-1, 1e-2, 2e-3, 1e-3, 5e-4, 1e-4, 1e-6, 1e-9, 1e-12, 0.0):
+        for _ in range(100):
+            a, b, c = rng.randn(3)
+            run(with_spectrum([a, a + gap, b, c]))
+            run(with_spectrum([a, a + gap, b, b + gap]))
+            run(with_spectrum([a, a + gap, a + 2 * gap, b]))
+    special = [np.diag(rng.randn(4)).astype(complex), np.zeros((4, 4), dtype=complex), np.eye(4, dtype=complex) * 3.0,
+               1e-9 * _rand_herm(rng, 4) + np.eye(4), 1e6 * _rand_herm(rng, 4), 1e-9 * _rand_herm(rng, 4),
+               _rand_herm(rng, 4) + 1e3 * np.eye(4), np.kron(_rand_herm(rng, 2), np.eye(2)), np.kron(np.eye(2), _rand_herm(rng, 2))]
+    tri = np.diag(rng.randn(4)).astype(complex) + np.diag(rng.randn(3) + 1j * rng.randn(3), -1)
+    special.append(tri + np.tril(tri, -1).conj().T)
+    blk = np.zeros((4, 4), dtype=complex)
+    blk[:2, :2] = _rand_herm(rng, 2); blk[2:, 2:] = _rand_herm(rng, 2)
+    special.append(blk)
+    for h in special:
+        run(h)
+    # the Kane-Mele model of the headline workload on a mesh through the TRIM points (exact Kramers pairs there)
+    import pythtb_b200 as tb
+    from tests import models as M
+    from oracle import pythtb_oracle as orc
+    km = M.kane_mele(tb, "odd")
+    nk = 33
+    kpts = np.array([[i / (nk - 1) - 0.5, j / (nk - 1) - 0.5] for i in range(nk) for j in range(nk)])
+    hams = orc.gen_ham(km, kpts)
+    lanes = [run(hams[i].reshape(4, 4)) for i in range(len(kpts))]
+    assert np.mean(lanes) < 0.02
+
+
 @pytest.mark.parametrize("n", [1, 2, 5, 8, 17, 32, 40, 64])
 def test_group_heev(n):
     lib = hostemu.lib()
