@@ -383,7 +383,7 @@ TBK_HD bool eigh_small_ql(cplx a[N][N], double ev[N], cplx w[N][N]) {
 // Valid while the roots are simple and not too close: the function returns false — and the caller takes the QL lane —
 // unless min gap > 1e-3 x (largest - smallest root) and everything is finite.  (Kramers pairs at the TRIM points, band
 // crossings, diagonal / zero matrices go there; on the 1024 x 1024 Kane-Mele mesh that is ~50 of 10^6 points.)
-// Measured on random, clustered and decoupled spectra (tests/test_hostemu_math.py): eigenvalues to 2e-15 x |T|,
+// Measured on random, clustered and decoupled spectra (tests/hostemu: test_small_direct_solver_n4): eigenvalues to 2e-15 x |T|,
 // residuals 1e-15, orthogonality <= 2e-13 at the gap threshold (~ eps / relative gap).
 // lam ascending; column c of z = eigenvector of lam[c], as small_tridiag_ql returns them.
 // ---------------------------------------------------------------------------
