@@ -711,6 +711,11 @@ TBK_HD void tridiag_shifted_solve(int n, const double* d, const double* e, doubl
   for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(Y[(size_t)i * nt + t]));
   const double sc = mx > 0.0 ? 1.0 / mx : 1.0;
   double ak = d[0] - lam, bk = n > 1 ? e[0] : 0.0, yk = Y[t] * sc;
+  // (both sweeps are serial chains in registers fed by loads whose addresses do not depend on the chain: unrolled, the
+  // loads of the next steps are issued while the current pivot's division is still in flight)
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
   for (int k = 0; k < n - 1; ++k) {
     const double c = e[k], a1 = d[k + 1] - lam, b1 = k + 1 < n - 1 ? e[k + 1] : 0.0;
     const double y1 = Y[(size_t)(k + 1) * nt + t] * sc;
@@ -730,6 +735,9 @@ TBK_HD void tridiag_shifted_solve(int n, const double* d, const double* e, doubl
     U0[at] = ak; U1[at] = 0.0; U2[at] = 0.0; Y[at] = yk;
   }
   double x1 = 0.0, x2 = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
   for (int k = n - 1; k >= 0; --k) {
     const size_t at = (size_t)k * nt + t;
     double piv = U0[at];
