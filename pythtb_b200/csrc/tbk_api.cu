@@ -247,12 +247,50 @@ int tbk_model_create(const tbk_model_desc* d, tbk_model** out) {
           ds.mask[p] |= 1u << e;
       }
   }
+  // ---- nsta = 5..8: dense REAL coefficient table for the tensor-pipe Hamiltonian assembly of the eigenvalue sweeps
+  // (solve_reg_gemm_kernel):  [Re H_e; Im H_e](k) = A [cos 2 pi k.R_p; sin 2 pi k.R_p; 1], rows m < NP = Re of the packed
+  // lower-triangle element m, rows NP + m = Im; columns 2p / 2p + 1 = cos / sin of phase p, column 2 nph = constant terms.
+  // amp E = (ar c - ai s) + i (ar s + ai c),  amp conj(E) = (ar c + ai s) + i (ai c - ar s).
+  // Stored in mma.sync.m8n8k4 A-fragment order: tab[(mt * KS + ks) * 32 + lane] = A[8 mt + lane / 4][4 ks + lane % 4].
+  m->gemm_tab = nullptr; m->gemm_ks = 0;
+  if (d->nsta >= 5 && d->nsta <= 8 && d->dim_k >= 1 && (2 * d->nph + 1 + 3) / 4 <= kGemmMaxKS) {
+    const int NP = d->nsta * (d->nsta + 1) / 2, MT = (2 * NP + 7) / 8, KS = (2 * d->nph + 1 + 3) / 4, K = 4 * KS;
+    std::vector<double> A((size_t)MT * 8 * K, 0.0);
+    for (int p = 0; p <= d->nph; ++p) {
+      for (int t = d->pm_ptr[p]; t < d->pm_ptr[p + 1]; ++t) {
+        const int e = d->pm_el[t] & TBK_PH_MASK;
+        const bool cj = (d->pm_el[t] & TBK_PH_CONJ) != 0;
+        const int r = d->el_row[e], c = d->el_col[e];
+        const int pk = r * (r + 1) / 2 + c;
+        const double ar = d->pm_amp[2 * t], ai = d->pm_amp[2 * t + 1];
+        double* re = A.data() + (size_t)pk * K;
+        double* im = A.data() + (size_t)(NP + pk) * K;
+        if (p == d->nph) { re[2 * d->nph] += ar; im[2 * d->nph] += ai; }
+        else if (!cj) { re[2 * p] += ar; re[2 * p + 1] -= ai; im[2 * p] += ai; im[2 * p + 1] += ar; }
+        else { re[2 * p] += ar; re[2 * p + 1] += ai; im[2 * p] += ai; im[2 * p + 1] -= ar; }
+      }
+    }
+    std::vector<double> frag((size_t)MT * KS * 32);
+    for (int mt = 0; mt < MT; ++mt)
+      for (int ks = 0; ks < KS; ++ks)
+        for (int lane = 0; lane < 32; ++lane)
+          frag[((size_t)mt * KS + ks) * 32 + lane] = A[(size_t)(8 * mt + lane / 4) * K + 4 * ks + lane % 4];
+    if (cudaMalloc(&m->gemm_tab, frag.size() * 8) == cudaSuccess &&
+        cudaMemcpy(m->gemm_tab, frag.data(), frag.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess) {
+      m->gemm_ks = KS;
+    } else {
+      cudaGetLastError();
+      if (m->gemm_tab) cudaFree(m->gemm_tab);
+      m->gemm_tab = nullptr;                 // not fatal: the scalar assembly is used instead
+    }
+  }
   *out = m;
   return TBK_OK;
 }
 
 int tbk_model_destroy(tbk_model* m) {
   if (!m) return TBK_OK;
+  if (m->gemm_tab) cudaFree(m->gemm_tab);
   cudaFree(m->blob);
   delete m;
   return TBK_OK;

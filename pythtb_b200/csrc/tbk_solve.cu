@@ -301,6 +301,179 @@ solve_small_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long lon
 }
 
 // ===========================================================================
+// Eigenvalues only, N = 5..8 (band-structure sweeps of small Wannier models: BASELINE configs[2], silicon on 256^3):
+// one k-point per thread, eigensolver in registers (eigvals_small<N>).
+// H(k), element-major: a thread first tabulates E_p = exp(2 pi i k.R_p) of its k-point for every unique lattice vector in
+// its own column of a shared-memory table ([nph][128]: conflict-free), then accumulates every lower-triangle element in a
+// REGISTER over that element's term list (amplitude and phase index are warp-uniform read-only loads, batched by the
+// unrolled loop; one 16-byte shared-memory read of the phase per term).  The element loop is unrolled over the
+// compile-time (row, column) pairs so that the matrix never leaves registers.  (A phase-major version that accumulated
+// into shared memory was measured 3x slower: every term was a load - FMA - store round trip behind an L2-latency load.)
+// The cooperative solver this replaces (8 lanes per matrix, matrix in shared memory, a barrier per phase of
+// the Householder / QL steps) spent ~2600 SM cycles per n = 8 matrix in the eigensolver alone (profiles/split_cfg3.py).
+// ===========================================================================
+constexpr int kRegThreads = 128;
+template <int N>
+__global__ void __launch_bounds__(kRegThreads)
+solve_reg_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long long npts, OutSpec out) {
+  constexpr int NP = N * (N + 1) / 2;
+  extern __shared__ __align__(16) char smem[];
+  cplx* ph = (cplx*)smem;                              // [nph][kRegThreads]: phases of this thread's k-point in column tid
+  int* elmap = (int*)(ph + (size_t)(hsrc ? 0 : pv.nph) * kRegThreads);   // [NP] plan element of the packed lower index, or -1
+  const int tid = threadIdx.x;
+  if (hsrc == nullptr) {
+    for (int e = tid; e < NP; e += kRegThreads) elmap[e] = -1;
+    __syncthreads();
+    for (int e = tid; e < pv.nel; e += kRegThreads) { const int r = pv.el_row[e], c = pv.el_col[e]; elmap[r * (r + 1) / 2 + c] = e; }
+    __syncthreads();
+  }
+  const cplx* __restrict__ t_amp = (const cplx*)pv.t_amp;
+  const int* __restrict__ t_ph = pv.t_ph;
+  for (long long base = (long long)blockIdx.x * kRegThreads; base < npts; base += (long long)gridDim.x * kRegThreads) {
+    const long long idx = base + tid;
+    const bool active = idx < npts;
+    cplx a[N][N];
+    if (hsrc != nullptr) {
+      if (active) {
+        const cplx* h = hsrc + idx * (long long)(N * N);
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+          for (int c = 0; c <= r; ++c) a[r][c] = h[r * N + c];
+      }
+    } else if (active) {
+      int mi[TBK_MAX_DIM] = {0, 0, 0, 0};
+      double k[TBK_MAX_DIM] = {0.0, 0.0, 0.0, 0.0};
+      load_k(ks, idx, mi, k);
+      for (int p = 0; p < pv.nph; ++p) {
+        double x = 0.0;
+        for (int d = 0; d < pv.dim_k; ++d) x = fma(k[d], pv.ph_R[p * pv.dim_k + d], x);
+        ph[p * kRegThreads + tid] = expi_turns(x);
+      }
+#pragma unroll
+      for (int r = 0; r < N; ++r) {
+#pragma unroll
+        for (int c = 0; c <= r; ++c) {
+          cplx acc = mk(0.0, 0.0);
+          const int pe = elmap[r * (r + 1) / 2 + c];
+          if (pe >= 0) {
+            const int t1 = pv.el_ptr[pe + 1];
+#pragma unroll 4
+            for (int t = pv.el_ptr[pe]; t < t1; ++t) {
+              const int p = __ldg(t_ph + t);
+              const double2 av = __ldg(reinterpret_cast<const double2*>(t_amp + t));
+              cplx z = mk(1.0, 0.0);
+              if (p >= 0) {
+                z = ph[(p & TBK_PH_MASK) * kRegThreads + tid];
+                if (p & TBK_PH_CONJ) z.im = -z.im;
+              }
+              fma_acc(acc, mk(av.x, av.y), z);
+            }
+          }
+          a[r][c] = acc;
+        }
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int r = 0; r < N; ++r) a[r][r].im = 0.0;
+      double ev[N];
+      const bool ok = eigvals_small<N>(a, ev);
+      if (out.eval) {
+#pragma unroll
+        for (int b = 0; b < N; ++b) out.eval[b * out.ev_sb + idx * out.ev_sk] = ok ? ev[b] : NAN;   // not converged: poisoned
+      }
+    }
+  }
+}
+
+// ===========================================================================
+// The same sweep with the Hamiltonian assembled on the FP64 TENSOR PIPE.  With the phases as cos / sin pairs the
+// assembly is a real matrix product,  [Re H; Im H] (2 NP x k-points) = A (2 NP x (2 nph + 1)) . [cos; sin; 1],  A being the
+// model's dense coefficient table (tbk_api.cu, stored in mma.sync.m8n8k4 A-fragment order: one coalesced 256-byte load
+// per fragment).  A CTA of 4 warps handles 128 k-points per pass; every thread tabulates the cos / sin column of ITS
+// k-point in shared memory (B operand, leading dimension 132 = 4 mod 16: conflict-free 8-byte fragment reads), every WARP
+// multiplies the table into the 32 columns of its own threads (MT x 4 accumulator tiles in registers), writes the result
+// back over those columns and each thread picks its matrix up from its column — the only synchronisation is __syncwarp.
+// A scalar assembly reads one 16-byte phase from shared memory per term: 53 KB per k-point for the silicon model
+// (3348 terms), which alone costs the 1.5 ms per 2^20 k-points that the whole kernel now takes; here the phases are read
+// 768 bytes per k-point and the 27 DMMA per k-point take ~110 SM cycles.
+// ===========================================================================
+constexpr int kRegLDB = 132;
+template <int N>
+__global__ void __launch_bounds__(kRegThreads)
+solve_reg_gemm_kernel(PlanView pv, KSrc ks, long long npts, OutSpec out, const double* __restrict__ tab, int KS) {
+  constexpr int NP = N * (N + 1) / 2;
+  constexpr int MT = (2 * NP + 7) / 8;
+  extern __shared__ __align__(16) char smem[];
+  double* Bs = (double*)smem;                          // [max(4 KS, 8 MT)][kRegLDB]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int nph = pv.nph;
+  for (long long base = (long long)blockIdx.x * kRegThreads; base < npts; base += (long long)gridDim.x * kRegThreads) {
+    const bool active = base + tid < npts;
+    const long long idx = active ? base + tid : npts - 1;         // idle lanes repeat the last point (they take part in the MMAs)
+    {
+      int mi[TBK_MAX_DIM] = {0, 0, 0, 0};
+      double k[TBK_MAX_DIM] = {0.0, 0.0, 0.0, 0.0};
+      load_k(ks, idx, mi, k);
+      for (int p = 0; p < nph; ++p) {
+        double x = 0.0;
+        for (int d = 0; d < pv.dim_k; ++d) x = fma(k[d], pv.ph_R[p * pv.dim_k + d], x);
+        const cplx z = expi_turns(x);
+        Bs[(2 * p) * kRegLDB + tid] = z.re;
+        Bs[(2 * p + 1) * kRegLDB + tid] = z.im;
+      }
+      Bs[(2 * nph) * kRegLDB + tid] = 1.0;
+      for (int kk = 2 * nph + 1; kk < 4 * KS; ++kk) Bs[kk * kRegLDB + tid] = 0.0;
+    }
+    __syncwarp();
+    double acc[MT][4][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { acc[mt][j][0] = 0.0; acc[mt][j][1] = 0.0; }
+    const double* bcol = Bs + 32 * warp + g;
+#pragma unroll 2
+    for (int ksi = 0; ksi < KS; ++ksi) {
+      double afr[MT], bfr[4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) afr[mt] = __ldg(tab + ((size_t)(mt * KS + ksi) * 32 + lane));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bfr[j] = bcol[(ksi * 4 + q) * kRegLDB + 8 * j];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) blk_dmma(acc[mt][j][0], acc[mt][j][1], afr[mt], bfr[j]);
+    }
+    __syncwarp();                                      // every lane of the warp is done with the warp's columns of Bs
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double* dst = Bs + (mt * 8 + g) * kRegLDB + 32 * warp + 8 * j + 2 * q;
+        dst[0] = acc[mt][j][0];
+        dst[1] = acc[mt][j][1];
+      }
+    __syncwarp();
+    cplx a[N][N];
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+      for (int c = 0; c <= r; ++c) {
+        const int pk = r * (r + 1) / 2 + c;
+        a[r][c] = mk(Bs[pk * kRegLDB + tid], c == r ? 0.0 : Bs[(NP + pk) * kRegLDB + tid]);
+      }
+    __syncwarp();                                      // the columns are free for the next pass
+    double ev[N];
+    const bool ok = eigvals_small<N>(a, ev);
+    if (active && out.eval) {
+#pragma unroll
+      for (int b = 0; b < N; ++b) out.eval[b * out.ev_sb + idx * out.ev_sk] = ok ? ev[b] : NAN;
+    }
+  }
+}
+
+// ===========================================================================
 // One k-point per thread group, matrix in shared memory or in a workspace
 // ===========================================================================
 struct GroupShape {
@@ -783,7 +956,8 @@ static size_t small_plan_smem(const PlanView& pv, int n) {
 static int block_threads_for(int n) { return n <= 64 ? 64 : (n <= 128 ? 128 : 256); }
 
 static int launch_solve(const PlanView& pv, const KSrc& ks, const cplx* hsrc, int n, long long npts,
-                        const OutSpec& out, int want_vec, void* ws, size_t ws_bytes, cudaStream_t st) {
+                        const OutSpec& out, int want_vec, void* ws, size_t ws_bytes, cudaStream_t st,
+                        const double* gemm_tab = nullptr, int gemm_ks = 0) {
   if (npts <= 0) return TBK_OK;
   if (n <= 4 && n >= 2) {
     const size_t sm = hsrc ? 0 : small_plan_smem(pv, n);
@@ -799,6 +973,64 @@ static int launch_solve(const PlanView& pv, const KSrc& ks, const cplx* hsrc, in
     return TBK_OK;
   }
   const int nph = hsrc ? 0 : pv.nph;
+  {
+    // eigenvalues only, n = 5..8: one k-point per thread, eigensolver in registers (TBK_REG_EIGVALS=0: the tile solver)
+    static int reg_on = -1;
+    if (reg_on < 0) { const char* e = getenv("TBK_REG_EIGVALS"); reg_on = (e && atoi(e) == 0) ? 0 : 1; }
+    static int gemm_on = -1;                           // TBK_REG_GEMM=0: scalar assembly (A/B knob)
+    if (gemm_on < 0) { const char* e = getenv("TBK_REG_GEMM"); gemm_on = (e && atoi(e) == 0) ? 0 : 1; }
+    if (reg_on && gemm_on && gemm_tab != nullptr && hsrc == nullptr && n >= 5 && n <= 8 && !want_vec && out.mode == 0 &&
+        out.eval != nullptr && npts > 0) {
+      const int MT = (n * (n + 1) + 7) / 8;
+      const int rows = 4 * gemm_ks > 8 * MT ? 4 * gemm_ks : 8 * MT;
+      const size_t dyn = (size_t)rows * kRegLDB * 8;
+      if (dyn + 1024 <= (size_t)kMaxSmem) {
+        int per_sm = (int)((size_t)kMaxSmem / (dyn + 1024));
+        if (per_sm > 2) per_sm = 2;
+        long long blocks = (npts + kRegThreads - 1) / kRegThreads;
+        if (blocks > (long long)kNumSM * per_sm) blocks = (long long)kNumSM * per_sm;
+#define TBK_REGG_LAUNCH(NN)                                                                                             \
+        do {                                                                                                            \
+          TBK_CUDA(cudaFuncSetAttribute(solve_reg_gemm_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+          solve_reg_gemm_kernel<NN><<<(unsigned)blocks, kRegThreads, dyn, st>>>(pv, ks, npts, out, gemm_tab, gemm_ks);  \
+        } while (0)
+        switch (n) {
+          case 5: TBK_REGG_LAUNCH(5); break;
+          case 6: TBK_REGG_LAUNCH(6); break;
+          case 7: TBK_REGG_LAUNCH(7); break;
+          default: TBK_REGG_LAUNCH(8); break;
+        }
+#undef TBK_REGG_LAUNCH
+        TBK_LAUNCH_CHECK("solve_reg_gemm_kernel");
+        note_kernel("solve_reg_gemm_kernel");
+        return TBK_OK;
+      }
+    }
+    if (reg_on && n >= 5 && n <= 8 && !want_vec && out.mode == 0 && out.eval != nullptr &&
+        (size_t)nph * kRegThreads * 16 + 1024 <= (size_t)kMaxSmem) {
+      const size_t dyn = (size_t)nph * kRegThreads * 16 + (size_t)(n * (n + 1) / 2) * 4 + 16;    // phase table + element map
+      int per_sm = (int)((size_t)kMaxSmem / (dyn + 1024));
+      if (per_sm > 4) per_sm = 4;
+      if (per_sm < 1) per_sm = 1;
+      long long blocks = (npts + kRegThreads - 1) / kRegThreads;
+      if (blocks > (long long)kNumSM * per_sm) blocks = (long long)kNumSM * per_sm;
+#define TBK_REG_LAUNCH(NN)                                                                                          \
+      do {                                                                                                          \
+        TBK_CUDA(cudaFuncSetAttribute(solve_reg_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+        solve_reg_kernel<NN><<<(unsigned)blocks, kRegThreads, dyn, st>>>(pv, ks, hsrc, npts, out);                  \
+      } while (0)
+      switch (n) {
+        case 5: TBK_REG_LAUNCH(5); break;
+        case 6: TBK_REG_LAUNCH(6); break;
+        case 7: TBK_REG_LAUNCH(7); break;
+        default: TBK_REG_LAUNCH(8); break;
+      }
+#undef TBK_REG_LAUNCH
+      TBK_LAUNCH_CHECK("solve_reg_kernel");
+      note_kernel("solve_reg_kernel");
+      return TBK_OK;
+    }
+  }
   if (n <= 32) {
     const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
     const int mats = 128 / G;
@@ -1060,7 +1292,8 @@ int tbk_solve_k(const tbk_model* m, const double* k_dev, int64_t nk, double* eva
     TBK_LAUNCH_CHECK("solve_n1_kernel");
     return TBK_OK;
   }
-  return launch_solve(m->pv, ks, nullptr, m->pv.nsta, nk, out, want_vec, ws_dev, ws_bytes, (cudaStream_t)stream);
+  return launch_solve(m->pv, ks, nullptr, m->pv.nsta, nk, out, want_vec, ws_dev, ws_bytes, (cudaStream_t)stream,
+                      m->gemm_tab, m->gemm_ks);
 }
 
 // mesh_small_kernel dispatch; returns 1 if it took the job, 0 if the shape does not fit, < 0 on error

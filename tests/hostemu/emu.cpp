@@ -78,6 +78,13 @@ struct TeamGroup {
 
 static int g_hetrd_sym = 1;
 
+template <int N>
+static int emu_eigvals_n(const cplx* h, double* ev) {
+  cplx a[N][N];
+  for (int r = 0; r < N; ++r) for (int c = 0; c < N; ++c) a[r][c] = h[r * N + c];
+  return eigvals_small<N>(a, ev) ? 1 : 0;
+}
+
 extern "C" {
 
 // which tridiagonalisation the emu_heev_blocked* entry points run: 1 = lower triangle only, 0 = full matrix
@@ -167,6 +174,20 @@ int emu_small_ql(int n, const double* H, double* ev, double* w) {
     const bool ok = eigh_small_ql<4>(a, ev, ww);
     std::memcpy(w, ww, sizeof(ww));
     return ok ? 1 : 0;
+  }
+  return -1;
+}
+
+// eigenvalues-only register solver (n = 5..8 band-structure sweeps); returns 1 if the QL iteration converged
+int emu_eigvals_small(int n, const double* H, double* ev) {
+  const cplx* h = (const cplx*)H;
+  switch (n) {
+    case 3: return emu_eigvals_n<3>(h, ev);
+    case 4: return emu_eigvals_n<4>(h, ev);
+    case 5: return emu_eigvals_n<5>(h, ev);
+    case 6: return emu_eigvals_n<6>(h, ev);
+    case 7: return emu_eigvals_n<7>(h, ev);
+    case 8: return emu_eigvals_n<8>(h, ev);
   }
   return -1;
 }

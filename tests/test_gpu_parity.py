@@ -505,7 +505,10 @@ def test_solve_all_on_a_device_generated_mesh():
         assert np.array_equal(ev_e, ev_l) and np.array_equal(vec_e, vec_l) and vec_l.shape == vec_e.shape
         assert np.max(np.abs(model.solve_all(lazy) - orc.solve_all(model, eager))) < 1e-10
         ev_d = model.solve_all(lazy, device_result=True)
-        assert ev_d.is_cuda and np.array_equal(ev_d.cpu().numpy(), ev_e)
+        # (eigenvalues-only calls of 5..8-band models run the register solver, calls with eigenvectors the tile solver:
+        # bit-identical among themselves, equal to rounding between them)
+        assert ev_d.is_cuda and np.array_equal(ev_d.cpu().numpy(), model.solve_all(eager))
+        assert np.max(np.abs(ev_d.cpu().numpy() - ev_e)) < 1e-12 * max(1.0, np.max(np.abs(ev_e)))
     with pytest.raises(Exception, match="wrong shape"):
         M.haldane(mod).solve_all(M.kane_mele(mod, "odd").k_uniform_mesh([3, 3], lazy=True)[:0] if False else
                                  M.random_model(mod, norb=3, dim=1, nhop=5, nspin=1, seed=22).k_uniform_mesh([4], lazy=True))

@@ -106,6 +106,25 @@ def test_small_direct_solver(n):
         _check_eig(h, ev, w)
 
 
+@pytest.mark.parametrize("n", [3, 4, 5, 6, 7, 8])
+def test_small_eigenvalues_only_solver(n):
+    """eigvals_small<N>: the one-matrix-per-thread register solver of eigenvalue-only sweeps (n = 5..8 Wannier models)."""
+    lib = hostemu.lib()
+    rng = np.random.RandomState(70 + n)
+    mats = [_rand_herm(rng, n) for _ in range(300)] + [_rand_herm(rng, n, degenerate=True) for _ in range(60)]
+    mats += [np.diag(rng.randn(n)).astype(complex), np.zeros((n, n), dtype=complex), np.eye(n, dtype=complex) * 3.0,
+             1e-9 * _rand_herm(rng, n) + np.eye(n), 1e6 * _rand_herm(rng, n)]
+    tri = np.diag(rng.randn(n)).astype(complex) + np.diag(rng.randn(n - 1) + 1j * rng.randn(n - 1), -1)
+    mats.append(tri + np.tril(tri, -1).conj().T)
+    for h in mats:
+        ev = np.zeros(n)
+        hc = np.ascontiguousarray(h, dtype=complex)
+        assert lib.emu_eigvals_small(n, _p(hc.view(np.float64)), _p(ev)) == 1
+        scale = max(1.0, np.max(np.abs(h)))
+        assert np.all(np.diff(ev) >= 0)
+        assert np.max(np.abs(ev - np.linalg.eigvalsh(h))) < 1e-12 * scale * n
+
+
 def test_small_direct_solver_n4():
     """eigh4_direct, the n = 4 solver of the mesh kernels: closed-form roots of the tridiagonal's quartic + Newton on the
     Sturm recurrence + adjugate-column eigenvectors, with the implicit-QL lane behind it for close or multiple roots.
