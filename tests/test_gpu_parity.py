@@ -490,6 +490,30 @@ def test_replayed_calls_follow_their_arguments():
     assert np.max(np.abs(b - gaps_ref)) < 1e-10 and abs(a[0] - b[0]) > 1e-3
 
 
+def test_pipelined_host_results_equal_the_single_shot():
+    """solve_all with host results on a long k-list is cut into chunks whose copies overlap the next chunk's kernels
+    (engine.solve_all_host); with a small chunk size the chunked sweep must equal the single-shot one bit for bit —
+    eigenvalues and eigenvectors, last partial chunk included."""
+    mod = _mod()
+    from pythtb_b200 import _engine
+    eng = _engine.get_engine()
+    old = eng.CHUNK_K
+    try:
+        for model in (M.haldane(mod, delta=0.2), M.random_model(mod, norb=8, dim=3, nhop=40, nspin=1, seed=5),
+                      M.random_model(mod, norb=3, dim=2, nhop=8, nspin=2, seed=9)):
+            k = np.random.RandomState(3).rand(3500, model._dim_k)
+            eng.CHUNK_K = 1 << 21
+            ev0 = model.solve_all(k)
+            ev0v, vec0 = model.solve_all(k, eig_vectors=True)
+            eng.CHUNK_K = 1000
+            ev1 = model.solve_all(k)
+            ev1v, vec1 = model.solve_all(k, eig_vectors=True)
+            assert ev1.shape == ev0.shape and np.array_equal(ev0, ev1)
+            assert vec1.shape == vec0.shape and np.array_equal(ev0v, ev1v) and np.array_equal(vec0, vec1)
+    finally:
+        eng.CHUNK_K = old
+
+
 def test_solve_all_on_a_device_generated_mesh():
     """solve_all(k_uniform_mesh(mesh, lazy=True)): k-points generated on the device (tbk_kmesh_uniform) give
     exactly what the host list gives, for values, vectors (spinor layout included) and device-resident results."""
