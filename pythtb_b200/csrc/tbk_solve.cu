@@ -409,6 +409,8 @@ solve_reg_gemm_kernel(PlanView pv, KSrc ks, long long npts, OutSpec out, const d
   double* Bs = (double*)smem;                          // [max(4 KS, 8 MT)][kRegLDB]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   const int nph = pv.nph;
+  // (the lattice vectors stay in global memory: staged in shared memory, the warp-uniform reads of the phase loop made
+  // the kernel 16 % slower — 1.85 instead of 1.59 ms per 2^20 k-points)
   for (long long base = (long long)blockIdx.x * kRegThreads; base < npts; base += (long long)gridDim.x * kRegThreads) {
     const bool active = base + tid < npts;
     const long long idx = active ? base + tid : npts - 1;         // idle lanes repeat the last point (they take part in the MMAs)
