@@ -680,7 +680,8 @@ class B200Engine(object):
     # ------------------------------------------------- streamed 1-D strings (BASELINE config 4)
     def stream_chunk(self, n):
         """Links per chunk of the streamed string: whole waves of the solver that takes matrices of this size
-        (one 512-thread CTA per SM above n = 256, two 256-thread CTAs below), capped at ~1 GiB of eigenvectors."""
+        (one 512-thread CTA per SM above n = 256, two 256-thread CTAs below), capped at ~1 GiB of eigenvectors
+        (twice as long chunks were measured: same rate, twice the memory)."""
         if n > 256:
             c = 148 * 2
         elif n > 32:

@@ -717,7 +717,20 @@ static BlkStage blk_stage_layout(const BlkShape& shp, long long npts) {
   s.wy.off_T = off;    off += r256((size_t)s.wy.nblk * kWyNB * kWyNB * 16);
   s.wy.off_flag = off; off += 256;
   s.wy.slot_bytes = off;
-  s.slots = npts < (long long)kNumSM * kBlkSlotsPerSM ? (npts < 1 ? 1 : npts) : (long long)kNumSM * kBlkSlotsPerSM;
+  // matrices per SM and chunk: as many as ~12 GB of slots allow, between 4 and 16 (TBK_BLK_SLOTS overrides).  A chunk
+  // ends with the tail of its slowest matrices (up to 3x the mean) and three launches; measured on the norb-499 slab
+  // over a [129, 129] mesh: 5.75 / 5.10 / 4.78 s at 4 / 8 / 16 matrices per SM (profiles/README.md r15).
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("TBK_BLK_SLOTS"); forced = e ? atoi(e) : 0; if (forced < 0 || forced > 32) forced = 0; }
+  int per_sm = forced;
+  if (per_sm == 0) {
+    const double budget = 12.0e9;
+    per_sm = (int)(budget / ((double)kNumSM * (double)off));
+    if (per_sm < kBlkSlotsPerSM) per_sm = kBlkSlotsPerSM;
+    if (per_sm > 16) per_sm = 16;
+  }
+  const long long cap = (long long)kNumSM * per_sm;
+  s.slots = npts < cap ? (npts < 1 ? 1 : npts) : cap;
   s.ctas = blk_blocks(shp, s.slots);
   s.lu_bytes = shp.ws_lu;
   s.total = (size_t)s.slots * s.wy.slot_bytes + (size_t)s.ctas * s.lu_bytes;
