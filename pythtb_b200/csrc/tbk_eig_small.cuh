@@ -256,17 +256,66 @@ TBK_HD void small_hetd2(cplx a[N][N], double d[N], double e[N], cplx tau[N]) {
 }
 
 // (2) implicit-shift QL on (d, e): on exit d ascending, column c of z the eigenvector of d[c]; false = not converged
-// WANT_Z = false: eigenvalues only (z is not touched; pass any array)
-template <int N, bool WANT_Z = true>
-TBK_HD bool small_tridiag_ql(double d[N], double e[N], double z[N][N]) {
-  const double eps = 1.1102230246251565e-16;
-  if constexpr (WANT_Z) {
+// Where the rotations go: Z provides init(), rot(i, sn, cs) (columns i, i + 1 of the accumulated rotation matrix) and
+// swap(x, y) (the final ordering).  ZRegs: an N x N register array (the column indices are compile-time constants after
+// unrolling); ZNone: eigenvalues only; ZMem: a strided array in (shared) memory + a column permutation instead of swaps.
+template <int N>
+struct ZRegs {
+  double (*z)[N];
+  TBK_HD void init() {
     TBK_UNROLL
     for (int r = 0; r < N; ++r) {
       TBK_UNROLL
       for (int c = 0; c < N; ++c) z[r][c] = r == c ? 1.0 : 0.0;
     }
   }
+  TBK_HD void rot(int i, double sn, double cs) {
+    TBK_UNROLL
+    for (int k = 0; k < N; ++k) {
+      const double zf = z[k][i + 1];
+      z[k][i + 1] = sn * z[k][i] + cs * zf;
+      z[k][i] = cs * z[k][i] - sn * zf;
+    }
+  }
+  TBK_HD void swap(int x, int y) {
+    TBK_UNROLL
+    for (int k = 0; k < N; ++k) { const double tz = z[k][x]; z[k][x] = z[k][y]; z[k][y] = tz; }
+  }
+};
+struct ZNone {
+  TBK_HD void init() {}
+  TBK_HD void rot(int, double, double) {}
+  TBK_HD void swap(int, int) {}
+};
+template <int N>
+struct ZMem {
+  double* z;        // element (k, i) at z[(k * N + i) * stride]
+  int stride;
+  int perm[N];      // on exit: column perm[b] belongs to the b-th smallest eigenvalue
+  TBK_HD void init() {
+    TBK_UNROLL
+    for (int r = 0; r < N; ++r) {
+      perm[r] = r;
+      TBK_UNROLL
+      for (int c = 0; c < N; ++c) z[(r * N + c) * stride] = r == c ? 1.0 : 0.0;
+    }
+  }
+  TBK_HD void rot(int i, double sn, double cs) {
+    TBK_UNROLL
+    for (int k = 0; k < N; ++k) {
+      double* p = z + (k * N + i) * stride;
+      const double z0 = p[0], z1 = p[stride];
+      p[stride] = sn * z0 + cs * z1;
+      p[0] = cs * z0 - sn * z1;
+    }
+  }
+  TBK_HD void swap(int x, int y) { const int t = perm[x]; perm[x] = perm[y]; perm[y] = t; }
+};
+
+template <int N, class Z>
+TBK_HD bool small_tridiag_ql_t(double d[N], double e[N], Z& z) {
+  const double eps = 1.1102230246251565e-16;
+  z.init();
   bool ok = true;
   TBK_UNROLL
   for (int l = 0; l < N - 1; ++l) {
@@ -308,14 +357,7 @@ TBK_HD bool small_tridiag_ql(double d[N], double e[N], double z[N][N]) {
             p = sn * r;
             d[i + 1] = g + p;
             g = cs * r - b;
-            if constexpr (WANT_Z) {
-              TBK_UNROLL
-              for (int k = 0; k < N; ++k) {
-                const double zf = z[k][i + 1];
-                z[k][i + 1] = sn * z[k][i] + cs * zf;
-                z[k][i] = cs * z[k][i] - sn * zf;
-              }
-            }
+            z.rot(i, sn, cs);
           }
         }
       }
@@ -332,14 +374,23 @@ TBK_HD bool small_tridiag_ql(double d[N], double e[N], double z[N][N]) {
     for (int y = x + 1; y < N; ++y) {
       if (d[y] < d[x]) {
         const double td = d[x]; d[x] = d[y]; d[y] = td;
-        if constexpr (WANT_Z) {
-          TBK_UNROLL
-          for (int k = 0; k < N; ++k) { const double tz = z[k][x]; z[k][x] = z[k][y]; z[k][y] = tz; }
-        }
+        z.swap(x, y);
       }
     }
   }
   return ok;
+}
+
+// WANT_Z = false: eigenvalues only (z is not touched; pass any array)
+template <int N, bool WANT_Z = true>
+TBK_HD bool small_tridiag_ql(double d[N], double e[N], double z[N][N]) {
+  if constexpr (WANT_Z) {
+    ZRegs<N> zr{z};
+    return small_tridiag_ql_t<N>(d, e, zr);
+  } else {
+    ZNone zn;
+    return small_tridiag_ql_t<N>(d, e, zn);
+  }
 }
 
 // (3) eigenvectors of H: x = H_0 H_1 ... H_{N-2} z_c, row b of w = eigenvector b
@@ -542,6 +593,41 @@ TBK_HD bool eigvals_small(cplx a[N][N], double ev[N]) {
   const bool ok = small_tridiag_ql<N, false>(d, e, nz);
   TBK_UNROLL
   for (int b = 0; b < N; ++b) ev[b] = d[b];
+  return ok;
+}
+
+// Eigenvalues AND eigenvectors, 3 <= N <= 8, one matrix per thread: the reflectors stay in registers, the N x N real
+// rotation matrix of the QL iteration lives in memory (zs: N^2 doubles, `stride` apart — a thread's own column of a
+// shared-memory tile), the eigenvectors are back-transformed one at a time and handed to store(b, o, x_o) (b-th smallest
+// eigenvalue, component o, NOT conjugated: H x = ev[b] x).  Returns false if the QL iteration did not converge.
+template <int N, class Store>
+TBK_HD bool eigh_small_mem(cplx a[N][N], double ev[N], double* zs, int stride, Store store) {
+  double d[N], e[N];
+  cplx tau[N];
+  small_hetd2<N>(a, d, e, tau);
+  ZMem<N> zm;
+  zm.z = zs; zm.stride = stride;
+  const bool ok = small_tridiag_ql_t<N>(d, e, zm);
+  TBK_UNROLL
+  for (int b = 0; b < N; ++b) {
+    ev[b] = d[b];
+    const int col = zm.perm[b];
+    cplx x[N];
+    TBK_UNROLL
+    for (int k = 0; k < N; ++k) x[k] = mk(zs[(k * N + col) * stride], 0.0);
+    TBK_UNROLL
+    for (int j = N - 2; j >= 0; --j) {
+      cplx dot = x[j + 1];                                   // v^H x with v[j+1] = 1
+      TBK_UNROLL
+      for (int r = j + 2; r < N; ++r) fma_acc_conj(dot, a[r][j], x[r]);
+      const cplx f = tau[j] * dot;
+      x[j + 1] = x[j + 1] - f;
+      TBK_UNROLL
+      for (int r = j + 2; r < N; ++r) x[r] = x[r] - f * a[r][j];
+    }
+    TBK_UNROLL
+    for (int o = 0; o < N; ++o) store(b, o, x[o]);
+  }
   return ok;
 }
 

@@ -400,7 +400,11 @@ solve_reg_kernel(PlanView pv, KSrc ks, const cplx* __restrict__ hsrc, long long 
 // 768 bytes per k-point and the 27 DMMA per k-point take ~110 SM cycles.
 // ===========================================================================
 constexpr int kRegLDB = 132;
-template <int N>
+// VEC: eigenvectors too (solve_all with eig_vectors, solve_on_grid of 5..8-band models): the real rotation matrix of the
+// QL iteration lives in the thread's own column of the tile (free once the matrix has been picked up), the eigenvectors
+// are back-transformed one at a time from the reflectors in registers and written with the Convention-I gauge factors,
+// periodic images and closing-row factor (blk_store_vec); grid solves also reduce the minimal direct gaps.
+template <int N, bool VEC>
 __global__ void __launch_bounds__(kRegThreads)
 solve_reg_gemm_kernel(PlanView pv, KSrc ks, long long npts, OutSpec out, const double* __restrict__ tab, int KS) {
   constexpr int NP = N * (N + 1) / 2;
@@ -417,6 +421,7 @@ solve_reg_gemm_kernel(PlanView pv, KSrc ks, long long npts, OutSpec out, const d
     {
       int mi[TBK_MAX_DIM] = {0, 0, 0, 0};
       double k[TBK_MAX_DIM] = {0.0, 0.0, 0.0, 0.0};
+      if (out.mode == 1) decode_index(idx, out, mi);
       load_k(ks, idx, mi, k);
       for (int p = 0; p < nph; ++p) {
         double x = 0.0;
@@ -467,10 +472,53 @@ solve_reg_gemm_kernel(PlanView pv, KSrc ks, long long npts, OutSpec out, const d
       }
     __syncwarp();                                      // the columns are free for the next pass
     double ev[N];
-    const bool ok = eigvals_small<N>(a, ev);
-    if (active && out.eval) {
+    if constexpr (!VEC) {
+      const bool ok = eigvals_small<N>(a, ev);
+      if (active && out.eval) {
 #pragma unroll
-      for (int b = 0; b < N; ++b) out.eval[b * out.ev_sb + idx * out.ev_sk] = ok ? ev[b] : NAN;
+        for (int b = 0; b < N; ++b) out.eval[b * out.ev_sb + idx * out.ev_sk] = ok ? ev[b] : NAN;
+      }
+    } else {
+      int mi[TBK_MAX_DIM] = {0, 0, 0, 0};
+      double k[TBK_MAX_DIM] = {0.0, 0.0, 0.0, 0.0};
+      if (out.mode == 1) decode_index(idx, out, mi);
+      load_k(ks, idx, mi, k);
+      // gauge factors conj(d_o(k)) in rows N^2 .. N^2 + 2N - 1 of the thread's column (registers are scarce here)
+      double* gfs = Bs + (size_t)(N * N) * kRegLDB + tid;
+#pragma unroll
+      for (int o = 0; o < N; ++o) {
+        const cplx f = (pv.convention == 1 && pv.dim_k > 0) ? conj(plan_gauge(pv, k, o)) : mk(1.0, 0.0);
+        gfs[(2 * o) * kRegLDB] = f.re;
+        gfs[(2 * o + 1) * kRegLDB] = f.im;
+      }
+      BlkStorePoint pt;
+      pt.idx = idx; pt.base = 0; pt.zero_mask = 0; pt.closing = false;
+      if (out.mode == 1) {
+        pt.closing = is_closing(ks, mi);
+        for (int d = 0; d < out.nd; ++d) {
+          pt.base += mi[d] * out.gstride[d];
+          if (mi[d] == 0 && out.wrap[d]) pt.zero_mask |= 1 << d;
+        }
+      }
+      // (the rotation matrix goes into this thread's own column: no other lane reads or writes it until the next pass)
+      const bool ok = eigh_small_mem<N>(a, ev, Bs + tid, kRegLDB, [&](int b, int o, cplx x) {
+        if (active) blk_store_vec(out, N, pt, b, o, x * mk(gfs[(2 * o) * kRegLDB], gfs[(2 * o + 1) * kRegLDB]));
+      });
+      if (out.mode == 0) {
+        if (active && out.eval) {
+#pragma unroll
+          for (int b = 0; b < N; ++b) out.eval[b * out.ev_sb + idx * out.ev_sk] = ok ? ev[b] : NAN;
+        }
+      } else if (out.gaps_bits != nullptr) {
+#pragma unroll
+        for (int b = 0; b < N - 1; ++b) {
+          double gp = active ? (ok ? ev[b + 1] - ev[b] : 0.0) : INFINITY;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) gp = fmin(gp, __shfl_xor_sync(0xffffffffu, gp, o));
+          if (lane == 0) atomic_min_nonneg(out.gaps_bits + b, gp);
+        }
+      }
+      __syncwarp();                                    // the rotation matrices are done with before the next pass
     }
   }
 }
@@ -994,10 +1042,12 @@ static int launch_solve(const PlanView& pv, const KSrc& ks, const cplx* hsrc, in
     if (reg_on < 0) { const char* e = getenv("TBK_REG_EIGVALS"); reg_on = (e && atoi(e) == 0) ? 0 : 1; }
     static int gemm_on = -1;                           // TBK_REG_GEMM=0: scalar assembly (A/B knob)
     if (gemm_on < 0) { const char* e = getenv("TBK_REG_GEMM"); gemm_on = (e && atoi(e) == 0) ? 0 : 1; }
-    if (reg_on && gemm_on && gemm_tab != nullptr && hsrc == nullptr && n >= 5 && n <= 8 && !want_vec && out.mode == 0 &&
-        out.eval != nullptr && npts > 0) {
+    const bool reg_vals = !want_vec && out.mode == 0 && out.eval != nullptr;
+    const bool reg_vecs = want_vec && out.evec != nullptr && (out.mode == 1 || out.mode == 0);
+    if (reg_on && gemm_on && gemm_tab != nullptr && hsrc == nullptr && n >= 5 && n <= 8 && (reg_vals || reg_vecs) && npts > 0) {
       const int MT = (n * (n + 1) + 7) / 8;
-      const int rows = 4 * gemm_ks > 8 * MT ? 4 * gemm_ks : 8 * MT;
+      int rows = 4 * gemm_ks > 8 * MT ? 4 * gemm_ks : 8 * MT;
+      if (want_vec && rows < n * n + 2 * n) rows = n * n + 2 * n;      // rotation matrix + gauge factors of the eigenvector variant
       const size_t dyn = (size_t)rows * kRegLDB * 8;
       if (dyn + 1024 <= (size_t)kMaxSmem) {
         int per_sm = (int)((size_t)kMaxSmem / (dyn + 1024));
@@ -1006,8 +1056,13 @@ static int launch_solve(const PlanView& pv, const KSrc& ks, const cplx* hsrc, in
         if (blocks > (long long)kNumSM * per_sm) blocks = (long long)kNumSM * per_sm;
 #define TBK_REGG_LAUNCH(NN)                                                                                             \
         do {                                                                                                            \
-          TBK_CUDA(cudaFuncSetAttribute(solve_reg_gemm_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
-          solve_reg_gemm_kernel<NN><<<(unsigned)blocks, kRegThreads, dyn, st>>>(pv, ks, npts, out, gemm_tab, gemm_ks);  \
+          if (want_vec) {                                                                                               \
+            TBK_CUDA(cudaFuncSetAttribute(solve_reg_gemm_kernel<NN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+            solve_reg_gemm_kernel<NN, true><<<(unsigned)blocks, kRegThreads, dyn, st>>>(pv, ks, npts, out, gemm_tab, gemm_ks);  \
+          } else {                                                                                                      \
+            TBK_CUDA(cudaFuncSetAttribute(solve_reg_gemm_kernel<NN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+            solve_reg_gemm_kernel<NN, false><<<(unsigned)blocks, kRegThreads, dyn, st>>>(pv, ks, npts, out, gemm_tab, gemm_ks);  \
+          }                                                                                                             \
         } while (0)
         switch (n) {
           case 5: TBK_REGG_LAUNCH(5); break;
@@ -1464,7 +1519,7 @@ int tbk_solve_grid_x(const tbk_model* m, const double* start_k, const int32_t* m
     fill_u64_kernel<<<(n - 1 + 127) / 128, 128, 0, st>>>(out.gaps_bits, n - 1, 0x7FF0000000000000ULL);
     TBK_LAUNCH_CHECK("fill_u64_kernel");
   }
-  return launch_solve(m->pv, ks, nullptr, n, npts, out, 1, ws_dev, ws_bytes, st);
+  return launch_solve(m->pv, ks, nullptr, n, npts, out, 1, ws_dev, ws_bytes, st, m->gemm_tab, m->gemm_ks);
 }
 
 }  // extern "C"

@@ -85,6 +85,15 @@ static int emu_eigvals_n(const cplx* h, double* ev) {
   return eigvals_small<N>(a, ev) ? 1 : 0;
 }
 
+// eigenvectors-through-memory register solver (n = 5..8 with eigenvectors); returns 1 if converged
+template <int N>
+static int emu_eigh_mem_n(const cplx* h, double* ev, cplx* w) {
+  cplx a[N][N];
+  for (int r = 0; r < N; ++r) for (int c = 0; c < N; ++c) a[r][c] = h[r * N + c];
+  std::vector<double> zs((size_t)N * N * 3);
+  return eigh_small_mem<N>(a, ev, zs.data(), 3, [&](int b, int o, cplx x) { w[b * N + o] = x; }) ? 1 : 0;
+}
+
 extern "C" {
 
 // which tridiagonalisation the emu_heev_blocked* entry points run: 1 = lower triangle only, 0 = full matrix
@@ -179,6 +188,18 @@ int emu_small_ql(int n, const double* H, double* ev, double* w) {
 }
 
 // eigenvalues-only register solver (n = 5..8 band-structure sweeps); returns 1 if the QL iteration converged
+int emu_eigh_small_mem(int n, const double* H, double* ev, double* w) {
+  const cplx* h = (const cplx*)H;
+  cplx* ww = (cplx*)w;
+  switch (n) {
+    case 3: return emu_eigh_mem_n<3>(h, ev, ww);
+    case 5: return emu_eigh_mem_n<5>(h, ev, ww);
+    case 6: return emu_eigh_mem_n<6>(h, ev, ww);
+    case 7: return emu_eigh_mem_n<7>(h, ev, ww);
+    case 8: return emu_eigh_mem_n<8>(h, ev, ww);
+  }
+  return -1;
+}
 int emu_eigvals_small(int n, const double* H, double* ev) {
   const cplx* h = (const cplx*)H;
   switch (n) {

@@ -125,6 +125,23 @@ def test_small_eigenvalues_only_solver(n):
         assert np.max(np.abs(ev - np.linalg.eigvalsh(h))) < 1e-12 * scale * n
 
 
+@pytest.mark.parametrize("n", [3, 5, 6, 7, 8])
+def test_small_solver_with_vectors_through_memory(n):
+    """eigh_small_mem<N>: reflectors in registers, the QL rotation matrix in a strided memory column, eigenvectors
+    back-transformed one at a time (the n = 5..8 path with eigenvectors)."""
+    lib = hostemu.lib()
+    rng = np.random.RandomState(90 + n)
+    mats = [_rand_herm(rng, n) for _ in range(200)] + [_rand_herm(rng, n, degenerate=True) for _ in range(60)]
+    mats += [np.diag(rng.randn(n)).astype(complex), np.zeros((n, n), dtype=complex), np.eye(n, dtype=complex) * 3.0,
+             1e-9 * _rand_herm(rng, n) + np.eye(n), 1e6 * _rand_herm(rng, n)]
+    for h in mats:
+        ev = np.zeros(n)
+        w = np.zeros((n, n), dtype=complex)
+        hc = np.ascontiguousarray(h, dtype=complex)
+        assert lib.emu_eigh_small_mem(n, _p(hc.view(np.float64)), _p(ev), _p(w.view(np.float64))) == 1
+        _check_eig(h, ev, w)
+
+
 def test_small_direct_solver_n4():
     """eigh4_direct, the n = 4 solver of the mesh kernels: closed-form roots of the tridiagonal's quartic + Newton on the
     Sturm recurrence + adjugate-column eigenvectors, with the implicit-QL lane behind it for close or multiple roots.
