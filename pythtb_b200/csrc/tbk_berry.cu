@@ -851,14 +851,16 @@ __device__ __forceinline__ void gemm_stage_store(const GemmStage& st, const Gemm
   }
 }
 
+// herm: the product is Hermitian (B is A's conjugate partner, ma == nb_: X^H X, <u| r |u>): only the tiles on and above
+// the diagonal are computed, the others are written as conjugate transposes — half the DMMAs.
 __device__ __noinline__ void cta_gemm_dmma(const GemmSide& A, int ma, const GemmSide& B, int nb_, int kdim, const double* __restrict__ wgt,
-                                           cplx* __restrict__ C, int ldc, OvSmem& sm) {
+                                           cplx* __restrict__ C, int ldc, OvSmem& sm, bool herm = false) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int wr = warp >> 1, wc = warp & 1;
   const double sa = A.conj ? -1.0 : 1.0, sb = B.conj ? -1.0 : 1.0;
   for (int m0 = 0; m0 < ma; m0 += kOvTile) {
-    for (int q0 = 0; q0 < nb_; q0 += kOvTile) {
+    for (int q0 = herm ? m0 : 0; q0 < nb_; q0 += kOvTile) {
       double cre[2][4][2], cim[2][4][2];
 #pragma unroll
       for (int rt = 0; rt < 2; ++rt)
@@ -919,6 +921,10 @@ __device__ __noinline__ void cta_gemm_dmma(const GemmSide& A, int ma, const Gemm
           if (m < ma) {
             if (q < nb_) C[(size_t)m * ldc + q] = mk(cre[rt][ct][0], cim[rt][ct][0]);
             if (q + 1 < nb_) C[(size_t)m * ldc + q + 1] = mk(cre[rt][ct][1], cim[rt][ct][1]);
+            if (herm && q0 > m0) {                      // the mirror tile
+              if (q < nb_) C[(size_t)q * ldc + m] = mk(cre[rt][ct][0], -cim[rt][ct][0]);
+              if (q + 1 < nb_) C[(size_t)(q + 1) * ldc + m] = mk(cre[rt][ct][1], -cim[rt][ct][1]);
+            }
           }
         }
     }
@@ -1096,7 +1102,7 @@ link_matrix_kernel(WfView v, LinkMap map, long long nlinks, int mode, cplx* __re
         bool converged = false;
         for (int it = 0; it < 100; ++it) {
           const GemmSide A1{X, 1, ld, nullptr, 1}, B1{X, 1, ld, nullptr, 0};
-          cta_gemm_dmma(A1, nocc, B1, nocc, nocc, nullptr, G, ld, ov);          // G = X^H X
+          cta_gemm_dmma(A1, nocc, B1, nocc, nocc, nullptr, G, ld, ov, true);    // G = X^H X (Hermitian: half the tiles)
           double dev = 0.0;
           for (int idx = threadIdx.x; idx < nocc * nocc; idx += blockDim.x) {
             const int r = idx / nocc, c = idx - r * nocc;
@@ -1109,6 +1115,9 @@ link_matrix_kernel(WfView v, LinkMap map, long long nlinks, int mode, cplx* __re
           if (!(dev == dev) || dev > 1.0e300) break;                              // NaN / Inf in the input
           converged = true;                                                       // finite: X is the best iterate so far
           if (!(dev > 1.0e-28 * nocc)) break;                                     // |X^H X - I|_F <= 1e-14 sqrt(nocc)
+          // quadratic convergence: with delta = |X^H X - I|_F the next iterate has ~(3/4) delta^2, so once
+          // delta^2 = dev <= 1e-14 sqrt(nocc) the update below is the last one and needs no check product
+          const bool last = !(dev > 1.0e-14 * sqrt((double)nocc));
           const GemmSide A2{X, ld, 1, nullptr, 0}, B2{G, 1, ld, nullptr, 0};
           cta_gemm_dmma(A2, nocc, B2, nocc, nocc, nullptr, Xn, ld, ov);          // Xn = X P
           for (int idx = threadIdx.x; idx < nocc * nocc; idx += blockDim.x) {
@@ -1116,6 +1125,7 @@ link_matrix_kernel(WfView v, LinkMap map, long long nlinks, int mode, cplx* __re
             X[at] = Xn[at];
           }
           __syncthreads();
+          if (last) break;
         }
         if (!converged) {
           for (int idx = threadIdx.x; idx < nocc * nocc; idx += blockDim.x) X[(size_t)(idx / nocc) * ld + idx % nocc] = mk(NAN, NAN);
@@ -1404,7 +1414,7 @@ position_matrix_dmma_kernel(const cplx* __restrict__ evec, long long batch, int 
   for (long long k = blockIdx.x; k < batch; k += gridDim.x) {
     const cplx* e = evec + k * (long long)nocc * n;
     const GemmSide A{e, n, 1, nullptr, 1}, B{e, n, 1, nullptr, 0};
-    cta_gemm_dmma(A, nocc, B, nocc, n, pos, xmat + k * (long long)nocc * nocc, nocc, sm);
+    cta_gemm_dmma(A, nocc, B, nocc, n, pos, xmat + k * (long long)nocc * nocc, nocc, sm, true);   // <u| r |u> is Hermitian
   }
 }
 

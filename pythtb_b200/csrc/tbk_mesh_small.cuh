@@ -12,7 +12,8 @@
 //     nph + nsta;
 //   * H(k) from a dense coefficient table held in the kernel-parameter constant
 //     bank (DenseSmall): 4 FMA per (element, phase), no indexed accumulators;
-//   * closed-form (n = 2) / Jacobi (n = 3, 4) eigensolver in registers;
+//   * closed-form (n = 2) / Householder + QL (n = 3) / Householder + direct quartic solver (n = 4) in registers
+//     (tbk_eig_small.cuh);
 //   * Convention-I gauge, periodic images and the running minimum of the direct
 //     gaps fused in; the gap reduction finishes in the last CTA (ticket), so a
 //     grid solve is ONE launch.

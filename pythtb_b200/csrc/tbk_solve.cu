@@ -4,10 +4,14 @@
 //
 // Kernel families (chosen by nsta):
 //   solve_small_kernel<N>   N = 2,3,4: one k-point per thread, H and the
-//                           eigenvectors never leave registers; closed form for
-//                           N = 2, cyclic Jacobi for N = 3,4.
+//                           eigenvectors never leave registers (tbk_eig_small.cuh).
+//   solve_reg_gemm_kernel   5 <= nsta <= 8: one k-point per thread, H(k) assembled on the
+//   solve_reg_kernel        FP64 tensor pipe from a dense coefficient table (or by a scalar
+//                           element-major loop), eigensolver in registers.
 //   solve_tile_kernel<G>    5 <= nsta <= 32: one k-point per G-lane tile of a
 //                           warp (G = 8,16,32), matrix resident in shared memory.
+//   solve_blocked_kernel    33 <= nsta <= 512: staged blocked solver (tbk_eig_blocked.cuh,
+//                           tbk_eig_wy.cuh).
 //   solve_block_kernel      nsta > 32: one k-point per CTA, matrix in shared
 //                           memory up to nsta = 112, else in an L2/HBM workspace.
 // All of them generate k on the fly (mesh descriptor) or read a k-list, build
