@@ -598,8 +598,8 @@ TBK_HD bool eigvals_small(cplx a[N][N], double ev[N]) {
 
 // Eigenvalues AND eigenvectors, 3 <= N <= 8, one matrix per thread: the reflectors stay in registers, the N x N real
 // rotation matrix of the QL iteration lives in memory (zs: N^2 doubles, `stride` apart — a thread's own column of a
-// shared-memory tile), the eigenvectors are back-transformed one at a time and handed to store(b, o, x_o) (b-th smallest
-// eigenvalue, component o, NOT conjugated: H x = ev[b] x).  Returns false if the QL iteration did not converge.
+// shared-memory tile), the eigenvectors are back-transformed one at a time and handed to store(b, x) (b-th smallest
+// eigenvalue, x[N] its components, NOT conjugated: H x = ev[b] x).  Returns false if the QL iteration did not converge.
 template <int N, class Store>
 TBK_HD bool eigh_small_mem(cplx a[N][N], double ev[N], double* zs, int stride, Store store) {
   double d[N], e[N];
@@ -608,10 +608,16 @@ TBK_HD bool eigh_small_mem(cplx a[N][N], double ev[N], double* zs, int stride, S
   ZMem<N> zm;
   zm.z = zs; zm.stride = stride;
   const bool ok = small_tridiag_ql_t<N>(d, e, zm);
+  // the band loop is deliberately NOT unrolled (N copies of the back-transformation and of the caller's store code made
+  // the kernel instruction-fetch bound: ncu "no instruction" stalls); the column permutation travels as packed nibbles
+  unsigned packed = 0u;
   TBK_UNROLL
+  for (int b = 0; b < N; ++b) { ev[b] = d[b]; packed |= (unsigned)zm.perm[b] << (4 * b); }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
   for (int b = 0; b < N; ++b) {
-    ev[b] = d[b];
-    const int col = zm.perm[b];
+    const int col = (int)((packed >> (4 * b)) & 15u);
     cplx x[N];
     TBK_UNROLL
     for (int k = 0; k < N; ++k) x[k] = mk(zs[(k * N + col) * stride], 0.0);
@@ -625,8 +631,7 @@ TBK_HD bool eigh_small_mem(cplx a[N][N], double ev[N], double* zs, int stride, S
       TBK_UNROLL
       for (int r = j + 2; r < N; ++r) x[r] = x[r] - f * a[r][j];
     }
-    TBK_UNROLL
-    for (int o = 0; o < N; ++o) store(b, o, x[o]);
+    store(b, x);
   }
   return ok;
 }

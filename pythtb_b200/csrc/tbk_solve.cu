@@ -504,9 +504,37 @@ solve_reg_gemm_kernel(PlanView pv, KSrc ks, long long npts, OutSpec out, const d
           if (mi[d] == 0 && out.wrap[d]) pt.zero_mask |= 1 << d;
         }
       }
+      // Grid output (k-major _wfs: a band's N components are one 16 N-byte run, the bands of a mesh point N of them, the
+      // points of a warp 16 N^2 bytes apart): written thread by thread, a store instruction touched 32 different lines.
+      // Unless a lane sits on a periodic image or the closing row (those go the general way), a band is therefore staged
+      // in rows N^2 + 2N .. N^2 + 4N - 1 of the warp's columns and written out with N consecutive lanes per mesh point.
+      const bool coalesce = out.mode == 1 && !__any_sync(0xffffffffu, pt.zero_mask != 0 || pt.closing);
+      double* stg = Bs + (size_t)(N * N + 2 * N) * kRegLDB;
       // (the rotation matrix goes into this thread's own column: no other lane reads or writes it until the next pass)
-      const bool ok = eigh_small_mem<N>(a, ev, Bs + tid, kRegLDB, [&](int b, int o, cplx x) {
-        if (active) blk_store_vec(out, N, pt, b, o, x * mk(gfs[(2 * o) * kRegLDB], gfs[(2 * o + 1) * kRegLDB]));
+      const bool ok = eigh_small_mem<N>(a, ev, Bs + tid, kRegLDB, [&](int b, const cplx (&x)[N]) {
+        if (!coalesce) {
+          if (active) {
+#pragma unroll
+            for (int o = 0; o < N; ++o) blk_store_vec(out, N, pt, b, o, x[o] * mk(gfs[(2 * o) * kRegLDB], gfs[(2 * o + 1) * kRegLDB]));
+          }
+          return;
+        }
+#pragma unroll
+        for (int o = 0; o < N; ++o) {
+          const cplx v = x[o] * mk(gfs[(2 * o) * kRegLDB], gfs[(2 * o + 1) * kRegLDB]);
+          stg[(2 * o) * kRegLDB + tid] = v.re;
+          stg[(2 * o + 1) * kRegLDB + tid] = v.im;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const int e = j * 32 + lane, kp = e / N, o = e - kp * N;
+          const long long base_kp = __shfl_sync(0xffffffffu, pt.base, kp);
+          const int act_kp = __shfl_sync(0xffffffffu, (int)active, kp);
+          const double re = stg[(2 * o) * kRegLDB + 32 * warp + kp], im = stg[(2 * o + 1) * kRegLDB + 32 * warp + kp];
+          if (act_kp) out.evec[base_kp + (long long)b * out.sstride + o] = mk(re, im);
+        }
+        __syncwarp();
       });
       if (out.mode == 0) {
         if (active && out.eval) {
@@ -1051,7 +1079,7 @@ static int launch_solve(const PlanView& pv, const KSrc& ks, const cplx* hsrc, in
     if (reg_on && gemm_on && gemm_tab != nullptr && hsrc == nullptr && n >= 5 && n <= 8 && (reg_vals || reg_vecs) && npts > 0) {
       const int MT = (n * (n + 1) + 7) / 8;
       int rows = 4 * gemm_ks > 8 * MT ? 4 * gemm_ks : 8 * MT;
-      if (want_vec && rows < n * n + 2 * n) rows = n * n + 2 * n;      // rotation matrix + gauge factors of the eigenvector variant
+      if (want_vec && rows < n * n + 4 * n) rows = n * n + 4 * n;      // rotation matrix, gauge factors, one staged band (eigenvector variant)
       const size_t dyn = (size_t)rows * kRegLDB * 8;
       if (dyn + 1024 <= (size_t)kMaxSmem) {
         int per_sm = (int)((size_t)kMaxSmem / (dyn + 1024));

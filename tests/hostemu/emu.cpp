@@ -91,7 +91,7 @@ static int emu_eigh_mem_n(const cplx* h, double* ev, cplx* w) {
   cplx a[N][N];
   for (int r = 0; r < N; ++r) for (int c = 0; c < N; ++c) a[r][c] = h[r * N + c];
   std::vector<double> zs((size_t)N * N * 3);
-  return eigh_small_mem<N>(a, ev, zs.data(), 3, [&](int b, int o, cplx x) { w[b * N + o] = x; }) ? 1 : 0;
+  return eigh_small_mem<N>(a, ev, zs.data(), 3, [&](int b, const cplx (&x)[N]) { for (int o = 0; o < N; ++o) w[b * N + o] = x[o]; }) ? 1 : 0;
 }
 
 extern "C" {
