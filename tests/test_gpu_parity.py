@@ -490,6 +490,42 @@ def test_replayed_calls_follow_their_arguments():
     assert np.max(np.abs(b - gaps_ref)) < 1e-10 and abs(a[0] - b[0]) > 1e-3
 
 
+def test_five_to_eight_band_register_paths_edge_cases():
+    """The one-k-point-per-thread kernels of 5..8-band models on their edge cases: a finite (dim_k = 0) cluster (no
+    phases, no dense coefficient table -> scalar assembly), a single k-point (127 idle lanes), a model with on-site terms
+    only, eigenvalues only and with eigenvectors, against the oracle."""
+    from oracle import pythtb_oracle as orc
+    mod = _mod()
+    rng = np.random.RandomState(77)
+    mol = mod.tb_model(0, 2, [[1.0, 0.0], [0.0, 1.0]], rng.rand(6, 2).tolist())
+    mol.set_onsite(rng.randn(6).tolist())
+    for i in range(6):
+        for j in range(i + 1, 6):
+            if rng.rand() < 0.7:
+                mol.set_hop(complex(rng.randn(), rng.randn()), i, j)
+    ev = mol.solve_all()
+    assert np.max(np.abs(ev - orc.solve_all(mol))) < 1e-10
+    ev2, vec = mol.solve_all(eig_vectors=True)
+    assert np.max(np.abs(ev2 - ev)) < 1e-12
+    h = orc.gen_ham(mol).reshape(6, 6)
+    assert np.max(np.abs(h @ vec.T - vec.T * ev2[None, :])) < 1e-11
+    for norb in (5, 6, 7, 8):
+        m = M.random_model(mod, norb=norb, dim=2, nhop=3 * norb, nspin=1, seed=100 + norb)
+        for k in ([[0.123, -0.4]], np.random.RandomState(norb).rand(129, 2)):
+            k = np.asarray(k)
+            ref = orc.solve_all(m, k)
+            assert np.max(np.abs(m.solve_all(k) - ref)) < 1e-10 * max(1.0, np.max(np.abs(ref)))
+            evv, vecv = m.solve_all(k, eig_vectors=True)
+            assert np.max(np.abs(evv - ref)) < 1e-10 * max(1.0, np.max(np.abs(ref)))
+            assert _residual(m, k, evv, vecv) < 1e-11 * max(1.0, np.max(np.abs(ref)))
+    flat = mod.tb_model(1, 1, [[1.0]], [[0.1 * i] for i in range(5)])
+    flat.set_onsite([0.3, -0.2, 0.3, 1.5, -0.2])               # no hoppings at all: degenerate pairs, no phases
+    kk = [[0.0], [0.3]]
+    assert np.max(np.abs(flat.solve_all(kk) - orc.solve_all(flat, kk))) < 1e-12
+    evf, vecf = flat.solve_all(kk, eig_vectors=True)
+    assert _residual(flat, np.array(kk), evf, vecf) < 1e-12
+
+
 def test_pipelined_host_results_equal_the_single_shot():
     """solve_all with host results on a long k-list is cut into chunks whose copies overlap the next chunk's kernels
     (engine.solve_all_host); with a small chunk size the chunked sweep must equal the single-shot one bit for bit —
