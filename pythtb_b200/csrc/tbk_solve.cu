@@ -745,7 +745,9 @@ static BlkShape blk_shape(int n, int nph) {
       const char* e = getenv("TBK_BLK_SHAPE");
       if (e) { int a = 0, b = 0; if (sscanf(e, "%d,%d", &a, &b) == 2 && (a == 256 || a == 512) && (b == 4 || b == 8 || b == 16)) { kt = a; knb = b; } }
     }
-    if (kt > 0 && n > 256 && !s.sym) { s.threads = kt; s.nb = knb; s.nred = 0; }
+    static int ksmall = -1;                             // TBK_BLK_SHAPE_ALL=1: the knob also applies to n <= 256
+    if (ksmall < 0) { const char* e = getenv("TBK_BLK_SHAPE_ALL"); ksmall = (e && atoi(e) == 1) ? 1 : 0; }
+    if (kt > 0 && (n > 256 || ksmall) && !s.sym && total(knb, 0) + 1024 <= (size_t)kMaxSmem) { s.threads = kt; s.nb = knb; s.nred = 0; }
   }
   size_t off = (blk_shared_bytes(n, s.nb, s.nred, s.threads) + 15) & ~(size_t)15;
   s.off_ph = off;   off += (size_t)(nph > 0 ? nph : 1) * 16;
@@ -1173,9 +1175,9 @@ static int launch_solve(const PlanView& pv, const KSrc& ks, const cplx* hsrc, in
         } while (0)
 #define TBK_BLK_DISPATCH(BLOCKS, COUNT, GWS, IDX0)                                                                \
         do {                                                                                                      \
-          if (n <= 128) TBK_BLK_LAUNCH(4, BLOCKS, COUNT, GWS, IDX0);                                              \
-          else if (n <= 256) TBK_BLK_LAUNCH(8, BLOCKS, COUNT, GWS, IDX0);                                         \
-          else TBK_BLK_LAUNCH(16, BLOCKS, COUNT, GWS, IDX0);                                                      \
+          if (shp.threads == 512) TBK_BLK_LAUNCH(16, BLOCKS, COUNT, GWS, IDX0);   /* (compiled for 512 threads) */ \
+          else if (n <= 128) TBK_BLK_LAUNCH(4, BLOCKS, COUNT, GWS, IDX0);                                         \
+          else TBK_BLK_LAUNCH(8, BLOCKS, COUNT, GWS, IDX0);                                                       \
         } while (0)
         if (want_vec && blk_staged_enabled()) {
           BlkStage sg = blk_stage_layout(shp, npts);
