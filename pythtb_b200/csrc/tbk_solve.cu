@@ -812,7 +812,11 @@ static BlkStage blk_stage_layout(const BlkShape& shp, long long npts) {
     if (per_sm > 16) per_sm = 16;
   }
   const long long cap = (long long)kNumSM * per_sm;
-  s.slots = npts < cap ? (npts < 1 ? 1 : npts) : cap;
+  // equal chunks: 2048 matrices with room for 1776 are two chunks of 1024, not 1776 + a 272-matrix chunk that leaves
+  // most SMs idle behind its slowest matrix (a shard of the [129, 129] slab mesh on 8 GPUs)
+  const long long want = npts < 1 ? 1 : npts;
+  const long long nchunk = (want + cap - 1) / cap;
+  s.slots = (want + nchunk - 1) / nchunk;
   s.ctas = blk_blocks(shp, s.slots);
   s.lu_bytes = shp.ws_lu;
   s.total = (size_t)s.slots * s.wy.slot_bytes + (size_t)s.ctas * s.lu_bytes;
