@@ -266,6 +266,7 @@ blk_backtransform_kernel(const WyArgs a, const PlanView pv, const KSrc ks, const
       // Y[i][c] += sum_r conj(V[r][i]) X[r][c]: rows 32 kh .. 32 kh + 31 of the chunk, i = 8 rt1 + g
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
+        if (r0 + kh * 32 + ks * 4 >= n) break;              // warp-uniform: the rest of this half chunk lies past row n - 1
         const int rr = kh * 32 + ks * 4 + q;
         const cplx v = cb[(rt1 * 8 + g) * kWyLD1 + rr];
         const int r = r0 + rr;
@@ -310,6 +311,7 @@ blk_backtransform_kernel(const WyArgs a, const PlanView pv, const KSrc ks, const
     } else {
       // X[r][c] -= sum_i V[r][i] Y'[i][c]: warp owns rows 8 warp .. + 7 of the chunk
       const int rr = warp * 8 + g, r = r0 + rr;
+      if (r0 + warp * 8 < n) {                              // warp-uniform: this warp's eight rows are not all past row n - 1
       double xre[2][2], xim[2][2];
 #pragma unroll
       for (int ct = 0; ct < 2; ++ct) {
@@ -336,6 +338,7 @@ blk_backtransform_kernel(const WyArgs a, const PlanView pv, const KSrc ks, const
           Xs[(ct * 8 + p0) * ldx + r] = mk(xre[ct][0], xim[ct][0]);
           Xs[(ct * 8 + p1) * ldx + r] = mk(xre[ct][1], xim[ct][1]);
         }
+      }
       }
     }
     wy_advance(cur, n);
