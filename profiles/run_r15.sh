@@ -1,7 +1,7 @@
 #!/bin/bash
 # r15: last full pass of round 2 — parity suite, smoke, bench line (every workload / config) + reference arm, launch list of the
 # bench command, full-set capture of the register / tensor-pipe sweep kernel.  Every step under a timeout.
-OUT=gpurun_out/${1:-r17}
+OUT=gpurun_out/${1:-r18}
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $OUT/gpu.txt
 timeout 600 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log; tail -4 $OUT/pytest_gpu.log
